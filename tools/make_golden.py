@@ -1,0 +1,345 @@
+"""Generate tests/golden/* by running the UNMODIFIED reference (imported from
+/root/reference) on structure specs built from the reference's own test data.
+
+DEV-CONTAINER ONLY.  Run:  python tools/make_golden.py
+The committed outputs are what the CPU/GPU test-suites compare against; the
+GPU box never sees /root/reference.
+
+Outputs (all JSON, gz where large):
+  spec_*.json.gz            input structures (plain coordinates + ids)
+  frames_<spec>.json.gz     per-nt centre, rotation, placed hydrogens (reference Component)
+  annot_<spec>.json.gz      candidate pairs in reference order, per-rule stage traces,
+                            final interaction_to_list_of_tuples (ordered) per category set
+  geometry.json.gz          Kabsch / discrepancy known answers + reference outputs on seeded inputs
+  matlab_1gid_frames.json.gz  the Matlab golden centres/rotations (second witness)
+"""
+
+import contextlib
+import gzip
+import io
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import ref_fixtures as rf  # noqa: E402
+
+rf.add_reference_to_path()
+GOLD = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+LW18 = ['cWW', 'cSS', 'cHH', 'cHS', 'cHW', 'cSH', 'cSW', 'cWH', 'cWS', 'tSS', 'tHH', 'tHS', 'tHW',
+        'tSH', 'tSW', 'tWH', 'tWS', 'tWW']
+BACKBONE = ["P", "OP1", "OP2", "O5'", "C5'", "C4'", "O4'", "C3'", "O3'", "C2'", "O2'", "C1'"]
+
+
+def dump(name, obj):
+    path = os.path.join(GOLD, name)
+    data = json.dumps(obj, separators=(",", ":")).encode()
+    if name.endswith(".gz"):
+        with gzip.GzipFile(path, "wb", mtime=0) as f:
+            f.write(data)
+    else:
+        with open(path, "wb") as f:
+            f.write(data)
+    print("wrote %s (%d bytes)" % (name, os.path.getsize(path)))
+
+
+def residues(structure):
+    return list(structure.residues(type=["RNA linking", "DNA linking"]))
+
+
+def make_spec_1gid_full(base_spec, strand_spec):
+    """S_1GID_full: template backbone transfer."""
+    sb = residues(rf.ref_structure_from_spec(base_spec))
+    st = residues(rf.ref_structure_from_spec(strand_spec))
+    by_num = {c.number: c for c in st}
+    templates = {'A': by_num['11'], 'U': by_num['12'], 'G': by_num['13'], 'C': by_num['14']}
+    local = {}
+    for seq, t in templates.items():
+        U = np.asarray(t.rotation_matrix)
+        c = np.asarray(t.centers["base"])
+        local[seq] = [(n, (np.asarray(t.centers[n]) - c) @ U) for n in BACKBONE]
+    nts = []
+    for nt_spec, comp in zip(base_spec["nts"], sb):
+        U = np.asarray(comp.rotation_matrix)
+        c = np.asarray(comp.centers["base"])
+        atoms = []
+        for n, x in local[nt_spec["sequence"]]:
+            p = c + U @ x
+            atoms.append([n, float(p[0]), float(p[1]), float(p[2])])
+        new = dict(nt_spec)
+        new["atoms"] = atoms + nt_spec["atoms"]
+        nts.append(new)
+    return {"pdb": "1GID", "nts": nts}
+
+
+def frames_golden(spec):
+    comps = residues(rf.ref_structure_from_spec(spec))
+    observed = [set(a[0] for a in nt["atoms"]) for nt in spec["nts"]]
+    out = []
+    for comp, obs in zip(comps, observed):
+        hyd = {a.name: [float(a.x), float(a.y), float(a.z)] for a in comp.atoms() if a.name not in obs}
+        out.append({"unit_id": comp.unit_id(),
+                    "center": [float(v) for v in comp.centers["base"]],
+                    "rotation": np.asarray(comp.rotation_matrix).tolist(),
+                    "hydrogens": hyd})
+    return out
+
+
+def annotate_with_traces(spec, categories):
+    """Run annotate_nt_nt_in_structure with every rule function wrapped so each
+    call's (nt1, nt2, result) is recorded in call order."""
+    from fr3d.classifiers import NA_pairwise_interactions as NA
+    structure = rf.ref_structure_from_spec(spec)
+    comps = residues(structure)
+    idx = {c.unit_id(): k for k, c in enumerate(comps)}
+    tr = {"candidates": [], "sO": [], "stacking": [], "sugar_ribose": [], "backbone": [],
+          "coplanar": [], "basepair": []}
+    orig = {}
+
+    def wrap(name, fn):
+        orig[name] = getattr(NA, name)
+        setattr(NA, name, fn)
+
+    def so(nt1, nt2, parent1, dp):
+        r = orig["check_base_oxygen_stack_rings"](nt1, nt2, parent1, dp)
+        tr["sO"].append([idx[nt1.unit_id()], idx[nt2.unit_id()], r[0]])
+        return r
+
+    def stack(nt1, nt2, p1, p2, dp):
+        r = orig["check_base_base_stacking"](nt1, nt2, p1, p2, dp)
+        tr["stacking"].append([idx[nt1.unit_id()], idx[nt2.unit_id()], r[0]])
+        return r
+
+    def sr(nt1, nt2, parent1, dp):
+        r = orig["check_sugar_ribose"](nt1, nt2, parent1, dp)
+        tr["sugar_ribose"].append([idx[nt1.unit_id()], idx[nt2.unit_id()], r[0]])
+        return r
+
+    def bb(nt1, nt2, prevO3, p1, p2, dp):
+        r = orig["check_base_backbone_interactions"](nt1, nt2, prevO3, p1, p2, dp)
+        tr["backbone"].append([idx[nt1.unit_id()], idx[nt2.unit_id()], r[0], r[1]])
+        return r
+
+    def cp(nt1, nt2, pair_data, dp):
+        r = orig["check_coplanar"](nt1, nt2, pair_data, dp)
+        pd = r[0]
+        tr["coplanar"].append([idx[nt1.unit_id()], idx[nt2.unit_id()], bool(pd["coplanar"]),
+                               float(pd["gap12"]),
+                               float(pd["min_distance"]) if "min_distance" in pd else None,
+                               float(pd["coplanar_value"]) if pd["coplanar_value"] is not None else None])
+        return r
+
+    def bp(nt1, nt2, pair_data, cutoffs, hb, dp):
+        r = orig["check_basepair_cutoffs"](nt1, nt2, pair_data, cutoffs, hb, dp)
+        q = r[2]
+        tr["basepair"].append([idx[nt1.unit_id()], idx[nt2.unit_id()], r[0],
+                               r[1] if r[0] else None,
+                               float(q["cutoff_distance"]) if q else None,
+                               float(q["max_gap"]) if q else None])
+        return r
+
+    # candidate order: the screens end right before parent2 = get_parent(nt2.sequence)
+    # (NA_pairwise_interactions.py:726-729); unit_id_pair is built first.  Wrap the
+    # first per-candidate call instead: with 'sO' on it is check_base_oxygen_stack_rings(nt1,nt2).
+    wrap("check_base_oxygen_stack_rings", so)
+    wrap("check_base_base_stacking", stack)
+    wrap("check_sugar_ribose", sr)
+    wrap("check_base_backbone_interactions", bb)
+    wrap("check_coplanar", cp)
+    wrap("check_basepair_cutoffs", bp)
+    buf = io.StringIO()
+    try:
+        with contextlib.redirect_stdout(buf):
+            result = NA.annotate_nt_nt_in_structure(structure, categories)
+    finally:
+        for name, fn in orig.items():
+            setattr(NA, name, fn)
+    if "stacking" in categories:
+        tr["candidates"] = [[a, b] for a, b, _ in tr["stacking"]]
+    i2t = {label: [[idx[a], idx[b], c] for a, b, c in lst] for label, lst in result[0].items()}
+    c2i = {cat: sorted(v) for cat, v in result[1].items()}
+    found = [l for l in buf.getvalue().splitlines() if "Found" in l]
+    return {"categories": categories, "unit_ids": [c.unit_id() for c in comps],
+            "traces": tr, "interaction_to_list_of_tuples": i2t,
+            "category_to_interactions": c2i, "found_line": found[0] if found else ""}
+
+
+def geometry_golden(strand_spec, sarcin_spec):
+    from fr3d.geometry.superpositions import besttransformation, besttransformation_weighted
+    from fr3d.geometry.discrepancy import matrix_discrepancy, matrix_discrepancy_cutoff
+    from fr3d.search import discrepancy as sdisc
+    from fr3d.geometry.angleofrotation import angle_of_rotation
+    out = {}
+
+    # --- Kabsch KATs: inputs of tests/superpositions_test.py:11-119, outputs from the reference
+    a = np.array([[1, 0, 0], [0, 1, 0], [-1, 0, 0], [0, -1, 0], [0, 0, 1.0], [0, 0, -1.0]])
+    b = np.array([[0, 1, 0], [-1, 0, 0], [0, -1, 0], [1, 0, 0], [0, 0, 1.0], [0, 0, -1.0]])
+    kats = [("octahedron_90z", a, b)]
+    p4 = np.array([[2.0, 0, 0], [0, 3.0, 0], [0, 0, 4.0], [1.0, 1.0, 1.0]])
+
+    def rot(axis, ang):
+        c, s = np.cos(ang), np.sin(ang)
+        if axis == 'x':
+            return np.array([[1, 0, 0], [0, c, -s], [0, s, c]])
+        if axis == 'y':
+            return np.array([[c, 0, s], [0, 1, 0], [-s, 0, c]])
+        return np.array([[c, -s, 0], [s, c, 0], [0, 0, 1]])
+
+    for ax in "xyz":
+        kats.append(("p4_45" + ax, p4, p4 @ rot(ax, np.pi / 4).T))
+    kats.append(("p4_xyz", p4, p4 @ (rot('x', 0.3) @ rot('y', -0.7) @ rot('z', 1.1)).T))
+    # reflection case: best fit needs the det fix
+    refl = p4 * np.array([1, 1, -1.0])
+    kats.append(("p4_reflected", p4, refl))
+    rng = np.random.Generator(np.random.PCG64(77))
+    for k in range(40):
+        n = int(rng.integers(3, 12))
+        s1 = rng.normal(size=(n, 3)) * 5
+        R = np.linalg.qr(rng.normal(size=(3, 3)))[0]
+        s2 = s1 @ R + rng.normal(size=(n, 3)) * (0.0 if k % 4 == 0 else 0.3) + rng.normal(size=3) * 10
+        kats.append(("rand%02d" % k, s1, s2))
+    kab = []
+    for name, s1, s2 in kats:
+        U, new1, mean1, rmsd, sse, mean2 = besttransformation(s1, s2)
+        w = (1.0 + np.arange(len(s1)) % 3).tolist()
+        Uw, new1w, mean1w, rmsdw, ssew = besttransformation_weighted(s1, s2, w)
+        kab.append({"name": name, "set1": s1.tolist(), "set2": s2.tolist(),
+                    "U": np.asarray(U).tolist(), "new1": np.asarray(new1).tolist(),
+                    "mean1": np.asarray(mean1).tolist(), "mean2": np.asarray(mean2).tolist(),
+                    "rmsd": float(rmsd), "sse": float(sse),
+                    "weights": w, "Uw": np.asarray(Uw).tolist(), "ssew": float(ssew), "rmsdw": float(rmsdw),
+                    "angle": float(angle_of_rotation(np.asarray(U)))})
+    out["kabsch"] = kab
+
+    # --- discrepancy KATs (tests/discrepancy_tests.py:301-335)
+    st = residues(rf.ref_structure_from_spec(strand_spec))
+    by = {int(c.number): c for c in st}
+
+    def info(nums, source):
+        return ([np.asarray(source[k].centers["base"]) for k in nums],
+                [np.asarray(source[k].rotation_matrix) for k in nums])
+
+    dk = []
+    for name, n1, n2 in [("simple", [10, 11, 12, 13, 14], [15, 16, 17, 18, 19]),
+                         ("another", [10, 12, 14, 16, 18], [11, 13, 15, 17, 19]),
+                         ("pair2", [10, 12], [11, 13])]:
+        c1, r1 = info(n1, by)
+        c2, r2 = info(n2, by)
+        d = float(matrix_discrepancy(c1, r1, c2, r2))
+        ds = float(sdisc.matrix_discrepancy(c1, r1, c2, r2))
+        dc_hi = matrix_discrepancy_cutoff(c1, r1, c2, r2, 2.5)
+        dc_lo = matrix_discrepancy_cutoff(c1, r1, c2, r2, 0.5)
+        dk.append({"name": name, "nts1": n1, "nts2": n2, "d": d, "d_search_copy": ds,
+                   "cutoff_2.5": None if dc_hi is None else float(dc_hi),
+                   "cutoff_0.5": None if dc_lo is None else float(dc_lo),
+                   "centers1": np.array(c1).tolist(), "rotations1": np.array(r1).tolist(),
+                   "centers2": np.array(c2).tolist(), "rotations2": np.array(r2).tolist()})
+    sa = residues(rf.ref_structure_from_spec(sarcin_spec))
+    c1 = [np.asarray(c.centers["base"]) for c in sa[:7]]
+    r1 = [np.asarray(c.rotation_matrix) for c in sa[:7]]
+    c2 = [np.asarray(c.centers["base"]) for c in sa[7:]]
+    r2 = [np.asarray(c.rotation_matrix) for c in sa[7:]]
+    dk.append({"name": "sarcin7", "d": float(matrix_discrepancy(c1, r1, c2, r2)),
+               "centers1": np.array(c1).tolist(), "rotations1": np.array(r1).tolist(),
+               "centers2": np.array(c2).tolist(), "rotations2": np.array(r2).tolist()})
+    sel = [0, 1, 2, 4, 5]
+    dk.append({"name": "sarcin5", "d": float(matrix_discrepancy([c1[k] for k in sel], [r1[k] for k in sel],
+                                                                 [c2[k] for k in sel], [r2[k] for k in sel])),
+               "centers1": np.array([c1[k] for k in sel]).tolist(), "rotations1": np.array([r1[k] for k in sel]).tolist(),
+               "centers2": np.array([c2[k] for k in sel]).tolist(), "rotations2": np.array([r2[k] for k in sel]).tolist()})
+    out["discrepancy_kats"] = dk
+
+    # --- a seeded all-vs-all block: instance set made like SURVEY §8(d) C5 (seed 5000), N=48, n=7
+    inst_c, inst_r = make_instances(np.array(c1), np.array(r1), 48, 5000)
+    N = len(inst_c)
+    D = np.zeros((N, N))
+    for i in range(N):
+        for j in range(i + 1, N):
+            D[i, j] = matrix_discrepancy(list(inst_c[i]), list(inst_r[i]), list(inst_c[j]), list(inst_r[j]))
+            D[j, i] = D[i, j]
+    # position-0 rotation-less variant (NA_protein_annotation.py:1705-1714)
+    Dn = np.zeros((N, N))
+    empty = np.empty((0, 0))
+    for i in range(N):
+        for j in range(i + 1, N):
+            ri = [empty] + list(inst_r[i][1:])
+            rj = [empty] + list(inst_r[j][1:])
+            Dn[i, j] = matrix_discrepancy(list(inst_c[i]), ri, list(inst_c[j]), rj)
+            Dn[j, i] = Dn[i, j]
+    cut = 0.6
+    row0 = [matrix_discrepancy_cutoff(list(inst_c[0]), list(inst_r[0]), list(inst_c[j]), list(inst_r[j]), cut)
+            for j in range(N)]
+    out["all_vs_all"] = {"seed": 5000, "N": N, "n": 7, "base_centers": np.array(c1).tolist(),
+                         "base_rotations": np.array(r1).tolist(),
+                         "centers": inst_c.tolist(), "rotations": inst_r.tolist(),
+                         "D": D.tolist(), "D_norot0": Dn.tolist(), "cutoff": cut,
+                         "row0_cutoff": [None if v is None else float(v) for v in row0]}
+    return out
+
+
+def make_instances(base_c, base_r, N, seed):
+    """SURVEY §8(d) C5 recipe: rigid motion + centre noise N(0,0.5) + per-rotation
+    perturbation of angle ~N(0,0.15 rad).  MUST stay in sync with
+    fr3d_python_b200.synthetic.make_instances (tests compare the arrays)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    n = base_c.shape[0]
+    C = np.zeros((N, n, 3))
+    R = np.zeros((N, n, 3, 3))
+    for k in range(N):
+        Q = _random_rotation(rng)
+        t = rng.normal(size=3) * 20.0
+        C[k] = base_c @ Q.T + t + rng.normal(size=(n, 3)) * 0.5
+        for p in range(n):
+            axis = rng.normal(size=3)
+            axis /= np.linalg.norm(axis)
+            ang = rng.normal() * 0.15
+            R[k, p] = Q @ base_r[p] @ _axis_angle(axis, ang)
+    return C, R
+
+
+def _random_rotation(rng):
+    q = rng.normal(size=4)
+    q /= np.linalg.norm(q)
+    w, x, y, z = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+def _axis_angle(axis, ang):
+    x, y, z = axis
+    K = np.array([[0, -z, y], [z, 0, -x], [-y, x, 0]])
+    return np.eye(3) + np.sin(ang) * K + (1 - np.cos(ang)) * (K @ K)
+
+
+ALL9 = {'basepair': LW18 + ['cWB', 'cBW'], 'basepair_detail': [], 'stacking': [], 'sO': [], 'backbone': [],
+        'coplanar': [], 'sugar_ribose': [], 'covalent': [], 'near': []}
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    base = rf.spec_1gid_base()
+    strand = rf.spec_1s72_strand()
+    sarcin = rf.spec_1s72_sarcin()
+    full = make_spec_1gid_full(base, strand)
+    dump("spec_1gid_base.json.gz", base)
+    dump("spec_1gid_full.json.gz", full)
+    dump("spec_1s72_strand.json.gz", strand)
+    dump("spec_1s72_sarcin.json.gz", sarcin)
+    dump("matlab_1gid_frames.json.gz", rf.parse_matlab_rotations())
+    for name, spec in [("1gid_full", full), ("1s72_strand", strand), ("1s72_sarcin", sarcin)]:
+        dump("frames_%s.json.gz" % name, frames_golden(spec))
+    dump("annot_1gid_full_all9.json.gz", annotate_with_traces(full, ALL9))
+    dump("annot_1s72_strand_all9.json.gz", annotate_with_traces(strand, ALL9))
+    dump("annot_1gid_base_bp_stack_cp.json.gz",
+         annotate_with_traces(base, {'basepair': LW18, 'stacking': [], 'coplanar': []}))
+    dump("annot_1gid_base_bp.json.gz", annotate_with_traces(base, {'basepair': LW18}))
+    dump("geometry.json.gz", geometry_golden(strand, sarcin))
+
+
+if __name__ == "__main__":
+    main()
