@@ -1,0 +1,119 @@
+"""ctypes binding of libfr3d_b200.so (C ABI in include/fr3d_b200.h).
+
+There is no CPU fallback: if the shared library is missing or a CUDA device
+is not available, every compute entry point raises.
+"""
+
+import ctypes as C
+import os
+import subprocess
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libfr3d_b200.so")
+CSRC = os.path.join(_HERE, "csrc")
+INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
+
+BASE_SLOTS = 16
+BB_SLOTS = 10
+META_INTS = 8
+N_PARENTS = 5
+MASK_HAS_FRAME = 0x80000000
+FLAG_STD_RNA = 1
+FLAG_MODIFIED = 2
+
+CAT_SO, CAT_STACKING, CAT_SUGAR_RIBOSE, CAT_BACKBONE, CAT_COPLANAR = 1, 2, 4, 8, 16
+SLOT_SO12, SLOT_SO21, SLOT_STACK, SLOT_SR12, SLOT_SR21, SLOT_BPH, SLOT_BR, SLOT_CP, SLOT_BP = range(9)
+
+E_CUDA, E_ARG, E_CAPACITY, E_NOTABLES, E_RANGE = -1, -2, -3, -4, -5
+
+EXPORTS = ["fr3d_version", "fr3d_last_error", "fr3d_init", "fr3d_upload_tables", "fr3d_frames_fit",
+           "fr3d_pair_search_workspace", "fr3d_pair_search", "fr3d_classify_pairs", "fr3d_kabsch_batched",
+           "fr3d_discrepancy_all_vs_all", "fr3d_discrepancy_one_vs_many"]
+
+
+class Fr3dError(RuntimeError):
+    pass
+
+
+class NtsStruct(C.Structure):
+    _fields_ = [("n_nt", C.c_int32), ("reserved", C.c_int32),
+                ("center", C.c_void_p), ("rot", C.c_void_p), ("base_xyz", C.c_void_p), ("bb_xyz", C.c_void_p),
+                ("base_mask", C.c_void_p), ("bb_mask", C.c_void_p), ("meta", C.c_void_p)]
+
+
+class StaticTables(C.Structure):
+    _fields_ = [("std_xyz", C.c_double * 3 * BASE_SLOTS * N_PARENTS),
+                ("n_heavy", C.c_int32 * N_PARENTS), ("n_slots", C.c_int32 * N_PARENTS),
+                ("has_div", C.c_int32 * N_PARENTS), ("sr_slot", C.c_int32 * N_PARENTS),
+                ("ring_div", C.c_double * 3 * N_PARENTS),
+                ("ring5", C.c_double * 3 * 4 * N_PARENTS), ("ring6", C.c_double * 3 * 6 * N_PARENTS),
+                ("ell5", C.c_double * 5 * N_PARENTS), ("ell6", C.c_double * 5 * N_PARENTS),
+                ("hull", C.c_double * 3 * 7 * N_PARENTS),
+                ("n_sites", C.c_int32 * N_PARENTS),
+                ("site_h", C.c_int32 * 5 * N_PARENTS), ("site_m", C.c_int32 * 5 * N_PARENTS),
+                ("site_carbon", C.c_int32 * 5 * N_PARENTS), ("site_digit", C.c_int32 * 5 * N_PARENTS),
+                ("combo_ok", C.c_int32 * (N_PARENTS * N_PARENTS))]
+
+
+_lock = threading.Lock()
+_lib = None
+
+
+def build(verbose=False):
+    """Compile csrc/fr3d_b200.cu for sm_100a into lib/libfr3d_b200.so (in-tree)."""
+    os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
+    cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+           "-shared", "-Xcompiler", "-fPIC", "-cudart", "static", "-o", LIB_PATH,
+           os.path.join(CSRC, "fr3d_b200.cu")]
+    if verbose:
+        cmd.insert(1, "-Xptxas")
+        cmd.insert(2, "-v")
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise Fr3dError("nvcc failed:\n" + res.stdout + res.stderr)
+    return res.stdout + res.stderr
+
+
+def needs_build():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(INCLUDE, "fr3d_b200.h")]
+    return any(os.path.getmtime(s) > t for s in srcs)
+
+
+def load():
+    """dlopen the library and declare prototypes (no CUDA call is made here)."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise Fr3dError("libfr3d_b200.so not built (%s); run `python -c 'import __graft_entry__ as g; g.build()'`. "
+                            "There is no CPU fallback." % LIB_PATH)
+        lib = C.CDLL(LIB_PATH)
+        vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+        lib.fr3d_version.restype = C.c_int
+        lib.fr3d_last_error.restype = C.c_char_p
+        lib.fr3d_init.argtypes = [C.c_int]
+        lib.fr3d_upload_tables.argtypes = [C.POINTER(StaticTables)]
+        lib.fr3d_frames_fit.argtypes = [C.POINTER(NtsStruct), vp, C.c_int, vp]
+        lib.fr3d_pair_search_workspace.argtypes = [i32]
+        lib.fr3d_pair_search_workspace.restype = C.c_size_t
+        lib.fr3d_pair_search.argtypes = [C.POINTER(NtsStruct), dbl, vp, C.c_size_t, vp, vp, vp, i64, vp, vp]
+        lib.fr3d_classify_pairs.argtypes = [C.POINTER(NtsStruct), vp, vp, vp, vp, vp, i64, C.c_uint32, vp, i64, vp, vp]
+        lib.fr3d_kabsch_batched.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp]
+        lib.fr3d_discrepancy_all_vs_all.argtypes = [vp, vp, vp, i32, i32, dbl, i32, i32, vp, vp]
+        lib.fr3d_discrepancy_one_vs_many.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, dbl, dbl, vp, vp, vp]
+        for name in EXPORTS:
+            if name not in ("fr3d_last_error", "fr3d_pair_search_workspace"):
+                getattr(lib, name).restype = C.c_int
+        _lib = lib
+        return lib
+
+
+def check(code, what=""):
+    if code != 0:
+        msg = load().fr3d_last_error().decode(errors="replace")
+        raise Fr3dError("%s failed with code %d: %s" % (what or "libfr3d_b200 call", code, msg))

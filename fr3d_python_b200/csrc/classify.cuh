@@ -1,0 +1,647 @@
+// K4: one warp per candidate pair applies every pairwise rule of the reference
+// annotator and emits compacted hit records.
+//
+// Replaces, per pair (nt1, nt2), in the reference's own evaluation order
+// (NA = fr3d/classifiers/NA_pairwise_interactions.py):
+//   check_base_oxygen_stack_rings x2   NA:1278-1473   (lanes 0-5 / 8-13: one oxygen each)
+//   check_base_base_stacking           NA:1602-1739   (lanes 0-15: base atoms of nt2 in frame 1,
+//                                                      lanes 16-31: base atoms of nt1 in frame 2)
+//   check_sugar_ribose x2              NA:2262-2342   (lane 0 / lane 1)
+//   check_base_backbone_interactions   NA:1867-2049   (lane = site*6 + oxygen; sticky selection on lane 0)
+//   check_coplanar + calculate_basepair_gap + calculate_base_min_distances
+//                                      NA:2051-2259, 1799-1829 (both half-warps at once)
+//   check_basepair_cutoffs x2          NA:2364-2759   (one lane per cutoff box)
+//   12-vs-21 arbitration               NA:935-957
+// Everything that decides a threshold is fp64.  All branches are warp-uniform
+// (a warp owns one pair), expensive stages (15x15 min distance, gaps) run only
+// when the reference would reach them.
+//
+// Memory: the two nts' base atoms (<= 32 x 3 doubles) are staged in shared
+// memory per warp with coalesced loads (lane k reads atom k's contiguous 24 B),
+// frames are broadcast loads.  Algorithmic traffic per pair (gather model,
+// SURVEY §8(d)): 2 x 760 B nt records + 12 B pair + 32 B hit slot.
+#pragma once
+
+#include "tables.cuh"
+
+namespace fr3d {
+
+#define FULL 0xFFFFFFFFu
+
+struct Frame {
+    double c[3];
+    double U[9];   // row major rotation_matrix
+};
+
+__device__ __forceinline__ void load_frame(const fr3d_nts_t &nts, int n, Frame &f) {
+    const double *c = nts.center + (size_t)n * 3;
+    const double *r = nts.rot + (size_t)n * 9;
+    f.c[0] = c[0]; f.c[1] = c[1]; f.c[2] = c[2];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) f.U[k] = r[k];
+}
+
+// translate_rotate_point (NA:1263-1275): (p - centre) . U as a row vector
+__device__ __forceinline__ void to_frame(const Frame &f, double px, double py, double pz, double &x, double &y,
+                                         double &z) {
+    const double v0 = px - f.c[0], v1 = py - f.c[1], v2 = pz - f.c[2];
+    x = v0 * f.U[0] + v1 * f.U[3] + v2 * f.U[6];
+    y = v0 * f.U[1] + v1 * f.U[4] + v2 * f.U[7];
+    z = v0 * f.U[2] + v1 * f.U[5] + v2 * f.U[8];
+}
+
+__device__ __forceinline__ bool left_of(const double *l, double x, double y) { return l[0] * x + l[1] * y + l[2] > 0; }
+
+// check_convex_hull_atoms, NA:1475-1528
+__device__ __forceinline__ bool in_hull(int parent, double x, double y, double z) {
+    if (!(fabs(z) < 4.5)) return false;
+    bool in = true;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) in = in && left_of(c_tab.hull[parent][k], x, y);
+    return in;
+}
+
+__device__ __forceinline__ bool in_ellipse(const double *e, double x, double y) {
+    const double dx = x - e[2], dy = y - e[3];
+    return e[0] * (dx * dx) + e[1] * dx * dy + dy * dy < e[4];
+}
+
+// min over a group of `width` lanes of (key, idx) pairs, lexicographic; all lanes get the result
+template <int WIDTH>
+__device__ __forceinline__ void group_argmin(double &key, int &idx) {
+#pragma unroll
+    for (int off = WIDTH / 2; off > 0; off >>= 1) {
+        const double k2 = __shfl_xor_sync(FULL, key, off);
+        const int i2 = __shfl_xor_sync(FULL, idx, off);
+        if (k2 < key || (k2 == key && i2 < idx)) { key = k2; idx = i2; }
+    }
+}
+
+template <int WIDTH>
+__device__ __forceinline__ double group_min(double v) {
+#pragma unroll
+    for (int off = WIDTH / 2; off > 0; off >>= 1) v = fmin(v, __shfl_xor_sync(FULL, v, off));
+    return v;
+}
+
+template <int WIDTH>
+__device__ __forceinline__ double group_max(double v) {
+#pragma unroll
+    for (int off = WIDTH / 2; off > 0; off >>= 1) v = fmax(v, __shfl_xor_sync(FULL, v, off));
+    return v;
+}
+
+// angle_between_vectors (NA:2873-2881) of (A-B, C-B), degrees
+__device__ __forceinline__ double hb_angle(const double *A, const double *B, const double *C) {
+    const double u0 = A[0] - B[0], u1 = A[1] - B[1], u2 = A[2] - B[2];
+    const double w0 = C[0] - B[0], w1 = C[1] - B[1], w2 = C[2] - B[2];
+    const double cosang = u0 * w0 + u1 * w1 + u2 * w2;
+    const double x0 = u1 * w2 - u2 * w1, x1 = u2 * w0 - u0 * w2, x2 = u0 * w1 - u1 * w0;
+    const double sinang = sqrt(x0 * x0 + x1 * x1 + x2 * x2);
+    return 180.0 * atan2(sinang, cosang) / 3.141592653589793;
+}
+
+__device__ __forceinline__ double dist3(const double *a, const double *b) {
+    const double d0 = a[0] - b[0], d1 = a[1] - b[1], d2 = a[2] - b[2];
+    return sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+}
+
+// check_sugar_ribose, NA:2262-2342 (scalar, one lane).  Returns -1 none, 0 cSR, 1 tSR.
+__device__ int sugar_ribose(const fr3d_nts_t &nts, int na, int nb, int parent_a, const Frame &fa) {
+    const uint32_t bba = nts.bb_mask[na], bbb = nts.bb_mask[nb];
+    if (!(bba >> 6 & 1u) || !(bbb >> 6 & 1u)) return -1;            // O2' of both
+    const double *A = nts.bb_xyz + (size_t)na * FR3D_BB_SLOTS * 3;
+    const double *B = nts.bb_xyz + (size_t)nb * FR3D_BB_SLOTS * 3;
+    if (dist3(A + 6 * 3, B + 6 * 3) > 3.8) return -1;
+    const int bs = c_tab.sr_slot[parent_a];
+    if (bs < 0) return -1;
+    if (!(nts.base_mask[na] >> bs & 1u)) return -1;
+    const double *bp = nts.base_xyz + ((size_t)na * FR3D_BASE_SLOTS + bs) * 3;
+    const double d0 = bp[0] - B[18], d1 = bp[1] - B[19], d2 = bp[2] - B[20];
+    if (sqrt(d0 * d0 + d1 * d1 + d2 * d2) > 3.8) return -1;
+    const double z = fabs(d0 * fa.U[2] + d1 * fa.U[5] + d2 * fa.U[8]);
+    if (z > 2.0) return -1;
+    // torsion C1'(a) C2'(a) C2'(b) C1'(b), NA:2904-2930
+    if (!(bba >> 7 & 1u) || !(bba >> 8 & 1u) || !(bbb >> 7 & 1u) || !(bbb >> 8 & 1u)) return -1;
+    const double *p0 = A + 7 * 3, *p1 = A + 8 * 3, *p2 = B + 8 * 3, *p3 = B + 7 * 3;
+    double b0[3], b1[3], b2[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { b0[k] = -1.0 * (p1[k] - p0[k]); b1[k] = p2[k] - p1[k]; b2[k] = p3[k] - p2[k]; }
+    const double nb1 = sqrt(b1[0] * b1[0] + b1[1] * b1[1] + b1[2] * b1[2]);
+    b1[0] /= nb1; b1[1] /= nb1; b1[2] /= nb1;
+    const double d01 = b0[0] * b1[0] + b0[1] * b1[1] + b0[2] * b1[2];
+    const double d21 = b2[0] * b1[0] + b2[1] * b1[1] + b2[2] * b1[2];
+    double v[3], w[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { v[k] = b0[k] - d01 * b1[k]; w[k] = b2[k] - d21 * b1[k]; }
+    const double x = v[0] * w[0] + v[1] * w[1] + v[2] * w[2];
+    const double cx0 = b1[1] * v[2] - b1[2] * v[1], cx1 = b1[2] * v[0] - b1[0] * v[2], cx2 = b1[0] * v[1] - b1[1] * v[0];
+    const double y = cx0 * w[0] + cx1 * w[1] + cx2 * w[2];
+    const double angle = atan2(y, x) * (180.0 / 3.141592653589793);
+    return fabs(angle) > 90.0 ? 0 : 1;
+}
+
+// Result of check_basepair_cutoffs for one orientation
+struct BpResult {
+    int box;        // -1: no annotation
+    int near;       // LW gets the "n" prefix
+    double cd;      // cutoff_distance
+};
+
+static constexpr int WARPS_PER_BLOCK = 4;
+
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+classify_pairs_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, const int32_t *__restrict__ box_index,
+                      const int32_t *__restrict__ pair_i, const int32_t *__restrict__ pair_j,
+                      const int32_t *__restrict__ pair_rank, int64_t pair_cap, uint32_t cats,
+                      fr3d_hit_t *__restrict__ hits, int64_t hit_cap, int64_t *counters) {
+    __shared__ double s_atoms[WARPS_PER_BLOCK][32][3];   // lanes 0-15: nt2 base atoms, 16-31: nt1 base atoms
+    __shared__ double s_ang[WARPS_PER_BLOCK][32];
+    __shared__ double s_dst[WARPS_PER_BLOCK][32];
+
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    const long long warp0 = (long long)blockIdx.x * WARPS_PER_BLOCK + wib;
+    const long long nwarps = (long long)gridDim.x * WARPS_PER_BLOCK;
+    long long n_pairs = counters[0];
+    if (n_pairs > pair_cap) n_pairs = pair_cap;
+    const int half = lane >> 4;      // 0: atoms of nt2 seen from frame 1, 1: atoms of nt1 seen from frame 2
+    const int a = lane & 15;
+
+    for (long long p = warp0; p < n_pairs; p += nwarps) {
+        const int n1 = pair_i[p], n2 = pair_j[p], rank = pair_rank[p];
+        Frame f1, f2;
+        load_frame(nts, n1, f1);
+        load_frame(nts, n2, f2);
+        const int par1 = nts.meta[(size_t)n1 * FR3D_META_INTS], par2 = nts.meta[(size_t)n2 * FR3D_META_INTS];
+        const int fl1 = nts.meta[(size_t)n1 * FR3D_META_INTS + 1], fl2 = nts.meta[(size_t)n2 * FR3D_META_INTS + 1];
+        const uint32_t bm1 = nts.base_mask[n1], bm2 = nts.base_mask[n2];
+
+        // ---- stage base atoms: lane -> (own nt, atom a), projected into the OTHER nt's frame
+        const int own = half ? n1 : n2;
+        const uint32_t ownmask = half ? bm1 : bm2;
+        const bool valid = (ownmask >> a) & 1u;
+        double px = 0, py = 0, pz = 0;
+        if (valid) {
+            const double *q = nts.base_xyz + ((size_t)own * FR3D_BASE_SLOTS + a) * 3;
+            px = q[0]; py = q[1]; pz = q[2];
+        }
+        __syncwarp();
+        s_atoms[wib][lane][0] = px; s_atoms[wib][lane][1] = py; s_atoms[wib][lane][2] = pz;
+        __syncwarp();
+        const Frame &fo = half ? f2 : f1;         // frame the atom is projected into
+        const int paro = half ? par2 : par1;
+        double x, y, z;
+        to_frame(fo, px, py, pz, x, y, z);
+        // squared distance to the other base centre (for calculate_basepair_gap's argsort)
+        const double d2c = valid ? ((px - fo.c[0]) * (px - fo.c[0]) + (py - fo.c[1]) * (py - fo.c[1]) +
+                                    (pz - fo.c[2]) * (pz - fo.c[2]))
+                                 : 1e300;
+
+        // lazily computed, shared by coplanar and both basepair orientations
+        bool have_gaps = false, have_mind = false;
+        double gap12 = 100.0, gap21 = 100.0, mind = 9999.0;
+
+        auto compute_gaps = [&]() {               // calculate_basepair_gap, NA:2189-2259, both directions
+            double key = d2c;
+            double g = 100.0;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                double k = key; int idx = a;
+                group_argmin<16>(k, idx);
+                const double zz = fabs(__shfl_sync(FULL, z, (lane & 16) | idx));
+                if (k < 1e299) {
+                    if (zz < g) g = zz;
+                    if (a == idx) key = 1e300;
+                }
+            }
+            gap12 = __shfl_sync(FULL, g, 0);
+            gap21 = __shfl_sync(FULL, g, 16);
+            have_gaps = true;
+        };
+        auto compute_mind = [&]() {               // calculate_base_min_distances, NA:1799-1829
+            // lower half: nt2 atom `a` against nt1 atoms 0-7; upper half: nt2 atom `a` against nt1 atoms 8-15
+            const bool v2 = (bm2 >> a) & 1u;
+            const double qx = s_atoms[wib][a][0], qy = s_atoms[wib][a][1], qz = s_atoms[wib][a][2];
+            double best = 1e300;
+#pragma unroll
+            for (int s = 0; s < 8; ++s) {
+                const int k1 = s + 8 * half;
+                if (v2 && ((bm1 >> k1) & 1u)) {
+                    const double dx = s_atoms[wib][16 + k1][0] - qx, dy = s_atoms[wib][16 + k1][1] - qy,
+                                 dz = s_atoms[wib][16 + k1][2] - qz;
+                    best = fmin(best, dx * dx + dy * dy + dz * dz);
+                }
+            }
+            best = group_min<32>(best);
+            mind = best < 1e299 ? sqrt(best) : 9999.0;
+            have_mind = true;
+        };
+
+        // decisions for the nine hit slots (warp-uniform)
+        int h_valid[9], h_code[9];
+#pragma unroll
+        for (int k = 0; k < 9; ++k) { h_valid[k] = 0; h_code[k] = 0; }
+        int bp_box = 0;
+        double bp_cd = 0.0, bp_gap = 0.0;
+
+        // ================= base-oxygen stacking, both directions (NA:758-778) =================
+        if (cats & FR3D_CAT_SO) {
+            // group g = lane>>3 (0: base nt1 / oxygens nt2, 1: base nt2 / oxygens nt1), o = lane&7 < 6
+            const int g = (lane >> 3) & 1, o = lane & 7;
+            const bool act = lane < 16 && o < 6;
+            const int nb = g ? n2 : n1;            // base owner
+            const int no = g ? n1 : n2;            // oxygen owner
+            const Frame &fb = g ? f2 : f1;
+            const int pb = g ? par2 : par1;
+            // oxygens O2' O3' O4' O5' OP1 OP2 (NA:1290) -> backbone slots 6 5 4 3 1 2
+            const int oslot = (o == 0) ? 6 : (o == 1) ? 5 : (o == 2) ? 4 : (o == 3) ? 3 : (o == 4) ? 1 : 2;
+            bool present = false;
+            double ox = 0, oy = 0, oz = 0;
+            if (act && (nts.bb_mask[no] >> oslot & 1u)) {
+                const double *q = nts.bb_xyz + ((size_t)no * FR3D_BB_SLOTS + oslot) * 3;
+                to_frame(fb, q[0], q[1], q[2], ox, oy, oz);
+                present = true;
+            }
+            bool ring = false;
+            const bool has_tab = pb >= 0 && pb < FR3D_N_PARENTS;
+            if (present && has_tab && !(fabs(oz) < 2.0) && fabs(oz) < 3.6) {
+                if (c_tab.has_div[pb]) {
+                    if (left_of(c_tab.ring_div[pb], ox, oy)) {
+                        ring = true;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) ring = ring && left_of(c_tab.ring5[pb][k], ox, oy);
+                    } else {
+                        ring = true;
+#pragma unroll
+                        for (int k = 0; k < 6; ++k) ring = ring && left_of(c_tab.ring6[pb][k], ox, oy);
+                    }
+                } else {
+                    ring = true;
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) ring = ring && left_of(c_tab.ring6[pb][k], ox, oy);
+                }
+            }
+            const unsigned ring_b = __ballot_sync(FULL, ring);
+            const unsigned true_b = __ballot_sync(FULL, ring && fabs(oz) < 3.5);
+            const unsigned gmask = 0xFFu << (g * 8);
+            double key = ring ? fabs(oz) : 1e300;
+            int idx = o;
+            group_argmin<8>(key, idx);
+            // over a ring: true if any |z| < 3.5, else near (NA:1386-1400)
+            const double zsel_ring = __shfl_sync(FULL, oz, (lane & ~7) | idx);
+            // near-ring ellipses, used only when no oxygen is over a ring (NA:1402-1459)
+            bool nr = false;
+            if (present && has_tab && fabs(oz) < 3.5) {
+                if (c_tab.has_div[pb]) {
+                    if (left_of(c_tab.ring_div[pb], ox, oy)) nr = in_ellipse(c_tab.ell5[pb], ox, oy);
+                    else nr = in_ellipse(c_tab.ell6[pb], ox, oy);
+                } else {
+                    nr = in_ellipse(c_tab.ell6[pb], ox, oy);
+                }
+            }
+            double k2 = nr ? (ox * ox + oy * oy) : 1e300;
+            int i2 = o;
+            group_argmin<8>(k2, i2);
+            const double zsel_near = __shfl_sync(FULL, oz, (lane & ~7) | i2);
+            int code = -1;
+            if (ring_b & gmask) code = idx | ((zsel_ring > 0) ? 0 : 8) | ((true_b & gmask) ? 0 : 16);
+            else if (k2 < 1e299) code = i2 | ((zsel_near > 0) ? 0 : 8) | 16;
+            const int code12 = __shfl_sync(FULL, code, 0);
+            const int code21 = __shfl_sync(FULL, code, 8);
+            if (code12 >= 0) { h_valid[FR3D_SLOT_SO12] = 1; h_code[FR3D_SLOT_SO12] = code12; }
+            if (code21 >= 0) { h_valid[FR3D_SLOT_SO21] = 1; h_code[FR3D_SLOT_SO21] = code21; }
+        }
+
+        // ================= base-base stacking (NA:1602-1739) =================
+        if ((cats & FR3D_CAT_STACKING) && par1 >= 0 && par2 >= 0) {
+            const bool inside = valid && in_hull(paro, x, y, z);
+            const unsigned in_b = __ballot_sync(FULL, inside);
+            const double zmin = group_min<16>(valid ? z : 1e300);
+            const double zmax = group_max<16>(valid ? z : -1e300);
+            double key = valid ? fabs(z) : 1e300;
+            int idx = a;
+            group_argmin<16>(key, idx);
+            const double zsel = __shfl_sync(FULL, z, (lane & 16) | idx);
+            const unsigned hmask = 0xFFFFu << (half * 16);
+            const bool ov = (in_b & hmask) && !(zmax > 0 && zmin < 0);       // return_overlap, NA:1567-1571
+            const bool nt2on1 = __shfl_sync(FULL, (int)ov, 0);
+            const bool nt1on2 = __shfl_sync(FULL, (int)ov, 16);
+            const double z_2on1 = __shfl_sync(FULL, zsel, 0);
+            const double z_1on2 = __shfl_sync(FULL, zsel, 16);
+            if (nt2on1 || nt1on2) {
+                const double normal_Z = f1.U[2] * f2.U[2] + f1.U[5] * f2.U[5] + f1.U[8] * f2.U[8];
+                const bool reverse = nt1on2 && !nt2on1;                        // NA:1663-1667
+                const double mvd = reverse ? z_1on2 : z_2on1;
+                int code = -1;                                                 // 0 s35 1 s53 2 s33 3 s55
+                if (mvd > 0) { if (normal_Z > 0) code = 0; else if (normal_Z < 0) code = 2; }
+                else if (mvd < 0) { if (normal_Z > 0) code = 1; else if (normal_Z < 0) code = 3; }
+                if (reverse && code >= 0 && code < 2) code ^= 1;              // swap s35 <-> s53 (NA:1699-1702)
+                compute_mind();
+                int near = 1;
+                if (fabs(mind) < 4.0 && fabs(mind) > 1.0 && fabs(normal_Z) > 0.6 && nt2on1 && nt1on2) near = 0;
+                if (fabs(mind) < 1.0 || fabs(normal_Z) < 0.5) code = -1;       // NA:1717
+                if (code >= 0) { h_valid[FR3D_SLOT_STACK] = 1; h_code[FR3D_SLOT_STACK] = code | (near << 2); }
+            }
+        }
+
+        // ================= sugar-ribose, both directions (NA:791-804) =================
+        if ((cats & FR3D_CAT_SUGAR_RIBOSE) && par1 >= 0 && par2 >= 0 && par1 != 4 && par2 != 4) {
+            int r = -1;
+            if (lane == 0) r = sugar_ribose(nts, n1, n2, par1, f1);
+            else if (lane == 1) r = sugar_ribose(nts, n2, n1, par2, f2);
+            const int r12 = __shfl_sync(FULL, r, 0), r21 = __shfl_sync(FULL, r, 1);
+            if (r12 >= 0) { h_valid[FR3D_SLOT_SR12] = 1; h_code[FR3D_SLOT_SR12] = r12; }
+            if (r21 >= 0) { h_valid[FR3D_SLOT_SR21] = 1; h_code[FR3D_SLOT_SR21] = r21; }
+        }
+
+        // ================= base-phosphate / base-ribose, nt1 base -> nt2 backbone (NA:807-829) =================
+        if ((cats & FR3D_CAT_BACKBONE) && par1 >= 0) {
+            const int site = lane / 6, ok = lane - site * 6;    // ok: 0 O5' 1 OP1 2 OP2 3 prevO3' | 4 O2' 5 O4'
+            const int nsites = c_tab.n_sites[par1];
+            const uint32_t bb2 = nts.bb_mask[n2];
+            const double *B = nts.bb_xyz + (size_t)n2 * FR3D_BB_SLOTS * 3;
+            double ang = 0.0, dst = 0.0;
+            if (lane < 30 && site < nsites) {
+                const int oslot = (ok == 0) ? 3 : (ok == 1) ? 1 : (ok == 2) ? 2 : (ok == 3) ? 9 : (ok == 4) ? 6 : 4;
+                const int hs = c_tab.site_h[par1][site], ms = c_tab.site_m[par1][site];
+                if ((bb2 >> oslot & 1u) && (bm1 >> hs & 1u) && (bm1 >> ms & 1u)) {
+                    const double *O = B + oslot * 3;
+                    if (O[0] != 0.0 || O[1] != 0.0 || O[2] != 0.0) {            // .any(), NA:1939,1959
+                        const double *H = nts.base_xyz + ((size_t)n1 * FR3D_BASE_SLOTS + hs) * 3;
+                        const double *Mv = nts.base_xyz + ((size_t)n1 * FR3D_BASE_SLOTS + ms) * 3;
+                        ang = hb_angle(Mv, H, O);
+                        dst = dist3(Mv, O);
+                    }
+                }
+            }
+            __syncwarp();
+            s_ang[wib][lane] = ang; s_dst[wib][lane] = dst;
+            __syncwarp();
+            int bph = -1, br = -1;
+            if (lane == 0) {
+                // if nt2 has a P atom far from the plane of base 1, no BPh (NA:1915-1921)
+                bool use_ph = true;
+                if (bb2 & 1u) {
+                    if (B[0] != 0.0 || B[1] != 0.0 || B[2] != 0.0) {
+                        double tx, ty, tz;
+                        to_frame(f1, B[0], B[1], B[2], tx, ty, tz);
+                        if (fabs(tz) > 4.5) use_ph = false;
+                    }
+                }
+                int n_true = 0, n_near = 0, n_keys = 0;
+                unsigned long long site_ox = 0;        // 4 bits of oxygen indices per label digit
+                double best_tq = -1e300, best_nq = -1e300;
+                int best_tl = -1, best_nl = -1, first_tl = -1, first_nl = -1;
+                int rt = 0, rn = 0, best_rtl = -1, best_rnl = -1, first_rtl = -1, first_rnl = -1;
+                double best_rtq = -1e300, best_rnq = -1e300;
+                double cutoff = 0.0, ncutoff = 0.0;
+                for (int s = 0; s < nsites; ++s) {
+                    const int carbon = c_tab.site_carbon[par1][s];
+                    const int digit = c_tab.site_digit[par1][s];
+                    if (carbon == 1) { cutoff = 4.0; ncutoff = 4.5; }          // NA:1930-1935
+                    else if (carbon == 0) { cutoff = 3.5; ncutoff = 4.0; }
+                    if (use_ph) {
+                        for (int i = 0; i < 4; ++i) {
+                            const double an = s_ang[wib][s * 6 + i], ds = s_dst[wib][s * 6 + i];
+                            if (an != 0.0 && ds != 0.0) {                      // `if phosphateAngle:` / `if phosphateDistance:`
+                                if (an > 130.0 && ds < cutoff) {
+                                    const double q = (cutoff - ds) + (an - 130.0) / 20.0;
+                                    if (n_true == 0) first_tl = digit;
+                                    ++n_true;
+                                    if (q > best_tq || (q == best_tq && digit < best_tl)) { best_tq = q; best_tl = digit; }
+                                    if (!((site_ox >> (digit * 4)) & 0xFull)) ++n_keys;
+                                    site_ox |= 1ull << (digit * 4 + i);
+                                } else if (an > 110.0 && ds < ncutoff) {
+                                    const double q = (ncutoff - ds) + (an - 110.0) / 20.0;
+                                    if (n_near == 0) first_nl = digit;
+                                    ++n_near;
+                                    if (q > best_nq || (q == best_nq && digit < best_nl)) { best_nq = q; best_nl = digit; }
+                                }
+                            }
+                        }
+                    }
+                    for (int i = 4; i < 6; ++i) {
+                        const double an = s_ang[wib][s * 6 + i], ds = s_dst[wib][s * 6 + i];
+                        if (an != 0.0 && ds != 0.0) {
+                            if (an > 130.0 && ds < cutoff) {
+                                const double q = (cutoff - ds) + (an - 130.0) / 20.0;
+                                if (rt == 0) first_rtl = digit;
+                                ++rt;
+                                if (q > best_rtq || (q == best_rtq && digit < best_rtl)) { best_rtq = q; best_rtl = digit; }
+                            } else if (an > 110.0 && ds < ncutoff) {
+                                const double q = (ncutoff - ds) + (an - 110.0) / 20.0;
+                                if (rn == 0) first_rnl = digit;
+                                ++rn;
+                                if (q > best_rnq || (q == best_rnq && digit < best_rnl)) { best_rnq = q; best_rnl = digit; }
+                            }
+                        }
+                    }
+                    // record the best phosphate interaction: sticky, evaluated after EVERY site (NA:1973-2003)
+                    if (n_true == 1) {
+                        bph = first_tl;
+                    } else if (n_keys > 1) {
+                        const unsigned o7 = (site_ox >> 28) & 0xF, o9 = (site_ox >> 36) & 0xF;
+                        const unsigned o3 = (site_ox >> 12) & 0xF, o5 = (site_ox >> 20) & 0xF;
+                        if (o7 && o9) { if (__popc(o7 | o9) > 1) bph = 8; }
+                        else if (o3 && o5) { if (__popc(o3 | o5) > 1) bph = 4; }
+                        if (bph < 0) bph = best_tl;
+                    } else if (n_true > 1) {
+                        bph = best_tl;
+                    } else if (n_near == 1) {
+                        bph = first_nl | 16;
+                    } else if (n_near > 1) {
+                        bph = best_nl | 16;
+                    }
+                    // best ribose interaction (NA:2005-2019)
+                    if (rt == 1) br = first_rtl;
+                    else if (rt > 1) br = best_rtl;
+                    else if (rn == 1) br = first_rnl | 16;
+                    else if (rn > 1) br = best_rnl | 16;
+                }
+            }
+            bph = __shfl_sync(FULL, bph, 0);
+            br = __shfl_sync(FULL, br, 0);
+            if (bph >= 0) { h_valid[FR3D_SLOT_BPH] = 1; h_code[FR3D_SLOT_BPH] = bph; }
+            if (br >= 0) { h_valid[FR3D_SLOT_BR] = 1; h_code[FR3D_SLOT_BR] = br; }
+        }
+
+        // ================= coplanar + basepair, orientation 12 then 21 (NA:834-1013) =================
+        const bool gly_ok = (bm1 & 1u) && (bm2 & 1u) && par1 >= 0 && par2 >= 0;   // NA:674, 834-837
+        if (gly_ok) {
+            const double *g1 = nts.base_xyz + (size_t)n1 * FR3D_BASE_SLOTS * 3;    // slot 0 = N9 / N1
+            const double *g2 = nts.base_xyz + (size_t)n2 * FR3D_BASE_SLOTS * 3;
+            const double gd0 = g2[0] - g1[0], gd1 = g2[1] - g1[1], gd2 = g2[2] - g1[2];
+            BpResult res[2];
+            bool marked_cp = false;
+#pragma unroll
+            for (int ori = 0; ori < 2; ++ori) {
+                res[ori].box = -1; res[ori].near = 0; res[ori].cd = 0.0;
+                const int pa = ori ? par2 : par1, pb = ori ? par1 : par2;
+                const int combo = pa * FR3D_N_PARENTS + pb;
+                if (!c_tab.combo_ok[combo]) continue;                              // NA:842 / 894
+                const Frame &fa = ori ? f2 : f1;
+                const Frame &fb = ori ? f1 : f2;
+                const double s = ori ? -1.0 : 1.0;
+                const double v0 = s * gd0, v1 = s * gd1, v2 = s * gd2;            // glycosidic_displacement
+                const double dX = v0 * fa.U[0] + v1 * fa.U[3] + v2 * fa.U[6];      // displ12 (NA:847)
+                const double dY = v0 * fa.U[1] + v1 * fa.U[4] + v2 * fa.U[7];
+                const double dZ = v0 * fa.U[2] + v1 * fa.U[5] + v2 * fa.U[8];
+
+                if (cats & FR3D_CAT_COPLANAR) {                                    // check_coplanar, NA:2051-2186
+                    if (!have_gaps) compute_gaps();
+                    const double gab = ori ? gap21 : gap12;
+                    bool cp = false;
+                    if (gab < 1.5179) {
+                        if (!have_mind) compute_mind();
+                        const bool both_std = (fl1 & FR3D_FLAG_STD_RNA) && (fl2 & FR3D_FLAG_STD_RNA);
+                        if (mind < 3.4589 && !(mind >= 2.4589 && both_std)) {
+                            double e0 = fa.c[0] - fb.c[0], e1 = fa.c[1] - fb.c[1], e2 = fa.c[2] - fb.c[2];
+                            const double en = sqrt(e0 * e0 + e1 * e1 + e2 * e2);
+                            e0 /= en; e1 /= en; e2 /= en;
+                            const double dot1 = fabs(e0 * fa.U[2] + e1 * fa.U[5] + e2 * fa.U[8]);
+                            if (dot1 < 0.3381) {
+                                const double dot2 = fabs(e0 * fb.U[2] + e1 * fb.U[5] + e2 * fb.U[8]);
+                                if (dot2 < 0.3381) {
+                                    const double dot3 = fabs(fa.U[2] * fb.U[2] + fa.U[5] * fb.U[5] + fa.U[8] * fb.U[8]);
+                                    if (dot3 > 0.7757) cp = true;
+                                }
+                            }
+                        }
+                    }
+                    if (cp && !marked_cp) { h_valid[FR3D_SLOT_CP] = 1; marked_cp = true; }
+                }
+
+                // ---- check_basepair_cutoffs, NA:2364-2759 (datapoint = None)
+                if (fabs(dZ) > 3.6) continue;                                      // NA:2380
+                const double nZ = fa.U[2] * fb.U[2] + fa.U[5] * fb.U[5] + fa.U[8] * fb.U[8];   // M[2][2]
+                const int sg = nZ > 0 ? 0 : 1;
+                const int bstart = box_index[(combo * 2 + sg) * 2 + 0];
+                const int bcount = box_index[(combo * 2 + sg) * 2 + 1];
+                if (bcount <= 0) continue;
+                const bool mine = lane < bcount;
+                double cd = 1e300;
+                fr3d_box_t bx;
+                if (mine) {
+                    bx = boxes[bstart + lane];
+                    cd = 0.0;
+                    cd += fmax(0.0, bx.xmin - dX);
+                    cd += fmax(0.0, dX - bx.xmax);
+                    cd += fmax(0.0, bx.ymin - dY);
+                    cd += fmax(0.0, dY - bx.ymax);
+                    if (bx.flags & 8) cd += fmax(0.0, sqrt(dX * dX + dY * dY) - bx.radiusmax);
+                    cd += fmax(0.0, bx.zmin - dZ);
+                    cd += fmax(0.0, dZ - bx.zmax);
+                    cd += 3.0 * fmax(0.0, bx.normalmin - nZ);
+                    cd += 3.0 * fmax(0.0, nZ - bx.normalmax);
+                }
+                bool ok = mine && cd < 1.0;                                        // NA:2580
+                if (!__any_sync(FULL, ok)) continue;                               // NA:2584
+                const double M11 = fa.U[1] * fb.U[1] + fa.U[4] * fb.U[4] + fa.U[7] * fb.U[7];
+                const double M01 = fa.U[0] * fb.U[1] + fa.U[3] * fb.U[4] + fa.U[6] * fb.U[7];
+                double ang = atan2(M11, M01) * 57.29577951308232 - 90.0;           // NA:2594
+                if (ang <= -90.0) ang += 360.0;
+                if (ok) {
+                    if (bx.anglemin < bx.anglemax) {
+                        cd += 0.05 * fmax(0.0, bx.anglemin - ang);
+                        cd += 0.05 * fmax(0.0, ang - bx.anglemax);
+                    } else {
+                        cd += 0.05 * fmin(fmax(0.0, bx.anglemin - ang), fmax(0.0, ang - bx.anglemax));
+                    }
+                    ok = cd < 1.0;                                                 // NA:2611
+                }
+                if (!__any_sync(FULL, ok)) continue;                               // NA:2615
+                if (!have_gaps) compute_gaps();
+                if (!have_mind) compute_mind();
+                const double gmax = fmax(gap12, gap21);
+                bool is_match = false, is_near = false;
+                if (ok) {
+                    if (bx.gapmax > 0.1) cd += 4.0 * fmax(0.0, gmax - bx.gapmax); // NA:2643-2645
+                    bool one_hb = false;                                           // NA:2648-2652
+                    if ((bx.flags & 2) && (pb == 1 || pb == 3)) one_hb = true;     // cSs with parent2 C or U
+                    else if ((bx.flags & 4) && pb == 3) one_hb = true;             // csS with parent2 U
+                    const bool starts_n = bx.flags & 1;
+                    if (cd > 0) {
+                        if (cd < 1.0 && !starts_n && (mind < 4.1 || one_hb)) is_near = true;
+                    } else if (starts_n) {
+                        is_near = true;
+                    } else if (mind > 3.75 && !one_hb) {
+                        is_near = true;
+                    } else {
+                        is_match = true;
+                    }
+                }
+                const unsigned match_b = __ballot_sync(FULL, is_match);
+                const unsigned near_b = __ballot_sync(FULL, is_near);
+                int sel = -1;
+                if (match_b) {                     // stable sort by (subcategory, len(name)), NA:2682
+                    double key = is_match ? (double)(bx.subcat * 64 + bx.name_len) : 1e300;
+                    int idx = lane;
+                    group_argmin<32>(key, idx);
+                    sel = idx;
+                } else if (near_b) {               // nearest near match, NA:2685-2686
+                    double key = is_near ? cd : 1e300;
+                    int idx = lane;
+                    group_argmin<32>(key, idx);
+                    sel = idx;
+                }
+                if (sel >= 0) {
+                    const double cds = __shfl_sync(FULL, cd, sel);
+                    const int fls = __shfl_sync(FULL, mine ? bx.flags : 0, sel);
+                    res[ori].box = bstart + sel;
+                    res[ori].cd = cds;
+                    res[ori].near = (cds > 0 && !(fls & 1)) ? 1 : 0;              // NA:2693-2696 ("n" in name <=> starts with n)
+                    // `"n" in interaction` tests below use the LW label: near prefix or an n-named box
+                    if (fls & 1) res[ori].near |= 2;
+                }
+            }
+            // ---- 12-vs-21 arbitration, NA:935-957
+            int use = -1;
+            if (res[0].box >= 0 && res[1].box >= 0) {
+                const fr3d_box_t &b0 = boxes[res[0].box];
+                const fr3d_box_t &b1 = boxes[res[1].box];
+                const bool n0 = res[0].near != 0, n1_ = res[1].near != 0;
+                // interaction12_reversed.lower() == interaction21.lower(): same "n" prefix state and same family
+                const bool same = ((res[0].near & 1) == (res[1].near & 1)) && (b0.rev_lower_id == b1.lower_id);
+                if (same) use = 0;
+                else if (n0 && n1_) use = (res[0].cd < res[1].cd) ? 0 : 1;
+                else if (n1_) use = 0;
+                else if (n0) use = 1;
+                else use = 0;
+            } else if (res[0].box >= 0) use = 0;
+            else if (res[1].box >= 0) use = 1;
+            if (use >= 0) {
+                h_valid[FR3D_SLOT_BP] = 1;
+                h_code[FR3D_SLOT_BP] = (res[use].near & 1) | (use << 1);
+                bp_box = res[use].box;
+                bp_cd = res[use].cd;
+                bp_gap = fmax(gap12, gap21);
+            }
+        }
+
+        // ================= emit: lane s owns hit slot s, ballot compaction =================
+        int myvalid = 0, mycode = 0;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) if (lane == k) { myvalid = h_valid[k]; mycode = h_code[k]; }
+        const unsigned hb = __ballot_sync(FULL, myvalid != 0);
+        if (hb) {
+            long long base = 0;
+            if (lane == 0) base = (long long)atomicAdd((unsigned long long *)&counters[1], (unsigned long long)__popc(hb));
+            base = __shfl_sync(FULL, base, 0);
+            if (myvalid) {
+                const long long pos = base + __popc(hb & ((1u << lane) - 1u));
+                if (pos < hit_cap) {
+                    const bool isbp = lane == FR3D_SLOT_BP;
+                    const double cdv = isbp ? bp_cd : 0.0, gv = isbp ? bp_gap : 0.0;
+                    const uint32_t w3 = (uint32_t)lane | ((uint32_t)mycode << 8) | ((uint32_t)(isbp ? bp_box : 0) << 16);
+                    uint4 *dst = reinterpret_cast<uint4 *>(hits + pos);
+                    dst[0] = make_uint4((uint32_t)n1, (uint32_t)n2, (uint32_t)rank, w3);
+                    dst[1] = make_uint4((uint32_t)__double2loint(cdv), (uint32_t)__double2hiint(cdv),
+                                        (uint32_t)__double2loint(gv), (uint32_t)__double2hiint(gv));
+                }
+            }
+        }
+    }
+}
+
+}  // namespace fr3d

@@ -1,0 +1,193 @@
+// libfr3d_b200.so — C ABI over the sm_100a kernels (see include/fr3d_b200.h).
+// Single translation unit: the kernels share one __constant__ table block.
+
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/fr3d_b200.h"
+#include "tables.cuh"
+#include "rotfit.cuh"
+#include "frames.cuh"
+#include "search.cuh"
+#include "classify.cuh"
+#include "geometry.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+bool g_tables_loaded = false;
+
+int fail(int code, const char *what, cudaError_t e = cudaSuccess) {
+    if (e != cudaSuccess) snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+    else snprintf(g_err, sizeof(g_err), "%s", what);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                 \
+    do {                                                               \
+        cudaError_t _e = (expr);                                       \
+        if (_e != cudaSuccess) return fail(FR3D_E_CUDA, #expr, _e);    \
+    } while (0)
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+uint32_t table_size_for(int32_t n_nt) {
+    uint32_t t = 64;
+    while (t < (uint32_t)n_nt * 2u) t <<= 1;
+    return t;
+}
+
+// carve the caller's workspace into the search arrays
+fr3d::SearchWs carve(void *workspace, int32_t n_nt) {
+    fr3d::SearchWs ws;
+    const uint32_t T = table_size_for(n_nt);
+    char *p = static_cast<char *>(workspace);
+    ws.keys = reinterpret_cast<unsigned long long *>(p); p += align_up(sizeof(unsigned long long) * T, 256);
+    ws.count = reinterpret_cast<int32_t *>(p); p += align_up(sizeof(int32_t) * T, 256);
+    ws.first = reinterpret_cast<int32_t *>(p); p += align_up(sizeof(int32_t) * T, 256);
+    ws.start = reinterpret_cast<int32_t *>(p); p += align_up(sizeof(int32_t) * T, 256);
+    ws.cursor = reinterpret_cast<int32_t *>(p); p += align_up(sizeof(int32_t) * T, 256);
+    ws.members = reinterpret_cast<int32_t *>(p); p += align_up(sizeof(int32_t) * (size_t)n_nt, 256);
+    ws.cell_slot = reinterpret_cast<int32_t *>(p); p += align_up(sizeof(int32_t) * (size_t)n_nt, 256);
+    ws.cell_xyz = reinterpret_cast<int32_t *>(p); p += align_up(sizeof(int32_t) * 3 * (size_t)n_nt, 256);
+    ws.table_mask = T - 1;
+    return ws;
+}
+
+int g_sm_count = 148;
+
+}  // namespace
+
+extern "C" {
+
+int fr3d_version(void) { return FR3D_ABI_VERSION; }
+
+const char *fr3d_last_error(void) { return g_err; }
+
+int fr3d_init(int device) {
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    g_sm_count = prop.multiProcessorCount;
+    if (prop.major < 10) return fail(FR3D_E_CUDA, "libfr3d_b200 is built for sm_100a only");
+    return FR3D_OK;
+}
+
+int fr3d_upload_tables(const fr3d_static_tables_t *host_tables) {
+    if (!host_tables) return fail(FR3D_E_ARG, "host_tables is NULL");
+    CUDA_TRY(cudaMemcpyToSymbol(fr3d::c_tab, host_tables, sizeof(fr3d_static_tables_t)));
+    g_tables_loaded = true;
+    return FR3D_OK;
+}
+
+int fr3d_frames_fit(const fr3d_nts_t *nts, int32_t *status, int place_h, void *stream) {
+    if (!nts) return fail(FR3D_E_ARG, "nts is NULL");
+    if (!g_tables_loaded) return fail(FR3D_E_NOTABLES, "fr3d_upload_tables not called");
+    if (nts->n_nt <= 0) return FR3D_OK;
+    const int block = 128;
+    const int grid = (nts->n_nt + block - 1) / block;
+    fr3d::frames_fit_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(*nts, status, place_h);
+    CUDA_TRY(cudaGetLastError());
+    return FR3D_OK;
+}
+
+size_t fr3d_pair_search_workspace(int32_t n_nt) {
+    if (n_nt < 0) n_nt = 0;
+    const uint32_t T = table_size_for(n_nt);
+    size_t b = 0;
+    b += align_up(sizeof(unsigned long long) * T, 256);
+    b += 4 * align_up(sizeof(int32_t) * T, 256);
+    b += 2 * align_up(sizeof(int32_t) * (size_t)n_nt, 256);
+    b += align_up(sizeof(int32_t) * 3 * (size_t)n_nt, 256);
+    return b + 256;
+}
+
+int fr3d_pair_search(const fr3d_nts_t *nts, double cell_size, void *workspace, size_t workspace_bytes,
+                     int32_t *pair_i, int32_t *pair_j, int32_t *pair_rank, int64_t pair_cap, int64_t *counters,
+                     void *stream) {
+    if (!nts || !workspace || !pair_i || !pair_j || !pair_rank || !counters) return fail(FR3D_E_ARG, "NULL argument");
+    if (!(cell_size > 0)) return fail(FR3D_E_ARG, "cell_size must be positive");
+    if (workspace_bytes < fr3d_pair_search_workspace(nts->n_nt)) return fail(FR3D_E_ARG, "workspace too small");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CUDA_TRY(cudaMemsetAsync(counters, 0, 4 * sizeof(int64_t), st));
+    if (nts->n_nt <= 0) return FR3D_OK;
+    fr3d::SearchWs ws = carve(workspace, nts->n_nt);
+    const uint32_t T = ws.table_mask + 1;
+    const int block = 256;
+    fr3d::search_reset_kernel<<<(T + block - 1) / block, block, 0, st>>>(ws);
+    fr3d::cell_assign_kernel<<<(nts->n_nt + block - 1) / block, block, 0, st>>>(*nts, ws, cell_size, counters);
+    fr3d::cell_offsets_kernel<<<(T + block - 1) / block, block, 0, st>>>(ws, counters);
+    fr3d::cell_fill_kernel<<<(nts->n_nt + block - 1) / block, block, 0, st>>>(*nts, ws);
+    const int wpb = 4;
+    fr3d::pair_search_kernel<<<(nts->n_nt + wpb - 1) / wpb, wpb * 32, 0, st>>>(*nts, ws, cell_size, pair_i, pair_j,
+                                                                               pair_rank, pair_cap, counters);
+    CUDA_TRY(cudaGetLastError());
+    return FR3D_OK;
+}
+
+int fr3d_classify_pairs(const fr3d_nts_t *nts, const fr3d_box_t *boxes, const int32_t *box_index,
+                        const int32_t *pair_i, const int32_t *pair_j, const int32_t *pair_rank, int64_t pair_cap,
+                        uint32_t category_mask, fr3d_hit_t *hits, int64_t hit_cap, int64_t *counters, void *stream) {
+    if (!nts || !boxes || !box_index || !pair_i || !pair_j || !pair_rank || !hits || !counters)
+        return fail(FR3D_E_ARG, "NULL argument");
+    if (!g_tables_loaded) return fail(FR3D_E_NOTABLES, "fr3d_upload_tables not called");
+    if (pair_cap <= 0) return FR3D_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // persistent warps: grid is a multiple of the SM count; n_pairs is read on the device
+    long long want = (pair_cap + fr3d::WARPS_PER_BLOCK - 1) / fr3d::WARPS_PER_BLOCK;
+    long long maxgrid = (long long)g_sm_count * 16;
+    int grid = (int)(want < maxgrid ? want : maxgrid);
+    if (grid < 1) grid = 1;
+    fr3d::classify_pairs_kernel<<<grid, fr3d::WARPS_PER_BLOCK * 32, 0, st>>>(
+        *nts, boxes, box_index, pair_i, pair_j, pair_rank, pair_cap, category_mask, hits, hit_cap, counters);
+    CUDA_TRY(cudaGetLastError());
+    return FR3D_OK;
+}
+
+int fr3d_kabsch_batched(const double *set1, const double *set2, const double *w, const int32_t *off, int32_t n_prob,
+                        double *U, double *mean1, double *mean2, double *rmsd, double *sse, double *new1,
+                        void *stream) {
+    if (!set1 || !set2 || !off) return fail(FR3D_E_ARG, "NULL argument");
+    if (n_prob <= 0) return FR3D_OK;
+    const int block = 128;
+    fr3d::kabsch_batched_kernel<<<(n_prob + block - 1) / block, block, 0, static_cast<cudaStream_t>(stream)>>>(
+        set1, set2, w, off, n_prob, U, mean1, mean2, rmsd, sse, new1);
+    CUDA_TRY(cudaGetLastError());
+    return FR3D_OK;
+}
+
+int fr3d_discrepancy_all_vs_all(const double *centers, const double *rots, const uint8_t *has_rot, int32_t N,
+                                int32_t n, double angle_weight, int32_t row0, int32_t row1, double *out,
+                                void *stream) {
+    if (!centers || !rots || !out) return fail(FR3D_E_ARG, "NULL argument");
+    if (n < 2 || n > fr3d::DISC_MAXN) return fail(FR3D_E_ARG, "n must be in [2, 16]");
+    if (row0 < 0 || row1 > N || row0 > row1) return fail(FR3D_E_ARG, "bad row range");
+    if (row0 == row1 || N == 0) return FR3D_OK;
+    const size_t smem = (size_t)fr3d::DISC_TILE * (size_t)n * 12 * 2 * sizeof(double) + 2 * fr3d::DISC_TILE * fr3d::DISC_MAXN;
+    CUDA_TRY(cudaFuncSetAttribute(fr3d::discrepancy_all_vs_all_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+    dim3 block(32, 8);
+    dim3 grid((N + fr3d::DISC_TILE - 1) / fr3d::DISC_TILE, (row1 - row0 + fr3d::DISC_TILE - 1) / fr3d::DISC_TILE);
+    fr3d::discrepancy_all_vs_all_kernel<<<grid, block, smem, static_cast<cudaStream_t>(stream)>>>(
+        centers, rots, has_rot, N, n, angle_weight, row0, row1, out);
+    CUDA_TRY(cudaGetLastError());
+    return FR3D_OK;
+}
+
+int fr3d_discrepancy_one_vs_many(const double *q_centers, const double *q_rots, const uint8_t *q_has_rot,
+                                 const double *centers, const double *rots, const uint8_t *has_rot, int32_t M,
+                                 int32_t n, double cutoff, double angle_weight, const double *center_weight,
+                                 double *out, void *stream) {
+    if (!q_centers || !q_rots || !centers || !rots || !out) return fail(FR3D_E_ARG, "NULL argument");
+    if (n < 2 || n > fr3d::DISC_MAXN) return fail(FR3D_E_ARG, "n must be in [2, 16]");
+    if (M <= 0) return FR3D_OK;
+    const int block = 128;
+    fr3d::discrepancy_one_vs_many_kernel<<<(M + block - 1) / block, block, 0, static_cast<cudaStream_t>(stream)>>>(
+        q_centers, q_rots, q_has_rot, centers, rots, has_rot, M, n, cutoff, angle_weight, center_weight, out);
+    CUDA_TRY(cudaGetLastError());
+    return FR3D_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,105 @@
+// K1: per-nucleotide base frames + hydrogen placement, one thread per nt.
+//
+// Replaces Component.calculate_rotation_matrix (fr3d/data/components.py:273-349)
+// -> besttransformation (fr3d/geometry/superpositions.py:10-89) and the
+// arithmetic of infer_NA_hydrogens (components.py:452-462).
+//
+// Work per nt is tiny (<= 11 atoms): the kernel is latency bound; one thread
+// per nt keeps the 4x4 Jacobi in registers and the loads of the nt's
+// contiguous 16x3 slot block sequential per thread.
+#pragma once
+
+#include "rotfit.cuh"
+#include "tables.cuh"
+
+namespace fr3d {
+
+__global__ void __launch_bounds__(128) frames_fit_kernel(fr3d_nts_t nts, int32_t *__restrict__ status, int place_h) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= nts.n_nt) return;
+    const int parent = nts.meta[n * FR3D_META_INTS + 0];
+    const int flags = nts.meta[n * FR3D_META_INTS + 1];
+    uint32_t mask = nts.base_mask[n] & 0xFFFFu;
+    if (parent < 0 || parent >= FR3D_N_PARENTS) {
+        nts.base_mask[n] = mask;
+        if (status) status[n] = -1;
+        return;
+    }
+    const int nh = c_tab.n_heavy[parent];
+    const int ns = c_tab.n_slots[parent];
+    double *xyz = nts.base_xyz + (size_t)n * FR3D_BASE_SLOTS * 3;
+
+    // means over the observed heavy atoms (superpositions.py:40-41)
+    double mr[3] = {0, 0, 0}, ms[3] = {0, 0, 0};
+    int cnt = 0;
+    for (int k = 0; k < nh; ++k) {
+        if (mask >> k & 1u) {
+            mr[0] += xyz[k * 3 + 0]; mr[1] += xyz[k * 3 + 1]; mr[2] += xyz[k * 3 + 2];
+            ms[0] += c_tab.std_xyz[parent][k][0]; ms[1] += c_tab.std_xyz[parent][k][1];
+            ms[2] += c_tab.std_xyz[parent][k][2];
+            ++cnt;
+        }
+    }
+    if (cnt < 3) {
+        // fewer than three base atoms: LAPACK's null-space choice is not reproducible
+        // (SURVEY §7 hard part 5); the nt is left without a frame, like a failed fit
+        // (components.py:324-337), and drops out of the cubes (NA:390,426).
+        nts.base_mask[n] = mask;
+        if (status) status[n] = -2;
+        return;
+    }
+    const double inv = 1.0 / (double)cnt;
+    mr[0] *= inv; mr[1] *= inv; mr[2] *= inv;
+    ms[0] *= inv; ms[1] *= inv; ms[2] *= inv;
+
+    // M[i][j] = sum_k dev1_k[i] * dev2_k[j]  (= A^T of superpositions.py:53)
+    double M[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    for (int k = 0; k < nh; ++k) {
+        if (mask >> k & 1u) {
+            const double a0 = xyz[k * 3 + 0] - mr[0], a1 = xyz[k * 3 + 1] - mr[1], a2 = xyz[k * 3 + 2] - mr[2];
+            const double b0 = c_tab.std_xyz[parent][k][0] - ms[0], b1 = c_tab.std_xyz[parent][k][1] - ms[1],
+                         b2 = c_tab.std_xyz[parent][k][2] - ms[2];
+            M[0][0] += a0 * b0; M[0][1] += a0 * b1; M[0][2] += a0 * b2;
+            M[1][0] += a1 * b0; M[1][1] += a1 * b1; M[1][2] += a1 * b2;
+            M[2][0] += a2 * b0; M[2][1] += a2 * b1; M[2][2] += a2 * b2;
+        }
+    }
+    double Q[3][3];
+    horn_rotation(M, Q);
+    // dev1 . U ~ dev2 with row vectors  <=>  U = Q^T
+    double U[3][3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) U[r][c] = Q[c][r];
+
+    double ctr[3] = {mr[0], mr[1], mr[2]};
+    if (flags & FR3D_FLAG_MODIFIED) {   // components.py:348-349
+#pragma unroll
+        for (int r = 0; r < 3; ++r) ctr[r] = mr[r] - (U[r][0] * ms[0] + U[r][1] * ms[1] + U[r][2] * ms[2]);
+    }
+    double *co = nts.center + (size_t)n * 3;
+    co[0] = ctr[0]; co[1] = ctr[1]; co[2] = ctr[2];
+    double *ro = nts.rot + (size_t)n * 9;
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) ro[r * 3 + c] = U[r][c];
+
+    if (place_h) {   // components.py:452-462: centre + U . h_std for every missing base hydrogen
+        for (int k = nh; k < ns; ++k) {
+            if (!(mask >> k & 1u)) {
+                const double h0 = c_tab.std_xyz[parent][k][0], h1 = c_tab.std_xyz[parent][k][1],
+                             h2 = c_tab.std_xyz[parent][k][2];
+                xyz[k * 3 + 0] = ctr[0] + (U[0][0] * h0 + U[0][1] * h1 + U[0][2] * h2);
+                xyz[k * 3 + 1] = ctr[1] + (U[1][0] * h0 + U[1][1] * h1 + U[1][2] * h2);
+                xyz[k * 3 + 2] = ctr[2] + (U[2][0] * h0 + U[2][1] * h1 + U[2][2] * h2);
+                mask |= 1u << k;
+            }
+        }
+    }
+    nts.base_mask[n] = mask | FR3D_MASK_HAS_FRAME;
+    if (status) status[n] = 0;
+}
+
+}  // namespace fr3d

@@ -1,0 +1,272 @@
+// K5 batched Kabsch superposition and K6 all-vs-all / one-vs-many geometric discrepancy.
+//
+// Replaces besttransformation(_weighted) (fr3d/geometry/superpositions.py:10-121),
+// matrix_discrepancy / matrix_discrepancy_cutoff (fr3d/geometry/discrepancy.py:165-313;
+// same arithmetic as fr3d/search/discrepancy.py:165-313 with default weights) and
+// angle_of_rotation (fr3d/geometry/angleofrotation.py:4-7).
+//
+// K6 is FP64-pipe bound: one thread per (i, j) instance pair, a 32 x 32 tile of
+// pairs per CTA with the 64 instances' centred coordinates and rotations staged
+// in shared memory (each is reused 32 times).  Flops per pair ~ 154 n + Jacobi.
+#pragma once
+
+#include "rotfit.cuh"
+
+namespace fr3d {
+
+// ---------------------------------------------------------------- K5 -------
+__global__ void __launch_bounds__(128)
+kabsch_batched_kernel(const double *__restrict__ set1, const double *__restrict__ set2, const double *__restrict__ w,
+                      const int32_t *__restrict__ off, int n_prob, double *__restrict__ Uo, double *__restrict__ mean1o,
+                      double *__restrict__ mean2o, double *__restrict__ rmsdo, double *__restrict__ sseo,
+                      double *__restrict__ new1o) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_prob) return;
+    const int r0 = off[p], r1 = off[p + 1];
+    const int len = r1 - r0;
+    double m1[3] = {0, 0, 0}, m2[3] = {0, 0, 0};
+    for (int k = r0; k < r1; ++k) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { m1[c] += set1[(size_t)k * 3 + c]; m2[c] += set2[(size_t)k * 3 + c]; }
+    }
+    const double L = (double)len;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { m1[c] /= L; m2[c] /= L; }
+    // M = dev1^T diag(w) dev2   (= A^T of superpositions.py:53 / :109)
+    double M[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    for (int k = r0; k < r1; ++k) {
+        const double wk = w ? w[k] : 1.0;
+        const double a0 = set1[(size_t)k * 3 + 0] - m1[0], a1 = set1[(size_t)k * 3 + 1] - m1[1],
+                     a2 = set1[(size_t)k * 3 + 2] - m1[2];
+        const double b0 = (set2[(size_t)k * 3 + 0] - m2[0]) * wk, b1 = (set2[(size_t)k * 3 + 1] - m2[1]) * wk,
+                     b2 = (set2[(size_t)k * 3 + 2] - m2[2]) * wk;
+        M[0][0] += a0 * b0; M[0][1] += a0 * b1; M[0][2] += a0 * b2;
+        M[1][0] += a1 * b0; M[1][1] += a1 * b1; M[1][2] += a1 * b2;
+        M[2][0] += a2 * b0; M[2][1] += a2 * b1; M[2][2] += a2 * b2;
+    }
+    double Q[3][3];
+    horn_rotation(M, Q);
+    // U = Q^T (row-vector convention: new1 = dev1 . U)
+    double sse = 0.0;
+    for (int k = r0; k < r1; ++k) {
+        const double a0 = set1[(size_t)k * 3 + 0] - m1[0], a1 = set1[(size_t)k * 3 + 1] - m1[1],
+                     a2 = set1[(size_t)k * 3 + 2] - m1[2];
+        const double n0 = a0 * Q[0][0] + a1 * Q[0][1] + a2 * Q[0][2];
+        const double n1 = a0 * Q[1][0] + a1 * Q[1][1] + a2 * Q[1][2];
+        const double n2 = a0 * Q[2][0] + a1 * Q[2][1] + a2 * Q[2][2];
+        if (new1o) { new1o[(size_t)k * 3 + 0] = n0; new1o[(size_t)k * 3 + 1] = n1; new1o[(size_t)k * 3 + 2] = n2; }
+        const double e0 = n0 - (set2[(size_t)k * 3 + 0] - m2[0]), e1 = n1 - (set2[(size_t)k * 3 + 1] - m2[1]),
+                     e2 = n2 - (set2[(size_t)k * 3 + 2] - m2[2]);
+        sse += e0 * e0 + e1 * e1 + e2 * e2;               // unweighted, RMSD.py:27
+    }
+    if (Uo) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) Uo[(size_t)p * 9 + r * 3 + c] = Q[c][r];
+    }
+    if (mean1o) { mean1o[(size_t)p * 3 + 0] = m1[0]; mean1o[(size_t)p * 3 + 1] = m1[1]; mean1o[(size_t)p * 3 + 2] = m1[2]; }
+    if (mean2o) { mean2o[(size_t)p * 3 + 0] = m2[0]; mean2o[(size_t)p * 3 + 1] = m2[1]; mean2o[(size_t)p * 3 + 2] = m2[2]; }
+    if (sseo) sseo[p] = sse;
+    if (rmsdo) rmsdo[p] = sqrt(sse / L);                    // RMSD.py:15
+}
+
+// ---------------------------------------------------------------- K6 -------
+// Discrepancy of instance A (centred coords ca[n][3], rotations ra[n][9]) and B, n > 2
+// (discrepancy.py:192-204).  `cutoff2 >= 0` enables the early exit of
+// matrix_discrepancy_cutoff (discrepancy.py:263-281) -> NaN.
+template <int MAXN>
+__device__ __forceinline__ double discrepancy_pair(const double *ca, const double *ra, const uint8_t *ha,
+                                                   const double *cb, const double *rb, const uint8_t *hb, int n,
+                                                   double angle_weight, const double *cw, double cutoff2) {
+    // A = dev2^T diag(w) dev1 with set1 = A's centres, set2 = B's; M = A^T
+    double M[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    for (int k = 0; k < n; ++k) {
+        const double wk = cw ? cw[k] : 1.0;
+        const double a0 = ca[k * 3 + 0], a1 = ca[k * 3 + 1], a2 = ca[k * 3 + 2];
+        const double b0 = cb[k * 3 + 0] * wk, b1 = cb[k * 3 + 1] * wk, b2 = cb[k * 3 + 2] * wk;
+        M[0][0] += a0 * b0; M[0][1] += a0 * b1; M[0][2] += a0 * b2;
+        M[1][0] += a1 * b0; M[1][1] += a1 * b1; M[1][2] += a1 * b2;
+        M[2][0] += a2 * b0; M[2][1] += a2 * b1; M[2][2] += a2 * b2;
+    }
+    double Q[3][3];
+    horn_rotation(M, Q);          // U = Q^T
+    double sse = 0.0;
+    for (int k = 0; k < n; ++k) {
+        const double a0 = ca[k * 3 + 0], a1 = ca[k * 3 + 1], a2 = ca[k * 3 + 2];
+        const double e0 = a0 * Q[0][0] + a1 * Q[0][1] + a2 * Q[0][2] - cb[k * 3 + 0];
+        const double e1 = a0 * Q[1][0] + a1 * Q[1][1] + a2 * Q[1][2] - cb[k * 3 + 1];
+        const double e2 = a0 * Q[2][0] + a1 * Q[2][1] + a2 * Q[2][2] - cb[k * 3 + 2];
+        sse += e0 * e0 + e1 * e1 + e2 * e2;
+    }
+    double total = sse;
+    if (cutoff2 >= 0 && total > cutoff2) return nan("");
+    double orient = 0.0;
+    for (int k = 0; k < n; ++k) {
+        if ((ha == nullptr || ha[k]) && (hb == nullptr || hb[k])) {
+            // trace(U . r2 . r1^T) with r1 = A's rotation, r2 = B's:  sum_ij (U r2)_ij r1_ij, U = Q^T
+            const double *r1 = ra + k * 9, *r2 = rb + k * 9;
+            double tr = 0.0;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const double ur2 = Q[0][i] * r2[0 * 3 + j] + Q[1][i] * r2[1 * 3 + j] + Q[2][i] * r2[2 * 3 + j];
+                    tr += ur2 * r1[i * 3 + j];
+                }
+            }
+            const double ang = angle_from_trace(tr);
+            if (cutoff2 >= 0) {
+                total += ang * ang;
+                if (total > cutoff2) return nan("");
+            } else {
+                orient += ang * ang;
+            }
+        }
+    }
+    if (cutoff2 >= 0) return sqrt(total) / (double)n;
+    return sqrt(sse + angle_weight * orient) / (double)n;
+}
+
+// n == 2 closed form (discrepancy.py:206-231).  ca/cb are RAW centres here.
+__device__ __forceinline__ double discrepancy_pair2(const double *c1, const double *r1, const double *c2,
+                                                    const double *r2, double angle_weight) {
+    // R1 = r1[1]^T r1[0];  R2 = r2[0]^T r2[1]
+    double R1[9], R2[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            R1[i * 3 + j] = r1[9 + 0 * 3 + i] * r1[0 * 3 + j] + r1[9 + 1 * 3 + i] * r1[1 * 3 + j] + r1[9 + 2 * 3 + i] * r1[2 * 3 + j];
+            R2[i * 3 + j] = r2[0 * 3 + i] * r2[9 + 0 * 3 + j] + r2[1 * 3 + i] * r2[9 + 1 * 3 + j] + r2[2 * 3 + i] * r2[9 + 2 * 3 + j];
+        }
+    // ang1 = angle(R1 R2): trace = sum_ij R1_ij R2_ji ; ang2 = angle(R1^T R2^T): trace = sum_ij R1_ji R2_ij (same)
+    double tr = 0.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) tr += R1[i * 3 + j] * R2[j * 3 + i];
+    const double ang1 = angle_from_trace(tr);
+    const double ang2 = ang1;
+    double D1[3], D2[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        double T1 = 0, T2 = 0, S1 = 0, S2 = 0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            T1 += (c1[3 + k] - c1[k]) * r1[k * 3 + j];
+            T2 += (c1[k] - c1[3 + k]) * r1[9 + k * 3 + j];
+            S1 += (c2[3 + k] - c2[k]) * r2[k * 3 + j];
+            S2 += (c2[k] - c2[3 + k]) * r2[9 + k * 3 + j];
+        }
+        D1[j] = T1 - S1;
+        D2[j] = T2 - S2;
+    }
+    double d = sqrt(D1[0] * D1[0] + D1[1] * D1[1] + D1[2] * D1[2] + (angle_weight * ang1) * (angle_weight * ang1));
+    d += sqrt(D2[0] * D2[0] + D2[1] * D2[1] + D2[2] * D2[2] + (angle_weight * ang2) * (angle_weight * ang2));
+    return d * 0.17677669529663687;
+}
+
+static constexpr int DISC_TILE = 32;
+static constexpr int DISC_MAXN = 16;      // positions per instance supported by the tiled kernel
+
+// grid: (ceil(N/32), ceil(rows/32)); block 32x8 threads, each thread 4 rows of the tile.
+__global__ void __launch_bounds__(256)
+discrepancy_all_vs_all_kernel(const double *__restrict__ centers, const double *__restrict__ rots,
+                              const uint8_t *__restrict__ has_rot, int N, int n, double angle_weight, int row0,
+                              int row1, double *__restrict__ out) {
+    extern __shared__ double smem[];
+    // layout: rowc[32][n*3] rowr[32][n*9] colc[32][n*3] colr[32][n*9] + flags
+    const int cs = n * 3, rs = n * 9;
+    double *rowc = smem;
+    double *rowr = rowc + DISC_TILE * cs;
+    double *colc = rowr + DISC_TILE * rs;
+    double *colr = colc + DISC_TILE * cs;
+    uint8_t *rowh = reinterpret_cast<uint8_t *>(colr + DISC_TILE * rs);
+    uint8_t *colh = rowh + DISC_TILE * DISC_MAXN;
+
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    const int rbase = row0 + blockIdx.y * DISC_TILE;
+    const int cbase = blockIdx.x * DISC_TILE;
+
+    // stage: raw centres, rotations (coalesced: consecutive threads read consecutive doubles)
+    for (int e = tid; e < DISC_TILE * cs; e += 256) {
+        const int t = e / cs, r = rbase + t, c = cbase + t;
+        rowc[e] = (r < row1) ? centers[(size_t)r * cs + (e - t * cs)] : 0.0;
+        colc[e] = (c < N) ? centers[(size_t)c * cs + (e - t * cs)] : 0.0;
+    }
+    for (int e = tid; e < DISC_TILE * rs; e += 256) {
+        const int t = e / rs, r = rbase + t, c = cbase + t;
+        rowr[e] = (r < row1) ? rots[(size_t)r * rs + (e - t * rs)] : 0.0;
+        colr[e] = (c < N) ? rots[(size_t)c * rs + (e - t * rs)] : 0.0;
+    }
+    for (int e = tid; e < DISC_TILE * n; e += 256) {
+        const int t = e / n, k = e - t * n, r = rbase + t, c = cbase + t;
+        rowh[t * DISC_MAXN + k] = (has_rot && r < row1) ? has_rot[(size_t)r * n + k] : 1;
+        colh[t * DISC_MAXN + k] = (has_rot && c < N) ? has_rot[(size_t)c * n + k] : 1;
+    }
+    __syncthreads();
+    if (n > 2) {
+        // centre each staged instance in place (superpositions.py:105-108); one thread per instance
+        if (tid < 2 * DISC_TILE) {
+            double *cc = (tid < DISC_TILE) ? rowc + tid * cs : colc + (tid - DISC_TILE) * cs;
+            double m0 = 0, m1 = 0, m2 = 0;
+            for (int k = 0; k < n; ++k) { m0 += cc[k * 3]; m1 += cc[k * 3 + 1]; m2 += cc[k * 3 + 2]; }
+            const double L = (double)n;
+            m0 /= L; m1 /= L; m2 /= L;
+            for (int k = 0; k < n; ++k) { cc[k * 3] -= m0; cc[k * 3 + 1] -= m1; cc[k * 3 + 2] -= m2; }
+        }
+        __syncthreads();
+    }
+    const int c = cbase + threadIdx.x;
+#pragma unroll 1
+    for (int rr = threadIdx.y; rr < DISC_TILE; rr += 8) {
+        const int r = rbase + rr;
+        if (r >= row1 || c >= N) continue;
+        double d = 0.0;
+        if (r != c) {
+            // the reference computes (i, j) with i < j and mirrors it (FR3D.py:433-442): keep that
+            // argument order so both triangles hold the same bits
+            const bool swap = r > c;
+            const double *ca = swap ? colc + threadIdx.x * cs : rowc + rr * cs;
+            const double *ra = swap ? colr + threadIdx.x * rs : rowr + rr * rs;
+            const uint8_t *ha = swap ? colh + threadIdx.x * DISC_MAXN : rowh + rr * DISC_MAXN;
+            const double *cb = swap ? rowc + rr * cs : colc + threadIdx.x * cs;
+            const double *rb = swap ? rowr + rr * rs : colr + threadIdx.x * rs;
+            const uint8_t *hb = swap ? rowh + rr * DISC_MAXN : colh + threadIdx.x * DISC_MAXN;
+            if (n > 2) d = discrepancy_pair<DISC_MAXN>(ca, ra, ha, cb, rb, hb, n, angle_weight, nullptr, -1.0);
+            else d = discrepancy_pair2(ca, ra, cb, rb, angle_weight);
+        }
+        out[(size_t)(r - row0) * N + c] = d;
+    }
+}
+
+// one query against M candidates, one thread per candidate (search.py:1073-1085)
+__global__ void __launch_bounds__(128)
+discrepancy_one_vs_many_kernel(const double *__restrict__ qc, const double *__restrict__ qr,
+                               const uint8_t *__restrict__ qh, const double *__restrict__ centers,
+                               const double *__restrict__ rots, const uint8_t *__restrict__ has_rot, int M, int n,
+                               double cutoff, double angle_weight, const double *__restrict__ cw,
+                               double *__restrict__ out) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= M) return;
+    const double *cb_raw = centers + (size_t)m * n * 3;
+    const double *rb = rots + (size_t)m * n * 9;
+    const uint8_t *hb = has_rot ? has_rot + (size_t)m * n : nullptr;
+    if (n == 2) {
+        out[m] = discrepancy_pair2(qc, qr, cb_raw, rb, angle_weight);
+        return;
+    }
+    double ca[DISC_MAXN * 3], cb[DISC_MAXN * 3];
+    double ma[3] = {0, 0, 0}, mb[3] = {0, 0, 0};
+    for (int k = 0; k < n; ++k)
+        for (int c = 0; c < 3; ++c) { ma[c] += qc[k * 3 + c]; mb[c] += cb_raw[k * 3 + c]; }
+    const double L = (double)n;
+    for (int c = 0; c < 3; ++c) { ma[c] /= L; mb[c] /= L; }
+    for (int k = 0; k < n; ++k)
+        for (int c = 0; c < 3; ++c) { ca[k * 3 + c] = qc[k * 3 + c] - ma[c]; cb[k * 3 + c] = cb_raw[k * 3 + c] - mb[c]; }
+    const double cutoff2 = (cutoff >= 0) ? ((double)n * cutoff) * ((double)n * cutoff) : -1.0;
+    out[m] = discrepancy_pair<DISC_MAXN>(ca, qr, qh, cb, rb, hb, n, angle_weight, cw, cutoff2);
+}
+
+}  // namespace fr3d

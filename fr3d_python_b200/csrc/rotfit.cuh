@@ -1,0 +1,115 @@
+// Small fp64 device helpers shared by the frame-fit, Kabsch and discrepancy kernels.
+//
+// The reference finds the optimal proper rotation with LAPACK's SVD plus a
+// reflection fix (fr3d/geometry/superpositions.py:53-78).  On the device the
+// same optimum is obtained from Horn's quaternion form: the rotation is the
+// eigenvector of the largest eigenvalue of a symmetric 4x4 matrix built from
+// the 3x3 covariance, found here by cyclic Jacobi sweeps kept entirely in
+// registers.  It is always a proper rotation, so the reference's det test is
+// implicit, and it agrees with the SVD route to ~1e-15 whenever the optimum is
+// unique (the reference is itself arbitrary when it is not).
+#pragma once
+
+#include <math.h>
+
+namespace fr3d {
+
+// One Jacobi rotation on the symmetric 4x4 matrix a (full storage) and the
+// accumulated eigenvector matrix v, zeroing a[P][Q].
+template <int P, int Q>
+__device__ __forceinline__ void jacobi_rotate(double (&a)[4][4], double (&v)[4][4]) {
+    const double apq = a[P][Q];
+    if (apq == 0.0) return;
+    const double app = a[P][P], aqq = a[Q][Q];
+    const double theta = (aqq - app) / (2.0 * apq);
+    // t = sgn(theta) / (|theta| + sqrt(theta^2 + 1)), stable for large theta
+    const double t = copysign(1.0, theta) / (fabs(theta) + sqrt(fma(theta, theta, 1.0)));
+    const double c = rsqrt(fma(t, t, 1.0));
+    const double s = t * c;
+    const double tau = s / (1.0 + c);
+    a[P][P] = app - t * apq;
+    a[Q][Q] = aqq + t * apq;
+    a[P][Q] = 0.0;
+    a[Q][P] = 0.0;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        if (r != P && r != Q) {
+            const double arp = a[r][P], arq = a[r][Q];
+            const double np_ = arp - s * (arq + tau * arp);
+            const double nq_ = arq + s * (arp - tau * arq);
+            a[r][P] = np_; a[P][r] = np_;
+            a[r][Q] = nq_; a[Q][r] = nq_;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const double vrp = v[r][P], vrq = v[r][Q];
+        v[r][P] = vrp - s * (vrq + tau * vrp);
+        v[r][Q] = vrq + s * (vrp - tau * vrq);
+    }
+}
+
+// Proper rotation Q (row major 3x3) maximising sum_k b_k . (Q a_k), where
+// M[i][j] = sum_k a_k[i] * b_k[j].
+__device__ __forceinline__ void horn_rotation(const double (&M)[3][3], double (&Qm)[3][3]) {
+    double a[4][4], v[4][4];
+    const double Sxx = M[0][0], Sxy = M[0][1], Sxz = M[0][2];
+    const double Syx = M[1][0], Syy = M[1][1], Syz = M[1][2];
+    const double Szx = M[2][0], Szy = M[2][1], Szz = M[2][2];
+    a[0][0] = Sxx + Syy + Szz;
+    a[0][1] = Syz - Szy; a[0][2] = Szx - Sxz; a[0][3] = Sxy - Syx;
+    a[1][1] = Sxx - Syy - Szz; a[1][2] = Sxy + Syx; a[1][3] = Szx + Sxz;
+    a[2][2] = -Sxx + Syy - Szz; a[2][3] = Syz + Szy;
+    a[3][3] = -Sxx - Syy + Szz;
+    a[1][0] = a[0][1]; a[2][0] = a[0][2]; a[3][0] = a[0][3];
+    a[2][1] = a[1][2]; a[3][1] = a[1][3]; a[3][2] = a[2][3];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) v[r][c] = (r == c) ? 1.0 : 0.0;
+
+    // Cyclic sweeps; quadratic convergence makes 4x4 reach fp64 round-off in <= 6.
+    for (int sweep = 0; sweep < 10; ++sweep) {
+        const double off = fabs(a[0][1]) + fabs(a[0][2]) + fabs(a[0][3]) + fabs(a[1][2]) + fabs(a[1][3]) +
+                           fabs(a[2][3]);
+        const double diag = fabs(a[0][0]) + fabs(a[1][1]) + fabs(a[2][2]) + fabs(a[3][3]);
+        if (off <= 1e-18 * diag || off == 0.0) break;
+        jacobi_rotate<0, 1>(a, v);
+        jacobi_rotate<0, 2>(a, v);
+        jacobi_rotate<0, 3>(a, v);
+        jacobi_rotate<1, 2>(a, v);
+        jacobi_rotate<1, 3>(a, v);
+        jacobi_rotate<2, 3>(a, v);
+    }
+    // largest eigenvalue
+    int best = 0;
+    double lam = a[0][0];
+    if (a[1][1] > lam) { lam = a[1][1]; best = 1; }
+    if (a[2][2] > lam) { lam = a[2][2]; best = 2; }
+    if (a[3][3] > lam) { lam = a[3][3]; best = 3; }
+    double q0, q1, q2, q3;
+    if (best == 0)      { q0 = v[0][0]; q1 = v[1][0]; q2 = v[2][0]; q3 = v[3][0]; }
+    else if (best == 1) { q0 = v[0][1]; q1 = v[1][1]; q2 = v[2][1]; q3 = v[3][1]; }
+    else if (best == 2) { q0 = v[0][2]; q1 = v[1][2]; q2 = v[2][2]; q3 = v[3][2]; }
+    else                { q0 = v[0][3]; q1 = v[1][3]; q2 = v[2][3]; q3 = v[3][3]; }
+    const double nrm = rsqrt(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3);
+    q0 *= nrm; q1 *= nrm; q2 *= nrm; q3 *= nrm;
+    Qm[0][0] = q0 * q0 + q1 * q1 - q2 * q2 - q3 * q3;
+    Qm[0][1] = 2.0 * (q1 * q2 - q0 * q3);
+    Qm[0][2] = 2.0 * (q1 * q3 + q0 * q2);
+    Qm[1][0] = 2.0 * (q1 * q2 + q0 * q3);
+    Qm[1][1] = q0 * q0 - q1 * q1 + q2 * q2 - q3 * q3;
+    Qm[1][2] = 2.0 * (q2 * q3 - q0 * q1);
+    Qm[2][0] = 2.0 * (q1 * q3 - q0 * q2);
+    Qm[2][1] = 2.0 * (q2 * q3 + q0 * q1);
+    Qm[2][2] = q0 * q0 - q1 * q1 - q2 * q2 + q3 * q3;
+}
+
+// angle_of_rotation (fr3d/geometry/angleofrotation.py:4-7) given the trace.
+__device__ __forceinline__ double angle_from_trace(double tr) {
+    double value = (tr - 1.0) / 2.0;
+    value = fmin(1.0, fmax(-1.0, value));
+    return acos(value);
+}
+
+}  // namespace fr3d

@@ -1,0 +1,244 @@
+"""Device side of the annotator: owns torch buffers, calls the C ABI (K1-K4).
+
+PyTorch is used only for device memory, pinned host memory and streams.
+Everything fails loudly when CUDA or the extension is unavailable — there is
+no CPU path in this package.
+"""
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from . import definitions as defs
+
+HIT_DTYPE = np.dtype([('i', '<i4'), ('j', '<i4'), ('rank', '<i4'), ('slot', 'u1'), ('code', 'u1'),
+                      ('box', '<u2'), ('cutoff_distance', '<f8'), ('max_gap', '<f8')])
+BOX_DTYPE = np.dtype([('lim', '<f8', (12,)), ('name_id', '<i4'), ('lower_id', '<i4'), ('rev_lower_id', '<i4'),
+                      ('subcat', '<i4'), ('name_len', '<i4'), ('flags', '<i4'), ('pad', '<i4', (2,))])
+assert HIT_DTYPE.itemsize == 32 and BOX_DTYPE.itemsize == 128
+
+_LIM_KEYS = ['xmin', 'xmax', 'ymin', 'ymax', 'zmin', 'zmax', 'normalmin', 'normalmax', 'anglemin', 'anglemax',
+             'gapmax', 'radiusmax']
+
+
+def reverse_edges(inter):
+    """NA_pairwise_interactions.py:446-465."""
+    if len(inter) <= 2 or inter == 'N/A':
+        return inter
+    if len(inter) == 3:
+        return inter[0] + inter[2] + inter[1]
+    if len(inter) == 4 and inter[0] in 'n!':
+        return inter[0] + inter[1] + inter[3] + inter[2]
+    if len(inter) == 4:
+        return inter[0] + inter[2] + inter[1] + inter[3]
+    if len(inter) == 5:
+        return inter[0] + inter[1] + inter[3] + inter[2] + inter[4]
+    return inter[0:(len(inter) - 2)] + inter[len(inter) - 1] + inter[len(inter) - 2]
+
+
+class BoxTable(object):
+    """Flattened focused_basepair_cutoffs: {combo: {+1/-1: {interaction: {subcategory: limits}}}}
+    (the output of focus_basepair_cutoffs, NA:88-136) in iteration order."""
+
+    def __init__(self, focused):
+        rows = []
+        self.names = []          # name_id -> interaction name
+        self.box_name = []       # box -> interaction name
+        self.box_subcat = []     # box -> subcategory (as given, may be any hashable)
+        self.box_combo = []      # box -> 'A,U' parent combination it belongs to
+        name_ids = {}
+        lower_ids = {}
+        index = np.zeros((_lib.N_PARENTS * _lib.N_PARENTS, 2, 2), dtype=np.int32)
+        for a, pa in enumerate(defs.PARENTS):
+            for b, pb in enumerate(defs.PARENTS):
+                combo = pa + "," + pb
+                if combo not in defs.BASEPAIR_COMBOS or combo not in focused:
+                    continue
+                for sg, key in enumerate((1, -1)):
+                    inters = focused[combo].get(key, {})
+                    start = len(rows)
+                    for inter, subs in inters.items():
+                        for sub, cut in subs.items():
+                            row = np.zeros((), dtype=BOX_DTYPE)
+                            for q, lk in enumerate(_LIM_KEYS):
+                                if lk == 'radiusmax':
+                                    row['lim'][q] = cut.get(lk, 0.0)
+                                else:
+                                    row['lim'][q] = cut[lk]
+                            if inter not in name_ids:
+                                name_ids[inter] = len(self.names)
+                                self.names.append(inter)
+                            row['name_id'] = name_ids[inter]
+                            row['lower_id'] = lower_ids.setdefault(inter.lower(), len(lower_ids))
+                            row['rev_lower_id'] = lower_ids.setdefault(reverse_edges(inter).lower(), len(lower_ids))
+                            row['subcat'] = int(sub)
+                            row['name_len'] = len(inter)
+                            row['flags'] = (1 if inter.startswith("n") else 0) | (2 if inter == 'cSs' else 0) | \
+                                           (4 if inter == 'csS' else 0) | (8 if 'radiusmax' in cut else 0)
+                            rows.append(row)
+                            self.box_name.append(inter)
+                            self.box_subcat.append(sub)
+                            self.box_combo.append(combo)
+                    count = len(rows) - start
+                    if count > 32:
+                        raise _lib.Fr3dError("more than 32 cutoff boxes for %s sign %d" % (combo, key))
+                    index[a * _lib.N_PARENTS + b, sg, 0] = start
+                    index[a * _lib.N_PARENTS + b, sg, 1] = count
+        if len(rows) > 65535:
+            raise _lib.Fr3dError("too many cutoff boxes")
+        self.boxes = np.array(rows, dtype=BOX_DTYPE) if rows else np.zeros(1, dtype=BOX_DTYPE)
+        self.index = index
+        self._dev = {}
+
+    def device(self, torch, device):
+        key = str(device)
+        if key not in self._dev:
+            bx = torch.from_numpy(self.boxes.view(np.uint8).reshape(-1).copy()).to(device)
+            ix = torch.from_numpy(self.index.reshape(-1).copy()).to(device)
+            self._dev[key] = (bx, ix)
+        return self._dev[key]
+
+
+class DeviceBatch(object):
+    """The NtBatch arrays resident in HBM (torch tensors) + the fr3d_nts_t pointer block."""
+
+    def __init__(self, torch, device, batch, pinned=None):
+        self.n = batch.n
+        t = {}
+        for name in ("center", "rot", "base_xyz", "bb_xyz", "base_mask", "bb_mask", "meta"):
+            src = pinned[name] if pinned is not None else torch.from_numpy(_as_signed(getattr(batch, name)))
+            t[name] = src.to(device, non_blocking=True)
+        self.t = t
+        self.nts = _lib.NtsStruct(n_nt=batch.n, reserved=0, center=t["center"].data_ptr(), rot=t["rot"].data_ptr(),
+                                  base_xyz=t["base_xyz"].data_ptr(), bb_xyz=t["bb_xyz"].data_ptr(),
+                                  base_mask=t["base_mask"].data_ptr(), bb_mask=t["bb_mask"].data_ptr(),
+                                  meta=t["meta"].data_ptr())
+
+
+def _as_signed(a):
+    """torch has no uint32 arithmetic we need; move masks as int32 bit patterns."""
+    if a.dtype == np.uint32:
+        return a.view(np.int32)
+    return a
+
+
+def pin_batch(torch, batch):
+    """Copy the batch into pinned host memory once (so timed H2D copies are DMA transfers)."""
+    out = {}
+    for name in ("center", "rot", "base_xyz", "bb_xyz", "base_mask", "bb_mask", "meta"):
+        out[name] = torch.from_numpy(_as_signed(getattr(batch, name))).pin_memory()
+    return out
+
+
+class Engine(object):
+    """One per process / GPU."""
+
+    _instances = {}
+
+    @classmethod
+    def get(cls, device=None):
+        import torch
+        if not torch.cuda.is_available():
+            raise _lib.Fr3dError("fr3d_python_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        if device is None:
+            device = torch.cuda.current_device()
+        dev = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
+        key = dev.index if dev.index is not None else torch.cuda.current_device()
+        if key not in cls._instances:
+            cls._instances[key] = cls(torch, torch.device("cuda", key))
+        return cls._instances[key]
+
+    def __init__(self, torch, device):
+        self.torch = torch
+        self.device = device
+        self.lib = _lib.load()
+        _lib.check(self.lib.fr3d_init(device.index), "fr3d_init")
+        self._tables = defs.static_tables()
+        with torch.cuda.device(device):
+            _lib.check(self.lib.fr3d_upload_tables(C.byref(self._tables)), "fr3d_upload_tables")
+        self.launches = 0          # kernels launched by this engine (bench's gpu_launches)
+
+    def stream_ptr(self):
+        return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ---------------------------------------------------------------- K1
+    def fit_frames(self, dbatch, place_h=True):
+        torch = self.torch
+        status = torch.empty(dbatch.n, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.fr3d_frames_fit(C.byref(dbatch.nts), status.data_ptr(), 1 if place_h else 0,
+                                                self.stream_ptr()), "fr3d_frames_fit")
+        self.launches += 1
+        return status
+
+    # ---------------------------------------------------------------- K2/K3
+    def search(self, dbatch, cell_size=12.0, pair_cap=None):
+        torch = self.torch
+        n = dbatch.n
+        if pair_cap is None:
+            pair_cap = 24 * n + 1024
+        ws_bytes = int(self.lib.fr3d_pair_search_workspace(n))
+        while True:
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
+            pair_i = torch.empty(pair_cap, dtype=torch.int32, device=self.device)
+            pair_j = torch.empty(pair_cap, dtype=torch.int32, device=self.device)
+            pair_rank = torch.empty(pair_cap, dtype=torch.int32, device=self.device)
+            counters = torch.empty(4, dtype=torch.int64, device=self.device)
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.fr3d_pair_search(C.byref(dbatch.nts), float(cell_size), ws.data_ptr(), ws_bytes,
+                                                     pair_i.data_ptr(), pair_j.data_ptr(), pair_rank.data_ptr(),
+                                                     pair_cap, counters.data_ptr(), self.stream_ptr()),
+                           "fr3d_pair_search")
+            self.launches += 5
+            cnt = counters.cpu()
+            if int(cnt[2]) != 0:
+                raise _lib.Fr3dError("fr3d_pair_search: base centre outside the spatial-hash range (FR3D_E_RANGE)")
+            n_pairs = int(cnt[0])
+            if n_pairs <= pair_cap:
+                return pair_i, pair_j, pair_rank, counters, n_pairs, pair_cap
+            pair_cap = n_pairs + 1024      # FR3D_E_CAPACITY: re-run with the required count
+
+    # ---------------------------------------------------------------- K4
+    def classify(self, dbatch, boxtable, pairs, category_mask, hit_cap=None):
+        torch = self.torch
+        pair_i, pair_j, pair_rank, counters, n_pairs, pair_cap = pairs
+        bx, ix = boxtable.device(torch, self.device)
+        if hit_cap is None:
+            hit_cap = 2 * n_pairs + 1024
+        while True:
+            hits = torch.empty(hit_cap * HIT_DTYPE.itemsize, dtype=torch.uint8, device=self.device)
+            counters[1] = 0
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.fr3d_classify_pairs(C.byref(dbatch.nts), bx.data_ptr(), ix.data_ptr(),
+                                                        pair_i.data_ptr(), pair_j.data_ptr(), pair_rank.data_ptr(),
+                                                        pair_cap, int(category_mask), hits.data_ptr(), hit_cap,
+                                                        counters.data_ptr(), self.stream_ptr()),
+                           "fr3d_classify_pairs")
+            self.launches += 1
+            n_hits = int(counters[1].item())
+            if n_hits <= hit_cap:
+                return hits, n_hits
+            hit_cap = n_hits + 1024
+
+    # ---------------------------------------------------------------- whole path
+    def annotate_batch(self, batch, boxtable, category_mask, pinned=None, return_frames=False):
+        """H2D -> [K1] -> K2/K3 -> K4 -> D2H.  Returns (hits structured array, n_pairs, extras)."""
+        torch = self.torch
+        with torch.cuda.device(self.device):
+            db = DeviceBatch(torch, self.device, batch, pinned)
+            extras = {}
+            if not batch.frames_given:
+                extras["status"] = self.fit_frames(db, place_h=True)
+            pairs = self.search(db)
+            hits_dev, n_hits = self.classify(db, boxtable, pairs, category_mask)
+            hits = hits_dev[: n_hits * HIT_DTYPE.itemsize].cpu().numpy().view(HIT_DTYPE)
+            if return_frames:
+                extras["center"] = db.t["center"].cpu().numpy()
+                extras["rot"] = db.t["rot"].cpu().numpy()
+                extras["base_xyz"] = db.t["base_xyz"].cpu().numpy()
+                extras["base_mask"] = db.t["base_mask"].cpu().numpy().view(np.uint32)
+                extras["status"] = extras["status"].cpu().numpy() if "status" in extras else None
+                extras["pairs"] = (pairs[0][:pairs[4]].cpu().numpy(), pairs[1][:pairs[4]].cpu().numpy(),
+                                   pairs[2][:pairs[4]].cpu().numpy())
+        return hits, pairs[4], extras

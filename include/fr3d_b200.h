@@ -1,0 +1,191 @@
+/*
+ * fr3d_b200.h — C ABI of libfr3d_b200.so (sm_100a).
+ *
+ * The reference (BGSU-RNA/fr3d-python) is pure Python and has no FFI; the
+ * boundary it exposes is a set of Python call signatures.
+ * Each entry point below names the reference function(s) whose arithmetic it
+ * replaces; fr3d_python_b200/ keeps the Python signatures on top of this ABI
+ * through ctypes.
+ *
+ * Conventions
+ *  - every function returns 0 (FR3D_OK) or a negative FR3D_E_* code, never
+ *    throws, never prints; fr3d_last_error() gives a thread-local message.
+ *  - all data pointers are DEVICE pointers owned by the caller (torch
+ *    tensors' data_ptr()) unless the parameter name starts with host_.
+ *  - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
+ *  - the library allocates nothing that outlives a call except the constant
+ *    tables uploaded by fr3d_upload_tables.
+ *  - all floating point is IEEE fp64.
+ */
+#ifndef FR3D_B200_H
+#define FR3D_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FR3D_ABI_VERSION 1
+
+#define FR3D_OK 0
+#define FR3D_E_CUDA (-1)      /* a CUDA runtime call failed; see fr3d_last_error */
+#define FR3D_E_ARG (-2)       /* bad argument */
+#define FR3D_E_CAPACITY (-3)  /* output buffer too small; required count left in the counter */
+#define FR3D_E_NOTABLES (-4)  /* fr3d_upload_tables has not been called */
+#define FR3D_E_RANGE (-5)     /* coordinates outside the spatial-hash key range */
+
+/* ---- layout constants ---------------------------------------------------- */
+#define FR3D_BASE_SLOTS 16 /* base atoms per nt: heavy atoms then hydrogens of the parent base */
+#define FR3D_BB_SLOTS 10   /* P OP1 OP2 O5' O4' O3' O2' C1' C2' prevO3' */
+#define FR3D_META_INTS 8   /* parent, flags, group, chain_rank, index, resid_key, alt_rank, reserved */
+#define FR3D_N_PARENTS 5   /* A C G U DT */
+
+#define FR3D_MASK_HAS_FRAME 0x80000000u /* bit 31 of base_mask: centre + rotation valid */
+
+/* meta[1] flags */
+#define FR3D_FLAG_STD_RNA 1  /* sequence is one of A C G U   (check_coplanar, NA:2095) */
+#define FR3D_FLAG_MODIFIED 2 /* modified residue: centre = meanR - U.meanS (components.py:348) */
+
+/* category bits for fr3d_classify_pairs (keys of the reference's `categories` dict) */
+#define FR3D_CAT_SO 1
+#define FR3D_CAT_STACKING 2
+#define FR3D_CAT_SUGAR_RIBOSE 4
+#define FR3D_CAT_BACKBONE 8
+#define FR3D_CAT_COPLANAR 16
+
+/* hit slots, in the order the reference evaluates them for one candidate pair
+ * (NA_pairwise_interactions.py:758-1013) */
+enum {
+    FR3D_SLOT_SO12 = 0,  /* code: oxygen(0..5 = O2' O3' O4' O5' OP1 OP2) | face5<<3 | near<<4 */
+    FR3D_SLOT_SO21 = 1,  /* same, base of nt2 / oxygen of nt1 */
+    FR3D_SLOT_STACK = 2, /* code: 0 s35, 1 s53, 2 s33, 3 s55 | near<<2 */
+    FR3D_SLOT_SR12 = 3,  /* code: 0 cSR, 1 tSR */
+    FR3D_SLOT_SR21 = 4,
+    FR3D_SLOT_BPH = 5,   /* code: digit | near<<4   ("7BPh", "n7BPh") */
+    FR3D_SLOT_BR = 6,    /* code: digit | near<<4 */
+    FR3D_SLOT_CP = 7,
+    FR3D_SLOT_BP = 8     /* code: bit0 near ("n" prefix), bit1 orientation 21 was used; box = cutoff box */
+};
+
+/* One annotation found for one candidate pair. 32 bytes. */
+typedef struct {
+    int32_t i;              /* nt1 of the candidate pair (global nt index) */
+    int32_t j;              /* nt2 of the candidate pair */
+    int32_t rank;           /* first_seen(cell of nt1) * 16 + stencil index: reference visit order */
+    uint8_t slot;           /* FR3D_SLOT_* */
+    uint8_t code;           /* label code, meaning depends on slot */
+    uint16_t box;           /* FR3D_SLOT_BP: index into the uploaded box table */
+    double cutoff_distance; /* FR3D_SLOT_BP: quality['cutoff_distance'] (NA:2347) */
+    double max_gap;         /* FR3D_SLOT_BP: quality['max_gap']         (NA:2348) */
+} fr3d_hit_t;
+
+/* Nucleotide records, structure-of-arrays, n_nt entries each (device pointers).
+ * Flattens what the annotator reads from fr3d.data.Component
+ * (fr3d/data/components.py:118-202, fr3d/data/base.py:80-209). */
+typedef struct {
+    int32_t n_nt;
+    int32_t reserved;
+    double *center;      /* [n][3]      centers['base'] */
+    double *rot;         /* [n][9]      rotation_matrix, row major */
+    double *base_xyz;    /* [n][16][3]  base atoms by parent slot */
+    double *bb_xyz;      /* [n][10][3]  backbone atoms */
+    uint32_t *base_mask; /* [n] bit k: slot k present; bit 31: frame valid */
+    uint32_t *bb_mask;   /* [n] bit k: backbone slot k present */
+    int32_t *meta;       /* [n][8] */
+} fr3d_nts_t;
+
+/* Constant rule tables (HOST struct, copied to __constant__ memory). Built by the
+ * Python layer from fr3d_python_b200/tables/{definitions,planes}.json. */
+typedef struct {
+    double std_xyz[FR3D_N_PARENTS][FR3D_BASE_SLOTS][3]; /* definitions.py:467-611 */
+    int32_t n_heavy[FR3D_N_PARENTS];
+    int32_t n_slots[FR3D_N_PARENTS];
+    int32_t has_div[FR3D_N_PARENTS];
+    int32_t sr_slot[FR3D_N_PARENTS];       /* N3 (A,G) / O2 (C,U) slot, -1 none (NA:2291-2296) */
+    double ring_div[FR3D_N_PARENTS][3];    /* NA:1318,1340 */
+    double ring5[FR3D_N_PARENTS][4][3];    /* NA:1319-1322 ... */
+    double ring6[FR3D_N_PARENTS][6][3];    /* padded with {0,0,1} */
+    double ell5[FR3D_N_PARENTS][5];        /* a b cx cy r  (NA:1415,1425) */
+    double ell6[FR3D_N_PARENTS][5];
+    double hull[FR3D_N_PARENTS][7][3];     /* NA:1485-1523, padded with {0,0,1} */
+    int32_t n_sites[FR3D_N_PARENTS];       /* definitions.py:260-298 */
+    int32_t site_h[FR3D_N_PARENTS][5];     /* hydrogen slot */
+    int32_t site_m[FR3D_N_PARENTS][5];     /* massive atom slot */
+    int32_t site_carbon[FR3D_N_PARENTS][5];/* 1: "C" in name, 0: "N" in name, -1 neither */
+    int32_t site_digit[FR3D_N_PARENTS][5]; /* n of "nBPh"/"nBR" */
+    int32_t combo_ok[FR3D_N_PARENTS * FR3D_N_PARENTS]; /* NA:654 */
+} fr3d_static_tables_t;
+
+/* One basepair cutoff box (class_limits_2023.py after focus_basepair_cutoffs, NA:88-136). 128 B. */
+typedef struct {
+    double xmin, xmax, ymin, ymax, zmin, zmax, normalmin, normalmax, anglemin, anglemax, gapmax, radiusmax;
+    int32_t name_id;      /* host-side id of the interaction name */
+    int32_t lower_id;     /* id of name.lower() */
+    int32_t rev_lower_id; /* id of reverse_edges(name).lower() */
+    int32_t subcat;
+    int32_t name_len;
+    int32_t flags;        /* bit0 name starts with 'n', bit1 name=='cSs', bit2 name=='csS', bit3 has radiusmax */
+    int32_t pad[2];
+} fr3d_box_t;
+
+/* ---- library ------------------------------------------------------------ */
+int fr3d_version(void);
+const char *fr3d_last_error(void);
+int fr3d_init(int device);
+int fr3d_upload_tables(const fr3d_static_tables_t *host_tables);
+
+/* K1. Replaces Component.calculate_rotation_matrix (fr3d/data/components.py:273-349) +
+ * besttransformation (fr3d/geometry/superpositions.py:10-89) for every nt in one launch, and
+ * the hydrogen placement arithmetic of infer_NA_hydrogens (components.py:452-462) when
+ * place_h != 0.  Reads base_xyz/base_mask/meta; writes center, rot, missing hydrogen slots,
+ * base_mask (hydrogen bits + FR3D_MASK_HAS_FRAME) and status[n] (0 ok, -1 no parent, -2 <3 atoms). */
+int fr3d_frames_fit(const fr3d_nts_t *nts, int32_t *status, int place_h, void *stream);
+
+/* K2+K3. Replaces make_nt_cubes_half (NA:410-443) and the loop/screens of
+ * annotate_nt_nt_interactions (NA:661-724): oriented candidate pairs with 2 <= d <= 12.
+ * counters (device int64[4]): [0] n_pairs (may exceed cap: FR3D_E_CAPACITY is NOT raised here,
+ * the caller compares after its sync), [1] n_hits, [2] error flags, [3] n_cells. */
+size_t fr3d_pair_search_workspace(int32_t n_nt);
+int fr3d_pair_search(const fr3d_nts_t *nts, double cell_size, void *workspace, size_t workspace_bytes,
+                     int32_t *pair_i, int32_t *pair_j, int32_t *pair_rank, int64_t pair_cap,
+                     int64_t *counters, void *stream);
+
+/* K4. Replaces check_base_oxygen_stack_rings (NA:1278), check_base_base_stacking (NA:1602),
+ * check_sugar_ribose (NA:2262), check_base_backbone_interactions (NA:1867), check_coplanar
+ * (NA:2051), check_basepair_cutoffs (NA:2364) and the 12-vs-21 arbitration (NA:935-957):
+ * one warp per candidate pair, hits compacted with a warp ballot.
+ * n_pairs is read from counters[0] on the device (clamped to pair_cap). */
+int fr3d_classify_pairs(const fr3d_nts_t *nts, const fr3d_box_t *boxes, const int32_t *box_index /*[25][2][2]*/,
+                        const int32_t *pair_i, const int32_t *pair_j, const int32_t *pair_rank,
+                        int64_t pair_cap, uint32_t category_mask, fr3d_hit_t *hits, int64_t hit_cap,
+                        int64_t *counters, void *stream);
+
+/* K5. Replaces besttransformation / besttransformation_weighted
+ * (fr3d/geometry/superpositions.py:10-121) for n_prob independent problems.
+ * Problem p uses rows off[p]..off[p+1]-1 of set1/set2/w (w may be NULL = unweighted).
+ * Outputs (any may be NULL): U[p][9], mean1[p][3], mean2[p][3], rmsd[p], sse[p], new1[rows][3]. */
+int fr3d_kabsch_batched(const double *set1, const double *set2, const double *w, const int32_t *off,
+                        int32_t n_prob, double *U, double *mean1, double *mean2, double *rmsd,
+                        double *sse, double *new1, void *stream);
+
+/* K6. Replaces matrix_discrepancy (fr3d/geometry/discrepancy.py:165-233,
+ * fr3d/search/discrepancy.py:165-233) over the double loop of fr3d/search/FR3D.py:433-442.
+ * centers [N][n][3], rots [N][n][9], has_rot [N][n] (NULL = all present).
+ * Writes out[(r - row0) * N + c] for row0 <= r < row1, 0 <= c < N; the diagonal is 0. */
+int fr3d_discrepancy_all_vs_all(const double *centers, const double *rots, const uint8_t *has_rot,
+                                int32_t N, int32_t n, double angle_weight, int32_t row0, int32_t row1,
+                                double *out, void *stream);
+
+/* Replaces matrix_discrepancy_cutoff (discrepancy.py:235-313) of one query against M candidates
+ * (fr3d/search/search.py:1073-1085). out[m] = NaN where the reference returns None. */
+int fr3d_discrepancy_one_vs_many(const double *q_centers, const double *q_rots, const uint8_t *q_has_rot,
+                                 const double *centers, const double *rots, const uint8_t *has_rot,
+                                 int32_t M, int32_t n, double cutoff /* < 0: no cutoff */, double angle_weight,
+                                 const double *center_weight /* [n] or NULL */, double *out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FR3D_B200_H */
