@@ -172,73 +172,94 @@ class Engine(object):
         self.launches += 1
         return status
 
-    # ---------------------------------------------------------------- K2/K3
-    def search(self, dbatch, cell_size=12.0, pair_cap=None):
+    # ---------------------------------------------------------------- plans
+    def make_plan(self, n_nt, pair_cap=None, hit_cap=None):
+        """Pre-allocate every device buffer one pass over an n_nt batch needs, so that the pass
+        itself is launches only (no allocation, no host sync)."""
         torch = self.torch
-        n = dbatch.n
         if pair_cap is None:
-            pair_cap = 24 * n + 1024
-        ws_bytes = int(self.lib.fr3d_pair_search_workspace(n))
-        while True:
-            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
-            pair_i = torch.empty(pair_cap, dtype=torch.int32, device=self.device)
-            pair_j = torch.empty(pair_cap, dtype=torch.int32, device=self.device)
-            pair_rank = torch.empty(pair_cap, dtype=torch.int32, device=self.device)
-            counters = torch.empty(4, dtype=torch.int64, device=self.device)
-            with torch.cuda.device(self.device):
-                _lib.check(self.lib.fr3d_pair_search(C.byref(dbatch.nts), float(cell_size), ws.data_ptr(), ws_bytes,
-                                                     pair_i.data_ptr(), pair_j.data_ptr(), pair_rank.data_ptr(),
-                                                     pair_cap, counters.data_ptr(), self.stream_ptr()),
-                           "fr3d_pair_search")
-            self.launches += 5
-            cnt = counters.cpu()
-            if int(cnt[2]) != 0:
-                raise _lib.Fr3dError("fr3d_pair_search: base centre outside the spatial-hash range (FR3D_E_RANGE)")
-            n_pairs = int(cnt[0])
-            if n_pairs <= pair_cap:
-                return pair_i, pair_j, pair_rank, counters, n_pairs, pair_cap
-            pair_cap = n_pairs + 1024      # FR3D_E_CAPACITY: re-run with the required count
-
-    # ---------------------------------------------------------------- K4
-    def classify(self, dbatch, boxtable, pairs, category_mask, hit_cap=None):
-        torch = self.torch
-        pair_i, pair_j, pair_rank, counters, n_pairs, pair_cap = pairs
-        bx, ix = boxtable.device(torch, self.device)
+            pair_cap = 12 * n_nt + 1024        # ~6.3 candidate pairs per nt on RNA (SURVEY §6)
         if hit_cap is None:
-            hit_cap = 2 * n_pairs + 1024
-        while True:
-            hits = torch.empty(hit_cap * HIT_DTYPE.itemsize, dtype=torch.uint8, device=self.device)
-            counters[1] = 0
-            with torch.cuda.device(self.device):
-                _lib.check(self.lib.fr3d_classify_pairs(C.byref(dbatch.nts), bx.data_ptr(), ix.data_ptr(),
-                                                        pair_i.data_ptr(), pair_j.data_ptr(), pair_rank.data_ptr(),
-                                                        pair_cap, int(category_mask), hits.data_ptr(), hit_cap,
-                                                        counters.data_ptr(), self.stream_ptr()),
-                           "fr3d_classify_pairs")
+            hit_cap = pair_cap + 1024
+        p = Plan()
+        p.n_nt, p.pair_cap, p.hit_cap = n_nt, int(pair_cap), int(hit_cap)
+        p.ws_bytes = int(self.lib.fr3d_pair_search_workspace(n_nt))
+        dev = self.device
+        p.ws = torch.empty(p.ws_bytes, dtype=torch.uint8, device=dev)
+        p.pair_i = torch.empty(p.pair_cap, dtype=torch.int32, device=dev)
+        p.pair_j = torch.empty(p.pair_cap, dtype=torch.int32, device=dev)
+        p.pair_rank = torch.empty(p.pair_cap, dtype=torch.int32, device=dev)
+        p.counters = torch.zeros(4, dtype=torch.int64, device=dev)
+        p.hits = torch.empty(p.hit_cap * HIT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+        p.status = torch.empty(max(n_nt, 1), dtype=torch.int32, device=dev)
+        return p
+
+    def run_plan(self, dbatch, plan, boxtable, category_mask, fit_frames=True, events=None):
+        """K1 -> K2/K3 -> K4 on the current stream, asynchronously.  `events` (dict) receives
+        torch CUDA events around the classify launch for per-kernel timing."""
+        torch = self.torch
+        bx, ix = boxtable.device(torch, self.device)
+        st = self.stream_ptr()
+        with torch.cuda.device(self.device):
+            if fit_frames:
+                _lib.check(self.lib.fr3d_frames_fit(C.byref(dbatch.nts), plan.status.data_ptr(), 1, st),
+                           "fr3d_frames_fit")
+                self.launches += 1
+            if events is not None:
+                events["search0"].record()
+            _lib.check(self.lib.fr3d_pair_search(C.byref(dbatch.nts), 12.0, plan.ws.data_ptr(), plan.ws_bytes,
+                                                 plan.pair_i.data_ptr(), plan.pair_j.data_ptr(),
+                                                 plan.pair_rank.data_ptr(), plan.pair_cap, plan.counters.data_ptr(), st),
+                       "fr3d_pair_search")
+            self.launches += 5
+            if events is not None:
+                events["classify0"].record()
+            _lib.check(self.lib.fr3d_classify_pairs(C.byref(dbatch.nts), bx.data_ptr(), ix.data_ptr(),
+                                                    plan.pair_i.data_ptr(), plan.pair_j.data_ptr(),
+                                                    plan.pair_rank.data_ptr(), plan.pair_cap, int(category_mask),
+                                                    plan.hits.data_ptr(), plan.hit_cap, plan.counters.data_ptr(), st),
+                       "fr3d_classify_pairs")
             self.launches += 1
-            n_hits = int(counters[1].item())
-            if n_hits <= hit_cap:
-                return hits, n_hits
-            hit_cap = n_hits + 1024
+            if events is not None:
+                events["classify1"].record()
+
+    def read_counts(self, plan):
+        """(n_pairs, n_hits) after a sync; raises on range errors; None if a capacity was exceeded."""
+        cnt = plan.counters.cpu()
+        if int(cnt[2]) != 0:
+            raise _lib.Fr3dError("fr3d_pair_search: base centre outside the spatial-hash range (FR3D_E_RANGE)")
+        return int(cnt[0]), int(cnt[1])
 
     # ---------------------------------------------------------------- whole path
-    def annotate_batch(self, batch, boxtable, category_mask, pinned=None, return_frames=False):
-        """H2D -> [K1] -> K2/K3 -> K4 -> D2H.  Returns (hits structured array, n_pairs, extras)."""
+    def annotate_batch(self, batch, boxtable, category_mask, pinned=None, return_frames=False, plan=None):
+        """H2D -> [K1] -> K2/K3 -> K4 -> D2H.  Returns (hits structured array, n_pairs, extras).
+        Capacity overflow (FR3D_E_CAPACITY) re-runs with the exact counts; nothing is truncated."""
         torch = self.torch
         with torch.cuda.device(self.device):
             db = DeviceBatch(torch, self.device, batch, pinned)
-            extras = {}
-            if not batch.frames_given:
-                extras["status"] = self.fit_frames(db, place_h=True)
-            pairs = self.search(db)
-            hits_dev, n_hits = self.classify(db, boxtable, pairs, category_mask)
-            hits = hits_dev[: n_hits * HIT_DTYPE.itemsize].cpu().numpy().view(HIT_DTYPE)
+            if plan is None or plan.n_nt != batch.n:
+                plan = self.make_plan(batch.n)
+            fit = not batch.frames_given
+            while True:
+                self.run_plan(db, plan, boxtable, category_mask, fit_frames=fit)
+                n_pairs, n_hits = self.read_counts(plan)
+                if n_pairs <= plan.pair_cap and n_hits <= plan.hit_cap:
+                    break
+                fit = False          # frames are already in place in the device batch
+                plan = self.make_plan(batch.n, max(n_pairs, plan.pair_cap) + 1024,
+                                      max(n_hits, 2 * max(n_pairs, 1)) + 1024)
+            hits = plan.hits[: n_hits * HIT_DTYPE.itemsize].cpu().numpy().view(HIT_DTYPE)
+            extras = {"plan": plan}
             if return_frames:
                 extras["center"] = db.t["center"].cpu().numpy()
                 extras["rot"] = db.t["rot"].cpu().numpy()
                 extras["base_xyz"] = db.t["base_xyz"].cpu().numpy()
                 extras["base_mask"] = db.t["base_mask"].cpu().numpy().view(np.uint32)
-                extras["status"] = extras["status"].cpu().numpy() if "status" in extras else None
-                extras["pairs"] = (pairs[0][:pairs[4]].cpu().numpy(), pairs[1][:pairs[4]].cpu().numpy(),
-                                   pairs[2][:pairs[4]].cpu().numpy())
-        return hits, pairs[4], extras
+                extras["status"] = plan.status[:batch.n].cpu().numpy() if not batch.frames_given else None
+                extras["pairs"] = (plan.pair_i[:n_pairs].cpu().numpy(), plan.pair_j[:n_pairs].cpu().numpy(),
+                                   plan.pair_rank[:n_pairs].cpu().numpy())
+        return hits, n_pairs, extras
+
+
+class Plan(object):
+    pass

@@ -69,6 +69,30 @@ class NtBatch(object):
                                       self.bb_mask, self.meta))
 
 
+def select_structures(batch, which):
+    """Sub-batch holding the structures listed in `which` (in that order); nt-level arrays are
+    sliced, group ids are kept (they only need to be distinct per structure/model)."""
+    which = [int(w) for w in which]
+    rows = np.concatenate([np.arange(batch.struct_off[w], batch.struct_off[w + 1]) for w in which]) \
+        if which else np.zeros(0, dtype=np.int64)
+    out = NtBatch(len(rows))
+    for name in ("center", "rot", "base_xyz", "bb_xyz", "base_mask", "bb_mask", "meta"):
+        getattr(out, name)[:] = getattr(batch, name)[rows]
+    out.frames_given = batch.frames_given
+    out.pdb = [batch.pdb[w] for w in which]
+    lens = [int(batch.struct_off[w + 1] - batch.struct_off[w]) for w in which]
+    out.struct_off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    for name in ("model", "chain", "sequence", "number", "index", "symmetry", "alt_id", "insertion_code"):
+        src = getattr(batch, name)
+        dst = []
+        for w in which:
+            dst.extend(src[int(batch.struct_off[w]):int(batch.struct_off[w + 1])])
+        setattr(out, name, dst)
+    if batch._unit_ids is not None:
+        out._unit_ids = [batch._unit_ids[r] for r in rows]
+    return out
+
+
 def encode_unit_id(pdb, model, chain, sequence, number, alt_id, insertion_code, symmetry):
     """fr3d/unit_ids.py:31-64 for a component (no atom name)."""
     ordered = ['' if v is None else str(v) for v in

@@ -1,0 +1,310 @@
+"""Parity of the CUDA path (through the public API / C ABI) against the reference golden vectors
+and the oracle.  Integer / label work must be identical; fp64 outputs within 1e-9 (the tolerance
+BASELINE.json states)."""
+
+import copy
+
+import numpy as np
+import pytest
+
+from conftest import ALL9
+from fr3d_python_b200 import _lib, packing, synthetic
+from fr3d_python_b200 import definitions as defs
+from fr3d_python_b200.classifiers import NA_pairwise_interactions as NA
+from fr3d_python_b200.data import Structure
+from fr3d_python_b200.engine import Engine
+from fr3d_python_b200.geometry import frames as gframes
+from oracle import fr3d_oracle as O
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+def oracle_tuples(spec, categories):
+    nts = O.build_nts(spec)
+    out, c2i, tr = O.annotate(spec, categories, nts)
+    res = {k: [(nts[a].unit_id(), nts[b].unit_id(), c) for a, b, c in v] for k, v in out.items() if v}
+    return res, {k: set(v) for k, v in c2i.items() if v}, tr, nts
+
+
+def as_plain(result):
+    i2t, c2i = result[0], result[1]
+    return {k: list(v) for k, v in i2t.items() if v}, {k: set(v) for k, v in c2i.items() if v}
+
+
+# ------------------------------------------------------------------ frames (K1)
+@pytest.mark.parametrize("name", ["1gid_full", "1s72_strand", "1s72_sarcin"])
+def test_frames_and_hydrogens_match_reference(golden, name):
+    spec = golden("spec_%s.json.gz" % name)
+    want = golden("frames_%s.json.gz" % name)
+    b = packing.pack_specs(spec)
+    status = gframes.fit_batch_frames(b, place_h=True)
+    assert np.all(status == 0)
+    for k, f in enumerate(want):
+        assert np.abs(b.center[k] - np.array(f["center"])).max() < TOL
+        assert np.abs(b.rot[k].reshape(3, 3) - np.array(f["rotation"])).max() < TOL
+        parent = defs.PARENTS[b.meta[k, 0]]
+        for hname, xyz in f["hydrogens"].items():
+            slot = defs.SLOT_OF[parent][hname]
+            assert b.base_mask[k] >> slot & 1
+            assert np.abs(b.base_xyz[k, slot] - np.array(xyz)).max() < TOL
+        assert b.base_mask[k] & _lib.MASK_HAS_FRAME
+
+
+def test_frames_match_matlab_golden(golden):
+    b = packing.pack_specs(golden("spec_1gid_base.json.gz"))
+    gframes.fit_batch_frames(b)
+    for k, m in enumerate(golden("matlab_1gid_frames.json.gz")):
+        assert np.abs(b.center[k] - np.array(m["center"])).max() < 1e-6       # inputs carry 6 decimals
+        assert np.abs(b.rot[k].reshape(3, 3) - np.array(m["rotation"])).max() < 1e-6
+
+
+def test_component_api_fits_frames_on_gpu(golden):
+    spec = golden("spec_1s72_strand.json.gz")
+    st = Structure.from_spec(spec)
+    want = golden("frames_1s72_strand.json.gz")
+    res = st.residues(type=["RNA linking", "DNA linking"])
+    assert len(res) == 10
+    for c, f in zip(res, want):
+        assert c.unit_id() == f["unit_id"]
+        assert isinstance(c.rotation_matrix, np.matrix)
+        assert np.abs(np.asarray(c.rotation_matrix) - np.array(f["rotation"])).max() < TOL
+        assert np.abs(c.centers["base"] - np.array(f["center"])).max() < TOL
+        for hname, xyz in f["hydrogens"].items():
+            assert np.abs(c.centers[hname] - np.array(xyz)).max() < TOL
+        gly = "N9" if c.sequence in "AG" else "N1"
+        assert np.array_equal(c.centers["glycosidic"], c.centers[gly])
+
+
+def test_degenerate_and_unknown_residues(golden):
+    spec = copy.deepcopy(golden("spec_1s72_strand.json.gz"))
+    spec["nts"][2]["atoms"] = [a for a in spec["nts"][2]["atoms"] if a[0] in ("N1", "C2", "P", "O2'")]   # 2 base atoms
+    spec["nts"][4]["sequence"] = "XYZ"                                                                   # unknown residue
+    b = packing.pack_specs(spec)
+    status = gframes.fit_batch_frames(b)
+    assert status[2] == -2 and status[4] == -1 and np.all(np.delete(status, [2, 4]) == 0)
+    assert not (b.base_mask[2] & _lib.MASK_HAS_FRAME) and not (b.base_mask[4] & _lib.MASK_HAS_FRAME)
+    res = NA.annotate_batch(spec, ALL9)[0]
+    pairs = [t for v in res[0].values() for t in v]
+    bad = {b.unit_ids()[2], b.unit_ids()[4]}
+    assert not any((t[0] in bad or t[1] in bad) and t[2] is not None for t in pairs)     # only p_ links mention them
+
+
+# ------------------------------------------------------------------ search (K2/K3)
+def test_candidate_pairs_in_reference_order(golden):
+    spec = golden("spec_1gid_full.json.gz")
+    g = golden("annot_1gid_full_all9.json.gz")
+    results, ex = NA.annotate_batch(spec, ALL9, return_raw=True)
+    pi, pj, pr = ex["pairs"]
+    order = np.lexsort((pj, pi, pr))
+    got = [[int(a), int(b)] for a, b in zip(pi[order], pj[order])]
+    assert got == g["traces"]["candidates"]
+    assert ex["n_pairs"] == 1983
+
+
+def test_search_edge_cases(golden):
+    eng = Engine.get()
+    assert as_plain(NA.annotate_batch({"pdb": "E", "nts": []}, ALL9)[0]) == ({}, {})      # empty structure
+    spec = copy.deepcopy(golden("spec_1s72_strand.json.gz"))
+    # symmetry copy of nt 3 a few Angstrom away, same chain and index: the reference visits the
+    # pair in both orders (NA:684-688); negative coordinates exercise floor()
+    for nt in spec["nts"]:
+        for a in nt["atoms"]:
+            a[1] -= 200.0
+            a[2] -= 160.0
+    twin = copy.deepcopy(spec["nts"][3])
+    twin["symmetry"] = "2_555"
+    for a in twin["atoms"]:
+        a[3] += 3.4
+    spec["nts"].append(twin)
+    # alt-id twins of nt 6: never compared with each other (NA:706-713)
+    alt = copy.deepcopy(spec["nts"][6])
+    spec["nts"][6]["alt_id"] = "A"
+    alt["alt_id"] = "B"
+    for a in alt["atoms"]:
+        a[1] += 2.5
+    spec["nts"].append(alt)
+    want, wc, tr, nts = oracle_tuples(spec, ALL9)
+    results, ex = NA.annotate_batch(spec, ALL9, return_raw=True)
+    pi, pj, pr = ex["pairs"]
+    order = np.lexsort((pj, pi, pr))
+    got = [(int(a), int(b)) for a, b in zip(pi[order], pj[order])]
+    assert got == [tuple(p) for p in tr["candidates"]]
+    assert (3, 10) in got or (10, 3) in got                      # the symmetry twin is a partner
+    assert (6, 11) not in got and (11, 6) not in got
+    assert as_plain(results[0]) == (want, wc)
+    del eng
+
+
+def test_out_of_range_coordinates_raise(golden):
+    spec = copy.deepcopy(golden("spec_1s72_strand.json.gz"))
+    for a in spec["nts"][0]["atoms"]:
+        a[1] += 1.0e6
+    with pytest.raises(_lib.Fr3dError):
+        NA.annotate_batch(spec, ALL9)
+
+
+def test_capacity_overflow_is_retried_not_truncated(golden):
+    spec = golden("spec_1gid_full.json.gz")
+    batch = packing.pack_specs(spec)
+    eng = Engine.get()
+    bt, atoms = NA._box_table(NA._default_focused(ALL9['basepair']), NA.load_ideal_basepair_hydrogen_bonds())
+    tiny = eng.make_plan(batch.n, pair_cap=100, hit_cap=10)
+    hits, n_pairs, ex = eng.annotate_batch(batch, bt, NA.category_mask(ALL9), plan=tiny)
+    assert n_pairs == 1983 and len(hits) == 783
+
+
+# ------------------------------------------------------------------ full annotation (K1-K4 + host tail)
+@pytest.mark.parametrize("spec_name,annot_name", [
+    ("spec_1s72_strand.json.gz", "annot_1s72_strand_all9.json.gz"),
+    ("spec_1gid_full.json.gz", "annot_1gid_full_all9.json.gz"),
+    ("spec_1gid_base.json.gz", "annot_1gid_base_bp_stack_cp.json.gz"),
+    ("spec_1gid_base.json.gz", "annot_1gid_base_bp.json.gz"),
+])
+def test_annotation_identical_to_reference(golden, spec_name, annot_name):
+    spec = golden(spec_name)
+    g = golden(annot_name)
+    uid = g["unit_ids"]
+    want = {k: [(uid[a], uid[b], c) for a, b, c in v] for k, v in g["interaction_to_list_of_tuples"].items()}
+    wantc = {k: set(v) for k, v in g["category_to_interactions"].items()}
+    # batched entry point, frames fitted on the GPU
+    i2t, c2i = as_plain(NA.annotate_batch(spec, g["categories"])[0])
+    assert i2t == want and c2i == wantc                 # same rows, same order as fr3d-python
+    # reference entry point on Structure / Component objects
+    st = Structure.from_spec(spec)
+    r = NA.annotate_nt_nt_in_structure(st, g["categories"])
+    assert len(r) == 4
+    i2t2, c2i2 = as_plain(r)
+    assert i2t2 == want and c2i2 == wantc
+    assert isinstance(r[2], dict) and "allStates" in r[2] and r[3] == {}
+
+
+def test_get_datapoint_is_refused(golden):
+    st = Structure.from_spec(golden("spec_1s72_strand.json.gz"))
+    with pytest.raises(NotImplementedError):
+        NA.annotate_nt_nt_in_structure(st, ALL9, get_datapoint=True)
+
+
+def test_chain_filter(golden):
+    spec = golden("spec_1gid_full.json.gz")
+    st = Structure.from_spec(spec)
+    r = NA.annotate_nt_nt_in_structure(st, {'basepair': NA.Leontis_Westhof_basepairs, 'stacking': []}, chains=["A"])
+    sub = {"pdb": spec["pdb"], "nts": [nt for nt in spec["nts"] if nt["chain"] == "A"]}
+    want, wc, _, _ = oracle_tuples(sub, {'basepair': NA.Leontis_Westhof_basepairs, 'stacking': []})
+    assert as_plain(r) == (want, wc)
+
+
+def test_perturbed_batch_against_oracle():
+    """Seeded perturbed copies annotated in ONE batch launch == oracle per structure."""
+    base = synthetic.pack_base()
+    batch = synthetic.make_structure_batch(base, 6, seed0=4000)
+    results = NA.annotate_batch(batch, ALL9)
+    for s in range(6):
+        want, wc, _, _ = oracle_tuples(synthetic.batch_to_spec(batch, s), ALL9)
+        assert as_plain(results[s]) == (want, wc), "structure %d" % s
+
+
+def test_dna_and_missing_atoms_against_oracle(golden):
+    spec = copy.deepcopy(golden("spec_1gid_full.json.gz"))
+    nts = O.build_nts(spec)
+    std = defs.NAbasecoordinates["DT"]
+    for k, nt in enumerate(spec["nts"][:120]):
+        if k % 3 == 0 and nt["sequence"] in ("A", "C", "G"):
+            nt["sequence"] = "D" + nt["sequence"]
+            nt["atoms"] = [a for a in nt["atoms"] if a[0] != "O2'"]
+        elif k % 3 == 1 and nt["sequence"] == "U":
+            nt["sequence"] = "DT"
+            c7 = nts[k].base_center + nts[k].rotation.dot(np.array(std["C7"]))
+            nt["atoms"] = [a for a in nt["atoms"] if a[0] != "O2'"] + [["C7", float(c7[0]), float(c7[1]), float(c7[2])]]
+        elif k % 7 == 2:
+            nt["atoms"] = [a for a in nt["atoms"] if a[0] not in ("P", "OP1", "O4'", "C2'")]
+        elif k % 11 == 5:
+            nt["atoms"] = [a for a in nt["atoms"] if a[0] not in ("N9", "N1")]            # no glycosidic atom
+        elif k % 13 == 6:
+            nt["atoms"] = [a for a in nt["atoms"] if a[0] not in ("N3", "O2", "C5")]
+    want, wc, tr, _ = oracle_tuples(spec, ALL9)
+    got = as_plain(NA.annotate_batch(spec, ALL9)[0])
+    assert got == (want, wc)
+    assert any("DT" in t[0] or "DT" in t[1] for v in want.values() for t in v)
+
+
+def test_observed_hydrogens_are_kept(golden):
+    """High-resolution input with observed (and mislabelled) amino hydrogens, components.py:405-445."""
+    spec = copy.deepcopy(golden("spec_1s72_strand.json.gz"))
+    fr = golden("frames_1s72_strand.json.gz")
+    for k in (1, 3):                         # A and G: put H61/H62 (H21/H22) in, swapped and shifted
+        h = fr[k]["hydrogens"]
+        names = ("H61", "H62") if "H61" in h else ("H21", "H22")
+        spec["nts"][k]["atoms"] += [[names[0]] + [v + 0.05 for v in h[names[1]]], [names[1]] + [v + 0.05 for v in h[names[0]]]]
+    b = packing.pack_specs(spec)
+    gframes.fit_batch_frames(b)
+    for k in (1, 3):
+        parent = defs.PARENTS[b.meta[k, 0]]
+        h = fr[k]["hydrogens"]
+        names = ("H61", "H62") if "H61" in h else ("H21", "H22")
+        for n in names:      # relabelled back, observed coordinates kept (not replaced by ideal ones)
+            assert np.abs(b.base_xyz[k, defs.SLOT_OF[parent][n]] - (np.array(h[n]) + 0.05)).max() < 1e-12
+
+
+def test_s1s72_like_structure_against_oracle():
+    """C2 stand-in: 9 rotated, noised copies of 1GID-full in ONE structure, 2 844 nt."""
+    base = synthetic.pack_base()
+    t = synthetic.make_tiled_structure(base, 9, (3, 3, 1), seed=1072, pdb="1S72L")
+    res, ex = NA.annotate_batch(t, ALL9, return_raw=True)
+    want, wc, tr, _ = oracle_tuples(synthetic.batch_to_spec(t, 0), ALL9)
+    assert ex["n_pairs"] == len(tr["candidates"])
+    assert as_plain(res[0]) == (want, wc)
+
+
+def test_full_size_batch_properties():
+    """C4 (1000 structures) and C3 (25 280 nt in one structure): size-independent properties."""
+    base = synthetic.pack_base()
+    batch = synthetic.make_structure_batch(base, 1000, seed0=4000)
+    eng = Engine.get()
+    bt, atoms = NA._box_table(NA._default_focused(ALL9['basepair']), NA.load_ideal_basepair_hydrogen_bonds())
+    mask = NA.category_mask(ALL9)
+    hits, n_pairs, ex = eng.annotate_batch(batch, bt, mask, return_frames=True)
+    hits2, n_pairs2, _ = eng.annotate_batch(batch, bt, mask)
+    key = lambda h: np.lexsort((h['slot'], h['j'], h['i'], h['rank']))
+    assert n_pairs == n_pairs2 and np.array_equal(hits[key(hits)], hits2[key(hits2)])     # deterministic set
+    pi, pj, pr = ex["pairs"]
+    sid = np.searchsorted(batch.struct_off, pi, side='right') - 1
+    assert np.array_equal(sid, np.searchsorted(batch.struct_off, pj, side='right') - 1)   # never across structures
+    d = np.linalg.norm(ex["center"][pi] - ex["center"][pj], axis=1)
+    assert d.min() >= 2.0 and d.max() <= 12.0
+    code = pi.astype(np.int64) * batch.n + pj
+    assert len(np.unique(code)) == len(code)                                             # each oriented pair once
+    und = np.minimum(pi, pj).astype(np.int64) * batch.n + np.maximum(pi, pj)
+    assert len(np.unique(und)) == len(und)                                               # and in one orientation only
+    # every unordered pair within 12 A is found: brute force on three structures
+    for s in (0, 499, 999):
+        lo, hi = batch.struct_off[s], batch.struct_off[s + 1]
+        c = ex["center"][lo:hi]
+        dd = np.linalg.norm(c[:, None] - c[None], axis=2)
+        want = int(((dd >= 2.0) & (dd <= 12.0)).sum() // 2)
+        assert int((sid == s).sum()) == want
+    # rotations are proper and orthonormal
+    R = ex["rot"].reshape(-1, 3, 3)
+    assert np.abs(np.einsum('nij,nkj->nik', R, R) - np.eye(3)).max() < 1e-12
+    assert np.abs(np.linalg.det(R) - 1).max() < 1e-12
+    # structure k of the batch == the same structure annotated alone
+    res_all = NA.annotate_batch(packing.select_structures(batch, [0, 499, 999]), ALL9)
+    sub = postprocess_subset(batch, hits, bt, atoms, [0, 499, 999])
+    for a, b in zip(res_all, sub):
+        assert as_plain(a) == as_plain(b)
+    # C3: one 25 280-nt structure
+    big = synthetic.make_tiled_structure(base, 80, (5, 4, 4), seed=25000, pdb="C3")
+    hb, npb, exb = eng.annotate_batch(big, bt, mask, return_frames=True)
+    pi, pj, pr = exb["pairs"]
+    d = np.linalg.norm(exb["center"][pi] - exb["center"][pj], axis=1)
+    assert big.n == 25280 and d.min() >= 2.0 and d.max() <= 12.0
+    und = np.minimum(pi, pj).astype(np.int64) * big.n + np.maximum(pi, pj)
+    assert len(np.unique(und)) == len(und)
+    assert np.all(hb['slot'] <= 8)
+
+
+def postprocess_subset(batch, hits, bt, atoms, which):
+    from fr3d_python_b200 import postprocess
+    hits = postprocess.sort_hits(hits)
+    sidx = np.searchsorted(batch.struct_off, hits['i'], side='right') - 1
+    return [postprocess.build_results(batch, s, hits[sidx == s], bt, atoms, ALL9) for s in which]

@@ -1,0 +1,139 @@
+"""The oracle (oracle/fr3d_oracle.py) against the golden vectors produced by the unmodified
+reference (tools/make_golden.py) and against the known answers the reference's own tests hold.
+CPU only."""
+
+import numpy as np
+import pytest
+
+from oracle import fr3d_oracle as O
+
+
+def _close_rows(a, b, tol=0.0):
+    assert len(a) == len(b)
+    for x, y in zip(a, b):
+        assert x[:3] == y[:3], (x, y)
+        for u, v in zip(x[3:], y[3:]):
+            assert (u is None) == (v is None), (x, y)
+            if u is not None:
+                if isinstance(u, str):
+                    assert u == v
+                else:
+                    assert abs(u - v) <= tol, (x, y)
+
+
+@pytest.mark.parametrize("spec_name,annot_name", [
+    ("spec_1s72_strand.json.gz", "annot_1s72_strand_all9.json.gz"),
+    ("spec_1gid_full.json.gz", "annot_1gid_full_all9.json.gz"),
+    ("spec_1gid_base.json.gz", "annot_1gid_base_bp_stack_cp.json.gz"),
+    ("spec_1gid_base.json.gz", "annot_1gid_base_bp.json.gz"),
+])
+def test_annotation_matches_reference(golden, spec_name, annot_name):
+    spec = golden(spec_name)
+    g = golden(annot_name)
+    out, c2i, tr = O.annotate(spec, g["categories"])
+    if g["traces"]["candidates"]:
+        assert tr["candidates"] == g["traces"]["candidates"]          # oriented pairs, reference visit order
+    for key in ("sO", "stacking", "sugar_ribose", "backbone"):
+        assert tr[key] == g["traces"][key], key
+    _close_rows(tr["coplanar"], g["traces"]["coplanar"])
+    _close_rows(tr["basepair"], g["traces"]["basepair"])
+    got = {k: [list(t) for t in v] for k, v in out.items()}
+    assert got == g["interaction_to_list_of_tuples"]                   # same rows, same order
+    assert {k: sorted(v) for k, v in c2i.items()} == g["category_to_interactions"]
+    assert "Found %d nucleotide" % tr["count_pair"] in g["found_line"]
+
+
+def test_1gid_probe_counts(golden):
+    """basepair-only run on the 1GID bases."""
+    g = golden("annot_1gid_base_bp.json.gz")
+    counts = {k: len(v) for k, v in g["interaction_to_list_of_tuples"].items()}
+    assert counts["cWW"] == 202 and counts["tHS"] == 7 and counts["ncWW"] == 10 and counts["p_1"] == 314
+    assert "Found 154" in g["found_line"]
+
+
+@pytest.mark.parametrize("name", ["1gid_full", "1s72_strand", "1s72_sarcin"])
+def test_frames_match_reference(golden, name):
+    spec = golden("spec_%s.json.gz" % name)
+    frames = golden("frames_%s.json.gz" % name)
+    nts = O.build_nts(spec)
+    for nt, f in zip(nts, frames):
+        assert nt.unit_id() == f["unit_id"]
+        assert np.abs(nt.base_center - np.array(f["center"])).max() == 0.0
+        assert np.abs(nt.rotation - np.array(f["rotation"])).max() == 0.0
+        placed = {n: x for n, x in zip(nt.atom_names, nt.atom_xyz) if n in f["hydrogens"]}
+        assert set(placed) == set(f["hydrogens"])
+        for n, x in placed.items():
+            assert np.abs(x - np.array(f["hydrogens"][n])).max() == 0.0
+
+
+def test_frames_match_matlab_golden(golden):
+    """tests/FR3D-Matlab-1GID-rotation-matrices.txt (second witness; inputs have 6 decimals)."""
+    spec = golden("spec_1gid_base.json.gz")
+    mat = golden("matlab_1gid_frames.json.gz")
+    nts = O.build_nts(spec)
+    assert len(nts) == len(mat) == 316
+    for nt, m in zip(nts, mat):
+        assert (nt.chain, nt.sequence, nt.number) == (m["chain"], m["sequence"], m["number"])
+        assert np.abs(nt.base_center - np.array(m["center"])).max() < 1e-6
+        assert np.abs(nt.rotation - np.array(m["rotation"])).max() < 1e-6
+    first = nts[0]
+    assert first.unit_id() == "1GID|1|A|G|103"
+    assert np.allclose(first.base_center, [52.65518173, 52.42990909, 90.244], atol=1e-8)
+
+
+def test_kabsch_known_answers(golden):
+    """tests/superpositions_test.py:11-119 (octahedron 90 deg about z; 45 deg rotations have
+    angle_of_rotation == pi/4) and the reference's outputs on seeded problems."""
+    geo = golden("geometry.json.gz")
+    by = {k["name"]: k for k in geo["kabsch"]}
+    U = O.besttransformation(by["octahedron_90z"]["set1"], by["octahedron_90z"]["set2"])[0]
+    np.testing.assert_almost_equal(U, [[0, 1, 0], [-1, 0, 0], [0, 0, 1]], decimal=7)
+    for ax in "xyz":
+        U = O.besttransformation(by["p4_45" + ax]["set1"], by["p4_45" + ax]["set2"])[0]
+        np.testing.assert_almost_equal(O.angle_of_rotation(U), np.pi / 4, decimal=7)
+    for k in geo["kabsch"]:
+        U, new1, mean1, rmsd, sse, mean2 = O.besttransformation(k["set1"], k["set2"])
+        assert np.abs(U - np.array(k["U"])).max() < 1e-12
+        assert np.abs(new1 - np.array(k["new1"])).max() < 1e-11
+        assert abs(sse - k["sse"]) < 1e-10 and abs(rmsd - k["rmsd"]) < 1e-12
+        Uw, _, _, rmsdw, ssew = O.besttransformation_weighted(k["set1"], k["set2"], k["weights"])
+        assert np.abs(Uw - np.array(k["Uw"])).max() < 1e-12 and abs(ssew - k["ssew"]) < 1e-10
+
+
+def test_discrepancy_known_answers(golden):
+    """tests/discrepancy_tests.py:301-335: 0.9402 and 1.1414 to 3 decimals; assertion behaviour
+    :337-348; nucleotide_superposition_test.py:49-77 sarcin values."""
+    geo = golden("geometry.json.gz")
+    by = {k["name"]: k for k in geo["discrepancy_kats"]}
+
+    def args(k):
+        return ([np.array(c) for c in k["centers1"]], [np.array(r) for r in k["rotations1"]],
+                [np.array(c) for c in k["centers2"]], [np.array(r) for r in k["rotations2"]])
+
+    np.testing.assert_almost_equal(0.9402, O.matrix_discrepancy(*args(by["simple"])), decimal=3)
+    np.testing.assert_almost_equal(1.1414, O.matrix_discrepancy(*args(by["another"])), decimal=3)
+    for k in geo["discrepancy_kats"]:
+        assert abs(O.matrix_discrepancy(*args(k)) - k["d"]) < 1e-13
+    assert abs(by["sarcin7"]["d"] - 0.1159) < 1e-3
+    k = by["simple"]
+    assert O.matrix_discrepancy_cutoff(*args(k), 2.5) == pytest.approx(k["cutoff_2.5"], abs=1e-13)
+    assert O.matrix_discrepancy_cutoff(*args(k), 0.5) is None and k["cutoff_0.5"] is None
+    with pytest.raises(AssertionError):
+        O.matrix_discrepancy([], [], [], [])
+    a = list(args(by["another"]))
+    a[2] = a[2][:-1]
+    a[3] = a[3][:-1]
+    with pytest.raises(AssertionError):
+        O.matrix_discrepancy(*a)
+
+
+def test_all_vs_all_block(golden):
+    av = golden("geometry.json.gz")["all_vs_all"]
+    C, R = np.array(av["centers"]), np.array(av["rotations"])
+    sub = 12
+    D = O.all_vs_all_discrepancy(C[:sub], R[:sub])
+    assert np.abs(D - np.array(av["D"])[:sub, :sub]).max() < 1e-13
+    has = np.ones((sub, av["n"]), dtype=bool)
+    has[:, 0] = False
+    Dn = O.all_vs_all_discrepancy(C[:sub], R[:sub], has)
+    assert np.abs(Dn - np.array(av["D_norot0"])[:sub, :sub]).max() < 1e-13
