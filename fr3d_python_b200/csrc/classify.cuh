@@ -16,10 +16,16 @@
 // (a warp owns one pair), expensive stages (15x15 min distance, gaps) run only
 // when the reference would reach them.
 //
-// Memory: the two nts' base atoms (<= 32 x 3 doubles) are staged in shared
-// memory per warp with coalesced loads (lane k reads atom k's contiguous 24 B),
-// frames are broadcast loads.  Algorithmic traffic per pair (gather model,
-// SURVEY §8(d)): 2 x 760 B nt records + 12 B pair + 32 B hit slot.
+// Memory: per pair the warp stages both nts' frames (24 doubles), base atoms
+// (32 x 3) and backbone atoms (20 x 3) in shared memory with coalesced loads
+// (lane k reads element k's contiguous bytes); every rule then reads shared
+// memory only.  The next pair's indices are prefetched.  Algorithmic traffic
+// per pair (gather model): 2 x 760 B nt records + 12 B pair +
+// 32 B hit slot.  Each rule family starts with a warp vote on a cheap
+// NECESSARY condition (atom over the hull, oxygen inside the slab/disc that
+// contains every ring, donor-oxygen distance below the near cutoff, frame-only
+// coplanarity terms, |z| of the glycosidic displacement), so the expensive
+// reductions run only for pairs that can still produce a label.
 #pragma once
 
 #include "tables.cuh"
@@ -27,28 +33,6 @@
 namespace fr3d {
 
 #define FULL 0xFFFFFFFFu
-
-struct Frame {
-    double c[3];
-    double U[9];   // row major rotation_matrix
-};
-
-__device__ __forceinline__ void load_frame(const fr3d_nts_t &nts, int n, Frame &f) {
-    const double *c = nts.center + (size_t)n * 3;
-    const double *r = nts.rot + (size_t)n * 9;
-    f.c[0] = c[0]; f.c[1] = c[1]; f.c[2] = c[2];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) f.U[k] = r[k];
-}
-
-// translate_rotate_point (NA:1263-1275): (p - centre) . U as a row vector
-__device__ __forceinline__ void to_frame(const Frame &f, double px, double py, double pz, double &x, double &y,
-                                         double &z) {
-    const double v0 = px - f.c[0], v1 = py - f.c[1], v2 = pz - f.c[2];
-    x = v0 * f.U[0] + v1 * f.U[3] + v2 * f.U[6];
-    y = v0 * f.U[1] + v1 * f.U[4] + v2 * f.U[7];
-    z = v0 * f.U[2] + v1 * f.U[5] + v2 * f.U[8];
-}
 
 __device__ __forceinline__ bool left_of(const double *l, double x, double y) { return l[0] * x + l[1] * y + l[2] > 0; }
 
@@ -106,27 +90,57 @@ __device__ __forceinline__ double dist3(const double *a, const double *b) {
     return sqrt(d0 * d0 + d1 * d1 + d2 * d2);
 }
 
-// check_sugar_ribose, NA:2262-2342 (scalar, one lane).  Returns -1 none, 0 cSR, 1 tSR.
-__device__ int sugar_ribose(const fr3d_nts_t &nts, int na, int nb, int parent_a, const Frame &fa) {
-    const uint32_t bba = nts.bb_mask[na], bbb = nts.bb_mask[nb];
-    if (!(bba >> 6 & 1u) || !(bbb >> 6 & 1u)) return -1;            // O2' of both
-    const double *A = nts.bb_xyz + (size_t)na * FR3D_BB_SLOTS * 3;
-    const double *B = nts.bb_xyz + (size_t)nb * FR3D_BB_SLOTS * 3;
-    if (dist3(A + 6 * 3, B + 6 * 3) > 3.8) return -1;
-    const int bs = c_tab.sr_slot[parent_a];
-    if (bs < 0) return -1;
-    if (!(nts.base_mask[na] >> bs & 1u)) return -1;
-    const double *bp = nts.base_xyz + ((size_t)na * FR3D_BASE_SLOTS + bs) * 3;
-    const double d0 = bp[0] - B[18], d1 = bp[1] - B[19], d2 = bp[2] - B[20];
+// Result of check_basepair_cutoffs for one orientation
+struct BpResult {
+    int box;        // -1: no annotation
+    int near;       // bit0: LW gets the "n" prefix, bit1: the box name itself starts with n
+    double cd;      // cutoff_distance
+};
+
+static constexpr int WARPS_PER_BLOCK = 4;
+
+// Per-warp staging area in shared memory: everything the rules read for one pair.
+struct WarpScratch {
+    double fr[24];        // c1[3] U1[9] c2[3] U2[9]
+    double atoms[32][3];  // 0-15: base atoms of nt2, 16-31: base atoms of nt1
+    double bb[20][3];     // 0-9: backbone atoms of nt2, 10-19: backbone atoms of nt1
+    double ang[32];
+    double dst[32];
+};
+
+#define C1(k) (S.fr[(k)])
+#define U1(k) (S.fr[3 + (k)])
+#define C2(k) (S.fr[12 + (k)])
+#define U2(k) (S.fr[15 + (k)])
+
+// (p - c) . U for the frame stored at S.fr[base .. base+11]
+__device__ __forceinline__ void project(const double *fr, double px, double py, double pz, double &x, double &y,
+                                        double &z) {
+    const double v0 = px - fr[0], v1 = py - fr[1], v2 = pz - fr[2];
+    x = v0 * fr[3] + v1 * fr[6] + v2 * fr[9];
+    y = v0 * fr[4] + v1 * fr[7] + v2 * fr[10];
+    z = v0 * fr[5] + v1 * fr[8] + v2 * fr[11];
+}
+
+// check_sugar_ribose, NA:2262-2342, after the shared O2'-O2' screen.  Evaluated by every lane on
+// broadcast shared-memory reads (warp-uniform).  Returns -1 none, 0 cSR, 1 tSR.
+// A / B: backbone blocks of nt_a / nt_b in S.bb; base_pt: N3 / O2 of nt_a; Ua2,5,8: normal of nt_a.
+__device__ __forceinline__ int sugar_ribose_tail(const double (*A)[3], const double (*B)[3], uint32_t bba,
+                                                 uint32_t bbb, bool have_pt, const double *base_pt, double n0,
+                                                 double n1, double n2) {
+    if (!have_pt) return -1;
+    const double d0 = base_pt[0] - B[6][0], d1 = base_pt[1] - B[6][1], d2 = base_pt[2] - B[6][2];
     if (sqrt(d0 * d0 + d1 * d1 + d2 * d2) > 3.8) return -1;
-    const double z = fabs(d0 * fa.U[2] + d1 * fa.U[5] + d2 * fa.U[8]);
-    if (z > 2.0) return -1;
+    if (fabs(d0 * n0 + d1 * n1 + d2 * n2) > 2.0) return -1;
     // torsion C1'(a) C2'(a) C2'(b) C1'(b), NA:2904-2930
     if (!(bba >> 7 & 1u) || !(bba >> 8 & 1u) || !(bbb >> 7 & 1u) || !(bbb >> 8 & 1u)) return -1;
-    const double *p0 = A + 7 * 3, *p1 = A + 8 * 3, *p2 = B + 8 * 3, *p3 = B + 7 * 3;
     double b0[3], b1[3], b2[3];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) { b0[k] = -1.0 * (p1[k] - p0[k]); b1[k] = p2[k] - p1[k]; b2[k] = p3[k] - p2[k]; }
+    for (int k = 0; k < 3; ++k) {
+        b0[k] = -1.0 * (A[8][k] - A[7][k]);
+        b1[k] = B[8][k] - A[8][k];
+        b2[k] = B[7][k] - B[8][k];
+    }
     const double nb1 = sqrt(b1[0] * b1[0] + b1[1] * b1[1] + b1[2] * b1[2]);
     b1[0] /= nb1; b1[1] /= nb1; b1[2] /= nb1;
     const double d01 = b0[0] * b1[0] + b0[1] * b1[1] + b0[2] * b1[2];
@@ -141,69 +155,75 @@ __device__ int sugar_ribose(const fr3d_nts_t &nts, int na, int nb, int parent_a,
     return fabs(angle) > 90.0 ? 0 : 1;
 }
 
-// Result of check_basepair_cutoffs for one orientation
-struct BpResult {
-    int box;        // -1: no annotation
-    int near;       // LW gets the "n" prefix
-    double cd;      // cutoff_distance
-};
-
-static constexpr int WARPS_PER_BLOCK = 4;
-
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32)
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4)
 classify_pairs_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, const int32_t *__restrict__ box_index,
                       const int32_t *__restrict__ pair_i, const int32_t *__restrict__ pair_j,
                       const int32_t *__restrict__ pair_rank, int64_t pair_cap, uint32_t cats,
                       fr3d_hit_t *__restrict__ hits, int64_t hit_cap, int64_t *counters) {
-    __shared__ double s_atoms[WARPS_PER_BLOCK][32][3];   // lanes 0-15: nt2 base atoms, 16-31: nt1 base atoms
-    __shared__ double s_ang[WARPS_PER_BLOCK][32];
-    __shared__ double s_dst[WARPS_PER_BLOCK][32];
+    __shared__ WarpScratch s_scratch[WARPS_PER_BLOCK];
 
     const int lane = threadIdx.x & 31;
-    const int wib = threadIdx.x >> 5;
-    const long long warp0 = (long long)blockIdx.x * WARPS_PER_BLOCK + wib;
+    WarpScratch &S = s_scratch[threadIdx.x >> 5];
+    const long long warp0 = (long long)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
     const long long nwarps = (long long)gridDim.x * WARPS_PER_BLOCK;
     long long n_pairs = counters[0];
     if (n_pairs > pair_cap) n_pairs = pair_cap;
     const int half = lane >> 4;      // 0: atoms of nt2 seen from frame 1, 1: atoms of nt1 seen from frame 2
     const int a = lane & 15;
 
-    for (long long p = warp0; p < n_pairs; p += nwarps) {
-        const int n1 = pair_i[p], n2 = pair_j[p], rank = pair_rank[p];
-        Frame f1, f2;
-        load_frame(nts, n1, f1);
-        load_frame(nts, n2, f2);
-        const int par1 = nts.meta[(size_t)n1 * FR3D_META_INTS], par2 = nts.meta[(size_t)n2 * FR3D_META_INTS];
-        const int fl1 = nts.meta[(size_t)n1 * FR3D_META_INTS + 1], fl2 = nts.meta[(size_t)n2 * FR3D_META_INTS + 1];
-        const uint32_t bm1 = nts.base_mask[n1], bm2 = nts.base_mask[n2];
+    // software prefetch of the next pair's indices
+    int nx1 = 0, nx2 = 0, nxr = 0;
+    if (warp0 < n_pairs) { nx1 = pair_i[warp0]; nx2 = pair_j[warp0]; nxr = pair_rank[warp0]; }
 
-        // ---- stage base atoms: lane -> (own nt, atom a), projected into the OTHER nt's frame
+    for (long long p = warp0; p < n_pairs; p += nwarps) {
+        const int n1 = nx1, n2 = nx2, rank = nxr;
+        if (p + nwarps < n_pairs) { nx1 = pair_i[p + nwarps]; nx2 = pair_j[p + nwarps]; nxr = pair_rank[p + nwarps]; }
+
+        // ---- stage: frames (24 doubles), base atoms (32 x 3), backbone atoms (20 x 3), masks
+        const uint32_t bm1 = nts.base_mask[n1], bm2 = nts.base_mask[n2];
+        const uint32_t bb1 = nts.bb_mask[n1], bb2 = nts.bb_mask[n2];
+        const int par1 = (int)((bm1 >> 16) & 15u) - 1, par2 = (int)((bm2 >> 16) & 15u) - 1;
         const int own = half ? n1 : n2;
-        const uint32_t ownmask = half ? bm1 : bm2;
-        const bool valid = (ownmask >> a) & 1u;
+        const bool valid = ((half ? bm1 : bm2) >> a) & 1u;
         double px = 0, py = 0, pz = 0;
         if (valid) {
             const double *q = nts.base_xyz + ((size_t)own * FR3D_BASE_SLOTS + a) * 3;
             px = q[0]; py = q[1]; pz = q[2];
         }
+        double fv = 0.0;
+        if (lane < 24) {
+            const int n = lane < 12 ? n1 : n2;
+            const int e = lane < 12 ? lane : lane - 12;
+            fv = e < 3 ? nts.center[(size_t)n * 3 + e] : nts.rot[(size_t)n * 9 + (e - 3)];
+        }
+        double bx_ = 0, by_ = 0, bz_ = 0;
+        if (lane < 20) {
+            const int n = lane < 10 ? n2 : n1;
+            const int e = lane < 10 ? lane : lane - 10;
+            if (((lane < 10 ? bb2 : bb1) >> e) & 1u) {
+                const double *q = nts.bb_xyz + ((size_t)n * FR3D_BB_SLOTS + e) * 3;
+                bx_ = q[0]; by_ = q[1]; bz_ = q[2];
+            }
+        }
         __syncwarp();
-        s_atoms[wib][lane][0] = px; s_atoms[wib][lane][1] = py; s_atoms[wib][lane][2] = pz;
+        S.atoms[lane][0] = px; S.atoms[lane][1] = py; S.atoms[lane][2] = pz;
+        if (lane < 24) S.fr[lane] = fv;
+        if (lane < 20) { S.bb[lane][0] = bx_; S.bb[lane][1] = by_; S.bb[lane][2] = bz_; }
         __syncwarp();
-        const Frame &fo = half ? f2 : f1;         // frame the atom is projected into
+
+        const double *fo = half ? &S.fr[12] : &S.fr[0];      // frame the lane's atom is projected into
         const int paro = half ? par2 : par1;
         double x, y, z;
-        to_frame(fo, px, py, pz, x, y, z);
-        // squared distance to the other base centre (for calculate_basepair_gap's argsort)
-        const double d2c = valid ? ((px - fo.c[0]) * (px - fo.c[0]) + (py - fo.c[1]) * (py - fo.c[1]) +
-                                    (pz - fo.c[2]) * (pz - fo.c[2]))
-                                 : 1e300;
+        project(fo, px, py, pz, x, y, z);
 
         // lazily computed, shared by coplanar and both basepair orientations
         bool have_gaps = false, have_mind = false;
         double gap12 = 100.0, gap21 = 100.0, mind = 9999.0;
 
         auto compute_gaps = [&]() {               // calculate_basepair_gap, NA:2189-2259, both directions
-            double key = d2c;
+            // squared distance to the other base centre orders the atoms like the reference's argsort
+            double key = valid ? ((px - fo[0]) * (px - fo[0]) + (py - fo[1]) * (py - fo[1]) +
+                                  (pz - fo[2]) * (pz - fo[2])) : 1e300;
             double g = 100.0;
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
@@ -222,14 +242,14 @@ classify_pairs_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, cons
         auto compute_mind = [&]() {               // calculate_base_min_distances, NA:1799-1829
             // lower half: nt2 atom `a` against nt1 atoms 0-7; upper half: nt2 atom `a` against nt1 atoms 8-15
             const bool v2 = (bm2 >> a) & 1u;
-            const double qx = s_atoms[wib][a][0], qy = s_atoms[wib][a][1], qz = s_atoms[wib][a][2];
+            const double qx = S.atoms[a][0], qy = S.atoms[a][1], qz = S.atoms[a][2];
             double best = 1e300;
 #pragma unroll
             for (int s = 0; s < 8; ++s) {
                 const int k1 = s + 8 * half;
                 if (v2 && ((bm1 >> k1) & 1u)) {
-                    const double dx = s_atoms[wib][16 + k1][0] - qx, dy = s_atoms[wib][16 + k1][1] - qy,
-                                 dz = s_atoms[wib][16 + k1][2] - qz;
+                    const double dx = S.atoms[16 + k1][0] - qx, dy = S.atoms[16 + k1][1] - qy,
+                                 dz = S.atoms[16 + k1][2] - qz;
                     best = fmin(best, dx * dx + dy * dy + dz * dz);
                 }
             }
@@ -238,315 +258,332 @@ classify_pairs_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, cons
             have_mind = true;
         };
 
-        // decisions for the nine hit slots (warp-uniform)
-        int h_valid[9], h_code[9];
-#pragma unroll
-        for (int k = 0; k < 9; ++k) { h_valid[k] = 0; h_code[k] = 0; }
+        // decisions for the nine hit slots (warp-uniform): bit s of hmask, code in hcode[s]
+        unsigned hmask = 0;
+        int c_so12 = 0, c_so21 = 0, c_stack = 0, c_sr12 = 0, c_sr21 = 0, c_bph = 0, c_br = 0, c_bp = 0;
         int bp_box = 0;
         double bp_cd = 0.0, bp_gap = 0.0;
 
         // ================= base-oxygen stacking, both directions (NA:758-778) =================
         if (cats & FR3D_CAT_SO) {
-            // group g = lane>>3 (0: base nt1 / oxygens nt2, 1: base nt2 / oxygens nt1), o = lane&7 < 6
+            // group g (0: base nt1 / oxygens nt2, 1: base nt2 / oxygens nt1), o = lane&7 < 6
             const int g = (lane >> 3) & 1, o = lane & 7;
             const bool act = lane < 16 && o < 6;
-            const int nb = g ? n2 : n1;            // base owner
-            const int no = g ? n1 : n2;            // oxygen owner
-            const Frame &fb = g ? f2 : f1;
             const int pb = g ? par2 : par1;
             // oxygens O2' O3' O4' O5' OP1 OP2 (NA:1290) -> backbone slots 6 5 4 3 1 2
-            const int oslot = (o == 0) ? 6 : (o == 1) ? 5 : (o == 2) ? 4 : (o == 3) ? 3 : (o == 4) ? 1 : 2;
-            bool present = false;
+            const int oslot = (0x213456 >> (4 * o)) & 7;
+            const bool present = act && (((g ? bb1 : bb2) >> oslot) & 1u);
             double ox = 0, oy = 0, oz = 0;
-            if (act && (nts.bb_mask[no] >> oslot & 1u)) {
-                const double *q = nts.bb_xyz + ((size_t)no * FR3D_BB_SLOTS + oslot) * 3;
-                to_frame(fb, q[0], q[1], q[2], ox, oy, oz);
-                present = true;
-            }
-            bool ring = false;
+            const double *ob = S.bb[(g ? 10 : 0) + (act ? oslot : 0)];
+            project(g ? &S.fr[12] : &S.fr[0], ob[0], ob[1], ob[2], ox, oy, oz);
             const bool has_tab = pb >= 0 && pb < FR3D_N_PARENTS;
-            if (present && has_tab && !(fabs(oz) < 2.0) && fabs(oz) < 3.6) {
-                if (c_tab.has_div[pb]) {
-                    if (left_of(c_tab.ring_div[pb], ox, oy)) {
-                        ring = true;
+            // every ring and near-ring ellipse lies inside the disc x^2 + y^2 < 25 (tests/test_abi.py checks
+            // the tables), so an oxygen outside the slab |z| < 3.6 or the disc cannot score
+            const bool maybe = present && has_tab && fabs(oz) < 3.6 && (ox * ox + oy * oy) < 25.0;
+            if (__any_sync(FULL, maybe)) {
+                bool ring = false;
+                if (maybe && !(fabs(oz) < 2.0)) {
+                    if (c_tab.has_div[pb]) {
+                        if (left_of(c_tab.ring_div[pb], ox, oy)) {
+                            ring = true;
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) ring = ring && left_of(c_tab.ring5[pb][k], ox, oy);
+                            for (int k = 0; k < 4; ++k) ring = ring && left_of(c_tab.ring5[pb][k], ox, oy);
+                        } else {
+                            ring = true;
+#pragma unroll
+                            for (int k = 0; k < 6; ++k) ring = ring && left_of(c_tab.ring6[pb][k], ox, oy);
+                        }
                     } else {
                         ring = true;
 #pragma unroll
                         for (int k = 0; k < 6; ++k) ring = ring && left_of(c_tab.ring6[pb][k], ox, oy);
                     }
-                } else {
-                    ring = true;
-#pragma unroll
-                    for (int k = 0; k < 6; ++k) ring = ring && left_of(c_tab.ring6[pb][k], ox, oy);
                 }
-            }
-            const unsigned ring_b = __ballot_sync(FULL, ring);
-            const unsigned true_b = __ballot_sync(FULL, ring && fabs(oz) < 3.5);
-            const unsigned gmask = 0xFFu << (g * 8);
-            double key = ring ? fabs(oz) : 1e300;
-            int idx = o;
-            group_argmin<8>(key, idx);
-            // over a ring: true if any |z| < 3.5, else near (NA:1386-1400)
-            const double zsel_ring = __shfl_sync(FULL, oz, (lane & ~7) | idx);
-            // near-ring ellipses, used only when no oxygen is over a ring (NA:1402-1459)
-            bool nr = false;
-            if (present && has_tab && fabs(oz) < 3.5) {
-                if (c_tab.has_div[pb]) {
-                    if (left_of(c_tab.ring_div[pb], ox, oy)) nr = in_ellipse(c_tab.ell5[pb], ox, oy);
-                    else nr = in_ellipse(c_tab.ell6[pb], ox, oy);
-                } else {
-                    nr = in_ellipse(c_tab.ell6[pb], ox, oy);
+                const unsigned ring_b = __ballot_sync(FULL, ring);
+                const unsigned true_b = __ballot_sync(FULL, ring && fabs(oz) < 3.5);
+                const unsigned gmask = 0xFFu << (g * 8);
+                double key = ring ? fabs(oz) : 1e300;
+                int idx = o;
+                group_argmin<8>(key, idx);
+                // over a ring: true if any |z| < 3.5, else near (NA:1386-1400)
+                const double zsel_ring = __shfl_sync(FULL, oz, (lane & ~7) | idx);
+                // near-ring ellipses, used only when no oxygen is over a ring (NA:1402-1459)
+                bool nr = false;
+                if (maybe && fabs(oz) < 3.5) {
+                    if (c_tab.has_div[pb]) {
+                        if (left_of(c_tab.ring_div[pb], ox, oy)) nr = in_ellipse(c_tab.ell5[pb], ox, oy);
+                        else nr = in_ellipse(c_tab.ell6[pb], ox, oy);
+                    } else {
+                        nr = in_ellipse(c_tab.ell6[pb], ox, oy);
+                    }
                 }
+                double k2 = nr ? (ox * ox + oy * oy) : 1e300;
+                int i2 = o;
+                group_argmin<8>(k2, i2);
+                const double zsel_near = __shfl_sync(FULL, oz, (lane & ~7) | i2);
+                int code = -1;
+                if (ring_b & gmask) code = idx | ((zsel_ring > 0) ? 0 : 8) | ((true_b & gmask) ? 0 : 16);
+                else if (k2 < 1e299) code = i2 | ((zsel_near > 0) ? 0 : 8) | 16;
+                const int code12 = __shfl_sync(FULL, code, 0);
+                const int code21 = __shfl_sync(FULL, code, 8);
+                if (code12 >= 0) { hmask |= 1u << FR3D_SLOT_SO12; c_so12 = code12; }
+                if (code21 >= 0) { hmask |= 1u << FR3D_SLOT_SO21; c_so21 = code21; }
             }
-            double k2 = nr ? (ox * ox + oy * oy) : 1e300;
-            int i2 = o;
-            group_argmin<8>(k2, i2);
-            const double zsel_near = __shfl_sync(FULL, oz, (lane & ~7) | i2);
-            int code = -1;
-            if (ring_b & gmask) code = idx | ((zsel_ring > 0) ? 0 : 8) | ((true_b & gmask) ? 0 : 16);
-            else if (k2 < 1e299) code = i2 | ((zsel_near > 0) ? 0 : 8) | 16;
-            const int code12 = __shfl_sync(FULL, code, 0);
-            const int code21 = __shfl_sync(FULL, code, 8);
-            if (code12 >= 0) { h_valid[FR3D_SLOT_SO12] = 1; h_code[FR3D_SLOT_SO12] = code12; }
-            if (code21 >= 0) { h_valid[FR3D_SLOT_SO21] = 1; h_code[FR3D_SLOT_SO21] = code21; }
         }
 
         // ================= base-base stacking (NA:1602-1739) =================
         if ((cats & FR3D_CAT_STACKING) && par1 >= 0 && par2 >= 0) {
             const bool inside = valid && in_hull(paro, x, y, z);
             const unsigned in_b = __ballot_sync(FULL, inside);
-            const double zmin = group_min<16>(valid ? z : 1e300);
-            const double zmax = group_max<16>(valid ? z : -1e300);
-            double key = valid ? fabs(z) : 1e300;
-            int idx = a;
-            group_argmin<16>(key, idx);
-            const double zsel = __shfl_sync(FULL, z, (lane & 16) | idx);
-            const unsigned hmask = 0xFFFFu << (half * 16);
-            const bool ov = (in_b & hmask) && !(zmax > 0 && zmin < 0);       // return_overlap, NA:1567-1571
-            const bool nt2on1 = __shfl_sync(FULL, (int)ov, 0);
-            const bool nt1on2 = __shfl_sync(FULL, (int)ov, 16);
-            const double z_2on1 = __shfl_sync(FULL, zsel, 0);
-            const double z_1on2 = __shfl_sync(FULL, zsel, 16);
-            if (nt2on1 || nt1on2) {
-                const double normal_Z = f1.U[2] * f2.U[2] + f1.U[5] * f2.U[5] + f1.U[8] * f2.U[8];
-                const bool reverse = nt1on2 && !nt2on1;                        // NA:1663-1667
-                const double mvd = reverse ? z_1on2 : z_2on1;
-                int code = -1;                                                 // 0 s35 1 s53 2 s33 3 s55
-                if (mvd > 0) { if (normal_Z > 0) code = 0; else if (normal_Z < 0) code = 2; }
-                else if (mvd < 0) { if (normal_Z > 0) code = 1; else if (normal_Z < 0) code = 3; }
-                if (reverse && code >= 0 && code < 2) code ^= 1;              // swap s35 <-> s53 (NA:1699-1702)
-                compute_mind();
-                int near = 1;
-                if (fabs(mind) < 4.0 && fabs(mind) > 1.0 && fabs(normal_Z) > 0.6 && nt2on1 && nt1on2) near = 0;
-                if (fabs(mind) < 1.0 || fabs(normal_Z) < 0.5) code = -1;       // NA:1717
-                if (code >= 0) { h_valid[FR3D_SLOT_STACK] = 1; h_code[FR3D_SLOT_STACK] = code | (near << 2); }
+            if (in_b) {                            // no atom over the other base: no overlap either way
+                const double zmin = group_min<16>(valid ? z : 1e300);
+                const double zmax = group_max<16>(valid ? z : -1e300);
+                double key = valid ? fabs(z) : 1e300;
+                int idx = a;
+                group_argmin<16>(key, idx);
+                const double zsel = __shfl_sync(FULL, z, (lane & 16) | idx);
+                const unsigned hm = 0xFFFFu << (half * 16);
+                const bool ov = (in_b & hm) && !(zmax > 0 && zmin < 0);       // return_overlap, NA:1567-1571
+                const bool nt2on1 = __shfl_sync(FULL, (int)ov, 0);
+                const bool nt1on2 = __shfl_sync(FULL, (int)ov, 16);
+                const double z_2on1 = __shfl_sync(FULL, zsel, 0);
+                const double z_1on2 = __shfl_sync(FULL, zsel, 16);
+                if (nt2on1 || nt1on2) {
+                    const double normal_Z = U1(2) * U2(2) + U1(5) * U2(5) + U1(8) * U2(8);
+                    const bool reverse = nt1on2 && !nt2on1;                        // NA:1663-1667
+                    const double mvd = reverse ? z_1on2 : z_2on1;
+                    int code = -1;                                                 // 0 s35 1 s53 2 s33 3 s55
+                    if (mvd > 0) { if (normal_Z > 0) code = 0; else if (normal_Z < 0) code = 2; }
+                    else if (mvd < 0) { if (normal_Z > 0) code = 1; else if (normal_Z < 0) code = 3; }
+                    if (reverse && code >= 0 && code < 2) code ^= 1;              // swap s35 <-> s53 (NA:1699-1702)
+                    if (fabs(normal_Z) < 0.5) code = -1;                           // NA:1717 (cheap half first)
+                    if (code >= 0) {
+                        compute_mind();
+                        int near = 1;
+                        if (fabs(mind) < 4.0 && fabs(mind) > 1.0 && fabs(normal_Z) > 0.6 && nt2on1 && nt1on2) near = 0;
+                        if (fabs(mind) < 1.0) code = -1;                           // NA:1717
+                        if (code >= 0) { hmask |= 1u << FR3D_SLOT_STACK; c_stack = code | (near << 2); }
+                    }
+                }
             }
         }
 
         // ================= sugar-ribose, both directions (NA:791-804) =================
-        if ((cats & FR3D_CAT_SUGAR_RIBOSE) && par1 >= 0 && par2 >= 0 && par1 != 4 && par2 != 4) {
-            int r = -1;
-            if (lane == 0) r = sugar_ribose(nts, n1, n2, par1, f1);
-            else if (lane == 1) r = sugar_ribose(nts, n2, n1, par2, f2);
-            const int r12 = __shfl_sync(FULL, r, 0), r21 = __shfl_sync(FULL, r, 1);
-            if (r12 >= 0) { h_valid[FR3D_SLOT_SR12] = 1; h_code[FR3D_SLOT_SR12] = r12; }
-            if (r21 >= 0) { h_valid[FR3D_SLOT_SR21] = 1; h_code[FR3D_SLOT_SR21] = r21; }
+        if ((cats & FR3D_CAT_SUGAR_RIBOSE) && par1 >= 0 && par2 >= 0 && par1 != 4 && par2 != 4 &&
+            (bb1 >> 6 & 1u) && (bb2 >> 6 & 1u)) {
+            // both directions start with the same O2'-O2' distance screen (NA:2281-2286)
+            const double e0 = S.bb[16][0] - S.bb[6][0], e1 = S.bb[16][1] - S.bb[6][1], e2 = S.bb[16][2] - S.bb[6][2];
+            if (!(sqrt(e0 * e0 + e1 * e1 + e2 * e2) > 3.8)) {
+                const int s1 = c_tab.sr_slot[par1], s2 = c_tab.sr_slot[par2];
+                const int r12 = sugar_ribose_tail(&S.bb[10], &S.bb[0], bb1, bb2, s1 >= 0 && ((bm1 >> s1) & 1u),
+                                                  S.atoms[16 + (s1 < 0 ? 0 : s1)], U1(2), U1(5), U1(8));
+                const int r21 = sugar_ribose_tail(&S.bb[0], &S.bb[10], bb2, bb1, s2 >= 0 && ((bm2 >> s2) & 1u),
+                                                  S.atoms[s2 < 0 ? 0 : s2], U2(2), U2(5), U2(8));
+                if (r12 >= 0) { hmask |= 1u << FR3D_SLOT_SR12; c_sr12 = r12; }
+                if (r21 >= 0) { hmask |= 1u << FR3D_SLOT_SR21; c_sr21 = r21; }
+            }
         }
 
         // ================= base-phosphate / base-ribose, nt1 base -> nt2 backbone (NA:807-829) =================
         if ((cats & FR3D_CAT_BACKBONE) && par1 >= 0) {
             const int site = lane / 6, ok = lane - site * 6;    // ok: 0 O5' 1 OP1 2 OP2 3 prevO3' | 4 O2' 5 O4'
             const int nsites = c_tab.n_sites[par1];
-            const uint32_t bb2 = nts.bb_mask[n2];
-            const double *B = nts.bb_xyz + (size_t)n2 * FR3D_BB_SLOTS * 3;
             double ang = 0.0, dst = 0.0;
+            bool cand = false;
+            int hs = 0, ms = 0, oslot = 0;
             if (lane < 30 && site < nsites) {
-                const int oslot = (ok == 0) ? 3 : (ok == 1) ? 1 : (ok == 2) ? 2 : (ok == 3) ? 9 : (ok == 4) ? 6 : 4;
-                const int hs = c_tab.site_h[par1][site], ms = c_tab.site_m[par1][site];
+                oslot = (0x469213 >> (4 * ok)) & 15;            // backbone slots 3 1 2 9 6 4
+                hs = c_tab.site_h[par1][site];
+                ms = c_tab.site_m[par1][site];
                 if ((bb2 >> oslot & 1u) && (bm1 >> hs & 1u) && (bm1 >> ms & 1u)) {
-                    const double *O = B + oslot * 3;
+                    const double *O = S.bb[oslot];
                     if (O[0] != 0.0 || O[1] != 0.0 || O[2] != 0.0) {            // .any(), NA:1939,1959
-                        const double *H = nts.base_xyz + ((size_t)n1 * FR3D_BASE_SLOTS + hs) * 3;
-                        const double *Mv = nts.base_xyz + ((size_t)n1 * FR3D_BASE_SLOTS + ms) * 3;
-                        ang = hb_angle(Mv, H, O);
-                        dst = dist3(Mv, O);
+                        dst = dist3(S.atoms[16 + ms], O);
+                        // every true / near label needs distance < nCutoff (4.5 carbon, 4.0 nitrogen)
+                        cand = dst < (c_tab.site_carbon[par1][site] == 0 ? 4.0 : 4.5);
                     }
                 }
             }
-            __syncwarp();
-            s_ang[wib][lane] = ang; s_dst[wib][lane] = dst;
-            __syncwarp();
-            int bph = -1, br = -1;
-            if (lane == 0) {
-                // if nt2 has a P atom far from the plane of base 1, no BPh (NA:1915-1921)
-                bool use_ph = true;
-                if (bb2 & 1u) {
-                    if (B[0] != 0.0 || B[1] != 0.0 || B[2] != 0.0) {
-                        double tx, ty, tz;
-                        to_frame(f1, B[0], B[1], B[2], tx, ty, tz);
-                        if (fabs(tz) > 4.5) use_ph = false;
+            if (__any_sync(FULL, cand)) {
+                if (cand) ang = hb_angle(S.atoms[16 + ms], S.atoms[16 + hs], S.bb[oslot]);
+                else dst = 0.0;                    // not a candidate: the state machine skips it
+                __syncwarp();
+                S.ang[lane] = ang; S.dst[lane] = dst;
+                __syncwarp();
+                int bph = -1, br = -1;
+                if (lane == 0) {
+                    // if nt2 has a P atom far from the plane of base 1, no BPh (NA:1915-1921)
+                    bool use_ph = true;
+                    if (bb2 & 1u) {
+                        const double *P = S.bb[0];
+                        if (P[0] != 0.0 || P[1] != 0.0 || P[2] != 0.0) {
+                            double tx, ty, tz;
+                            project(&S.fr[0], P[0], P[1], P[2], tx, ty, tz);
+                            if (fabs(tz) > 4.5) use_ph = false;
+                        }
                     }
-                }
-                int n_true = 0, n_near = 0, n_keys = 0;
-                unsigned long long site_ox = 0;        // 4 bits of oxygen indices per label digit
-                double best_tq = -1e300, best_nq = -1e300;
-                int best_tl = -1, best_nl = -1, first_tl = -1, first_nl = -1;
-                int rt = 0, rn = 0, best_rtl = -1, best_rnl = -1, first_rtl = -1, first_rnl = -1;
-                double best_rtq = -1e300, best_rnq = -1e300;
-                double cutoff = 0.0, ncutoff = 0.0;
-                for (int s = 0; s < nsites; ++s) {
-                    const int carbon = c_tab.site_carbon[par1][s];
-                    const int digit = c_tab.site_digit[par1][s];
-                    if (carbon == 1) { cutoff = 4.0; ncutoff = 4.5; }          // NA:1930-1935
-                    else if (carbon == 0) { cutoff = 3.5; ncutoff = 4.0; }
-                    if (use_ph) {
-                        for (int i = 0; i < 4; ++i) {
-                            const double an = s_ang[wib][s * 6 + i], ds = s_dst[wib][s * 6 + i];
-                            if (an != 0.0 && ds != 0.0) {                      // `if phosphateAngle:` / `if phosphateDistance:`
-                                if (an > 130.0 && ds < cutoff) {
-                                    const double q = (cutoff - ds) + (an - 130.0) / 20.0;
-                                    if (n_true == 0) first_tl = digit;
-                                    ++n_true;
-                                    if (q > best_tq || (q == best_tq && digit < best_tl)) { best_tq = q; best_tl = digit; }
-                                    if (!((site_ox >> (digit * 4)) & 0xFull)) ++n_keys;
-                                    site_ox |= 1ull << (digit * 4 + i);
-                                } else if (an > 110.0 && ds < ncutoff) {
-                                    const double q = (ncutoff - ds) + (an - 110.0) / 20.0;
-                                    if (n_near == 0) first_nl = digit;
-                                    ++n_near;
-                                    if (q > best_nq || (q == best_nq && digit < best_nl)) { best_nq = q; best_nl = digit; }
+                    int n_true = 0, n_near = 0, n_keys = 0;
+                    unsigned long long site_ox = 0;        // 4 bits of oxygen indices per label digit
+                    double best_tq = -1e300, best_nq = -1e300;
+                    int best_tl = -1, best_nl = -1, first_tl = -1, first_nl = -1;
+                    int rt = 0, rn = 0, best_rtl = -1, best_rnl = -1, first_rtl = -1, first_rnl = -1;
+                    double best_rtq = -1e300, best_rnq = -1e300;
+                    double cutoff = 0.0, ncutoff = 0.0;
+                    for (int s = 0; s < nsites; ++s) {
+                        const int carbon = c_tab.site_carbon[par1][s];
+                        const int digit = c_tab.site_digit[par1][s];
+                        if (carbon == 1) { cutoff = 4.0; ncutoff = 4.5; }          // NA:1930-1935
+                        else if (carbon == 0) { cutoff = 3.5; ncutoff = 4.0; }
+                        if (use_ph) {
+                            for (int i = 0; i < 4; ++i) {
+                                const double an = S.ang[s * 6 + i], ds = S.dst[s * 6 + i];
+                                if (an != 0.0 && ds != 0.0) {              // `if phosphateAngle:` / `if phosphateDistance:`
+                                    if (an > 130.0 && ds < cutoff) {
+                                        const double q = (cutoff - ds) + (an - 130.0) / 20.0;
+                                        if (n_true == 0) first_tl = digit;
+                                        ++n_true;
+                                        if (q > best_tq || (q == best_tq && digit < best_tl)) { best_tq = q; best_tl = digit; }
+                                        if (!((site_ox >> (digit * 4)) & 0xFull)) ++n_keys;
+                                        site_ox |= 1ull << (digit * 4 + i);
+                                    } else if (an > 110.0 && ds < ncutoff) {
+                                        const double q = (ncutoff - ds) + (an - 110.0) / 20.0;
+                                        if (n_near == 0) first_nl = digit;
+                                        ++n_near;
+                                        if (q > best_nq || (q == best_nq && digit < best_nl)) { best_nq = q; best_nl = digit; }
+                                    }
                                 }
                             }
                         }
-                    }
-                    for (int i = 4; i < 6; ++i) {
-                        const double an = s_ang[wib][s * 6 + i], ds = s_dst[wib][s * 6 + i];
-                        if (an != 0.0 && ds != 0.0) {
-                            if (an > 130.0 && ds < cutoff) {
-                                const double q = (cutoff - ds) + (an - 130.0) / 20.0;
-                                if (rt == 0) first_rtl = digit;
-                                ++rt;
-                                if (q > best_rtq || (q == best_rtq && digit < best_rtl)) { best_rtq = q; best_rtl = digit; }
-                            } else if (an > 110.0 && ds < ncutoff) {
-                                const double q = (ncutoff - ds) + (an - 110.0) / 20.0;
-                                if (rn == 0) first_rnl = digit;
-                                ++rn;
-                                if (q > best_rnq || (q == best_rnq && digit < best_rnl)) { best_rnq = q; best_rnl = digit; }
+                        for (int i = 4; i < 6; ++i) {
+                            const double an = S.ang[s * 6 + i], ds = S.dst[s * 6 + i];
+                            if (an != 0.0 && ds != 0.0) {
+                                if (an > 130.0 && ds < cutoff) {
+                                    const double q = (cutoff - ds) + (an - 130.0) / 20.0;
+                                    if (rt == 0) first_rtl = digit;
+                                    ++rt;
+                                    if (q > best_rtq || (q == best_rtq && digit < best_rtl)) { best_rtq = q; best_rtl = digit; }
+                                } else if (an > 110.0 && ds < ncutoff) {
+                                    const double q = (ncutoff - ds) + (an - 110.0) / 20.0;
+                                    if (rn == 0) first_rnl = digit;
+                                    ++rn;
+                                    if (q > best_rnq || (q == best_rnq && digit < best_rnl)) { best_rnq = q; best_rnl = digit; }
+                                }
                             }
                         }
+                        // record the best phosphate interaction: sticky, evaluated after EVERY site (NA:1973-2003)
+                        if (n_true == 1) {
+                            bph = first_tl;
+                        } else if (n_keys > 1) {
+                            const unsigned o7 = (site_ox >> 28) & 0xF, o9 = (site_ox >> 36) & 0xF;
+                            const unsigned o3 = (site_ox >> 12) & 0xF, o5 = (site_ox >> 20) & 0xF;
+                            if (o7 && o9) { if (__popc(o7 | o9) > 1) bph = 8; }
+                            else if (o3 && o5) { if (__popc(o3 | o5) > 1) bph = 4; }
+                            if (bph < 0) bph = best_tl;
+                        } else if (n_true > 1) {
+                            bph = best_tl;
+                        } else if (n_near == 1) {
+                            bph = first_nl | 16;
+                        } else if (n_near > 1) {
+                            bph = best_nl | 16;
+                        }
+                        // best ribose interaction (NA:2005-2019)
+                        if (rt == 1) br = first_rtl;
+                        else if (rt > 1) br = best_rtl;
+                        else if (rn == 1) br = first_rnl | 16;
+                        else if (rn > 1) br = best_rnl | 16;
                     }
-                    // record the best phosphate interaction: sticky, evaluated after EVERY site (NA:1973-2003)
-                    if (n_true == 1) {
-                        bph = first_tl;
-                    } else if (n_keys > 1) {
-                        const unsigned o7 = (site_ox >> 28) & 0xF, o9 = (site_ox >> 36) & 0xF;
-                        const unsigned o3 = (site_ox >> 12) & 0xF, o5 = (site_ox >> 20) & 0xF;
-                        if (o7 && o9) { if (__popc(o7 | o9) > 1) bph = 8; }
-                        else if (o3 && o5) { if (__popc(o3 | o5) > 1) bph = 4; }
-                        if (bph < 0) bph = best_tl;
-                    } else if (n_true > 1) {
-                        bph = best_tl;
-                    } else if (n_near == 1) {
-                        bph = first_nl | 16;
-                    } else if (n_near > 1) {
-                        bph = best_nl | 16;
-                    }
-                    // best ribose interaction (NA:2005-2019)
-                    if (rt == 1) br = first_rtl;
-                    else if (rt > 1) br = best_rtl;
-                    else if (rn == 1) br = first_rnl | 16;
-                    else if (rn > 1) br = best_rnl | 16;
                 }
+                bph = __shfl_sync(FULL, bph, 0);
+                br = __shfl_sync(FULL, br, 0);
+                if (bph >= 0) { hmask |= 1u << FR3D_SLOT_BPH; c_bph = bph; }
+                if (br >= 0) { hmask |= 1u << FR3D_SLOT_BR; c_br = br; }
             }
-            bph = __shfl_sync(FULL, bph, 0);
-            br = __shfl_sync(FULL, br, 0);
-            if (bph >= 0) { h_valid[FR3D_SLOT_BPH] = 1; h_code[FR3D_SLOT_BPH] = bph; }
-            if (br >= 0) { h_valid[FR3D_SLOT_BR] = 1; h_code[FR3D_SLOT_BR] = br; }
         }
 
         // ================= coplanar + basepair, orientation 12 then 21 (NA:834-1013) =================
         const bool gly_ok = (bm1 & 1u) && (bm2 & 1u) && par1 >= 0 && par2 >= 0;   // NA:674, 834-837
         if (gly_ok) {
-            const double *g1 = nts.base_xyz + (size_t)n1 * FR3D_BASE_SLOTS * 3;    // slot 0 = N9 / N1
-            const double *g2 = nts.base_xyz + (size_t)n2 * FR3D_BASE_SLOTS * 3;
-            const double gd0 = g2[0] - g1[0], gd1 = g2[1] - g1[1], gd2 = g2[2] - g1[2];
+            // glycosidic displacement: slot 0 = N9 / N1
+            const double gd0 = S.atoms[0][0] - S.atoms[16][0], gd1 = S.atoms[0][1] - S.atoms[16][1],
+                         gd2 = S.atoms[0][2] - S.atoms[16][2];
+            const double nZ = U1(2) * U2(2) + U1(5) * U2(5) + U1(8) * U2(8);       // M[2][2], both orientations
             BpResult res[2];
             bool marked_cp = false;
+            // check_coplanar (NA:2051-2186) is a conjunction; the frame-only conditions (:2098-2113) are
+            // evaluated first, the gap / min-distance ones only for pairs that pass them.  dot1 and dot2
+            // swap roles between the orientations and dot3 is symmetric, so one evaluation serves both.
+            bool cp_frames = false;
+            if (cats & FR3D_CAT_COPLANAR) {
+                double e0 = C1(0) - C2(0), e1 = C1(1) - C2(1), e2 = C1(2) - C2(2);
+                const double en = sqrt(e0 * e0 + e1 * e1 + e2 * e2);
+                e0 /= en; e1 /= en; e2 /= en;
+                const double dot1 = fabs(e0 * U1(2) + e1 * U1(5) + e2 * U1(8));
+                const double dot2 = fabs(e0 * U2(2) + e1 * U2(5) + e2 * U2(8));
+                cp_frames = dot1 < 0.3381 && dot2 < 0.3381 && fabs(nZ) > 0.7757;
+            }
 #pragma unroll
             for (int ori = 0; ori < 2; ++ori) {
                 res[ori].box = -1; res[ori].near = 0; res[ori].cd = 0.0;
                 const int pa = ori ? par2 : par1, pb = ori ? par1 : par2;
                 const int combo = pa * FR3D_N_PARENTS + pb;
                 if (!c_tab.combo_ok[combo]) continue;                              // NA:842 / 894
-                const Frame &fa = ori ? f2 : f1;
-                const Frame &fb = ori ? f1 : f2;
+                const double *Ua = ori ? &S.fr[15] : &S.fr[3];
+                const double *Ub = ori ? &S.fr[3] : &S.fr[15];
                 const double s = ori ? -1.0 : 1.0;
                 const double v0 = s * gd0, v1 = s * gd1, v2 = s * gd2;            // glycosidic_displacement
-                const double dX = v0 * fa.U[0] + v1 * fa.U[3] + v2 * fa.U[6];      // displ12 (NA:847)
-                const double dY = v0 * fa.U[1] + v1 * fa.U[4] + v2 * fa.U[7];
-                const double dZ = v0 * fa.U[2] + v1 * fa.U[5] + v2 * fa.U[8];
+                const double dZ = v0 * Ua[2] + v1 * Ua[5] + v2 * Ua[8];            // displ12[2] (NA:847)
 
-                if (cats & FR3D_CAT_COPLANAR) {                                    // check_coplanar, NA:2051-2186
+                if (cp_frames && !marked_cp) {                                     // remaining coplanar conditions
                     if (!have_gaps) compute_gaps();
                     const double gab = ori ? gap21 : gap12;
-                    bool cp = false;
                     if (gab < 1.5179) {
                         if (!have_mind) compute_mind();
-                        const bool both_std = (fl1 & FR3D_FLAG_STD_RNA) && (fl2 & FR3D_FLAG_STD_RNA);
+                        const bool both_std = (bm1 >> 20 & 1u) && (bm2 >> 20 & 1u);
                         if (mind < 3.4589 && !(mind >= 2.4589 && both_std)) {
-                            double e0 = fa.c[0] - fb.c[0], e1 = fa.c[1] - fb.c[1], e2 = fa.c[2] - fb.c[2];
-                            const double en = sqrt(e0 * e0 + e1 * e1 + e2 * e2);
-                            e0 /= en; e1 /= en; e2 /= en;
-                            const double dot1 = fabs(e0 * fa.U[2] + e1 * fa.U[5] + e2 * fa.U[8]);
-                            if (dot1 < 0.3381) {
-                                const double dot2 = fabs(e0 * fb.U[2] + e1 * fb.U[5] + e2 * fb.U[8]);
-                                if (dot2 < 0.3381) {
-                                    const double dot3 = fabs(fa.U[2] * fb.U[2] + fa.U[5] * fb.U[5] + fa.U[8] * fb.U[8]);
-                                    if (dot3 > 0.7757) cp = true;
-                                }
-                            }
+                            hmask |= 1u << FR3D_SLOT_CP;
+                            marked_cp = true;
                         }
                     }
-                    if (cp && !marked_cp) { h_valid[FR3D_SLOT_CP] = 1; marked_cp = true; }
                 }
 
                 // ---- check_basepair_cutoffs, NA:2364-2759 (datapoint = None)
                 if (fabs(dZ) > 3.6) continue;                                      // NA:2380
-                const double nZ = fa.U[2] * fb.U[2] + fa.U[5] * fb.U[5] + fa.U[8] * fb.U[8];   // M[2][2]
+                const double dX = v0 * Ua[0] + v1 * Ua[3] + v2 * Ua[6];
+                const double dY = v0 * Ua[1] + v1 * Ua[4] + v2 * Ua[7];
                 const int sg = nZ > 0 ? 0 : 1;
                 const int bstart = box_index[(combo * 2 + sg) * 2 + 0];
                 const int bcount = box_index[(combo * 2 + sg) * 2 + 1];
                 if (bcount <= 0) continue;
                 const bool mine = lane < bcount;
+                const fr3d_box_t *bx = boxes + bstart + (mine ? lane : 0);
                 double cd = 1e300;
-                fr3d_box_t bx;
+                int flags = 0;
                 if (mine) {
-                    bx = boxes[bstart + lane];
+                    flags = bx->flags;
                     cd = 0.0;
-                    cd += fmax(0.0, bx.xmin - dX);
-                    cd += fmax(0.0, dX - bx.xmax);
-                    cd += fmax(0.0, bx.ymin - dY);
-                    cd += fmax(0.0, dY - bx.ymax);
-                    if (bx.flags & 8) cd += fmax(0.0, sqrt(dX * dX + dY * dY) - bx.radiusmax);
-                    cd += fmax(0.0, bx.zmin - dZ);
-                    cd += fmax(0.0, dZ - bx.zmax);
-                    cd += 3.0 * fmax(0.0, bx.normalmin - nZ);
-                    cd += 3.0 * fmax(0.0, nZ - bx.normalmax);
+                    cd += fmax(0.0, bx->xmin - dX);
+                    cd += fmax(0.0, dX - bx->xmax);
+                    cd += fmax(0.0, bx->ymin - dY);
+                    cd += fmax(0.0, dY - bx->ymax);
+                    if (flags & 8) cd += fmax(0.0, sqrt(dX * dX + dY * dY) - bx->radiusmax);
+                    cd += fmax(0.0, bx->zmin - dZ);
+                    cd += fmax(0.0, dZ - bx->zmax);
+                    cd += 3.0 * fmax(0.0, bx->normalmin - nZ);
+                    cd += 3.0 * fmax(0.0, nZ - bx->normalmax);
                 }
                 bool ok = mine && cd < 1.0;                                        // NA:2580
                 if (!__any_sync(FULL, ok)) continue;                               // NA:2584
-                const double M11 = fa.U[1] * fb.U[1] + fa.U[4] * fb.U[4] + fa.U[7] * fb.U[7];
-                const double M01 = fa.U[0] * fb.U[1] + fa.U[3] * fb.U[4] + fa.U[6] * fb.U[7];
+                const double M11 = Ua[1] * Ub[1] + Ua[4] * Ub[4] + Ua[7] * Ub[7];
+                const double M01 = Ua[0] * Ub[1] + Ua[3] * Ub[4] + Ua[6] * Ub[7];
                 double ang = atan2(M11, M01) * 57.29577951308232 - 90.0;           // NA:2594
                 if (ang <= -90.0) ang += 360.0;
                 if (ok) {
-                    if (bx.anglemin < bx.anglemax) {
-                        cd += 0.05 * fmax(0.0, bx.anglemin - ang);
-                        cd += 0.05 * fmax(0.0, ang - bx.anglemax);
+                    const double amin = bx->anglemin, amax = bx->anglemax;
+                    if (amin < amax) {
+                        cd += 0.05 * fmax(0.0, amin - ang);
+                        cd += 0.05 * fmax(0.0, ang - amax);
                     } else {
-                        cd += 0.05 * fmin(fmax(0.0, bx.anglemin - ang), fmax(0.0, ang - bx.anglemax));
+                        cd += 0.05 * fmin(fmax(0.0, amin - ang), fmax(0.0, ang - amax));
                     }
                     ok = cd < 1.0;                                                 // NA:2611
                 }
@@ -556,11 +593,12 @@ classify_pairs_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, cons
                 const double gmax = fmax(gap12, gap21);
                 bool is_match = false, is_near = false;
                 if (ok) {
-                    if (bx.gapmax > 0.1) cd += 4.0 * fmax(0.0, gmax - bx.gapmax); // NA:2643-2645
+                    const double gapmax = bx->gapmax;
+                    if (gapmax > 0.1) cd += 4.0 * fmax(0.0, gmax - gapmax);        // NA:2643-2645
                     bool one_hb = false;                                           // NA:2648-2652
-                    if ((bx.flags & 2) && (pb == 1 || pb == 3)) one_hb = true;     // cSs with parent2 C or U
-                    else if ((bx.flags & 4) && pb == 3) one_hb = true;             // csS with parent2 U
-                    const bool starts_n = bx.flags & 1;
+                    if ((flags & 2) && (pb == 1 || pb == 3)) one_hb = true;        // cSs with parent2 C or U
+                    else if ((flags & 4) && pb == 3) one_hb = true;                // csS with parent2 U
+                    const bool starts_n = flags & 1;
                     if (cd > 0) {
                         if (cd < 1.0 && !starts_n && (mind < 4.1 || one_hb)) is_near = true;
                     } else if (starts_n) {
@@ -575,7 +613,7 @@ classify_pairs_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, cons
                 const unsigned near_b = __ballot_sync(FULL, is_near);
                 int sel = -1;
                 if (match_b) {                     // stable sort by (subcategory, len(name)), NA:2682
-                    double key = is_match ? (double)(bx.subcat * 64 + bx.name_len) : 1e300;
+                    double key = is_match ? (double)(bx->subcat * 64 + bx->name_len) : 1e300;
                     int idx = lane;
                     group_argmin<32>(key, idx);
                     sel = idx;
@@ -587,22 +625,20 @@ classify_pairs_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, cons
                 }
                 if (sel >= 0) {
                     const double cds = __shfl_sync(FULL, cd, sel);
-                    const int fls = __shfl_sync(FULL, mine ? bx.flags : 0, sel);
+                    const int fls = __shfl_sync(FULL, flags, sel);
                     res[ori].box = bstart + sel;
                     res[ori].cd = cds;
-                    res[ori].near = (cds > 0 && !(fls & 1)) ? 1 : 0;              // NA:2693-2696 ("n" in name <=> starts with n)
-                    // `"n" in interaction` tests below use the LW label: near prefix or an n-named box
-                    if (fls & 1) res[ori].near |= 2;
+                    res[ori].near = (cds > 0 && !(fls & 1)) ? 1 : 0;              // NA:2693-2696
+                    if (fls & 1) res[ori].near |= 2;                               // an n-named box also has "n" in its label
                 }
             }
             // ---- 12-vs-21 arbitration, NA:935-957
             int use = -1;
             if (res[0].box >= 0 && res[1].box >= 0) {
-                const fr3d_box_t &b0 = boxes[res[0].box];
-                const fr3d_box_t &b1 = boxes[res[1].box];
                 const bool n0 = res[0].near != 0, n1_ = res[1].near != 0;
                 // interaction12_reversed.lower() == interaction21.lower(): same "n" prefix state and same family
-                const bool same = ((res[0].near & 1) == (res[1].near & 1)) && (b0.rev_lower_id == b1.lower_id);
+                const bool same = ((res[0].near & 1) == (res[1].near & 1)) &&
+                                  (boxes[res[0].box].rev_lower_id == boxes[res[1].box].lower_id);
                 if (same) use = 0;
                 else if (n0 && n1_) use = (res[0].cd < res[1].cd) ? 0 : 1;
                 else if (n1_) use = 0;
@@ -611,26 +647,34 @@ classify_pairs_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, cons
             } else if (res[0].box >= 0) use = 0;
             else if (res[1].box >= 0) use = 1;
             if (use >= 0) {
-                h_valid[FR3D_SLOT_BP] = 1;
-                h_code[FR3D_SLOT_BP] = (res[use].near & 1) | (use << 1);
+                hmask |= 1u << FR3D_SLOT_BP;
+                c_bp = (res[use].near & 1) | (use << 1);
                 bp_box = res[use].box;
                 bp_cd = res[use].cd;
                 bp_gap = fmax(gap12, gap21);
             }
         }
 
-        // ================= emit: lane s owns hit slot s, ballot compaction =================
-        int myvalid = 0, mycode = 0;
-#pragma unroll
-        for (int k = 0; k < 9; ++k) if (lane == k) { myvalid = h_valid[k]; mycode = h_code[k]; }
-        const unsigned hb = __ballot_sync(FULL, myvalid != 0);
-        if (hb) {
+        // ================= emit: lane s writes hit slot s, compacted =================
+        if (hmask) {
             long long base = 0;
-            if (lane == 0) base = (long long)atomicAdd((unsigned long long *)&counters[1], (unsigned long long)__popc(hb));
+            if (lane == 0) base = (long long)atomicAdd((unsigned long long *)&counters[1], (unsigned long long)__popc(hmask));
             base = __shfl_sync(FULL, base, 0);
-            if (myvalid) {
-                const long long pos = base + __popc(hb & ((1u << lane) - 1u));
+            if ((hmask >> lane) & 1u) {
+                const long long pos = base + __popc(hmask & ((1u << lane) - 1u));
                 if (pos < hit_cap) {
+                    int mycode = 0;
+                    switch (lane) {
+                        case FR3D_SLOT_SO12: mycode = c_so12; break;
+                        case FR3D_SLOT_SO21: mycode = c_so21; break;
+                        case FR3D_SLOT_STACK: mycode = c_stack; break;
+                        case FR3D_SLOT_SR12: mycode = c_sr12; break;
+                        case FR3D_SLOT_SR21: mycode = c_sr21; break;
+                        case FR3D_SLOT_BPH: mycode = c_bph; break;
+                        case FR3D_SLOT_BR: mycode = c_br; break;
+                        case FR3D_SLOT_BP: mycode = c_bp; break;
+                        default: break;
+                    }
                     const bool isbp = lane == FR3D_SLOT_BP;
                     const double cdv = isbp ? bp_cd : 0.0, gv = isbp ? bp_gap : 0.0;
                     const uint32_t w3 = (uint32_t)lane | ((uint32_t)mycode << 8) | ((uint32_t)(isbp ? bp_box : 0) << 16);
@@ -643,5 +687,10 @@ classify_pairs_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, cons
         }
     }
 }
+
+#undef C1
+#undef U1
+#undef C2
+#undef U2
 
 }  // namespace fr3d

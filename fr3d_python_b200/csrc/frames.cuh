@@ -20,6 +20,8 @@ __global__ void __launch_bounds__(128) frames_fit_kernel(fr3d_nts_t nts, int32_t
     const int parent = nts.meta[n * FR3D_META_INTS + 0];
     const int flags = nts.meta[n * FR3D_META_INTS + 1];
     uint32_t mask = nts.base_mask[n] & 0xFFFFu;
+    // bits 16-19: parent + 1, bits 20-23: flags (read by the classify kernel instead of meta)
+    const uint32_t tag = ((uint32_t)(parent + 1) & 15u) << 16 | ((uint32_t)flags & 15u) << 20;
     if (parent < 0 || parent >= FR3D_N_PARENTS) {
         nts.base_mask[n] = mask;
         if (status) status[n] = -1;
@@ -44,7 +46,7 @@ __global__ void __launch_bounds__(128) frames_fit_kernel(fr3d_nts_t nts, int32_t
         // fewer than three base atoms: LAPACK's null-space choice is not reproducible
         // (SURVEY §7 hard part 5); the nt is left without a frame, like a failed fit
         // (components.py:324-337), and drops out of the cubes (NA:390,426).
-        nts.base_mask[n] = mask;
+        nts.base_mask[n] = mask | tag;
         if (status) status[n] = -2;
         return;
     }
@@ -98,7 +100,7 @@ __global__ void __launch_bounds__(128) frames_fit_kernel(fr3d_nts_t nts, int32_t
             }
         }
     }
-    nts.base_mask[n] = mask | FR3D_MASK_HAS_FRAME;
+    nts.base_mask[n] = mask | tag | FR3D_MASK_HAS_FRAME;
     if (status) status[n] = 0;
 }
 

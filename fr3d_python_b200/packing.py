@@ -154,6 +154,7 @@ def _fill_atoms(batch, k, maps, atoms):
                 batch.bb_mask[k] |= np.uint32(1 << s)
     batch.meta[k, 0] = pcode
     batch.meta[k, 1] = flags
+    batch.base_mask[k] |= np.uint32(((pcode + 1) & 15) << 16 | (flags & 15) << 20)   # read by the classify kernel
 
 
 def _fix_amino_hydrogens(batch, k, parent):

@@ -39,7 +39,7 @@ def _observed_only(base):
     b = packing.NtBatch(base.n)
     b.base_xyz[:] = base.base_xyz
     b.bb_xyz[:] = base.bb_xyz
-    b.base_mask[:] = base.base_mask & np.uint32(0xFFFF)
+    b.base_mask[:] = base.base_mask & np.uint32(0x00FFFFFF)
     b.bb_mask[:] = base.bb_mask & np.uint32(~(1 << defs.BB_PREV_O3) & 0xFFFFFFFF)
     b.meta[:] = base.meta
     return b

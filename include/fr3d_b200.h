@@ -91,7 +91,7 @@ typedef struct {
     double *rot;         /* [n][9]      rotation_matrix, row major */
     double *base_xyz;    /* [n][16][3]  base atoms by parent slot */
     double *bb_xyz;      /* [n][10][3]  backbone atoms */
-    uint32_t *base_mask; /* [n] bit k: slot k present; bit 31: frame valid */
+    uint32_t *base_mask; /* [n] bits 0-15: slot k present; 16-19: parent + 1; 20-23: meta flags; 31: frame valid */
     uint32_t *bb_mask;   /* [n] bit k: backbone slot k present */
     int32_t *meta;       /* [n][8] */
 } fr3d_nts_t;

@@ -68,3 +68,40 @@ def test_header_cites_reference_lines():
     for needle in ("components.py:273-349", "NA:410-443", "NA:1278", "superpositions.py:10-121",
                    "discrepancy.py:165-233", "FR3D.py:433-442"):
         assert needle in text
+
+
+def test_rings_and_ellipses_lie_inside_the_prefilter_disc():
+    """csrc/classify.cuh skips the ring / ellipse tests for oxygens with x^2 + y^2 >= 25: every ring
+    polygon and near-ring ellipse (convex) must lie strictly inside that disc.  A convex region with a
+    point inside the disc and no point on the circle is contained in the disc."""
+    ang = np.linspace(0, 2 * np.pi, 7200, endpoint=False)
+    cx, cy = 5.0 * np.cos(ang), 5.0 * np.sin(ang)
+
+    def inside(lines, x, y):
+        ok = np.ones_like(x, dtype=bool)
+        for a, b, c in lines:
+            ok &= a * x + b * y + c > 0
+        return ok
+
+    def in_ell(e, x, y):
+        a, b, ex, ey, r = e
+        return a * (x - ex) ** 2 + b * (x - ex) * (y - ey) + (y - ey) ** 2 < r
+
+    for parent in defs.PARENTS:
+        rings = defs.PLANES["rings"][parent]
+        ell = defs.PLANES["ellipses"][parent]
+        regions = []
+        if rings["divider"]:
+            d = rings["divider"]
+            regions.append([d] + rings["ring5"])
+            regions.append([[-d[0], -d[1], -d[2] + 1e-12]] + rings["ring6"])
+        else:
+            regions.append(rings["ring6"])
+        gx, gy = np.meshgrid(np.linspace(-4, 4, 161), np.linspace(-4, 4, 161))
+        for reg in regions:
+            assert not inside(reg, cx, cy).any(), parent
+            assert inside(reg, gx.ravel(), gy.ravel()).any(), parent        # non-empty, near the origin
+        for e in (ell["near5"], ell["near6"]):
+            if e:
+                assert not in_ell(e, cx, cy).any(), parent
+                assert in_ell(e, np.array([e[2]]), np.array([e[3]])).all()
