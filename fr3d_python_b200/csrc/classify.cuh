@@ -75,6 +75,11 @@ __device__ __forceinline__ double group_max(double v) {
     return v;
 }
 
+// The kernel is instruction-cache sensitive (ncu: stall_no_instruction dominated the first
+// version, 9.9 k SASS instructions): the fp64 atan2 expansion and the rare, long scalar paths are
+// kept out of line so that they exist once, and the orientation loop is not unrolled.
+__device__ __noinline__ double atan2_once(double y, double x) { return atan2(y, x); }
+
 // angle_between_vectors (NA:2873-2881) of (A-B, C-B), degrees
 __device__ __forceinline__ double hb_angle(const double *A, const double *B, const double *C) {
     const double u0 = A[0] - B[0], u1 = A[1] - B[1], u2 = A[2] - B[2];
@@ -82,20 +87,13 @@ __device__ __forceinline__ double hb_angle(const double *A, const double *B, con
     const double cosang = u0 * w0 + u1 * w1 + u2 * w2;
     const double x0 = u1 * w2 - u2 * w1, x1 = u2 * w0 - u0 * w2, x2 = u0 * w1 - u1 * w0;
     const double sinang = sqrt(x0 * x0 + x1 * x1 + x2 * x2);
-    return 180.0 * atan2(sinang, cosang) / 3.141592653589793;
+    return 180.0 * atan2_once(sinang, cosang) / 3.141592653589793;
 }
 
 __device__ __forceinline__ double dist3(const double *a, const double *b) {
     const double d0 = a[0] - b[0], d1 = a[1] - b[1], d2 = a[2] - b[2];
     return sqrt(d0 * d0 + d1 * d1 + d2 * d2);
 }
-
-// Result of check_basepair_cutoffs for one orientation
-struct BpResult {
-    int box;        // -1: no annotation
-    int near;       // bit0: LW gets the "n" prefix, bit1: the box name itself starts with n
-    double cd;      // cutoff_distance
-};
 
 static constexpr int WARPS_PER_BLOCK = 4;
 
@@ -113,7 +111,7 @@ struct WarpScratch {
 #define C2(k) (S.fr[12 + (k)])
 #define U2(k) (S.fr[15 + (k)])
 
-// (p - c) . U for the frame stored at S.fr[base .. base+11]
+// (p - c) . U for the frame stored at fr[0..11]   (translate_rotate_point, NA:1263-1275)
 __device__ __forceinline__ void project(const double *fr, double px, double py, double pz, double &x, double &y,
                                         double &z) {
     const double v0 = px - fr[0], v1 = py - fr[1], v2 = pz - fr[2];
@@ -124,10 +122,9 @@ __device__ __forceinline__ void project(const double *fr, double px, double py, 
 
 // check_sugar_ribose, NA:2262-2342, after the shared O2'-O2' screen.  Evaluated by every lane on
 // broadcast shared-memory reads (warp-uniform).  Returns -1 none, 0 cSR, 1 tSR.
-// A / B: backbone blocks of nt_a / nt_b in S.bb; base_pt: N3 / O2 of nt_a; Ua2,5,8: normal of nt_a.
-__device__ __forceinline__ int sugar_ribose_tail(const double (*A)[3], const double (*B)[3], uint32_t bba,
-                                                 uint32_t bbb, bool have_pt, const double *base_pt, double n0,
-                                                 double n1, double n2) {
+// A / B: backbone blocks of nt_a / nt_b; base_pt: N3 / O2 of nt_a; (n0,n1,n2): base normal of nt_a.
+__device__ __noinline__ int sugar_ribose_tail(const double (*A)[3], const double (*B)[3], uint32_t bba, uint32_t bbb,
+                                              bool have_pt, const double *base_pt, double n0, double n1, double n2) {
     if (!have_pt) return -1;
     const double d0 = base_pt[0] - B[6][0], d1 = base_pt[1] - B[6][1], d2 = base_pt[2] - B[6][2];
     if (sqrt(d0 * d0 + d1 * d1 + d2 * d2) > 3.8) return -1;
@@ -151,8 +148,95 @@ __device__ __forceinline__ int sugar_ribose_tail(const double (*A)[3], const dou
     const double x = v[0] * w[0] + v[1] * w[1] + v[2] * w[2];
     const double cx0 = b1[1] * v[2] - b1[2] * v[1], cx1 = b1[2] * v[0] - b1[0] * v[2], cx2 = b1[0] * v[1] - b1[1] * v[0];
     const double y = cx0 * w[0] + cx1 * w[1] + cx2 * w[2];
-    const double angle = atan2(y, x) * (180.0 / 3.141592653589793);
+    const double angle = atan2_once(y, x) * (180.0 / 3.141592653589793);
     return fabs(angle) > 90.0 ? 0 : 1;
+}
+
+// The sequential selection of check_base_backbone_interactions (NA:1925-2019) over the per-lane
+// (angle, distance) values in S.ang / S.dst (index site*6 + oxygen; 0 = not a candidate).
+// One lane runs it.  Returns bph | br << 8, each digit | near << 4, or 0xFF for none.
+__device__ __noinline__ int backbone_select(const WarpScratch &S, int par1, uint32_t bb2) {
+    int bph = -1, br = -1;
+    // if nt2 has a P atom far from the plane of base 1, no BPh (NA:1915-1921)
+    bool use_ph = true;
+    if (bb2 & 1u) {
+        const double *P = S.bb[0];
+        if (P[0] != 0.0 || P[1] != 0.0 || P[2] != 0.0) {
+            double tx, ty, tz;
+            project(&S.fr[0], P[0], P[1], P[2], tx, ty, tz);
+            if (fabs(tz) > 4.5) use_ph = false;
+        }
+    }
+    const int nsites = c_tab.n_sites[par1];
+    int n_true = 0, n_near = 0, n_keys = 0;
+    unsigned long long site_ox = 0;        // 4 bits of oxygen indices per label digit
+    double best_tq = -1e300, best_nq = -1e300;
+    int best_tl = -1, best_nl = -1, first_tl = -1, first_nl = -1;
+    int rt = 0, rn = 0, best_rtl = -1, best_rnl = -1, first_rtl = -1, first_rnl = -1;
+    double best_rtq = -1e300, best_rnq = -1e300;
+    double cutoff = 0.0, ncutoff = 0.0;
+#pragma unroll 1
+    for (int s = 0; s < nsites; ++s) {
+        const int carbon = c_tab.site_carbon[par1][s];
+        const int digit = c_tab.site_digit[par1][s];
+        if (carbon == 1) { cutoff = 4.0; ncutoff = 4.5; }          // NA:1930-1935
+        else if (carbon == 0) { cutoff = 3.5; ncutoff = 4.0; }
+#pragma unroll 1
+        for (int i = 0; i < 6; ++i) {
+            const double an = S.ang[s * 6 + i], ds = S.dst[s * 6 + i];
+            if (!(an != 0.0 && ds != 0.0)) continue;   // `if phosphateAngle:` / `if phosphateDistance:`
+            if (i < 4) {                               // phosphate oxygens O5' OP1 OP2 prevO3' (NA:1938-1955)
+                if (!use_ph) continue;
+                if (an > 130.0 && ds < cutoff) {
+                    const double q = (cutoff - ds) + (an - 130.0) / 20.0;
+                    if (n_true == 0) first_tl = digit;
+                    ++n_true;
+                    if (q > best_tq || (q == best_tq && digit < best_tl)) { best_tq = q; best_tl = digit; }
+                    if (!((site_ox >> (digit * 4)) & 0xFull)) ++n_keys;
+                    site_ox |= 1ull << (digit * 4 + i);
+                } else if (an > 110.0 && ds < ncutoff) {
+                    const double q = (ncutoff - ds) + (an - 110.0) / 20.0;
+                    if (n_near == 0) first_nl = digit;
+                    ++n_near;
+                    if (q > best_nq || (q == best_nq && digit < best_nl)) { best_nq = q; best_nl = digit; }
+                }
+            } else {                                   // ribose oxygens O2' O4' (NA:1958-1971)
+                if (an > 130.0 && ds < cutoff) {
+                    const double q = (cutoff - ds) + (an - 130.0) / 20.0;
+                    if (rt == 0) first_rtl = digit;
+                    ++rt;
+                    if (q > best_rtq || (q == best_rtq && digit < best_rtl)) { best_rtq = q; best_rtl = digit; }
+                } else if (an > 110.0 && ds < ncutoff) {
+                    const double q = (ncutoff - ds) + (an - 110.0) / 20.0;
+                    if (rn == 0) first_rnl = digit;
+                    ++rn;
+                    if (q > best_rnq || (q == best_rnq && digit < best_rnl)) { best_rnq = q; best_rnl = digit; }
+                }
+            }
+        }
+        // record the best phosphate interaction: sticky, evaluated after EVERY site (NA:1973-2003)
+        if (n_true == 1) {
+            bph = first_tl;
+        } else if (n_keys > 1) {
+            const unsigned o7 = (site_ox >> 28) & 0xF, o9 = (site_ox >> 36) & 0xF;
+            const unsigned o3 = (site_ox >> 12) & 0xF, o5 = (site_ox >> 20) & 0xF;
+            if (o7 && o9) { if (__popc(o7 | o9) > 1) bph = 8; }
+            else if (o3 && o5) { if (__popc(o3 | o5) > 1) bph = 4; }
+            if (bph < 0) bph = best_tl;
+        } else if (n_true > 1) {
+            bph = best_tl;
+        } else if (n_near == 1) {
+            bph = first_nl | 16;
+        } else if (n_near > 1) {
+            bph = best_nl | 16;
+        }
+        // best ribose interaction (NA:2005-2019)
+        if (rt == 1) br = first_rtl;
+        else if (rt > 1) br = best_rtl;
+        else if (rn == 1) br = first_rnl | 16;
+        else if (rn > 1) br = best_rnl | 16;
+    }
+    return (bph & 0xFF) | ((br & 0xFF) << 8);
 }
 
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4)
@@ -175,6 +259,7 @@ classify_pairs_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, cons
     int nx1 = 0, nx2 = 0, nxr = 0;
     if (warp0 < n_pairs) { nx1 = pair_i[warp0]; nx2 = pair_j[warp0]; nxr = pair_rank[warp0]; }
 
+#pragma unroll 1
     for (long long p = warp0; p < n_pairs; p += nwarps) {
         const int n1 = nx1, n2 = nx2, rank = nxr;
         if (p + nwarps < n_pairs) { nx1 = pair_i[p + nwarps]; nx2 = pair_j[p + nwarps]; nxr = pair_rank[p + nwarps]; }
@@ -183,11 +268,10 @@ classify_pairs_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, cons
         const uint32_t bm1 = nts.base_mask[n1], bm2 = nts.base_mask[n2];
         const uint32_t bb1 = nts.bb_mask[n1], bb2 = nts.bb_mask[n2];
         const int par1 = (int)((bm1 >> 16) & 15u) - 1, par2 = (int)((bm2 >> 16) & 15u) - 1;
-        const int own = half ? n1 : n2;
         const bool valid = ((half ? bm1 : bm2) >> a) & 1u;
         double px = 0, py = 0, pz = 0;
         if (valid) {
-            const double *q = nts.base_xyz + ((size_t)own * FR3D_BASE_SLOTS + a) * 3;
+            const double *q = nts.base_xyz + ((size_t)(half ? n1 : n2) * FR3D_BASE_SLOTS + a) * 3;
             px = q[0]; py = q[1]; pz = q[2];
         }
         double fv = 0.0;
@@ -198,10 +282,9 @@ classify_pairs_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, cons
         }
         double bx_ = 0, by_ = 0, bz_ = 0;
         if (lane < 20) {
-            const int n = lane < 10 ? n2 : n1;
             const int e = lane < 10 ? lane : lane - 10;
             if (((lane < 10 ? bb2 : bb1) >> e) & 1u) {
-                const double *q = nts.bb_xyz + ((size_t)n * FR3D_BB_SLOTS + e) * 3;
+                const double *q = nts.bb_xyz + ((size_t)(lane < 10 ? n2 : n1) * FR3D_BB_SLOTS + e) * 3;
                 bx_ = q[0]; by_ = q[1]; bz_ = q[2];
             }
         }
@@ -212,57 +295,15 @@ classify_pairs_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, cons
         __syncwarp();
 
         const double *fo = half ? &S.fr[12] : &S.fr[0];      // frame the lane's atom is projected into
-        const int paro = half ? par2 : par1;
         double x, y, z;
         project(fo, px, py, pz, x, y, z);
+        const double nZ = U1(2) * U2(2) + U1(5) * U2(5) + U1(8) * U2(8);   // normal . normal = M[2][2] either way
 
-        // lazily computed, shared by coplanar and both basepair orientations
-        bool have_gaps = false, have_mind = false;
-        double gap12 = 100.0, gap21 = 100.0, mind = 9999.0;
-
-        auto compute_gaps = [&]() {               // calculate_basepair_gap, NA:2189-2259, both directions
-            // squared distance to the other base centre orders the atoms like the reference's argsort
-            double key = valid ? ((px - fo[0]) * (px - fo[0]) + (py - fo[1]) * (py - fo[1]) +
-                                  (pz - fo[2]) * (pz - fo[2])) : 1e300;
-            double g = 100.0;
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                double k = key; int idx = a;
-                group_argmin<16>(k, idx);
-                const double zz = fabs(__shfl_sync(FULL, z, (lane & 16) | idx));
-                if (k < 1e299) {
-                    if (zz < g) g = zz;
-                    if (a == idx) key = 1e300;
-                }
-            }
-            gap12 = __shfl_sync(FULL, g, 0);
-            gap21 = __shfl_sync(FULL, g, 16);
-            have_gaps = true;
-        };
-        auto compute_mind = [&]() {               // calculate_base_min_distances, NA:1799-1829
-            // lower half: nt2 atom `a` against nt1 atoms 0-7; upper half: nt2 atom `a` against nt1 atoms 8-15
-            const bool v2 = (bm2 >> a) & 1u;
-            const double qx = S.atoms[a][0], qy = S.atoms[a][1], qz = S.atoms[a][2];
-            double best = 1e300;
-#pragma unroll
-            for (int s = 0; s < 8; ++s) {
-                const int k1 = s + 8 * half;
-                if (v2 && ((bm1 >> k1) & 1u)) {
-                    const double dx = S.atoms[16 + k1][0] - qx, dy = S.atoms[16 + k1][1] - qy,
-                                 dz = S.atoms[16 + k1][2] - qz;
-                    best = fmin(best, dx * dx + dy * dy + dz * dz);
-                }
-            }
-            best = group_min<32>(best);
-            mind = best < 1e299 ? sqrt(best) : 9999.0;
-            have_mind = true;
-        };
-
-        // decisions for the nine hit slots (warp-uniform): bit s of hmask, code in hcode[s]
+        // decisions for the nine hit slots (warp-uniform): bit s of hmask, codes below
         unsigned hmask = 0;
         int c_so12 = 0, c_so21 = 0, c_stack = 0, c_sr12 = 0, c_sr21 = 0, c_bph = 0, c_br = 0, c_bp = 0;
         int bp_box = 0;
-        double bp_cd = 0.0, bp_gap = 0.0;
+        double bp_cd = 0.0;
 
         // ================= base-oxygen stacking, both directions (NA:758-778) =================
         if (cats & FR3D_CAT_SO) {
@@ -273,7 +314,7 @@ classify_pairs_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, cons
             // oxygens O2' O3' O4' O5' OP1 OP2 (NA:1290) -> backbone slots 6 5 4 3 1 2
             const int oslot = (0x213456 >> (4 * o)) & 7;
             const bool present = act && (((g ? bb1 : bb2) >> oslot) & 1u);
-            double ox = 0, oy = 0, oz = 0;
+            double ox, oy, oz;
             const double *ob = S.bb[(g ? 10 : 0) + (act ? oslot : 0)];
             project(g ? &S.fr[12] : &S.fr[0], ob[0], ob[1], ob[2], ox, oy, oz);
             const bool has_tab = pb >= 0 && pb < FR3D_N_PARENTS;
@@ -281,49 +322,35 @@ classify_pairs_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, cons
             // the tables), so an oxygen outside the slab |z| < 3.6 or the disc cannot score
             const bool maybe = present && has_tab && fabs(oz) < 3.6 && (ox * ox + oy * oy) < 25.0;
             if (__any_sync(FULL, maybe)) {
-                bool ring = false;
-                if (maybe && !(fabs(oz) < 2.0)) {
-                    if (c_tab.has_div[pb]) {
-                        if (left_of(c_tab.ring_div[pb], ox, oy)) {
-                            ring = true;
+                bool ring = false, nr = false;
+                if (maybe) {
+                    const bool has_div = c_tab.has_div[pb];
+                    const bool left = has_div && left_of(c_tab.ring_div[pb], ox, oy);
+                    if (!(fabs(oz) < 2.0)) {             // impossibly close oxygens are skipped for rings only
+                        ring = true;
+                        if (left) {
 #pragma unroll
                             for (int k = 0; k < 4; ++k) ring = ring && left_of(c_tab.ring5[pb][k], ox, oy);
                         } else {
-                            ring = true;
 #pragma unroll
                             for (int k = 0; k < 6; ++k) ring = ring && left_of(c_tab.ring6[pb][k], ox, oy);
                         }
-                    } else {
-                        ring = true;
-#pragma unroll
-                        for (int k = 0; k < 6; ++k) ring = ring && left_of(c_tab.ring6[pb][k], ox, oy);
                     }
+                    // near-ring ellipses, used only when no oxygen is over a ring (NA:1402-1459)
+                    if (fabs(oz) < 3.5) nr = in_ellipse(left ? c_tab.ell5[pb] : c_tab.ell6[pb], ox, oy);
                 }
                 const unsigned ring_b = __ballot_sync(FULL, ring);
                 const unsigned true_b = __ballot_sync(FULL, ring && fabs(oz) < 3.5);
                 const unsigned gmask = 0xFFu << (g * 8);
-                double key = ring ? fabs(oz) : 1e300;
+                // over a ring: closest to the plane wins; true if any |z| < 3.5, else near (NA:1370-1400);
+                // otherwise the ellipse hit closest to the base centre (NA:1440-1451)
+                const bool use_ring = (ring_b & gmask) != 0;
+                double key = use_ring ? (ring ? fabs(oz) : 1e300) : (nr ? (ox * ox + oy * oy) : 1e300);
                 int idx = o;
                 group_argmin<8>(key, idx);
-                // over a ring: true if any |z| < 3.5, else near (NA:1386-1400)
-                const double zsel_ring = __shfl_sync(FULL, oz, (lane & ~7) | idx);
-                // near-ring ellipses, used only when no oxygen is over a ring (NA:1402-1459)
-                bool nr = false;
-                if (maybe && fabs(oz) < 3.5) {
-                    if (c_tab.has_div[pb]) {
-                        if (left_of(c_tab.ring_div[pb], ox, oy)) nr = in_ellipse(c_tab.ell5[pb], ox, oy);
-                        else nr = in_ellipse(c_tab.ell6[pb], ox, oy);
-                    } else {
-                        nr = in_ellipse(c_tab.ell6[pb], ox, oy);
-                    }
-                }
-                double k2 = nr ? (ox * ox + oy * oy) : 1e300;
-                int i2 = o;
-                group_argmin<8>(k2, i2);
-                const double zsel_near = __shfl_sync(FULL, oz, (lane & ~7) | i2);
+                const double zsel = __shfl_sync(FULL, oz, (lane & ~7) | idx);
                 int code = -1;
-                if (ring_b & gmask) code = idx | ((zsel_ring > 0) ? 0 : 8) | ((true_b & gmask) ? 0 : 16);
-                else if (k2 < 1e299) code = i2 | ((zsel_near > 0) ? 0 : 8) | 16;
+                if (key < 1e299) code = idx | ((zsel > 0) ? 0 : 8) | ((use_ring && (true_b & gmask)) ? 0 : 16);
                 const int code12 = __shfl_sync(FULL, code, 0);
                 const int code21 = __shfl_sync(FULL, code, 8);
                 if (code12 >= 0) { hmask |= 1u << FR3D_SLOT_SO12; c_so12 = code12; }
@@ -331,9 +358,11 @@ classify_pairs_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, cons
             }
         }
 
-        // ================= base-base stacking (NA:1602-1739) =================
+        // ================= base-base stacking, part 1 (NA:1602-1702) =================
+        int stack_code = -1;
+        bool stack_both = false;
         if ((cats & FR3D_CAT_STACKING) && par1 >= 0 && par2 >= 0) {
-            const bool inside = valid && in_hull(paro, x, y, z);
+            const bool inside = valid && in_hull(half ? par2 : par1, x, y, z);
             const unsigned in_b = __ballot_sync(FULL, inside);
             if (in_b) {                            // no atom over the other base: no overlap either way
                 const double zmin = group_min<16>(valid ? z : 1e300);
@@ -348,22 +377,15 @@ classify_pairs_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, cons
                 const bool nt1on2 = __shfl_sync(FULL, (int)ov, 16);
                 const double z_2on1 = __shfl_sync(FULL, zsel, 0);
                 const double z_1on2 = __shfl_sync(FULL, zsel, 16);
-                if (nt2on1 || nt1on2) {
-                    const double normal_Z = U1(2) * U2(2) + U1(5) * U2(5) + U1(8) * U2(8);
-                    const bool reverse = nt1on2 && !nt2on1;                        // NA:1663-1667
+                if ((nt2on1 || nt1on2) && !(fabs(nZ) < 0.5)) {                 // NA:1717, cheap half first
+                    const bool reverse = nt1on2 && !nt2on1;                    // NA:1663-1667
                     const double mvd = reverse ? z_1on2 : z_2on1;
-                    int code = -1;                                                 // 0 s35 1 s53 2 s33 3 s55
-                    if (mvd > 0) { if (normal_Z > 0) code = 0; else if (normal_Z < 0) code = 2; }
-                    else if (mvd < 0) { if (normal_Z > 0) code = 1; else if (normal_Z < 0) code = 3; }
-                    if (reverse && code >= 0 && code < 2) code ^= 1;              // swap s35 <-> s53 (NA:1699-1702)
-                    if (fabs(normal_Z) < 0.5) code = -1;                           // NA:1717 (cheap half first)
-                    if (code >= 0) {
-                        compute_mind();
-                        int near = 1;
-                        if (fabs(mind) < 4.0 && fabs(mind) > 1.0 && fabs(normal_Z) > 0.6 && nt2on1 && nt1on2) near = 0;
-                        if (fabs(mind) < 1.0) code = -1;                           // NA:1717
-                        if (code >= 0) { hmask |= 1u << FR3D_SLOT_STACK; c_stack = code | (near << 2); }
-                    }
+                    int code = -1;                                             // 0 s35 1 s53 2 s33 3 s55
+                    if (mvd > 0) { if (nZ > 0) code = 0; else if (nZ < 0) code = 2; }
+                    else if (mvd < 0) { if (nZ > 0) code = 1; else if (nZ < 0) code = 3; }
+                    if (reverse && code >= 0 && code < 2) code ^= 1;          // swap s35 <-> s53 (NA:1699-1702)
+                    stack_code = code;
+                    stack_both = nt2on1 && nt1on2;
                 }
             }
         }
@@ -372,8 +394,7 @@ classify_pairs_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, cons
         if ((cats & FR3D_CAT_SUGAR_RIBOSE) && par1 >= 0 && par2 >= 0 && par1 != 4 && par2 != 4 &&
             (bb1 >> 6 & 1u) && (bb2 >> 6 & 1u)) {
             // both directions start with the same O2'-O2' distance screen (NA:2281-2286)
-            const double e0 = S.bb[16][0] - S.bb[6][0], e1 = S.bb[16][1] - S.bb[6][1], e2 = S.bb[16][2] - S.bb[6][2];
-            if (!(sqrt(e0 * e0 + e1 * e1 + e2 * e2) > 3.8)) {
+            if (!(dist3(S.bb[16], S.bb[6]) > 3.8)) {
                 const int s1 = c_tab.sr_slot[par1], s2 = c_tab.sr_slot[par2];
                 const int r12 = sugar_ribose_tail(&S.bb[10], &S.bb[0], bb1, bb2, s1 >= 0 && ((bm1 >> s1) & 1u),
                                                   S.atoms[16 + (s1 < 0 ? 0 : s1)], U1(2), U1(5), U1(8));
@@ -387,11 +408,10 @@ classify_pairs_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, cons
         // ================= base-phosphate / base-ribose, nt1 base -> nt2 backbone (NA:807-829) =================
         if ((cats & FR3D_CAT_BACKBONE) && par1 >= 0) {
             const int site = lane / 6, ok = lane - site * 6;    // ok: 0 O5' 1 OP1 2 OP2 3 prevO3' | 4 O2' 5 O4'
-            const int nsites = c_tab.n_sites[par1];
-            double ang = 0.0, dst = 0.0;
+            double dst = 0.0;
             bool cand = false;
             int hs = 0, ms = 0, oslot = 0;
-            if (lane < 30 && site < nsites) {
+            if (lane < 30 && site < c_tab.n_sites[par1]) {
                 oslot = (0x469213 >> (4 * ok)) & 15;            // backbone slots 3 1 2 9 6 4
                 hs = c_tab.site_h[par1][site];
                 ms = c_tab.site_m[par1][site];
@@ -405,177 +425,77 @@ classify_pairs_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, cons
                 }
             }
             if (__any_sync(FULL, cand)) {
+                double ang = 0.0;
                 if (cand) ang = hb_angle(S.atoms[16 + ms], S.atoms[16 + hs], S.bb[oslot]);
-                else dst = 0.0;                    // not a candidate: the state machine skips it
+                else dst = 0.0;                    // not a candidate: the selection skips it
                 __syncwarp();
                 S.ang[lane] = ang; S.dst[lane] = dst;
                 __syncwarp();
-                int bph = -1, br = -1;
-                if (lane == 0) {
-                    // if nt2 has a P atom far from the plane of base 1, no BPh (NA:1915-1921)
-                    bool use_ph = true;
-                    if (bb2 & 1u) {
-                        const double *P = S.bb[0];
-                        if (P[0] != 0.0 || P[1] != 0.0 || P[2] != 0.0) {
-                            double tx, ty, tz;
-                            project(&S.fr[0], P[0], P[1], P[2], tx, ty, tz);
-                            if (fabs(tz) > 4.5) use_ph = false;
-                        }
-                    }
-                    int n_true = 0, n_near = 0, n_keys = 0;
-                    unsigned long long site_ox = 0;        // 4 bits of oxygen indices per label digit
-                    double best_tq = -1e300, best_nq = -1e300;
-                    int best_tl = -1, best_nl = -1, first_tl = -1, first_nl = -1;
-                    int rt = 0, rn = 0, best_rtl = -1, best_rnl = -1, first_rtl = -1, first_rnl = -1;
-                    double best_rtq = -1e300, best_rnq = -1e300;
-                    double cutoff = 0.0, ncutoff = 0.0;
-                    for (int s = 0; s < nsites; ++s) {
-                        const int carbon = c_tab.site_carbon[par1][s];
-                        const int digit = c_tab.site_digit[par1][s];
-                        if (carbon == 1) { cutoff = 4.0; ncutoff = 4.5; }          // NA:1930-1935
-                        else if (carbon == 0) { cutoff = 3.5; ncutoff = 4.0; }
-                        if (use_ph) {
-                            for (int i = 0; i < 4; ++i) {
-                                const double an = S.ang[s * 6 + i], ds = S.dst[s * 6 + i];
-                                if (an != 0.0 && ds != 0.0) {              // `if phosphateAngle:` / `if phosphateDistance:`
-                                    if (an > 130.0 && ds < cutoff) {
-                                        const double q = (cutoff - ds) + (an - 130.0) / 20.0;
-                                        if (n_true == 0) first_tl = digit;
-                                        ++n_true;
-                                        if (q > best_tq || (q == best_tq && digit < best_tl)) { best_tq = q; best_tl = digit; }
-                                        if (!((site_ox >> (digit * 4)) & 0xFull)) ++n_keys;
-                                        site_ox |= 1ull << (digit * 4 + i);
-                                    } else if (an > 110.0 && ds < ncutoff) {
-                                        const double q = (ncutoff - ds) + (an - 110.0) / 20.0;
-                                        if (n_near == 0) first_nl = digit;
-                                        ++n_near;
-                                        if (q > best_nq || (q == best_nq && digit < best_nl)) { best_nq = q; best_nl = digit; }
-                                    }
-                                }
-                            }
-                        }
-                        for (int i = 4; i < 6; ++i) {
-                            const double an = S.ang[s * 6 + i], ds = S.dst[s * 6 + i];
-                            if (an != 0.0 && ds != 0.0) {
-                                if (an > 130.0 && ds < cutoff) {
-                                    const double q = (cutoff - ds) + (an - 130.0) / 20.0;
-                                    if (rt == 0) first_rtl = digit;
-                                    ++rt;
-                                    if (q > best_rtq || (q == best_rtq && digit < best_rtl)) { best_rtq = q; best_rtl = digit; }
-                                } else if (an > 110.0 && ds < ncutoff) {
-                                    const double q = (ncutoff - ds) + (an - 110.0) / 20.0;
-                                    if (rn == 0) first_rnl = digit;
-                                    ++rn;
-                                    if (q > best_rnq || (q == best_rnq && digit < best_rnl)) { best_rnq = q; best_rnl = digit; }
-                                }
-                            }
-                        }
-                        // record the best phosphate interaction: sticky, evaluated after EVERY site (NA:1973-2003)
-                        if (n_true == 1) {
-                            bph = first_tl;
-                        } else if (n_keys > 1) {
-                            const unsigned o7 = (site_ox >> 28) & 0xF, o9 = (site_ox >> 36) & 0xF;
-                            const unsigned o3 = (site_ox >> 12) & 0xF, o5 = (site_ox >> 20) & 0xF;
-                            if (o7 && o9) { if (__popc(o7 | o9) > 1) bph = 8; }
-                            else if (o3 && o5) { if (__popc(o3 | o5) > 1) bph = 4; }
-                            if (bph < 0) bph = best_tl;
-                        } else if (n_true > 1) {
-                            bph = best_tl;
-                        } else if (n_near == 1) {
-                            bph = first_nl | 16;
-                        } else if (n_near > 1) {
-                            bph = best_nl | 16;
-                        }
-                        // best ribose interaction (NA:2005-2019)
-                        if (rt == 1) br = first_rtl;
-                        else if (rt > 1) br = best_rtl;
-                        else if (rn == 1) br = first_rnl | 16;
-                        else if (rn > 1) br = best_rnl | 16;
-                    }
-                }
-                bph = __shfl_sync(FULL, bph, 0);
-                br = __shfl_sync(FULL, br, 0);
-                if (bph >= 0) { hmask |= 1u << FR3D_SLOT_BPH; c_bph = bph; }
-                if (br >= 0) { hmask |= 1u << FR3D_SLOT_BR; c_br = br; }
+                int sel = 0xFFFF;
+                if (lane == 0) sel = backbone_select(S, par1, bb2);
+                sel = __shfl_sync(FULL, sel, 0);
+                if ((sel & 0xFF) != 0xFF) { hmask |= 1u << FR3D_SLOT_BPH; c_bph = sel & 0xFF; }
+                if (((sel >> 8) & 0xFF) != 0xFF) { hmask |= 1u << FR3D_SLOT_BR; c_br = (sel >> 8) & 0xFF; }
             }
         }
 
-        // ================= coplanar + basepair, orientation 12 then 21 (NA:834-1013) =================
+        // ================= coplanar + basepair, part 1: frame-only terms and cutoff boxes =================
+        // check_coplanar (NA:2051-2186) is a conjunction; its frame-only terms (:2098-2113) come first
+        // here, the gap / min-distance ones are evaluated in part 2 only for pairs that pass them.
+        // dot1 and dot2 swap roles between the two orientations and dot3 = |nZ| is symmetric.
         const bool gly_ok = (bm1 & 1u) && (bm2 & 1u) && par1 >= 0 && par2 >= 0;   // NA:674, 834-837
+        bool cp_frames = false;
+        unsigned ori_ok = 0;                     // bit ori: the parent combination is annotated (NA:842 / 894)
+        unsigned bp_live = 0;                    // bit ori: some box is still within 1.0 after the angle term
+        double cd0 = 1e300, cd1 = 1e300;         // per lane: running cutoff_distance of "my" box, per orientation
         if (gly_ok) {
-            // glycosidic displacement: slot 0 = N9 / N1
-            const double gd0 = S.atoms[0][0] - S.atoms[16][0], gd1 = S.atoms[0][1] - S.atoms[16][1],
-                         gd2 = S.atoms[0][2] - S.atoms[16][2];
-            const double nZ = U1(2) * U2(2) + U1(5) * U2(5) + U1(8) * U2(8);       // M[2][2], both orientations
-            BpResult res[2];
-            bool marked_cp = false;
-            // check_coplanar (NA:2051-2186) is a conjunction; the frame-only conditions (:2098-2113) are
-            // evaluated first, the gap / min-distance ones only for pairs that pass them.  dot1 and dot2
-            // swap roles between the orientations and dot3 is symmetric, so one evaluation serves both.
-            bool cp_frames = false;
-            if (cats & FR3D_CAT_COPLANAR) {
+            if (c_tab.combo_ok[par1 * FR3D_N_PARENTS + par2]) ori_ok |= 1u;
+            if (c_tab.combo_ok[par2 * FR3D_N_PARENTS + par1]) ori_ok |= 2u;
+            if ((cats & FR3D_CAT_COPLANAR) && ori_ok && fabs(nZ) > 0.7757) {
                 double e0 = C1(0) - C2(0), e1 = C1(1) - C2(1), e2 = C1(2) - C2(2);
                 const double en = sqrt(e0 * e0 + e1 * e1 + e2 * e2);
                 e0 /= en; e1 /= en; e2 /= en;
-                const double dot1 = fabs(e0 * U1(2) + e1 * U1(5) + e2 * U1(8));
-                const double dot2 = fabs(e0 * U2(2) + e1 * U2(5) + e2 * U2(8));
-                cp_frames = dot1 < 0.3381 && dot2 < 0.3381 && fabs(nZ) > 0.7757;
+                cp_frames = fabs(e0 * U1(2) + e1 * U1(5) + e2 * U1(8)) < 0.3381 &&
+                            fabs(e0 * U2(2) + e1 * U2(5) + e2 * U2(8)) < 0.3381;
             }
-#pragma unroll
+            // glycosidic displacement: slot 0 = N9 / N1
+            const double gd0 = S.atoms[0][0] - S.atoms[16][0], gd1 = S.atoms[0][1] - S.atoms[16][1],
+                         gd2 = S.atoms[0][2] - S.atoms[16][2];
+#pragma unroll 1
             for (int ori = 0; ori < 2; ++ori) {
-                res[ori].box = -1; res[ori].near = 0; res[ori].cd = 0.0;
-                const int pa = ori ? par2 : par1, pb = ori ? par1 : par2;
-                const int combo = pa * FR3D_N_PARENTS + pb;
-                if (!c_tab.combo_ok[combo]) continue;                              // NA:842 / 894
+                if (!((ori_ok >> ori) & 1u)) continue;
+                const int combo = ori ? par2 * FR3D_N_PARENTS + par1 : par1 * FR3D_N_PARENTS + par2;
                 const double *Ua = ori ? &S.fr[15] : &S.fr[3];
                 const double *Ub = ori ? &S.fr[3] : &S.fr[15];
                 const double s = ori ? -1.0 : 1.0;
                 const double v0 = s * gd0, v1 = s * gd1, v2 = s * gd2;            // glycosidic_displacement
                 const double dZ = v0 * Ua[2] + v1 * Ua[5] + v2 * Ua[8];            // displ12[2] (NA:847)
-
-                if (cp_frames && !marked_cp) {                                     // remaining coplanar conditions
-                    if (!have_gaps) compute_gaps();
-                    const double gab = ori ? gap21 : gap12;
-                    if (gab < 1.5179) {
-                        if (!have_mind) compute_mind();
-                        const bool both_std = (bm1 >> 20 & 1u) && (bm2 >> 20 & 1u);
-                        if (mind < 3.4589 && !(mind >= 2.4589 && both_std)) {
-                            hmask |= 1u << FR3D_SLOT_CP;
-                            marked_cp = true;
-                        }
-                    }
-                }
-
-                // ---- check_basepair_cutoffs, NA:2364-2759 (datapoint = None)
                 if (fabs(dZ) > 3.6) continue;                                      // NA:2380
                 const double dX = v0 * Ua[0] + v1 * Ua[3] + v2 * Ua[6];
                 const double dY = v0 * Ua[1] + v1 * Ua[4] + v2 * Ua[7];
                 const int sg = nZ > 0 ? 0 : 1;
                 const int bstart = box_index[(combo * 2 + sg) * 2 + 0];
                 const int bcount = box_index[(combo * 2 + sg) * 2 + 1];
-                if (bcount <= 0) continue;
                 const bool mine = lane < bcount;
                 const fr3d_box_t *bx = boxes + bstart + (mine ? lane : 0);
                 double cd = 1e300;
-                int flags = 0;
-                if (mine) {
-                    flags = bx->flags;
+                if (mine) {                                                        // NA:2546-2581
                     cd = 0.0;
                     cd += fmax(0.0, bx->xmin - dX);
                     cd += fmax(0.0, dX - bx->xmax);
                     cd += fmax(0.0, bx->ymin - dY);
                     cd += fmax(0.0, dY - bx->ymax);
-                    if (flags & 8) cd += fmax(0.0, sqrt(dX * dX + dY * dY) - bx->radiusmax);
+                    if (bx->flags & 8) cd += fmax(0.0, sqrt(dX * dX + dY * dY) - bx->radiusmax);
                     cd += fmax(0.0, bx->zmin - dZ);
                     cd += fmax(0.0, dZ - bx->zmax);
                     cd += 3.0 * fmax(0.0, bx->normalmin - nZ);
                     cd += 3.0 * fmax(0.0, nZ - bx->normalmax);
                 }
-                bool ok = mine && cd < 1.0;                                        // NA:2580
+                bool ok = cd < 1.0;                                                // NA:2580
                 if (!__any_sync(FULL, ok)) continue;                               // NA:2584
                 const double M11 = Ua[1] * Ub[1] + Ua[4] * Ub[4] + Ua[7] * Ub[7];
                 const double M01 = Ua[0] * Ub[1] + Ua[3] * Ub[4] + Ua[6] * Ub[7];
-                double ang = atan2(M11, M01) * 57.29577951308232 - 90.0;           // NA:2594
+                double ang = atan2_once(M11, M01) * 57.29577951308232 - 90.0;      // NA:2594
                 if (ang <= -90.0) ang += 360.0;
                 if (ok) {
                     const double amin = bx->anglemin, amax = bx->anglemax;
@@ -588,11 +508,82 @@ classify_pairs_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, cons
                     ok = cd < 1.0;                                                 // NA:2611
                 }
                 if (!__any_sync(FULL, ok)) continue;                               // NA:2615
-                if (!have_gaps) compute_gaps();
-                if (!have_mind) compute_mind();
-                const double gmax = fmax(gap12, gap21);
+                bp_live |= 1u << ori;
+                if (!ok) cd = 1e300;
+                if (ori) cd1 = cd; else cd0 = cd;
+            }
+        }
+
+        // ================= part 2: gaps and minimum base-base distance, once, only if needed =================
+        double gap12 = 100.0, gap21 = 100.0, mind = 9999.0;
+        const bool need_gaps = bp_live || cp_frames;
+        if (need_gaps) {                          // calculate_basepair_gap, NA:2189-2259, both directions at once
+            // squared distance to the other base centre orders the atoms like the reference's argsort
+            double key = valid ? ((px - fo[0]) * (px - fo[0]) + (py - fo[1]) * (py - fo[1]) +
+                                  (pz - fo[2]) * (pz - fo[2])) : 1e300;
+            double g = 100.0;
+#pragma unroll 1
+            for (int r = 0; r < 3; ++r) {
+                double k = key; int idx = a;
+                group_argmin<16>(k, idx);
+                const double zz = fabs(__shfl_sync(FULL, z, (lane & 16) | idx));
+                if (k < 1e299) {
+                    if (zz < g) g = zz;
+                    if (a == idx) key = 1e300;
+                }
+            }
+            gap12 = __shfl_sync(FULL, g, 0);
+            gap21 = __shfl_sync(FULL, g, 16);
+        }
+        const bool cp_gap = cp_frames && (((ori_ok & 1u) && gap12 < 1.5179) || ((ori_ok & 2u) && gap21 < 1.5179));
+        if (stack_code >= 0 || bp_live || cp_gap) {   // calculate_base_min_distances, NA:1799-1829
+            // lower half: nt2 atom `a` against nt1 atoms 0-7; upper half: nt2 atom `a` against nt1 atoms 8-15
+            const bool v2 = (bm2 >> a) & 1u;
+            const double qx = S.atoms[a][0], qy = S.atoms[a][1], qz = S.atoms[a][2];
+            double best = 1e300;
+#pragma unroll 2
+            for (int s = 0; s < 8; ++s) {
+                const int k1 = s + 8 * half;
+                if (v2 && ((bm1 >> k1) & 1u)) {
+                    const double dx = S.atoms[16 + k1][0] - qx, dy = S.atoms[16 + k1][1] - qy,
+                                 dz = S.atoms[16 + k1][2] - qz;
+                    best = fmin(best, dx * dx + dy * dy + dz * dz);
+                }
+            }
+            best = group_min<32>(best);
+            mind = best < 1e299 ? sqrt(best) : 9999.0;
+        }
+
+        // ---- stacking, part 2 (NA:1707-1718)
+        if (stack_code >= 0 && !(fabs(mind) < 1.0)) {
+            int near = 1;
+            if (fabs(mind) < 4.0 && fabs(mind) > 1.0 && fabs(nZ) > 0.6 && stack_both) near = 0;
+            hmask |= 1u << FR3D_SLOT_STACK;
+            c_stack = stack_code | (near << 2);
+        }
+        // ---- coplanar, part 2 (NA:2080-2096): orientation 12 or, failing that, 21 (NA:856-911)
+        if (cp_gap) {
+            const bool both_std = (bm1 >> 20 & 1u) && (bm2 >> 20 & 1u);
+            if (mind < 3.4589 && !(mind >= 2.4589 && both_std)) hmask |= 1u << FR3D_SLOT_CP;
+        }
+        // ---- basepair, part 2: gap term, true / near classification, choice (NA:2642-2759)
+        if (bp_live) {
+            const double gmax = fmax(gap12, gap21);
+            int box_sel[2] = {-1, -1}, near_sel[2] = {0, 0};
+            double cd_sel[2] = {0.0, 0.0};
+#pragma unroll
+            for (int ori = 0; ori < 2; ++ori) {
+                if (!((bp_live >> ori) & 1u)) continue;
+                const int pa = ori ? par2 : par1, pb = ori ? par1 : par2;
+                const int combo = pa * FR3D_N_PARENTS + pb;
+                const int bstart = box_index[(combo * 2 + (nZ > 0 ? 0 : 1)) * 2 + 0];
+                double cd = ori ? cd1 : cd0;
+                const bool ok = cd < 1e299;
+                const fr3d_box_t *bx = boxes + bstart + (ok ? lane : 0);
                 bool is_match = false, is_near = false;
+                int flags = 0;
                 if (ok) {
+                    flags = bx->flags;
                     const double gapmax = bx->gapmax;
                     if (gapmax > 0.1) cd += 4.0 * fmax(0.0, gmax - gapmax);        // NA:2643-2645
                     bool one_hb = false;                                           // NA:2648-2652
@@ -611,47 +602,41 @@ classify_pairs_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, cons
                 }
                 const unsigned match_b = __ballot_sync(FULL, is_match);
                 const unsigned near_b = __ballot_sync(FULL, is_near);
-                int sel = -1;
-                if (match_b) {                     // stable sort by (subcategory, len(name)), NA:2682
-                    double key = is_match ? (double)(bx->subcat * 64 + bx->name_len) : 1e300;
+                if (match_b | near_b) {
+                    // true matches: stable sort by (subcategory, len(name)) (NA:2682); else the nearest near
+                    // match (NA:2685-2686); ties go to the earlier box like Python's stable sort
+                    double key = 1e300;
+                    if (match_b) { if (is_match) key = (double)(bx->subcat * 64 + bx->name_len); }
+                    else if (is_near) key = cd;
                     int idx = lane;
                     group_argmin<32>(key, idx);
-                    sel = idx;
-                } else if (near_b) {               // nearest near match, NA:2685-2686
-                    double key = is_near ? cd : 1e300;
-                    int idx = lane;
-                    group_argmin<32>(key, idx);
-                    sel = idx;
-                }
-                if (sel >= 0) {
-                    const double cds = __shfl_sync(FULL, cd, sel);
-                    const int fls = __shfl_sync(FULL, flags, sel);
-                    res[ori].box = bstart + sel;
-                    res[ori].cd = cds;
-                    res[ori].near = (cds > 0 && !(fls & 1)) ? 1 : 0;              // NA:2693-2696
-                    if (fls & 1) res[ori].near |= 2;                               // an n-named box also has "n" in its label
+                    const double cds = __shfl_sync(FULL, cd, idx);
+                    const int fls = __shfl_sync(FULL, flags, idx);
+                    box_sel[ori] = bstart + idx;
+                    cd_sel[ori] = cds;
+                    // NA:2693-2696; bit1: an n-named box also carries "n" in its label
+                    near_sel[ori] = ((cds > 0 && !(fls & 1)) ? 1 : 0) | ((fls & 1) ? 2 : 0);
                 }
             }
             // ---- 12-vs-21 arbitration, NA:935-957
             int use = -1;
-            if (res[0].box >= 0 && res[1].box >= 0) {
-                const bool n0 = res[0].near != 0, n1_ = res[1].near != 0;
+            if (box_sel[0] >= 0 && box_sel[1] >= 0) {
+                const bool n0 = near_sel[0] != 0, n1_ = near_sel[1] != 0;
                 // interaction12_reversed.lower() == interaction21.lower(): same "n" prefix state and same family
-                const bool same = ((res[0].near & 1) == (res[1].near & 1)) &&
-                                  (boxes[res[0].box].rev_lower_id == boxes[res[1].box].lower_id);
+                const bool same = ((near_sel[0] & 1) == (near_sel[1] & 1)) &&
+                                  (boxes[box_sel[0]].rev_lower_id == boxes[box_sel[1]].lower_id);
                 if (same) use = 0;
-                else if (n0 && n1_) use = (res[0].cd < res[1].cd) ? 0 : 1;
+                else if (n0 && n1_) use = (cd_sel[0] < cd_sel[1]) ? 0 : 1;
                 else if (n1_) use = 0;
                 else if (n0) use = 1;
                 else use = 0;
-            } else if (res[0].box >= 0) use = 0;
-            else if (res[1].box >= 0) use = 1;
+            } else if (box_sel[0] >= 0) use = 0;
+            else if (box_sel[1] >= 0) use = 1;
             if (use >= 0) {
                 hmask |= 1u << FR3D_SLOT_BP;
-                c_bp = (res[use].near & 1) | (use << 1);
-                bp_box = res[use].box;
-                bp_cd = res[use].cd;
-                bp_gap = fmax(gap12, gap21);
+                c_bp = (near_sel[use] & 1) | (use << 1);
+                bp_box = box_sel[use];
+                bp_cd = cd_sel[use];
             }
         }
 
@@ -676,7 +661,7 @@ classify_pairs_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, cons
                         default: break;
                     }
                     const bool isbp = lane == FR3D_SLOT_BP;
-                    const double cdv = isbp ? bp_cd : 0.0, gv = isbp ? bp_gap : 0.0;
+                    const double cdv = isbp ? bp_cd : 0.0, gv = isbp ? fmax(gap12, gap21) : 0.0;
                     const uint32_t w3 = (uint32_t)lane | ((uint32_t)mycode << 8) | ((uint32_t)(isbp ? bp_box : 0) << 16);
                     uint4 *dst = reinterpret_cast<uint4 *>(hits + pos);
                     dst[0] = make_uint4((uint32_t)n1, (uint32_t)n2, (uint32_t)rank, w3);
