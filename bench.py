@@ -190,7 +190,19 @@ def main():
         raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL prints its version banner on stdout at communicator creation; the contract is ONE JSON
+        # line on stdout, so stdout is pointed at stderr while the communicator is built
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     sampler = ClockSampler(local_rank) if rank == 0 else None
 
     eng = Engine.get(local_rank)
