@@ -10,7 +10,7 @@ import subprocess
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libfr3d_b200.so")
+LIB_PATH = os.environ.get("FR3D_B200_LIB") or os.path.join(_HERE, "lib", "libfr3d_b200.so")   # env: A/B builds
 CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 
@@ -102,7 +102,7 @@ def load():
         lib.fr3d_pair_search_workspace.argtypes = [i32]
         lib.fr3d_pair_search_workspace.restype = C.c_size_t
         lib.fr3d_pair_search.argtypes = [C.POINTER(NtsStruct), dbl, vp, C.c_size_t, vp, vp, vp, i64, vp, vp]
-        lib.fr3d_classify_pairs.argtypes = [C.POINTER(NtsStruct), vp, vp, vp, vp, vp, i64, C.c_uint32, vp, i64, vp, vp]
+        lib.fr3d_classify_pairs.argtypes = [C.POINTER(NtsStruct), vp, vp, vp, vp, vp, i64, C.c_uint32, i32, vp, i64, vp, vp]
         lib.fr3d_kabsch_batched.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp]
         lib.fr3d_discrepancy_all_vs_all.argtypes = [vp, vp, vp, i32, i32, dbl, i32, i32, vp, vp]
         lib.fr3d_discrepancy_one_vs_many.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, dbl, dbl, vp, vp, vp]

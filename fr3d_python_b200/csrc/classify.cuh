@@ -239,10 +239,13 @@ __device__ __noinline__ int backbone_select(const WarpScratch &S, int par1, uint
     return (bph & 0xFF) | ((br & 0xFF) << 8);
 }
 
-__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, 4)
+#ifndef FR3D_CLASSIFY_MIN_BLOCKS
+#define FR3D_CLASSIFY_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, FR3D_CLASSIFY_MIN_BLOCKS)
 classify_pairs_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, const int32_t *__restrict__ box_index,
                       const int32_t *__restrict__ pair_i, const int32_t *__restrict__ pair_j,
-                      const int32_t *__restrict__ pair_rank, int64_t pair_cap, uint32_t cats,
+                      const int32_t *__restrict__ pair_rank, int64_t pair_cap, uint32_t cats, int32_t index_offset,
                       fr3d_hit_t *__restrict__ hits, int64_t hit_cap, int64_t *counters) {
     __shared__ WarpScratch s_scratch[WARPS_PER_BLOCK];
 
@@ -265,15 +268,9 @@ classify_pairs_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, cons
         if (p + nwarps < n_pairs) { nx1 = pair_i[p + nwarps]; nx2 = pair_j[p + nwarps]; nxr = pair_rank[p + nwarps]; }
 
         // ---- stage: frames (24 doubles), base atoms (32 x 3), backbone atoms (20 x 3), masks
-        const uint32_t bm1 = nts.base_mask[n1], bm2 = nts.base_mask[n2];
-        const uint32_t bb1 = nts.bb_mask[n1], bb2 = nts.bb_mask[n2];
-        const int par1 = (int)((bm1 >> 16) & 15u) - 1, par2 = (int)((bm2 >> 16) & 15u) - 1;
-        const bool valid = ((half ? bm1 : bm2) >> a) & 1u;
-        double px = 0, py = 0, pz = 0;
-        if (valid) {
-            const double *q = nts.base_xyz + ((size_t)(half ? n1 : n2) * FR3D_BASE_SLOTS + a) * 3;
-            px = q[0]; py = q[1]; pz = q[2];
-        }
+        // absent slots hold zeros (packer / K1), so the atom loads do not wait for the masks
+        const double *qa = nts.base_xyz + ((size_t)(half ? n1 : n2) * FR3D_BASE_SLOTS + a) * 3;
+        const double px = qa[0], py = qa[1], pz = qa[2];
         double fv = 0.0;
         if (lane < 24) {
             const int n = lane < 12 ? n1 : n2;
@@ -282,12 +279,13 @@ classify_pairs_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, cons
         }
         double bx_ = 0, by_ = 0, bz_ = 0;
         if (lane < 20) {
-            const int e = lane < 10 ? lane : lane - 10;
-            if (((lane < 10 ? bb2 : bb1) >> e) & 1u) {
-                const double *q = nts.bb_xyz + ((size_t)(lane < 10 ? n2 : n1) * FR3D_BB_SLOTS + e) * 3;
-                bx_ = q[0]; by_ = q[1]; bz_ = q[2];
-            }
+            const double *q = nts.bb_xyz + ((size_t)(lane < 10 ? n2 : n1) * FR3D_BB_SLOTS + (lane < 10 ? lane : lane - 10)) * 3;
+            bx_ = q[0]; by_ = q[1]; bz_ = q[2];
         }
+        const uint32_t bm1 = nts.base_mask[n1], bm2 = nts.base_mask[n2];
+        const uint32_t bb1 = nts.bb_mask[n1], bb2 = nts.bb_mask[n2];
+        const int par1 = (int)((bm1 >> 16) & 15u) - 1, par2 = (int)((bm2 >> 16) & 15u) - 1;
+        const bool valid = ((half ? bm1 : bm2) >> a) & 1u;
         __syncwarp();
         S.atoms[lane][0] = px; S.atoms[lane][1] = py; S.atoms[lane][2] = pz;
         if (lane < 24) S.fr[lane] = fv;
@@ -394,7 +392,9 @@ classify_pairs_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, cons
         if ((cats & FR3D_CAT_SUGAR_RIBOSE) && par1 >= 0 && par2 >= 0 && par1 != 4 && par2 != 4 &&
             (bb1 >> 6 & 1u) && (bb2 >> 6 & 1u)) {
             // both directions start with the same O2'-O2' distance screen (NA:2281-2286)
-            if (!(dist3(S.bb[16], S.bb[6]) > 3.8)) {
+            const double o0 = S.bb[16][0] - S.bb[6][0], o1 = S.bb[16][1] - S.bb[6][1], o2 = S.bb[16][2] - S.bb[6][2];
+            const double oo = o0 * o0 + o1 * o1 + o2 * o2;
+            if (oo < 14.4401 && !(sqrt(oo) > 3.8)) {
                 const int s1 = c_tab.sr_slot[par1], s2 = c_tab.sr_slot[par2];
                 const int r12 = sugar_ribose_tail(&S.bb[10], &S.bb[0], bb1, bb2, s1 >= 0 && ((bm1 >> s1) & 1u),
                                                   S.atoms[16 + (s1 < 0 ? 0 : s1)], U1(2), U1(5), U1(8));
@@ -418,15 +418,18 @@ classify_pairs_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, cons
                 if ((bb2 >> oslot & 1u) && (bm1 >> hs & 1u) && (bm1 >> ms & 1u)) {
                     const double *O = S.bb[oslot];
                     if (O[0] != 0.0 || O[1] != 0.0 || O[2] != 0.0) {            // .any(), NA:1939,1959
-                        dst = dist3(S.atoms[16 + ms], O);
-                        // every true / near label needs distance < nCutoff (4.5 carbon, 4.0 nitrogen)
-                        cand = dst < (c_tab.site_carbon[par1][site] == 0 ? 4.0 : 4.5);
+                        const double *Mv = S.atoms[16 + ms];
+                        const double q0 = Mv[0] - O[0], q1 = Mv[1] - O[1], q2 = Mv[2] - O[2];
+                        dst = q0 * q0 + q1 * q1 + q2 * q2;
+                        // every true / near label needs distance < nCutoff (4.5 carbon, 4.0 nitrogen); the vote
+                        // is on the square (a superset), the exact tests on the distance follow in the selection
+                        cand = dst < (c_tab.site_carbon[par1][site] == 0 ? 16.0001 : 20.2501);
                     }
                 }
             }
             if (__any_sync(FULL, cand)) {
                 double ang = 0.0;
-                if (cand) ang = hb_angle(S.atoms[16 + ms], S.atoms[16 + hs], S.bb[oslot]);
+                if (cand) { ang = hb_angle(S.atoms[16 + ms], S.atoms[16 + hs], S.bb[oslot]); dst = sqrt(dst); }
                 else dst = 0.0;                    // not a candidate: the selection skips it
                 __syncwarp();
                 S.ang[lane] = ang; S.dst[lane] = dst;
@@ -452,11 +455,12 @@ classify_pairs_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, cons
             if (c_tab.combo_ok[par1 * FR3D_N_PARENTS + par2]) ori_ok |= 1u;
             if (c_tab.combo_ok[par2 * FR3D_N_PARENTS + par1]) ori_ok |= 2u;
             if ((cats & FR3D_CAT_COPLANAR) && ori_ok && fabs(nZ) > 0.7757) {
-                double e0 = C1(0) - C2(0), e1 = C1(1) - C2(1), e2 = C1(2) - C2(2);
-                const double en = sqrt(e0 * e0 + e1 * e1 + e2 * e2);
-                e0 /= en; e1 /= en; e2 /= en;
-                cp_frames = fabs(e0 * U1(2) + e1 * U1(5) + e2 * U1(8)) < 0.3381 &&
-                            fabs(e0 * U2(2) + e1 * U2(5) + e2 * U2(8)) < 0.3381;
+                // |e . n| / |e| < 0.3381 written without the square root and the three divisions
+                const double e0 = C1(0) - C2(0), e1 = C1(1) - C2(1), e2 = C1(2) - C2(2);
+                const double lim = (0.3381 * 0.3381) * (e0 * e0 + e1 * e1 + e2 * e2);
+                const double d1 = e0 * U1(2) + e1 * U1(5) + e2 * U1(8);
+                const double d2 = e0 * U2(2) + e1 * U2(5) + e2 * U2(8);
+                cp_frames = d1 * d1 < lim && d2 * d2 < lim;
             }
             // glycosidic displacement: slot 0 = N9 / N1
             const double gd0 = S.atoms[0][0] - S.atoms[16][0], gd1 = S.atoms[0][1] - S.atoms[16][1],
@@ -664,7 +668,8 @@ classify_pairs_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, cons
                     const double cdv = isbp ? bp_cd : 0.0, gv = isbp ? fmax(gap12, gap21) : 0.0;
                     const uint32_t w3 = (uint32_t)lane | ((uint32_t)mycode << 8) | ((uint32_t)(isbp ? bp_box : 0) << 16);
                     uint4 *dst = reinterpret_cast<uint4 *>(hits + pos);
-                    dst[0] = make_uint4((uint32_t)n1, (uint32_t)n2, (uint32_t)rank, w3);
+                    dst[0] = make_uint4((uint32_t)(n1 + index_offset), (uint32_t)(n2 + index_offset),
+                                        (uint32_t)(rank + 16 * index_offset), w3);
                     dst[1] = make_uint4((uint32_t)__double2loint(cdv), (uint32_t)__double2hiint(cdv),
                                         (uint32_t)__double2loint(gv), (uint32_t)__double2hiint(gv));
                 }

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/fr3d_b200.h"
@@ -129,7 +130,8 @@ int fr3d_pair_search(const fr3d_nts_t *nts, double cell_size, void *workspace, s
 
 int fr3d_classify_pairs(const fr3d_nts_t *nts, const fr3d_box_t *boxes, const int32_t *box_index,
                         const int32_t *pair_i, const int32_t *pair_j, const int32_t *pair_rank, int64_t pair_cap,
-                        uint32_t category_mask, fr3d_hit_t *hits, int64_t hit_cap, int64_t *counters, void *stream) {
+                        uint32_t category_mask, int32_t index_offset, fr3d_hit_t *hits, int64_t hit_cap, int64_t *counters,
+                        void *stream) {
     if (!nts || !boxes || !box_index || !pair_i || !pair_j || !pair_rank || !hits || !counters)
         return fail(FR3D_E_ARG, "NULL argument");
     if (!g_tables_loaded) return fail(FR3D_E_NOTABLES, "fr3d_upload_tables not called");
@@ -137,11 +139,16 @@ int fr3d_classify_pairs(const fr3d_nts_t *nts, const fr3d_box_t *boxes, const in
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // persistent warps: grid is a multiple of the SM count; n_pairs is read on the device
     long long want = (pair_cap + fr3d::WARPS_PER_BLOCK - 1) / fr3d::WARPS_PER_BLOCK;
-    long long maxgrid = (long long)g_sm_count * 16;
+    static int mult = -1;                       // blocks per SM of the persistent grid (tuning knob)
+    if (mult < 0) {
+        const char *e = getenv("FR3D_CLASSIFY_GRID_MULT");
+        mult = (e && atoi(e) > 0) ? atoi(e) : 16;
+    }
+    long long maxgrid = (long long)g_sm_count * mult;
     int grid = (int)(want < maxgrid ? want : maxgrid);
     if (grid < 1) grid = 1;
     fr3d::classify_pairs_kernel<<<grid, fr3d::WARPS_PER_BLOCK * 32, 0, st>>>(
-        *nts, boxes, box_index, pair_i, pair_j, pair_rank, pair_cap, category_mask, hits, hit_cap, counters);
+        *nts, boxes, box_index, pair_i, pair_j, pair_rank, pair_cap, category_mask, index_offset, hits, hit_cap, counters);
     CUDA_TRY(cudaGetLastError());
     return FR3D_OK;
 }

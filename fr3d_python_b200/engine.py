@@ -194,7 +194,7 @@ class Engine(object):
         p.status = torch.empty(max(n_nt, 1), dtype=torch.int32, device=dev)
         return p
 
-    def run_plan(self, dbatch, plan, boxtable, category_mask, fit_frames=True, events=None):
+    def run_plan(self, dbatch, plan, boxtable, category_mask, fit_frames=True, events=None, index_offset=0):
         """K1 -> K2/K3 -> K4 on the current stream, asynchronously.  `events` (dict) receives
         torch CUDA events around the classify launch for per-kernel timing."""
         torch = self.torch
@@ -217,7 +217,8 @@ class Engine(object):
             _lib.check(self.lib.fr3d_classify_pairs(C.byref(dbatch.nts), bx.data_ptr(), ix.data_ptr(),
                                                     plan.pair_i.data_ptr(), plan.pair_j.data_ptr(),
                                                     plan.pair_rank.data_ptr(), plan.pair_cap, int(category_mask),
-                                                    plan.hits.data_ptr(), plan.hit_cap, plan.counters.data_ptr(), st),
+                                                    int(index_offset), plan.hits.data_ptr(), plan.hit_cap,
+                                                    plan.counters.data_ptr(), st),
                        "fr3d_classify_pairs")
             self.launches += 1
             if events is not None:
@@ -263,3 +264,90 @@ class Engine(object):
 
 class Plan(object):
     pass
+
+
+_FIELDS = ("center", "rot", "base_xyz", "bb_xyz", "base_mask", "bb_mask", "meta")
+
+
+class Pipeline(object):
+    """Chunked, multi-stream form of Engine.annotate_batch for large batches: structures are
+    independent, so the batch is cut into contiguous chunks of whole structures and chunk k+1's
+    H2D copy overlaps chunk k's kernels and chunk k-1's D2H copy.  All device / pinned buffers are
+    allocated once and re-used across calls.  Frames are always fitted on the device (K1), so the
+    centre / rotation planes are not uploaded."""
+
+    def __init__(self, engine, batch, pinned, boxtable, category_mask, n_chunks=4, pair_cap=None, hit_cap=None,
+                 n_streams=3):
+        torch = engine.torch
+        self.eng, self.batch, self.pinned, self.bt, self.mask = engine, batch, pinned, boxtable, category_mask
+        if batch.frames_given:
+            raise _lib.Fr3dError("Pipeline uploads observed atoms only; frames are fitted on the device")
+        S = batch.n_structures
+        n_chunks = max(1, min(n_chunks, S))
+        bounds = [int(round(k * S / n_chunks)) for k in range(n_chunks + 1)]
+        self.chunks = []
+        dev = engine.device
+        self.streams = [torch.cuda.Stream(device=dev) for _ in range(min(n_streams, n_chunks))]
+        for k in range(n_chunks):
+            lo, hi = int(batch.struct_off[bounds[k]]), int(batch.struct_off[bounds[k + 1]])
+            n = hi - lo
+            ch = Plan()
+            ch.lo, ch.hi, ch.n = lo, hi, n
+            ch.stream = self.streams[k % len(self.streams)]
+            ch.dev = {name: torch.empty((n,) + tuple(getattr(batch, name).shape[1:]),
+                                        dtype=pinned[name].dtype, device=dev) for name in _FIELDS}
+            t = ch.dev
+            ch.nts = _lib.NtsStruct(n_nt=n, reserved=0, center=t["center"].data_ptr(), rot=t["rot"].data_ptr(),
+                                    base_xyz=t["base_xyz"].data_ptr(), bb_xyz=t["bb_xyz"].data_ptr(),
+                                    base_mask=t["base_mask"].data_ptr(), bb_mask=t["bb_mask"].data_ptr(),
+                                    meta=t["meta"].data_ptr())
+            frac = n / max(batch.n, 1)
+            pc = int((pair_cap or (12 * batch.n + 1024)) * frac * 1.15) + 4096
+            hc = int((hit_cap or (12 * batch.n + 1024)) * frac * 1.15) + 4096
+            ch.plan = engine.make_plan(n, pc, hc)
+            ch.counters_host = torch.zeros(4, dtype=torch.int64).pin_memory()
+            ch.ev = torch.cuda.Event()
+            self.chunks.append(ch)
+        total_hc = sum(ch.plan.hit_cap for ch in self.chunks)
+        self.hits_host = torch.empty(total_hc * HIT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+        self.hits_np = self.hits_host.numpy()
+        self.h2d_bytes = sum(int(pinned[name][0:1].element_size()) * int(np.prod(pinned[name].shape))
+                             for name in _FIELDS if name not in ("center", "rot"))
+
+    def run(self):
+        """One pass.  Returns (hits, n_pairs): hits is a structured-array VIEW of the pipeline's pinned
+        result buffer with GLOBAL nt indices (valid until the next run())."""
+        eng, torch = self.eng, self.eng.torch
+        main = torch.cuda.current_stream(eng.device)
+        start = torch.cuda.Event()
+        start.record(main)
+        for ch in self.chunks:
+            ch.stream.wait_event(start)
+            with torch.cuda.stream(ch.stream):
+                for name in _FIELDS:
+                    if name in ("center", "rot"):
+                        continue
+                    ch.dev[name].copy_(self.pinned[name][ch.lo:ch.hi], non_blocking=True)
+                eng.run_plan(ch, ch.plan, self.bt, self.mask, fit_frames=True, index_offset=ch.lo)
+                ch.counters_host.copy_(ch.plan.counters, non_blocking=True)
+                ch.ev.record(ch.stream)
+        n_pairs = 0
+        off = 0
+        for ch in self.chunks:
+            ch.ev.synchronize()
+            cnt = ch.counters_host
+            if int(cnt[2]) != 0:
+                raise _lib.Fr3dError("fr3d_pair_search: base centre outside the spatial-hash range (FR3D_E_RANGE)")
+            npairs, nhits = int(cnt[0]), int(cnt[1])
+            if npairs > ch.plan.pair_cap or nhits > ch.plan.hit_cap:
+                raise _lib.Fr3dError("pipeline chunk capacity exceeded (pairs %d/%d, hits %d/%d): rebuild the "
+                                     "Pipeline with larger capacities" % (npairs, ch.plan.pair_cap, nhits,
+                                                                          ch.plan.hit_cap))
+            n_pairs += npairs
+            nb = nhits * HIT_DTYPE.itemsize
+            with torch.cuda.stream(ch.stream):
+                self.hits_host[off:off + nb].copy_(ch.plan.hits[:nb], non_blocking=True)
+            off += nb
+        for st in self.streams:
+            st.synchronize()
+        return self.hits_np[:off].view(HIT_DTYPE), n_pairs

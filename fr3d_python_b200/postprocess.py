@@ -54,6 +54,11 @@ class StructureIdentity(object):
         lo, hi = int(batch.struct_off[s]), int(batch.struct_off[s + 1])
         self.lo, self.hi = lo, hi
         self.chain = batch.chain[lo:hi]
+        self.chain_code = batch.meta[lo:hi, 3]          # rank of the chain id among the batch's chain ids
+        self.code_to_chain = {}
+        for c, name in zip(self.chain_code.tolist(), self.chain):
+            if c not in self.code_to_chain:
+                self.code_to_chain[c] = name
         self.index = batch.meta[lo:hi, 4]
         self.parent = batch.meta[lo:hi, 0]
         self.model = batch.model[lo:hi]
@@ -111,21 +116,23 @@ def same_edge_cleanup(u2bp):
 _NESTED_FAMILIES = ['cWW', 'cWw', 'cwW', 'acWW', 'acWw', 'acwW']
 _NESTED_PARENTS = {(0, 3), (3, 0), (1, 2), (2, 1), (2, 3), (3, 2)}      # AU UA CG GC GU UG (NA:1089)
 _DUP_STACK = {"s33", "s35", "s53", "s55", "cp", "ns33", "ns35", "ns53", "ns55"}
+_CROSS_CHUNK = 1 << 22      # elements of the (queries x nested pairs) broadcast handled at once
 
 
-def crossing_numbers(ident, i2p):
-    """calculate_crossing_numbers, NA:1057-1179, on local nt positions.  Chains are keyed by chain
-    id only (models / symmetry copies share a table).  The inner counting loop
-    (NA:1159-1164) is a vectorised slice per pair."""
+def _nested_endpoints(ident, i2p):
+    """Greedy nested-cWW selection of calculate_crossing_numbers (NA:1063-1131) per chain id."""
     chain = ident.chain
     index = ident.index
-    chain_max = defaultdict(lambda: 0)
-    for c, ix in zip(chain, index):
-        if ix > chain_max[c]:
-            chain_max[c] = int(ix)
+    chain_max = {}
+    for c, ix in zip(chain, index.tolist()):
+        if ix > chain_max.get(c, 0):
+            chain_max[c] = ix
     chain_cww = defaultdict(list)
     for inter in _NESTED_FAMILIES:
-        for a, b in i2p.get(inter, ()):
+        ab = i2p.get(inter)
+        if ab is None:
+            continue
+        for a, b in zip(ab[0], ab[1]):
             if chain[a] == chain[b]:
                 if (int(ident.parent[a]), int(ident.parent[b])) in _NESTED_PARENTS:
                     i1, i2 = int(index[a]), int(index[b])
@@ -133,7 +140,7 @@ def crossing_numbers(ident, i2p):
     nested = {}
     for c, pairs in chain_cww.items():
         pairs = sorted(pairs, key=lambda p: (p[1] - p[0], p[0]))
-        ends = list(range(0, chain_max[c] + 1))
+        ends = list(range(0, chain_max.get(c, 0) + 1))
         for i1, i2 in pairs:
             i = i1 + 1
             while i < i2 and ends[i] > i1 and ends[i] < i2:
@@ -141,98 +148,185 @@ def crossing_numbers(ident, i2p):
             if i == i2:
                 ends[i1] = i2
                 ends[i2] = i1
-        nested[c] = np.array(ends, dtype=np.int64)
+        e = np.array(ends, dtype=np.int64)
+        left = np.nonzero(e > np.arange(len(e)))[0]          # nested pairs (p, q), p < q
+        nested[c] = (left, e[left])
+    return nested
+
+
+def _crossing_counts(i1, i2, P, Q):
+    """For each query span (i1, i2), i1 <= i2: number of positions i with i1 < i < i2 whose nested
+    partner lies outside [i1, i2] (NA:1159-1164), as one broadcast over the nested pairs (P, Q)."""
+    out = np.zeros(len(i1), dtype=np.int64)
+    if len(P) == 0 or len(i1) == 0:
+        return out
+    step = max(1, _CROSS_CHUNK // len(P))
+    for lo in range(0, len(i1), step):
+        a = i1[lo:lo + step, None]
+        b = i2[lo:lo + step, None]
+        p_in = (P > a) & (P < b)
+        q_in = (Q > a) & (Q < b)
+        p_out = (P < a) | (P > b)
+        q_out = (Q < a) | (Q > b)
+        out[lo:lo + step] = np.count_nonzero((p_in & q_out) | (q_in & p_out), axis=1)
+    return out
+
+
+def crossing_numbers(ident, i2p):
+    """calculate_crossing_numbers, NA:1057-1179, on local nt positions.  i2p: label -> (A, B) lists of
+    nt positions in recording order.  Chains are keyed by chain id only (models / symmetry copies
+    share a table).  The per-pair counting loop (NA:1159-1164) is vectorised over all
+    rows of a label; the duplication of pairs in reversed order follows NA:1171-1177."""
+    nested = _nested_endpoints(ident, i2p)
+    chain_code = ident.chain_code
+    code_to_chain = ident.code_to_chain
+    index = ident.index
     uid = ident.unit_id
+    labels = [l for l, ab in i2p.items() if l != "" and len(ab[0])]
     out = defaultdict(list)
-    for inter, plist in i2p.items():
-        if inter == "" or not plist:
-            continue
-        rev = None
+    if not labels:
+        return out
+    sizes = [len(i2p[l][0]) for l in labels]
+    A = np.fromiter((k for l in labels for k in i2p[l][0]), dtype=np.int64, count=sum(sizes))
+    B = np.fromiter((k for l in labels for k in i2p[l][1]), dtype=np.int64, count=sum(sizes))
+    cross = np.zeros(len(A), dtype=np.int64)
+    if nested:                                   # one broadcast per chain over the rows of ALL labels
+        ca = chain_code[A]
+        same = ca == chain_code[B]
+        if same.any():
+            ia, ib = index[A], index[B]
+            lo_, hi_ = np.minimum(ia, ib), np.maximum(ia, ib)
+            for c in np.unique(ca[same]).tolist():
+                name = code_to_chain[c]
+                if name in nested:
+                    rows = np.nonzero(same & (ca == c))[0]
+                    P, Q = nested[name]
+                    cross[rows] = _crossing_counts(lo_[rows], hi_[rows], P, Q)
+    ua_all = [uid[k] for k in A.tolist()]
+    ub_all = [uid[k] for k in B.tolist()]
+    cl_all = cross.tolist()
+    pos = 0
+    for inter, n in zip(labels, sizes):
+        ua, ub, cl = ua_all[pos:pos + n], ub_all[pos:pos + n], cl_all[pos:pos + n]
+        pos += n
+        fwd = list(zip(ua, ub, cl))
         if inter in _DUP_STACK or inter[0] in "ct" or inter[0:2] in ("nc", "nt"):
             rev = reverse_edges(inter)
-        dst = out[inter]
-        for a, b in plist:
-            crossing = 0
-            ca = chain[a]
-            if ca == chain[b] and ca in nested:
-                i1, i2 = int(index[a]), int(index[b])
-                if i1 > i2:
-                    i1, i2 = i2, i1
-                if i2 - i1 > 1:
-                    seg = nested[ca][i1 + 1:i2]
-                    crossing = int(np.count_nonzero((seg < i1) | (seg > i2)))
-            dst.append((uid[a], uid[b], crossing))
-            if rev is not None:
-                out[rev].append((uid[b], uid[a], crossing))
+            bwd = list(zip(ub, ua, cl))
+            if rev == inter:
+                merged = [None] * (2 * n)
+                merged[0::2] = fwd
+                merged[1::2] = bwd
+                out[inter].extend(merged)
+            else:
+                out[inter].extend(fwd)
+                out[rev].extend(bwd)
+        else:
+            out[inter].extend(fwd)
     return out
+
+
+_group_names = {}
 
 
 def covalent_connections(ident, out, c2i):
     """annotate_covalent_connections, NA:1181-1210."""
     groups = defaultdict(list)
-    for k in range(len(ident.chain)):
-        groups[(str(ident.model[k]) + " " + str(ident.symmetry[k]) + " " + ident.chain[k], int(ident.index[k]))].append(k)
+    for k, (m, sy, ch, ix) in enumerate(zip(ident.model, ident.symmetry, ident.chain, ident.index.tolist())):
+        key = (m, sy, ch)
+        g = _group_names.get(key)
+        if g is None:
+            g = str(m) + " " + str(sy) + " " + ch
+            if len(_group_names) < 100000:
+                _group_names[key] = g
+        groups[(g, ix)].append(k)
     keys = sorted(groups.keys())
     uid = ident.unit_id
     for i in range(len(keys) - 1):
         k1, k2 = keys[i], keys[i + 1]
         if k1[0] == k2[0]:
             inter = "p_" + str(k2[1] - k1[1])
+            dst = out[inter]
             for a in groups[k1]:
                 for b in groups[k2]:
-                    out[inter].append((uid[a], uid[b], None))
-                    c2i["covalent"].add(inter)
+                    dst.append((uid[a], uid[b], None))
+            c2i["covalent"].add(inter)
+
+
+def _add_pairs(i2p, label, A, B):
+    ent = i2p.get(label)
+    if ent is None:
+        i2p[label] = (list(A), list(B))
+    else:
+        ent[0].extend(A)
+        ent[1].extend(B)
 
 
 def build_results(batch, s, hits, boxtable, box_atoms, categories):
     """hits: sorted hit records of structure s.  Returns (interaction_to_list_of_tuples,
-    category_to_interactions) exactly like annotate_nt_nt_interactions + covalent links."""
+    category_to_interactions) exactly like annotate_nt_nt_interactions + covalent links.
+    Non-basepair hits are grouped by (slot, code) with numpy (the order inside a label is the hit
+    order, as in the reference); basepair hits go through the order-dependent cleanup."""
     ident = StructureIdentity(batch, s)
     lo = ident.lo
-    i2p = defaultdict(list)
+    i2p = {}
     c2i = defaultdict(set)
+    slot = hits['slot']
+    code = hits['code']
+    A = (hits['i'] - lo)
+    B = (hits['j'] - lo)
+    if len(hits):
+        key = slot.astype(np.int32) * 256 + code
+        nonbp = slot != _lib.SLOT_BP
+        # labels appear in the dict in order of first occurrence, like the reference's defaultdict
+        uniq, first = np.unique(key[nonbp], return_index=True)
+        idx_nonbp = np.nonzero(nonbp)[0]
+        for kk in uniq[np.argsort(first)].tolist():
+            rows = idx_nonbp[key[nonbp] == kk]
+            sl, cd = kk >> 8, kk & 255
+            a, b = A[rows].tolist(), B[rows].tolist()
+            if sl == _lib.SLOT_SO12:
+                l, r = so_labels(cd)
+                _add_pairs(i2p, l, a, b); _add_pairs(i2p, r, b, a)
+                c2i['sO'].add(l); c2i['sO'].add(r)
+            elif sl == _lib.SLOT_SO21:
+                l, r = so_labels(cd)
+                _add_pairs(i2p, l, b, a); _add_pairs(i2p, r, a, b)
+                c2i['sO'].add(l); c2i['sO'].add(r)
+            elif sl == _lib.SLOT_STACK:
+                l, r = stack_labels(cd)
+                _add_pairs(i2p, l, a, b)
+                c2i['stacking'].add(l); c2i['stacking'].add(r)
+            elif sl == _lib.SLOT_SR12:
+                _add_pairs(i2p, _SR[cd], a, b); c2i['sugar_ribose'].add(_SR[cd])
+            elif sl == _lib.SLOT_SR21:
+                _add_pairs(i2p, _SR[cd], b, a); c2i['sugar_ribose'].add(_SR[cd])
+            elif sl == _lib.SLOT_BPH:
+                l = ("n" if cd & 16 else "") + str(cd & 15) + "BPh"
+                _add_pairs(i2p, l, a, b); c2i['backbone'].add(l)
+            elif sl == _lib.SLOT_BR:
+                l = ("n" if cd & 16 else "") + str(cd & 15) + "BR"
+                _add_pairs(i2p, l, a, b); c2i['backbone'].add(l)
+            elif sl == _lib.SLOT_CP:
+                _add_pairs(i2p, 'cp', a, b); c2i['coplanar'].add('cp')
+    # when two directions of sO (or SR) feed the same label, the reference interleaves them in pair
+    # order; restore that order for labels fed from more than one (slot, code) group
+    _restore_pair_order(i2p, hits, lo)
     u2bp = {}
     names = boxtable.box_name
-    for h in hits.tolist():
-        i, j, rank, slot, code, box, cd, gap = h
-        a, b = i - lo, j - lo
-        if slot == _lib.SLOT_SO12:
-            l, r = so_labels(code)
-            i2p[l].append((a, b)); i2p[r].append((b, a))
-            c2i['sO'].add(l); c2i['sO'].add(r)
-        elif slot == _lib.SLOT_SO21:
-            l, r = so_labels(code)
-            i2p[l].append((b, a)); i2p[r].append((a, b))
-            c2i['sO'].add(l); c2i['sO'].add(r)
-        elif slot == _lib.SLOT_STACK:
-            l, r = stack_labels(code)
-            i2p[l].append((a, b))
-            c2i['stacking'].add(l); c2i['stacking'].add(r)
-        elif slot == _lib.SLOT_SR12:
-            l = _SR[code]
-            i2p[l].append((a, b)); c2i['sugar_ribose'].add(l)
-        elif slot == _lib.SLOT_SR21:
-            l = _SR[code]
-            i2p[l].append((b, a)); c2i['sugar_ribose'].add(l)
-        elif slot == _lib.SLOT_BPH:
-            l = ("n" if code & 16 else "") + str(code & 15) + "BPh"
-            i2p[l].append((a, b)); c2i['backbone'].add(l)
-        elif slot == _lib.SLOT_BR:
-            l = ("n" if code & 16 else "") + str(code & 15) + "BR"
-            i2p[l].append((a, b)); c2i['backbone'].add(l)
-        elif slot == _lib.SLOT_CP:
-            i2p['cp'].append((a, b)); c2i['coplanar'].add('cp')
-        elif slot == _lib.SLOT_BP:
+    if len(hits):
+        for i, j, rank, sl, cd, box, cdist, gap in hits[slot == _lib.SLOT_BP].tolist():
+            a, b = i - lo, j - lo
             name = names[box]
-            lw = ("n" + name) if (code & 1) else name
-            u1, u2 = (b, a) if (code & 2) else (a, b)
+            lw = ("n" + name) if (cd & 1) else name
+            u1, u2 = (b, a) if (cd & 2) else (a, b)
             at1, at2 = box_atoms[box]
             if u1 not in u2bp:
                 u2bp[u1] = []
-            u2bp[u1].append([lw, (cd, gap, at1), u2])        # NA:1001-1003
+            u2bp[u1].append([lw, (cdist, gap, at1), u2])        # NA:1001-1003
             if u2 not in u2bp:
                 u2bp[u2] = []
-            u2bp[u2].append([reverse_edges(lw), (cd, gap, at2), u1])   # NA:1008-1013
+            u2bp[u2].append([reverse_edges(lw), (cdist, gap, at2), u1])   # NA:1008-1013
     remove_pairs, make_near = same_edge_cleanup(u2bp)
     saved = set()
     bp_seen = c2i['basepair']
@@ -241,7 +335,7 @@ def build_results(batch, s, hits, boxtable, box_atoms, categories):
             if (u, v) not in remove_pairs and (u, v) not in saved:
                 if (u, v) in make_near:
                     lw = "n" + lw
-                i2p[lw].append((u, v))
+                _add_pairs(i2p, lw, (u,), (v,))
                 saved.add((v, u)); saved.add((u, v))
                 if lw not in bp_seen:
                     r = reverse_edges(lw)
@@ -250,6 +344,38 @@ def build_results(batch, s, hits, boxtable, box_atoms, categories):
     out = crossing_numbers(ident, i2p)
     covalent_connections(ident, out, c2i)
     return out, c2i
+
+
+def _restore_pair_order(i2p, hits, lo):
+    """Labels that receive rows from several (slot, code) groups (sO both directions, SR both
+    directions) must list them in hit order.  Rebuild those labels from the hit stream."""
+    if not len(hits):
+        return
+    slot = hits['slot']
+    multi = (slot == _lib.SLOT_SO12) | (slot == _lib.SLOT_SO21) | (slot == _lib.SLOT_SR12) | (slot == _lib.SLOT_SR21)
+    if not multi.any():
+        return
+    rebuilt = {}
+    for i, j, rank, sl, cd, box, cdist, gap in hits[multi].tolist():
+        a, b = i - lo, j - lo
+        if sl == _lib.SLOT_SO12:
+            l, r = so_labels(cd)
+            rows = ((l, a, b), (r, b, a))
+        elif sl == _lib.SLOT_SO21:
+            l, r = so_labels(cd)
+            rows = ((l, b, a), (r, a, b))
+        elif sl == _lib.SLOT_SR12:
+            rows = ((_SR[cd], a, b),)
+        else:
+            rows = ((_SR[cd], b, a),)
+        for l, x, y in rows:
+            ent = rebuilt.get(l)
+            if ent is None:
+                rebuilt[l] = ([x], [y])
+            else:
+                ent[0].append(x); ent[1].append(y)
+    for l, ent in rebuilt.items():
+        i2p[l] = ent
 
 
 def box_atom_sets(boxtable, box_combo, hbonds):

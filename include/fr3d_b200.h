@@ -156,11 +156,13 @@ int fr3d_pair_search(const fr3d_nts_t *nts, double cell_size, void *workspace, s
  * check_sugar_ribose (NA:2262), check_base_backbone_interactions (NA:1867), check_coplanar
  * (NA:2051), check_basepair_cutoffs (NA:2364) and the 12-vs-21 arbitration (NA:935-957):
  * one warp per candidate pair, hits compacted with a warp ballot.
- * n_pairs is read from counters[0] on the device (clamped to pair_cap). */
+ * n_pairs is read from counters[0] on the device (clamped to pair_cap).  index_offset is added to the
+ * nt indices (and 16 x to the rank) written into the hit records, so that chunks of a larger batch
+ * produce globally indexed hits. */
 int fr3d_classify_pairs(const fr3d_nts_t *nts, const fr3d_box_t *boxes, const int32_t *box_index /*[25][2][2]*/,
                         const int32_t *pair_i, const int32_t *pair_j, const int32_t *pair_rank,
-                        int64_t pair_cap, uint32_t category_mask, fr3d_hit_t *hits, int64_t hit_cap,
-                        int64_t *counters, void *stream);
+                        int64_t pair_cap, uint32_t category_mask, int32_t index_offset, fr3d_hit_t *hits,
+                        int64_t hit_cap, int64_t *counters, void *stream);
 
 /* K5. Replaces besttransformation / besttransformation_weighted
  * (fr3d/geometry/superpositions.py:10-121) for n_prob independent problems.

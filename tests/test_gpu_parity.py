@@ -308,3 +308,22 @@ def postprocess_subset(batch, hits, bt, atoms, which):
     hits = postprocess.sort_hits(hits)
     sidx = np.searchsorted(batch.struct_off, hits['i'], side='right') - 1
     return [postprocess.build_results(batch, s, hits[sidx == s], bt, atoms, ALL9) for s in which]
+
+
+def test_pipelined_path_equals_single_pass():
+    """engine.Pipeline (chunked, multi-stream, what bench.py's e2e times) returns the same hit set."""
+    import torch
+    from fr3d_python_b200.engine import Pipeline, pin_batch
+    base = synthetic.pack_base()
+    batch = synthetic.make_structure_batch(base, 37, seed0=900)
+    eng = Engine.get()
+    bt, atoms = NA._box_table(NA._default_focused(ALL9['basepair']), NA.load_ideal_basepair_hydrogen_bonds())
+    mask = NA.category_mask(ALL9)
+    hits, n_pairs, _ = eng.annotate_batch(batch, bt, mask)
+    pinned = pin_batch(torch, batch)
+    for chunks in (1, 5, 37):
+        pipe = Pipeline(eng, batch, pinned, bt, mask, n_chunks=chunks, pair_cap=n_pairs, hit_cap=len(hits))
+        for _ in range(2):
+            h2, np2 = pipe.run()
+        key = lambda h: np.lexsort((h['slot'], h['j'], h['i'], h['rank']))
+        assert np2 == n_pairs and np.array_equal(hits[key(hits)], h2[key(h2)])

@@ -1,0 +1,9 @@
+#!/bin/bash
+# A/B of classify kernel variants on a GPU box: prints kernel_ms per variant / grid multiplier
+mkdir -p gpurun_out
+for lib in ab_mb3 ab_mb4 ab_mb5; do
+  for mult in 4 8 16 32; do
+    out=$(FR3D_B200_LIB=$PWD/fr3d_python_b200/lib/$lib.so FR3D_CLASSIFY_GRID_MULT=$mult timeout 200 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['kernel_ms']['classify_pairs'], d['value'], d['e2e']['value'])")
+    echo "$lib mult=$mult classify_ms,value,e2e: $out"
+  done
+done
