@@ -240,7 +240,7 @@ __device__ __noinline__ int backbone_select(const WarpScratch &S, int par1, uint
 }
 
 #ifndef FR3D_CLASSIFY_MIN_BLOCKS
-#define FR3D_CLASSIFY_MIN_BLOCKS 4
+#define FR3D_CLASSIFY_MIN_BLOCKS 5   // 5 CTAs x 4 warps per SM: best of the {3,4,5,6} sweep (profiles/README.md)
 #endif
 __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, FR3D_CLASSIFY_MIN_BLOCKS)
 classify_pairs_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, const int32_t *__restrict__ box_index,
