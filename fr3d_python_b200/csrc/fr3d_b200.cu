@@ -182,7 +182,8 @@ int fr3d_discrepancy_all_vs_all(const double *centers, const double *rots, const
     if (n < 2 || n > fr3d::DISC_MAXN) return fail(FR3D_E_ARG, "n must be in [2, 16]");
     if (row0 < 0 || row1 > N || row0 > row1) return fail(FR3D_E_ARG, "bad row range");
     if (row0 == row1 || N == 0) return FR3D_OK;
-    const size_t smem = (size_t)fr3d::DISC_TILE * (size_t)n * 12 * 2 * sizeof(double) + 2 * fr3d::DISC_TILE * fr3d::DISC_MAXN;
+    const size_t smem = (size_t)fr3d::DISC_TILE * (size_t)n * 12 * 2 * sizeof(double) + 2 * fr3d::DISC_TILE * fr3d::DISC_MAXN +
+                        (size_t)fr3d::DISC_TILE * (fr3d::DISC_TILE + 1) * sizeof(double);
     CUDA_TRY(cudaFuncSetAttribute(fr3d::discrepancy_all_vs_all_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)smem));
     dim3 block(32, 8);

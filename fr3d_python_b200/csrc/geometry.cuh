@@ -184,10 +184,15 @@ discrepancy_all_vs_all_kernel(const double *__restrict__ centers, const double *
     double *colr = colc + DISC_TILE * cs;
     uint8_t *rowh = reinterpret_cast<uint8_t *>(colr + DISC_TILE * rs);
     uint8_t *colh = rowh + DISC_TILE * DISC_MAXN;
+    double *tile = reinterpret_cast<double *>(colh + DISC_TILE * DISC_MAXN);     // [32][33] mirrored results
 
     const int tid = threadIdx.y * 32 + threadIdx.x;
     const int rbase = row0 + blockIdx.y * DISC_TILE;
     const int cbase = blockIdx.x * DISC_TILE;
+    // full-matrix launches compute only tiles on or above the diagonal and mirror them: the reference
+    // fills both triangles from one evaluation as well (FR3D.py:439-441)
+    const bool mirror = (row0 == 0 && row1 == N);
+    if (mirror && blockIdx.x < blockIdx.y) return;
 
     // stage: raw centres, rotations (coalesced: consecutive threads read consecutive doubles)
     for (int e = tid; e < DISC_TILE * cs; e += 256) {
@@ -238,6 +243,16 @@ discrepancy_all_vs_all_kernel(const double *__restrict__ centers, const double *
             else d = discrepancy_pair2(ca, ra, cb, rb, angle_weight);
         }
         out[(size_t)(r - row0) * N + c] = d;
+        if (mirror && blockIdx.x > blockIdx.y) tile[threadIdx.x * (DISC_TILE + 1) + rr] = d;
+    }
+    if (mirror && blockIdx.x > blockIdx.y) {
+        // transposed tile: rows c, columns r, written with consecutive threads along r (coalesced)
+        __syncthreads();
+#pragma unroll 1
+        for (int cc = threadIdx.y; cc < DISC_TILE; cc += 8) {
+            const int cg = cbase + cc, rg = rbase + threadIdx.x;
+            if (cg < N && rg < N) out[(size_t)cg * N + rg] = tile[cc * (DISC_TILE + 1) + threadIdx.x];
+        }
     }
 }
 
