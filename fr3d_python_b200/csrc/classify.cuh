@@ -98,10 +98,10 @@ __device__ __forceinline__ double dist3(const double *a, const double *b) {
 static constexpr int WARPS_PER_BLOCK = 4;
 
 // Per-warp staging area in shared memory: everything the rules read for one pair.
-struct WarpScratch {
+struct alignas(16) WarpScratch {
     double fr[24];        // c1[3] U1[9] c2[3] U2[9]
-    double atoms[32][3];  // 0-15: base atoms of nt2, 16-31: base atoms of nt1
-    double bb[20][3];     // 0-9: backbone atoms of nt2, 10-19: backbone atoms of nt1
+    double atoms[32][3];  // 0-15: base atoms of nt2, 16-31: base atoms of nt1   (offset 192, 16-byte aligned)
+    double bb[20][3];     // 0-9: backbone atoms of nt2, 10-19: backbone atoms of nt1   (offset 960)
     double ang[32];
     double dst[32];
 };

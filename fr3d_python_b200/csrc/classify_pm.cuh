@@ -10,6 +10,8 @@
 // arithmetic, same order of floating-point operations).
 #pragma once
 
+#include <cstddef>
+
 #include "classify.cuh"
 
 namespace fr3d {
@@ -20,7 +22,7 @@ static constexpr int PM_K = 4;
 #endif
 static constexpr int PM_UNROLL_N = PM_UNROLL;   // pairs of a phase loop interleaved by the compiler
 
-struct PairState {
+struct alignas(16) PairState {
     WarpScratch d;
     double cd[2][32];        // per lane: running cutoff_distance of "my" box, per orientation
     double gap12, gap21, mind;
@@ -37,6 +39,11 @@ struct PairState {
 __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem_src) : "memory");
+}
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src) : "memory");
 }
 
 __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src) {
@@ -67,6 +74,33 @@ classify_pairs_pm_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, c
     const int half = lane >> 4;      // 0: atoms of nt2 seen from frame 1, 1: atoms of nt1 seen from frame 2
     const int a = lane & 15;
 
+    // ---- per-lane copy plan (loop invariant).  A nt's base block is 384 contiguous bytes (24 x 16 B), its
+    // backbone block 240 bytes (15 x 16 B); both are 16-byte aligned.  Shared layout: atoms[0..15] = nt2,
+    // atoms[16..31] = nt1, bb[0..9] = nt2, bb[10..19] = nt1, fr[0..11] = nt1 frame, fr[12..23] = nt2 frame.
+    const char *base_b = reinterpret_cast<const char *>(nts.base_xyz);
+    const char *bb_b = reinterpret_cast<const char *>(nts.bb_xyz);
+    const int off_atoms = (int)offsetof(PairState, d) + (int)offsetof(WarpScratch, atoms);
+    const int off_bb = (int)offsetof(PairState, d) + (int)offsetof(WarpScratch, bb);
+    const int off_fr = (int)offsetof(PairState, d) + (int)offsetof(WarpScratch, fr);
+    // copy 1 (16 B): lanes 0-23 -> nt2 base chunks 0-23, lanes 24-31 -> nt1 base chunks 0-7
+    const bool c1_n1 = lane >= 24;
+    const char *c1_src = base_b + (lane < 24 ? lane : lane - 24) * 16;
+    const int c1_dst = off_atoms + (lane < 24 ? lane * 16 : 384 + (lane - 24) * 16);
+    // copy 2 (16 B): lanes 0-15 -> nt1 base chunks 8-23, lanes 16-30 -> nt2 backbone chunks 0-14
+    const bool c2_n1 = lane < 16;
+    const char *c2_src = lane < 16 ? base_b + (8 + lane) * 16 : bb_b + (lane - 16) * 16;
+    const size_t c2_stride = lane < 16 ? (size_t)FR3D_BASE_SLOTS * 24 : (size_t)FR3D_BB_SLOTS * 24;
+    const int c2_dst = lane < 16 ? off_atoms + 384 + (8 + lane) * 16 : off_bb + (lane - 16) * 16;
+    // copy 3 (16 B): lanes 0-14 -> nt1 backbone chunks
+    const char *c3_src = bb_b + lane * 16;
+    const int c3_dst = off_bb + 240 + lane * 16;
+    // copy 4 (8 B): lanes 0-11 -> nt1 centre (3) + rotation (9), lanes 12-23 -> nt2
+    const int fe = lane < 12 ? lane : lane - 12;
+    const char *c4_src = fe < 3 ? reinterpret_cast<const char *>(nts.center) + fe * 8
+                                : reinterpret_cast<const char *>(nts.rot) + (fe - 3) * 8;
+    const size_t c4_stride = fe < 3 ? 24 : 72;
+    const int c4_dst = off_fr + lane * 8;
+
 #pragma unroll 1
     for (long long p0 = warp0 * PM_K; p0 < n_pairs; p0 += nwarps * PM_K) {
         const int nk = (int)((n_pairs - p0) < PM_K ? (n_pairs - p0) : PM_K);
@@ -83,25 +117,13 @@ classify_pairs_pm_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, c
         for (int k = 0; k < nk; ++k) {
             PairState &P = W[k];
             const int n1 = P.n1, n2 = P.n2;
-            const double *qa = nts.base_xyz + ((size_t)(half ? n1 : n2) * FR3D_BASE_SLOTS + a) * 3;
-            cp_async8(&P.d.atoms[lane][0], qa);
-            cp_async8(&P.d.atoms[lane][1], qa + 1);
-            cp_async8(&P.d.atoms[lane][2], qa + 2);
-            if (lane < 24) {
-                const int n = lane < 12 ? n1 : n2;
-                const int e = lane < 12 ? lane : lane - 12;
-                cp_async8(&P.d.fr[lane], e < 3 ? nts.center + (size_t)n * 3 + e : nts.rot + (size_t)n * 9 + (e - 3));
-            }
-            if (lane < 20) {
-                const double *q = nts.bb_xyz + ((size_t)(lane < 10 ? n2 : n1) * FR3D_BB_SLOTS + (lane < 10 ? lane : lane - 10)) * 3;
-                cp_async8(&P.d.bb[lane][0], q);
-                cp_async8(&P.d.bb[lane][1], q + 1);
-                cp_async8(&P.d.bb[lane][2], q + 2);
-            }
-            if (lane < 4) {        // masks: bm1 bm2 bb1 bb2 are consecutive words of the state
-                const uint32_t *src = (lane < 2 ? nts.base_mask : nts.bb_mask) + ((lane & 1) ? n2 : n1);
-                cp_async4(&P.bm1 + lane, src);
-            }
+            // five copy instructions per pair; every lane's (array, nt, offset, destination) is loop invariant
+            char *sb = reinterpret_cast<char *>(&P);
+            cp_async16(sb + c1_dst, c1_src + (size_t)(c1_n1 ? n1 : n2) * (FR3D_BASE_SLOTS * 24));
+            if (lane < 31) cp_async16(sb + c2_dst, c2_src + (size_t)(c2_n1 ? n1 : n2) * c2_stride);
+            if (lane < 15) cp_async16(sb + c3_dst, c3_src + (size_t)n1 * (FR3D_BB_SLOTS * 24));
+            if (lane < 24) cp_async8(sb + c4_dst, c4_src + (size_t)(lane < 12 ? n1 : n2) * c4_stride);
+            if (lane < 4) cp_async4(&P.bm1 + lane, (lane < 2 ? nts.base_mask : nts.bb_mask) + ((lane & 1) ? n2 : n1));
             if (lane == 4) { P.hmask = 0; P.flags = 0; P.stack_code = -1; }
         }
         cp_async_wait_all();
