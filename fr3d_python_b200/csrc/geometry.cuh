@@ -81,6 +81,7 @@ __device__ __forceinline__ double discrepancy_pair(const double *ca, const doubl
                                                    double angle_weight, const double *cw, double cutoff2) {
     // A = dev2^T diag(w) dev1 with set1 = A's centres, set2 = B's; M = A^T
     double M[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    double ga = 0.0, gb = 0.0;
     for (int k = 0; k < n; ++k) {
         const double wk = cw ? cw[k] : 1.0;
         const double a0 = ca[k * 3 + 0], a1 = ca[k * 3 + 1], a2 = ca[k * 3 + 2];
@@ -88,9 +89,11 @@ __device__ __forceinline__ double discrepancy_pair(const double *ca, const doubl
         M[0][0] += a0 * b0; M[0][1] += a0 * b1; M[0][2] += a0 * b2;
         M[1][0] += a1 * b0; M[1][1] += a1 * b1; M[1][2] += a1 * b2;
         M[2][0] += a2 * b0; M[2][1] += a2 * b1; M[2][2] += a2 * b2;
+        ga += a0 * a0 + a1 * a1 + a2 * a2;
+        gb += b0 * b0 + b1 * b1 + b2 * b2;
     }
     double Q[3][3];
-    horn_rotation(M, Q);          // U = Q^T
+    horn_rotation_fast(M, 0.5 * (ga + gb), Q);          // U = Q^T
     double sse = 0.0;
     for (int k = 0; k < n; ++k) {
         const double a0 = ca[k * 3 + 0], a1 = ca[k * 3 + 1], a2 = ca[k * 3 + 2];
