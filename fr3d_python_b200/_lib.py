@@ -21,6 +21,7 @@ N_PARENTS = 5
 MASK_HAS_FRAME = 0x80000000
 FLAG_STD_RNA = 1
 FLAG_MODIFIED = 2
+FLAG_DUP = 4
 
 CAT_SO, CAT_STACKING, CAT_SUGAR_RIBOSE, CAT_BACKBONE, CAT_COPLANAR = 1, 2, 4, 8, 16
 SLOT_SO12, SLOT_SO21, SLOT_STACK, SLOT_SR12, SLOT_SR21, SLOT_BPH, SLOT_BR, SLOT_CP, SLOT_BP = range(9)

@@ -389,7 +389,16 @@ classify_pairs_pm_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, c
                 const int par1 = (int)((bm1 >> 16) & 15u) - 1, par2 = (int)((bm2 >> 16) & 15u) - 1;
                 const double nZ = PM_U1(2) * PM_U2(2) + PM_U1(5) * PM_U2(5) + PM_U1(8) * PM_U2(8);
                 const bool valid = ((half ? bm1 : bm2) >> a) & 1u;
-                if (bp_live || cp_frames) {            // calculate_basepair_gap, NA:2189-2259, both directions
+                // modified residues with ideal-position copies: both points of a twin slot count (rare path)
+                const bool twins = ((bm1 | bm2) >> 22) & 1u;
+                uint32_t tw1 = 0, tw2 = 0;
+                if (twins) {
+                    if ((bm1 >> 22) & 1u) tw1 = (uint32_t)nts.meta[(size_t)P.n1 * FR3D_META_INTS + 7] >> 16;
+                    if ((bm2 >> 22) & 1u) tw2 = (uint32_t)nts.meta[(size_t)P.n2 * FR3D_META_INTS + 7] >> 16;
+                }
+                if (twins && (bp_live || cp_frames)) {
+                    gaps_twins(S, bm1, bm2, tw1, tw2, par1, par2, lane, gap12, gap21);
+                } else if (bp_live || cp_frames) {            // calculate_basepair_gap, NA:2189-2259, both directions
                     const double *fo = half ? &S.fr[12] : &S.fr[0];
                     const double px = S.atoms[lane][0], py = S.atoms[lane][1], pz = S.atoms[lane][2];
                     const double w0 = px - fo[0], w1 = py - fo[1], w2 = pz - fo[2];
@@ -410,7 +419,9 @@ classify_pairs_pm_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, c
                     gap21 = __shfl_sync(FULL, g, 16);
                 }
                 const bool cp_gap = cp_frames && (((ori_ok & 1u) && gap12 < 1.5179) || ((ori_ok & 2u) && gap21 < 1.5179));
-                if (stack_code >= 0 || bp_live || cp_gap) {   // calculate_base_min_distances, NA:1799-1829
+                if (twins && (stack_code >= 0 || bp_live || cp_gap)) {
+                    mind = mind_twins(S, bm1, bm2, tw1, tw2, par1, par2, lane);
+                } else if (stack_code >= 0 || bp_live || cp_gap) {   // calculate_base_min_distances, NA:1799-1829
                     const bool v2 = (bm2 >> a) & 1u;
                     const double qx = S.atoms[a][0], qy = S.atoms[a][1], qz = S.atoms[a][2];
                     double best = 1e300;

@@ -139,26 +139,19 @@ int fr3d_classify_pairs(const fr3d_nts_t *nts, const fr3d_box_t *boxes, const in
     if (pair_cap <= 0) return FR3D_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // persistent warps: grid is a multiple of the SM count; n_pairs is read on the device
-    static int mult = -1, pm = -1;              // tuning knobs: blocks per SM, phase-major kernel on/off
+    static int mult = -1;                       // tuning knob: CTAs per SM of the persistent grid
     if (mult < 0) {
         const char *e = getenv("FR3D_CLASSIFY_GRID_MULT");
         mult = (e && atoi(e) > 0) ? atoi(e) : FR3D_CLASSIFY_MIN_BLOCKS;   // exactly the resident CTAs: one wave
-        const char *m = getenv("FR3D_CLASSIFY_PM");
-        pm = m ? atoi(m) : 1;
     }
-    const long long per_block = (long long)fr3d::WARPS_PER_BLOCK * (pm ? fr3d::PM_K : 1);
+    const long long per_block = (long long)fr3d::WARPS_PER_BLOCK * fr3d::PM_K;
     long long want = (pair_cap + per_block - 1) / per_block;
     long long maxgrid = (long long)g_sm_count * mult;
     int grid = (int)(want < maxgrid ? want : maxgrid);
     if (grid < 1) grid = 1;
-    if (pm)
-        fr3d::classify_pairs_pm_kernel<<<grid, fr3d::WARPS_PER_BLOCK * 32, 0, st>>>(
-            *nts, boxes, box_index, pair_i, pair_j, pair_rank, pair_cap, category_mask, index_offset, hits, hit_cap,
-            counters);
-    else
-        fr3d::classify_pairs_kernel<<<grid, fr3d::WARPS_PER_BLOCK * 32, 0, st>>>(
-            *nts, boxes, box_index, pair_i, pair_j, pair_rank, pair_cap, category_mask, index_offset, hits, hit_cap,
-            counters);
+    fr3d::classify_pairs_pm_kernel<<<grid, fr3d::WARPS_PER_BLOCK * 32, 0, st>>>(
+        *nts, boxes, box_index, pair_i, pair_j, pair_rank, pair_cap, category_mask, index_offset, hits, hit_cap,
+        counters);
     CUDA_TRY(cudaGetLastError());
     return FR3D_OK;
 }

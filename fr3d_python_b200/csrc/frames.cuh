@@ -19,7 +19,14 @@ __global__ void __launch_bounds__(128) frames_fit_kernel(fr3d_nts_t nts, int32_t
     if (n >= nts.n_nt) return;
     const int parent = nts.meta[n * FR3D_META_INTS + 0];
     const int flags = nts.meta[n * FR3D_META_INTS + 1];
-    uint32_t mask = nts.base_mask[n] & 0xFFFFu;
+    const uint32_t mask_in = nts.base_mask[n];
+    uint32_t mask = mask_in & 0xFFFFu;
+    // residues that already received their ideal-position copies hold averaged coordinates: fitting
+    // them again would not reproduce the frame, so a second pass leaves them alone
+    if ((flags & FR3D_FLAG_DUP) && (mask_in & FR3D_MASK_HAS_FRAME)) {
+        if (status) status[n] = 0;
+        return;
+    }
     // bits 16-19: parent + 1, bits 20-23: flags (read by the classify kernel instead of meta)
     const uint32_t tag = ((uint32_t)(parent + 1) & 15u) << 16 | ((uint32_t)flags & 15u) << 20;
     if (parent < 0 || parent >= FR3D_N_PARENTS) {
@@ -88,7 +95,32 @@ __global__ void __launch_bounds__(128) frames_fit_kernel(fr3d_nts_t nts, int32_t
 #pragma unroll
         for (int c = 0; c < 3; ++c) ro[r * 3 + c] = U[r][c];
 
-    if (place_h) {   // components.py:452-462: centre + U . h_std for every missing base hydrogen
+    if (flags & FR3D_FLAG_DUP) {
+        // components.py:505-513: an ideal-position copy of every mapped base atom (heavy atoms included) is
+        // appended; AtomProxy then returns the mean of the observed atom and its copy (base.py:150-166)
+        const uint32_t dup = (uint32_t)nts.meta[n * FR3D_META_INTS + 7] & 0xFFFFu;
+        uint32_t twin = 0;
+        for (int k = 0; k < ns; ++k) {
+            if (dup >> k & 1u) {
+                const double h0 = c_tab.std_xyz[parent][k][0], h1 = c_tab.std_xyz[parent][k][1],
+                             h2 = c_tab.std_xyz[parent][k][2];
+                const double i0 = ctr[0] + (U[0][0] * h0 + U[0][1] * h1 + U[0][2] * h2);
+                const double i1 = ctr[1] + (U[1][0] * h0 + U[1][1] * h1 + U[1][2] * h2);
+                const double i2 = ctr[2] + (U[2][0] * h0 + U[2][1] * h1 + U[2][2] * h2);
+                if (mask >> k & 1u) {
+                    xyz[k * 3 + 0] = (xyz[k * 3 + 0] + i0) / 2.0;
+                    xyz[k * 3 + 1] = (xyz[k * 3 + 1] + i1) / 2.0;
+                    xyz[k * 3 + 2] = (xyz[k * 3 + 2] + i2) / 2.0;
+                    twin |= 1u << k;
+                } else {
+                    xyz[k * 3 + 0] = i0; xyz[k * 3 + 1] = i1; xyz[k * 3 + 2] = i2;
+                    mask |= 1u << k;
+                }
+            }
+        }
+        nts.meta[n * FR3D_META_INTS + 7] = (int32_t)(dup | (twin << 16));
+    } else if (place_h && !(flags & FR3D_FLAG_MODIFIED)) {
+        // components.py:452-462: centre + U . h_std for every missing base hydrogen of a standard residue
         for (int k = nh; k < ns; ++k) {
             if (!(mask >> k & 1u)) {
                 const double h0 = c_tab.std_xyz[parent][k][0], h1 = c_tab.std_xyz[parent][k][1],

@@ -145,7 +145,19 @@ class Component(object):
     def infer_NA_hydrogens(self):
         """components.py:359-462 for standard residues: fix amino-hydrogen labels, then add every
         missing base hydrogen at centre + U . h_std."""
-        if self.sequence not in defs.NAbasehydrogens or self.rotation_matrix is None:
+        if self.rotation_matrix is None:
+            return
+        if self.sequence not in defs.NAbasehydrogens:
+            mod = defs.modified_table().get(self.sequence)
+            if mod is None or any('H' in a.name for a in self._atoms):
+                return
+            # components.py:505-513: no hydrogen observed -> an ideal-position copy of EVERY mapped base
+            # atom (heavy atoms included, mapping.py:76-79) is appended under the modified residue's names
+            std = defs.NAbasecoordinates[mod["parent"]]
+            U = np.asarray(self.rotation_matrix)
+            for name in mod["base_atoms"]:
+                new = self.base_center + U.dot(np.array(std[mod["modified_atom_to_parent"][name]]))
+                self._atoms.append(Atom(name=name, x=float(new[0]), y=float(new[1]), z=float(new[2])))
             return
         parent = defs.SEQ_TO_PARENT[self.sequence]
         already = set(a.name for a in self._atoms)

@@ -108,7 +108,9 @@ _slot_cache = {}
 
 
 def _slot_maps(sequence):
-    """(parent_code, flags, base name->slot, backbone name->slot) for a residue name, or None."""
+    """(parent_code, flags, base name->slot, backbone name->slot, dup_mask) for a residue name, or None.
+    dup_mask: slots of a modified residue whose atom is in the reference's mapping, i.e. the slots that
+    receive an ideal-position copy when no hydrogen is observed (components.py:505-513)."""
     if sequence in _slot_cache:
         return _slot_cache[sequence]
     parent = defs.get_parent(sequence)
@@ -116,23 +118,30 @@ def _slot_maps(sequence):
         res = None
     elif sequence in defs.SEQ_TO_PARENT:
         flags = _lib.FLAG_STD_RNA if sequence in ('A', 'C', 'G', 'U') else 0
-        res = (defs.PARENT_CODE[parent], flags, defs.SLOT_OF[parent], defs.BB_SLOT_OF)
+        res = (defs.PARENT_CODE[parent], flags, defs.SLOT_OF[parent], defs.BB_SLOT_OF, 0)
     else:
         # modified residue: parent atom X is read through parent_atom_to_modified (NA:324-371)
         p2m = defs.modified_table()[sequence]["parent_atom_to_modified"]
         base = {p2m.get(x, x): k for x, k in defs.SLOT_OF[parent].items()}
         bb = {p2m.get(x, x): k for x, k in defs.BB_SLOT_OF.items()}
-        res = (defs.PARENT_CODE[parent], _lib.FLAG_MODIFIED, base, bb)
+        dup = 0
+        for x, k in defs.SLOT_OF[parent].items():
+            if x in p2m:
+                dup |= 1 << k
+        res = (defs.PARENT_CODE[parent], _lib.FLAG_MODIFIED, base, bb, dup)
     _slot_cache[sequence] = res
     return res
 
 
-def _fill_atoms(batch, k, maps, atoms):
+def _fill_atoms(batch, k, maps, atoms, frames_given=False):
     """atoms: iterable of (name, x, y, z).  Duplicate names are averaged like AtomProxy
-    (fr3d/data/base.py:150-166)."""
-    pcode, flags, bslot, bbslot = maps
+    (fr3d/data/base.py:150-166).  Modified residues: see FR3D_FLAG_DUP in include/fr3d_b200.h."""
+    pcode, flags, bslot, bbslot, dupmask = maps
     bcount = {}
+    saw_h = False
     for name, x, y, z in atoms:
+        if 'H' in name:
+            saw_h = True
         s = bslot.get(name)
         if s is not None:
             if batch.base_mask[k] >> s & 1:
@@ -152,6 +161,19 @@ def _fill_atoms(batch, k, maps, atoms):
             else:
                 batch.bb_xyz[k, s] = (x, y, z)
                 batch.bb_mask[k] |= np.uint32(1 << s)
+    if flags & _lib.FLAG_MODIFIED:
+        if frames_given:
+            # Component objects of the reference already hold the ideal copies: twin slots are those seen twice
+            twin = 0
+            for s_, c in bcount.items():
+                if s_ < 100 and c == 2:
+                    twin |= 1 << s_
+            if twin:
+                flags |= _lib.FLAG_DUP
+                batch.meta[k, 7] = twin << 16
+        elif not saw_h:
+            flags |= _lib.FLAG_DUP
+            batch.meta[k, 7] = dupmask
     batch.meta[k, 0] = pcode
     batch.meta[k, 1] = flags
     batch.base_mask[k] |= np.uint32(((pcode + 1) & 15) << 16 | (flags & 15) << 20)   # read by the classify kernel
@@ -236,7 +258,8 @@ def pack_specs(specs):
                 b.meta[k, 0] = -1
             else:
                 _fill_atoms(b, k, maps, nt["atoms"])
-                _fix_amino_hydrogens(b, k, defs.PARENTS[maps[0]])
+                if not (maps[1] & _lib.FLAG_MODIFIED):
+                    _fix_amino_hydrogens(b, k, defs.PARENTS[maps[0]])
             k += 1
         off.append(k)
     b.struct_off = np.array(off, dtype=np.int64)
@@ -275,7 +298,7 @@ def pack_structures(structures, chains=None):
             if maps is None:
                 b.meta[k, 0] = -1
             else:
-                _fill_atoms(b, k, maps, ((a.name, a.x, a.y, a.z) for a in c.atoms()))
+                _fill_atoms(b, k, maps, ((a.name, a.x, a.y, a.z) for a in c.atoms()), frames_given=True)
                 R = c.rotation_matrix
                 ctr = c.centers["base"]
                 if R is not None and len(ctr) == 3:

@@ -39,7 +39,7 @@ extern "C" {
 /* ---- layout constants ---------------------------------------------------- */
 #define FR3D_BASE_SLOTS 16 /* base atoms per nt: heavy atoms then hydrogens of the parent base */
 #define FR3D_BB_SLOTS 10   /* P OP1 OP2 O5' O4' O3' O2' C1' C2' prevO3' */
-#define FR3D_META_INTS 8   /* parent, flags, group, chain_rank, index, resid_key, alt_rank, reserved */
+#define FR3D_META_INTS 8   /* parent, flags, group, chain_rank, index, resid_key, alt_rank, dup/twin masks */
 #define FR3D_N_PARENTS 5   /* A C G U DT */
 
 #define FR3D_MASK_HAS_FRAME 0x80000000u /* bit 31 of base_mask: centre + rotation valid */
@@ -47,6 +47,12 @@ extern "C" {
 /* meta[1] flags */
 #define FR3D_FLAG_STD_RNA 1  /* sequence is one of A C G U   (check_coplanar, NA:2095) */
 #define FR3D_FLAG_MODIFIED 2 /* modified residue: centre = meanR - U.meanS (components.py:348) */
+#define FR3D_FLAG_DUP 4      /* modified residue without observed hydrogens: the reference appends an ideal-position
+                                copy of every mapped base atom (components.py:505-513, mapping.py:76-79).
+                                meta[7] bits 0-15: slots that receive an ideal copy (input of fr3d_frames_fit);
+                                bits 16-31: "twin" slots holding BOTH an observed atom and its ideal copy, stored
+                                as their mean (= what AtomProxy returns); rules that loop over atoms() instead of
+                                centers[] (gap, minimum distance) recover both points on the device */
 
 /* category bits for fr3d_classify_pairs (keys of the reference's `categories` dict) */
 #define FR3D_CAT_SO 1

@@ -51,6 +51,7 @@ NAbasehydrogens = DEFS["NAbasehydrogens"]
 NAbasecoordinates = DEFS["NAbasecoordinates"]
 NAbaseMassiveAndHydrogens = DEFS["NAbaseMassiveAndHydrogens"]
 NAbaseatoms = {s: set(NAbaseheavyatoms[s] + NAbasehydrogens[s]) for s in NAbaseheavyatoms}
+MODIFIED = _load("modified.json.gz")     # fr3d/data/mapping.py:26-83 applied to atom_mappings.txt
 
 
 def nt_nt_cutoffs():
@@ -268,42 +269,87 @@ class Nt(object):
             return coords[0]
         return np.average(coords, axis=0)
 
+    def mapped(self, name):
+        """get_one_atom_coordinates / get_atom_coordinates (NA:324-371): parent atom name -> the name
+        this (possibly modified) residue uses."""
+        m = MODIFIED.get(self.sequence)
+        if m is not None:
+            return m["parent_atom_to_modified"].get(name, name)
+        return name
+
+    def base_atom_names(self):
+        """get_base_atom_names, NA:1574-1599."""
+        if self.sequence in NAbaseheavyatoms:
+            return NAbaseatoms[self.sequence]
+        m = MODIFIED.get(self.sequence)
+        if m is not None:
+            p2m = m["parent_atom_to_modified"]
+            return set(p2m[a] for a in NAbaseatoms[m["parent"]] if a in p2m)
+        return set()
+
     def _fit_frame(self):
-        """Component.calculate_rotation_matrix, components.py:273-349 (standard residues)."""
-        if self.sequence not in NAbaseheavyatoms:
-            return
-        heavy = NAbaseheavyatoms[self.sequence]
-        std = NAbasecoordinates[self.sequence]
+        """Component.calculate_rotation_matrix, components.py:273-349."""
         R = []
         S = []
-        for n, x in zip(self.atom_names, self.atom_xyz):
-            if n in heavy:
-                R.append(x)
-                S.append(std[n])
+        if self.sequence in NAbaseheavyatoms:
+            heavy = NAbaseheavyatoms[self.sequence]
+            std = NAbasecoordinates[self.sequence]
+            for n, x in zip(self.atom_names, self.atom_xyz):
+                if n in heavy:
+                    R.append(x)
+                    S.append(std[n])
+        elif self.sequence in MODIFIED:
+            m = MODIFIED[self.sequence]
+            heavy = NAbaseheavyatoms[m["parent"]]
+            std = NAbasecoordinates[m["parent"]]
+            listed = set(m["base_atoms"])
+            for n, x in zip(self.atom_names, self.atom_xyz):
+                if n in listed:
+                    pa = m["modified_atom_to_parent"][n]
+                    if pa in heavy:
+                        R.append(x)
+                        S.append(std[pa])
+        else:
+            return
         if len(R) == 0:
             return
         U, fitted, meanR, rmsd, sse, meanS = besttransformation(np.array(R), np.array(S))
         self.rotation = U
-        self.base_center = meanR
         self.fitted = fitted
+        if self.sequence in NAbaseheavyatoms:
+            self.base_center = meanR                               # components.py:342-344
+        else:
+            self.base_center = np.subtract(meanR, np.dot(U, meanS))   # components.py:348-349
 
     def _infer_hydrogens(self):
-        """Component.infer_NA_hydrogens, components.py:405-462 (missing base hydrogens of
-        standard residues placed at centre + U . h_std)."""
-        if self.sequence not in NAbasehydrogens or self.rotation is None:
+        """Component.infer_NA_hydrogens, components.py:359-516.  Standard residues: every missing base
+        hydrogen at centre + U . h_std.  Modified residues: if NO atom of the residue has an 'H' in its
+        name, an ideal-position copy of EVERY mapped base atom (heavy atoms included,
+        mapping.py:76-79) is appended (:505-513); otherwise nothing is added."""
+        if self.rotation is None:
             return
-        already = set(self.atom_names)
-        coords = NAbasecoordinates[self.sequence]
-        for h in NAbasehydrogens[self.sequence]:
-            if h not in already:
-                new = self.base_center + np.dot(self.rotation, np.array(coords[h]))
-                self.atom_names.append(h)
+        if self.sequence in NAbasehydrogens:
+            already = set(self.atom_names)
+            coords = NAbasecoordinates[self.sequence]
+            for h in NAbasehydrogens[self.sequence]:
+                if h not in already:
+                    new = self.base_center + np.dot(self.rotation, np.array(coords[h]))
+                    self.atom_names.append(h)
+                    self.atom_xyz.append(np.array(new, dtype=float))
+        elif self.sequence in MODIFIED:
+            if any('H' in n for n in self.atom_names):
+                return
+            m = MODIFIED[self.sequence]
+            std = NAbasecoordinates[m["parent"]]
+            for name in m["base_atoms"]:
+                new = self.base_center + np.dot(self.rotation, np.array(std[m["modified_atom_to_parent"][name]]))
+                self.atom_names.append(name)
                 self.atom_xyz.append(np.array(new, dtype=float))
 
     def base_points(self):
         """Coordinates of atoms whose name is a base atom, in atom order
         (NA:1811-1817, 2211-2220)."""
-        names = NAbaseatoms[self.sequence]
+        names = self.base_atom_names()
         return [x for n, x in zip(self.atom_names, self.atom_xyz) if n in names]
 
 
@@ -319,6 +365,8 @@ def get_parent(sequence):
         return sequence[1]
     if sequence == 'DT':
         return sequence
+    if sequence in MODIFIED:
+        return MODIFIED[sequence]["parent"]
     return None
 
 
@@ -328,6 +376,9 @@ def glycosidic(nt):
         return nt.center("N9")
     if nt.sequence in ['C', 'U', 'DC', 'DT']:
         return nt.center("N1")
+    if nt.sequence in MODIFIED:
+        parent = MODIFIED[nt.sequence]["parent"]
+        return nt.center(nt.mapped("N9" if parent in ['A', 'G', 'DA', 'DG'] else "N1"))
     return np.array([])
 
 
@@ -564,8 +615,10 @@ def check_base_base_stacking(nt1, nt2, parent1, parent2):
     reverse = False
     # atom order: the reference iterates a set; any order gives the same result except
     # for exact |z| ties (measure zero).  Sorted for determinism.
-    a1 = sorted(NAbaseatoms[nt1.sequence])
-    a2 = sorted(NAbaseatoms[nt2.sequence])
+    a1 = sorted(nt1.base_atom_names())
+    a2 = sorted(nt2.base_atom_names())
+    if len(a1) == 0 or len(a2) == 0:
+        return "", ""
     nt2on1, coords = return_overlap(a2, nt1, nt2, parent1)
     nt1on2, coords2 = return_overlap(a1, nt2, nt1, parent2)
     if nt2on1 or nt1on2:
@@ -616,18 +669,18 @@ def torsion_angle(p0, p1, p2, p3):
 
 def check_sugar_ribose(nt1, nt2, parent1):
     """NA:2262-2342."""
-    o1 = nt1.center("O2'")
+    o1 = nt1.center(nt1.mapped("O2'"))
     if not len(o1) == 3:
         return ""
-    o2 = nt2.center("O2'")
+    o2 = nt2.center(nt2.mapped("O2'"))
     if not len(o2) == 3:
         return ""
     if np.linalg.norm(np.subtract(o1, o2)) > 3.8:
         return ""
     if parent1 in ['A', 'G']:
-        base_point = nt1.center('N3')
+        base_point = nt1.center(nt1.mapped('N3'))
     elif parent1 in ['C', 'U']:
-        base_point = nt1.center('O2')
+        base_point = nt1.center(nt1.mapped('O2'))
     else:
         return ""
     if not len(base_point) == 3:
@@ -638,8 +691,8 @@ def check_sugar_ribose(nt1, nt2, parent1):
     z = abs(float(np.dot(displ, nt1.rotation[:, 2])))
     if z > 2.0:
         return ""
-    p0, p1 = nt1.center("C1'"), nt1.center("C2'")
-    p2, p3 = nt2.center("C2'"), nt2.center("C1'")
+    p0, p1 = nt1.center(nt1.mapped("C1'")), nt1.center(nt1.mapped("C2'"))
+    p2, p3 = nt2.center(nt2.mapped("C2'")), nt2.center(nt2.mapped("C1'"))
     if len(p0) == 3 and len(p1) == 3 and len(p2) == 3 and len(p3) == 3:
         angle = torsion_angle(p0, p1, p2, p3)
         return 'cSR' if abs(angle) > 90 else 'tSR'
@@ -665,7 +718,7 @@ def previous_O3_map(nts):
         nt = nts[k]
         if prev is not None and nt.model == prev.model and nt.symmetry == prev.symmetry \
                 and nt.chain == prev.chain and nt.index == prev.index + 1:
-            out[k] = prev.center("O3'")
+            out[k] = prev.center(prev.mapped("O3'"))
         else:
             out[k] = None
         prev = nt
@@ -684,18 +737,18 @@ def check_base_backbone_interactions(nt1, nt2, previousO3, parent1):
     carbonCutoff, nCarbonCutoff = 4.0, 4.5
     nitrogenCutoff, nNitrogenCutoff = 3.5, 4.0
     angleLimit, nAngleLimit = 130, 110
-    ph_ox = [nt2.center(n) for n in ["O5'", 'OP1', 'OP2']]
-    r_ox = [nt2.center(n) for n in ["O2'", "O4'"]]
+    ph_ox = [nt2.center(nt2.mapped(n)) for n in ["O5'", 'OP1', 'OP2']]
+    r_ox = [nt2.center(nt2.mapped(n)) for n in ["O2'", "O4'"]]
     if previousO3 is not None and len(previousO3) == 3 and previousO3.any():
         ph_ox.append(previousO3)
-    P = nt2.center("P")
+    P = nt2.center(nt2.mapped("P"))
     if P.any():
         if abs(translate_rotate_point(nt1, P)[2]) > 4.5:
             ph_ox = []
     cutoff = nCutoff = None
     for site in NAbaseMassiveAndHydrogens[parent1]:
-        H = nt1.center(site[0])
-        M = nt1.center(site[1])
+        H = nt1.center(nt1.mapped(site[0]))
+        M = nt1.center(nt1.mapped(site[1]))
         if "C" in site[1]:
             cutoff, nCutoff = carbonCutoff, nCarbonCutoff
         elif "N" in site[1]:

@@ -327,3 +327,39 @@ def test_pipelined_path_equals_single_pass():
             h2, np2 = pipe.run()
         key = lambda h: np.lexsort((h['slot'], h['j'], h['i'], h['rank']))
         assert np2 == n_pairs and np.array_equal(hits[key(hits)], h2[key(h2)])
+
+
+def test_modified_residues_identical_to_reference(golden):
+    """90 modified nucleotides (PSU 5MC OMG 2MG 1MA MA6 H2U) in 1GID-full: frames, the averaged
+    observed/ideal coordinates and the final annotation against the unmodified reference."""
+    spec = golden("spec_1gid_modified.json.gz")
+    frames = golden("frames_1gid_modified.json.gz")
+    g = golden("annot_1gid_modified_all9.json.gz")
+    b = packing.pack_specs(spec)
+    status = gframes.fit_batch_frames(b)
+    assert np.all(status == 0)
+    n_dup = 0
+    for k, f in enumerate(frames):
+        assert np.abs(b.center[k] - np.array(f["center"])).max() < TOL
+        assert np.abs(b.rot[k].reshape(3, 3) - np.array(f["rotation"])).max() < TOL
+        if f["sequence"] in defs.modified_table():
+            parent = defs.get_parent(f["sequence"])
+            m2p = defs.modified_table()[f["sequence"]]["modified_atom_to_parent"]
+            for name, xyz in f["centers"].items():
+                slot = defs.SLOT_OF[parent][m2p[name]]
+                assert b.base_mask[k] >> slot & 1
+                assert np.abs(b.base_xyz[k, slot] - np.array(xyz)).max() < TOL
+            assert bin(int(b.base_mask[k]) & 0xFFFF).count("1") == len(f["centers"])
+            n_dup += bool(b.meta[k, 1] & _lib.FLAG_DUP)
+    assert n_dup > 50
+    uid = g["unit_ids"]
+    want = {k: [(uid[a], uid[c], x) for a, c, x in v] for k, v in g["interaction_to_list_of_tuples"].items()}
+    wantc = {k: set(v) for k, v in g["category_to_interactions"].items()}
+    assert as_plain(NA.annotate_batch(spec, g["categories"])[0]) == (want, wantc)
+    # through Component objects (ideal copies live in the atom lists, like in the reference)
+    st = Structure.from_spec(spec)
+    assert as_plain(NA.annotate_nt_nt_in_structure(st, g["categories"])) == (want, wantc)
+    # a second K1 pass leaves residues holding averaged coordinates alone
+    again = gframes.fit_batch_frames(b)
+    assert np.all(again == 0)
+    assert np.abs(b.center[0] - np.array(frames[0]["center"])).max() < TOL

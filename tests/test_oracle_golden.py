@@ -137,3 +137,31 @@ def test_all_vs_all_block(golden):
     has[:, 0] = False
     Dn = O.all_vs_all_discrepancy(C[:sub], R[:sub], has)
     assert np.abs(Dn - np.array(av["D_norot0"])[:sub, :sub]).max() < 1e-13
+
+
+def test_modified_residues_match_reference(golden):
+    """Modified nucleotides (PSU, 5MC, OMG, 2MG, 1MA, MA6, H2U): parent-atom mapping, centre =
+    meanR - U.meanS, and the reference's insertion of ideal-position copies of every mapped base atom when
+    no hydrogen is observed (components.py:505-513)."""
+    spec = golden("spec_1gid_modified.json.gz")
+    frames = golden("frames_1gid_modified.json.gz")
+    g = golden("annot_1gid_modified_all9.json.gz")
+    nts = O.build_nts(spec)
+    assert sum(1 for nt in nts if nt.sequence in O.MODIFIED) == 90
+    for nt, f in zip(nts, frames):
+        assert nt.unit_id() == f["unit_id"]
+        assert np.abs(nt.base_center - np.array(f["center"])).max() == 0.0
+        assert np.abs(nt.rotation - np.array(f["rotation"])).max() == 0.0
+        for n, x in f["centers"].items():                       # AtomProxy means of observed + ideal
+            assert np.abs(nt.center(n) - np.array(x)).max() == 0.0
+        mine = sorted((n, tuple(x)) for n, x in zip(nt.atom_names, nt.atom_xyz) if n in nt.base_atom_names())
+        ref = sorted((b[0], tuple(b[1:])) for b in f["base_points"])
+        assert [m[0] for m in mine] == [r[0] for r in ref]
+        assert np.abs(np.array([m[1] for m in mine]) - np.array([r[1] for r in ref])).max() == 0.0
+    out, c2i, tr = O.annotate(spec, g["categories"], nts)
+    assert tr["candidates"] == g["traces"]["candidates"]
+    for key in ("sO", "stacking", "sugar_ribose", "backbone"):
+        assert tr[key] == g["traces"][key], key
+    _close_rows(tr["coplanar"], g["traces"]["coplanar"])
+    _close_rows(tr["basepair"], g["traces"]["basepair"])
+    assert {k: [list(t) for t in v] for k, v in out.items()} == g["interaction_to_list_of_tuples"]

@@ -76,3 +76,26 @@ def test_box_tables_equal_the_reference_focus():
         assert NA.reverse_edges(inter) == RNA.reverse_edges(inter)
     for seq in ["A", "DG", "DT", "PSU", "5MC", "OMG", "1MA", "XYZ"]:
         assert NA.get_parent(seq) == RNA.get_parent(seq)
+
+
+def test_reference_modified_components_pack_with_twin_masks(golden):
+    """The reference's Components of modified residues hold ideal-position duplicates of their base atoms;
+    pack_structures must flag exactly the slots that are both observed and copied."""
+    from fr3d_python_b200 import _lib, packing
+    spec = golden("spec_1gid_modified.json.gz")
+    sub = {"pdb": spec["pdb"], "nts": spec["nts"][:60]}
+    st = _ref_structure(sub)
+    b = packing.pack_structures(st)
+    raw = packing.pack_specs(sub)
+    n_mod = 0
+    for k in range(b.n):
+        if raw.meta[k, 1] & _lib.FLAG_MODIFIED:
+            n_mod += 1
+            dup = int(raw.meta[k, 7]) & 0xFFFF if raw.meta[k, 1] & _lib.FLAG_DUP else 0
+            observed = int(raw.base_mask[k]) & 0xFFFF
+            assert (int(b.meta[k, 7]) >> 16) & 0xFFFF == dup & observed
+            assert int(b.base_mask[k]) & 0xFFFF == observed | dup
+            assert bool(b.meta[k, 1] & _lib.FLAG_DUP) == bool(dup & observed)
+        else:
+            assert b.meta[k, 7] == 0
+    assert n_mod >= 10

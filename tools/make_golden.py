@@ -76,6 +76,77 @@ def make_spec_1gid_full(base_spec, strand_spec):
     return {"pdb": "1GID", "nts": nts}
 
 
+def make_spec_modified(full_spec):
+    """1GID-full with a deterministic subset of residues turned into modified nucleotides of the
+    reference's atom_mappings.txt (PSU, 5MC, OMG, 2MG, 1MA, MA6, H2U ...): atom names are renamed
+    through parent_atom_to_modified, extra methyl carbons are added at idealised positions, and a few
+    residues carry an observed hydrogen (which switches off the reference's ideal-atom insertion,
+    components.py:465-513)."""
+    from fr3d.data import mapping as mp
+    from fr3d import definitions as defs
+    comps = residues(rf.ref_structure_from_spec(full_spec))
+    nts = []
+
+    def unit(v):
+        return v / np.linalg.norm(v)
+
+    for k, (nt, comp) in enumerate(zip(full_spec["nts"], comps)):
+        seq = nt["sequence"]
+        U = np.asarray(comp.rotation_matrix)
+        c = np.asarray(comp.centers["base"])
+        std = {n: np.array(v) for n, v in defs.NAbasecoordinates[seq].items()}
+        place = lambda x: [float(v) for v in (c + U @ x)]     # noqa: E731
+        new_seq, extra = None, []
+        if seq == 'U' and k % 5 == 0:
+            new_seq = 'PSU'
+        elif seq == 'U' and k % 11 == 7:
+            new_seq = 'H2U'
+            extra = [['HN3'] + place(std['H3'] + np.array([0.03, -0.02, 0.01]))]       # observed hydrogen
+        elif seq == 'C' and k % 4 == 1:
+            new_seq = '5MC'
+            extra = [['CM5'] + place(std['C5'] + 1.5 * unit(std['H5'] - std['C5']))]
+            if k % 8 == 5:
+                extra.append(['H6'] + place(std['H6'] + np.array([0.02, 0.02, 0.0])))   # observed hydrogen
+        elif seq == 'G' and k % 6 == 2:
+            new_seq = 'OMG'
+            o2 = [a for a in nt["atoms"] if a[0] == "O2'"][0]
+            extra = [['CM2', o2[1] + 0.9, o2[2] + 0.7, o2[3] + 0.6]]
+        elif seq == 'G' and k % 6 == 4:
+            new_seq = '2MG'
+            extra = [['CM2'] + place(std['N2'] + 1.45 * unit(std['H21'] - std['N2']))]
+        elif seq == 'A' and k % 5 == 3:
+            new_seq = '1MA'
+            extra = [['CM1'] + place(std['N1'] + 1.47 * unit(std['N1'] - std['C5']))]
+        elif seq == 'A' and k % 7 == 5:
+            new_seq = 'MA6'
+            extra = [['C9'] + place(std['N6'] + 1.45 * unit(std['H61'] - std['N6'])),
+                     ['C10'] + place(std['N6'] + 1.45 * unit(std['H62'] - std['N6']))]
+        new = dict(nt)
+        if new_seq is not None:
+            p2m = mp.parent_atom_to_modified[new_seq]
+            new["sequence"] = new_seq
+            new["atoms"] = [[p2m.get(a[0], a[0])] + a[1:] for a in nt["atoms"]] + extra
+        nts.append(new)
+    return {"pdb": "1GID", "nts": nts}
+
+
+def frames_golden_modified(spec):
+    """Like frames_golden plus, per residue, centers[name] of every base atom name the annotator looks
+    up (get_base_atom_names, NA:1574-1599) and the base points its atoms() loops see (NA:2211-2220)."""
+    from fr3d.classifiers import NA_pairwise_interactions as NA
+    comps = residues(rf.ref_structure_from_spec(spec))
+    out = []
+    for comp in comps:
+        names = sorted(NA.get_base_atom_names(comp.sequence))
+        centers = {n: [float(v) for v in comp.centers[n]] for n in names if len(comp.centers[n]) == 3}
+        points = [[a.name, float(a.x), float(a.y), float(a.z)] for a in comp.atoms() if a.name in set(names)]
+        out.append({"unit_id": comp.unit_id(), "sequence": comp.sequence,
+                    "center": [float(v) for v in comp.centers["base"]],
+                    "rotation": np.asarray(comp.rotation_matrix).tolist(),
+                    "centers": centers, "base_points": points})
+    return out
+
+
 def frames_golden(spec):
     comps = residues(rf.ref_structure_from_spec(spec))
     observed = [set(a[0] for a in nt["atoms"]) for nt in spec["nts"]]
@@ -339,6 +410,10 @@ def main():
          annotate_with_traces(base, {'basepair': LW18, 'stacking': [], 'coplanar': []}))
     dump("annot_1gid_base_bp.json.gz", annotate_with_traces(base, {'basepair': LW18}))
     dump("geometry.json.gz", geometry_golden(strand, sarcin))
+    modified = make_spec_modified(full)
+    dump("spec_1gid_modified.json.gz", modified)
+    dump("frames_1gid_modified.json.gz", frames_golden_modified(modified))
+    dump("annot_1gid_modified_all9.json.gz", annotate_with_traces(modified, ALL9))
 
 
 if __name__ == "__main__":
