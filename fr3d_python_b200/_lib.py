@@ -91,8 +91,13 @@ def load():
         if _lib is not None:
             return _lib
         if not os.path.exists(LIB_PATH):
-            raise Fr3dError("libfr3d_b200.so not built (%s); run `python -c 'import __graft_entry__ as g; g.build()'`. "
-                            "There is no CPU fallback." % LIB_PATH)
+            # a fresh checkout: compile once with nvcc (sm_100a cross-compiles without a GPU)
+            try:
+                build()
+            except Exception as ex:
+                raise Fr3dError("libfr3d_b200.so is not built (%s) and building it failed: %s.  Run `python -c "
+                                "'import __graft_entry__ as g; g.build()'`.  There is no CPU fallback."
+                                % (LIB_PATH, ex))
         lib = C.CDLL(LIB_PATH)
         vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
         lib.fr3d_version.restype = C.c_int
