@@ -1,0 +1,650 @@
+// K4, thread-per-pair form.
+//
+// ncu on the warp-per-pair kernels (classify_pm.cuh, profiles/README.md) shows that the rule engine is
+// bound by instruction issue, and that most of the ~950 warp instructions spent per pair are
+// warp-UNIFORM bookkeeping (address arithmetic, mask decoding, votes, loop control, the scalar
+// coplanar / basepair-box / sugar-ribose logic) executed by 32 lanes for one pair.  Here one THREAD owns
+// one candidate pair and walks the same rules sequentially, so that bookkeeping is amortised over 32
+// pairs per warp instruction, while the data-parallel parts (32 atom projections, 12 oxygens, 30
+// donor/oxygen combinations, 256 atom-atom distances) become unrolled loops with plenty of
+// instruction-level parallelism.  Records are read straight from global memory through L1: pairs are
+// emitted grouped by nt1, so a warp's 32 pairs share a handful of nt1 records (broadcast) and spatially
+// neighbouring nt2 records.
+//
+// The arithmetic is the same as in the warp-per-pair kernels and as in the reference; every function
+// below cites the reference lines it restates (NA = fr3d/classifiers/NA_pairwise_interactions.py).
+#pragma once
+
+#include "classify.cuh"
+
+namespace fr3d {
+
+struct TFrame {
+    double c0, c1, c2;
+    double u0, u1, u2, u3, u4, u5, u6, u7, u8;     // row-major rotation_matrix
+};
+
+__device__ __forceinline__ TFrame load_tframe(const fr3d_nts_t &nts, int n) {
+    const double *c = nts.center + (size_t)n * 3;
+    const double *r = nts.rot + (size_t)n * 9;
+    TFrame f;
+    f.c0 = c[0]; f.c1 = c[1]; f.c2 = c[2];
+    f.u0 = r[0]; f.u1 = r[1]; f.u2 = r[2]; f.u3 = r[3]; f.u4 = r[4]; f.u5 = r[5]; f.u6 = r[6]; f.u7 = r[7]; f.u8 = r[8];
+    return f;
+}
+
+// translate_rotate_point (NA:1263-1275): (p - centre) . U as a row vector
+__device__ __forceinline__ void tproject(const TFrame &f, double px, double py, double pz, double &x, double &y,
+                                         double &z) {
+    const double v0 = px - f.c0, v1 = py - f.c1, v2 = pz - f.c2;
+    x = v0 * f.u0 + v1 * f.u3 + v2 * f.u6;
+    y = v0 * f.u1 + v1 * f.u4 + v2 * f.u7;
+    z = v0 * f.u2 + v1 * f.u5 + v2 * f.u8;
+}
+
+// return_overlap (NA:1530-1571): base atoms of nt_b seen from the frame of nt_a
+__device__ __forceinline__ bool t_overlap(const fr3d_nts_t &nts, const TFrame &fa, int par_a, int nb, uint32_t bmb,
+                                          double &zsel) {
+    const double *q = nts.base_xyz + (size_t)nb * FR3D_BASE_SLOTS * 3;
+    bool inside = false;
+    double zmin = 1e300, zmax = -1e300, best = 1e300;
+    zsel = 0.0;
+#pragma unroll 4
+    for (int a = 0; a < FR3D_BASE_SLOTS; ++a) {
+        if (!((bmb >> a) & 1u)) continue;
+        double x, y, z;
+        tproject(fa, q[a * 3], q[a * 3 + 1], q[a * 3 + 2], x, y, z);
+        if (in_hull(par_a, x, y, z)) inside = true;
+        if (fabs(z) < best) { best = fabs(z); zsel = z; }
+        zmin = fmin(zmin, z);
+        zmax = fmax(zmax, z);
+    }
+    return inside && !(zmax > 0 && zmin < 0);
+}
+
+// check_base_oxygen_stack_rings (NA:1278-1473): base of nt_a, oxygens of nt_b.  Returns the code or -1.
+__device__ __forceinline__ int t_so(const fr3d_nts_t &nts, const TFrame &fa, int pa, int nb, uint32_t bbb) {
+    if (pa < 0 || pa >= FR3D_N_PARENTS) return -1;
+    const double *B = nts.bb_xyz + (size_t)nb * FR3D_BB_SLOTS * 3;
+    const bool has_div = c_tab.has_div[pa];
+    bool true_found = false, ring_found = false;
+    double zmin_abs = 1e300, zring = 0.0;
+    int oring = -1;
+    double r2min = 1e300, znear = 0.0;
+    int onear = -1;
+#pragma unroll
+    for (int o = 0; o < 6; ++o) {
+        const int oslot = (0x213456 >> (4 * o)) & 7;          // O2' O3' O4' O5' OP1 OP2 -> slots 6 5 4 3 1 2
+        if (!((bbb >> oslot) & 1u)) continue;
+        double x, y, z;
+        tproject(fa, B[oslot * 3], B[oslot * 3 + 1], B[oslot * 3 + 2], x, y, z);
+        // every ring and near-ring ellipse lies inside the disc x^2 + y^2 < 25 (tests/test_abi.py)
+        if (!(fabs(z) < 3.6) || !(x * x + y * y < 25.0)) continue;
+        const bool left = has_div && left_of(c_tab.ring_div[pa], x, y);
+        if (!(fabs(z) < 2.0)) {
+            bool ring = true;
+            if (left) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) ring = ring && left_of(c_tab.ring5[pa][k], x, y);
+            } else {
+#pragma unroll
+                for (int k = 0; k < 6; ++k) ring = ring && left_of(c_tab.ring6[pa][k], x, y);
+            }
+            if (ring) {
+                ring_found = true;
+                if (fabs(z) < 3.5) true_found = true;
+                if (fabs(z) < zmin_abs) { zmin_abs = fabs(z); zring = z; oring = o; }
+            }
+        }
+        if (fabs(z) < 3.5 && in_ellipse(left ? c_tab.ell5[pa] : c_tab.ell6[pa], x, y)) {
+            const double r2 = x * x + y * y;
+            if (r2 < r2min) { r2min = r2; znear = z; onear = o; }
+        }
+    }
+    if (ring_found) return oring | ((zring > 0) ? 0 : 8) | (true_found ? 0 : 16);
+    if (onear >= 0) return onear | ((znear > 0) ? 0 : 8) | 16;
+    return -1;
+}
+
+// check_sugar_ribose (NA:2262-2342) after the shared O2'-O2' screen.  -1 none, 0 cSR, 1 tSR.
+__device__ __noinline__ int t_sr_tail(const fr3d_nts_t &nts, int na, int nb, uint32_t bma, uint32_t bba, uint32_t bbb,
+                                      int pa, double n0, double n1, double n2) {
+    const int bs = c_tab.sr_slot[pa];
+    if (bs < 0 || !((bma >> bs) & 1u)) return -1;
+    const double *A = nts.bb_xyz + (size_t)na * FR3D_BB_SLOTS * 3;
+    const double *B = nts.bb_xyz + (size_t)nb * FR3D_BB_SLOTS * 3;
+    const double *bp = nts.base_xyz + ((size_t)na * FR3D_BASE_SLOTS + bs) * 3;
+    const double d0 = bp[0] - B[18], d1 = bp[1] - B[19], d2 = bp[2] - B[20];
+    if (sqrt(d0 * d0 + d1 * d1 + d2 * d2) > 3.8) return -1;
+    if (fabs(d0 * n0 + d1 * n1 + d2 * n2) > 2.0) return -1;
+    if (!(bba >> 7 & 1u) || !(bba >> 8 & 1u) || !(bbb >> 7 & 1u) || !(bbb >> 8 & 1u)) return -1;
+    double b0[3], b1[3], b2[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        b0[k] = -1.0 * (A[24 + k] - A[21 + k]);
+        b1[k] = B[24 + k] - A[24 + k];
+        b2[k] = B[21 + k] - B[24 + k];
+    }
+    const double nb1 = sqrt(b1[0] * b1[0] + b1[1] * b1[1] + b1[2] * b1[2]);
+    b1[0] /= nb1; b1[1] /= nb1; b1[2] /= nb1;
+    const double d01 = b0[0] * b1[0] + b0[1] * b1[1] + b0[2] * b1[2];
+    const double d21 = b2[0] * b1[0] + b2[1] * b1[1] + b2[2] * b1[2];
+    double v[3], w[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { v[k] = b0[k] - d01 * b1[k]; w[k] = b2[k] - d21 * b1[k]; }
+    const double x = v[0] * w[0] + v[1] * w[1] + v[2] * w[2];
+    const double cx0 = b1[1] * v[2] - b1[2] * v[1], cx1 = b1[2] * v[0] - b1[0] * v[2], cx2 = b1[0] * v[1] - b1[1] * v[0];
+    const double y = cx0 * w[0] + cx1 * w[1] + cx2 * w[2];
+    const double angle = atan2_once(y, x) * (180.0 / 3.141592653589793);
+    return fabs(angle) > 90.0 ? 0 : 1;
+}
+
+// check_base_backbone_interactions (NA:1867-2049): nt1 base -> nt2 backbone, with the reference's own
+// sequential, sticky selection.  Returns bph | br << 8 (digit | near << 4; 0xFF none).
+__device__ __noinline__ int t_backbone(const fr3d_nts_t &nts, const TFrame &f1, int par1, int n1, int n2, uint32_t bm1,
+                                       uint32_t bb2) {
+    const double *B = nts.bb_xyz + (size_t)n2 * FR3D_BB_SLOTS * 3;
+    const double *A = nts.base_xyz + (size_t)n1 * FR3D_BASE_SLOTS * 3;
+    int bph = -1, br = -1;
+    bool use_ph = true;                    // P far from the plane of base 1: no BPh (NA:1915-1921)
+    if (bb2 & 1u) {
+        if (B[0] != 0.0 || B[1] != 0.0 || B[2] != 0.0) {
+            double tx, ty, tz;
+            tproject(f1, B[0], B[1], B[2], tx, ty, tz);
+            if (fabs(tz) > 4.5) use_ph = false;
+        }
+    }
+    const int nsites = c_tab.n_sites[par1];
+    int n_true = 0, n_near = 0, n_keys = 0;
+    unsigned long long site_ox = 0;
+    double best_tq = -1e300, best_nq = -1e300;
+    int best_tl = -1, best_nl = -1, first_tl = -1, first_nl = -1;
+    int rt = 0, rn = 0, best_rtl = -1, best_rnl = -1, first_rtl = -1, first_rnl = -1;
+    double best_rtq = -1e300, best_rnq = -1e300;
+    double cutoff = 0.0, ncutoff = 0.0;
+#pragma unroll 1
+    for (int s = 0; s < nsites; ++s) {
+        const int carbon = c_tab.site_carbon[par1][s];
+        const int digit = c_tab.site_digit[par1][s];
+        if (carbon == 1) { cutoff = 4.0; ncutoff = 4.5; }          // NA:1930-1935
+        else if (carbon == 0) { cutoff = 3.5; ncutoff = 4.0; }
+        const int hs = c_tab.site_h[par1][s], ms = c_tab.site_m[par1][s];
+        if ((bm1 >> hs & 1u) && (bm1 >> ms & 1u)) {
+            const double *H = A + hs * 3, *Mv = A + ms * 3;
+#pragma unroll 1
+            for (int i = 0; i < 6; ++i) {
+                if (i < 4 && !use_ph) continue;
+                const int oslot = (0x469213 >> (4 * i)) & 15;       // O5' OP1 OP2 prevO3' | O2' O4'
+                if (!((bb2 >> oslot) & 1u)) continue;
+                const double *O = B + oslot * 3;
+                if (!(O[0] != 0.0 || O[1] != 0.0 || O[2] != 0.0)) continue;      // .any(), NA:1939,1959
+                const double q0 = Mv[0] - O[0], q1 = Mv[1] - O[1], q2 = Mv[2] - O[2];
+                const double d2 = q0 * q0 + q1 * q1 + q2 * q2;
+                if (!(d2 < 20.2501)) continue;                     // every label needs distance < 4.5
+                const double ds = sqrt(d2);
+                const double an = hb_angle(Mv, H, O);
+                if (!(an != 0.0 && ds != 0.0)) continue;
+                if (i < 4) {
+                    if (an > 130.0 && ds < cutoff) {
+                        const double q = (cutoff - ds) + (an - 130.0) / 20.0;
+                        if (n_true == 0) first_tl = digit;
+                        ++n_true;
+                        if (q > best_tq || (q == best_tq && digit < best_tl)) { best_tq = q; best_tl = digit; }
+                        if (!((site_ox >> (digit * 4)) & 0xFull)) ++n_keys;
+                        site_ox |= 1ull << (digit * 4 + i);
+                    } else if (an > 110.0 && ds < ncutoff) {
+                        const double q = (ncutoff - ds) + (an - 110.0) / 20.0;
+                        if (n_near == 0) first_nl = digit;
+                        ++n_near;
+                        if (q > best_nq || (q == best_nq && digit < best_nl)) { best_nq = q; best_nl = digit; }
+                    }
+                } else {
+                    if (an > 130.0 && ds < cutoff) {
+                        const double q = (cutoff - ds) + (an - 130.0) / 20.0;
+                        if (rt == 0) first_rtl = digit;
+                        ++rt;
+                        if (q > best_rtq || (q == best_rtq && digit < best_rtl)) { best_rtq = q; best_rtl = digit; }
+                    } else if (an > 110.0 && ds < ncutoff) {
+                        const double q = (ncutoff - ds) + (an - 110.0) / 20.0;
+                        if (rn == 0) first_rnl = digit;
+                        ++rn;
+                        if (q > best_rnq || (q == best_rnq && digit < best_rnl)) { best_rnq = q; best_rnl = digit; }
+                    }
+                }
+            }
+        }
+        // sticky selection, evaluated after EVERY site (NA:1973-2019)
+        if (n_true == 1) {
+            bph = first_tl;
+        } else if (n_keys > 1) {
+            const unsigned o7 = (site_ox >> 28) & 0xF, o9 = (site_ox >> 36) & 0xF;
+            const unsigned o3 = (site_ox >> 12) & 0xF, o5 = (site_ox >> 20) & 0xF;
+            if (o7 && o9) { if (__popc(o7 | o9) > 1) bph = 8; }
+            else if (o3 && o5) { if (__popc(o3 | o5) > 1) bph = 4; }
+            if (bph < 0) bph = best_tl;
+        } else if (n_true > 1) {
+            bph = best_tl;
+        } else if (n_near == 1) {
+            bph = first_nl | 16;
+        } else if (n_near > 1) {
+            bph = best_nl | 16;
+        }
+        if (rt == 1) br = first_rtl;
+        else if (rt > 1) br = best_rtl;
+        else if (rn == 1) br = first_rnl | 16;
+        else if (rn > 1) br = best_rnl | 16;
+    }
+    return (bph & 0xFF) | ((br & 0xFF) << 8);
+}
+
+// cheap necessary condition for t_backbone: some donor heavy atom of nt1 within 4.5 A of a backbone oxygen
+__device__ __forceinline__ bool t_backbone_possible(const fr3d_nts_t &nts, int par1, int n1, int n2, uint32_t bm1,
+                                                    uint32_t bb2) {
+    const double *B = nts.bb_xyz + (size_t)n2 * FR3D_BB_SLOTS * 3;
+    const double *A = nts.base_xyz + (size_t)n1 * FR3D_BASE_SLOTS * 3;
+    const int nsites = c_tab.n_sites[par1];
+    bool any = false;
+#pragma unroll 1
+    for (int s = 0; s < nsites; ++s) {
+        const int ms = c_tab.site_m[par1][s];
+        if (!((bm1 >> ms) & 1u)) continue;
+        const double m0 = A[ms * 3], m1 = A[ms * 3 + 1], m2 = A[ms * 3 + 2];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            const int oslot = (0x469213 >> (4 * i)) & 15;
+            const double q0 = m0 - B[oslot * 3], q1 = m1 - B[oslot * 3 + 1], q2 = m2 - B[oslot * 3 + 2];
+            if (((bb2 >> oslot) & 1u) && (q0 * q0 + q1 * q1 + q2 * q2 < 20.2501)) any = true;
+        }
+    }
+    return any;
+}
+
+// one point of a (possibly twin) slot: v < 16 -> the observed / stored point, v >= 16 -> the ideal copy
+__device__ __forceinline__ bool t_point(const fr3d_nts_t &nts, const TFrame &f, int par, int n, uint32_t bm, uint32_t tw,
+                                        int v, double &p0, double &p1, double &p2) {
+    const int k = v & 15;
+    if (!((bm >> k) & 1u)) return false;
+    const bool twin = (tw >> k) & 1u;
+    if (v >= 16 && !twin) return false;
+    const double *q = nts.base_xyz + ((size_t)n * FR3D_BASE_SLOTS + k) * 3;
+    p0 = q[0]; p1 = q[1]; p2 = q[2];
+    if (twin) {
+        const double s0 = c_tab.std_xyz[par][k][0], s1 = c_tab.std_xyz[par][k][1], s2 = c_tab.std_xyz[par][k][2];
+        const double i0 = f.c0 + (f.u0 * s0 + f.u1 * s1 + f.u2 * s2);
+        const double i1 = f.c1 + (f.u3 * s0 + f.u4 * s1 + f.u5 * s2);
+        const double i2 = f.c2 + (f.u6 * s0 + f.u7 * s1 + f.u8 * s2);
+        if (v >= 16) { p0 = i0; p1 = i1; p2 = i2; }
+        else { p0 = 2.0 * p0 - i0; p1 = 2.0 * p1 - i1; p2 = 2.0 * p2 - i2; }
+    }
+    return true;
+}
+
+// calculate_basepair_gap (NA:2189-2259): min |z| (frame of nt_a) over the 3 base atoms of nt_b nearest
+// to the centre of nt_a
+__device__ __noinline__ double t_gap(const fr3d_nts_t &nts, const TFrame &fa, const TFrame &fb, int par_b, int nb,
+                                     uint32_t bmb, uint32_t twb) {
+    double k0 = 1e300, k1 = 1e300, k2 = 1e300, z0 = 100.0, z1 = 100.0, z2 = 100.0;
+    const int nv = twb ? 32 : 16;
+#pragma unroll 1
+    for (int v = 0; v < nv; ++v) {
+        double p0, p1, p2;
+        if (!t_point(nts, fb, par_b, nb, bmb, twb, v, p0, p1, p2)) continue;
+        const double w0 = p0 - fa.c0, w1 = p1 - fa.c1, w2 = p2 - fa.c2;
+        const double key = w0 * w0 + w1 * w1 + w2 * w2;
+        const double z = fabs(w0 * fa.u2 + w1 * fa.u5 + w2 * fa.u8);
+        if (key < k0) { k2 = k1; z2 = z1; k1 = k0; z1 = z0; k0 = key; z0 = z; }
+        else if (key < k1) { k2 = k1; z2 = z1; k1 = key; z1 = z; }
+        else if (key < k2) { k2 = key; z2 = z; }
+    }
+    return fmin(z0, fmin(z1, z2));
+}
+
+// calculate_base_min_distances (NA:1799-1829)
+__device__ __noinline__ double t_mind(const fr3d_nts_t &nts, const TFrame &f1, const TFrame &f2, int par1, int par2,
+                                      int n1, int n2, uint32_t bm1, uint32_t bm2, uint32_t tw1, uint32_t tw2) {
+    double best = 1e300;
+    const int nv1 = tw1 ? 32 : 16, nv2 = tw2 ? 32 : 16;
+#pragma unroll 1
+    for (int v = 0; v < nv1; ++v) {
+        double a0, a1, a2;
+        if (!t_point(nts, f1, par1, n1, bm1, tw1, v, a0, a1, a2)) continue;
+        if (!tw2) {
+            const double *q = nts.base_xyz + (size_t)n2 * FR3D_BASE_SLOTS * 3;
+#pragma unroll 4
+            for (int k = 0; k < FR3D_BASE_SLOTS; ++k) {
+                const double d0 = q[k * 3] - a0, d1 = q[k * 3 + 1] - a1, d2 = q[k * 3 + 2] - a2;
+                const double dd = d0 * d0 + d1 * d1 + d2 * d2;
+                if (((bm2 >> k) & 1u) && dd < best) best = dd;
+            }
+        } else {
+#pragma unroll 1
+            for (int w = 0; w < nv2; ++w) {
+                double b0, b1, b2;
+                if (!t_point(nts, f2, par2, n2, bm2, tw2, w, b0, b1, b2)) continue;
+                const double d0 = b0 - a0, d1 = b1 - a1, d2 = b2 - a2;
+                best = fmin(best, d0 * d0 + d1 * d1 + d2 * d2);
+            }
+        }
+    }
+    return best < 1e299 ? sqrt(best) : 9999.0;
+}
+
+// One pass of check_basepair_cutoffs (NA:2546-2612) over the boxes of one orientation: L1 distance to every
+// box up to and including the angle term.  With `final` the gap term and the true / near classification
+// follow (NA:2642-2689) and the chosen box is returned; without it only "is any box still within 1.0".
+struct TBp {
+    int box;        // chosen box or -1
+    int near;       // bit0 "n" prefix, bit1 n-named box
+    double cd;
+};
+
+__device__ __noinline__ bool t_boxes(const fr3d_box_t *__restrict__ boxes, int bstart, int bcount, double dX, double dY,
+                                     double dZ, double nZ, double M11, double M01, bool final, double gmax, double mind,
+                                     int pb, TBp &out) {
+    double ang = 0.0;
+    bool have_ang = false, any = false;
+    int best_match = -1, best_near = -1;
+    int match_key = 0x7FFFFFFF;
+    double near_cd = 1e300, match_cd = 0.0;
+    int match_flags = 0, near_flags = 0;
+#pragma unroll 1
+    for (int b = 0; b < bcount; ++b) {
+        const fr3d_box_t *bx = boxes + bstart + b;
+        double cd = 0.0;
+        cd += fmax(0.0, bx->xmin - dX);
+        cd += fmax(0.0, dX - bx->xmax);
+        cd += fmax(0.0, bx->ymin - dY);
+        cd += fmax(0.0, dY - bx->ymax);
+        const int flags = bx->flags;
+        if (flags & 8) cd += fmax(0.0, sqrt(dX * dX + dY * dY) - bx->radiusmax);
+        cd += fmax(0.0, bx->zmin - dZ);
+        cd += fmax(0.0, dZ - bx->zmax);
+        cd += 3.0 * fmax(0.0, bx->normalmin - nZ);
+        cd += 3.0 * fmax(0.0, nZ - bx->normalmax);
+        if (!(cd < 1.0)) continue;                                   // NA:2580
+        if (!have_ang) {
+            ang = atan2_once(M11, M01) * 57.29577951308232 - 90.0;   // NA:2594
+            if (ang <= -90.0) ang += 360.0;
+            have_ang = true;
+        }
+        const double amin = bx->anglemin, amax = bx->anglemax;
+        if (amin < amax) {
+            cd += 0.05 * fmax(0.0, amin - ang);
+            cd += 0.05 * fmax(0.0, ang - amax);
+        } else {
+            cd += 0.05 * fmin(fmax(0.0, amin - ang), fmax(0.0, ang - amax));
+        }
+        if (!(cd < 1.0)) continue;                                   // NA:2611
+        any = true;
+        if (!final) return true;
+        const double gapmax = bx->gapmax;
+        if (gapmax > 0.1) cd += 4.0 * fmax(0.0, gmax - gapmax);      // NA:2643-2645
+        bool one_hb = false;                                         // NA:2648-2652
+        if ((flags & 2) && (pb == 1 || pb == 3)) one_hb = true;
+        else if ((flags & 4) && pb == 3) one_hb = true;
+        const bool starts_n = flags & 1;
+        bool is_match = false, is_near = false;
+        if (cd > 0) {
+            if (cd < 1.0 && !starts_n && (mind < 4.1 || one_hb)) is_near = true;
+        } else if (starts_n) {
+            is_near = true;
+        } else if (mind > 3.75 && !one_hb) {
+            is_near = true;
+        } else {
+            is_match = true;
+        }
+        if (is_match) {                       // stable sort by (subcategory, len(name)): first smallest key wins
+            const int key = bx->subcat * 64 + bx->name_len;
+            if (key < match_key) { match_key = key; best_match = bstart + b; match_cd = cd; match_flags = flags; }
+        } else if (is_near) {                 // nearest near match, earlier box on ties
+            if (cd < near_cd) { near_cd = cd; best_near = bstart + b; near_flags = flags; }
+        }
+    }
+    if (!final) return any;
+    out.box = -1; out.near = 0; out.cd = 0.0;
+    if (best_match >= 0) {
+        out.box = best_match; out.cd = match_cd;
+        out.near = ((match_cd > 0 && !(match_flags & 1)) ? 1 : 0) | ((match_flags & 1) ? 2 : 0);
+    } else if (best_near >= 0) {
+        out.box = best_near; out.cd = near_cd;
+        out.near = ((near_cd > 0 && !(near_flags & 1)) ? 1 : 0) | ((near_flags & 1) ? 2 : 0);
+    }
+    return any;
+}
+
+#ifndef FR3D_TPP_MIN_BLOCKS
+#define FR3D_TPP_MIN_BLOCKS 3
+#endif
+
+__global__ void __launch_bounds__(128, FR3D_TPP_MIN_BLOCKS)
+classify_pairs_tpp_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, const int32_t *__restrict__ box_index,
+                          const int32_t *__restrict__ pair_i, const int32_t *__restrict__ pair_j,
+                          const int32_t *__restrict__ pair_rank, int64_t pair_cap, uint32_t cats, int32_t index_offset,
+                          fr3d_hit_t *__restrict__ hits, int64_t hit_cap, int64_t *counters) {
+    const int lane = threadIdx.x & 31;
+    long long n_pairs = counters[0];
+    if (n_pairs > pair_cap) n_pairs = pair_cap;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    // whole warps iterate together so that the emission below can use warp collectives
+    const long long first = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long rounds = (n_pairs + stride - 1) / stride;
+
+#pragma unroll 1
+    for (long long r = 0; r < rounds; ++r) {
+        const long long p = first + r * stride;
+        const bool active = p < n_pairs;
+        unsigned hmask = 0;
+        int c_so12 = 0, c_so21 = 0, c_stack = 0, c_sr12 = 0, c_sr21 = 0, c_bph = 0, c_br = 0, c_bp = 0, bp_box = 0;
+        double bp_cd = 0.0, bp_gap = 0.0;
+        int n1 = 0, n2 = 0, rank = 0;
+        if (active) {
+            n1 = pair_i[p]; n2 = pair_j[p]; rank = pair_rank[p];
+            const uint32_t bm1 = nts.base_mask[n1], bm2 = nts.base_mask[n2];
+            const uint32_t bb1 = nts.bb_mask[n1], bb2 = nts.bb_mask[n2];
+            const int par1 = (int)((bm1 >> 16) & 15u) - 1, par2 = (int)((bm2 >> 16) & 15u) - 1;
+            const TFrame f1 = load_tframe(nts, n1), f2 = load_tframe(nts, n2);
+            const double nZ = f1.u2 * f2.u2 + f1.u5 * f2.u5 + f1.u8 * f2.u8;      // M[2][2] in both orientations
+
+            // ---- base-oxygen stacking, both directions (NA:758-778)
+            if (cats & FR3D_CAT_SO) {
+                const int a = t_so(nts, f1, par1, n2, bb2);
+                const int b = t_so(nts, f2, par2, n1, bb1);
+                if (a >= 0) { hmask |= 1u << FR3D_SLOT_SO12; c_so12 = a; }
+                if (b >= 0) { hmask |= 1u << FR3D_SLOT_SO21; c_so21 = b; }
+            }
+            // ---- base-base stacking, part 1 (NA:1602-1702)
+            int stack_code = -1;
+            bool stack_both = false;
+            if ((cats & FR3D_CAT_STACKING) && par1 >= 0 && par2 >= 0) {
+                double z_2on1, z_1on2;
+                const bool nt2on1 = t_overlap(nts, f1, par1, n2, bm2, z_2on1);
+                const bool nt1on2 = t_overlap(nts, f2, par2, n1, bm1, z_1on2);
+                if ((nt2on1 || nt1on2) && !(fabs(nZ) < 0.5)) {
+                    const bool reverse = nt1on2 && !nt2on1;
+                    const double mvd = reverse ? z_1on2 : z_2on1;
+                    int code = -1;
+                    if (mvd > 0) { if (nZ > 0) code = 0; else if (nZ < 0) code = 2; }
+                    else if (mvd < 0) { if (nZ > 0) code = 1; else if (nZ < 0) code = 3; }
+                    if (reverse && code >= 0 && code < 2) code ^= 1;
+                    stack_code = code;
+                    stack_both = nt2on1 && nt1on2;
+                }
+            }
+            // ---- sugar-ribose, both directions (NA:791-804)
+            if ((cats & FR3D_CAT_SUGAR_RIBOSE) && par1 >= 0 && par2 >= 0 && par1 != 4 && par2 != 4 &&
+                (bb1 >> 6 & 1u) && (bb2 >> 6 & 1u)) {
+                const double *A = nts.bb_xyz + (size_t)n1 * FR3D_BB_SLOTS * 3;
+                const double *B = nts.bb_xyz + (size_t)n2 * FR3D_BB_SLOTS * 3;
+                const double o0 = A[18] - B[18], o1 = A[19] - B[19], o2 = A[20] - B[20];
+                const double oo = o0 * o0 + o1 * o1 + o2 * o2;
+                if (oo < 14.4401 && !(sqrt(oo) > 3.8)) {
+                    const int r12 = t_sr_tail(nts, n1, n2, bm1, bb1, bb2, par1, f1.u2, f1.u5, f1.u8);
+                    const int r21 = t_sr_tail(nts, n2, n1, bm2, bb2, bb1, par2, f2.u2, f2.u5, f2.u8);
+                    if (r12 >= 0) { hmask |= 1u << FR3D_SLOT_SR12; c_sr12 = r12; }
+                    if (r21 >= 0) { hmask |= 1u << FR3D_SLOT_SR21; c_sr21 = r21; }
+                }
+            }
+            // ---- base-phosphate / base-ribose, nt1 base -> nt2 backbone (NA:807-829)
+            if ((cats & FR3D_CAT_BACKBONE) && par1 >= 0 && t_backbone_possible(nts, par1, n1, n2, bm1, bb2)) {
+                const int sel = t_backbone(nts, f1, par1, n1, n2, bm1, bb2);
+                if ((sel & 0xFF) != 0xFF) { hmask |= 1u << FR3D_SLOT_BPH; c_bph = sel & 0xFF; }
+                if (((sel >> 8) & 0xFF) != 0xFF) { hmask |= 1u << FR3D_SLOT_BR; c_br = (sel >> 8) & 0xFF; }
+            }
+            // ---- coplanar + basepair (NA:834-1013)
+            const bool gly_ok = (bm1 & 1u) && (bm2 & 1u) && par1 >= 0 && par2 >= 0;
+            unsigned ori_ok = 0, bp_live = 0;
+            bool cp_frames = false;
+            double gd0 = 0, gd1 = 0, gd2 = 0;
+            if (gly_ok) {
+                if (c_tab.combo_ok[par1 * FR3D_N_PARENTS + par2]) ori_ok |= 1u;
+                if (c_tab.combo_ok[par2 * FR3D_N_PARENTS + par1]) ori_ok |= 2u;
+                if ((cats & FR3D_CAT_COPLANAR) && ori_ok && fabs(nZ) > 0.7757) {
+                    const double e0 = f1.c0 - f2.c0, e1 = f1.c1 - f2.c1, e2 = f1.c2 - f2.c2;
+                    const double lim = (0.3381 * 0.3381) * (e0 * e0 + e1 * e1 + e2 * e2);
+                    const double d1 = e0 * f1.u2 + e1 * f1.u5 + e2 * f1.u8;
+                    const double d2 = e0 * f2.u2 + e1 * f2.u5 + e2 * f2.u8;
+                    cp_frames = d1 * d1 < lim && d2 * d2 < lim;
+                }
+                const double *g1 = nts.base_xyz + (size_t)n1 * FR3D_BASE_SLOTS * 3;
+                const double *g2 = nts.base_xyz + (size_t)n2 * FR3D_BASE_SLOTS * 3;
+                gd0 = g2[0] - g1[0]; gd1 = g2[1] - g1[1]; gd2 = g2[2] - g1[2];
+#pragma unroll 1
+                for (int ori = 0; ori < 2; ++ori) {
+                    if (!((ori_ok >> ori) & 1u)) continue;
+                    const TFrame &fa = ori ? f2 : f1;
+                    const TFrame &fb = ori ? f1 : f2;
+                    const double s = ori ? -1.0 : 1.0;
+                    const double v0 = s * gd0, v1 = s * gd1, v2 = s * gd2;
+                    const double dZ = v0 * fa.u2 + v1 * fa.u5 + v2 * fa.u8;
+                    if (fabs(dZ) > 3.6) continue;
+                    const double dX = v0 * fa.u0 + v1 * fa.u3 + v2 * fa.u6;
+                    const double dY = v0 * fa.u1 + v1 * fa.u4 + v2 * fa.u7;
+                    const int combo = ori ? par2 * FR3D_N_PARENTS + par1 : par1 * FR3D_N_PARENTS + par2;
+                    const int sg = nZ > 0 ? 0 : 1;
+                    const int bstart = box_index[(combo * 2 + sg) * 2 + 0];
+                    const int bcount = box_index[(combo * 2 + sg) * 2 + 1];
+                    const double M11 = fa.u1 * fb.u1 + fa.u4 * fb.u4 + fa.u7 * fb.u7;
+                    const double M01 = fa.u0 * fb.u1 + fa.u3 * fb.u4 + fa.u6 * fb.u7;
+                    TBp dummy;
+                    if (t_boxes(boxes, bstart, bcount, dX, dY, dZ, nZ, M11, M01, false, 0.0, 0.0, 0, dummy))
+                        bp_live |= 1u << ori;
+                }
+            }
+            // ---- gaps / minimum distance, only when something can still use them
+            double gap12 = 100.0, gap21 = 100.0, mind = 9999.0;
+            if (stack_code >= 0 || bp_live || cp_frames) {
+                uint32_t tw1 = 0, tw2 = 0;
+                if ((bm1 >> 22) & 1u) tw1 = (uint32_t)nts.meta[(size_t)n1 * FR3D_META_INTS + 7] >> 16;
+                if ((bm2 >> 22) & 1u) tw2 = (uint32_t)nts.meta[(size_t)n2 * FR3D_META_INTS + 7] >> 16;
+                if (bp_live || cp_frames) {
+                    gap12 = t_gap(nts, f1, f2, par2, n2, bm2, tw2);
+                    gap21 = t_gap(nts, f2, f1, par1, n1, bm1, tw1);
+                }
+                const bool cp_gap = cp_frames && (((ori_ok & 1u) && gap12 < 1.5179) || ((ori_ok & 2u) && gap21 < 1.5179));
+                if (stack_code >= 0 || bp_live || cp_gap)
+                    mind = t_mind(nts, f1, f2, par1, par2, n1, n2, bm1, bm2, tw1, tw2);
+                if (stack_code >= 0 && !(fabs(mind) < 1.0)) {                 // NA:1707-1718
+                    int near = 1;
+                    if (fabs(mind) < 4.0 && fabs(mind) > 1.0 && fabs(nZ) > 0.6 && stack_both) near = 0;
+                    hmask |= 1u << FR3D_SLOT_STACK;
+                    c_stack = stack_code | (near << 2);
+                }
+                if (cp_gap) {                                                 // NA:2080-2096
+                    const bool both_std = (bm1 >> 20 & 1u) && (bm2 >> 20 & 1u);
+                    if (mind < 3.4589 && !(mind >= 2.4589 && both_std)) hmask |= 1u << FR3D_SLOT_CP;
+                }
+                if (bp_live) {
+                    const double gmax = fmax(gap12, gap21);
+                    TBp res[2];
+                    res[0].box = -1; res[1].box = -1; res[0].near = res[1].near = 0; res[0].cd = res[1].cd = 0.0;
+#pragma unroll 1
+                    for (int ori = 0; ori < 2; ++ori) {
+                        if (!((bp_live >> ori) & 1u)) continue;
+                        const TFrame &fa = ori ? f2 : f1;
+                        const TFrame &fb = ori ? f1 : f2;
+                        const double s = ori ? -1.0 : 1.0;
+                        const double v0 = s * gd0, v1 = s * gd1, v2 = s * gd2;
+                        const double dZ = v0 * fa.u2 + v1 * fa.u5 + v2 * fa.u8;
+                        const double dX = v0 * fa.u0 + v1 * fa.u3 + v2 * fa.u6;
+                        const double dY = v0 * fa.u1 + v1 * fa.u4 + v2 * fa.u7;
+                        const int pb = ori ? par1 : par2;
+                        const int combo = ori ? par2 * FR3D_N_PARENTS + par1 : par1 * FR3D_N_PARENTS + par2;
+                        const int sg = nZ > 0 ? 0 : 1;
+                        const int bstart = box_index[(combo * 2 + sg) * 2 + 0];
+                        const int bcount = box_index[(combo * 2 + sg) * 2 + 1];
+                        const double M11 = fa.u1 * fb.u1 + fa.u4 * fb.u4 + fa.u7 * fb.u7;
+                        const double M01 = fa.u0 * fb.u1 + fa.u3 * fb.u4 + fa.u6 * fb.u7;
+                        TBp o;
+                        t_boxes(boxes, bstart, bcount, dX, dY, dZ, nZ, M11, M01, true, gmax, mind, pb, o);
+                        if (ori) res[1] = o; else res[0] = o;
+                    }
+                    int use = -1;                                             // NA:935-957
+                    if (res[0].box >= 0 && res[1].box >= 0) {
+                        const bool n0 = res[0].near != 0, n1_ = res[1].near != 0;
+                        const bool same = ((res[0].near & 1) == (res[1].near & 1)) &&
+                                          (boxes[res[0].box].rev_lower_id == boxes[res[1].box].lower_id);
+                        if (same) use = 0;
+                        else if (n0 && n1_) use = (res[0].cd < res[1].cd) ? 0 : 1;
+                        else if (n1_) use = 0;
+                        else if (n0) use = 1;
+                        else use = 0;
+                    } else if (res[0].box >= 0) use = 0;
+                    else if (res[1].box >= 0) use = 1;
+                    if (use >= 0) {
+                        hmask |= 1u << FR3D_SLOT_BP;
+                        const TBp &u = use ? res[1] : res[0];
+                        c_bp = (u.near & 1) | (use << 1);
+                        bp_box = u.box;
+                        bp_cd = u.cd;
+                        bp_gap = gmax;
+                    }
+                }
+            }
+        }
+        // ---- emit: warp-aggregated allocation (one atomicAdd per warp), then each thread writes its hits
+        const int cnt = __popc(hmask);
+        int incl = cnt;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int t = __shfl_up_sync(FULL, incl, off);
+            if (lane >= off) incl += t;
+        }
+        const int total = __shfl_sync(FULL, incl, 31);
+        if (total) {
+            long long base = 0;
+            if (lane == 31) base = (long long)atomicAdd((unsigned long long *)&counters[1], (unsigned long long)total);
+            base = __shfl_sync(FULL, base, 31);
+            long long pos = base + (incl - cnt);
+            unsigned m = hmask;
+            while (m) {
+                const int s = __ffs(m) - 1;
+                m &= m - 1;
+                if (pos < hit_cap) {
+                    int code = 0;
+                    switch (s) {
+                        case FR3D_SLOT_SO12: code = c_so12; break;
+                        case FR3D_SLOT_SO21: code = c_so21; break;
+                        case FR3D_SLOT_STACK: code = c_stack; break;
+                        case FR3D_SLOT_SR12: code = c_sr12; break;
+                        case FR3D_SLOT_SR21: code = c_sr21; break;
+                        case FR3D_SLOT_BPH: code = c_bph; break;
+                        case FR3D_SLOT_BR: code = c_br; break;
+                        case FR3D_SLOT_BP: code = c_bp; break;
+                        default: break;
+                    }
+                    const bool isbp = s == FR3D_SLOT_BP;
+                    const double cdv = isbp ? bp_cd : 0.0, gv = isbp ? bp_gap : 0.0;
+                    const uint32_t w3 = (uint32_t)s | ((uint32_t)code << 8) | ((uint32_t)(isbp ? bp_box : 0) << 16);
+                    uint4 *dst = reinterpret_cast<uint4 *>(hits + pos);
+                    dst[0] = make_uint4((uint32_t)(n1 + index_offset), (uint32_t)(n2 + index_offset),
+                                        (uint32_t)(rank + 16 * index_offset), w3);
+                    dst[1] = make_uint4((uint32_t)__double2loint(cdv), (uint32_t)__double2hiint(cdv),
+                                        (uint32_t)__double2loint(gv), (uint32_t)__double2hiint(gv));
+                }
+                ++pos;
+            }
+        }
+    }
+}
+
+}  // namespace fr3d

@@ -14,6 +14,7 @@
 #include "search.cuh"
 #include "classify.cuh"
 #include "classify_pm.cuh"
+#include "classify_tpp.cuh"
 #include "geometry.cuh"
 
 namespace {
@@ -139,19 +140,33 @@ int fr3d_classify_pairs(const fr3d_nts_t *nts, const fr3d_box_t *boxes, const in
     if (pair_cap <= 0) return FR3D_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // persistent warps: grid is a multiple of the SM count; n_pairs is read on the device
-    static int mult = -1;                       // tuning knob: CTAs per SM of the persistent grid
+    static int mult = -1, tpp = -1;             // tuning knobs: CTAs per SM, thread-per-pair kernel on/off
     if (mult < 0) {
         const char *e = getenv("FR3D_CLASSIFY_GRID_MULT");
-        mult = (e && atoi(e) > 0) ? atoi(e) : FR3D_CLASSIFY_MIN_BLOCKS;   // exactly the resident CTAs: one wave
+        mult = (e && atoi(e) > 0) ? atoi(e) : 0;
+        const char *t = getenv("FR3D_CLASSIFY_TPP");
+        tpp = t ? atoi(t) : 1;
     }
-    const long long per_block = (long long)fr3d::WARPS_PER_BLOCK * fr3d::PM_K;
-    long long want = (pair_cap + per_block - 1) / per_block;
-    long long maxgrid = (long long)g_sm_count * mult;
-    int grid = (int)(want < maxgrid ? want : maxgrid);
-    if (grid < 1) grid = 1;
-    fr3d::classify_pairs_pm_kernel<<<grid, fr3d::WARPS_PER_BLOCK * 32, 0, st>>>(
-        *nts, boxes, box_index, pair_i, pair_j, pair_rank, pair_cap, category_mask, index_offset, hits, hit_cap,
-        counters);
+    if (tpp) {
+        const int m = mult ? mult : 4 * FR3D_TPP_MIN_BLOCKS;
+        long long want = (pair_cap + 127) / 128;
+        long long maxgrid = (long long)g_sm_count * m;
+        int grid = (int)(want < maxgrid ? want : maxgrid);
+        if (grid < 1) grid = 1;
+        fr3d::classify_pairs_tpp_kernel<<<grid, 128, 0, st>>>(*nts, boxes, box_index, pair_i, pair_j, pair_rank,
+                                                              pair_cap, category_mask, index_offset, hits, hit_cap,
+                                                              counters);
+    } else {
+        const int m = mult ? mult : FR3D_CLASSIFY_MIN_BLOCKS;          // exactly the resident CTAs: one wave
+        const long long per_block = (long long)fr3d::WARPS_PER_BLOCK * fr3d::PM_K;
+        long long want = (pair_cap + per_block - 1) / per_block;
+        long long maxgrid = (long long)g_sm_count * m;
+        int grid = (int)(want < maxgrid ? want : maxgrid);
+        if (grid < 1) grid = 1;
+        fr3d::classify_pairs_pm_kernel<<<grid, fr3d::WARPS_PER_BLOCK * 32, 0, st>>>(
+            *nts, boxes, box_index, pair_i, pair_j, pair_rank, pair_cap, category_mask, index_offset, hits, hit_cap,
+            counters);
+    }
     CUDA_TRY(cudaGetLastError());
     return FR3D_OK;
 }
