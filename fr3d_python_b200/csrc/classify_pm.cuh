@@ -62,14 +62,16 @@ __global__ void __launch_bounds__(WARPS_PER_BLOCK * 32, FR3D_CLASSIFY_MIN_BLOCKS
 classify_pairs_pm_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, const int32_t *__restrict__ box_index,
                          const int32_t *__restrict__ pair_i, const int32_t *__restrict__ pair_j,
                          const int32_t *__restrict__ pair_rank, int64_t pair_cap, uint32_t cats, int32_t index_offset,
-                         fr3d_hit_t *__restrict__ hits, int64_t hit_cap, int64_t *counters) {
+                         fr3d_hit_t *__restrict__ hits, int64_t hit_cap, int64_t *counters,
+                         const int32_t *__restrict__ worklist) {
     __shared__ PairState s_state[WARPS_PER_BLOCK][PM_K];
 
     const int lane = threadIdx.x & 31;
     PairState *W = s_state[threadIdx.x >> 5];
     const long long warp0 = (long long)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
     const long long nwarps = (long long)gridDim.x * WARPS_PER_BLOCK;
-    long long n_pairs = counters[0];
+    // with a work list (classify_screen.cuh) the kernel walks its entries instead of the whole pair list
+    long long n_pairs = worklist ? counters[5] : counters[0];
     if (n_pairs > pair_cap) n_pairs = pair_cap;
     const int half = lane >> 4;      // 0: atoms of nt2 seen from frame 1, 1: atoms of nt1 seen from frame 2
     const int a = lane & 15;
@@ -108,9 +110,10 @@ classify_pairs_pm_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, c
         // ---------------- phase 0: indices, then every record of the PM_K pairs with cp.async
         __syncwarp();
         if (lane < nk) {
-            W[lane].n1 = pair_i[p0 + lane];
-            W[lane].n2 = pair_j[p0 + lane];
-            W[lane].rank = pair_rank[p0 + lane];
+            const long long q = worklist ? (long long)worklist[p0 + lane] : p0 + lane;
+            W[lane].n1 = pair_i[q];
+            W[lane].n2 = pair_j[q];
+            W[lane].rank = pair_rank[q];
         }
         __syncwarp();
 #pragma unroll 1

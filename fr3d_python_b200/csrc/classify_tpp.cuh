@@ -420,9 +420,11 @@ __global__ void __launch_bounds__(128, FR3D_TPP_MIN_BLOCKS)
 classify_pairs_tpp_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, const int32_t *__restrict__ box_index,
                           const int32_t *__restrict__ pair_i, const int32_t *__restrict__ pair_j,
                           const int32_t *__restrict__ pair_rank, int64_t pair_cap, uint32_t cats, int32_t index_offset,
-                          fr3d_hit_t *__restrict__ hits, int64_t hit_cap, int64_t *counters) {
+                          fr3d_hit_t *__restrict__ hits, int64_t hit_cap, int64_t *counters,
+                          const int32_t *__restrict__ worklist, int do_bp) {
     const int lane = threadIdx.x & 31;
-    long long n_pairs = counters[0];
+    // with a work list (classify_screen.cuh) the kernel walks its entries instead of the whole pair list
+    long long n_pairs = worklist ? counters[4] : counters[0];
     if (n_pairs > pair_cap) n_pairs = pair_cap;
     const long long stride = (long long)gridDim.x * blockDim.x;
     // whole warps iterate together so that the emission below can use warp collectives
@@ -438,7 +440,8 @@ classify_pairs_tpp_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, 
         double bp_cd = 0.0, bp_gap = 0.0;
         int n1 = 0, n2 = 0, rank = 0;
         if (active) {
-            n1 = pair_i[p]; n2 = pair_j[p]; rank = pair_rank[p];
+            const long long q = worklist ? (long long)worklist[p] : p;
+            n1 = pair_i[q]; n2 = pair_j[q]; rank = pair_rank[q];
             const uint32_t bm1 = nts.base_mask[n1], bm2 = nts.base_mask[n2];
             const uint32_t bb1 = nts.bb_mask[n1], bb2 = nts.bb_mask[n2];
             const int par1 = (int)((bm1 >> 16) & 15u) - 1, par2 = (int)((bm2 >> 16) & 15u) - 1;
@@ -491,7 +494,7 @@ classify_pairs_tpp_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, 
                 if (((sel >> 8) & 0xFF) != 0xFF) { hmask |= 1u << FR3D_SLOT_BR; c_br = (sel >> 8) & 0xFF; }
             }
             // ---- coplanar + basepair (NA:834-1013)
-            const bool gly_ok = (bm1 & 1u) && (bm2 & 1u) && par1 >= 0 && par2 >= 0;
+            const bool gly_ok = do_bp && (bm1 & 1u) && (bm2 & 1u) && par1 >= 0 && par2 >= 0;
             unsigned ori_ok = 0, bp_live = 0;
             bool cp_frames = false;
             double gd0 = 0, gd1 = 0, gd2 = 0;

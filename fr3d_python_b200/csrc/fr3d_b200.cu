@@ -15,6 +15,7 @@
 #include "classify.cuh"
 #include "classify_pm.cuh"
 #include "classify_tpp.cuh"
+#include "classify_screen.cuh"
 #include "geometry.cuh"
 
 namespace {
@@ -114,7 +115,7 @@ int fr3d_pair_search(const fr3d_nts_t *nts, double cell_size, void *workspace, s
     if (!(cell_size > 0)) return fail(FR3D_E_ARG, "cell_size must be positive");
     if (workspace_bytes < fr3d_pair_search_workspace(nts->n_nt)) return fail(FR3D_E_ARG, "workspace too small");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    CUDA_TRY(cudaMemsetAsync(counters, 0, 4 * sizeof(int64_t), st));
+    CUDA_TRY(cudaMemsetAsync(counters, 0, 8 * sizeof(int64_t), st));
     if (nts->n_nt <= 0) return FR3D_OK;
     fr3d::SearchWs ws = carve(workspace, nts->n_nt);
     const uint32_t T = ws.table_mask + 1;
@@ -130,42 +131,60 @@ int fr3d_pair_search(const fr3d_nts_t *nts, double cell_size, void *workspace, s
     return FR3D_OK;
 }
 
+size_t fr3d_classify_workspace(int64_t pair_cap) {
+    if (pair_cap < 0) pair_cap = 0;
+    return 2 * align_up(sizeof(int32_t) * (size_t)pair_cap, 256) + 256;
+}
+
 int fr3d_classify_pairs(const fr3d_nts_t *nts, const fr3d_box_t *boxes, const int32_t *box_index,
                         const int32_t *pair_i, const int32_t *pair_j, const int32_t *pair_rank, int64_t pair_cap,
-                        uint32_t category_mask, int32_t index_offset, fr3d_hit_t *hits, int64_t hit_cap, int64_t *counters,
-                        void *stream) {
+                        uint32_t category_mask, int32_t index_offset, void *workspace, size_t workspace_bytes,
+                        fr3d_hit_t *hits, int64_t hit_cap, int64_t *counters, void *stream) {
     if (!nts || !boxes || !box_index || !pair_i || !pair_j || !pair_rank || !hits || !counters)
         return fail(FR3D_E_ARG, "NULL argument");
     if (!g_tables_loaded) return fail(FR3D_E_NOTABLES, "fr3d_upload_tables not called");
     if (pair_cap <= 0) return FR3D_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    // persistent warps: grid is a multiple of the SM count; n_pairs is read on the device
-    static int mult = -1, tpp = -1;             // tuning knobs: CTAs per SM, thread-per-pair kernel on/off
+    // Tuning knobs (environment): FR3D_CLASSIFY_MODE 2 = screen + two work-list kernels (default when a
+    // workspace is given), 1 = thread-per-pair kernel over all pairs, 0 = warp-per-pair kernel over all pairs.
+    static int mult = -1, mode = -1;
     if (mult < 0) {
         const char *e = getenv("FR3D_CLASSIFY_GRID_MULT");
         mult = (e && atoi(e) > 0) ? atoi(e) : 0;
-        const char *t = getenv("FR3D_CLASSIFY_TPP");
-        tpp = t ? atoi(t) : 1;
+        const char *m = getenv("FR3D_CLASSIFY_MODE");
+        mode = m ? atoi(m) : 2;
     }
-    if (tpp) {
-        const int m = mult ? mult : 4 * FR3D_TPP_MIN_BLOCKS;
-        long long want = (pair_cap + 127) / 128;
-        long long maxgrid = (long long)g_sm_count * m;
-        int grid = (int)(want < maxgrid ? want : maxgrid);
-        if (grid < 1) grid = 1;
-        fr3d::classify_pairs_tpp_kernel<<<grid, 128, 0, st>>>(*nts, boxes, box_index, pair_i, pair_j, pair_rank,
-                                                              pair_cap, category_mask, index_offset, hits, hit_cap,
-                                                              counters);
-    } else {
-        const int m = mult ? mult : FR3D_CLASSIFY_MIN_BLOCKS;          // exactly the resident CTAs: one wave
-        const long long per_block = (long long)fr3d::WARPS_PER_BLOCK * fr3d::PM_K;
-        long long want = (pair_cap + per_block - 1) / per_block;
-        long long maxgrid = (long long)g_sm_count * m;
-        int grid = (int)(want < maxgrid ? want : maxgrid);
-        if (grid < 1) grid = 1;
-        fr3d::classify_pairs_pm_kernel<<<grid, fr3d::WARPS_PER_BLOCK * 32, 0, st>>>(
+    int use_mode = mode;
+    if (use_mode == 2 && (!workspace || workspace_bytes < fr3d_classify_workspace(pair_cap))) use_mode = 0;
+    const long long tpp_grid_max = (long long)g_sm_count * (mult ? mult : 4 * FR3D_TPP_MIN_BLOCKS);
+    const long long pm_grid_max = (long long)g_sm_count * (mult ? mult : FR3D_CLASSIFY_MIN_BLOCKS);
+    const long long per_block = (long long)fr3d::WARPS_PER_BLOCK * fr3d::PM_K;
+    auto clampg = [](long long want, long long mx) { long long g = want < mx ? want : mx; return (int)(g < 1 ? 1 : g); };
+    if (use_mode == 2) {
+        int32_t *wl_detail = static_cast<int32_t *>(workspace);
+        int32_t *wl_geom = reinterpret_cast<int32_t *>(static_cast<char *>(workspace) +
+                                                       align_up(sizeof(int32_t) * (size_t)pair_cap, 256));
+        CUDA_TRY(cudaMemsetAsync(counters + 4, 0, 2 * sizeof(int64_t), st));
+        fr3d::classify_screen_kernel<<<clampg((pair_cap + 127) / 128, (long long)g_sm_count * 16), 128, 0, st>>>(
+            *nts, boxes, box_index, pair_i, pair_j, pair_cap, category_mask, wl_detail, wl_geom, counters);
+        const uint32_t detail_cats = category_mask & (FR3D_CAT_SO | FR3D_CAT_SUGAR_RIBOSE | FR3D_CAT_BACKBONE);
+        if (detail_cats)
+            fr3d::classify_pairs_tpp_kernel<<<clampg((pair_cap + 127) / 128, tpp_grid_max), 128, 0, st>>>(
+                *nts, boxes, box_index, pair_i, pair_j, pair_rank, pair_cap, detail_cats, index_offset, hits, hit_cap,
+                counters, wl_detail, 0);
+        fr3d::classify_pairs_pm_kernel<<<clampg((pair_cap + per_block - 1) / per_block, pm_grid_max),
+                                         fr3d::WARPS_PER_BLOCK * 32, 0, st>>>(
+            *nts, boxes, box_index, pair_i, pair_j, pair_rank, pair_cap,
+            category_mask & (FR3D_CAT_STACKING | FR3D_CAT_COPLANAR), index_offset, hits, hit_cap, counters, wl_geom);
+    } else if (use_mode == 1) {
+        fr3d::classify_pairs_tpp_kernel<<<clampg((pair_cap + 127) / 128, tpp_grid_max), 128, 0, st>>>(
             *nts, boxes, box_index, pair_i, pair_j, pair_rank, pair_cap, category_mask, index_offset, hits, hit_cap,
-            counters);
+            counters, nullptr, 1);
+    } else {
+        fr3d::classify_pairs_pm_kernel<<<clampg((pair_cap + per_block - 1) / per_block, pm_grid_max),
+                                         fr3d::WARPS_PER_BLOCK * 32, 0, st>>>(
+            *nts, boxes, box_index, pair_i, pair_j, pair_rank, pair_cap, category_mask, index_offset, hits, hit_cap,
+            counters, nullptr);
     }
     CUDA_TRY(cudaGetLastError());
     return FR3D_OK;

@@ -189,7 +189,9 @@ class Engine(object):
         p.pair_i = torch.empty(p.pair_cap, dtype=torch.int32, device=dev)
         p.pair_j = torch.empty(p.pair_cap, dtype=torch.int32, device=dev)
         p.pair_rank = torch.empty(p.pair_cap, dtype=torch.int32, device=dev)
-        p.counters = torch.zeros(4, dtype=torch.int64, device=dev)
+        p.counters = torch.zeros(8, dtype=torch.int64, device=dev)
+        p.cws_bytes = int(self.lib.fr3d_classify_workspace(p.pair_cap))
+        p.cws = torch.empty(p.cws_bytes, dtype=torch.uint8, device=dev)
         p.hits = torch.empty(p.hit_cap * HIT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
         p.status = torch.empty(max(n_nt, 1), dtype=torch.int32, device=dev)
         return p
@@ -217,10 +219,10 @@ class Engine(object):
             _lib.check(self.lib.fr3d_classify_pairs(C.byref(dbatch.nts), bx.data_ptr(), ix.data_ptr(),
                                                     plan.pair_i.data_ptr(), plan.pair_j.data_ptr(),
                                                     plan.pair_rank.data_ptr(), plan.pair_cap, int(category_mask),
-                                                    int(index_offset), plan.hits.data_ptr(), plan.hit_cap,
-                                                    plan.counters.data_ptr(), st),
+                                                    int(index_offset), plan.cws.data_ptr(), plan.cws_bytes,
+                                                    plan.hits.data_ptr(), plan.hit_cap, plan.counters.data_ptr(), st),
                        "fr3d_classify_pairs")
-            self.launches += 1
+            self.launches += 4          # work-list memset + screen + detail + geometry kernels
             if events is not None:
                 events["classify1"].record()
 
@@ -305,7 +307,7 @@ class Pipeline(object):
             pc = int((pair_cap or (12 * batch.n + 1024)) * frac * 1.15) + 4096
             hc = int((hit_cap or (12 * batch.n + 1024)) * frac * 1.15) + 4096
             ch.plan = engine.make_plan(n, pc, hc)
-            ch.counters_host = torch.zeros(4, dtype=torch.int64).pin_memory()
+            ch.counters_host = torch.zeros(8, dtype=torch.int64).pin_memory()
             ch.ev = torch.cuda.Event()
             self.chunks.append(ch)
         total_hc = sum(ch.plan.hit_cap for ch in self.chunks)

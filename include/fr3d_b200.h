@@ -151,8 +151,9 @@ int fr3d_frames_fit(const fr3d_nts_t *nts, int32_t *status, int place_h, void *s
 
 /* K2+K3. Replaces make_nt_cubes_half (NA:410-443) and the loop/screens of
  * annotate_nt_nt_interactions (NA:661-724): oriented candidate pairs with 2 <= d <= 12.
- * counters (device int64[4]): [0] n_pairs (may exceed cap: FR3D_E_CAPACITY is NOT raised here,
- * the caller compares after its sync), [1] n_hits, [2] error flags, [3] n_cells. */
+ * counters (device int64[8]): [0] n_pairs (may exceed cap: FR3D_E_CAPACITY is NOT raised here,
+ * the caller compares after its sync), [1] n_hits, [2] error flags, [3] n_cells, [4] [5] work-list sizes of
+ * fr3d_classify_pairs, [6] [7] reserved. */
 size_t fr3d_pair_search_workspace(int32_t n_nt);
 int fr3d_pair_search(const fr3d_nts_t *nts, double cell_size, void *workspace, size_t workspace_bytes,
                      int32_t *pair_i, int32_t *pair_j, int32_t *pair_rank, int64_t pair_cap,
@@ -164,11 +165,16 @@ int fr3d_pair_search(const fr3d_nts_t *nts, double cell_size, void *workspace, s
  * one warp per candidate pair, hits compacted with a warp ballot.
  * n_pairs is read from counters[0] on the device (clamped to pair_cap).  index_offset is added to the
  * nt indices (and 16 x to the rank) written into the hit records, so that chunks of a larger batch
- * produce globally indexed hits. */
+ * produce globally indexed hits.  workspace (fr3d_classify_workspace(pair_cap) bytes, may be NULL): work lists
+ * of the screen kernel; with it the call is three launches: a thread-per-pair screen of the cheap necessary
+ * conditions, a thread-per-pair kernel for sO / sugar-ribose / BPh / BR on the pairs that passed, and the
+ * warp-per-pair kernel for stacking / coplanar / basepair on the pairs that passed; without it one
+ * warp-per-pair launch over all pairs. */
+size_t fr3d_classify_workspace(int64_t pair_cap);
 int fr3d_classify_pairs(const fr3d_nts_t *nts, const fr3d_box_t *boxes, const int32_t *box_index /*[25][2][2]*/,
                         const int32_t *pair_i, const int32_t *pair_j, const int32_t *pair_rank,
-                        int64_t pair_cap, uint32_t category_mask, int32_t index_offset, fr3d_hit_t *hits,
-                        int64_t hit_cap, int64_t *counters, void *stream);
+                        int64_t pair_cap, uint32_t category_mask, int32_t index_offset, void *workspace,
+                        size_t workspace_bytes, fr3d_hit_t *hits, int64_t hit_cap, int64_t *counters, void *stream);
 
 /* K5. Replaces besttransformation / besttransformation_weighted
  * (fr3d/geometry/superpositions.py:10-121) for n_prob independent problems.

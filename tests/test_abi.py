@@ -105,3 +105,18 @@ def test_rings_and_ellipses_lie_inside_the_prefilter_disc():
             if e:
                 assert not in_ell(e, cx, cy).any(), parent
                 assert in_ell(e, np.array([e[2]]), np.array([e[3]])).all()
+
+
+def test_hulls_lie_inside_the_screen_disc():
+    """csrc/classify_screen.cuh tests the hull half planes only for atoms with x^2 + y^2 < 16: every convex
+    hull of check_convex_hull_atoms (NA:1485-1523) must lie strictly inside that disc."""
+    ang = np.linspace(0, 2 * np.pi, 7200, endpoint=False)
+    cx, cy = 4.0 * np.cos(ang), 4.0 * np.sin(ang)
+    for parent in defs.PARENTS:
+        ok = np.ones_like(cx, dtype=bool)
+        inside0 = True
+        for a, b, c in defs.PLANES["hull"][parent]:
+            ok &= a * cx + b * cy + c > 0
+            inside0 = inside0 and c > 0
+        assert not ok.any(), parent
+        assert inside0, parent                      # the base centre is inside the hull
