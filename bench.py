@@ -244,6 +244,7 @@ def main():
     gpu_launches = eng.launches - launches0
     ms_total = e0.elapsed_time(e1)
     np_chk, nh_chk = eng.read_counts(plan)
+    wl = plan.counters.cpu().tolist()
     assert np_chk == n_pairs and nh_chk == n_hits, "resident pass disagrees with the calibration pass"
     classify_ms = float(np.mean([ev["classify0"].elapsed_time(ev["classify1"]) for ev in evs]))
     search_ms = float(np.mean([ev["search0"].elapsed_time(ev["classify0"]) for ev in evs]))
@@ -301,6 +302,8 @@ def main():
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, S),
                 "structures_per_s": S * world * args.steps / (ms_total / 1000.0),
                 "pairs_per_step": pairs_all, "hits_per_step": hits_all,
+                "worklists_rank0": {"detail_pairs": int(wl[4]), "geometry_pairs": int(wl[5]),
+                                    "flagged_stacking": int(wl[6]), "flagged_basepair_box": int(wl[7])},
                 "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "structures_per_s": S * world * args.steps / t_e2e, "ms_per_step": 1000.0 * t_e2e / args.steps,
                         "what": "engine.Pipeline.run: pinned host nt records -> H2D -> K1..K4 -> D2H hit records, "

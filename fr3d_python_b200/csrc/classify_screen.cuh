@@ -13,6 +13,7 @@
 // unchanged; tests/test_gpu_parity.py compares complete annotation sets with the reference.
 #pragma once
 
+#include "classify_pm.cuh"
 #include "classify_tpp.cuh"
 
 namespace fr3d {
@@ -27,50 +28,112 @@ namespace fr3d {
 #define SCR_DETAIL (SCR_SO12 | SCR_SO21 | SCR_SR | SCR_BPH)
 #define SCR_GEOM (SCR_STACK | SCR_CP | SCR_BP)
 
-// any base atom of nt_b inside the hull prism of nt_a?  (check_convex_hull_atoms, NA:1475-1528; every hull
-// lies inside the disc x^2 + y^2 < 16, tests/test_abi.py)
-__device__ __forceinline__ bool s_any_inside(const fr3d_nts_t &nts, const TFrame &fa, int par_a, int nb, uint32_t bmb) {
-    const double *q = nts.base_xyz + (size_t)nb * FR3D_BASE_SLOTS * 3;
-    bool any = false;
-#pragma unroll 4
+// Shared-memory row of one nt2 record (doubles): centre 0..2, rotation 3..11, base atoms 12..59, backbone slots
+// 1..6 (OP1 OP2 O5' O4' O3' O2') 60..77, backbone slot 9 (previous O3') 78..80.  The stride is odd so that "lane k
+// reads its own row" is bank-conflict free for 64-bit accesses.
+constexpr int SCR_ROW = 81;
+constexpr int SCR_STRIDE = 81;
+#define SCR_BB_OFF(slot) ((slot) == 9 ? 78 : 57 + (slot) * 3)
+constexpr int SCR_WARPS = 4;
+constexpr int SCR_UBOX = FR3D_N_PARENTS * FR3D_N_PARENTS * 2;      // (combo, sign of nZ) entries
+constexpr int SCR_MAX_BOXES = 256;                                 // cutoff boxes kept in shared memory (else global)
+constexpr int SCR_BOX_STRIDE = 9;                                  // odd: lane b reads box b without bank conflicts
+constexpr int SCR_HULL = FR3D_N_PARENTS * 7 * 3;
+constexpr int SCR_FIXED = SCR_UBOX * 8 + SCR_MAX_BOXES * SCR_BOX_STRIDE + SCR_HULL + SCR_UBOX;   // doubles
+constexpr size_t SCR_SMEM = sizeof(double) * (SCR_FIXED + SCR_WARPS * 32 * SCR_STRIDE);
+
+// which atoms (bit per slot) of the 16 points q[0..47] lie in the cylinder |z| < 4.5, x^2 + y^2 < 16 of frame fa
+// (every hull lies inside that disc, tests/test_abi.py); converged, branch free
+__device__ __forceinline__ unsigned s_cylinder_mask(const TFrame &fa, const double *q) {
+    unsigned cand = 0;
+#pragma unroll
     for (int a = 0; a < FR3D_BASE_SLOTS; ++a) {
         const double v0 = q[a * 3] - fa.c0, v1 = q[a * 3 + 1] - fa.c1, v2 = q[a * 3 + 2] - fa.c2;
         const double z = v0 * fa.u2 + v1 * fa.u5 + v2 * fa.u8;
-        const double x = v0 * fa.u0 + v1 * fa.u3 + v2 * fa.u6;
-        const double y = v0 * fa.u1 + v1 * fa.u4 + v2 * fa.u7;
-        if (((bmb >> a) & 1u) && fabs(z) < 4.5 && (x * x + y * y) < 16.0) {
-            bool in = true;
+        const double r2 = (v0 * v0 + v1 * v1 + v2 * v2) - z * z;        // x^2 + y^2 (U is orthonormal)
+        if (fabs(z) < 4.5 && r2 < 16.0 + 1e-9) cand |= 1u << a;
+    }
+    return cand;
+}
+
+// any of the candidate atoms inside the hull prism of fa's base?  (check_convex_hull_atoms, NA:1475-1528)
+__device__ __forceinline__ bool s_hull_any(const TFrame &fa, const double *hull, const double *q, unsigned cand) {
+    bool any = false;
+    while (cand && !any) {
+        const int a = __ffs(cand) - 1;
+        cand &= cand - 1;
+        double x, y, z;
+        tproject(fa, q[a * 3], q[a * 3 + 1], q[a * 3 + 2], x, y, z);
+        bool in = fabs(z) < 4.5;
 #pragma unroll
-            for (int k = 0; k < 7; ++k) in = in && left_of(c_tab.hull[par_a][k], x, y);
-            any = any || in;
-        }
+        for (int k = 0; k < 7; ++k) in = in && left_of(hull + k * 3, x, y);
+        any = in;
     }
     return any;
 }
 
-// any backbone oxygen of nt_b inside the slab / disc that contains every ring of nt_a's base?
-__device__ __forceinline__ bool s_so_possible(const fr3d_nts_t &nts, const TFrame &fa, int pa, int nb, uint32_t bbb) {
+// any backbone oxygen (slots 1..6 of the row B) inside the slab / disc that contains every ring of fa's base?
+__device__ __forceinline__ bool s_so_possible(const TFrame &fa, int pa, const double *B, uint32_t bbb) {
     if (pa < 0 || pa >= FR3D_N_PARENTS) return false;
-    const double *B = nts.bb_xyz + (size_t)nb * FR3D_BB_SLOTS * 3;
     bool any = false;
 #pragma unroll
-    for (int o = 0; o < 6; ++o) {
-        const int oslot = (0x213456 >> (4 * o)) & 7;
+    for (int oslot = 1; oslot <= 6; ++oslot) {
         const double v0 = B[oslot * 3] - fa.c0, v1 = B[oslot * 3 + 1] - fa.c1, v2 = B[oslot * 3 + 2] - fa.c2;
         const double z = v0 * fa.u2 + v1 * fa.u5 + v2 * fa.u8;
-        const double x = v0 * fa.u0 + v1 * fa.u3 + v2 * fa.u6;
-        const double y = v0 * fa.u1 + v1 * fa.u4 + v2 * fa.u7;
-        any = any || (((bbb >> oslot) & 1u) && fabs(z) < 3.6 && (x * x + y * y) < 25.0);
+        const double r2 = (v0 * v0 + v1 * v1 + v2 * v2) - z * z;
+        any = any || (((bbb >> oslot) & 1u) && fabs(z) < 3.6 && r2 < 25.0 + 1e-9);
     }
     return any;
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(SCR_WARPS * 32)
 classify_screen_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, const int32_t *__restrict__ box_index,
                        const int32_t *__restrict__ pair_i, const int32_t *__restrict__ pair_j, int64_t pair_cap,
                        uint32_t cats, int32_t *__restrict__ wl_detail, int32_t *__restrict__ wl_geom,
                        int64_t *counters) {
-    const int lane = threadIdx.x & 31;
+    extern __shared__ double scr_smem[];
+    double *ubox = scr_smem;                                                  // [SCR_UBOX][8] union boxes
+    double *sbox = ubox + SCR_UBOX * 8;                                       // [SCR_MAX_BOXES][SCR_BOX_STRIDE]
+    double *shull = sbox + SCR_MAX_BOXES * SCR_BOX_STRIDE;                    // [parents][7][3]
+    int *sidx = reinterpret_cast<int *>(shull + SCR_HULL);                    // [SCR_UBOX][2] start, count
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double *rows = scr_smem + SCR_FIXED + warp * 32 * SCR_STRIDE;
+    __shared__ int s_nboxes;
+    if (threadIdx.x == 0) s_nboxes = 0;
+    __syncthreads();
+    // prologue: the union of the cutoff boxes of every (combination, sign) entry.  A pair whose L1 excess over the
+    // union box already reaches 1 cannot come within 1 of any single box (each box's excess is at least the union's).
+    for (int item = threadIdx.x; item < SCR_UBOX * 8; item += blockDim.x) {
+        const int e = item >> 3, q = item & 7;
+        const int bstart = box_index[e * 2], bcount = box_index[e * 2 + 1];
+        const bool is_min = !(q & 1);
+        double acc = is_min ? 1e300 : -1e300;
+        for (int b = 0; b < bcount; ++b) {
+            const double v = reinterpret_cast<const double *>(boxes + bstart + b)[q];
+            acc = is_min ? fmin(acc, v) : fmax(acc, v);
+        }
+        ubox[item] = acc;
+        if (q == 0) { sidx[e * 2] = bstart; sidx[e * 2 + 1] = bcount; if (bcount > 0) atomicMax(&s_nboxes, bstart + bcount); }
+    }
+    for (int item = threadIdx.x; item < SCR_HULL; item += blockDim.x) shull[item] = (&c_tab.hull[0][0][0])[item];
+    __syncthreads();
+    const bool boxes_in_smem = s_nboxes <= SCR_MAX_BOXES;
+    if (boxes_in_smem)
+        for (int item = threadIdx.x; item < s_nboxes * 8; item += blockDim.x)
+            sbox[(item >> 3) * SCR_BOX_STRIDE + (item & 7)] = reinterpret_cast<const double *>(boxes + (item >> 3))[item & 7];
+    __syncthreads();
+    // per-lane sources of the three copies that move one 90-double row
+    const double *src[3];
+    int mult[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const int t = j * 32 + lane;
+        if (t < 3) { src[j] = nts.center + t; mult[j] = 3; }
+        else if (t < 12) { src[j] = nts.rot + (t - 3); mult[j] = 9; }
+        else if (t < 60) { src[j] = nts.base_xyz + (t - 12); mult[j] = FR3D_BASE_SLOTS * 3; }
+        else if (t < 78) { src[j] = nts.bb_xyz + (t - 60 + 3); mult[j] = FR3D_BB_SLOTS * 3; }
+        else { src[j] = nts.bb_xyz + (t - 78 + 27); mult[j] = FR3D_BB_SLOTS * 3; }
+    }
     long long n_pairs = counters[0];
     if (n_pairs > pair_cap) n_pairs = pair_cap;
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -79,33 +142,75 @@ classify_screen_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, con
 #pragma unroll 1
     for (long long r = 0; r < rounds; ++r) {
         const long long p = first + r * stride;
-        unsigned fl = 0;
-        if (p < n_pairs) {
-            const int n1 = pair_i[p], n2 = pair_j[p];
-            const uint32_t bm1 = nts.base_mask[n1], bm2 = nts.base_mask[n2];
-            const uint32_t bb1 = nts.bb_mask[n1], bb2 = nts.bb_mask[n2];
-            const int par1 = (int)((bm1 >> 16) & 15u) - 1, par2 = (int)((bm2 >> 16) & 15u) - 1;
-            const TFrame f1 = load_tframe(nts, n1), f2 = load_tframe(nts, n2);
+        const bool valid = p < n_pairs;
+        if (!__any_sync(FULL, valid)) continue;
+        const int n1 = valid ? pair_i[p] : 0, n2 = valid ? pair_j[p] : 0;
+        // stage the 32 nt2 records with coalesced asynchronous copies: row k belongs to lane k
+        __syncwarp();
+#pragma unroll 4
+        for (int k = 0; k < 32; ++k) {
+            const int nb = __shfl_sync(FULL, n2, k);
+            double *dst = rows + k * SCR_STRIDE + lane;
+            cp_async8(dst, src[0] + (size_t)nb * mult[0]);
+            cp_async8(dst + 32, src[1] + (size_t)nb * mult[1]);
+            if (lane < SCR_ROW - 64) cp_async8(dst + 64, src[2] + (size_t)nb * mult[2]);
+        }
+        unsigned fl = 0, live = 0;
+        double dX0 = 0, dY0 = 0, dZ0 = 0, dX1 = 0, dY1 = 0, dZ1 = 0, nZ = 0;
+        int entry0 = 0, entry1 = 0;
+        const uint32_t bm1 = nts.base_mask[n1], bm2 = nts.base_mask[n2];
+        const uint32_t bb1 = nts.bb_mask[n1], bb2 = nts.bb_mask[n2];
+        const int par1 = (int)((bm1 >> 16) & 15u) - 1, par2 = (int)((bm2 >> 16) & 15u) - 1;
+        const TFrame f1 = load_tframe(nts, n1);
+        const double *A_base = nts.base_xyz + (size_t)n1 * FR3D_BASE_SLOTS * 3;     // nt1: mostly warp-uniform addresses
+        const double *A_bb = nts.bb_xyz + (size_t)n1 * FR3D_BB_SLOTS * 3;
+        cp_async_wait_all();
+        __syncwarp();
+        if (valid) {
+            const double *R = rows + lane * SCR_STRIDE;
+            const double *B_base = R + 12, *B_bb = R + 57;      // B_bb[slot * 3 + c] for slots 1..6
+            TFrame f2;
+            f2.c0 = R[0]; f2.c1 = R[1]; f2.c2 = R[2];
+            f2.u0 = R[3]; f2.u1 = R[4]; f2.u2 = R[5]; f2.u3 = R[6]; f2.u4 = R[7]; f2.u5 = R[8];
+            f2.u6 = R[9]; f2.u7 = R[10]; f2.u8 = R[11];
             if (cats & FR3D_CAT_SO) {
-                if (s_so_possible(nts, f1, par1, n2, bb2)) fl |= SCR_SO12;
-                if (s_so_possible(nts, f2, par2, n1, bb1)) fl |= SCR_SO21;
+                if (s_so_possible(f1, par1, B_bb, bb2)) fl |= SCR_SO12;
+                if (s_so_possible(f2, par2, A_bb, bb1)) fl |= SCR_SO21;
             }
             if ((cats & FR3D_CAT_STACKING) && par1 >= 0 && par2 >= 0) {
-                if (s_any_inside(nts, f1, par1, n2, bm2) || s_any_inside(nts, f2, par2, n1, bm1)) fl |= SCR_STACK;
+                const unsigned c12 = s_cylinder_mask(f1, B_base) & bm2;
+                const unsigned c21 = s_cylinder_mask(f2, A_base) & bm1;
+                if (s_hull_any(f1, shull + par1 * 21, B_base, c12) || s_hull_any(f2, shull + par2 * 21, A_base, c21)) fl |= SCR_STACK;
             }
             if ((cats & FR3D_CAT_SUGAR_RIBOSE) && par1 >= 0 && par2 >= 0 && par1 != 4 && par2 != 4 &&
                 (bb1 >> 6 & 1u) && (bb2 >> 6 & 1u)) {
-                const double *A = nts.bb_xyz + (size_t)n1 * FR3D_BB_SLOTS * 3;
-                const double *B = nts.bb_xyz + (size_t)n2 * FR3D_BB_SLOTS * 3;
-                const double o0 = A[18] - B[18], o1 = A[19] - B[19], o2 = A[20] - B[20];
+                const double o0 = A_bb[18] - B_bb[18], o1 = A_bb[19] - B_bb[19], o2 = A_bb[20] - B_bb[20];
                 if (o0 * o0 + o1 * o1 + o2 * o2 < 14.4401) fl |= SCR_SR;
             }
-            if ((cats & FR3D_CAT_BACKBONE) && par1 >= 0 && t_backbone_possible(nts, par1, n1, n2, bm1, bb2)) fl |= SCR_BPH;
+            if ((cats & FR3D_CAT_BACKBONE) && par1 >= 0) {
+                // some massive atom of a base-phosphate site of nt1 within 4.5 A of a backbone oxygen of nt2
+                const int nsites = c_tab.n_sites[par1];
+                bool any = false;
+#pragma unroll 1
+                for (int s = 0; s < nsites; ++s) {
+                    const int ms = c_tab.site_m[par1][s];
+                    if (!((bm1 >> ms) & 1u)) continue;
+                    const double m0 = A_base[ms * 3], m1 = A_base[ms * 3 + 1], m2 = A_base[ms * 3 + 2];
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) {
+                        const int oslot = (0x469213 >> (4 * i)) & 15;
+                        const double *O = R + SCR_BB_OFF(oslot);
+                        const double q0 = m0 - O[0], q1 = m1 - O[1], q2 = m2 - O[2];
+                        if (((bb2 >> oslot) & 1u) && (q0 * q0 + q1 * q1 + q2 * q2 < 20.2501)) any = true;
+                    }
+                }
+                if (any) fl |= SCR_BPH;
+            }
             if ((bm1 & 1u) && (bm2 & 1u) && par1 >= 0 && par2 >= 0) {
                 unsigned ori_ok = 0;
                 if (c_tab.combo_ok[par1 * FR3D_N_PARENTS + par2]) ori_ok |= 1u;
                 if (c_tab.combo_ok[par2 * FR3D_N_PARENTS + par1]) ori_ok |= 2u;
-                const double nZ = f1.u2 * f2.u2 + f1.u5 * f2.u5 + f1.u8 * f2.u8;
+                nZ = f1.u2 * f2.u2 + f1.u5 * f2.u5 + f1.u8 * f2.u8;
                 if ((cats & FR3D_CAT_COPLANAR) && ori_ok && fabs(nZ) > 0.7757) {
                     const double e0 = f1.c0 - f2.c0, e1 = f1.c1 - f2.c1, e2 = f1.c2 - f2.c2;
                     const double lim = (0.3381 * 0.3381) * (e0 * e0 + e1 * e1 + e2 * e2);
@@ -113,42 +218,64 @@ classify_screen_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, con
                     const double d2 = e0 * f2.u2 + e1 * f2.u5 + e2 * f2.u8;
                     if (d1 * d1 < lim && d2 * d2 < lim) fl |= SCR_CP;
                 }
-                const double *g1 = nts.base_xyz + (size_t)n1 * FR3D_BASE_SLOTS * 3;
-                const double *g2 = nts.base_xyz + (size_t)n2 * FR3D_BASE_SLOTS * 3;
-                const double gd0 = g2[0] - g1[0], gd1 = g2[1] - g1[1], gd2 = g2[2] - g1[2];
-#pragma unroll 1
+                const double gd0 = B_base[0] - A_base[0], gd1 = B_base[1] - A_base[1], gd2 = B_base[2] - A_base[2];
+                const int sg = nZ > 0 ? 0 : 1;
+                // stage 1, converged: displacement of each live orientation against the union box of its entry
+                entry0 = (par1 * FR3D_N_PARENTS + par2) * 2 + sg;
+                entry1 = (par2 * FR3D_N_PARENTS + par1) * 2 + sg;
+#pragma unroll
                 for (int ori = 0; ori < 2; ++ori) {
-                    if (!((ori_ok >> ori) & 1u) || (fl & SCR_BP)) continue;
                     const TFrame &fa = ori ? f2 : f1;
-                    const TFrame &fb = ori ? f1 : f2;
                     const double s = ori ? -1.0 : 1.0;
                     const double v0 = s * gd0, v1 = s * gd1, v2 = s * gd2;
                     const double dZ = v0 * fa.u2 + v1 * fa.u5 + v2 * fa.u8;
-                    if (fabs(dZ) > 3.6) continue;                                  // NA:2380
                     const double dX = v0 * fa.u0 + v1 * fa.u3 + v2 * fa.u6;
                     const double dY = v0 * fa.u1 + v1 * fa.u4 + v2 * fa.u7;
-                    const int combo = ori ? par2 * FR3D_N_PARENTS + par1 : par1 * FR3D_N_PARENTS + par2;
-                    const int sg = nZ > 0 ? 0 : 1;
-                    const int bstart = box_index[(combo * 2 + sg) * 2 + 0];
-                    const int bcount = box_index[(combo * 2 + sg) * 2 + 1];
-                    // some box within 1.0 before the angle term (NA:2546-2581); the angle and gap terms only add
-                    bool any = false;
-#pragma unroll 1
-                    for (int b = 0; b < bcount && !any; ++b) {
-                        const fr3d_box_t *bx = boxes + bstart + b;
-                        double cd = fmax(0.0, bx->xmin - dX) + fmax(0.0, dX - bx->xmax) + fmax(0.0, bx->ymin - dY) +
-                                    fmax(0.0, dY - bx->ymax) + fmax(0.0, bx->zmin - dZ) + fmax(0.0, dZ - bx->zmax) +
-                                    3.0 * (fmax(0.0, bx->normalmin - nZ) + fmax(0.0, nZ - bx->normalmax));
-                        any = cd < 1.0 + 1e-9;         // summation order differs from the reference's: keep a margin
-                    }
-                    if (any) fl |= SCR_BP;
-                    (void)fb;
+                    if (ori) { dX1 = dX; dY1 = dY; dZ1 = dZ; } else { dX0 = dX; dY0 = dY; dZ0 = dZ; }
+                    const double *ub = ubox + (ori ? entry1 : entry0) * 8;
+                    const double cd = fmax(0.0, ub[0] - dX) + fmax(0.0, dX - ub[1]) + fmax(0.0, ub[2] - dY) +
+                                      fmax(0.0, dY - ub[3]) + fmax(0.0, ub[4] - dZ) + fmax(0.0, dZ - ub[5]) +
+                                      3.0 * (fmax(0.0, ub[6] - nZ) + fmax(0.0, nZ - ub[7]));
+                    if (((ori_ok >> ori) & 1u) && !(fabs(dZ) > 3.6) && cd < 1.0 + 1e-9) live |= 1u << ori;   // NA:2380
                 }
             }
+        }
+        // stage 2, warp cooperative: lane b evaluates box b of the entry of one live (pair, orientation) per step:
+        // some box within 1.0 before the angle term (NA:2546-2581)?  The angle and gap terms only add.
+        unsigned pending = __ballot_sync(FULL, live != 0);
+        while (pending) {
+            const int srcl = __ffs(pending) - 1;
+            const bool first_ori = live & 1u;
+            const double tX = __shfl_sync(FULL, first_ori ? dX0 : dX1, srcl);
+            const double tY = __shfl_sync(FULL, first_ori ? dY0 : dY1, srcl);
+            const double tZ = __shfl_sync(FULL, first_ori ? dZ0 : dZ1, srcl);
+            const double tN = __shfl_sync(FULL, nZ, srcl);
+            const int te = __shfl_sync(FULL, first_ori ? entry0 : entry1, srcl);
+            const int bstart = sidx[te * 2], bcount = sidx[te * 2 + 1];
+            bool hit = false;
+            if (lane < bcount) {
+                const double *bx = boxes_in_smem ? sbox + (bstart + lane) * SCR_BOX_STRIDE
+                                                 : reinterpret_cast<const double *>(boxes + bstart + lane);
+                const double cd = fmax(0.0, bx[0] - tX) + fmax(0.0, tX - bx[1]) + fmax(0.0, bx[2] - tY) +
+                                  fmax(0.0, tY - bx[3]) + fmax(0.0, bx[4] - tZ) + fmax(0.0, tZ - bx[5]) +
+                                  3.0 * (fmax(0.0, bx[6] - tN) + fmax(0.0, tN - bx[7]));
+                hit = cd < 1.0 + 1e-9;             // summation order differs from the reference's: keep a margin
+            }
+            const bool any = __any_sync(FULL, hit);
+            if (lane == srcl) {
+                if (any) { fl |= SCR_BP; live = 0; }
+                else live &= live - 1;
+            }
+            pending = __ballot_sync(FULL, live != 0);
         }
         // warp-aggregated appends to the two work lists
         const unsigned bd = __ballot_sync(FULL, (fl & SCR_DETAIL) != 0);
         const unsigned bg = __ballot_sync(FULL, (fl & SCR_GEOM) != 0);
+        // diagnostics (bench.py reports them): pairs flagged for stacking / for a live basepair box
+        const unsigned bs_ = __ballot_sync(FULL, (fl & SCR_STACK) != 0);
+        const unsigned bb_ = __ballot_sync(FULL, (fl & SCR_BP) != 0);
+        if (lane == 0 && bs_) atomicAdd((unsigned long long *)&counters[6], (unsigned long long)__popc(bs_));
+        if (lane == 0 && bb_) atomicAdd((unsigned long long *)&counters[7], (unsigned long long)__popc(bb_));
         if (bd) {
             long long base = 0;
             if (lane == 0) base = (long long)atomicAdd((unsigned long long *)&counters[4], (unsigned long long)__popc(bd));

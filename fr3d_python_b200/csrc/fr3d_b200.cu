@@ -164,8 +164,13 @@ int fr3d_classify_pairs(const fr3d_nts_t *nts, const fr3d_box_t *boxes, const in
         int32_t *wl_detail = static_cast<int32_t *>(workspace);
         int32_t *wl_geom = reinterpret_cast<int32_t *>(static_cast<char *>(workspace) +
                                                        align_up(sizeof(int32_t) * (size_t)pair_cap, 256));
-        CUDA_TRY(cudaMemsetAsync(counters + 4, 0, 2 * sizeof(int64_t), st));
-        fr3d::classify_screen_kernel<<<clampg((pair_cap + 127) / 128, (long long)g_sm_count * 16), 128, 0, st>>>(
+        CUDA_TRY(cudaMemsetAsync(counters + 4, 0, 4 * sizeof(int64_t), st));
+        CUDA_TRY(cudaFuncSetAttribute(fr3d::classify_screen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)fr3d::SCR_SMEM));
+        const int scr_threads = fr3d::SCR_WARPS * 32;
+        fr3d::classify_screen_kernel<<<clampg((pair_cap + scr_threads - 1) / scr_threads,
+                                              (long long)g_sm_count * (mult ? mult : 2)),
+                                       scr_threads, fr3d::SCR_SMEM, st>>>(
             *nts, boxes, box_index, pair_i, pair_j, pair_cap, category_mask, wl_detail, wl_geom, counters);
         const uint32_t detail_cats = category_mask & (FR3D_CAT_SO | FR3D_CAT_SUGAR_RIBOSE | FR3D_CAT_BACKBONE);
         if (detail_cats)
