@@ -302,8 +302,8 @@ def main():
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, S),
                 "structures_per_s": S * world * args.steps / (ms_total / 1000.0),
                 "pairs_per_step": pairs_all, "hits_per_step": hits_all,
-                "worklists_rank0": {"detail_pairs": int(wl[4]), "geometry_pairs": int(wl[5]),
-                                    "flagged_stacking": int(wl[6]), "flagged_basepair_box": int(wl[7])},
+                "worklists_rank0": {"detail_pairs": int(wl[4]), "stacking_pairs": int(wl[5]),
+                                    "pairing_pairs": int(wl[6])},
                 "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "structures_per_s": S * world * args.steps / t_e2e, "ms_per_step": 1000.0 * t_e2e / args.steps,
                         "what": "engine.Pipeline.run: pinned host nt records -> H2D -> K1..K4 -> D2H hit records, "

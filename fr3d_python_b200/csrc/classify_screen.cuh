@@ -7,8 +7,12 @@
 // tails serialise the warp.  So the work is split: this kernel evaluates, one THREAD per pair and fully
 // converged, the cheap NECESSARY condition of every rule family (the same predicates the warp-per-pair
 // kernel votes on) and compacts the pairs that can still produce something into two work lists:
-//   detail list  -> classify_pairs_tpp_kernel   (sO, sugar-ribose, base-phosphate / base-ribose; thread per pair)
-//   geometry list-> classify_pairs_pm_kernel    (stacking, coplanar, basepair; warp per pair, shared-memory staging)
+//   detail list   -> classify_pairs_tpp_kernel  (sO, sugar-ribose, base-phosphate / base-ribose)
+//   stacking list -> classify_pairs_tpp_kernel  (base stacking)
+//   pairing list  -> classify_pairs_tpp_kernel  (coplanar, basepair)
+// Each list is homogeneous - nearly every pair on it runs the same rule to the end - so the thread-per-pair
+// kernel stays converged on it.  (FR3D_CLASSIFY_MODE=3 sends the union of the last two lists to the warp-per-pair
+// kernel classify_pairs_pm_kernel instead, for comparison.)
 // Every predicate is a superset of "this family yields a hit" (each rule is a conjunction), so results are
 // unchanged; tests/test_gpu_parity.py compares complete annotation sets with the reference.
 #pragma once
@@ -39,7 +43,7 @@ constexpr int SCR_UBOX = FR3D_N_PARENTS * FR3D_N_PARENTS * 2;      // (combo, si
 constexpr int SCR_MAX_BOXES = 256;                                 // cutoff boxes kept in shared memory (else global)
 constexpr int SCR_BOX_STRIDE = 9;                                  // odd: lane b reads box b without bank conflicts
 constexpr int SCR_HULL = FR3D_N_PARENTS * 7 * 3;
-constexpr int SCR_FIXED = SCR_UBOX * 8 + SCR_MAX_BOXES * SCR_BOX_STRIDE + SCR_HULL + SCR_UBOX;   // doubles
+constexpr int SCR_FIXED = SCR_UBOX * 8 + (SCR_MAX_BOXES * SCR_BOX_STRIDE + 1) / 2 + SCR_HULL + SCR_UBOX;   // doubles
 constexpr size_t SCR_SMEM = sizeof(double) * (SCR_FIXED + SCR_WARPS * 32 * SCR_STRIDE);
 
 // which atoms (bit per slot) of the 16 points q[0..47] lie in the cylinder |z| < 4.5, x^2 + y^2 < 16 of frame fa
@@ -89,12 +93,12 @@ __device__ __forceinline__ bool s_so_possible(const TFrame &fa, int pa, const do
 __global__ void __launch_bounds__(SCR_WARPS * 32)
 classify_screen_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, const int32_t *__restrict__ box_index,
                        const int32_t *__restrict__ pair_i, const int32_t *__restrict__ pair_j, int64_t pair_cap,
-                       uint32_t cats, int32_t *__restrict__ wl_detail, int32_t *__restrict__ wl_geom,
-                       int64_t *counters) {
+                       uint32_t cats, int32_t *__restrict__ wl_detail, int32_t *__restrict__ wl_stack,
+                       int32_t *__restrict__ wl_pair, int merge_geometry, int64_t *counters) {
     extern __shared__ double scr_smem[];
     double *ubox = scr_smem;                                                  // [SCR_UBOX][8] union boxes
-    double *sbox = ubox + SCR_UBOX * 8;                                       // [SCR_MAX_BOXES][SCR_BOX_STRIDE]
-    double *shull = sbox + SCR_MAX_BOXES * SCR_BOX_STRIDE;                    // [parents][7][3]
+    float *sbox = reinterpret_cast<float *>(ubox + SCR_UBOX * 8);             // [SCR_MAX_BOXES][SCR_BOX_STRIDE] mid, half
+    double *shull = ubox + SCR_UBOX * 8 + (SCR_MAX_BOXES * SCR_BOX_STRIDE + 1) / 2;   // [parents][7][3]
     int *sidx = reinterpret_cast<int *>(shull + SCR_HULL);                    // [SCR_UBOX][2] start, count
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *rows = scr_smem + SCR_FIXED + warp * 32 * SCR_STRIDE;
@@ -117,10 +121,20 @@ classify_screen_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, con
     }
     for (int item = threadIdx.x; item < SCR_HULL; item += blockDim.x) shull[item] = (&c_tab.hull[0][0][0])[item];
     __syncthreads();
+    // Cutoff boxes as single-precision (mid, half-width) pairs: the L1 excess of v over [lo, hi] is
+    // max(0, |v - mid| - half).  Single precision is enough for a screen: the acceptance margin below (1e-3) is far
+    // above its rounding error for displacements of a few Angstrom, so the screen stays a superset.
     const bool boxes_in_smem = s_nboxes <= SCR_MAX_BOXES;
+    int max_count = 0;
+    for (int e = 0; e < SCR_UBOX; ++e) max_count = max(max_count, sidx[e * 2 + 1]);
+    const bool two_tasks = boxes_in_smem && max_count <= 16;        // one (pair, orientation) per half warp
     if (boxes_in_smem)
-        for (int item = threadIdx.x; item < s_nboxes * 8; item += blockDim.x)
-            sbox[(item >> 3) * SCR_BOX_STRIDE + (item & 7)] = reinterpret_cast<const double *>(boxes + (item >> 3))[item & 7];
+        for (int item = threadIdx.x; item < s_nboxes * 4; item += blockDim.x) {
+            const double *bx = reinterpret_cast<const double *>(boxes + (item >> 2));
+            const double lo = bx[(item & 3) * 2], hi = bx[(item & 3) * 2 + 1];
+            sbox[(item >> 2) * SCR_BOX_STRIDE + (item & 3) * 2] = (float)(0.5 * (lo + hi));
+            sbox[(item >> 2) * SCR_BOX_STRIDE + (item & 3) * 2 + 1] = (float)(0.5 * (hi - lo));
+        }
     __syncthreads();
     // per-lane sources of the three copies that move one 90-double row
     const double *src[3];
@@ -244,50 +258,61 @@ classify_screen_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, con
         // some box within 1.0 before the angle term (NA:2546-2581)?  The angle and gap terms only add.
         unsigned pending = __ballot_sync(FULL, live != 0);
         while (pending) {
-            const int srcl = __ffs(pending) - 1;
+            // task of this lane's half warp (two_tasks) or of the whole warp
+            const int src_a = __ffs(pending) - 1;
+            const unsigned rest = pending & (pending - 1);
+            const int src_b = (two_tasks && rest) ? __ffs(rest) - 1 : -1;
+            const bool second = two_tasks && (lane >> 4);
+            const int srcl = second ? src_b : src_a;
+            const int sub = two_tasks ? (lane & 15) : lane;
             const bool first_ori = live & 1u;
-            const double tX = __shfl_sync(FULL, first_ori ? dX0 : dX1, srcl);
-            const double tY = __shfl_sync(FULL, first_ori ? dY0 : dY1, srcl);
-            const double tZ = __shfl_sync(FULL, first_ori ? dZ0 : dZ1, srcl);
-            const double tN = __shfl_sync(FULL, nZ, srcl);
-            const int te = __shfl_sync(FULL, first_ori ? entry0 : entry1, srcl);
-            const int bstart = sidx[te * 2], bcount = sidx[te * 2 + 1];
+            const int from = srcl < 0 ? 0 : srcl;
+            const float tX = __shfl_sync(FULL, (float)(first_ori ? dX0 : dX1), from);
+            const float tY = __shfl_sync(FULL, (float)(first_ori ? dY0 : dY1), from);
+            const float tZ = __shfl_sync(FULL, (float)(first_ori ? dZ0 : dZ1), from);
+            const float tN = __shfl_sync(FULL, (float)nZ, from);
+            const int te = __shfl_sync(FULL, first_ori ? entry0 : entry1, from);
+            const int bstart = sidx[te * 2], bcount = srcl < 0 ? 0 : sidx[te * 2 + 1];
             bool hit = false;
-            if (lane < bcount) {
-                const double *bx = boxes_in_smem ? sbox + (bstart + lane) * SCR_BOX_STRIDE
-                                                 : reinterpret_cast<const double *>(boxes + bstart + lane);
-                const double cd = fmax(0.0, bx[0] - tX) + fmax(0.0, tX - bx[1]) + fmax(0.0, bx[2] - tY) +
-                                  fmax(0.0, tY - bx[3]) + fmax(0.0, bx[4] - tZ) + fmax(0.0, tZ - bx[5]) +
-                                  3.0 * (fmax(0.0, bx[6] - tN) + fmax(0.0, tN - bx[7]));
-                hit = cd < 1.0 + 1e-9;             // summation order differs from the reference's: keep a margin
+            if (sub < bcount) {
+                float cd;
+                if (boxes_in_smem) {
+                    const float *bx = sbox + (bstart + sub) * SCR_BOX_STRIDE;
+                    cd = fmaxf(0.f, fabsf(tX - bx[0]) - bx[1]) + fmaxf(0.f, fabsf(tY - bx[2]) - bx[3]) +
+                         fmaxf(0.f, fabsf(tZ - bx[4]) - bx[5]) + 3.f * fmaxf(0.f, fabsf(tN - bx[6]) - bx[7]);
+                } else {
+                    const double *bx = reinterpret_cast<const double *>(boxes + bstart + sub);
+                    cd = fmaxf(0.f, (float)bx[0] - tX) + fmaxf(0.f, tX - (float)bx[1]) + fmaxf(0.f, (float)bx[2] - tY) +
+                         fmaxf(0.f, tY - (float)bx[3]) + fmaxf(0.f, (float)bx[4] - tZ) + fmaxf(0.f, tZ - (float)bx[5]) +
+                         3.f * (fmaxf(0.f, (float)bx[6] - tN) + fmaxf(0.f, tN - (float)bx[7]));
+                }
+                hit = cd < 1.0f + 1e-3f;
             }
-            const bool any = __any_sync(FULL, hit);
-            if (lane == srcl) {
+            const unsigned hits = __ballot_sync(FULL, hit);
+            if (lane == src_a || lane == src_b) {
+                const bool any = two_tasks ? ((lane == src_b ? hits >> 16 : hits & 0xFFFFu) != 0) : hits != 0;
                 if (any) { fl |= SCR_BP; live = 0; }
                 else live &= live - 1;
             }
             pending = __ballot_sync(FULL, live != 0);
         }
-        // warp-aggregated appends to the two work lists
+        // warp-aggregated appends to the work lists: counters[4] detail, [5] stacking, [6] coplanar / basepair
+        // (merge_geometry: the union of the last two goes to the stacking list, for the warp-per-pair kernel)
+        const unsigned want_stack = merge_geometry ? (fl & SCR_GEOM) : (fl & SCR_STACK);
+        const unsigned want_pair = merge_geometry ? 0u : (fl & (SCR_CP | SCR_BP));
         const unsigned bd = __ballot_sync(FULL, (fl & SCR_DETAIL) != 0);
-        const unsigned bg = __ballot_sync(FULL, (fl & SCR_GEOM) != 0);
-        // diagnostics (bench.py reports them): pairs flagged for stacking / for a live basepair box
-        const unsigned bs_ = __ballot_sync(FULL, (fl & SCR_STACK) != 0);
-        const unsigned bb_ = __ballot_sync(FULL, (fl & SCR_BP) != 0);
-        if (lane == 0 && bs_) atomicAdd((unsigned long long *)&counters[6], (unsigned long long)__popc(bs_));
-        if (lane == 0 && bb_) atomicAdd((unsigned long long *)&counters[7], (unsigned long long)__popc(bb_));
-        if (bd) {
-            long long base = 0;
-            if (lane == 0) base = (long long)atomicAdd((unsigned long long *)&counters[4], (unsigned long long)__popc(bd));
-            base = __shfl_sync(FULL, base, 0);
-            if (fl & SCR_DETAIL) wl_detail[base + __popc(bd & ((1u << lane) - 1u))] = (int32_t)p;
-        }
-        if (bg) {
-            long long base = 0;
-            if (lane == 0) base = (long long)atomicAdd((unsigned long long *)&counters[5], (unsigned long long)__popc(bg));
-            base = __shfl_sync(FULL, base, 0);
-            if (fl & SCR_GEOM) wl_geom[base + __popc(bg & ((1u << lane) - 1u))] = (int32_t)p;
-        }
+        const unsigned bs = __ballot_sync(FULL, want_stack != 0);
+        const unsigned bp = __ballot_sync(FULL, want_pair != 0);
+        long long base = 0;
+        if (lane == 0 && bd) base = (long long)atomicAdd((unsigned long long *)&counters[4], (unsigned long long)__popc(bd));
+        if (lane == 1 && bs) base = (long long)atomicAdd((unsigned long long *)&counters[5], (unsigned long long)__popc(bs));
+        if (lane == 2 && bp) base = (long long)atomicAdd((unsigned long long *)&counters[6], (unsigned long long)__popc(bp));
+        const long long base_d = __shfl_sync(FULL, base, 0), base_s = __shfl_sync(FULL, base, 1),
+                        base_p = __shfl_sync(FULL, base, 2);
+        const unsigned below = (1u << lane) - 1u;
+        if (fl & SCR_DETAIL) wl_detail[base_d + __popc(bd & below)] = (int32_t)p;
+        if (want_stack) wl_stack[base_s + __popc(bs & below)] = (int32_t)p;
+        if (want_pair) wl_pair[base_p + __popc(bp & below)] = (int32_t)p;
     }
 }
 

@@ -7,15 +7,21 @@
 // one candidate pair and walks the same rules sequentially, so that bookkeeping is amortised over 32
 // pairs per warp instruction, while the data-parallel parts (32 atom projections, 12 oxygens, 30
 // donor/oxygen combinations, 256 atom-atom distances) become unrolled loops with plenty of
-// instruction-level parallelism.  Records are read straight from global memory through L1: pairs are
-// emitted grouped by nt1, so a warp's 32 pairs share a handful of nt1 records (broadcast) and spatially
-// neighbouring nt2 records.
+// instruction-level parallelism.
+//
+// Data access: a thread that reads "its" nt record straight from global memory makes every load instruction
+// touch 32 different cache lines - ncu shows such a kernel pinned at ~80 % of the L1 wavefront rate with the
+// issue slots 90 % idle.  So (ROW_LEN > 0) each warp first stages the records of its 32 pairs in shared memory
+// with coalesced cp.async copies (lanes copy consecutive doubles of one record) and every thread then works out
+// of its own row; the row stride is odd, which makes "lane k reads row k" bank-conflict free.  The helpers take
+// plain pointers, so the same code also runs on global memory (ROW_LEN == 0).
 //
 // The arithmetic is the same as in the warp-per-pair kernels and as in the reference; every function
 // below cites the reference lines it restates (NA = fr3d/classifiers/NA_pairwise_interactions.py).
 #pragma once
 
 #include "classify.cuh"
+#include "classify_pm.cuh"
 
 namespace fr3d {
 
@@ -23,6 +29,14 @@ struct TFrame {
     double c0, c1, c2;
     double u0, u1, u2, u3, u4, u5, u6, u7, u8;     // row-major rotation_matrix
 };
+
+// frame from a staged row: centre 0..2, rotation 3..11
+__device__ __forceinline__ TFrame load_tframe_row(const double *R) {
+    TFrame f;
+    f.c0 = R[0]; f.c1 = R[1]; f.c2 = R[2];
+    f.u0 = R[3]; f.u1 = R[4]; f.u2 = R[5]; f.u3 = R[6]; f.u4 = R[7]; f.u5 = R[8]; f.u6 = R[9]; f.u7 = R[10]; f.u8 = R[11];
+    return f;
+}
 
 __device__ __forceinline__ TFrame load_tframe(const fr3d_nts_t &nts, int n) {
     const double *c = nts.center + (size_t)n * 3;
@@ -43,9 +57,7 @@ __device__ __forceinline__ void tproject(const TFrame &f, double px, double py, 
 }
 
 // return_overlap (NA:1530-1571): base atoms of nt_b seen from the frame of nt_a
-__device__ __forceinline__ bool t_overlap(const fr3d_nts_t &nts, const TFrame &fa, int par_a, int nb, uint32_t bmb,
-                                          double &zsel) {
-    const double *q = nts.base_xyz + (size_t)nb * FR3D_BASE_SLOTS * 3;
+__device__ __forceinline__ bool t_overlap(const TFrame &fa, int par_a, const double *q, uint32_t bmb, double &zsel) {
     bool inside = false;
     double zmin = 1e300, zmax = -1e300, best = 1e300;
     zsel = 0.0;
@@ -63,9 +75,8 @@ __device__ __forceinline__ bool t_overlap(const fr3d_nts_t &nts, const TFrame &f
 }
 
 // check_base_oxygen_stack_rings (NA:1278-1473): base of nt_a, oxygens of nt_b.  Returns the code or -1.
-__device__ __forceinline__ int t_so(const fr3d_nts_t &nts, const TFrame &fa, int pa, int nb, uint32_t bbb) {
+__device__ __forceinline__ int t_so(const TFrame &fa, int pa, const double *B, uint32_t bbb) {
     if (pa < 0 || pa >= FR3D_N_PARENTS) return -1;
-    const double *B = nts.bb_xyz + (size_t)nb * FR3D_BB_SLOTS * 3;
     const bool has_div = c_tab.has_div[pa];
     bool true_found = false, ring_found = false;
     double zmin_abs = 1e300, zring = 0.0;
@@ -107,13 +118,11 @@ __device__ __forceinline__ int t_so(const fr3d_nts_t &nts, const TFrame &fa, int
 }
 
 // check_sugar_ribose (NA:2262-2342) after the shared O2'-O2' screen.  -1 none, 0 cSR, 1 tSR.
-__device__ __noinline__ int t_sr_tail(const fr3d_nts_t &nts, int na, int nb, uint32_t bma, uint32_t bba, uint32_t bbb,
-                                      int pa, double n0, double n1, double n2) {
+__device__ __noinline__ int t_sr_tail(const double *A, const double *B, const double *base_a, uint32_t bma,
+                                      uint32_t bba, uint32_t bbb, int pa, double n0, double n1, double n2) {
     const int bs = c_tab.sr_slot[pa];
     if (bs < 0 || !((bma >> bs) & 1u)) return -1;
-    const double *A = nts.bb_xyz + (size_t)na * FR3D_BB_SLOTS * 3;
-    const double *B = nts.bb_xyz + (size_t)nb * FR3D_BB_SLOTS * 3;
-    const double *bp = nts.base_xyz + ((size_t)na * FR3D_BASE_SLOTS + bs) * 3;
+    const double *bp = base_a + bs * 3;
     const double d0 = bp[0] - B[18], d1 = bp[1] - B[19], d2 = bp[2] - B[20];
     if (sqrt(d0 * d0 + d1 * d1 + d2 * d2) > 3.8) return -1;
     if (fabs(d0 * n0 + d1 * n1 + d2 * n2) > 2.0) return -1;
@@ -141,10 +150,8 @@ __device__ __noinline__ int t_sr_tail(const fr3d_nts_t &nts, int na, int nb, uin
 
 // check_base_backbone_interactions (NA:1867-2049): nt1 base -> nt2 backbone, with the reference's own
 // sequential, sticky selection.  Returns bph | br << 8 (digit | near << 4; 0xFF none).
-__device__ __noinline__ int t_backbone(const fr3d_nts_t &nts, const TFrame &f1, int par1, int n1, int n2, uint32_t bm1,
+__device__ __noinline__ int t_backbone(const TFrame &f1, int par1, const double *A, const double *B, uint32_t bm1,
                                        uint32_t bb2) {
-    const double *B = nts.bb_xyz + (size_t)n2 * FR3D_BB_SLOTS * 3;
-    const double *A = nts.base_xyz + (size_t)n1 * FR3D_BASE_SLOTS * 3;
     int bph = -1, br = -1;
     bool use_ph = true;                    // P far from the plane of base 1: no BPh (NA:1915-1921)
     if (bb2 & 1u) {
@@ -238,10 +245,8 @@ __device__ __noinline__ int t_backbone(const fr3d_nts_t &nts, const TFrame &f1, 
 }
 
 // cheap necessary condition for t_backbone: some donor heavy atom of nt1 within 4.5 A of a backbone oxygen
-__device__ __forceinline__ bool t_backbone_possible(const fr3d_nts_t &nts, int par1, int n1, int n2, uint32_t bm1,
+__device__ __forceinline__ bool t_backbone_possible(int par1, const double *A, const double *B, uint32_t bm1,
                                                     uint32_t bb2) {
-    const double *B = nts.bb_xyz + (size_t)n2 * FR3D_BB_SLOTS * 3;
-    const double *A = nts.base_xyz + (size_t)n1 * FR3D_BASE_SLOTS * 3;
     const int nsites = c_tab.n_sites[par1];
     bool any = false;
 #pragma unroll 1
@@ -260,13 +265,13 @@ __device__ __forceinline__ bool t_backbone_possible(const fr3d_nts_t &nts, int p
 }
 
 // one point of a (possibly twin) slot: v < 16 -> the observed / stored point, v >= 16 -> the ideal copy
-__device__ __forceinline__ bool t_point(const fr3d_nts_t &nts, const TFrame &f, int par, int n, uint32_t bm, uint32_t tw,
+__device__ __forceinline__ bool t_point(const TFrame &f, int par, const double *base, uint32_t bm, uint32_t tw,
                                         int v, double &p0, double &p1, double &p2) {
     const int k = v & 15;
     if (!((bm >> k) & 1u)) return false;
     const bool twin = (tw >> k) & 1u;
     if (v >= 16 && !twin) return false;
-    const double *q = nts.base_xyz + ((size_t)n * FR3D_BASE_SLOTS + k) * 3;
+    const double *q = base + k * 3;
     p0 = q[0]; p1 = q[1]; p2 = q[2];
     if (twin) {
         const double s0 = c_tab.std_xyz[par][k][0], s1 = c_tab.std_xyz[par][k][1], s2 = c_tab.std_xyz[par][k][2];
@@ -281,14 +286,14 @@ __device__ __forceinline__ bool t_point(const fr3d_nts_t &nts, const TFrame &f, 
 
 // calculate_basepair_gap (NA:2189-2259): min |z| (frame of nt_a) over the 3 base atoms of nt_b nearest
 // to the centre of nt_a
-__device__ __noinline__ double t_gap(const fr3d_nts_t &nts, const TFrame &fa, const TFrame &fb, int par_b, int nb,
+__device__ __noinline__ double t_gap(const TFrame &fa, const TFrame &fb, int par_b, const double *base_b,
                                      uint32_t bmb, uint32_t twb) {
     double k0 = 1e300, k1 = 1e300, k2 = 1e300, z0 = 100.0, z1 = 100.0, z2 = 100.0;
     const int nv = twb ? 32 : 16;
 #pragma unroll 1
     for (int v = 0; v < nv; ++v) {
         double p0, p1, p2;
-        if (!t_point(nts, fb, par_b, nb, bmb, twb, v, p0, p1, p2)) continue;
+        if (!t_point(fb, par_b, base_b, bmb, twb, v, p0, p1, p2)) continue;
         const double w0 = p0 - fa.c0, w1 = p1 - fa.c1, w2 = p2 - fa.c2;
         const double key = w0 * w0 + w1 * w1 + w2 * w2;
         const double z = fabs(w0 * fa.u2 + w1 * fa.u5 + w2 * fa.u8);
@@ -300,16 +305,16 @@ __device__ __noinline__ double t_gap(const fr3d_nts_t &nts, const TFrame &fa, co
 }
 
 // calculate_base_min_distances (NA:1799-1829)
-__device__ __noinline__ double t_mind(const fr3d_nts_t &nts, const TFrame &f1, const TFrame &f2, int par1, int par2,
-                                      int n1, int n2, uint32_t bm1, uint32_t bm2, uint32_t tw1, uint32_t tw2) {
+__device__ __noinline__ double t_mind(const TFrame &f1, const TFrame &f2, int par1, int par2, const double *base1,
+                                      const double *base2, uint32_t bm1, uint32_t bm2, uint32_t tw1, uint32_t tw2) {
     double best = 1e300;
     const int nv1 = tw1 ? 32 : 16, nv2 = tw2 ? 32 : 16;
 #pragma unroll 1
     for (int v = 0; v < nv1; ++v) {
         double a0, a1, a2;
-        if (!t_point(nts, f1, par1, n1, bm1, tw1, v, a0, a1, a2)) continue;
+        if (!t_point(f1, par1, base1, bm1, tw1, v, a0, a1, a2)) continue;
         if (!tw2) {
-            const double *q = nts.base_xyz + (size_t)n2 * FR3D_BASE_SLOTS * 3;
+            const double *q = base2;
 #pragma unroll 4
             for (int k = 0; k < FR3D_BASE_SLOTS; ++k) {
                 const double d0 = q[k * 3] - a0, d1 = q[k * 3 + 1] - a1, d2 = q[k * 3 + 2] - a2;
@@ -320,7 +325,7 @@ __device__ __noinline__ double t_mind(const fr3d_nts_t &nts, const TFrame &f1, c
 #pragma unroll 1
             for (int w = 0; w < nv2; ++w) {
                 double b0, b1, b2;
-                if (!t_point(nts, f2, par2, n2, bm2, tw2, w, b0, b1, b2)) continue;
+                if (!t_point(f2, par2, base2, bm2, tw2, w, b0, b1, b2)) continue;
                 const double d0 = b0 - a0, d1 = b1 - a1, d2 = b2 - a2;
                 best = fmin(best, d0 * d0 + d1 * d1 + d2 * d2);
             }
@@ -416,18 +421,42 @@ __device__ __noinline__ bool t_boxes(const fr3d_box_t *__restrict__ boxes, int b
 #define FR3D_TPP_MIN_BLOCKS 3
 #endif
 
-__global__ void __launch_bounds__(128, FR3D_TPP_MIN_BLOCKS)
+// ROW_LEN doubles of each nt record are staged per pair: 0 = none (read global memory), 60 = frame + base atoms,
+// 90 = frame + base atoms + backbone atoms.  WARPS = warps per block (dynamic shared memory = tpp_smem_bytes).
+template <int ROW_LEN, int WARPS>
+__host__ __device__ constexpr size_t tpp_smem_bytes() {
+    return ROW_LEN ? sizeof(double) * (size_t)WARPS * 32 * (2 * ROW_LEN + 1) : 0;
+}
+
+template <int ROW_LEN, int WARPS, int MIN_BLOCKS>
+__global__ void __launch_bounds__(WARPS * 32, MIN_BLOCKS)
 classify_pairs_tpp_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, const int32_t *__restrict__ box_index,
                           const int32_t *__restrict__ pair_i, const int32_t *__restrict__ pair_j,
                           const int32_t *__restrict__ pair_rank, int64_t pair_cap, uint32_t cats, int32_t index_offset,
                           fr3d_hit_t *__restrict__ hits, int64_t hit_cap, int64_t *counters,
-                          const int32_t *__restrict__ worklist, int do_bp) {
+                          const int32_t *__restrict__ worklist, int list_counter, int do_bp) {
+    extern __shared__ double tpp_smem[];
+    constexpr int PSTRIDE = 2 * ROW_LEN + 1;                 // odd: lane k reads row k without bank conflicts
     const int lane = threadIdx.x & 31;
+    double *rows = tpp_smem + (size_t)(threadIdx.x >> 5) * 32 * PSTRIDE;
+    // per-lane sources of the (up to three) copies that move one staged record
+    const double *src[3] = {nullptr, nullptr, nullptr};
+    int mult[3] = {0, 0, 0};
+    if (ROW_LEN) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const int t = j * 32 + lane;
+            if (t < 3) { src[j] = nts.center + t; mult[j] = 3; }
+            else if (t < 12) { src[j] = nts.rot + (t - 3); mult[j] = 9; }
+            else if (t < 60) { src[j] = nts.base_xyz + (t - 12); mult[j] = FR3D_BASE_SLOTS * 3; }
+            else { src[j] = nts.bb_xyz + (t - 60); mult[j] = FR3D_BB_SLOTS * 3; }
+        }
+    }
     // with a work list (classify_screen.cuh) the kernel walks its entries instead of the whole pair list
-    long long n_pairs = worklist ? counters[4] : counters[0];
+    long long n_pairs = worklist ? counters[list_counter] : counters[0];
     if (n_pairs > pair_cap) n_pairs = pair_cap;
     const long long stride = (long long)gridDim.x * blockDim.x;
-    // whole warps iterate together so that the emission below can use warp collectives
+    // whole warps iterate together so that the staging and the emission below can use warp collectives
     const long long first = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long rounds = (n_pairs + stride - 1) / stride;
 
@@ -435,6 +464,7 @@ classify_pairs_tpp_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, 
     for (long long r = 0; r < rounds; ++r) {
         const long long p = first + r * stride;
         const bool active = p < n_pairs;
+        if (!__any_sync(FULL, active)) continue;
         unsigned hmask = 0;
         int c_so12 = 0, c_so21 = 0, c_stack = 0, c_sr12 = 0, c_sr21 = 0, c_bph = 0, c_br = 0, c_bp = 0, bp_box = 0;
         double bp_cd = 0.0, bp_gap = 0.0;
@@ -442,16 +472,49 @@ classify_pairs_tpp_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, 
         if (active) {
             const long long q = worklist ? (long long)worklist[p] : p;
             n1 = pair_i[q]; n2 = pair_j[q]; rank = pair_rank[q];
-            const uint32_t bm1 = nts.base_mask[n1], bm2 = nts.base_mask[n2];
-            const uint32_t bb1 = nts.bb_mask[n1], bb2 = nts.bb_mask[n2];
+        }
+        if (ROW_LEN) {
+            __syncwarp();                                   // everybody is done with the previous round's rows
+#pragma unroll 2
+            for (int k = 0; k < 32; ++k) {
+                const int na = __shfl_sync(FULL, n1, k), nb = __shfl_sync(FULL, n2, k);
+                double *dst = rows + k * PSTRIDE + lane;
+                cp_async8(dst, src[0] + (size_t)na * mult[0]);
+                cp_async8(dst + ROW_LEN, src[0] + (size_t)nb * mult[0]);
+                if (lane + 32 < ROW_LEN) {
+                    cp_async8(dst + 32, src[1] + (size_t)na * mult[1]);
+                    cp_async8(dst + ROW_LEN + 32, src[1] + (size_t)nb * mult[1]);
+                }
+                if (ROW_LEN > 64 && lane + 64 < ROW_LEN) {
+                    cp_async8(dst + 64, src[2] + (size_t)na * mult[2]);
+                    cp_async8(dst + ROW_LEN + 64, src[2] + (size_t)nb * mult[2]);
+                }
+            }
+        }
+        uint32_t bm1 = 0, bm2 = 0, bb1 = 0, bb2 = 0;
+        if (active) {
+            bm1 = nts.base_mask[n1]; bm2 = nts.base_mask[n2];
+            bb1 = nts.bb_mask[n1]; bb2 = nts.bb_mask[n2];
+        }
+        if (ROW_LEN) {
+            cp_async_wait_all();
+            __syncwarp();
+        }
+        if (active) {
             const int par1 = (int)((bm1 >> 16) & 15u) - 1, par2 = (int)((bm2 >> 16) & 15u) - 1;
-            const TFrame f1 = load_tframe(nts, n1), f2 = load_tframe(nts, n2);
+            const double *R1 = rows + lane * PSTRIDE, *R2 = R1 + ROW_LEN;
+            const TFrame f1 = ROW_LEN ? load_tframe_row(R1) : load_tframe(nts, n1);
+            const TFrame f2 = ROW_LEN ? load_tframe_row(R2) : load_tframe(nts, n2);
+            const double *base1 = ROW_LEN ? R1 + 12 : nts.base_xyz + (size_t)n1 * FR3D_BASE_SLOTS * 3;
+            const double *base2 = ROW_LEN ? R2 + 12 : nts.base_xyz + (size_t)n2 * FR3D_BASE_SLOTS * 3;
+            const double *bbp1 = ROW_LEN > 64 ? R1 + 60 : nts.bb_xyz + (size_t)n1 * FR3D_BB_SLOTS * 3;
+            const double *bbp2 = ROW_LEN > 64 ? R2 + 60 : nts.bb_xyz + (size_t)n2 * FR3D_BB_SLOTS * 3;
             const double nZ = f1.u2 * f2.u2 + f1.u5 * f2.u5 + f1.u8 * f2.u8;      // M[2][2] in both orientations
 
             // ---- base-oxygen stacking, both directions (NA:758-778)
             if (cats & FR3D_CAT_SO) {
-                const int a = t_so(nts, f1, par1, n2, bb2);
-                const int b = t_so(nts, f2, par2, n1, bb1);
+                const int a = t_so(f1, par1, bbp2, bb2);
+                const int b = t_so(f2, par2, bbp1, bb1);
                 if (a >= 0) { hmask |= 1u << FR3D_SLOT_SO12; c_so12 = a; }
                 if (b >= 0) { hmask |= 1u << FR3D_SLOT_SO21; c_so21 = b; }
             }
@@ -460,8 +523,8 @@ classify_pairs_tpp_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, 
             bool stack_both = false;
             if ((cats & FR3D_CAT_STACKING) && par1 >= 0 && par2 >= 0) {
                 double z_2on1, z_1on2;
-                const bool nt2on1 = t_overlap(nts, f1, par1, n2, bm2, z_2on1);
-                const bool nt1on2 = t_overlap(nts, f2, par2, n1, bm1, z_1on2);
+                const bool nt2on1 = t_overlap(f1, par1, base2, bm2, z_2on1);
+                const bool nt1on2 = t_overlap(f2, par2, base1, bm1, z_1on2);
                 if ((nt2on1 || nt1on2) && !(fabs(nZ) < 0.5)) {
                     const bool reverse = nt1on2 && !nt2on1;
                     const double mvd = reverse ? z_1on2 : z_2on1;
@@ -476,20 +539,19 @@ classify_pairs_tpp_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, 
             // ---- sugar-ribose, both directions (NA:791-804)
             if ((cats & FR3D_CAT_SUGAR_RIBOSE) && par1 >= 0 && par2 >= 0 && par1 != 4 && par2 != 4 &&
                 (bb1 >> 6 & 1u) && (bb2 >> 6 & 1u)) {
-                const double *A = nts.bb_xyz + (size_t)n1 * FR3D_BB_SLOTS * 3;
-                const double *B = nts.bb_xyz + (size_t)n2 * FR3D_BB_SLOTS * 3;
+                const double *A = bbp1, *B = bbp2;
                 const double o0 = A[18] - B[18], o1 = A[19] - B[19], o2 = A[20] - B[20];
                 const double oo = o0 * o0 + o1 * o1 + o2 * o2;
                 if (oo < 14.4401 && !(sqrt(oo) > 3.8)) {
-                    const int r12 = t_sr_tail(nts, n1, n2, bm1, bb1, bb2, par1, f1.u2, f1.u5, f1.u8);
-                    const int r21 = t_sr_tail(nts, n2, n1, bm2, bb2, bb1, par2, f2.u2, f2.u5, f2.u8);
+                    const int r12 = t_sr_tail(bbp1, bbp2, base1, bm1, bb1, bb2, par1, f1.u2, f1.u5, f1.u8);
+                    const int r21 = t_sr_tail(bbp2, bbp1, base2, bm2, bb2, bb1, par2, f2.u2, f2.u5, f2.u8);
                     if (r12 >= 0) { hmask |= 1u << FR3D_SLOT_SR12; c_sr12 = r12; }
                     if (r21 >= 0) { hmask |= 1u << FR3D_SLOT_SR21; c_sr21 = r21; }
                 }
             }
             // ---- base-phosphate / base-ribose, nt1 base -> nt2 backbone (NA:807-829)
-            if ((cats & FR3D_CAT_BACKBONE) && par1 >= 0 && t_backbone_possible(nts, par1, n1, n2, bm1, bb2)) {
-                const int sel = t_backbone(nts, f1, par1, n1, n2, bm1, bb2);
+            if ((cats & FR3D_CAT_BACKBONE) && par1 >= 0 && t_backbone_possible(par1, base1, bbp2, bm1, bb2)) {
+                const int sel = t_backbone(f1, par1, base1, bbp2, bm1, bb2);
                 if ((sel & 0xFF) != 0xFF) { hmask |= 1u << FR3D_SLOT_BPH; c_bph = sel & 0xFF; }
                 if (((sel >> 8) & 0xFF) != 0xFF) { hmask |= 1u << FR3D_SLOT_BR; c_br = (sel >> 8) & 0xFF; }
             }
@@ -508,8 +570,7 @@ classify_pairs_tpp_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, 
                     const double d2 = e0 * f2.u2 + e1 * f2.u5 + e2 * f2.u8;
                     cp_frames = d1 * d1 < lim && d2 * d2 < lim;
                 }
-                const double *g1 = nts.base_xyz + (size_t)n1 * FR3D_BASE_SLOTS * 3;
-                const double *g2 = nts.base_xyz + (size_t)n2 * FR3D_BASE_SLOTS * 3;
+                const double *g1 = base1, *g2 = base2;
                 gd0 = g2[0] - g1[0]; gd1 = g2[1] - g1[1]; gd2 = g2[2] - g1[2];
 #pragma unroll 1
                 for (int ori = 0; ori < 2; ++ori) {
@@ -540,12 +601,12 @@ classify_pairs_tpp_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, 
                 if ((bm1 >> 22) & 1u) tw1 = (uint32_t)nts.meta[(size_t)n1 * FR3D_META_INTS + 7] >> 16;
                 if ((bm2 >> 22) & 1u) tw2 = (uint32_t)nts.meta[(size_t)n2 * FR3D_META_INTS + 7] >> 16;
                 if (bp_live || cp_frames) {
-                    gap12 = t_gap(nts, f1, f2, par2, n2, bm2, tw2);
-                    gap21 = t_gap(nts, f2, f1, par1, n1, bm1, tw1);
+                    gap12 = t_gap(f1, f2, par2, base2, bm2, tw2);
+                    gap21 = t_gap(f2, f1, par1, base1, bm1, tw1);
                 }
                 const bool cp_gap = cp_frames && (((ori_ok & 1u) && gap12 < 1.5179) || ((ori_ok & 2u) && gap21 < 1.5179));
                 if (stack_code >= 0 || bp_live || cp_gap)
-                    mind = t_mind(nts, f1, f2, par1, par2, n1, n2, bm1, bm2, tw1, tw2);
+                    mind = t_mind(f1, f2, par1, par2, base1, base2, bm1, bm2, tw1, tw2);
                 if (stack_code >= 0 && !(fabs(mind) < 1.0)) {                 // NA:1707-1718
                     int near = 1;
                     if (fabs(mind) < 4.0 && fabs(mind) > 1.0 && fabs(nZ) > 0.6 && stack_both) near = 0;

@@ -133,7 +133,7 @@ int fr3d_pair_search(const fr3d_nts_t *nts, double cell_size, void *workspace, s
 
 size_t fr3d_classify_workspace(int64_t pair_cap) {
     if (pair_cap < 0) pair_cap = 0;
-    return 2 * align_up(sizeof(int32_t) * (size_t)pair_cap, 256) + 256;
+    return 3 * align_up(sizeof(int32_t) * (size_t)pair_cap, 256) + 256;
 }
 
 int fr3d_classify_pairs(const fr3d_nts_t *nts, const fr3d_box_t *boxes, const int32_t *box_index,
@@ -155,15 +155,16 @@ int fr3d_classify_pairs(const fr3d_nts_t *nts, const fr3d_box_t *boxes, const in
         mode = m ? atoi(m) : 2;
     }
     int use_mode = mode;
-    if (use_mode == 2 && (!workspace || workspace_bytes < fr3d_classify_workspace(pair_cap))) use_mode = 0;
+    if ((use_mode == 2 || use_mode == 3) && (!workspace || workspace_bytes < fr3d_classify_workspace(pair_cap))) use_mode = 0;
     const long long tpp_grid_max = (long long)g_sm_count * (mult ? mult : 4 * FR3D_TPP_MIN_BLOCKS);
     const long long pm_grid_max = (long long)g_sm_count * (mult ? mult : FR3D_CLASSIFY_MIN_BLOCKS);
     const long long per_block = (long long)fr3d::WARPS_PER_BLOCK * fr3d::PM_K;
     auto clampg = [](long long want, long long mx) { long long g = want < mx ? want : mx; return (int)(g < 1 ? 1 : g); };
-    if (use_mode == 2) {
+    if (use_mode == 2 || use_mode == 3) {
+        const size_t list_bytes = align_up(sizeof(int32_t) * (size_t)pair_cap, 256);
         int32_t *wl_detail = static_cast<int32_t *>(workspace);
-        int32_t *wl_geom = reinterpret_cast<int32_t *>(static_cast<char *>(workspace) +
-                                                       align_up(sizeof(int32_t) * (size_t)pair_cap, 256));
+        int32_t *wl_stack = reinterpret_cast<int32_t *>(static_cast<char *>(workspace) + list_bytes);
+        int32_t *wl_pair = reinterpret_cast<int32_t *>(static_cast<char *>(workspace) + 2 * list_bytes);
         CUDA_TRY(cudaMemsetAsync(counters + 4, 0, 4 * sizeof(int64_t), st));
         CUDA_TRY(cudaFuncSetAttribute(fr3d::classify_screen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)fr3d::SCR_SMEM));
@@ -171,20 +172,45 @@ int fr3d_classify_pairs(const fr3d_nts_t *nts, const fr3d_box_t *boxes, const in
         fr3d::classify_screen_kernel<<<clampg((pair_cap + scr_threads - 1) / scr_threads,
                                               (long long)g_sm_count * (mult ? mult : 2)),
                                        scr_threads, fr3d::SCR_SMEM, st>>>(
-            *nts, boxes, box_index, pair_i, pair_j, pair_cap, category_mask, wl_detail, wl_geom, counters);
+            *nts, boxes, box_index, pair_i, pair_j, pair_cap, category_mask, wl_detail, wl_stack, wl_pair,
+            use_mode == 3 ? 1 : 0, counters);
+        const int tpp_grid = clampg((pair_cap + 127) / 128, tpp_grid_max);
         const uint32_t detail_cats = category_mask & (FR3D_CAT_SO | FR3D_CAT_SUGAR_RIBOSE | FR3D_CAT_BACKBONE);
-        if (detail_cats)
-            fr3d::classify_pairs_tpp_kernel<<<clampg((pair_cap + 127) / 128, tpp_grid_max), 128, 0, st>>>(
-                *nts, boxes, box_index, pair_i, pair_j, pair_rank, pair_cap, detail_cats, index_offset, hits, hit_cap,
-                counters, wl_detail, 0);
-        fr3d::classify_pairs_pm_kernel<<<clampg((pair_cap + per_block - 1) / per_block, pm_grid_max),
-                                         fr3d::WARPS_PER_BLOCK * 32, 0, st>>>(
-            *nts, boxes, box_index, pair_i, pair_j, pair_rank, pair_cap,
-            category_mask & (FR3D_CAT_STACKING | FR3D_CAT_COPLANAR), index_offset, hits, hit_cap, counters, wl_geom);
+        // staged thread-per-pair kernels: frame + base atoms (60 doubles per nt) for stacking / pairing, 7 warps per SM
+        auto tpp60 = fr3d::classify_pairs_tpp_kernel<60, 7, 1>;
+        auto tpp90 = fr3d::classify_pairs_tpp_kernel<90, 4, 1>;
+        auto tpp0 = fr3d::classify_pairs_tpp_kernel<0, 4, FR3D_TPP_MIN_BLOCKS>;
+        constexpr size_t smem60 = fr3d::tpp_smem_bytes<60, 7>(), smem90 = fr3d::tpp_smem_bytes<90, 4>();
+        CUDA_TRY(cudaFuncSetAttribute(tpp60, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem60));
+        CUDA_TRY(cudaFuncSetAttribute(tpp90, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem90));
+        const int grid60 = clampg((pair_cap + 223) / 224, (long long)g_sm_count * (mult ? mult : 1));
+        const int grid90 = clampg((pair_cap + 127) / 128, (long long)g_sm_count * (mult ? mult : 1));
+        static const int detail_staged = getenv("FR3D_DETAIL_STAGED") ? atoi(getenv("FR3D_DETAIL_STAGED")) : 0;
+        if (detail_cats) {
+            if (detail_staged)
+                tpp90<<<grid90, 128, smem90, st>>>(*nts, boxes, box_index, pair_i, pair_j, pair_rank, pair_cap, detail_cats,
+                                                   index_offset, hits, hit_cap, counters, wl_detail, 4, 0);
+            else
+                tpp0<<<tpp_grid, 128, 0, st>>>(*nts, boxes, box_index, pair_i, pair_j, pair_rank, pair_cap, detail_cats,
+                                               index_offset, hits, hit_cap, counters, wl_detail, 4, 0);
+        }
+        if (use_mode == 3) {
+            fr3d::classify_pairs_pm_kernel<<<clampg((pair_cap + per_block - 1) / per_block, pm_grid_max),
+                                             fr3d::WARPS_PER_BLOCK * 32, 0, st>>>(
+                *nts, boxes, box_index, pair_i, pair_j, pair_rank, pair_cap,
+                category_mask & (FR3D_CAT_STACKING | FR3D_CAT_COPLANAR), index_offset, hits, hit_cap, counters, wl_stack);
+        } else {
+            if (category_mask & FR3D_CAT_STACKING)
+                tpp60<<<grid60, 224, smem60, st>>>(*nts, boxes, box_index, pair_i, pair_j, pair_rank, pair_cap,
+                                                   FR3D_CAT_STACKING, index_offset, hits, hit_cap, counters, wl_stack, 5, 0);
+            tpp60<<<grid60, 224, smem60, st>>>(*nts, boxes, box_index, pair_i, pair_j, pair_rank, pair_cap,
+                                               category_mask & FR3D_CAT_COPLANAR, index_offset, hits, hit_cap, counters,
+                                               wl_pair, 6, 1);
+        }
     } else if (use_mode == 1) {
-        fr3d::classify_pairs_tpp_kernel<<<clampg((pair_cap + 127) / 128, tpp_grid_max), 128, 0, st>>>(
+        fr3d::classify_pairs_tpp_kernel<0, 4, FR3D_TPP_MIN_BLOCKS><<<clampg((pair_cap + 127) / 128, tpp_grid_max), 128, 0, st>>>(
             *nts, boxes, box_index, pair_i, pair_j, pair_rank, pair_cap, category_mask, index_offset, hits, hit_cap,
-            counters, nullptr, 1);
+            counters, nullptr, 0, 1);
     } else {
         fr3d::classify_pairs_pm_kernel<<<clampg((pair_cap + per_block - 1) / per_block, pm_grid_max),
                                          fr3d::WARPS_PER_BLOCK * 32, 0, st>>>(

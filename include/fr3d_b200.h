@@ -152,8 +152,8 @@ int fr3d_frames_fit(const fr3d_nts_t *nts, int32_t *status, int place_h, void *s
 /* K2+K3. Replaces make_nt_cubes_half (NA:410-443) and the loop/screens of
  * annotate_nt_nt_interactions (NA:661-724): oriented candidate pairs with 2 <= d <= 12.
  * counters (device int64[8]): [0] n_pairs (may exceed cap: FR3D_E_CAPACITY is NOT raised here,
- * the caller compares after its sync), [1] n_hits, [2] error flags, [3] n_cells, [4] [5] work-list sizes of
- * fr3d_classify_pairs, [6] [7] reserved. */
+ * the caller compares after its sync), [1] n_hits, [2] error flags, [3] n_cells, [4] [5] [6] work-list sizes of
+ * fr3d_classify_pairs (detail, stacking, coplanar / basepair), [7] reserved. */
 size_t fr3d_pair_search_workspace(int32_t n_nt);
 int fr3d_pair_search(const fr3d_nts_t *nts, double cell_size, void *workspace, size_t workspace_bytes,
                      int32_t *pair_i, int32_t *pair_j, int32_t *pair_rank, int64_t pair_cap,
@@ -162,14 +162,14 @@ int fr3d_pair_search(const fr3d_nts_t *nts, double cell_size, void *workspace, s
 /* K4. Replaces check_base_oxygen_stack_rings (NA:1278), check_base_base_stacking (NA:1602),
  * check_sugar_ribose (NA:2262), check_base_backbone_interactions (NA:1867), check_coplanar
  * (NA:2051), check_basepair_cutoffs (NA:2364) and the 12-vs-21 arbitration (NA:935-957):
- * one warp per candidate pair, hits compacted with a warp ballot.
+ * hits compacted with a warp-aggregated atomic.
  * n_pairs is read from counters[0] on the device (clamped to pair_cap).  index_offset is added to the
  * nt indices (and 16 x to the rank) written into the hit records, so that chunks of a larger batch
  * produce globally indexed hits.  workspace (fr3d_classify_workspace(pair_cap) bytes, may be NULL): work lists
- * of the screen kernel; with it the call is three launches: a thread-per-pair screen of the cheap necessary
- * conditions, a thread-per-pair kernel for sO / sugar-ribose / BPh / BR on the pairs that passed, and the
- * warp-per-pair kernel for stacking / coplanar / basepair on the pairs that passed; without it one
- * warp-per-pair launch over all pairs. */
+ * of the screen kernel; with it the call is four launches: a thread-per-pair screen of the cheap necessary
+ * conditions of every rule family, then one thread-per-pair launch per work list (sO / sugar-ribose / BPh / BR;
+ * stacking; coplanar / basepair) over the pairs that passed; without it one warp-per-pair launch over all
+ * pairs. */
 size_t fr3d_classify_workspace(int64_t pair_cap);
 int fr3d_classify_pairs(const fr3d_nts_t *nts, const fr3d_box_t *boxes, const int32_t *box_index /*[25][2][2]*/,
                         const int32_t *pair_i, const int32_t *pair_j, const int32_t *pair_rank,
