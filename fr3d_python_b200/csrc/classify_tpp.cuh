@@ -56,8 +56,11 @@ __device__ __forceinline__ void tproject(const TFrame &f, double px, double py, 
     z = v0 * f.u2 + v1 * f.u5 + v2 * f.u8;
 }
 
-// return_overlap (NA:1530-1571): base atoms of nt_b seen from the frame of nt_a
-__device__ __forceinline__ bool t_overlap(const TFrame &fa, int par_a, const double *q, uint32_t bmb, double &zsel) {
+// return_overlap (NA:1530-1571): base atoms of nt_b seen from the frame of nt_a.  hull = the 7 half planes of
+// nt_a's parent ([7][3]); "inside" is an OR over the atoms, so the hull is only tested until the first atom is
+// in, and only for atoms inside the disc x^2 + y^2 < 16 that contains every hull (tests/test_abi.py).
+__device__ __forceinline__ bool t_overlap(const TFrame &fa, const double *hull, const double *q, uint32_t bmb,
+                                          double &zsel) {
     bool inside = false;
     double zmin = 1e300, zmax = -1e300, best = 1e300;
     zsel = 0.0;
@@ -66,7 +69,12 @@ __device__ __forceinline__ bool t_overlap(const TFrame &fa, int par_a, const dou
         if (!((bmb >> a) & 1u)) continue;
         double x, y, z;
         tproject(fa, q[a * 3], q[a * 3 + 1], q[a * 3 + 2], x, y, z);
-        if (in_hull(par_a, x, y, z)) inside = true;
+        if (!inside && fabs(z) < 4.5 && x * x + y * y < 16.0 + 1e-9) {
+            bool in = true;
+#pragma unroll
+            for (int k = 0; k < 7; ++k) in = in && left_of(hull + k * 3, x, y);
+            inside = in;
+        }
         if (fabs(z) < best) { best = fabs(z); zsel = z; }
         zmin = fmin(zmin, z);
         zmax = fmax(zmax, z);
@@ -304,10 +312,39 @@ __device__ __noinline__ double t_gap(const TFrame &fa, const TFrame &fb, int par
     return fmin(z0, fmin(z1, z2));
 }
 
-// calculate_base_min_distances (NA:1799-1829)
-__device__ __noinline__ double t_mind(const TFrame &f1, const TFrame &f2, int par1, int par2, const double *base1,
-                                      const double *base2, uint32_t bm1, uint32_t bm2, uint32_t tw1, uint32_t tw2) {
+// calculate_base_min_distances (NA:1799-1829).  REGS: the 16 points of nt2 are held in registers (an absent
+// atom sits at x = 1e150, so it can never be the minimum) and every point of nt1 is read once.
+template <bool REGS>
+__device__ __forceinline__ double t_mind(const TFrame &f1, const TFrame &f2, int par1, int par2, const double *base1,
+                                         const double *base2, uint32_t bm1, uint32_t bm2, uint32_t tw1, uint32_t tw2) {
     double best = 1e300;
+    if (REGS && !tw1 && !tw2) {
+        double q[FR3D_BASE_SLOTS * 3];
+#pragma unroll
+        for (int k = 0; k < FR3D_BASE_SLOTS; ++k) {
+            const bool have = (bm2 >> k) & 1u;
+            q[k * 3] = have ? base2[k * 3] : 1e150;
+            q[k * 3 + 1] = base2[k * 3 + 1];
+            q[k * 3 + 2] = base2[k * 3 + 2];
+        }
+        double b0 = 1e300, b1 = 1e300;
+#pragma unroll 1
+        for (int v = 0; v < FR3D_BASE_SLOTS; ++v) {
+            if (!((bm1 >> v) & 1u)) continue;
+            const double a0 = base1[v * 3], a1 = base1[v * 3 + 1], a2 = base1[v * 3 + 2];
+#pragma unroll
+            for (int k = 0; k < FR3D_BASE_SLOTS; k += 2) {
+                const double d0 = q[k * 3] - a0, d1 = q[k * 3 + 1] - a1, d2 = q[k * 3 + 2] - a2;
+                const double dd = d0 * d0 + d1 * d1 + d2 * d2;
+                if (dd < b0) b0 = dd;
+                const double e0 = q[k * 3 + 3] - a0, e1 = q[k * 3 + 4] - a1, e2 = q[k * 3 + 5] - a2;
+                const double ee = e0 * e0 + e1 * e1 + e2 * e2;
+                if (ee < b1) b1 = ee;
+            }
+        }
+        best = b1 < b0 ? b1 : b0;
+        return best < 1e299 ? sqrt(best) : 9999.0;
+    }
     const int nv1 = tw1 ? 32 : 16, nv2 = tw2 ? 32 : 16;
 #pragma unroll 1
     for (int v = 0; v < nv1; ++v) {
@@ -334,54 +371,75 @@ __device__ __noinline__ double t_mind(const TFrame &f1, const TFrame &f2, int pa
     return best < 1e299 ? sqrt(best) : 9999.0;
 }
 
-// One pass of check_basepair_cutoffs (NA:2546-2612) over the boxes of one orientation: L1 distance to every
-// box up to and including the angle term.  With `final` the gap term and the true / near classification
-// follow (NA:2642-2689) and the chosen box is returned; without it only "is any box still within 1.0".
+// check_basepair_cutoffs (NA:2546-2612) over the boxes of one orientation, in two passes.
 struct TBp {
     int box;        // chosen box or -1
     int near;       // bit0 "n" prefix, bit1 n-named box
     double cd;
 };
 
-__device__ __noinline__ bool t_boxes(const fr3d_box_t *__restrict__ boxes, int bstart, int bcount, double dX, double dY,
-                                     double dZ, double nZ, double M11, double M01, bool final, double gmax, double mind,
-                                     int pb, TBp &out) {
-    double ang = 0.0;
-    bool have_ang = false, any = false;
+// L1 distance of one box up to and including the normal term (NA:2546-2581), in the reference's summation order
+__device__ __forceinline__ double t_box_cd(const fr3d_box_t *bx, double dX, double dY, double dZ, double nZ) {
+    double cd = 0.0;
+    cd += fmax(0.0, bx->xmin - dX);
+    cd += fmax(0.0, dX - bx->xmax);
+    cd += fmax(0.0, bx->ymin - dY);
+    cd += fmax(0.0, dY - bx->ymax);
+    if (bx->flags & 8) cd += fmax(0.0, sqrt(dX * dX + dY * dY) - bx->radiusmax);
+    cd += fmax(0.0, bx->zmin - dZ);
+    cd += fmax(0.0, dZ - bx->zmax);
+    cd += 3.0 * fmax(0.0, bx->normalmin - nZ);
+    cd += 3.0 * fmax(0.0, nZ - bx->normalmax);
+    return cd;
+}
+
+// ... plus the angle term (NA:2594-2611)
+__device__ __forceinline__ double t_box_angle(const fr3d_box_t *bx, double cd, double ang) {
+    const double amin = bx->anglemin, amax = bx->anglemax;
+    if (amin < amax) {
+        cd += 0.05 * fmax(0.0, amin - ang);
+        cd += 0.05 * fmax(0.0, ang - amax);
+    } else {
+        cd += 0.05 * fmin(fmax(0.0, amin - ang), fmax(0.0, ang - amax));
+    }
+    return cd;
+}
+
+// Pass 1: bit b set <=> box bstart + b is still within 1.0 after the angle term (bcount <= 32, engine.BoxTable).
+// The angle is only computed if some box survives the displacement / normal terms, and is returned for pass 2.
+__device__ __forceinline__ unsigned t_boxes_live(const fr3d_box_t *__restrict__ boxes, int bstart, int bcount, double dX,
+                                                 double dY, double dZ, double nZ, double M11, double M01, double &ang) {
+    unsigned m = 0;
+#pragma unroll 2
+    for (int b = 0; b < bcount; ++b)
+        if (t_box_cd(boxes + bstart + b, dX, dY, dZ, nZ) < 1.0) m |= 1u << b;        // NA:2580
+    if (!m) return 0;
+    ang = atan2_once(M11, M01) * 57.29577951308232 - 90.0;                           // NA:2594
+    if (ang <= -90.0) ang += 360.0;
+    unsigned live = 0;
+    while (m) {
+        const int b = __ffs(m) - 1;
+        m &= m - 1;
+        const fr3d_box_t *bx = boxes + bstart + b;
+        if (t_box_angle(bx, t_box_cd(bx, dX, dY, dZ, nZ), ang) < 1.0) live |= 1u << b;   // NA:2611
+    }
+    return live;
+}
+
+// Pass 2 over the surviving boxes: gap term, true / near classification and the choice (NA:2642-2759)
+__device__ __forceinline__ void t_boxes_final(const fr3d_box_t *__restrict__ boxes, int bstart, unsigned live, double dX,
+                                              double dY, double dZ, double nZ, double ang, double gmax, double mind,
+                                              int pb, TBp &out) {
     int best_match = -1, best_near = -1;
     int match_key = 0x7FFFFFFF;
     double near_cd = 1e300, match_cd = 0.0;
     int match_flags = 0, near_flags = 0;
-#pragma unroll 1
-    for (int b = 0; b < bcount; ++b) {
+    while (live) {
+        const int b = __ffs(live) - 1;
+        live &= live - 1;
         const fr3d_box_t *bx = boxes + bstart + b;
-        double cd = 0.0;
-        cd += fmax(0.0, bx->xmin - dX);
-        cd += fmax(0.0, dX - bx->xmax);
-        cd += fmax(0.0, bx->ymin - dY);
-        cd += fmax(0.0, dY - bx->ymax);
+        double cd = t_box_angle(bx, t_box_cd(bx, dX, dY, dZ, nZ), ang);
         const int flags = bx->flags;
-        if (flags & 8) cd += fmax(0.0, sqrt(dX * dX + dY * dY) - bx->radiusmax);
-        cd += fmax(0.0, bx->zmin - dZ);
-        cd += fmax(0.0, dZ - bx->zmax);
-        cd += 3.0 * fmax(0.0, bx->normalmin - nZ);
-        cd += 3.0 * fmax(0.0, nZ - bx->normalmax);
-        if (!(cd < 1.0)) continue;                                   // NA:2580
-        if (!have_ang) {
-            ang = atan2_once(M11, M01) * 57.29577951308232 - 90.0;   // NA:2594
-            if (ang <= -90.0) ang += 360.0;
-            have_ang = true;
-        }
-        const double amin = bx->anglemin, amax = bx->anglemax;
-        if (amin < amax) {
-            cd += 0.05 * fmax(0.0, amin - ang);
-            cd += 0.05 * fmax(0.0, ang - amax);
-        } else {
-            cd += 0.05 * fmin(fmax(0.0, amin - ang), fmax(0.0, ang - amax));
-        }
-        if (!(cd < 1.0)) continue;                                   // NA:2611
-        any = true;
-        if (!final) return true;
         const double gapmax = bx->gapmax;
         if (gapmax > 0.1) cd += 4.0 * fmax(0.0, gmax - gapmax);      // NA:2643-2645
         bool one_hb = false;                                         // NA:2648-2652
@@ -405,7 +463,6 @@ __device__ __noinline__ bool t_boxes(const fr3d_box_t *__restrict__ boxes, int b
             if (cd < near_cd) { near_cd = cd; best_near = bstart + b; near_flags = flags; }
         }
     }
-    if (!final) return any;
     out.box = -1; out.near = 0; out.cd = 0.0;
     if (best_match >= 0) {
         out.box = best_match; out.cd = match_cd;
@@ -414,7 +471,6 @@ __device__ __noinline__ bool t_boxes(const fr3d_box_t *__restrict__ boxes, int b
         out.box = best_near; out.cd = near_cd;
         out.near = ((near_cd > 0 && !(near_flags & 1)) ? 1 : 0) | ((near_flags & 1) ? 2 : 0);
     }
-    return any;
 }
 
 #ifndef FR3D_TPP_MIN_BLOCKS
@@ -436,6 +492,10 @@ classify_pairs_tpp_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, 
                           fr3d_hit_t *__restrict__ hits, int64_t hit_cap, int64_t *counters,
                           const int32_t *__restrict__ worklist, int list_counter, int do_bp) {
     extern __shared__ double tpp_smem[];
+    __shared__ double s_hull[FR3D_N_PARENTS * 7 * 3];        // a per-lane parent index would serialise constant loads
+    for (int item = threadIdx.x; item < FR3D_N_PARENTS * 7 * 3; item += blockDim.x)
+        s_hull[item] = (&c_tab.hull[0][0][0])[item];
+    __syncthreads();
     constexpr int PSTRIDE = 2 * ROW_LEN + 1;                 // odd: lane k reads row k without bank conflicts
     const int lane = threadIdx.x & 31;
     double *rows = tpp_smem + (size_t)(threadIdx.x >> 5) * 32 * PSTRIDE;
@@ -523,8 +583,8 @@ classify_pairs_tpp_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, 
             bool stack_both = false;
             if ((cats & FR3D_CAT_STACKING) && par1 >= 0 && par2 >= 0) {
                 double z_2on1, z_1on2;
-                const bool nt2on1 = t_overlap(f1, par1, base2, bm2, z_2on1);
-                const bool nt1on2 = t_overlap(f2, par2, base1, bm1, z_1on2);
+                const bool nt2on1 = t_overlap(f1, s_hull + par1 * 21, base2, bm2, z_2on1);
+                const bool nt1on2 = t_overlap(f2, s_hull + par2 * 21, base1, bm1, z_1on2);
                 if ((nt2on1 || nt1on2) && !(fabs(nZ) < 0.5)) {
                     const bool reverse = nt1on2 && !nt2on1;
                     const double mvd = reverse ? z_1on2 : z_2on1;
@@ -560,6 +620,9 @@ classify_pairs_tpp_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, 
             unsigned ori_ok = 0, bp_live = 0;
             bool cp_frames = false;
             double gd0 = 0, gd1 = 0, gd2 = 0;
+            unsigned bx_live[2] = {0u, 0u};                  // surviving boxes, angle and displacement per orientation
+            int bx_start[2] = {0, 0};
+            double bx_ang[2] = {0.0, 0.0}, bx_d[2][3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
             if (gly_ok) {
                 if (c_tab.combo_ok[par1 * FR3D_N_PARENTS + par2]) ori_ok |= 1u;
                 if (c_tab.combo_ok[par2 * FR3D_N_PARENTS + par1]) ori_ok |= 2u;
@@ -572,7 +635,7 @@ classify_pairs_tpp_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, 
                 }
                 const double *g1 = base1, *g2 = base2;
                 gd0 = g2[0] - g1[0]; gd1 = g2[1] - g1[1]; gd2 = g2[2] - g1[2];
-#pragma unroll 1
+#pragma unroll
                 for (int ori = 0; ori < 2; ++ori) {
                     if (!((ori_ok >> ori) & 1u)) continue;
                     const TFrame &fa = ori ? f2 : f1;
@@ -589,9 +652,10 @@ classify_pairs_tpp_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, 
                     const int bcount = box_index[(combo * 2 + sg) * 2 + 1];
                     const double M11 = fa.u1 * fb.u1 + fa.u4 * fb.u4 + fa.u7 * fb.u7;
                     const double M01 = fa.u0 * fb.u1 + fa.u3 * fb.u4 + fa.u6 * fb.u7;
-                    TBp dummy;
-                    if (t_boxes(boxes, bstart, bcount, dX, dY, dZ, nZ, M11, M01, false, 0.0, 0.0, 0, dummy))
-                        bp_live |= 1u << ori;
+                    bx_live[ori] = t_boxes_live(boxes, bstart, bcount, dX, dY, dZ, nZ, M11, M01, bx_ang[ori]);
+                    bx_start[ori] = bstart;
+                    bx_d[ori][0] = dX; bx_d[ori][1] = dY; bx_d[ori][2] = dZ;
+                    if (bx_live[ori]) bp_live |= 1u << ori;
                 }
             }
             // ---- gaps / minimum distance, only when something can still use them
@@ -606,7 +670,7 @@ classify_pairs_tpp_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, 
                 }
                 const bool cp_gap = cp_frames && (((ori_ok & 1u) && gap12 < 1.5179) || ((ori_ok & 2u) && gap21 < 1.5179));
                 if (stack_code >= 0 || bp_live || cp_gap)
-                    mind = t_mind(f1, f2, par1, par2, base1, base2, bm1, bm2, tw1, tw2);
+                    mind = t_mind<(ROW_LEN > 0)>(f1, f2, par1, par2, base1, base2, bm1, bm2, tw1, tw2);
                 if (stack_code >= 0 && !(fabs(mind) < 1.0)) {                 // NA:1707-1718
                     int near = 1;
                     if (fabs(mind) < 4.0 && fabs(mind) > 1.0 && fabs(nZ) > 0.6 && stack_both) near = 0;
@@ -621,26 +685,11 @@ classify_pairs_tpp_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, 
                     const double gmax = fmax(gap12, gap21);
                     TBp res[2];
                     res[0].box = -1; res[1].box = -1; res[0].near = res[1].near = 0; res[0].cd = res[1].cd = 0.0;
-#pragma unroll 1
+#pragma unroll
                     for (int ori = 0; ori < 2; ++ori) {
                         if (!((bp_live >> ori) & 1u)) continue;
-                        const TFrame &fa = ori ? f2 : f1;
-                        const TFrame &fb = ori ? f1 : f2;
-                        const double s = ori ? -1.0 : 1.0;
-                        const double v0 = s * gd0, v1 = s * gd1, v2 = s * gd2;
-                        const double dZ = v0 * fa.u2 + v1 * fa.u5 + v2 * fa.u8;
-                        const double dX = v0 * fa.u0 + v1 * fa.u3 + v2 * fa.u6;
-                        const double dY = v0 * fa.u1 + v1 * fa.u4 + v2 * fa.u7;
-                        const int pb = ori ? par1 : par2;
-                        const int combo = ori ? par2 * FR3D_N_PARENTS + par1 : par1 * FR3D_N_PARENTS + par2;
-                        const int sg = nZ > 0 ? 0 : 1;
-                        const int bstart = box_index[(combo * 2 + sg) * 2 + 0];
-                        const int bcount = box_index[(combo * 2 + sg) * 2 + 1];
-                        const double M11 = fa.u1 * fb.u1 + fa.u4 * fb.u4 + fa.u7 * fb.u7;
-                        const double M01 = fa.u0 * fb.u1 + fa.u3 * fb.u4 + fa.u6 * fb.u7;
-                        TBp o;
-                        t_boxes(boxes, bstart, bcount, dX, dY, dZ, nZ, M11, M01, true, gmax, mind, pb, o);
-                        if (ori) res[1] = o; else res[0] = o;
+                        t_boxes_final(boxes, bx_start[ori], bx_live[ori], bx_d[ori][0], bx_d[ori][1], bx_d[ori][2], nZ,
+                                      bx_ang[ori], gmax, mind, ori ? par1 : par2, res[ori]);
                     }
                     int use = -1;                                             // NA:935-957
                     if (res[0].box >= 0 && res[1].box >= 0) {
