@@ -484,13 +484,17 @@ __host__ __device__ constexpr size_t tpp_smem_bytes() {
     return ROW_LEN ? sizeof(double) * (size_t)WARPS * 32 * (2 * ROW_LEN + 1) : 0;
 }
 
-template <int ROW_LEN, int WARPS, int MIN_BLOCKS>
+// CATS_CT / BP_CT: the rule families compiled into the instantiation (the run-time mask is ANDed with it), so the
+// kernel of one work list carries neither the code nor the registers of the other families.
+template <int ROW_LEN, int WARPS, int MIN_BLOCKS, uint32_t CATS_CT, bool BP_CT>
 __global__ void __launch_bounds__(WARPS * 32, MIN_BLOCKS)
 classify_pairs_tpp_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, const int32_t *__restrict__ box_index,
                           const int32_t *__restrict__ pair_i, const int32_t *__restrict__ pair_j,
                           const int32_t *__restrict__ pair_rank, int64_t pair_cap, uint32_t cats, int32_t index_offset,
                           fr3d_hit_t *__restrict__ hits, int64_t hit_cap, int64_t *counters,
-                          const int32_t *__restrict__ worklist, int list_counter, int do_bp) {
+                          const int32_t *__restrict__ worklist, int list_counter, int do_bp_rt) {
+    cats &= CATS_CT;
+    const bool do_bp = BP_CT && do_bp_rt;
     extern __shared__ double tpp_smem[];
     __shared__ double s_hull[FR3D_N_PARENTS * 7 * 3];        // a per-lane parent index would serialise constant loads
     for (int item = threadIdx.x; item < FR3D_N_PARENTS * 7 * 3; item += blockDim.x)

@@ -177,11 +177,14 @@ int fr3d_classify_pairs(const fr3d_nts_t *nts, const fr3d_box_t *boxes, const in
         const int tpp_grid = clampg((pair_cap + 127) / 128, tpp_grid_max);
         const uint32_t detail_cats = category_mask & (FR3D_CAT_SO | FR3D_CAT_SUGAR_RIBOSE | FR3D_CAT_BACKBONE);
         // staged thread-per-pair kernels: frame + base atoms (60 doubles per nt) for stacking / pairing, 7 warps per SM
-        auto tpp60 = fr3d::classify_pairs_tpp_kernel<60, 7, 1>;
-        auto tpp90 = fr3d::classify_pairs_tpp_kernel<90, 4, 1>;
-        auto tpp0 = fr3d::classify_pairs_tpp_kernel<0, 4, FR3D_TPP_MIN_BLOCKS>;
+        constexpr uint32_t DETAIL_CATS = FR3D_CAT_SO | FR3D_CAT_SUGAR_RIBOSE | FR3D_CAT_BACKBONE;
+        auto tpp_stack = fr3d::classify_pairs_tpp_kernel<60, 7, 1, FR3D_CAT_STACKING, false>;
+        auto tpp_pair = fr3d::classify_pairs_tpp_kernel<60, 7, 1, FR3D_CAT_COPLANAR, true>;
+        auto tpp90 = fr3d::classify_pairs_tpp_kernel<90, 4, 1, DETAIL_CATS, false>;
+        auto tpp0 = fr3d::classify_pairs_tpp_kernel<0, 4, 4, DETAIL_CATS, false>;
         constexpr size_t smem60 = fr3d::tpp_smem_bytes<60, 7>(), smem90 = fr3d::tpp_smem_bytes<90, 4>();
-        CUDA_TRY(cudaFuncSetAttribute(tpp60, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem60));
+        CUDA_TRY(cudaFuncSetAttribute(tpp_stack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem60));
+        CUDA_TRY(cudaFuncSetAttribute(tpp_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem60));
         CUDA_TRY(cudaFuncSetAttribute(tpp90, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem90));
         const int grid60 = clampg((pair_cap + 223) / 224, (long long)g_sm_count * (mult ? mult : 1));
         const int grid90 = clampg((pair_cap + 127) / 128, (long long)g_sm_count * (mult ? mult : 1));
@@ -201,14 +204,14 @@ int fr3d_classify_pairs(const fr3d_nts_t *nts, const fr3d_box_t *boxes, const in
                 category_mask & (FR3D_CAT_STACKING | FR3D_CAT_COPLANAR), index_offset, hits, hit_cap, counters, wl_stack);
         } else {
             if (category_mask & FR3D_CAT_STACKING)
-                tpp60<<<grid60, 224, smem60, st>>>(*nts, boxes, box_index, pair_i, pair_j, pair_rank, pair_cap,
-                                                   FR3D_CAT_STACKING, index_offset, hits, hit_cap, counters, wl_stack, 5, 0);
-            tpp60<<<grid60, 224, smem60, st>>>(*nts, boxes, box_index, pair_i, pair_j, pair_rank, pair_cap,
-                                               category_mask & FR3D_CAT_COPLANAR, index_offset, hits, hit_cap, counters,
-                                               wl_pair, 6, 1);
+                tpp_stack<<<grid60, 224, smem60, st>>>(*nts, boxes, box_index, pair_i, pair_j, pair_rank, pair_cap,
+                                                       FR3D_CAT_STACKING, index_offset, hits, hit_cap, counters, wl_stack, 5, 0);
+            tpp_pair<<<grid60, 224, smem60, st>>>(*nts, boxes, box_index, pair_i, pair_j, pair_rank, pair_cap,
+                                                  category_mask & FR3D_CAT_COPLANAR, index_offset, hits, hit_cap, counters,
+                                                  wl_pair, 6, 1);
         }
     } else if (use_mode == 1) {
-        fr3d::classify_pairs_tpp_kernel<0, 4, FR3D_TPP_MIN_BLOCKS><<<clampg((pair_cap + 127) / 128, tpp_grid_max), 128, 0, st>>>(
+        fr3d::classify_pairs_tpp_kernel<0, 4, FR3D_TPP_MIN_BLOCKS, 0xFFFFFFFFu, true><<<clampg((pair_cap + 127) / 128, tpp_grid_max), 128, 0, st>>>(
             *nts, boxes, box_index, pair_i, pair_j, pair_rank, pair_cap, category_mask, index_offset, hits, hit_cap,
             counters, nullptr, 0, 1);
     } else {

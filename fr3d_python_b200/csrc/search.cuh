@@ -9,7 +9,7 @@
 // are built with count -> allocate -> fill, and the search walks the
 // reference's 14-cell half stencil so that the ORIENTATION of every pair and
 // the visit-order rank (first nt seen in the cell of nt1, stencil index) are
-// the reference's own.  One warp per nt1; hits are compacted with a ballot
+// the reference's own.  One warp per nt1; hits are compacted with ballots
 // and one atomicAdd per warp.
 #pragma once
 
@@ -82,14 +82,23 @@ __global__ void cell_assign_kernel(fr3d_nts_t nts, SearchWs ws, double cell_size
     ws.cell_slot[n] = slot;
 }
 
+// member-list allocation: a warp scan of the cell counts and ONE atomicAdd per warp on the cursor
 __global__ void cell_offsets_kernel(SearchWs ws, int64_t *counters) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t <= ws.table_mask) {
-        const int c = ws.count[t];
-        if (c > 0) {
-            ws.start[t] = (int32_t)atomicAdd((unsigned long long *)&counters[3], (unsigned long long)c);
-        }
+    const int lane = threadIdx.x & 31;
+    const int c = (t <= ws.table_mask) ? ws.count[t] : 0;
+    int incl = c;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int v = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+        if (lane >= off) incl += v;
     }
+    const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+    if (!total) return;
+    long long base = 0;
+    if (lane == 31) base = (long long)atomicAdd((unsigned long long *)&counters[3], (unsigned long long)total);
+    base = __shfl_sync(0xFFFFFFFFu, base, 31);
+    if (c > 0) ws.start[t] = (int32_t)(base + incl - c);
 }
 
 __global__ void cell_fill_kernel(fr3d_nts_t nts, SearchWs ws) {
@@ -116,9 +125,16 @@ __device__ __forceinline__ int hash_find(const SearchWs &ws, unsigned long long 
 __constant__ int8_t c_half_stencil[14][3] = {{0, 0, 0}, {0, 0, 1}, {0, 1, 0}, {0, 1, 1}, {0, 1, -1}, {1, 0, 0}, {1, 0, 1},
                                              {1, 0, -1}, {1, 1, 0}, {1, 1, 1}, {1, 1, -1}, {1, -1, 0}, {1, -1, 1}, {1, -1, -1}};
 
+// One warp per nt1.  The 14 cube lookups (hash probe, count, start) are done by 14 lanes at once, the member
+// lists of the cubes are then walked as ONE concatenated candidate list in full chunks of 32, and the kept pairs
+// of up to SEARCH_CHUNKS chunks are appended with a single atomicAdd (the append cursor is one address: an atomic
+// per ballot made it the bottleneck of this kernel).
+constexpr int SEARCH_CHUNKS = 8;
+
 __global__ void __launch_bounds__(128)
 pair_search_kernel(fr3d_nts_t nts, SearchWs ws, double cutoff, int32_t *__restrict__ pair_i,
                    int32_t *__restrict__ pair_j, int32_t *__restrict__ pair_rank, int64_t pair_cap, int64_t *counters) {
+    constexpr unsigned ALL = 0xFFFFFFFFu;
     const int lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
     const int n1 = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
@@ -132,20 +148,42 @@ pair_search_kernel(fr3d_nts_t nts, SearchWs ws, double cutoff, int32_t *__restri
     const int cx = ws.cell_xyz[n1 * 3 + 0], cy = ws.cell_xyz[n1 * 3 + 1], cz = ws.cell_xyz[n1 * 3 + 2];
     const int first1 = ws.first[slot1];
 
-    for (int s = 0; s < 14; ++s) {
-        int slot2;
-        if (s == 0) slot2 = slot1;
-        else slot2 = hash_find(ws, cell_key(group, cx + c_half_stencil[s][0], cy + c_half_stencil[s][1],
-                                            cz + c_half_stencil[s][2]));
-        if (slot2 < 0) continue;                        // cube was never made (NA:663)
-        const int cnt = ws.count[slot2];
-        const int beg = ws.start[slot2];
-        for (int base = 0; base < cnt; base += 32) {
-            const int k = base + lane;
+    // lane s < 14: the cube of stencil entry s (a cube that was never made has no members, NA:663)
+    int cnt = 0, beg = 0;
+    if (lane < 14) {
+        const int slot2 = lane == 0 ? slot1
+                                    : hash_find(ws, cell_key(group, cx + c_half_stencil[lane][0],
+                                                             cy + c_half_stencil[lane][1], cz + c_half_stencil[lane][2]));
+        if (slot2 >= 0) { cnt = ws.count[slot2]; beg = ws.start[slot2]; }
+    }
+    int end = cnt;                                      // inclusive prefix: candidates [end - cnt, end) are cube s's
+#pragma unroll
+    for (int off = 1; off < 16; off <<= 1) {
+        const int v = __shfl_up_sync(ALL, end, off);
+        if (lane >= off) end += v;
+    }
+    const int total = __shfl_sync(ALL, end, 13);
+    const int shift = beg - (end - cnt);                // member index = candidate index + shift
+
+    for (int sb = 0; sb < total; sb += 32 * SEARCH_CHUNKS) {
+        int n2v[SEARCH_CHUNKS];
+        unsigned kept[SEARCH_CHUNKS];
+        unsigned spack = 0;                             // 4 bits per chunk: stencil entry of this lane's candidate
+        int nkept = 0;
+#pragma unroll
+        for (int c = 0; c < SEARCH_CHUNKS; ++c) {
+            kept[c] = 0;
+            n2v[c] = -1;
+            if (sb + c * 32 >= total) continue;         // warp uniform
+            const int k = sb + c * 32 + lane;
             bool keep = false;
-            int n2 = -1;
-            if (k < cnt) {
-                n2 = ws.members[beg + k];
+            int s = 0;
+#pragma unroll
+            for (int j = 0; j < 13; ++j) s += (k >= __shfl_sync(ALL, end, j)) ? 1 : 0;
+            const int sh = __shfl_sync(ALL, shift, s < 14 ? s : 13);
+            if (k < total) {
+                const int n2 = ws.members[k + sh];
+                n2v[c] = n2;
                 const int32_t *m2 = nts.meta + (size_t)n2 * FR3D_META_INTS;
                 keep = true;
                 if (s == 0) {                           // NA:684-688
@@ -165,21 +203,25 @@ pair_search_kernel(fr3d_nts_t nts, SearchWs ws, double cutoff, int32_t *__restri
                     }
                 }
             }
-            const unsigned ballot = __ballot_sync(0xFFFFFFFFu, keep);
-            if (ballot) {
-                long long basepos = 0;
-                if (lane == 0) basepos = (long long)atomicAdd((unsigned long long *)&counters[0],
-                                                              (unsigned long long)__popc(ballot));
-                basepos = __shfl_sync(0xFFFFFFFFu, basepos, 0);
-                if (keep) {
-                    const long long pos = basepos + __popc(ballot & ((1u << lane) - 1u));
-                    if (pos < pair_cap) {
-                        pair_i[pos] = n1;
-                        pair_j[pos] = n2;
-                        pair_rank[pos] = first1 * 16 + s;
-                    }
+            spack |= (unsigned)s << (4 * c);
+            kept[c] = __ballot_sync(ALL, keep);
+            nkept += __popc(kept[c]);
+        }
+        if (!nkept) continue;
+        long long basepos = 0;
+        if (lane == 0) basepos = (long long)atomicAdd((unsigned long long *)&counters[0], (unsigned long long)nkept);
+        basepos = __shfl_sync(ALL, basepos, 0);
+#pragma unroll
+        for (int c = 0; c < SEARCH_CHUNKS; ++c) {
+            if ((kept[c] >> lane) & 1u) {
+                const long long pos = basepos + __popc(kept[c] & ((1u << lane) - 1u));
+                if (pos < pair_cap) {
+                    pair_i[pos] = n1;
+                    pair_j[pos] = n2v[c];
+                    pair_rank[pos] = first1 * 16 + (int)((spack >> (4 * c)) & 15u);
                 }
             }
+            basepos += __popc(kept[c]);
         }
     }
 }
