@@ -1141,8 +1141,9 @@ BASEPAIR_COMBOS = set(['A,A', 'A,C', 'A,G', 'A,U', 'C,C', 'G,C', 'C,U', 'G,G', '
                        'A,DT', 'C,DT', 'G,DT', 'DT,DT'])     # NA:654
 
 
-def annotate(spec, categories, nts=None):
+def annotate(spec, categories, nts=None, focused=None):
     """annotate_nt_nt_in_structure (NA:1213-1243) + annotate_nt_nt_interactions (NA:635-1055).
+    focused: the focused_basepair_cutoffs argument of the reference (default: focused from the shipped tables).
 
     Returns (interaction_to_list_of_tuples, category_to_interactions, traces) where the
     tuples hold nt positions (index into spec["nts"]) instead of unit-id strings and
@@ -1150,7 +1151,8 @@ def annotate(spec, categories, nts=None):
     """
     if nts is None:
         nts = build_nts(spec)
-    focused = focus_basepair_cutoffs(nt_nt_cutoffs(), categories.get('basepair', []))
+    if focused is None:
+        focused = focus_basepair_cutoffs(nt_nt_cutoffs(), categories.get('basepair', []))
     pairs = candidate_pairs(nts)
     prevO3 = previous_O3_map(nts) if 'backbone' in categories else {}
     i2p = defaultdict(list)

@@ -20,9 +20,9 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-9
 
 
-def oracle_tuples(spec, categories):
+def oracle_tuples(spec, categories, focused=None):
     nts = O.build_nts(spec)
-    out, c2i, tr = O.annotate(spec, categories, nts)
+    out, c2i, tr = O.annotate(spec, categories, nts, focused=focused)
     res = {k: [(nts[a].unit_id(), nts[b].unit_id(), c) for a, b, c in v] for k, v in out.items() if v}
     return res, {k: set(v) for k, v in c2i.items() if v}, tr, nts
 
@@ -226,6 +226,43 @@ def test_dna_and_missing_atoms_against_oracle(golden):
     got = as_plain(NA.annotate_batch(spec, ALL9)[0])
     assert got == (want, wc)
     assert any("DT" in t[0] or "DT" in t[1] for v in want.values() for t in v)
+
+
+def _inflated_cutoffs(only_largest):
+    """focused_basepair_cutoffs with every subcategory box duplicated under a new subcategory key with shifted
+    limits: more than 16 boxes per (combination, sign) entry and - unless only the largest entry is inflated -
+    more than 256 boxes in total, which are the two table sizes the screen kernel treats differently."""
+    focused = copy.deepcopy(NA.focus_basepair_cutoffs(NA.nt_nt_cutoffs, []))
+    sizes = {(c, sg): sum(len(v) for v in focused[c][sg].values()) for c in focused for sg in focused[c]}
+    largest = max(sizes, key=sizes.get)
+    for c in focused:
+        for sg in focused[c]:
+            if only_largest and (c, sg) != largest:
+                continue
+            for inter, subs in focused[c][sg].items():
+                for sub in list(subs.keys()):
+                    box = dict(subs[sub])
+                    for k in ("xmin", "xmax", "ymin", "ymax"):
+                        box[k] = box[k] + 0.35
+                    box["gapmax"] = box.get("gapmax", 0.0) + 0.2
+                    subs[sub + 50] = box
+    return focused
+
+
+@pytest.mark.parametrize("only_largest", [True, False])
+def test_custom_cutoff_tables_against_oracle(golden, only_largest):
+    """Caller-supplied focused_basepair_cutoffs (the reference's third argument) with large tables."""
+    from fr3d_python_b200.engine import BoxTable
+    focused = _inflated_cutoffs(only_largest)
+    bt = BoxTable(focused)
+    assert bt.index[:, :, 1].max() > 16
+    assert (len(bt.boxes) > 256) == (not only_largest)
+    spec = golden("spec_1gid_full.json.gz")
+    want, wc, _, _ = oracle_tuples(spec, ALL9, focused=focused)
+    got = as_plain(NA.annotate_batch(spec, ALL9, focused_basepair_cutoffs=focused)[0])
+    assert got == (want, wc)
+    base_want, _, _, _ = oracle_tuples(spec, ALL9)
+    assert want != base_want                       # the inflated table really changes the annotation
 
 
 def test_observed_hydrogens_are_kept(golden):
