@@ -32,13 +32,20 @@ namespace fr3d {
 #define SCR_DETAIL (SCR_SO12 | SCR_SO21 | SCR_SR | SCR_BPH)
 #define SCR_GEOM (SCR_STACK | SCR_CP | SCR_BP)
 
-// Shared-memory row of one nt2 record (doubles): centre 0..2, rotation 3..11, base atoms 12..59, backbone slots
-// 1..6 (OP1 OP2 O5' O4' O3' O2') 60..77, backbone slot 9 (previous O3') 78..80.  The stride is odd so that "lane k
-// reads its own row" is bank-conflict free for 64-bit accesses.
-constexpr int SCR_ROW = 81;
-constexpr int SCR_STRIDE = 81;
-#define SCR_BB_OFF(slot) ((slot) == 9 ? 78 : 57 + (slot) * 3)
-constexpr int SCR_WARPS = 4;
+// Shared-memory row of one nt2 record (doubles), staged in two phases that re-use the same buffer so that twice as
+// many warps fit on an SM:
+//   phase A: centre 0..2, rotation 3..11, backbone slots 1..6 (OP1 OP2 O5' O4' O3' O2') 12..29, slot 9 (previous
+//            O3') 30..32                       -> sO, sugar-ribose, base-phosphate screens
+//   phase B: the 16 base points 0..47          -> stacking, coplanar / basepair screens
+// The stride is odd so that "lane k reads its own row" is bank-conflict free for 64-bit accesses.
+constexpr int SCR_ROW_A = 33;
+constexpr int SCR_ROW_B = 48;
+constexpr int SCR_STRIDE = 49;
+#define SCR_BB_OFF(slot) ((slot) == 9 ? 30 : 9 + (slot) * 3)
+#ifndef FR3D_SCR_WARPS
+#define FR3D_SCR_WARPS 16
+#endif
+constexpr int SCR_WARPS = FR3D_SCR_WARPS;
 constexpr int SCR_UBOX = FR3D_N_PARENTS * FR3D_N_PARENTS * 2;      // (combo, sign of nZ) entries
 constexpr int SCR_MAX_BOXES = 256;                                 // cutoff boxes kept in shared memory (else global)
 constexpr int SCR_BOX_STRIDE = 9;                                  // odd: lane b reads box b without bank conflicts
@@ -136,18 +143,14 @@ classify_screen_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, con
             sbox[(item >> 2) * SCR_BOX_STRIDE + (item & 3) * 2 + 1] = (float)(0.5 * (hi - lo));
         }
     __syncthreads();
-    // per-lane sources of the three copies that move one 90-double row
-    const double *src[3];
-    int mult[3];
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-        const int t = j * 32 + lane;
-        if (t < 3) { src[j] = nts.center + t; mult[j] = 3; }
-        else if (t < 12) { src[j] = nts.rot + (t - 3); mult[j] = 9; }
-        else if (t < 60) { src[j] = nts.base_xyz + (t - 12); mult[j] = FR3D_BASE_SLOTS * 3; }
-        else if (t < 78) { src[j] = nts.bb_xyz + (t - 60 + 3); mult[j] = FR3D_BB_SLOTS * 3; }
-        else { src[j] = nts.bb_xyz + (t - 78 + 27); mult[j] = FR3D_BB_SLOTS * 3; }
-    }
+    // per-lane sources of the copies that move one row (phase A: 32 + 1 doubles, phase B: 32 + 16)
+    const double *src_a0, *src_b0 = nts.base_xyz + lane, *src_b1 = nts.base_xyz + 32 + lane;
+    int mult_a0;
+    if (lane < 3) { src_a0 = nts.center + lane; mult_a0 = 3; }
+    else if (lane < 12) { src_a0 = nts.rot + (lane - 3); mult_a0 = 9; }
+    else if (lane < 30) { src_a0 = nts.bb_xyz + (lane - 12 + 3); mult_a0 = FR3D_BB_SLOTS * 3; }
+    else { src_a0 = nts.bb_xyz + (lane - 30 + 27); mult_a0 = FR3D_BB_SLOTS * 3; }
+    const double *src_a1 = nts.bb_xyz + 29;                                   // item 32: z of slot 9
     long long n_pairs = counters[0];
     if (n_pairs > pair_cap) n_pairs = pair_cap;
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -159,15 +162,15 @@ classify_screen_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, con
         const bool valid = p < n_pairs;
         if (!__any_sync(FULL, valid)) continue;
         const int n1 = valid ? pair_i[p] : 0, n2 = valid ? pair_j[p] : 0;
-        // stage the 32 nt2 records with coalesced asynchronous copies: row k belongs to lane k
+        // phase A: stage frame + backbone oxygens of the 32 nt2 records with coalesced asynchronous copies
+        // (row k belongs to lane k)
         __syncwarp();
 #pragma unroll 4
         for (int k = 0; k < 32; ++k) {
             const int nb = __shfl_sync(FULL, n2, k);
             double *dst = rows + k * SCR_STRIDE + lane;
-            cp_async8(dst, src[0] + (size_t)nb * mult[0]);
-            cp_async8(dst + 32, src[1] + (size_t)nb * mult[1]);
-            if (lane < SCR_ROW - 64) cp_async8(dst + 64, src[2] + (size_t)nb * mult[2]);
+            cp_async8(dst, src_a0 + (size_t)nb * mult_a0);
+            if (lane == 0) cp_async8(dst + 32, src_a1 + (size_t)nb * (FR3D_BB_SLOTS * 3));
         }
         unsigned fl = 0, live = 0;
         double dX0 = 0, dY0 = 0, dZ0 = 0, dX1 = 0, dY1 = 0, dZ1 = 0, nZ = 0;
@@ -180,21 +183,17 @@ classify_screen_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, con
         const double *A_bb = nts.bb_xyz + (size_t)n1 * FR3D_BB_SLOTS * 3;
         cp_async_wait_all();
         __syncwarp();
+        const double *R = rows + lane * SCR_STRIDE;
+        TFrame f2;
+        f2.c0 = f2.c1 = f2.c2 = f2.u0 = f2.u1 = f2.u2 = f2.u3 = f2.u4 = f2.u5 = f2.u6 = f2.u7 = f2.u8 = 0.0;
         if (valid) {
-            const double *R = rows + lane * SCR_STRIDE;
-            const double *B_base = R + 12, *B_bb = R + 57;      // B_bb[slot * 3 + c] for slots 1..6
-            TFrame f2;
+            const double *B_bb = R + 9;                         // B_bb[slot * 3 + c] for slots 1..6
             f2.c0 = R[0]; f2.c1 = R[1]; f2.c2 = R[2];
             f2.u0 = R[3]; f2.u1 = R[4]; f2.u2 = R[5]; f2.u3 = R[6]; f2.u4 = R[7]; f2.u5 = R[8];
             f2.u6 = R[9]; f2.u7 = R[10]; f2.u8 = R[11];
             if (cats & FR3D_CAT_SO) {
                 if (s_so_possible(f1, par1, B_bb, bb2)) fl |= SCR_SO12;
                 if (s_so_possible(f2, par2, A_bb, bb1)) fl |= SCR_SO21;
-            }
-            if ((cats & FR3D_CAT_STACKING) && par1 >= 0 && par2 >= 0) {
-                const unsigned c12 = s_cylinder_mask(f1, B_base) & bm2;
-                const unsigned c21 = s_cylinder_mask(f2, A_base) & bm1;
-                if (s_hull_any(f1, shull + par1 * 21, B_base, c12) || s_hull_any(f2, shull + par2 * 21, A_base, c21)) fl |= SCR_STACK;
             }
             if ((cats & FR3D_CAT_SUGAR_RIBOSE) && par1 >= 0 && par2 >= 0 && par1 != 4 && par2 != 4 &&
                 (bb1 >> 6 & 1u) && (bb2 >> 6 & 1u)) {
@@ -219,6 +218,25 @@ classify_screen_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, con
                     }
                 }
                 if (any) fl |= SCR_BPH;
+            }
+        }
+        // phase B: the base points of the 32 nt2 records take the place of the phase A rows
+        __syncwarp();
+#pragma unroll 4
+        for (int k = 0; k < 32; ++k) {
+            const int nb = __shfl_sync(FULL, n2, k);
+            double *dst = rows + k * SCR_STRIDE + lane;
+            cp_async8(dst, src_b0 + (size_t)nb * (FR3D_BASE_SLOTS * 3));
+            if (lane < SCR_ROW_B - 32) cp_async8(dst + 32, src_b1 + (size_t)nb * (FR3D_BASE_SLOTS * 3));
+        }
+        cp_async_wait_all();
+        __syncwarp();
+        if (valid) {
+            const double *B_base = R;
+            if ((cats & FR3D_CAT_STACKING) && par1 >= 0 && par2 >= 0) {
+                const unsigned c12 = s_cylinder_mask(f1, B_base) & bm2;
+                const unsigned c21 = s_cylinder_mask(f2, A_base) & bm1;
+                if (s_hull_any(f1, shull + par1 * 21, B_base, c12) || s_hull_any(f2, shull + par2 * 21, A_base, c21)) fl |= SCR_STACK;
             }
             if ((bm1 & 1u) && (bm2 & 1u) && par1 >= 0 && par2 >= 0) {
                 unsigned ori_ok = 0;

@@ -170,7 +170,7 @@ int fr3d_classify_pairs(const fr3d_nts_t *nts, const fr3d_box_t *boxes, const in
                                       (int)fr3d::SCR_SMEM));
         const int scr_threads = fr3d::SCR_WARPS * 32;
         fr3d::classify_screen_kernel<<<clampg((pair_cap + scr_threads - 1) / scr_threads,
-                                              (long long)g_sm_count * (mult ? mult : 2)),
+                                              (long long)g_sm_count * (mult ? mult : 1)),
                                        scr_threads, fr3d::SCR_SMEM, st>>>(
             *nts, boxes, box_index, pair_i, pair_j, pair_cap, category_mask, wl_detail, wl_stack, wl_pair,
             use_mode == 3 ? 1 : 0, counters);
