@@ -314,7 +314,8 @@ def main():
                 "gpu_launches": gpu_launches,
                 "kernel_ms": {"classify_pairs": classify_ms, "pair_search_5_kernels": search_ms,
                               "frames_fit_and_launch_gaps": ms_per_step - classify_ms - search_ms},
-                "roofline": {"kernel": "classify_pairs_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
+                "roofline": {"kernel": "fr3d_classify_pairs = classify_screen_kernel + 3 x classify_pairs_tpp_kernel "
+                                       "(detail / stacking / pairing work lists)", "bound": "hbm", "achieved": achieved, "peak": peak,
                              "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                              "algorithmic_bytes_per_pair": PAIR_BYTES, "model": "gather: 2 x 760 B nt records + 12 B "
                              "pair + 32 B hit slot per candidate pair"},

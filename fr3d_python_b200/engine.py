@@ -222,7 +222,10 @@ class Engine(object):
                                                     int(index_offset), plan.cws.data_ptr(), plan.cws_bytes,
                                                     plan.hits.data_ptr(), plan.hit_cap, plan.counters.data_ptr(), st),
                        "fr3d_classify_pairs")
-            self.launches += 4          # work-list memset + screen + detail + geometry kernels
+            # screen + one thread-per-pair kernel per work list (detail / stacking lists only if requested)
+            cm = int(category_mask)
+            self.launches += 2 + (1 if cm & (_lib.CAT_SO | _lib.CAT_SUGAR_RIBOSE | _lib.CAT_BACKBONE) else 0) + \
+                (1 if cm & _lib.CAT_STACKING else 0)
             if events is not None:
                 events["classify1"].record()
 
