@@ -108,7 +108,11 @@ class DeviceBatch(object):
         t = {}
         for name in ("center", "rot", "base_xyz", "bb_xyz", "base_mask", "bb_mask", "meta"):
             src = pinned[name] if pinned is not None else torch.from_numpy(_as_signed(getattr(batch, name)))
-            t[name] = src.to(device, non_blocking=True)
+            if name == "base_xyz" and src.shape[1] < _lib.BASE_SLOTS:       # compact pinned form, see pin_batch
+                t[name] = torch.zeros((batch.n, _lib.BASE_SLOTS, 3), dtype=src.dtype, device=device)
+                t[name][:, :src.shape[1]].copy_(src.to(device, non_blocking=True))
+            else:
+                t[name] = src.to(device, non_blocking=True)
         self.t = t
         self.nts = _lib.NtsStruct(n_nt=batch.n, reserved=0, center=t["center"].data_ptr(), rot=t["rot"].data_ptr(),
                                   base_xyz=t["base_xyz"].data_ptr(), bb_xyz=t["bb_xyz"].data_ptr(),
@@ -123,11 +127,21 @@ def _as_signed(a):
     return a
 
 
+HEAVY_SLOTS = 11        # the most heavy base atoms any parent has (G); slots from here on only ever hold hydrogens
+
+
 def pin_batch(torch, batch):
-    """Copy the batch into pinned host memory once (so timed H2D copies are DMA transfers)."""
+    """Copy the batch into pinned host memory once (so timed H2D copies are DMA transfers).
+
+    Hydrogens are normally not observed and are placed on the device by K1, so when no nt of the batch has an
+    atom in base slots 11..15 the pinned base plane keeps only slots 0..10 (264 instead of 384 bytes per nt go
+    over PCIe); the device record keeps all 16 slots."""
     out = {}
     for name in ("center", "rot", "base_xyz", "bb_xyz", "base_mask", "bb_mask", "meta"):
-        out[name] = torch.from_numpy(_as_signed(getattr(batch, name))).pin_memory()
+        a = _as_signed(getattr(batch, name))
+        if name == "base_xyz" and batch.n and not (batch.base_mask & np.uint32(0xF800)).any():
+            a = np.ascontiguousarray(a[:, :HEAVY_SLOTS])
+        out[name] = torch.from_numpy(a).pin_memory()
     return out
 
 
@@ -299,9 +313,13 @@ class Pipeline(object):
             ch = Plan()
             ch.lo, ch.hi, ch.n = lo, hi, n
             ch.stream = self.streams[k % len(self.streams)]
-            ch.dev = {name: torch.empty((n,) + tuple(getattr(batch, name).shape[1:]),
+            ch.dev = {name: torch.zeros((n,) + tuple(getattr(batch, name).shape[1:]),
                                         dtype=pinned[name].dtype, device=dev) for name in _FIELDS}
             t = ch.dev
+            ch.base_stage = None                  # compact pinned base plane: land here, then widen on the device
+            if pinned["base_xyz"].shape[1] < _lib.BASE_SLOTS:
+                ch.base_stage = torch.empty((n,) + tuple(pinned["base_xyz"].shape[1:]), dtype=pinned["base_xyz"].dtype,
+                                            device=dev)
             ch.nts = _lib.NtsStruct(n_nt=n, reserved=0, center=t["center"].data_ptr(), rot=t["rot"].data_ptr(),
                                     base_xyz=t["base_xyz"].data_ptr(), bb_xyz=t["bb_xyz"].data_ptr(),
                                     base_mask=t["base_mask"].data_ptr(), bb_mask=t["bb_mask"].data_ptr(),
@@ -332,7 +350,11 @@ class Pipeline(object):
                 for name in _FIELDS:
                     if name in ("center", "rot"):
                         continue
-                    ch.dev[name].copy_(self.pinned[name][ch.lo:ch.hi], non_blocking=True)
+                    if name == "base_xyz" and ch.base_stage is not None:
+                        ch.base_stage.copy_(self.pinned[name][ch.lo:ch.hi], non_blocking=True)
+                        ch.dev[name][:, :ch.base_stage.shape[1]].copy_(ch.base_stage, non_blocking=True)
+                    else:
+                        ch.dev[name].copy_(self.pinned[name][ch.lo:ch.hi], non_blocking=True)
                 eng.run_plan(ch, ch.plan, self.bt, self.mask, fit_frames=True, index_offset=ch.lo)
                 ch.counters_host.copy_(ch.plan.counters, non_blocking=True)
                 ch.ev.record(ch.stream)

@@ -348,17 +348,28 @@ def postprocess_subset(batch, hits, bt, atoms, which):
     return [postprocess.build_results(batch, s, hits[sidx == s], bt, atoms, ALL9) for s in which]
 
 
-def test_pipelined_path_equals_single_pass():
-    """engine.Pipeline (chunked, multi-stream, what bench.py's e2e times) returns the same hit set."""
+@pytest.mark.parametrize("observed_h", [False, True])
+def test_pipelined_path_equals_single_pass(observed_h):
+    """engine.Pipeline (chunked, multi-stream, what bench.py's e2e times) returns the same hit set; with and
+    without observed hydrogens (pin_batch uploads only base slots 0..10 when none is observed)."""
     import torch
-    from fr3d_python_b200.engine import Pipeline, pin_batch
+    from fr3d_python_b200.engine import HEAVY_SLOTS, Pipeline, pin_batch
     base = synthetic.pack_base()
     batch = synthetic.make_structure_batch(base, 37, seed0=900)
+    if observed_h:                       # give every 5th G an observed H22 (slot 15) displaced from the ideal spot
+        fitted = packing.select_structures(batch, range(batch.n_structures))
+        gframes.fit_batch_frames(fitted)
+        slot = defs.SLOT_OF["G"]["H22"]
+        assert slot >= HEAVY_SLOTS
+        gs = np.nonzero(batch.meta[:, 0] == defs.PARENTS.index("G"))[0][::5]
+        batch.base_xyz[gs, slot] = fitted.base_xyz[gs, slot] + 0.07
+        batch.base_mask[gs] |= np.uint32(1 << slot)
     eng = Engine.get()
     bt, atoms = NA._box_table(NA._default_focused(ALL9['basepair']), NA.load_ideal_basepair_hydrogen_bonds())
     mask = NA.category_mask(ALL9)
     hits, n_pairs, _ = eng.annotate_batch(batch, bt, mask)
     pinned = pin_batch(torch, batch)
+    assert pinned["base_xyz"].shape[1] == (16 if observed_h else HEAVY_SLOTS)
     for chunks in (1, 5, 37):
         pipe = Pipeline(eng, batch, pinned, bt, mask, n_chunks=chunks, pair_cap=n_pairs, hit_cap=len(hits))
         for _ in range(2):
