@@ -91,6 +91,19 @@ __device__ __forceinline__ double hb_angle(const double *A, const double *B, con
     return 180.0 * atan2_once(sinang, cosang) / 3.141592653589793;
 }
 
+// The same angle, but 0.0 (the reference's "no angle" value, which every caller skips) when it is certainly below
+// 107.4 degrees: cos >= 0, or sin > 3.2 |cos| (tan 72.6 deg = 3.2).  Every base-phosphate / base-ribose label needs
+// more than 110 degrees (NA:1947-1968), so the fp64 atan2 expansion only runs for the angles that can matter.
+__device__ __forceinline__ double hb_angle_if_wide(const double *A, const double *B, const double *C) {
+    const double u0 = A[0] - B[0], u1 = A[1] - B[1], u2 = A[2] - B[2];
+    const double w0 = C[0] - B[0], w1 = C[1] - B[1], w2 = C[2] - B[2];
+    const double cosang = u0 * w0 + u1 * w1 + u2 * w2;
+    const double x0 = u1 * w2 - u2 * w1, x1 = u2 * w0 - u0 * w2, x2 = u0 * w1 - u1 * w0;
+    const double sinang = sqrt(x0 * x0 + x1 * x1 + x2 * x2);
+    if (cosang >= 0.0 || sinang > 3.2 * (-cosang)) return 0.0;
+    return 180.0 * atan2_once(sinang, cosang) / 3.141592653589793;
+}
+
 __device__ __forceinline__ double dist3(const double *a, const double *b) {
     const double d0 = a[0] - b[0], d1 = a[1] - b[1], d2 = a[2] - b[2];
     return sqrt(d0 * d0 + d1 * d1 + d2 * d2);

@@ -197,7 +197,7 @@ __device__ __noinline__ int t_backbone(const TFrame &f1, int par1, const double 
                 const double d2 = q0 * q0 + q1 * q1 + q2 * q2;
                 if (!(d2 < 20.2501)) continue;                     // every label needs distance < 4.5
                 const double ds = sqrt(d2);
-                const double an = hb_angle(Mv, H, O);
+                const double an = hb_angle_if_wide(Mv, H, O);
                 if (!(an != 0.0 && ds != 0.0)) continue;
                 if (i < 4) {
                     if (an > 130.0 && ds < cutoff) {
@@ -297,6 +297,24 @@ __device__ __forceinline__ bool t_point(const TFrame &f, int par, const double *
 __device__ __noinline__ double t_gap(const TFrame &fa, const TFrame &fb, int par_b, const double *base_b,
                                      uint32_t bmb, uint32_t twb) {
     double k0 = 1e300, k1 = 1e300, k2 = 1e300, z0 = 100.0, z1 = 100.0, z2 = 100.0;
+    if (!twb) {
+        // no ideal-copy twins (the usual case): branch-free insertion into the three smallest keys; an absent atom
+        // gets key 1e300, which is never below the initial keys, so it changes nothing (the reference skips it)
+#pragma unroll 4
+        for (int v = 0; v < FR3D_BASE_SLOTS; ++v) {
+            const double w0 = base_b[v * 3] - fa.c0, w1 = base_b[v * 3 + 1] - fa.c1, w2 = base_b[v * 3 + 2] - fa.c2;
+            const double key = ((bmb >> v) & 1u) ? w0 * w0 + w1 * w1 + w2 * w2 : 1e300;
+            const double z = fabs(w0 * fa.u2 + w1 * fa.u5 + w2 * fa.u8);
+            const bool lt0 = key < k0, lt1 = key < k1, lt2 = key < k2;
+            k2 = lt1 ? k1 : (lt2 ? key : k2);
+            z2 = lt1 ? z1 : (lt2 ? z : z2);
+            k1 = lt0 ? k0 : (lt1 ? key : k1);
+            z1 = lt0 ? z0 : (lt1 ? z : z1);
+            k0 = lt0 ? key : k0;
+            z0 = lt0 ? z : z0;
+        }
+        return fmin(z0, fmin(z1, z2));
+    }
     const int nv = twb ? 32 : 16;
 #pragma unroll 1
     for (int v = 0; v < nv; ++v) {
@@ -379,12 +397,14 @@ struct TBp {
 };
 
 // L1 distance of one box up to and including the normal term (NA:2546-2581), in the reference's summation order
+// (every term is >= 0, so once the x / y terms reach 1.0 the box is out whatever follows: return early)
 __device__ __forceinline__ double t_box_cd(const fr3d_box_t *bx, double dX, double dY, double dZ, double nZ) {
     double cd = 0.0;
     cd += fmax(0.0, bx->xmin - dX);
     cd += fmax(0.0, dX - bx->xmax);
     cd += fmax(0.0, bx->ymin - dY);
     cd += fmax(0.0, dY - bx->ymax);
+    if (!(cd < 1.0)) return cd;
     if (bx->flags & 8) cd += fmax(0.0, sqrt(dX * dX + dY * dY) - bx->radiusmax);
     cd += fmax(0.0, bx->zmin - dZ);
     cd += fmax(0.0, dZ - bx->zmax);

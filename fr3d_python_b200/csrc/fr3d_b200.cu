@@ -76,6 +76,16 @@ int fr3d_init(int device) {
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     g_sm_count = prop.multiProcessorCount;
     if (prop.major < 10) return fail(FR3D_E_CUDA, "libfr3d_b200 is built for sm_100a only");
+    // opt in to the large dynamic shared-memory carve-outs once per device (not on every call)
+    constexpr uint32_t DETAIL_CATS = FR3D_CAT_SO | FR3D_CAT_SUGAR_RIBOSE | FR3D_CAT_BACKBONE;
+    CUDA_TRY(cudaFuncSetAttribute(fr3d::classify_screen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)fr3d::SCR_SMEM));
+    CUDA_TRY(cudaFuncSetAttribute(fr3d::classify_pairs_tpp_kernel<60, 7, 1, FR3D_CAT_STACKING, false>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fr3d::tpp_smem_bytes<60, 7>()));
+    CUDA_TRY(cudaFuncSetAttribute(fr3d::classify_pairs_tpp_kernel<60, 7, 1, FR3D_CAT_COPLANAR, true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fr3d::tpp_smem_bytes<60, 7>()));
+    CUDA_TRY(cudaFuncSetAttribute(fr3d::classify_pairs_tpp_kernel<90, 4, 1, DETAIL_CATS, false>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fr3d::tpp_smem_bytes<90, 4>()));
     return FR3D_OK;
 }
 
@@ -166,8 +176,6 @@ int fr3d_classify_pairs(const fr3d_nts_t *nts, const fr3d_box_t *boxes, const in
         int32_t *wl_stack = reinterpret_cast<int32_t *>(static_cast<char *>(workspace) + list_bytes);
         int32_t *wl_pair = reinterpret_cast<int32_t *>(static_cast<char *>(workspace) + 2 * list_bytes);
         CUDA_TRY(cudaMemsetAsync(counters + 4, 0, 4 * sizeof(int64_t), st));
-        CUDA_TRY(cudaFuncSetAttribute(fr3d::classify_screen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)fr3d::SCR_SMEM));
         const int scr_threads = fr3d::SCR_WARPS * 32;
         fr3d::classify_screen_kernel<<<clampg((pair_cap + scr_threads - 1) / scr_threads,
                                               (long long)g_sm_count * (mult ? mult : 1)),
@@ -183,9 +191,6 @@ int fr3d_classify_pairs(const fr3d_nts_t *nts, const fr3d_box_t *boxes, const in
         auto tpp90 = fr3d::classify_pairs_tpp_kernel<90, 4, 1, DETAIL_CATS, false>;
         auto tpp0 = fr3d::classify_pairs_tpp_kernel<0, 4, 4, DETAIL_CATS, false>;
         constexpr size_t smem60 = fr3d::tpp_smem_bytes<60, 7>(), smem90 = fr3d::tpp_smem_bytes<90, 4>();
-        CUDA_TRY(cudaFuncSetAttribute(tpp_stack, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem60));
-        CUDA_TRY(cudaFuncSetAttribute(tpp_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem60));
-        CUDA_TRY(cudaFuncSetAttribute(tpp90, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem90));
         const int grid60 = clampg((pair_cap + 223) / 224, (long long)g_sm_count * (mult ? mult : 1));
         const int grid90 = clampg((pair_cap + 127) / 128, (long long)g_sm_count * (mult ? mult : 1));
         static const int detail_staged = getenv("FR3D_DETAIL_STAGED") ? atoi(getenv("FR3D_DETAIL_STAGED")) : 0;

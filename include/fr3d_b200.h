@@ -139,7 +139,8 @@ typedef struct {
 /* ---- library ------------------------------------------------------------ */
 int fr3d_version(void);
 const char *fr3d_last_error(void);
-int fr3d_init(int device);
+int fr3d_init(int device);   /* REQUIRED once per process and device before any other call: selects the device,
+                                  checks sm_100, opts the kernels in to their shared-memory carve-outs */
 int fr3d_upload_tables(const fr3d_static_tables_t *host_tables);
 
 /* K1. Replaces Component.calculate_rotation_matrix (fr3d/data/components.py:273-349) +
