@@ -56,6 +56,8 @@ fr3d::SearchWs carve(void *workspace, int32_t n_nt) {
     ws.members = reinterpret_cast<int32_t *>(p); p += align_up(sizeof(int32_t) * (size_t)n_nt, 256);
     ws.cell_slot = reinterpret_cast<int32_t *>(p); p += align_up(sizeof(int32_t) * (size_t)n_nt, 256);
     ws.cell_xyz = reinterpret_cast<int32_t *>(p); p += align_up(sizeof(int32_t) * 3 * (size_t)n_nt, 256);
+    ws.cell_list = reinterpret_cast<int32_t *>(p); p += align_up(sizeof(int32_t) * (size_t)n_nt, 256);
+    ws.n_cells = reinterpret_cast<int32_t *>(p); p += 256;
     ws.table_mask = T - 1;
     return ws;
 }
@@ -113,9 +115,9 @@ size_t fr3d_pair_search_workspace(int32_t n_nt) {
     size_t b = 0;
     b += align_up(sizeof(unsigned long long) * T, 256);
     b += 4 * align_up(sizeof(int32_t) * T, 256);
-    b += 2 * align_up(sizeof(int32_t) * (size_t)n_nt, 256);
+    b += 3 * align_up(sizeof(int32_t) * (size_t)n_nt, 256);
     b += align_up(sizeof(int32_t) * 3 * (size_t)n_nt, 256);
-    return b + 256;
+    return b + 512;
 }
 
 int fr3d_pair_search(const fr3d_nts_t *nts, double cell_size, void *workspace, size_t workspace_bytes,
@@ -134,9 +136,12 @@ int fr3d_pair_search(const fr3d_nts_t *nts, double cell_size, void *workspace, s
     fr3d::cell_assign_kernel<<<(nts->n_nt + block - 1) / block, block, 0, st>>>(*nts, ws, cell_size, counters);
     fr3d::cell_offsets_kernel<<<(T + block - 1) / block, block, 0, st>>>(ws, counters);
     fr3d::cell_fill_kernel<<<(nts->n_nt + block - 1) / block, block, 0, st>>>(*nts, ws);
-    const int wpb = 4;
-    fr3d::pair_search_kernel<<<(nts->n_nt + wpb - 1) / wpb, wpb * 32, 0, st>>>(*nts, ws, cell_size, pair_i, pair_j,
-                                                                               pair_rank, pair_cap, counters);
+    // one warp per occupied cube; the cube count lives on the device, so size the grid for the worst case
+    // (a cube per nt) capped at a few resident waves - the kernel strides over the cube list
+    const long long want = ((long long)nts->n_nt + fr3d::SEARCH_WARPS - 1) / fr3d::SEARCH_WARPS;
+    const long long cap_blocks = (long long)g_sm_count * 32;
+    fr3d::pair_search_kernel<<<(int)(want < cap_blocks ? want : cap_blocks), fr3d::SEARCH_WARPS * 32, 0, st>>>(
+        *nts, ws, cell_size, pair_i, pair_j, pair_rank, pair_cap, counters);
     CUDA_TRY(cudaGetLastError());
     return FR3D_OK;
 }

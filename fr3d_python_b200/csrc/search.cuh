@@ -9,8 +9,8 @@
 // are built with count -> allocate -> fill, and the search walks the
 // reference's 14-cell half stencil so that the ORIENTATION of every pair and
 // the visit-order rank (first nt seen in the cell of nt1, stencil index) are
-// the reference's own.  One warp per nt1; hits are compacted with ballots
-// and one atomicAdd per warp.
+// the reference's own.  One warp per occupied cube; hits are compacted with
+// ballots and one atomicAdd per (nt1, segment).
 #pragma once
 
 #include "tables.cuh"
@@ -29,6 +29,8 @@ struct SearchWs {
     int32_t *members;          // [n]
     int32_t *cell_slot;        // [n] (-1: nt not in any cube)
     int32_t *cell_xyz;         // [n][3]
+    int32_t *cell_list;        // [n] table slots of the occupied cubes (any order)
+    int32_t *n_cells;          // [1]
     uint32_t table_mask;       // T - 1
 };
 
@@ -51,6 +53,7 @@ __global__ void search_reset_kernel(SearchWs ws) {
         ws.start[t] = 0;
         ws.cursor[t] = 0;
     }
+    if (t == 0) *ws.n_cells = 0;
 }
 
 // make_nt_cubes_half, NA:424-436: floor(coord / 12) in fp64, insert into the cube.
@@ -99,6 +102,12 @@ __global__ void cell_offsets_kernel(SearchWs ws, int64_t *counters) {
     if (lane == 31) base = (long long)atomicAdd((unsigned long long *)&counters[3], (unsigned long long)total);
     base = __shfl_sync(0xFFFFFFFFu, base, 31);
     if (c > 0) ws.start[t] = (int32_t)(base + incl - c);
+    // ... and the occupied cubes go on a compact list (the search runs one warp per cube)
+    const unsigned occ = __ballot_sync(0xFFFFFFFFu, c > 0);
+    int cbase = 0;
+    if (lane == 0) cbase = atomicAdd(ws.n_cells, __popc(occ));
+    cbase = __shfl_sync(0xFFFFFFFFu, cbase, 0);
+    if (c > 0) ws.cell_list[cbase + __popc(occ & ((1u << lane) - 1u))] = (int32_t)t;
 }
 
 __global__ void cell_fill_kernel(fr3d_nts_t nts, SearchWs ws) {
@@ -125,103 +134,156 @@ __device__ __forceinline__ int hash_find(const SearchWs &ws, unsigned long long 
 __constant__ int8_t c_half_stencil[14][3] = {{0, 0, 0}, {0, 0, 1}, {0, 1, 0}, {0, 1, 1}, {0, 1, -1}, {1, 0, 0}, {1, 0, 1},
                                              {1, 0, -1}, {1, 1, 0}, {1, 1, 1}, {1, 1, -1}, {1, -1, 0}, {1, -1, 1}, {1, -1, -1}};
 
-// One warp per nt1.  The 14 cube lookups (hash probe, count, start) are done by 14 lanes at once, the member
-// lists of the cubes are then walked as ONE concatenated candidate list in full chunks of 32, and the kept pairs
-// of up to SEARCH_CHUNKS chunks are appended with a single atomicAdd (the append cursor is one address: an atomic
-// per ballot made it the bottleneck of this kernel).
-constexpr int SEARCH_CHUNKS = 8;
+// One warp per occupied cube.  The 14 cube lookups of the half stencil (hash probe, count, start) are done once per
+// cube by 14 lanes, the member lists are concatenated into ONE candidate list, and the candidates' centre and
+// identity fields are staged in shared memory once; every nt1 of the cube then scans that list in full chunks of
+// 32 out of shared memory.  (One warp per nt1 repeated the probes and the gathers for each of the ~5 nts of a
+// cube, and an atomicAdd per ballot on the single append cursor made it atomic bound: 655 us -> 321 us -> this.)
+constexpr int SEARCH_CAP = 128;          // candidates staged per segment
+constexpr int SEARCH_CHUNKS = SEARCH_CAP / 32;
+constexpr int SEARCH_WARPS = 4;
 
-__global__ void __launch_bounds__(128)
+struct SearchStage {
+    double xyz[SEARCH_CAP][3];           // candidates (nt2)
+    int32_t n2[SEARCH_CAP];
+    int32_t chain[SEARCH_CAP], index[SEARCH_CAP], resid[SEARCH_CAP], alt[SEARCH_CAP];
+    uint8_t s[SEARCH_CAP];
+    double q_xyz[32][3];                 // a batch of up to 32 nt1 of the cube
+    int32_t q_n1[32], q_chain[32], q_index[32], q_resid[32], q_alt[32];
+    unsigned kept[32][SEARCH_CHUNKS];    // ballots of (nt1, chunk)
+};
+
+__global__ void __launch_bounds__(SEARCH_WARPS * 32)
 pair_search_kernel(fr3d_nts_t nts, SearchWs ws, double cutoff, int32_t *__restrict__ pair_i,
                    int32_t *__restrict__ pair_j, int32_t *__restrict__ pair_rank, int64_t pair_cap, int64_t *counters) {
     constexpr unsigned ALL = 0xFFFFFFFFu;
+    __shared__ SearchStage stage[SEARCH_WARPS];
+    SearchStage &S = stage[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
-    const int warps_per_block = blockDim.x >> 5;
-    const int n1 = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
-    if (n1 >= nts.n_nt) return;
-    const int slot1 = ws.cell_slot[n1];
-    if (slot1 < 0) return;                              // no base centre (NA:666)
-    if (!(nts.base_mask[n1] & 1u)) return;              // nt1 lacks its glycosidic atom (NA:674)
-    const int32_t *m1 = nts.meta + (size_t)n1 * FR3D_META_INTS;
-    const int group = m1[2], chain1 = m1[3], index1 = m1[4], resid1 = m1[5], alt1 = m1[6];
-    const double c1x = nts.center[n1 * 3 + 0], c1y = nts.center[n1 * 3 + 1], c1z = nts.center[n1 * 3 + 2];
-    const int cx = ws.cell_xyz[n1 * 3 + 0], cy = ws.cell_xyz[n1 * 3 + 1], cz = ws.cell_xyz[n1 * 3 + 2];
-    const int first1 = ws.first[slot1];
+    const int n_cells = *ws.n_cells;
+    const int warps_total = gridDim.x * SEARCH_WARPS;
+    for (int w = blockIdx.x * SEARCH_WARPS + (threadIdx.x >> 5); w < n_cells; w += warps_total) {
+        const int slot1 = ws.cell_list[w];
+        const int cnt1 = ws.count[slot1], beg1 = ws.start[slot1];
+        const int first1 = ws.first[slot1];
+        const int rep = ws.members[beg1];                   // any member: the cube's coordinates and group
+        const int cx = ws.cell_xyz[rep * 3 + 0], cy = ws.cell_xyz[rep * 3 + 1], cz = ws.cell_xyz[rep * 3 + 2];
+        const int group = nts.meta[(size_t)rep * FR3D_META_INTS + 2];
+        // lane s < 14: the cube of stencil entry s (a cube that was never made has no members, NA:663)
+        int cnt = 0, beg = 0;
+        if (lane < 14) {
+            const int slot2 = lane == 0 ? slot1
+                                        : hash_find(ws, cell_key(group, cx + c_half_stencil[lane][0],
+                                                                 cy + c_half_stencil[lane][1], cz + c_half_stencil[lane][2]));
+            if (slot2 >= 0) { cnt = ws.count[slot2]; beg = ws.start[slot2]; }
+        }
+        int end = cnt;                                      // inclusive prefix: candidates [end - cnt, end) are cube s's
+#pragma unroll
+        for (int off = 1; off < 16; off <<= 1) {
+            const int v = __shfl_up_sync(ALL, end, off);
+            if (lane >= off) end += v;
+        }
+        const int total = __shfl_sync(ALL, end, 13);
+        const int shift = beg - (end - cnt);                // member index = candidate index + shift
 
-    // lane s < 14: the cube of stencil entry s (a cube that was never made has no members, NA:663)
-    int cnt = 0, beg = 0;
-    if (lane < 14) {
-        const int slot2 = lane == 0 ? slot1
-                                    : hash_find(ws, cell_key(group, cx + c_half_stencil[lane][0],
-                                                             cy + c_half_stencil[lane][1], cz + c_half_stencil[lane][2]));
-        if (slot2 >= 0) { cnt = ws.count[slot2]; beg = ws.start[slot2]; }
-    }
-    int end = cnt;                                      // inclusive prefix: candidates [end - cnt, end) are cube s's
+        for (int m0 = 0; m0 < cnt1; m0 += 32) {
+            // a batch of nt1: lane l loads member m0 + l (n1 = -1: no glycosidic atom, NA:674)
+            const int mm = min(32, cnt1 - m0);
+            __syncwarp();
+            if (lane < mm) {
+                const int n1 = ws.members[beg1 + m0 + lane];
+                const int32_t *m1 = nts.meta + (size_t)n1 * FR3D_META_INTS;
+                S.q_n1[lane] = (nts.base_mask[n1] & 1u) ? n1 : -1;
+                S.q_chain[lane] = m1[3]; S.q_index[lane] = m1[4]; S.q_resid[lane] = m1[5]; S.q_alt[lane] = m1[6];
+                S.q_xyz[lane][0] = nts.center[(size_t)n1 * 3 + 0];
+                S.q_xyz[lane][1] = nts.center[(size_t)n1 * 3 + 1];
+                S.q_xyz[lane][2] = nts.center[(size_t)n1 * 3 + 2];
+            }
+            for (int sb = 0; sb < total; sb += SEARCH_CAP) {
+                const int seg = min(SEARCH_CAP, total - sb);
+                // stage the segment's candidates
+                __syncwarp();
+                for (int t0 = 0; t0 < seg; t0 += 32) {      // warp-uniform trip count: the shuffles need every lane
+                    const int t = t0 + lane;
+                    const int k = sb + t;
+                    int s = 0;
 #pragma unroll
-    for (int off = 1; off < 16; off <<= 1) {
-        const int v = __shfl_up_sync(ALL, end, off);
-        if (lane >= off) end += v;
-    }
-    const int total = __shfl_sync(ALL, end, 13);
-    const int shift = beg - (end - cnt);                // member index = candidate index + shift
-
-    for (int sb = 0; sb < total; sb += 32 * SEARCH_CHUNKS) {
-        int n2v[SEARCH_CHUNKS];
-        unsigned kept[SEARCH_CHUNKS];
-        unsigned spack = 0;                             // 4 bits per chunk: stencil entry of this lane's candidate
-        int nkept = 0;
-#pragma unroll
-        for (int c = 0; c < SEARCH_CHUNKS; ++c) {
-            kept[c] = 0;
-            n2v[c] = -1;
-            if (sb + c * 32 >= total) continue;         // warp uniform
-            const int k = sb + c * 32 + lane;
-            bool keep = false;
-            int s = 0;
-#pragma unroll
-            for (int j = 0; j < 13; ++j) s += (k >= __shfl_sync(ALL, end, j)) ? 1 : 0;
-            const int sh = __shfl_sync(ALL, shift, s < 14 ? s : 13);
-            if (k < total) {
-                const int n2 = ws.members[k + sh];
-                n2v[c] = n2;
-                const int32_t *m2 = nts.meta + (size_t)n2 * FR3D_META_INTS;
-                keep = true;
-                if (s == 0) {                           // NA:684-688
-                    const int chain2 = m2[3];
-                    if (chain1 > chain2) keep = false;
-                    else if (chain1 == chain2 && index1 > m2[4]) keep = false;
+                    for (int j = 0; j < 13; ++j) s += (k >= __shfl_sync(ALL, end, j)) ? 1 : 0;
+                    const int sh = __shfl_sync(ALL, shift, s);
+                    if (t < seg) {
+                        const int n2 = ws.members[k + sh];
+                        const int32_t *m2 = nts.meta + (size_t)n2 * FR3D_META_INTS;
+                        S.s[t] = (uint8_t)s;
+                        S.n2[t] = n2;
+                        S.chain[t] = m2[3]; S.index[t] = m2[4]; S.resid[t] = m2[5]; S.alt[t] = m2[6];
+                        S.xyz[t][0] = nts.center[(size_t)n2 * 3 + 0];
+                        S.xyz[t][1] = nts.center[(size_t)n2 * 3 + 1];
+                        S.xyz[t][2] = nts.center[(size_t)n2 * 3 + 2];
+                    }
                 }
-                if (keep) {
-                    const double dx = fabs(nts.center[n2 * 3 + 0] - c1x);
-                    const double dy = fabs(nts.center[n2 * 3 + 1] - c1y);
-                    const double dz = fabs(nts.center[n2 * 3 + 2] - c1z);
-                    if (dx > cutoff || dy > cutoff || dz > cutoff) keep = false;             // NA:699-702
-                    else if (resid1 == m2[5] && alt1 != m2[6]) keep = false;                 // NA:706-713
-                    else {
-                        const double d = sqrt(dx * dx + dy * dy + dz * dz);                  // NA:716
-                        if (d > cutoff || d < 2.0) keep = false;                             // NA:719-724
+                __syncwarp();
+                // pass 1: every nt1 of the batch scans the staged candidates; ballots go to shared memory
+                int nkept = 0;
+                for (int m = 0; m < mm; ++m) {
+                    const int n1 = S.q_n1[m];
+                    const int chain1 = S.q_chain[m], index1 = S.q_index[m], resid1 = S.q_resid[m], alt1 = S.q_alt[m];
+                    const double c1x = S.q_xyz[m][0], c1y = S.q_xyz[m][1], c1z = S.q_xyz[m][2];
+#pragma unroll
+                    for (int c = 0; c < SEARCH_CHUNKS; ++c) {
+                        if (c * 32 >= seg) {                 // warp uniform: no candidates in this chunk
+                            if (lane == 0) S.kept[m][c] = 0;
+                            continue;
+                        }
+                        const int t = c * 32 + lane;
+                        bool keep = false;
+                        if (n1 >= 0 && t < seg) {
+                            keep = true;
+                            if (S.s[t] == 0) {              // NA:684-688
+                                const int chain2 = S.chain[t];
+                                if (chain1 > chain2) keep = false;
+                                else if (chain1 == chain2 && index1 > S.index[t]) keep = false;
+                            }
+                            if (keep) {
+                                const double dx = fabs(S.xyz[t][0] - c1x);
+                                const double dy = fabs(S.xyz[t][1] - c1y);
+                                const double dz = fabs(S.xyz[t][2] - c1z);
+                                if (dx > cutoff || dy > cutoff || dz > cutoff) keep = false;         // NA:699-702
+                                else if (resid1 == S.resid[t] && alt1 != S.alt[t]) keep = false;     // NA:706-713
+                                else {
+                                    const double d = sqrt(dx * dx + dy * dy + dz * dz);              // NA:716
+                                    if (d > cutoff || d < 2.0) keep = false;                         // NA:719-724
+                                }
+                            }
+                        }
+                        const unsigned b = __ballot_sync(ALL, keep);
+                        if (lane == 0) S.kept[m][c] = b;
+                        nkept += __popc(b);
+                    }
+                }
+                if (!nkept) continue;
+                // one append for the whole (batch, segment), then pass 2 writes the pairs grouped by nt1
+                long long basepos = 0;
+                if (lane == 0) basepos = (long long)atomicAdd((unsigned long long *)&counters[0], (unsigned long long)nkept);
+                basepos = __shfl_sync(ALL, basepos, 0);
+                __syncwarp();
+                for (int m = 0; m < mm; ++m) {
+                    const int n1 = S.q_n1[m];
+#pragma unroll
+                    for (int c = 0; c < SEARCH_CHUNKS; ++c) {
+                        const unsigned b = S.kept[m][c];
+                        if ((b >> lane) & 1u) {
+                            const int t = c * 32 + lane;
+                            const long long pos = basepos + __popc(b & ((1u << lane) - 1u));
+                            if (pos < pair_cap) {
+                                pair_i[pos] = n1;
+                                pair_j[pos] = S.n2[t];
+                                pair_rank[pos] = first1 * 16 + (int)S.s[t];
+                            }
+                        }
+                        basepos += __popc(b);
                     }
                 }
             }
-            spack |= (unsigned)s << (4 * c);
-            kept[c] = __ballot_sync(ALL, keep);
-            nkept += __popc(kept[c]);
-        }
-        if (!nkept) continue;
-        long long basepos = 0;
-        if (lane == 0) basepos = (long long)atomicAdd((unsigned long long *)&counters[0], (unsigned long long)nkept);
-        basepos = __shfl_sync(ALL, basepos, 0);
-#pragma unroll
-        for (int c = 0; c < SEARCH_CHUNKS; ++c) {
-            if ((kept[c] >> lane) & 1u) {
-                const long long pos = basepos + __popc(kept[c] & ((1u << lane) - 1u));
-                if (pos < pair_cap) {
-                    pair_i[pos] = n1;
-                    pair_j[pos] = n2v[c];
-                    pair_rank[pos] = first1 * 16 + (int)((spack >> (4 * c)) & 15u);
-                }
-            }
-            basepos += __popc(kept[c]);
         }
     }
 }
