@@ -34,11 +34,12 @@ namespace fr3d {
 
 // Shared-memory row of one nt2 record (doubles), staged in two phases that re-use the same buffer so that twice as
 // many warps fit on an SM:
-//   phase A: centre 0..2, rotation 3..11, backbone slots 1..6 (OP1 OP2 O5' O4' O3' O2') 12..29, slot 9 (previous
-//            O3') 30..32                       -> sO, sugar-ribose, base-phosphate screens
+//   phase A: centre 0..2, rotation 3..11, backbone slots 1..6 (OP1 OP2 O5' O4' O3' O2') 12..29, x and y of slot 9
+//            (previous O3') 30..31 - exactly one copy instruction per row; z of slot 9 is loaded by the owning
+//            lane directly                     -> sO, sugar-ribose, base-phosphate screens
 //   phase B: the 16 base points 0..47          -> stacking, coplanar / basepair screens
 // The stride is odd so that "lane k reads its own row" is bank-conflict free for 64-bit accesses.
-constexpr int SCR_ROW_A = 33;
+constexpr int SCR_ROW_A = 32;
 constexpr int SCR_ROW_B = 48;
 constexpr int SCR_STRIDE = 49;
 #define SCR_BB_OFF(slot) ((slot) == 9 ? 30 : 9 + (slot) * 3)
@@ -143,14 +144,13 @@ classify_screen_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, con
             sbox[(item >> 2) * SCR_BOX_STRIDE + (item & 3) * 2 + 1] = (float)(0.5 * (hi - lo));
         }
     __syncthreads();
-    // per-lane sources of the copies that move one row (phase A: 32 + 1 doubles, phase B: 32 + 16)
+    // per-lane sources of the copies that move one row (phase A: 32 doubles, phase B: 32 + 16)
     const double *src_a0, *src_b0 = nts.base_xyz + lane, *src_b1 = nts.base_xyz + 32 + lane;
     int mult_a0;
     if (lane < 3) { src_a0 = nts.center + lane; mult_a0 = 3; }
     else if (lane < 12) { src_a0 = nts.rot + (lane - 3); mult_a0 = 9; }
     else if (lane < 30) { src_a0 = nts.bb_xyz + (lane - 12 + 3); mult_a0 = FR3D_BB_SLOTS * 3; }
     else { src_a0 = nts.bb_xyz + (lane - 30 + 27); mult_a0 = FR3D_BB_SLOTS * 3; }
-    const double *src_a1 = nts.bb_xyz + 29;                                   // item 32: z of slot 9
     long long n_pairs = counters[0];
     if (n_pairs > pair_cap) n_pairs = pair_cap;
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -170,8 +170,8 @@ classify_screen_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, con
             const int nb = __shfl_sync(FULL, n2, k);
             double *dst = rows + k * SCR_STRIDE + lane;
             cp_async8(dst, src_a0 + (size_t)nb * mult_a0);
-            if (lane == 0) cp_async8(dst + 32, src_a1 + (size_t)nb * (FR3D_BB_SLOTS * 3));
         }
+        const double prev_o3_z = nts.bb_xyz[(size_t)n2 * (FR3D_BB_SLOTS * 3) + 29];
         unsigned fl = 0, live = 0;
         double dX0 = 0, dY0 = 0, dZ0 = 0, dX1 = 0, dY1 = 0, dZ1 = 0, nZ = 0;
         int entry0 = 0, entry1 = 0;
@@ -213,7 +213,7 @@ classify_screen_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, con
                     for (int i = 0; i < 6; ++i) {
                         const int oslot = (0x469213 >> (4 * i)) & 15;
                         const double *O = R + SCR_BB_OFF(oslot);
-                        const double q0 = m0 - O[0], q1 = m1 - O[1], q2 = m2 - O[2];
+                        const double q0 = m0 - O[0], q1 = m1 - O[1], q2 = m2 - (oslot == 9 ? prev_o3_z : O[2]);
                         if (((bb2 >> oslot) & 1u) && (q0 * q0 + q1 * q1 + q2 * q2 < 20.2501)) any = true;
                     }
                 }
