@@ -54,7 +54,10 @@ class StaticTables(C.Structure):
                 ("n_sites", C.c_int32 * N_PARENTS),
                 ("site_h", C.c_int32 * 5 * N_PARENTS), ("site_m", C.c_int32 * 5 * N_PARENTS),
                 ("site_carbon", C.c_int32 * 5 * N_PARENTS), ("site_digit", C.c_int32 * 5 * N_PARENTS),
-                ("combo_ok", C.c_int32 * (N_PARENTS * N_PARENTS))]
+                ("combo_ok", C.c_int32 * (N_PARENTS * N_PARENTS)),
+                ("pad_tail", C.c_int32),
+                ("so_r2max", C.c_double * N_PARENTS),
+                ("hull_r2max", C.c_double * N_PARENTS)]
 
 
 _lock = threading.Lock()

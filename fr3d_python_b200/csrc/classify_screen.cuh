@@ -54,16 +54,17 @@ constexpr int SCR_HULL = FR3D_N_PARENTS * 7 * 3;
 constexpr int SCR_FIXED = SCR_UBOX * 8 + (SCR_MAX_BOXES * SCR_BOX_STRIDE + 1) / 2 + SCR_HULL + SCR_UBOX;   // doubles
 constexpr size_t SCR_SMEM = sizeof(double) * (SCR_FIXED + SCR_WARPS * 32 * SCR_STRIDE);
 
-// which atoms (bit per slot) of the 16 points q[0..47] lie in the cylinder |z| < 4.5, x^2 + y^2 < 16 of frame fa
-// (every hull lies inside that disc, tests/test_abi.py); converged, branch free
-__device__ __forceinline__ unsigned s_cylinder_mask(const TFrame &fa, const double *q) {
+// which atoms (bit per slot) of the 16 points q[0..47] lie in the cylinder |z| < 4.5, x^2 + y^2 < r2max of frame
+// fa (r2max = c_tab.hull_r2max[parent of fa]: the hull lies inside that disc, tests/test_abi.py); converged,
+// branch free
+__device__ __forceinline__ unsigned s_cylinder_mask(const TFrame &fa, const double *q, double r2max) {
     unsigned cand = 0;
 #pragma unroll
     for (int a = 0; a < FR3D_BASE_SLOTS; ++a) {
         const double v0 = q[a * 3] - fa.c0, v1 = q[a * 3 + 1] - fa.c1, v2 = q[a * 3 + 2] - fa.c2;
         const double z = v0 * fa.u2 + v1 * fa.u5 + v2 * fa.u8;
         const double r2 = (v0 * v0 + v1 * v1 + v2 * v2) - z * z;        // x^2 + y^2 (U is orthonormal)
-        if (fabs(z) < 4.5 && r2 < 16.0 + 1e-9) cand |= 1u << a;
+        if (fabs(z) < 4.5 && r2 < r2max) cand |= 1u << a;
     }
     return cand;
 }
@@ -84,8 +85,9 @@ __device__ __forceinline__ bool s_hull_any(const TFrame &fa, const double *hull,
     return any;
 }
 
-// any backbone oxygen (slots 1..6 of the row B) inside the slab / disc that contains every ring of fa's base?
-__device__ __forceinline__ bool s_so_possible(const TFrame &fa, int pa, const double *B, uint32_t bbb) {
+// any backbone oxygen (slots 1..6 of the row B) inside the slab / disc (r2max = c_tab.so_r2max[pa]) that contains
+// every ring and near-ring ellipse of fa's base?
+__device__ __forceinline__ bool s_so_possible(const TFrame &fa, int pa, const double *B, uint32_t bbb, double r2max) {
     if (pa < 0 || pa >= FR3D_N_PARENTS) return false;
     bool any = false;
 #pragma unroll
@@ -93,7 +95,7 @@ __device__ __forceinline__ bool s_so_possible(const TFrame &fa, int pa, const do
         const double v0 = B[oslot * 3] - fa.c0, v1 = B[oslot * 3 + 1] - fa.c1, v2 = B[oslot * 3 + 2] - fa.c2;
         const double z = v0 * fa.u2 + v1 * fa.u5 + v2 * fa.u8;
         const double r2 = (v0 * v0 + v1 * v1 + v2 * v2) - z * z;
-        any = any || (((bbb >> oslot) & 1u) && fabs(z) < 3.6 && r2 < 25.0 + 1e-9);
+        any = any || (((bbb >> oslot) & 1u) && fabs(z) < 3.6 && r2 < r2max);
     }
     return any;
 }
@@ -111,7 +113,13 @@ classify_screen_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, con
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double *rows = scr_smem + SCR_FIXED + warp * 32 * SCR_STRIDE;
     __shared__ int s_nboxes;
+    __shared__ double s_r2[2 * FR3D_N_PARENTS + 2];       // [parent + 1]: sO disc, then hull disc (index 0: no parent)
     if (threadIdx.x == 0) s_nboxes = 0;
+    if (threadIdx.x <= FR3D_N_PARENTS) {
+        const int p = (int)threadIdx.x - 1;
+        s_r2[threadIdx.x] = p < 0 ? 0.0 : c_tab.so_r2max[p] + 1e-9;
+        s_r2[FR3D_N_PARENTS + 1 + threadIdx.x] = p < 0 ? 0.0 : c_tab.hull_r2max[p] + 1e-9;
+    }
     __syncthreads();
     // prologue: the union of the cutoff boxes of every (combination, sign) entry.  A pair whose L1 excess over the
     // union box already reaches 1 cannot come within 1 of any single box (each box's excess is at least the union's).
@@ -192,8 +200,8 @@ classify_screen_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, con
             f2.u0 = R[3]; f2.u1 = R[4]; f2.u2 = R[5]; f2.u3 = R[6]; f2.u4 = R[7]; f2.u5 = R[8];
             f2.u6 = R[9]; f2.u7 = R[10]; f2.u8 = R[11];
             if (cats & FR3D_CAT_SO) {
-                if (s_so_possible(f1, par1, B_bb, bb2)) fl |= SCR_SO12;
-                if (s_so_possible(f2, par2, A_bb, bb1)) fl |= SCR_SO21;
+                if (s_so_possible(f1, par1, B_bb, bb2, s_r2[par1 + 1])) fl |= SCR_SO12;
+                if (s_so_possible(f2, par2, A_bb, bb1, s_r2[par2 + 1])) fl |= SCR_SO21;
             }
             if ((cats & FR3D_CAT_SUGAR_RIBOSE) && par1 >= 0 && par2 >= 0 && par1 != 4 && par2 != 4 &&
                 (bb1 >> 6 & 1u) && (bb2 >> 6 & 1u)) {
@@ -206,15 +214,25 @@ classify_screen_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, con
                 bool any = false;
 #pragma unroll 1
                 for (int s = 0; s < nsites; ++s) {
-                    const int ms = c_tab.site_m[par1][s];
-                    if (!((bm1 >> ms) & 1u)) continue;
+                    const int ms = c_tab.site_m[par1][s], hs = c_tab.site_h[par1][s];
+                    if (!((bm1 >> ms) & 1u) || !((bm1 >> hs) & 1u)) continue;        // NA:1937: both atoms needed
                     const double m0 = A_base[ms * 3], m1 = A_base[ms * 3 + 1], m2 = A_base[ms * 3 + 2];
 #pragma unroll
                     for (int i = 0; i < 6; ++i) {
                         const int oslot = (0x469213 >> (4 * i)) & 15;
                         const double *O = R + SCR_BB_OFF(oslot);
-                        const double q0 = m0 - O[0], q1 = m1 - O[1], q2 = m2 - (oslot == 9 ? prev_o3_z : O[2]);
-                        if (((bb2 >> oslot) & 1u) && (q0 * q0 + q1 * q1 + q2 * q2 < 20.2501)) any = true;
+                        const double o0 = O[0], o1 = O[1], o2 = (oslot == 9 ? prev_o3_z : O[2]);
+                        const double q0 = m0 - o0, q1 = m1 - o1, q2 = m2 - o2;
+                        if (((bb2 >> oslot) & 1u) && (q0 * q0 + q1 * q1 + q2 * q2 < 20.2501)) {
+                            // rare: every label also needs the angle massive-H-oxygen above 110 degrees; keep the
+                            // pair unless it is certainly below 107 (cos >= 0 or sin^2 > 10.3 cos^2, tan^2 72.7 = 10.3)
+                            const double h0 = A_base[hs * 3], h1 = A_base[hs * 3 + 1], h2 = A_base[hs * 3 + 2];
+                            const double u0 = m0 - h0, u1 = m1 - h1, u2 = m2 - h2;
+                            const double w0 = o0 - h0, w1 = o1 - h1, w2 = o2 - h2;
+                            const double cs = u0 * w0 + u1 * w1 + u2 * w2;
+                            const double x0 = u1 * w2 - u2 * w1, x1 = u2 * w0 - u0 * w2, x2 = u0 * w1 - u1 * w0;
+                            if (!(cs >= 0.0 || x0 * x0 + x1 * x1 + x2 * x2 > 10.3 * cs * cs)) any = true;
+                        }
                     }
                 }
                 if (any) fl |= SCR_BPH;
@@ -234,8 +252,8 @@ classify_screen_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, con
         if (valid) {
             const double *B_base = R;
             if ((cats & FR3D_CAT_STACKING) && par1 >= 0 && par2 >= 0) {
-                const unsigned c12 = s_cylinder_mask(f1, B_base) & bm2;
-                const unsigned c21 = s_cylinder_mask(f2, A_base) & bm1;
+                const unsigned c12 = s_cylinder_mask(f1, B_base, s_r2[FR3D_N_PARENTS + 2 + par1]) & bm2;
+                const unsigned c21 = s_cylinder_mask(f2, A_base, s_r2[FR3D_N_PARENTS + 2 + par2]) & bm1;
                 if (s_hull_any(f1, shull + par1 * 21, B_base, c12) || s_hull_any(f2, shull + par2 * 21, A_base, c21)) fl |= SCR_STACK;
             }
             if ((bm1 & 1u) && (bm2 & 1u) && par1 >= 0 && par2 >= 0) {

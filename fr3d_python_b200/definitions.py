@@ -101,9 +101,20 @@ def load_ideal_basepair_hydrogen_bonds():
     return _hbonds
 
 
+# Radii (Angstrom, about the base centre) of the discs the screen kernel uses as necessary conditions: every ring
+# polygon and near-ring ellipse of check_base_oxygen_stack_rings lies inside SCREEN_SO_RADIUS[parent], the convex
+# hull of check_convex_hull_atoms inside SCREEN_HULL_RADIUS[parent]; tests/test_abi.py proves both for the tables
+# that are shipped (the tight values are 2.73 2.07 3.00 2.05 2.01 and 3.50 3.25 3.84 2.79 2.83).
+SCREEN_SO_RADIUS = {'A': 2.80, 'C': 2.15, 'G': 3.05, 'U': 2.10, 'DT': 2.10}
+SCREEN_HULL_RADIUS = {'A': 3.55, 'C': 3.30, 'G': 3.90, 'U': 2.85, 'DT': 2.90}
+
+
 def static_tables():
     """Fill the fr3d_static_tables_t host struct."""
     t = _lib.StaticTables()
+    for p, parent in enumerate(PARENTS):
+        t.so_r2max[p] = SCREEN_SO_RADIUS[parent] ** 2
+        t.hull_r2max[p] = SCREEN_HULL_RADIUS[parent] ** 2
     for p, parent in enumerate(PARENTS):
         names = SLOT_NAMES[parent]
         # standard coordinates of a DNA/RNA parent: RNA tables for A C G U, DT for DT

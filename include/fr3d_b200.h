@@ -122,6 +122,11 @@ typedef struct {
     int32_t site_carbon[FR3D_N_PARENTS][5];/* 1: "C" in name, 0: "N" in name, -1 neither */
     int32_t site_digit[FR3D_N_PARENTS][5]; /* n of "nBPh"/"nBR" */
     int32_t combo_ok[FR3D_N_PARENTS * FR3D_N_PARENTS]; /* NA:654 */
+    int32_t pad_tail;
+    /* Screen discs (classify_screen.cuh), squared radii about the base centre: every ring and near-ring ellipse of
+     * the parent lies inside so_r2max, its convex hull inside hull_r2max (proved in tests/test_abi.py). */
+    double so_r2max[FR3D_N_PARENTS];
+    double hull_r2max[FR3D_N_PARENTS];
 } fr3d_static_tables_t;
 
 /* One basepair cutoff box (class_limits_2023.py after focus_basepair_cutoffs, NA:88-136). 128 B. */

@@ -8,6 +8,7 @@ import subprocess
 import sys
 
 import numpy as np
+import pytest
 
 from fr3d_python_b200 import _lib
 from fr3d_python_b200 import definitions as defs
@@ -70,12 +71,13 @@ def test_header_cites_reference_lines():
         assert needle in text
 
 
-def test_rings_and_ellipses_lie_inside_the_prefilter_disc():
-    """csrc/classify.cuh skips the ring / ellipse tests for oxygens with x^2 + y^2 >= 25: every ring
-    polygon and near-ring ellipse (convex) must lie strictly inside that disc.  A convex region with a
-    point inside the disc and no point on the circle is contained in the disc."""
+@pytest.mark.parametrize("per_parent", [False, True])
+def test_rings_and_ellipses_lie_inside_the_prefilter_disc(per_parent):
+    """csrc/classify_tpp.cuh skips the ring / ellipse tests for oxygens with x^2 + y^2 >= 25 and the screen kernel
+    uses the per-parent radius definitions.SCREEN_SO_RADIUS: every ring polygon and near-ring ellipse (convex)
+    must lie strictly inside that disc.  A convex region with a point inside the disc and no point on the
+    circle is contained in the disc."""
     ang = np.linspace(0, 2 * np.pi, 7200, endpoint=False)
-    cx, cy = 5.0 * np.cos(ang), 5.0 * np.sin(ang)
 
     def inside(lines, x, y):
         ok = np.ones_like(x, dtype=bool)
@@ -88,6 +90,8 @@ def test_rings_and_ellipses_lie_inside_the_prefilter_disc():
         return a * (x - ex) ** 2 + b * (x - ex) * (y - ey) + (y - ey) ** 2 < r
 
     for parent in defs.PARENTS:
+        radius = defs.SCREEN_SO_RADIUS[parent] if per_parent else 5.0
+        cx, cy = radius * np.cos(ang), radius * np.sin(ang)
         rings = defs.PLANES["rings"][parent]
         ell = defs.PLANES["ellipses"][parent]
         regions = []
@@ -107,12 +111,15 @@ def test_rings_and_ellipses_lie_inside_the_prefilter_disc():
                 assert in_ell(e, np.array([e[2]]), np.array([e[3]])).all()
 
 
-def test_hulls_lie_inside_the_screen_disc():
-    """csrc/classify_screen.cuh tests the hull half planes only for atoms with x^2 + y^2 < 16: every convex
-    hull of check_convex_hull_atoms (NA:1485-1523) must lie strictly inside that disc."""
+@pytest.mark.parametrize("per_parent", [False, True])
+def test_hulls_lie_inside_the_screen_disc(per_parent):
+    """The thread-per-pair kernels test the hull half planes only for atoms with x^2 + y^2 < 16, the screen kernel
+    uses the per-parent radius definitions.SCREEN_HULL_RADIUS: every convex hull of check_convex_hull_atoms
+    (NA:1485-1523) must lie strictly inside that disc."""
     ang = np.linspace(0, 2 * np.pi, 7200, endpoint=False)
-    cx, cy = 4.0 * np.cos(ang), 4.0 * np.sin(ang)
     for parent in defs.PARENTS:
+        radius = defs.SCREEN_HULL_RADIUS[parent] if per_parent else 4.0
+        cx, cy = radius * np.cos(ang), radius * np.sin(ang)
         ok = np.ones_like(cx, dtype=bool)
         inside0 = True
         for a, b, c in defs.PLANES["hull"][parent]:
