@@ -49,7 +49,7 @@ constexpr int SCR_STRIDE = 49;
 constexpr int SCR_WARPS = FR3D_SCR_WARPS;
 constexpr int SCR_UBOX = FR3D_N_PARENTS * FR3D_N_PARENTS * 2;      // (combo, sign of nZ) entries
 constexpr int SCR_MAX_BOXES = 256;                                 // cutoff boxes kept in shared memory (else global)
-constexpr int SCR_BOX_STRIDE = 9;                                  // odd: lane b reads box b without bank conflicts
+constexpr int SCR_BOX_STRIDE = 11;                                 // 10 floats per box; odd: lane b reads box b conflict free
 constexpr int SCR_HULL = FR3D_N_PARENTS * 7 * 3;
 constexpr int SCR_FIXED = SCR_UBOX * 8 + (SCR_MAX_BOXES * SCR_BOX_STRIDE + 1) / 2 + SCR_HULL + SCR_UBOX;   // doubles
 constexpr size_t SCR_SMEM = sizeof(double) * (SCR_FIXED + SCR_WARPS * 32 * SCR_STRIDE);
@@ -150,6 +150,10 @@ classify_screen_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, con
             const double lo = bx[(item & 3) * 2], hi = bx[(item & 3) * 2 + 1];
             sbox[(item >> 2) * SCR_BOX_STRIDE + (item & 3) * 2] = (float)(0.5 * (lo + hi));
             sbox[(item >> 2) * SCR_BOX_STRIDE + (item & 3) * 2 + 1] = (float)(0.5 * (hi - lo));
+            if ((item & 3) == 0) {                                  // the in-plane angle range (may wrap around)
+                sbox[(item >> 2) * SCR_BOX_STRIDE + 8] = (float)bx[8];
+                sbox[(item >> 2) * SCR_BOX_STRIDE + 9] = (float)bx[9];
+            }
         }
     __syncthreads();
     // per-lane sources of the copies that move one row (phase A: 32 doubles, phase B: 32 + 16)
@@ -182,6 +186,7 @@ classify_screen_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, con
         const double prev_o3_z = nts.bb_xyz[(size_t)n2 * (FR3D_BB_SLOTS * 3) + 29];
         unsigned fl = 0, live = 0;
         double dX0 = 0, dY0 = 0, dZ0 = 0, dX1 = 0, dY1 = 0, dZ1 = 0, nZ = 0;
+        float ang0 = 0.f, ang1 = 0.f;
         int entry0 = 0, entry1 = 0;
         const uint32_t bm1 = nts.base_mask[n1], bm2 = nts.base_mask[n2];
         const uint32_t bb1 = nts.bb_mask[n1], bb2 = nts.bb_mask[n2];
@@ -286,12 +291,21 @@ classify_screen_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, con
                     const double cd = fmax(0.0, ub[0] - dX) + fmax(0.0, dX - ub[1]) + fmax(0.0, ub[2] - dY) +
                                       fmax(0.0, dY - ub[3]) + fmax(0.0, ub[4] - dZ) + fmax(0.0, dZ - ub[5]) +
                                       3.0 * (fmax(0.0, ub[6] - nZ) + fmax(0.0, nZ - ub[7]));
-                    if (((ori_ok >> ori) & 1u) && !(fabs(dZ) > 3.6) && cd < 1.0 + 1e-9) live |= 1u << ori;   // NA:2380
+                    if (((ori_ok >> ori) & 1u) && !(fabs(dZ) > 3.6) && cd < 1.0 + 1e-9) {             // NA:2380
+                        live |= 1u << ori;
+                        // in-plane angle of this orientation (NA:2594), single precision is enough for the screen
+                        const TFrame &fb = ori ? f1 : f2;
+                        const float m11 = (float)(fa.u1 * fb.u1 + fa.u4 * fb.u4 + fa.u7 * fb.u7);
+                        const float m01 = (float)(fa.u0 * fb.u1 + fa.u3 * fb.u4 + fa.u6 * fb.u7);
+                        float ang = atan2f(m11, m01) * 57.29577951f - 90.f;
+                        if (ang <= -90.f) ang += 360.f;
+                        if (ori) ang1 = ang; else ang0 = ang;
+                    }
                 }
             }
         }
         // stage 2, warp cooperative: lane b evaluates box b of the entry of one live (pair, orientation) per step:
-        // some box within 1.0 before the angle term (NA:2546-2581)?  The angle and gap terms only add.
+        // some box within 1.0 up to and including the angle term (NA:2546-2611)?  The gap term only adds.
         unsigned pending = __ballot_sync(FULL, live != 0);
         while (pending) {
             // task of this lane's half warp (two_tasks) or of the whole warp
@@ -307,21 +321,27 @@ classify_screen_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, con
             const float tY = __shfl_sync(FULL, (float)(first_ori ? dY0 : dY1), from);
             const float tZ = __shfl_sync(FULL, (float)(first_ori ? dZ0 : dZ1), from);
             const float tN = __shfl_sync(FULL, (float)nZ, from);
+            const float tA = __shfl_sync(FULL, first_ori ? ang0 : ang1, from);
             const int te = __shfl_sync(FULL, first_ori ? entry0 : entry1, from);
             const int bstart = sidx[te * 2], bcount = srcl < 0 ? 0 : sidx[te * 2 + 1];
             bool hit = false;
             if (sub < bcount) {
-                float cd;
+                float cd, amin, amax;
                 if (boxes_in_smem) {
                     const float *bx = sbox + (bstart + sub) * SCR_BOX_STRIDE;
                     cd = fmaxf(0.f, fabsf(tX - bx[0]) - bx[1]) + fmaxf(0.f, fabsf(tY - bx[2]) - bx[3]) +
                          fmaxf(0.f, fabsf(tZ - bx[4]) - bx[5]) + 3.f * fmaxf(0.f, fabsf(tN - bx[6]) - bx[7]);
+                    amin = bx[8]; amax = bx[9];
                 } else {
                     const double *bx = reinterpret_cast<const double *>(boxes + bstart + sub);
                     cd = fmaxf(0.f, (float)bx[0] - tX) + fmaxf(0.f, tX - (float)bx[1]) + fmaxf(0.f, (float)bx[2] - tY) +
                          fmaxf(0.f, tY - (float)bx[3]) + fmaxf(0.f, (float)bx[4] - tZ) + fmaxf(0.f, tZ - (float)bx[5]) +
                          3.f * (fmaxf(0.f, (float)bx[6] - tN) + fmaxf(0.f, tN - (float)bx[7]));
+                    amin = (float)bx[8]; amax = (float)bx[9];
                 }
+                // the angle term (NA:2596-2611; ranges with amin > amax wrap around)
+                const float below = fmaxf(0.f, amin - tA), above = fmaxf(0.f, tA - amax);
+                cd += 0.05f * (amin < amax ? below + above : fminf(below, above));
                 hit = cd < 1.0f + 1e-3f;
             }
             const unsigned hits = __ballot_sync(FULL, hit);
