@@ -294,8 +294,8 @@ __device__ __forceinline__ bool t_point(const TFrame &f, int par, const double *
 
 // calculate_basepair_gap (NA:2189-2259): min |z| (frame of nt_a) over the 3 base atoms of nt_b nearest
 // to the centre of nt_a
-__device__ __noinline__ double t_gap(const TFrame &fa, const TFrame &fb, int par_b, const double *base_b,
-                                     uint32_t bmb, uint32_t twb) {
+__device__ __forceinline__ double t_gap_inline(const TFrame &fa, const TFrame &fb, int par_b, const double *base_b,
+                                               uint32_t bmb, uint32_t twb) {
     double k0 = 1e300, k1 = 1e300, k2 = 1e300, z0 = 100.0, z1 = 100.0, z2 = 100.0;
     if (!twb) {
         // no ideal-copy twins (the usual case): branch-free insertion into the three smallest keys; an absent atom
@@ -328,6 +328,12 @@ __device__ __noinline__ double t_gap(const TFrame &fa, const TFrame &fb, int par
         else if (key < k2) { k2 = key; z2 = z; }
     }
     return fmin(z0, fmin(z1, z2));
+}
+
+// out-of-line form (keeps the generic kernel's code size down)
+__device__ __noinline__ double t_gap(const TFrame &fa, const TFrame &fb, int par_b, const double *base_b,
+                                     uint32_t bmb, uint32_t twb) {
+    return t_gap_inline(fa, fb, par_b, base_b, bmb, twb);
 }
 
 // calculate_base_min_distances (NA:1799-1829).  REGS: the 16 points of nt2 are held in registers (an absent

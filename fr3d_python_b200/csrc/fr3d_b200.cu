@@ -16,6 +16,7 @@
 #include "classify_pm.cuh"
 #include "classify_tpp.cuh"
 #include "classify_screen.cuh"
+#include "classify_list2.cuh"
 #include "geometry.cuh"
 
 namespace {
@@ -86,6 +87,12 @@ int fr3d_init(int device) {
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fr3d::tpp_smem_bytes<60, 7>()));
     CUDA_TRY(cudaFuncSetAttribute(fr3d::classify_pairs_tpp_kernel<60, 7, 1, FR3D_CAT_COPLANAR, true>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fr3d::tpp_smem_bytes<60, 7>()));
+    CUDA_TRY(cudaFuncSetAttribute(fr3d::classify_list2_kernel<false, fr3d::L2_WARPS_STACK>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)fr3d::l2_smem_bytes<fr3d::L2_WARPS_STACK>()));
+    CUDA_TRY(cudaFuncSetAttribute(fr3d::classify_list2_kernel<true, fr3d::L2_WARPS_PAIR>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)fr3d::l2_smem_bytes<fr3d::L2_WARPS_PAIR>()));
     CUDA_TRY(cudaFuncSetAttribute(fr3d::classify_pairs_tpp_kernel<90, 4, 1, DETAIL_CATS, false>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fr3d::tpp_smem_bytes<90, 4>()));
     return FR3D_OK;
@@ -213,12 +220,31 @@ int fr3d_classify_pairs(const fr3d_nts_t *nts, const fr3d_box_t *boxes, const in
                 *nts, boxes, box_index, pair_i, pair_j, pair_rank, pair_cap,
                 category_mask & (FR3D_CAT_STACKING | FR3D_CAT_COPLANAR), index_offset, hits, hit_cap, counters, wl_stack);
         } else {
-            if (category_mask & FR3D_CAT_STACKING)
-                tpp_stack<<<grid60, 224, smem60, st>>>(*nts, boxes, box_index, pair_i, pair_j, pair_rank, pair_cap,
-                                                       FR3D_CAT_STACKING, index_offset, hits, hit_cap, counters, wl_stack, 5, 0);
-            tpp_pair<<<grid60, 224, smem60, st>>>(*nts, boxes, box_index, pair_i, pair_j, pair_rank, pair_cap,
-                                                  category_mask & FR3D_CAT_COPLANAR, index_offset, hits, hit_cap, counters,
-                                                  wl_pair, 6, 1);
+            // stacking and pairing lists: two-phase staged kernels (10 warps per SM); FR3D_LIST2=0 selects the
+            // single-phase instantiations (7 warps per SM) for comparison
+            static const int list2 = getenv("FR3D_LIST2") ? atoi(getenv("FR3D_LIST2")) : 1;
+            constexpr int ts = fr3d::L2_WARPS_STACK * 32, tp = fr3d::L2_WARPS_PAIR * 32;
+            const int grid_s = clampg((pair_cap + ts - 1) / ts, (long long)g_sm_count * (mult ? mult : 1));
+            const int grid_p = clampg((pair_cap + tp - 1) / tp, (long long)g_sm_count * (mult ? mult : 1));
+            if (category_mask & FR3D_CAT_STACKING) {
+                if (list2)
+                    fr3d::classify_list2_kernel<false, fr3d::L2_WARPS_STACK>
+                        <<<grid_s, ts, fr3d::l2_smem_bytes<fr3d::L2_WARPS_STACK>(), st>>>(
+                        *nts, boxes, box_index, pair_i, pair_j, pair_rank, pair_cap, FR3D_CAT_STACKING, index_offset, hits,
+                        hit_cap, counters, wl_stack, 5);
+                else
+                    tpp_stack<<<grid60, 224, smem60, st>>>(*nts, boxes, box_index, pair_i, pair_j, pair_rank, pair_cap,
+                                                           FR3D_CAT_STACKING, index_offset, hits, hit_cap, counters, wl_stack, 5, 0);
+            }
+            if (list2)
+                fr3d::classify_list2_kernel<true, fr3d::L2_WARPS_PAIR>
+                    <<<grid_p, tp, fr3d::l2_smem_bytes<fr3d::L2_WARPS_PAIR>(), st>>>(
+                    *nts, boxes, box_index, pair_i, pair_j, pair_rank, pair_cap, category_mask & FR3D_CAT_COPLANAR,
+                    index_offset, hits, hit_cap, counters, wl_pair, 6);
+            else
+                tpp_pair<<<grid60, 224, smem60, st>>>(*nts, boxes, box_index, pair_i, pair_j, pair_rank, pair_cap,
+                                                      category_mask & FR3D_CAT_COPLANAR, index_offset, hits, hit_cap, counters,
+                                                      wl_pair, 6, 1);
         }
     } else if (use_mode == 1) {
         fr3d::classify_pairs_tpp_kernel<0, 4, FR3D_TPP_MIN_BLOCKS, 0xFFFFFFFFu, true><<<clampg((pair_cap + 127) / 128, tpp_grid_max), 128, 0, st>>>(
