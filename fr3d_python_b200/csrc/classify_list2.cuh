@@ -95,16 +95,24 @@ classify_list2_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, cons
     const long long first = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long rounds = (n_pairs + stride - 1) / stride;
 
+    // the indices of a round are fetched one round ahead (list entry -> pair -> nt indices is a chain of
+    // dependent global loads that would otherwise sit in front of every staging step)
+    int nx1 = 0, nx2 = 0, nxr = 0;
+    if (first < n_pairs) {
+        const long long q = (long long)worklist[first];
+        nx1 = pair_i[q]; nx2 = pair_j[q]; nxr = pair_rank[q];
+    }
 #pragma unroll 1
     for (long long r = 0; r < rounds; ++r) {
         const long long p = first + r * stride;
         const bool active = p < n_pairs;
-        if (!__any_sync(FULL, active)) continue;
-        int n1 = 0, n2 = 0, rank = 0;
-        if (active) {
-            const long long q = (long long)worklist[p];
-            n1 = pair_i[q]; n2 = pair_j[q]; rank = pair_rank[q];
+        const int n1 = nx1, n2 = nx2, rank = nxr;
+        nx1 = 0; nx2 = 0; nxr = 0;
+        if (p + stride < n_pairs) {
+            const long long q = (long long)worklist[p + stride];
+            nx1 = pair_i[q]; nx2 = pair_j[q]; nxr = pair_rank[q];
         }
+        if (!__any_sync(FULL, active)) continue;
         // ---------------- phase A staging
         __syncwarp();                                       // everybody is done with the previous round's rows
 #pragma unroll 2

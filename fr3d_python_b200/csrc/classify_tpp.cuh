@@ -57,27 +57,36 @@ __device__ __forceinline__ void tproject(const TFrame &f, double px, double py, 
 }
 
 // return_overlap (NA:1530-1571): base atoms of nt_b seen from the frame of nt_a.  hull = the 7 half planes of
-// nt_a's parent ([7][3]); "inside" is an OR over the atoms, so the hull is only tested until the first atom is
-// in, and only for atoms inside the disc x^2 + y^2 < 16 that contains every hull (tests/test_abi.py).
+// nt_a's parent ([7][3]).  Pass 1 is branch free over all 16 slots: the height z of every atom (min / max /
+// closest to the plane) and a bit for the atoms inside the cylinder |z| < 4.5, x^2 + y^2 < 16 that contains every
+// hull (tests/test_abi.py).  "inside" is an OR over the atoms, so pass 2 runs the exact half-plane test on the
+// cylinder atoms only until the first one is in - a thread-per-pair warp pays for a branch if ANY lane takes it,
+// and on the stacking list that is one or two iterations instead of sixteen.
 __device__ __forceinline__ bool t_overlap(const TFrame &fa, const double *hull, const double *q, uint32_t bmb,
                                           double &zsel) {
-    bool inside = false;
     double zmin = 1e300, zmax = -1e300, best = 1e300;
+    unsigned cand = 0;
     zsel = 0.0;
 #pragma unroll 4
     for (int a = 0; a < FR3D_BASE_SLOTS; ++a) {
-        if (!((bmb >> a) & 1u)) continue;
+        const bool have = (bmb >> a) & 1u;
+        const double v0 = q[a * 3] - fa.c0, v1 = q[a * 3 + 1] - fa.c1, v2 = q[a * 3 + 2] - fa.c2;
+        const double z = v0 * fa.u2 + v1 * fa.u5 + v2 * fa.u8;                // the z of translate_rotate_point
+        const double r2 = (v0 * v0 + v1 * v1 + v2 * v2) - z * z;              // x^2 + y^2 (U is orthonormal)
+        if (have && fabs(z) < 4.5 && r2 < 16.0 + 1e-6) cand |= 1u << a;
+        if (have && fabs(z) < best) { best = fabs(z); zsel = z; }
+        if (have) { zmin = fmin(zmin, z); zmax = fmax(zmax, z); }
+    }
+    bool inside = false;
+    while (cand && !inside) {
+        const int a = __ffs(cand) - 1;
+        cand &= cand - 1;
         double x, y, z;
         tproject(fa, q[a * 3], q[a * 3 + 1], q[a * 3 + 2], x, y, z);
-        if (!inside && fabs(z) < 4.5 && x * x + y * y < 16.0 + 1e-9) {
-            bool in = true;
+        bool in = fabs(z) < 4.5;
 #pragma unroll
-            for (int k = 0; k < 7; ++k) in = in && left_of(hull + k * 3, x, y);
-            inside = in;
-        }
-        if (fabs(z) < best) { best = fabs(z); zsel = z; }
-        zmin = fmin(zmin, z);
-        zmax = fmax(zmax, z);
+        for (int k = 0; k < 7; ++k) in = in && left_of(hull + k * 3, x, y);
+        inside = in;
     }
     return inside && !(zmax > 0 && zmin < 0);
 }
