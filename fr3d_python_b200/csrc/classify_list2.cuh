@@ -22,8 +22,15 @@ namespace fr3d {
 
 constexpr int L2_ROW = 75;               // doubles per pair; odd: lane k reads row k without bank conflicts
 constexpr int L2_WARPS_STACK = 11, L2_WARPS_PAIR = 8;
-template <int WARPS>
-__host__ __device__ constexpr size_t l2_smem_bytes() { return sizeof(double) * (size_t)WARPS * 32 * L2_ROW; }
+// The pairing kernel also keeps the cutoff boxes in shared memory when there are at most L2_MAX_BOXES of them (the
+// shipped tables have 243): 16 doubles per box at a stride of 17 doubles, so that lanes reading the same field of
+// different boxes hit different banks.
+constexpr int L2_MAX_BOXES = 256;
+constexpr int L2_BOX_STRIDE = 17;
+template <bool PAIRING, int WARPS>
+__host__ __device__ constexpr size_t l2_smem_bytes() {
+    return sizeof(double) * ((size_t)WARPS * 32 * L2_ROW + (PAIRING ? L2_MAX_BOXES * L2_BOX_STRIDE : 0));
+}
 
 // the 16 points of a base into registers; an absent atom sits at x = 1e150 so it can never be the minimum
 __device__ __forceinline__ void t_mind_load(const double *base, uint32_t bm, double (&q)[FR3D_BASE_SLOTS * 3]) {
@@ -73,6 +80,27 @@ classify_list2_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, cons
     __syncthreads();
     const int lane = threadIdx.x & 31;
     double *rows = l2_smem + (size_t)(threadIdx.x >> 5) * 32 * L2_ROW;
+    // cutoff boxes: shared-memory copy (pairing kernel, small tables) or the caller's array
+    const char *box_base = reinterpret_cast<const char *>(boxes);
+    size_t box_stride = sizeof(fr3d_box_t);
+    if (PAIRING) {
+        __shared__ int s_nboxes;
+        if (threadIdx.x == 0) s_nboxes = 0;
+        __syncthreads();
+        if (threadIdx.x < FR3D_N_PARENTS * FR3D_N_PARENTS * 2) {
+            const int bstart = box_index[threadIdx.x * 2], bcount = box_index[threadIdx.x * 2 + 1];
+            if (bcount > 0) atomicMax(&s_nboxes, bstart + bcount);
+        }
+        __syncthreads();
+        if (s_nboxes <= L2_MAX_BOXES) {
+            double *sbox = l2_smem + (size_t)WARPS * 32 * L2_ROW;
+            for (int item = threadIdx.x; item < s_nboxes * 16; item += blockDim.x)
+                sbox[(item >> 4) * L2_BOX_STRIDE + (item & 15)] = reinterpret_cast<const double *>(boxes + (item >> 4))[item & 15];
+            box_base = reinterpret_cast<const char *>(sbox);
+            box_stride = sizeof(double) * L2_BOX_STRIDE;
+        }
+        __syncthreads();
+    }
     // per-lane sources of the three copies of a phase A row (item t = j * 32 + lane) and the two of a phase B row
     const double *src_a[3];
     int mult_a[3];
@@ -183,7 +211,7 @@ classify_list2_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, cons
                         const int bcount = box_index[(combo * 2 + sg) * 2 + 1];
                         const double M11 = fa.u1 * fb.u1 + fa.u4 * fb.u4 + fa.u7 * fb.u7;
                         const double M01 = fa.u0 * fb.u1 + fa.u3 * fb.u4 + fa.u6 * fb.u7;
-                        bx_live[ori] = t_boxes_live(boxes, bstart, bcount, dX, dY, dZ, nZ, M11, M01, bx_ang[ori]);
+                        bx_live[ori] = t_boxes_live(box_base, box_stride, bstart, bcount, dX, dY, dZ, nZ, M11, M01, bx_ang[ori]);
                         bx_start[ori] = bstart;
                         bx_d[ori][0] = dX; bx_d[ori][1] = dY; bx_d[ori][2] = dZ;
                         if (bx_live[ori]) bp_live |= 1u << ori;
@@ -264,7 +292,7 @@ classify_list2_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, cons
 #pragma unroll
                     for (int ori = 0; ori < 2; ++ori) {
                         if (!((bp_live >> ori) & 1u)) continue;
-                        t_boxes_final(boxes, bx_start[ori], bx_live[ori], bx_d[ori][0], bx_d[ori][1], bx_d[ori][2], nZ,
+                        t_boxes_final(box_base, box_stride, bx_start[ori], bx_live[ori], bx_d[ori][0], bx_d[ori][1], bx_d[ori][2], nZ,
                                       bx_ang[ori], gmax, mind, ori ? par1 : par2, res[ori]);
                     }
                     int use = -1;                                                 // NA:935-957

@@ -168,12 +168,16 @@ classify_screen_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, con
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long first = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long rounds = (n_pairs + stride - 1) / stride;
+    // the nt indices of a round are fetched one round ahead, so the staging below never waits for them
+    int nx1 = first < n_pairs ? pair_i[first] : 0, nx2 = first < n_pairs ? pair_j[first] : 0;
 #pragma unroll 1
     for (long long r = 0; r < rounds; ++r) {
         const long long p = first + r * stride;
         const bool valid = p < n_pairs;
+        const int n1 = nx1, n2 = nx2;
+        nx1 = p + stride < n_pairs ? pair_i[p + stride] : 0;
+        nx2 = p + stride < n_pairs ? pair_j[p + stride] : 0;
         if (!__any_sync(FULL, valid)) continue;
-        const int n1 = valid ? pair_i[p] : 0, n2 = valid ? pair_j[p] : 0;
         // phase A: stage frame + backbone oxygens of the 32 nt2 records with coalesced asynchronous copies
         // (row k belongs to lane k)
         __syncwarp();

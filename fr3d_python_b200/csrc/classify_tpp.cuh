@@ -442,12 +442,17 @@ __device__ __forceinline__ double t_box_angle(const fr3d_box_t *bx, double cd, d
 
 // Pass 1: bit b set <=> box bstart + b is still within 1.0 after the angle term (bcount <= 32, engine.BoxTable).
 // The angle is only computed if some box survives the displacement / normal terms, and is returned for pass 2.
-__device__ __forceinline__ unsigned t_boxes_live(const fr3d_box_t *__restrict__ boxes, int bstart, int bcount, double dX,
+// (boxes are addressed as box_base + index * box_stride so that a padded shared-memory copy can be used)
+__device__ __forceinline__ const fr3d_box_t *t_box_at(const char *box_base, size_t box_stride, int index) {
+    return reinterpret_cast<const fr3d_box_t *>(box_base + (size_t)index * box_stride);
+}
+
+__device__ __forceinline__ unsigned t_boxes_live(const char *box_base, size_t box_stride, int bstart, int bcount, double dX,
                                                  double dY, double dZ, double nZ, double M11, double M01, double &ang) {
     unsigned m = 0;
 #pragma unroll 2
     for (int b = 0; b < bcount; ++b)
-        if (t_box_cd(boxes + bstart + b, dX, dY, dZ, nZ) < 1.0) m |= 1u << b;        // NA:2580
+        if (t_box_cd(t_box_at(box_base, box_stride, bstart + b), dX, dY, dZ, nZ) < 1.0) m |= 1u << b;   // NA:2580
     if (!m) return 0;
     ang = atan2_once(M11, M01) * 57.29577951308232 - 90.0;                           // NA:2594
     if (ang <= -90.0) ang += 360.0;
@@ -455,14 +460,14 @@ __device__ __forceinline__ unsigned t_boxes_live(const fr3d_box_t *__restrict__ 
     while (m) {
         const int b = __ffs(m) - 1;
         m &= m - 1;
-        const fr3d_box_t *bx = boxes + bstart + b;
+        const fr3d_box_t *bx = t_box_at(box_base, box_stride, bstart + b);
         if (t_box_angle(bx, t_box_cd(bx, dX, dY, dZ, nZ), ang) < 1.0) live |= 1u << b;   // NA:2611
     }
     return live;
 }
 
 // Pass 2 over the surviving boxes: gap term, true / near classification and the choice (NA:2642-2759)
-__device__ __forceinline__ void t_boxes_final(const fr3d_box_t *__restrict__ boxes, int bstart, unsigned live, double dX,
+__device__ __forceinline__ void t_boxes_final(const char *box_base, size_t box_stride, int bstart, unsigned live, double dX,
                                               double dY, double dZ, double nZ, double ang, double gmax, double mind,
                                               int pb, TBp &out) {
     int best_match = -1, best_near = -1;
@@ -472,7 +477,7 @@ __device__ __forceinline__ void t_boxes_final(const fr3d_box_t *__restrict__ box
     while (live) {
         const int b = __ffs(live) - 1;
         live &= live - 1;
-        const fr3d_box_t *bx = boxes + bstart + b;
+        const fr3d_box_t *bx = t_box_at(box_base, box_stride, bstart + b);
         double cd = t_box_angle(bx, t_box_cd(bx, dX, dY, dZ, nZ), ang);
         const int flags = bx->flags;
         const double gapmax = bx->gapmax;
@@ -691,7 +696,8 @@ classify_pairs_tpp_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, 
                     const int bcount = box_index[(combo * 2 + sg) * 2 + 1];
                     const double M11 = fa.u1 * fb.u1 + fa.u4 * fb.u4 + fa.u7 * fb.u7;
                     const double M01 = fa.u0 * fb.u1 + fa.u3 * fb.u4 + fa.u6 * fb.u7;
-                    bx_live[ori] = t_boxes_live(boxes, bstart, bcount, dX, dY, dZ, nZ, M11, M01, bx_ang[ori]);
+                    bx_live[ori] = t_boxes_live(reinterpret_cast<const char *>(boxes), sizeof(fr3d_box_t), bstart, bcount, dX, dY, dZ, nZ,
+                                                M11, M01, bx_ang[ori]);
                     bx_start[ori] = bstart;
                     bx_d[ori][0] = dX; bx_d[ori][1] = dY; bx_d[ori][2] = dZ;
                     if (bx_live[ori]) bp_live |= 1u << ori;
@@ -727,7 +733,7 @@ classify_pairs_tpp_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, 
 #pragma unroll
                     for (int ori = 0; ori < 2; ++ori) {
                         if (!((bp_live >> ori) & 1u)) continue;
-                        t_boxes_final(boxes, bx_start[ori], bx_live[ori], bx_d[ori][0], bx_d[ori][1], bx_d[ori][2], nZ,
+                        t_boxes_final(reinterpret_cast<const char *>(boxes), sizeof(fr3d_box_t), bx_start[ori], bx_live[ori], bx_d[ori][0], bx_d[ori][1], bx_d[ori][2], nZ,
                                       bx_ang[ori], gmax, mind, ori ? par1 : par2, res[ori]);
                     }
                     int use = -1;                                             // NA:935-957

@@ -89,10 +89,10 @@ int fr3d_init(int device) {
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fr3d::tpp_smem_bytes<60, 7>()));
     CUDA_TRY(cudaFuncSetAttribute(fr3d::classify_list2_kernel<false, fr3d::L2_WARPS_STACK>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)fr3d::l2_smem_bytes<fr3d::L2_WARPS_STACK>()));
+                                  (int)fr3d::l2_smem_bytes<false, fr3d::L2_WARPS_STACK>()));
     CUDA_TRY(cudaFuncSetAttribute(fr3d::classify_list2_kernel<true, fr3d::L2_WARPS_PAIR>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)fr3d::l2_smem_bytes<fr3d::L2_WARPS_PAIR>()));
+                                  (int)fr3d::l2_smem_bytes<true, fr3d::L2_WARPS_PAIR>()));
     CUDA_TRY(cudaFuncSetAttribute(fr3d::classify_pairs_tpp_kernel<90, 4, 1, DETAIL_CATS, false>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fr3d::tpp_smem_bytes<90, 4>()));
     return FR3D_OK;
@@ -229,7 +229,7 @@ int fr3d_classify_pairs(const fr3d_nts_t *nts, const fr3d_box_t *boxes, const in
             if (category_mask & FR3D_CAT_STACKING) {
                 if (list2)
                     fr3d::classify_list2_kernel<false, fr3d::L2_WARPS_STACK>
-                        <<<grid_s, ts, fr3d::l2_smem_bytes<fr3d::L2_WARPS_STACK>(), st>>>(
+                        <<<grid_s, ts, fr3d::l2_smem_bytes<false, fr3d::L2_WARPS_STACK>(), st>>>(
                         *nts, boxes, box_index, pair_i, pair_j, pair_rank, pair_cap, FR3D_CAT_STACKING, index_offset, hits,
                         hit_cap, counters, wl_stack, 5);
                 else
@@ -238,7 +238,7 @@ int fr3d_classify_pairs(const fr3d_nts_t *nts, const fr3d_box_t *boxes, const in
             }
             if (list2)
                 fr3d::classify_list2_kernel<true, fr3d::L2_WARPS_PAIR>
-                    <<<grid_p, tp, fr3d::l2_smem_bytes<fr3d::L2_WARPS_PAIR>(), st>>>(
+                    <<<grid_p, tp, fr3d::l2_smem_bytes<true, fr3d::L2_WARPS_PAIR>(), st>>>(
                     *nts, boxes, box_index, pair_i, pair_j, pair_rank, pair_cap, category_mask & FR3D_CAT_COPLANAR,
                     index_offset, hits, hit_cap, counters, wl_pair, 6);
             else
