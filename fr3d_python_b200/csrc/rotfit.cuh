@@ -21,12 +21,12 @@ __device__ __forceinline__ void jacobi_rotate(double (&a)[4][4], double (&v)[4][
     const double apq = a[P][Q];
     if (apq == 0.0) return;
     const double app = a[P][P], aqq = a[Q][Q];
-    const double theta = (aqq - app) / (2.0 * apq);
-    // t = sgn(theta) / (|theta| + sqrt(theta^2 + 1)), stable for large theta
-    const double t = copysign(1.0, theta) / (fabs(theta) + sqrt(fma(theta, theta, 1.0)));
+    // t = sgn(theta) / (|theta| + sqrt(theta^2 + 1)) with theta = d / h, d = aqq - app, h = 2 apq, written as
+    // sgn(d) h / (|d| + sqrt(d^2 + h^2)): one division instead of two, no overflow for tiny apq
+    const double d = aqq - app, h = 2.0 * apq;
+    const double t = copysign(1.0, d) * h / (fabs(d) + sqrt(fma(d, d, h * h)));
     const double c = rsqrt(fma(t, t, 1.0));
     const double s = t * c;
-    const double tau = s / (1.0 + c);
     a[P][P] = app - t * apq;
     a[Q][Q] = aqq + t * apq;
     a[P][Q] = 0.0;
@@ -35,8 +35,8 @@ __device__ __forceinline__ void jacobi_rotate(double (&a)[4][4], double (&v)[4][
     for (int r = 0; r < 4; ++r) {
         if (r != P && r != Q) {
             const double arp = a[r][P], arq = a[r][Q];
-            const double np_ = arp - s * (arq + tau * arp);
-            const double nq_ = arq + s * (arp - tau * arq);
+            const double np_ = c * arp - s * arq;
+            const double nq_ = s * arp + c * arq;
             a[r][P] = np_; a[P][r] = np_;
             a[r][Q] = nq_; a[Q][r] = nq_;
         }
@@ -44,8 +44,8 @@ __device__ __forceinline__ void jacobi_rotate(double (&a)[4][4], double (&v)[4][
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
         const double vrp = v[r][P], vrq = v[r][Q];
-        v[r][P] = vrp - s * (vrq + tau * vrp);
-        v[r][Q] = vrq + s * (vrp - tau * vrq);
+        v[r][P] = c * vrp - s * vrq;
+        v[r][Q] = s * vrp + c * vrq;
     }
 }
 
