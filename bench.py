@@ -302,8 +302,8 @@ def main():
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, S),
                 "structures_per_s": S * world * args.steps / (ms_total / 1000.0),
                 "pairs_per_step": pairs_all, "hits_per_step": hits_all,
-                "worklists_rank0": {"detail_pairs": int(wl[4]), "stacking_pairs": int(wl[5]),
-                                    "pairing_pairs": int(wl[6])},
+                "worklists_rank0": {"light_detail_pairs": int(wl[4]), "stacking_pairs": int(wl[5]),
+                                    "pairing_pairs": int(wl[6]), "base_phosphate_pairs": int(wl[7])},
                 "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "structures_per_s": S * world * args.steps / t_e2e, "ms_per_step": 1000.0 * t_e2e / args.steps,
                         "what": "engine.Pipeline.run: pinned host nt records -> H2D -> K1..K4 -> D2H hit records, "
@@ -314,8 +314,8 @@ def main():
                 "gpu_launches": gpu_launches,
                 "kernel_ms": {"classify_pairs": classify_ms, "pair_search_5_kernels": search_ms,
                               "frames_fit_and_launch_gaps": ms_per_step - classify_ms - search_ms},
-                "roofline": {"kernel": "fr3d_classify_pairs = classify_screen_kernel + 3 x classify_pairs_tpp_kernel "
-                                       "(detail / stacking / pairing work lists)", "bound": "hbm", "achieved": achieved, "peak": peak,
+                "roofline": {"kernel": "fr3d_classify_pairs = classify_screen_kernel + 2 x classify_pairs_tpp_kernel + "
+                                       "2 x classify_list2_kernel (one launch per work list)", "bound": "hbm", "achieved": achieved, "peak": peak,
                              "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                              "algorithmic_bytes_per_pair": PAIR_BYTES, "model": "gather: 2 x 760 B nt records + 12 B "
                              "pair + 32 B hit slot per candidate pair"},

@@ -7,12 +7,12 @@
 // tails serialise the warp.  So the work is split: this kernel evaluates, one THREAD per pair and fully
 // converged, the cheap NECESSARY condition of every rule family (the same predicates the warp-per-pair
 // kernel votes on) and compacts the pairs that can still produce something into two work lists:
-//   detail list   -> classify_pairs_tpp_kernel  (sO, sugar-ribose, base-phosphate / base-ribose)
-//   stacking list -> classify_pairs_tpp_kernel  (base stacking)
-//   pairing list  -> classify_pairs_tpp_kernel  (coplanar, basepair)
-// Each list is homogeneous - nearly every pair on it runs the same rule to the end - so the thread-per-pair
-// kernel stays converged on it.  (FR3D_CLASSIFY_MODE=3 sends the union of the last two lists to the warp-per-pair
-// kernel classify_pairs_pm_kernel instead, for comparison.)
+//   light list    -> classify_pairs_tpp_kernel  (sO, sugar-ribose)
+//   phosphate list-> classify_pairs_tpp_kernel  (base-phosphate / base-ribose)
+//   stacking list -> classify_list2_kernel      (base stacking)
+//   pairing list  -> classify_list2_kernel      (coplanar, basepair)
+// Each list is homogeneous - nearly every pair on it runs the same rule to the end - so a thread-per-pair kernel
+// stays converged on it.
 // Every predicate is a superset of "this family yields a hit" (each rule is a conjunction), so results are
 // unchanged; tests/test_gpu_parity.py compares complete annotation sets with the reference.
 #pragma once
@@ -103,8 +103,8 @@ __device__ __forceinline__ bool s_so_possible(const TFrame &fa, int pa, const do
 __global__ void __launch_bounds__(SCR_WARPS * 32)
 classify_screen_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, const int32_t *__restrict__ box_index,
                        const int32_t *__restrict__ pair_i, const int32_t *__restrict__ pair_j, int64_t pair_cap,
-                       uint32_t cats, int32_t *__restrict__ wl_detail, int32_t *__restrict__ wl_stack,
-                       int32_t *__restrict__ wl_pair, int merge_geometry, int64_t *counters) {
+                       uint32_t cats, int32_t *__restrict__ wl_light, int32_t *__restrict__ wl_stack,
+                       int32_t *__restrict__ wl_pair, int32_t *__restrict__ wl_bph, int64_t *counters) {
     extern __shared__ double scr_smem[];
     double *ubox = scr_smem;                                                  // [SCR_UBOX][8] union boxes
     float *sbox = reinterpret_cast<float *>(ubox + SCR_UBOX * 8);             // [SCR_MAX_BOXES][SCR_BOX_STRIDE] mid, half
@@ -356,23 +356,26 @@ classify_screen_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, con
             }
             pending = __ballot_sync(FULL, live != 0);
         }
-        // warp-aggregated appends to the work lists: counters[4] detail, [5] stacking, [6] coplanar / basepair
-        // (merge_geometry: the union of the last two goes to the stacking list, for the warp-per-pair kernel)
-        const unsigned want_stack = merge_geometry ? (fl & SCR_GEOM) : (fl & SCR_STACK);
-        const unsigned want_pair = merge_geometry ? 0u : (fl & (SCR_CP | SCR_BP));
-        const unsigned bd = __ballot_sync(FULL, (fl & SCR_DETAIL) != 0);
+        // warp-aggregated appends to the work lists: counters[4] light detail (sO, sugar-ribose), [5] stacking,
+        // [6] coplanar / basepair, [7] base-phosphate
+        const unsigned want_light = fl & (SCR_SO12 | SCR_SO21 | SCR_SR), want_stack = fl & SCR_STACK,
+                       want_pair = fl & (SCR_CP | SCR_BP), want_bph = fl & SCR_BPH;
+        const unsigned bl = __ballot_sync(FULL, want_light != 0);
         const unsigned bs = __ballot_sync(FULL, want_stack != 0);
         const unsigned bp = __ballot_sync(FULL, want_pair != 0);
+        const unsigned bb = __ballot_sync(FULL, want_bph != 0);
         long long base = 0;
-        if (lane == 0 && bd) base = (long long)atomicAdd((unsigned long long *)&counters[4], (unsigned long long)__popc(bd));
+        if (lane == 0 && bl) base = (long long)atomicAdd((unsigned long long *)&counters[4], (unsigned long long)__popc(bl));
         if (lane == 1 && bs) base = (long long)atomicAdd((unsigned long long *)&counters[5], (unsigned long long)__popc(bs));
         if (lane == 2 && bp) base = (long long)atomicAdd((unsigned long long *)&counters[6], (unsigned long long)__popc(bp));
-        const long long base_d = __shfl_sync(FULL, base, 0), base_s = __shfl_sync(FULL, base, 1),
-                        base_p = __shfl_sync(FULL, base, 2);
+        if (lane == 3 && bb) base = (long long)atomicAdd((unsigned long long *)&counters[7], (unsigned long long)__popc(bb));
+        const long long base_l = __shfl_sync(FULL, base, 0), base_s = __shfl_sync(FULL, base, 1),
+                        base_p = __shfl_sync(FULL, base, 2), base_b = __shfl_sync(FULL, base, 3);
         const unsigned below = (1u << lane) - 1u;
-        if (fl & SCR_DETAIL) wl_detail[base_d + __popc(bd & below)] = (int32_t)p;
+        if (want_light) wl_light[base_l + __popc(bl & below)] = (int32_t)p;
         if (want_stack) wl_stack[base_s + __popc(bs & below)] = (int32_t)p;
         if (want_pair) wl_pair[base_p + __popc(bp & below)] = (int32_t)p;
+        if (want_bph) wl_bph[base_b + __popc(bb & below)] = (int32_t)p;
     }
 }
 

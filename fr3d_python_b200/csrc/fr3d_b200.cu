@@ -80,21 +80,14 @@ int fr3d_init(int device) {
     g_sm_count = prop.multiProcessorCount;
     if (prop.major < 10) return fail(FR3D_E_CUDA, "libfr3d_b200 is built for sm_100a only");
     // opt in to the large dynamic shared-memory carve-outs once per device (not on every call)
-    constexpr uint32_t DETAIL_CATS = FR3D_CAT_SO | FR3D_CAT_SUGAR_RIBOSE | FR3D_CAT_BACKBONE;
     CUDA_TRY(cudaFuncSetAttribute(fr3d::classify_screen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)fr3d::SCR_SMEM));
-    CUDA_TRY(cudaFuncSetAttribute(fr3d::classify_pairs_tpp_kernel<60, 7, 1, FR3D_CAT_STACKING, false>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fr3d::tpp_smem_bytes<60, 7>()));
-    CUDA_TRY(cudaFuncSetAttribute(fr3d::classify_pairs_tpp_kernel<60, 7, 1, FR3D_CAT_COPLANAR, true>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fr3d::tpp_smem_bytes<60, 7>()));
     CUDA_TRY(cudaFuncSetAttribute(fr3d::classify_list2_kernel<false, fr3d::L2_WARPS_STACK>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)fr3d::l2_smem_bytes<false, fr3d::L2_WARPS_STACK>()));
     CUDA_TRY(cudaFuncSetAttribute(fr3d::classify_list2_kernel<true, fr3d::L2_WARPS_PAIR>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)fr3d::l2_smem_bytes<true, fr3d::L2_WARPS_PAIR>()));
-    CUDA_TRY(cudaFuncSetAttribute(fr3d::classify_pairs_tpp_kernel<90, 4, 1, DETAIL_CATS, false>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fr3d::tpp_smem_bytes<90, 4>()));
     return FR3D_OK;
 }
 
@@ -155,7 +148,7 @@ int fr3d_pair_search(const fr3d_nts_t *nts, double cell_size, void *workspace, s
 
 size_t fr3d_classify_workspace(int64_t pair_cap) {
     if (pair_cap < 0) pair_cap = 0;
-    return 3 * align_up(sizeof(int32_t) * (size_t)pair_cap, 256) + 256;
+    return 4 * align_up(sizeof(int32_t) * (size_t)pair_cap, 256) + 256;
 }
 
 int fr3d_classify_pairs(const fr3d_nts_t *nts, const fr3d_box_t *boxes, const int32_t *box_index,
@@ -177,75 +170,49 @@ int fr3d_classify_pairs(const fr3d_nts_t *nts, const fr3d_box_t *boxes, const in
         mode = m ? atoi(m) : 2;
     }
     int use_mode = mode;
-    if ((use_mode == 2 || use_mode == 3) && (!workspace || workspace_bytes < fr3d_classify_workspace(pair_cap))) use_mode = 0;
+    if (use_mode == 2 && (!workspace || workspace_bytes < fr3d_classify_workspace(pair_cap))) use_mode = 0;
     const long long tpp_grid_max = (long long)g_sm_count * (mult ? mult : 4 * FR3D_TPP_MIN_BLOCKS);
     const long long pm_grid_max = (long long)g_sm_count * (mult ? mult : FR3D_CLASSIFY_MIN_BLOCKS);
     const long long per_block = (long long)fr3d::WARPS_PER_BLOCK * fr3d::PM_K;
     auto clampg = [](long long want, long long mx) { long long g = want < mx ? want : mx; return (int)(g < 1 ? 1 : g); };
-    if (use_mode == 2 || use_mode == 3) {
+    if (use_mode == 2) {
+        // work lists: counters[4] light detail (sO, sugar-ribose), [5] stacking, [6] pairing, [7] base-phosphate
         const size_t list_bytes = align_up(sizeof(int32_t) * (size_t)pair_cap, 256);
-        int32_t *wl_detail = static_cast<int32_t *>(workspace);
-        int32_t *wl_stack = reinterpret_cast<int32_t *>(static_cast<char *>(workspace) + list_bytes);
-        int32_t *wl_pair = reinterpret_cast<int32_t *>(static_cast<char *>(workspace) + 2 * list_bytes);
+        char *wsp = static_cast<char *>(workspace);
+        int32_t *wl_light = reinterpret_cast<int32_t *>(wsp);
+        int32_t *wl_stack = reinterpret_cast<int32_t *>(wsp + list_bytes);
+        int32_t *wl_pair = reinterpret_cast<int32_t *>(wsp + 2 * list_bytes);
+        int32_t *wl_bph = reinterpret_cast<int32_t *>(wsp + 3 * list_bytes);
         CUDA_TRY(cudaMemsetAsync(counters + 4, 0, 4 * sizeof(int64_t), st));
         const int scr_threads = fr3d::SCR_WARPS * 32;
         fr3d::classify_screen_kernel<<<clampg((pair_cap + scr_threads - 1) / scr_threads,
                                               (long long)g_sm_count * (mult ? mult : 1)),
                                        scr_threads, fr3d::SCR_SMEM, st>>>(
-            *nts, boxes, box_index, pair_i, pair_j, pair_cap, category_mask, wl_detail, wl_stack, wl_pair,
-            use_mode == 3 ? 1 : 0, counters);
+            *nts, boxes, box_index, pair_i, pair_j, pair_cap, category_mask, wl_light, wl_stack, wl_pair, wl_bph, counters);
+        // one thread-per-pair launch per list, each instantiation compiled with its own rule families only
         const int tpp_grid = clampg((pair_cap + 127) / 128, tpp_grid_max);
-        const uint32_t detail_cats = category_mask & (FR3D_CAT_SO | FR3D_CAT_SUGAR_RIBOSE | FR3D_CAT_BACKBONE);
-        // staged thread-per-pair kernels: frame + base atoms (60 doubles per nt) for stacking / pairing, 7 warps per SM
-        constexpr uint32_t DETAIL_CATS = FR3D_CAT_SO | FR3D_CAT_SUGAR_RIBOSE | FR3D_CAT_BACKBONE;
-        auto tpp_stack = fr3d::classify_pairs_tpp_kernel<60, 7, 1, FR3D_CAT_STACKING, false>;
-        auto tpp_pair = fr3d::classify_pairs_tpp_kernel<60, 7, 1, FR3D_CAT_COPLANAR, true>;
-        auto tpp90 = fr3d::classify_pairs_tpp_kernel<90, 4, 1, DETAIL_CATS, false>;
-        auto tpp0 = fr3d::classify_pairs_tpp_kernel<0, 4, 4, DETAIL_CATS, false>;
-        constexpr size_t smem60 = fr3d::tpp_smem_bytes<60, 7>(), smem90 = fr3d::tpp_smem_bytes<90, 4>();
-        const int grid60 = clampg((pair_cap + 223) / 224, (long long)g_sm_count * (mult ? mult : 1));
-        const int grid90 = clampg((pair_cap + 127) / 128, (long long)g_sm_count * (mult ? mult : 1));
-        static const int detail_staged = getenv("FR3D_DETAIL_STAGED") ? atoi(getenv("FR3D_DETAIL_STAGED")) : 0;
-        if (detail_cats) {
-            if (detail_staged)
-                tpp90<<<grid90, 128, smem90, st>>>(*nts, boxes, box_index, pair_i, pair_j, pair_rank, pair_cap, detail_cats,
-                                                   index_offset, hits, hit_cap, counters, wl_detail, 4, 0);
-            else
-                tpp0<<<tpp_grid, 128, 0, st>>>(*nts, boxes, box_index, pair_i, pair_j, pair_rank, pair_cap, detail_cats,
-                                               index_offset, hits, hit_cap, counters, wl_detail, 4, 0);
-        }
-        if (use_mode == 3) {
-            fr3d::classify_pairs_pm_kernel<<<clampg((pair_cap + per_block - 1) / per_block, pm_grid_max),
-                                             fr3d::WARPS_PER_BLOCK * 32, 0, st>>>(
-                *nts, boxes, box_index, pair_i, pair_j, pair_rank, pair_cap,
-                category_mask & (FR3D_CAT_STACKING | FR3D_CAT_COPLANAR), index_offset, hits, hit_cap, counters, wl_stack);
-        } else {
-            // stacking and pairing lists: two-phase staged kernels (10 warps per SM); FR3D_LIST2=0 selects the
-            // single-phase instantiations (7 warps per SM) for comparison
-            static const int list2 = getenv("FR3D_LIST2") ? atoi(getenv("FR3D_LIST2")) : 1;
-            constexpr int ts = fr3d::L2_WARPS_STACK * 32, tp = fr3d::L2_WARPS_PAIR * 32;
-            const int grid_s = clampg((pair_cap + ts - 1) / ts, (long long)g_sm_count * (mult ? mult : 1));
-            const int grid_p = clampg((pair_cap + tp - 1) / tp, (long long)g_sm_count * (mult ? mult : 1));
-            if (category_mask & FR3D_CAT_STACKING) {
-                if (list2)
-                    fr3d::classify_list2_kernel<false, fr3d::L2_WARPS_STACK>
-                        <<<grid_s, ts, fr3d::l2_smem_bytes<false, fr3d::L2_WARPS_STACK>(), st>>>(
-                        *nts, boxes, box_index, pair_i, pair_j, pair_rank, pair_cap, FR3D_CAT_STACKING, index_offset, hits,
-                        hit_cap, counters, wl_stack, 5);
-                else
-                    tpp_stack<<<grid60, 224, smem60, st>>>(*nts, boxes, box_index, pair_i, pair_j, pair_rank, pair_cap,
-                                                           FR3D_CAT_STACKING, index_offset, hits, hit_cap, counters, wl_stack, 5, 0);
-            }
-            if (list2)
-                fr3d::classify_list2_kernel<true, fr3d::L2_WARPS_PAIR>
-                    <<<grid_p, tp, fr3d::l2_smem_bytes<true, fr3d::L2_WARPS_PAIR>(), st>>>(
-                    *nts, boxes, box_index, pair_i, pair_j, pair_rank, pair_cap, category_mask & FR3D_CAT_COPLANAR,
-                    index_offset, hits, hit_cap, counters, wl_pair, 6);
-            else
-                tpp_pair<<<grid60, 224, smem60, st>>>(*nts, boxes, box_index, pair_i, pair_j, pair_rank, pair_cap,
-                                                      category_mask & FR3D_CAT_COPLANAR, index_offset, hits, hit_cap, counters,
-                                                      wl_pair, 6, 1);
-        }
+        constexpr uint32_t LIGHT_CATS = FR3D_CAT_SO | FR3D_CAT_SUGAR_RIBOSE;
+        if (category_mask & LIGHT_CATS)
+            fr3d::classify_pairs_tpp_kernel<0, 4, 4, LIGHT_CATS, false><<<tpp_grid, 128, 0, st>>>(
+                *nts, boxes, box_index, pair_i, pair_j, pair_rank, pair_cap, category_mask & LIGHT_CATS, index_offset, hits,
+                hit_cap, counters, wl_light, 4, 0);
+        if (category_mask & FR3D_CAT_BACKBONE)
+            fr3d::classify_pairs_tpp_kernel<0, 4, 4, FR3D_CAT_BACKBONE, false><<<tpp_grid, 128, 0, st>>>(
+                *nts, boxes, box_index, pair_i, pair_j, pair_rank, pair_cap, FR3D_CAT_BACKBONE, index_offset, hits,
+                hit_cap, counters, wl_bph, 7, 0);
+        // stacking and pairing lists: records staged in shared memory in two phases (classify_list2.cuh)
+        constexpr int ts = fr3d::L2_WARPS_STACK * 32, tp = fr3d::L2_WARPS_PAIR * 32;
+        const int grid_s = clampg((pair_cap + ts - 1) / ts, (long long)g_sm_count * (mult ? mult : 1));
+        const int grid_p = clampg((pair_cap + tp - 1) / tp, (long long)g_sm_count * (mult ? mult : 1));
+        if (category_mask & FR3D_CAT_STACKING)
+            fr3d::classify_list2_kernel<false, fr3d::L2_WARPS_STACK>
+                <<<grid_s, ts, fr3d::l2_smem_bytes<false, fr3d::L2_WARPS_STACK>(), st>>>(
+                    *nts, boxes, box_index, pair_i, pair_j, pair_rank, pair_cap, FR3D_CAT_STACKING, index_offset, hits,
+                    hit_cap, counters, wl_stack, 5);
+        fr3d::classify_list2_kernel<true, fr3d::L2_WARPS_PAIR>
+            <<<grid_p, tp, fr3d::l2_smem_bytes<true, fr3d::L2_WARPS_PAIR>(), st>>>(
+                *nts, boxes, box_index, pair_i, pair_j, pair_rank, pair_cap, category_mask & FR3D_CAT_COPLANAR,
+                index_offset, hits, hit_cap, counters, wl_pair, 6);
     } else if (use_mode == 1) {
         fr3d::classify_pairs_tpp_kernel<0, 4, FR3D_TPP_MIN_BLOCKS, 0xFFFFFFFFu, true><<<clampg((pair_cap + 127) / 128, tpp_grid_max), 128, 0, st>>>(
             *nts, boxes, box_index, pair_i, pair_j, pair_rank, pair_cap, category_mask, index_offset, hits, hit_cap,

@@ -236,10 +236,10 @@ class Engine(object):
                                                     int(index_offset), plan.cws.data_ptr(), plan.cws_bytes,
                                                     plan.hits.data_ptr(), plan.hit_cap, plan.counters.data_ptr(), st),
                        "fr3d_classify_pairs")
-            # screen + one thread-per-pair kernel per work list (detail / stacking lists only if requested)
+            # screen + one thread-per-pair kernel per work list (lists of families that were not requested are skipped)
             cm = int(category_mask)
-            self.launches += 2 + (1 if cm & (_lib.CAT_SO | _lib.CAT_SUGAR_RIBOSE | _lib.CAT_BACKBONE) else 0) + \
-                (1 if cm & _lib.CAT_STACKING else 0)
+            self.launches += 2 + (1 if cm & (_lib.CAT_SO | _lib.CAT_SUGAR_RIBOSE) else 0) + \
+                (1 if cm & _lib.CAT_BACKBONE else 0) + (1 if cm & _lib.CAT_STACKING else 0)
             if events is not None:
                 events["classify1"].record()
 

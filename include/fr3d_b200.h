@@ -158,8 +158,8 @@ int fr3d_frames_fit(const fr3d_nts_t *nts, int32_t *status, int place_h, void *s
 /* K2+K3. Replaces make_nt_cubes_half (NA:410-443) and the loop/screens of
  * annotate_nt_nt_interactions (NA:661-724): oriented candidate pairs with 2 <= d <= 12.
  * counters (device int64[8]): [0] n_pairs (may exceed cap: FR3D_E_CAPACITY is NOT raised here,
- * the caller compares after its sync), [1] n_hits, [2] error flags, [3] n_cells, [4] [5] [6] work-list sizes of
- * fr3d_classify_pairs (detail, stacking, coplanar / basepair), [7] reserved. */
+ * the caller compares after its sync), [1] n_hits, [2] error flags, [3] n_cells, [4] [5] [6] [7] work-list sizes of
+ * fr3d_classify_pairs (sO + sugar-ribose, stacking, coplanar / basepair, base-phosphate). */
 size_t fr3d_pair_search_workspace(int32_t n_nt);
 int fr3d_pair_search(const fr3d_nts_t *nts, double cell_size, void *workspace, size_t workspace_bytes,
                      int32_t *pair_i, int32_t *pair_j, int32_t *pair_rank, int64_t pair_cap,
@@ -172,8 +172,8 @@ int fr3d_pair_search(const fr3d_nts_t *nts, double cell_size, void *workspace, s
  * n_pairs is read from counters[0] on the device (clamped to pair_cap).  index_offset is added to the
  * nt indices (and 16 x to the rank) written into the hit records, so that chunks of a larger batch
  * produce globally indexed hits.  workspace (fr3d_classify_workspace(pair_cap) bytes, may be NULL): work lists
- * of the screen kernel; with it the call is four launches: a thread-per-pair screen of the cheap necessary
- * conditions of every rule family, then one thread-per-pair launch per work list (sO / sugar-ribose / BPh / BR;
+ * of the screen kernel; with it the call is five launches: a thread-per-pair screen of the cheap necessary
+ * conditions of every rule family, then one thread-per-pair launch per work list (sO / sugar-ribose; BPh / BR;
  * stacking; coplanar / basepair) over the pairs that passed; without it one warp-per-pair launch over all
  * pairs. */
 size_t fr3d_classify_workspace(int64_t pair_cap);
