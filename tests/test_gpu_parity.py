@@ -412,3 +412,38 @@ def test_modified_residues_identical_to_reference(golden):
     again = gframes.fit_batch_frames(b)
     assert np.all(again == 0)
     assert np.abs(b.center[0] - np.array(frames[0]["center"])).max() < TOL
+
+
+@pytest.mark.parametrize("mode", ["0", "1"])
+def test_alternate_classify_paths_give_the_same_hits(mode, tmp_path):
+    """fr3d_classify_pairs without a workspace runs one warp-per-pair launch over all pairs (FR3D_CLASSIFY_MODE=0
+    forces it), =1 one thread-per-pair launch: both must produce exactly the hit set of the default screened path.
+    The mode is read once per process, hence the subprocess."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, numpy as np\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "from conftest import ALL9\n"
+        "from fr3d_python_b200 import synthetic\n"
+        "from fr3d_python_b200.classifiers import NA_pairwise_interactions as NA\n"
+        "from fr3d_python_b200.engine import Engine\n"
+        "batch = synthetic.make_structure_batch(synthetic.pack_base(), 5, seed0=77)\n"
+        "bt, _ = NA._box_table(NA._default_focused(ALL9['basepair']), NA.load_ideal_basepair_hydrogen_bonds())\n"
+        "hits, n_pairs, _ = Engine.get().annotate_batch(batch, bt, NA.category_mask(ALL9))\n"
+        "order = np.lexsort((hits['slot'], hits['j'], hits['i'], hits['rank']))\n"
+        "np.save(sys.argv[1], hits[order])\n" % (root, os.path.join(root, "tests")))
+    outs = []
+    for m in ("2", mode):
+        out = str(tmp_path / ("hits_mode%s.npy" % m))
+        env = dict(os.environ, FR3D_CLASSIFY_MODE=m)
+        subprocess.run([sys.executable, "-c", code, out], check=True, env=env, cwd=root)
+        outs.append(np.load(out))
+    a, b = outs
+    assert len(a) > 1000 and len(a) == len(b)
+    for f in ("i", "j", "rank", "slot", "code", "box"):
+        assert np.array_equal(a[f], b[f]), f
+    for f in ("cutoff_distance", "max_gap"):          # the warp-per-pair kernel sums the box terms in another fma pattern
+        assert np.abs(a[f] - b[f]).max() < 1e-12, f
