@@ -250,8 +250,14 @@ pair_search_kernel(fr3d_nts_t nts, SearchWs ws, double cutoff, int32_t *__restri
                                 if (dx > cutoff || dy > cutoff || dz > cutoff) keep = false;         // NA:699-702
                                 else if (resid1 == S.resid[t] && alt1 != S.alt[t]) keep = false;     // NA:706-713
                                 else {
-                                    const double d = sqrt(dx * dx + dy * dy + dz * dz);              // NA:716
-                                    if (d > cutoff || d < 2.0) keep = false;                         // NA:719-724
+                                    // d = sqrt(d2) against the cutoff and 2.0 (NA:716-724): decided on d2 unless it is
+                                    // within rounding of a threshold, where the reference's own sqrt decides
+                                    const double d2 = dx * dx + dy * dy + dz * dz, c2 = cutoff * cutoff;
+                                    if (d2 > c2 * (1.0 + 1e-12) || d2 < 4.0 * (1.0 - 1e-12)) keep = false;
+                                    else if (!(d2 < c2 * (1.0 - 1e-12) && d2 > 4.0 * (1.0 + 1e-12))) {
+                                        const double d = sqrt(d2);
+                                        if (d > cutoff || d < 2.0) keep = false;
+                                    }
                                 }
                             }
                         }
