@@ -44,7 +44,7 @@ __device__ __forceinline__ void t_mind_load(const double *base, uint32_t bm, dou
 }
 
 // calculate_base_min_distances (NA:1799-1829) of the points of base1 against the register-held points q of base2
-// (same operations, in the same order, as t_mind<true>)
+// (same operations, in the same order, as the untwinned branch of t_mind)
 __device__ __forceinline__ double t_mind_scan(const double *base1, uint32_t bm1, const double (&q)[FR3D_BASE_SLOTS * 3]) {
     double b0 = 1e300, b1 = 1e300;
 #pragma unroll 1
@@ -267,7 +267,7 @@ classify_list2_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, cons
                 }
                 if (stack_code >= 0) {
                     mind = have_q2 ? t_mind_scan(base1, bm1, q2)
-                                   : t_mind<false>(f1, f2, par1, par2, base1, base2_g, bm1, bm2, tw1, tw2);
+                                   : t_mind(f1, f2, par1, par2, base1, base2_g, bm1, bm2, tw1, tw2);
                     if (!(fabs(mind) < 1.0)) {                                    // NA:1707-1718
                         int near = 1;
                         if (fabs(mind) < 4.0 && fabs(mind) > 1.0 && fabs(nZ) > 0.6 && stack_both) near = 0;
@@ -280,7 +280,7 @@ classify_list2_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, cons
                 const bool cp_gap = cp_frames && (((ori_ok & 1u) && gap12 < 1.5179) || ((ori_ok & 2u) && gap21 < 1.5179));
                 if (bp_live || cp_gap)
                     mind = have_q2 ? t_mind_scan(base1, bm1, q2)
-                                   : t_mind<false>(f1, f2, par1, par2, base1, base2_g, bm1, bm2, tw1, tw2);
+                                   : t_mind(f1, f2, par1, par2, base1, base2_g, bm1, bm2, tw1, tw2);
                 if (cp_gap) {                                                     // NA:2080-2096
                     const bool both_std = (bm1 >> 20 & 1u) && (bm2 >> 20 & 1u);
                     if (mind < 3.4589 && !(mind >= 2.4589 && both_std)) hmask |= 1u << FR3D_SLOT_CP;

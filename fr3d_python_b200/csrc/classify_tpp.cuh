@@ -9,12 +9,12 @@
 // donor/oxygen combinations, 256 atom-atom distances) become unrolled loops with plenty of
 // instruction-level parallelism.
 //
-// Data access: a thread that reads "its" nt record straight from global memory makes every load instruction
-// touch 32 different cache lines - ncu shows such a kernel pinned at ~80 % of the L1 wavefront rate with the
-// issue slots 90 % idle.  So (ROW_LEN > 0) each warp first stages the records of its 32 pairs in shared memory
-// with coalesced cp.async copies (lanes copy consecutive doubles of one record) and every thread then works out
-// of its own row; the row stride is odd, which makes "lane k reads row k" bank-conflict free.  The helpers take
-// plain pointers, so the same code also runs on global memory (ROW_LEN == 0).
+// Data access: this kernel reads the nt records straight from global memory, which is fine for the two short
+// lists it serves (sO / sugar-ribose and base-phosphate) and for the single-launch A/B mode.  For the big lists
+// that pattern is L1-wavefront bound (every load instruction touches 32 cache lines: ~80 % of the L1 wavefront
+// rate with the issue slots 90 % idle), so they go through classify_list2.cuh, which stages the records of a
+// warp's 32 pairs in shared memory with coalesced cp.async copies.  The helpers below take plain pointers and
+// serve both kernels.
 //
 // The arithmetic is the same as in the warp-per-pair kernels and as in the reference; every function
 // below cites the reference lines it restates (NA = fr3d/classifiers/NA_pairwise_interactions.py).
@@ -345,39 +345,11 @@ __device__ __noinline__ double t_gap(const TFrame &fa, const TFrame &fb, int par
     return t_gap_inline(fa, fb, par_b, base_b, bmb, twb);
 }
 
-// calculate_base_min_distances (NA:1799-1829).  REGS: the 16 points of nt2 are held in registers (an absent
-// atom sits at x = 1e150, so it can never be the minimum) and every point of nt1 is read once.
-template <bool REGS>
+// calculate_base_min_distances (NA:1799-1829), general form (twin slots of modified residues included); the
+// register-resident form for the big lists is t_mind_load / t_mind_scan in classify_list2.cuh
 __device__ __forceinline__ double t_mind(const TFrame &f1, const TFrame &f2, int par1, int par2, const double *base1,
                                          const double *base2, uint32_t bm1, uint32_t bm2, uint32_t tw1, uint32_t tw2) {
     double best = 1e300;
-    if (REGS && !tw1 && !tw2) {
-        double q[FR3D_BASE_SLOTS * 3];
-#pragma unroll
-        for (int k = 0; k < FR3D_BASE_SLOTS; ++k) {
-            const bool have = (bm2 >> k) & 1u;
-            q[k * 3] = have ? base2[k * 3] : 1e150;
-            q[k * 3 + 1] = base2[k * 3 + 1];
-            q[k * 3 + 2] = base2[k * 3 + 2];
-        }
-        double b0 = 1e300, b1 = 1e300;
-#pragma unroll 1
-        for (int v = 0; v < FR3D_BASE_SLOTS; ++v) {
-            if (!((bm1 >> v) & 1u)) continue;
-            const double a0 = base1[v * 3], a1 = base1[v * 3 + 1], a2 = base1[v * 3 + 2];
-#pragma unroll
-            for (int k = 0; k < FR3D_BASE_SLOTS; k += 2) {
-                const double d0 = q[k * 3] - a0, d1 = q[k * 3 + 1] - a1, d2 = q[k * 3 + 2] - a2;
-                const double dd = d0 * d0 + d1 * d1 + d2 * d2;
-                if (dd < b0) b0 = dd;
-                const double e0 = q[k * 3 + 3] - a0, e1 = q[k * 3 + 4] - a1, e2 = q[k * 3 + 5] - a2;
-                const double ee = e0 * e0 + e1 * e1 + e2 * e2;
-                if (ee < b1) b1 = ee;
-            }
-        }
-        best = b1 < b0 ? b1 : b0;
-        return best < 1e299 ? sqrt(best) : 9999.0;
-    }
     const int nv1 = tw1 ? 32 : 16, nv2 = tw2 ? 32 : 16;
 #pragma unroll 1
     for (int v = 0; v < nv1; ++v) {
@@ -517,17 +489,10 @@ __device__ __forceinline__ void t_boxes_final(const char *box_base, size_t box_s
 #define FR3D_TPP_MIN_BLOCKS 3
 #endif
 
-// ROW_LEN doubles of each nt record are staged per pair: 0 = none (read global memory), 60 = frame + base atoms,
-// 90 = frame + base atoms + backbone atoms.  WARPS = warps per block (dynamic shared memory = tpp_smem_bytes).
-template <int ROW_LEN, int WARPS>
-__host__ __device__ constexpr size_t tpp_smem_bytes() {
-    return ROW_LEN ? sizeof(double) * (size_t)WARPS * 32 * (2 * ROW_LEN + 1) : 0;
-}
-
 // CATS_CT / BP_CT: the rule families compiled into the instantiation (the run-time mask is ANDed with it), so the
 // kernel of one work list carries neither the code nor the registers of the other families.
-template <int ROW_LEN, int WARPS, int MIN_BLOCKS, uint32_t CATS_CT, bool BP_CT>
-__global__ void __launch_bounds__(WARPS * 32, MIN_BLOCKS)
+template <int MIN_BLOCKS, uint32_t CATS_CT, bool BP_CT>
+__global__ void __launch_bounds__(128, MIN_BLOCKS)
 classify_pairs_tpp_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, const int32_t *__restrict__ box_index,
                           const int32_t *__restrict__ pair_i, const int32_t *__restrict__ pair_j,
                           const int32_t *__restrict__ pair_rank, int64_t pair_cap, uint32_t cats, int32_t index_offset,
@@ -535,27 +500,11 @@ classify_pairs_tpp_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, 
                           const int32_t *__restrict__ worklist, int list_counter, int do_bp_rt) {
     cats &= CATS_CT;
     const bool do_bp = BP_CT && do_bp_rt;
-    extern __shared__ double tpp_smem[];
     __shared__ double s_hull[FR3D_N_PARENTS * 7 * 3];        // a per-lane parent index would serialise constant loads
     for (int item = threadIdx.x; item < FR3D_N_PARENTS * 7 * 3; item += blockDim.x)
         s_hull[item] = (&c_tab.hull[0][0][0])[item];
     __syncthreads();
-    constexpr int PSTRIDE = 2 * ROW_LEN + 1;                 // odd: lane k reads row k without bank conflicts
     const int lane = threadIdx.x & 31;
-    double *rows = tpp_smem + (size_t)(threadIdx.x >> 5) * 32 * PSTRIDE;
-    // per-lane sources of the (up to three) copies that move one staged record
-    const double *src[3] = {nullptr, nullptr, nullptr};
-    int mult[3] = {0, 0, 0};
-    if (ROW_LEN) {
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            const int t = j * 32 + lane;
-            if (t < 3) { src[j] = nts.center + t; mult[j] = 3; }
-            else if (t < 12) { src[j] = nts.rot + (t - 3); mult[j] = 9; }
-            else if (t < 60) { src[j] = nts.base_xyz + (t - 12); mult[j] = FR3D_BASE_SLOTS * 3; }
-            else { src[j] = nts.bb_xyz + (t - 60); mult[j] = FR3D_BB_SLOTS * 3; }
-        }
-    }
     // with a work list (classify_screen.cuh) the kernel walks its entries instead of the whole pair list
     long long n_pairs = worklist ? counters[list_counter] : counters[0];
     if (n_pairs > pair_cap) n_pairs = pair_cap;
@@ -577,42 +526,18 @@ classify_pairs_tpp_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, 
             const long long q = worklist ? (long long)worklist[p] : p;
             n1 = pair_i[q]; n2 = pair_j[q]; rank = pair_rank[q];
         }
-        if (ROW_LEN) {
-            __syncwarp();                                   // everybody is done with the previous round's rows
-#pragma unroll 2
-            for (int k = 0; k < 32; ++k) {
-                const int na = __shfl_sync(FULL, n1, k), nb = __shfl_sync(FULL, n2, k);
-                double *dst = rows + k * PSTRIDE + lane;
-                cp_async8(dst, src[0] + (size_t)na * mult[0]);
-                cp_async8(dst + ROW_LEN, src[0] + (size_t)nb * mult[0]);
-                if (lane + 32 < ROW_LEN) {
-                    cp_async8(dst + 32, src[1] + (size_t)na * mult[1]);
-                    cp_async8(dst + ROW_LEN + 32, src[1] + (size_t)nb * mult[1]);
-                }
-                if (ROW_LEN > 64 && lane + 64 < ROW_LEN) {
-                    cp_async8(dst + 64, src[2] + (size_t)na * mult[2]);
-                    cp_async8(dst + ROW_LEN + 64, src[2] + (size_t)nb * mult[2]);
-                }
-            }
-        }
         uint32_t bm1 = 0, bm2 = 0, bb1 = 0, bb2 = 0;
         if (active) {
             bm1 = nts.base_mask[n1]; bm2 = nts.base_mask[n2];
             bb1 = nts.bb_mask[n1]; bb2 = nts.bb_mask[n2];
         }
-        if (ROW_LEN) {
-            cp_async_wait_all();
-            __syncwarp();
-        }
         if (active) {
             const int par1 = (int)((bm1 >> 16) & 15u) - 1, par2 = (int)((bm2 >> 16) & 15u) - 1;
-            const double *R1 = rows + lane * PSTRIDE, *R2 = R1 + ROW_LEN;
-            const TFrame f1 = ROW_LEN ? load_tframe_row(R1) : load_tframe(nts, n1);
-            const TFrame f2 = ROW_LEN ? load_tframe_row(R2) : load_tframe(nts, n2);
-            const double *base1 = ROW_LEN ? R1 + 12 : nts.base_xyz + (size_t)n1 * FR3D_BASE_SLOTS * 3;
-            const double *base2 = ROW_LEN ? R2 + 12 : nts.base_xyz + (size_t)n2 * FR3D_BASE_SLOTS * 3;
-            const double *bbp1 = ROW_LEN > 64 ? R1 + 60 : nts.bb_xyz + (size_t)n1 * FR3D_BB_SLOTS * 3;
-            const double *bbp2 = ROW_LEN > 64 ? R2 + 60 : nts.bb_xyz + (size_t)n2 * FR3D_BB_SLOTS * 3;
+            const TFrame f1 = load_tframe(nts, n1), f2 = load_tframe(nts, n2);
+            const double *base1 = nts.base_xyz + (size_t)n1 * FR3D_BASE_SLOTS * 3;
+            const double *base2 = nts.base_xyz + (size_t)n2 * FR3D_BASE_SLOTS * 3;
+            const double *bbp1 = nts.bb_xyz + (size_t)n1 * FR3D_BB_SLOTS * 3;
+            const double *bbp2 = nts.bb_xyz + (size_t)n2 * FR3D_BB_SLOTS * 3;
             const double nZ = f1.u2 * f2.u2 + f1.u5 * f2.u5 + f1.u8 * f2.u8;      // M[2][2] in both orientations
 
             // ---- base-oxygen stacking, both directions (NA:758-778)
@@ -715,7 +640,7 @@ classify_pairs_tpp_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, 
                 }
                 const bool cp_gap = cp_frames && (((ori_ok & 1u) && gap12 < 1.5179) || ((ori_ok & 2u) && gap21 < 1.5179));
                 if (stack_code >= 0 || bp_live || cp_gap)
-                    mind = t_mind<(ROW_LEN > 0)>(f1, f2, par1, par2, base1, base2, bm1, bm2, tw1, tw2);
+                    mind = t_mind(f1, f2, par1, par2, base1, base2, bm1, bm2, tw1, tw2);
                 if (stack_code >= 0 && !(fabs(mind) < 1.0)) {                 // NA:1707-1718
                     int near = 1;
                     if (fabs(mind) < 4.0 && fabs(mind) > 1.0 && fabs(nZ) > 0.6 && stack_both) near = 0;

@@ -193,11 +193,11 @@ int fr3d_classify_pairs(const fr3d_nts_t *nts, const fr3d_box_t *boxes, const in
         const int tpp_grid = clampg((pair_cap + 127) / 128, tpp_grid_max);
         constexpr uint32_t LIGHT_CATS = FR3D_CAT_SO | FR3D_CAT_SUGAR_RIBOSE;
         if (category_mask & LIGHT_CATS)
-            fr3d::classify_pairs_tpp_kernel<0, 4, 4, LIGHT_CATS, false><<<tpp_grid, 128, 0, st>>>(
+            fr3d::classify_pairs_tpp_kernel<4, LIGHT_CATS, false><<<tpp_grid, 128, 0, st>>>(
                 *nts, boxes, box_index, pair_i, pair_j, pair_rank, pair_cap, category_mask & LIGHT_CATS, index_offset, hits,
                 hit_cap, counters, wl_light, 4, 0);
         if (category_mask & FR3D_CAT_BACKBONE)
-            fr3d::classify_pairs_tpp_kernel<0, 4, 4, FR3D_CAT_BACKBONE, false><<<tpp_grid, 128, 0, st>>>(
+            fr3d::classify_pairs_tpp_kernel<4, FR3D_CAT_BACKBONE, false><<<tpp_grid, 128, 0, st>>>(
                 *nts, boxes, box_index, pair_i, pair_j, pair_rank, pair_cap, FR3D_CAT_BACKBONE, index_offset, hits,
                 hit_cap, counters, wl_bph, 7, 0);
         // stacking and pairing lists: records staged in shared memory in two phases (classify_list2.cuh)
@@ -214,7 +214,7 @@ int fr3d_classify_pairs(const fr3d_nts_t *nts, const fr3d_box_t *boxes, const in
                 *nts, boxes, box_index, pair_i, pair_j, pair_rank, pair_cap, category_mask & FR3D_CAT_COPLANAR,
                 index_offset, hits, hit_cap, counters, wl_pair, 6);
     } else if (use_mode == 1) {
-        fr3d::classify_pairs_tpp_kernel<0, 4, FR3D_TPP_MIN_BLOCKS, 0xFFFFFFFFu, true><<<clampg((pair_cap + 127) / 128, tpp_grid_max), 128, 0, st>>>(
+        fr3d::classify_pairs_tpp_kernel<FR3D_TPP_MIN_BLOCKS, 0xFFFFFFFFu, true><<<clampg((pair_cap + 127) / 128, tpp_grid_max), 128, 0, st>>>(
             *nts, boxes, box_index, pair_i, pair_j, pair_rank, pair_cap, category_mask, index_offset, hits, hit_cap,
             counters, nullptr, 0, 1);
     } else {
