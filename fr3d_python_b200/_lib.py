@@ -57,7 +57,8 @@ class StaticTables(C.Structure):
                 ("combo_ok", C.c_int32 * (N_PARENTS * N_PARENTS)),
                 ("pad_tail", C.c_int32),
                 ("so_r2max", C.c_double * N_PARENTS),
-                ("hull_r2max", C.c_double * N_PARENTS)]
+                ("hull_r2max", C.c_double * N_PARENTS),
+                ("hull_r2in", C.c_double * N_PARENTS)]
 
 
 _lock = threading.Lock()

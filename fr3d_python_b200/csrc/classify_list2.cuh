@@ -75,8 +75,10 @@ classify_list2_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, cons
                       const int32_t *__restrict__ worklist, int list_counter) {
     extern __shared__ double l2_smem[];
     __shared__ double s_hull[FR3D_N_PARENTS * 7 * 3];        // a per-lane parent index would serialise constant loads
+    __shared__ double s_r2in[FR3D_N_PARENTS];
     for (int item = threadIdx.x; item < FR3D_N_PARENTS * 7 * 3; item += blockDim.x)
         s_hull[item] = (&c_tab.hull[0][0][0])[item];
+    if (threadIdx.x < FR3D_N_PARENTS) s_r2in[threadIdx.x] = c_tab.hull_r2in[threadIdx.x];
     __syncthreads();
     const int lane = threadIdx.x & 31;
     double *rows = l2_smem + (size_t)(threadIdx.x >> 5) * 32 * L2_ROW;
@@ -177,7 +179,7 @@ classify_list2_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, cons
             if (!PAIRING) {
                 // ---- base-base stacking, nt2 over nt1 (NA:1602-1702)
                 if (par1 >= 0 && par2 >= 0) {
-                    nt2on1 = t_overlap(f1, s_hull + par1 * 21, base2, bm2, z_2on1);
+                    nt2on1 = t_overlap(f1, s_hull + par1 * 21, s_r2in[par1], base2, bm2, z_2on1);
                     want_q2 = true;
                 }
             } else {
@@ -253,7 +255,7 @@ classify_list2_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, cons
                 bool stack_both = false;
                 if (par1 >= 0 && par2 >= 0) {
                     double z_1on2;
-                    const bool nt1on2 = t_overlap(f2, s_hull + par2 * 21, base1, bm1, z_1on2);
+                    const bool nt1on2 = t_overlap(f2, s_hull + par2 * 21, s_r2in[par2], base1, bm1, z_1on2);
                     if ((nt2on1 || nt1on2) && !(fabs(nZ) < 0.5)) {
                         const bool reverse = nt1on2 && !nt2on1;
                         const double mvd = reverse ? z_1on2 : z_2on1;

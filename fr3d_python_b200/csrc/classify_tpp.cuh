@@ -61,11 +61,13 @@ __device__ __forceinline__ void tproject(const TFrame &f, double px, double py, 
 // closest to the plane) and a bit for the atoms inside the cylinder |z| < 4.5, x^2 + y^2 < 16 that contains every
 // hull (tests/test_abi.py).  "inside" is an OR over the atoms, so pass 2 runs the exact half-plane test on the
 // cylinder atoms only until the first one is in - a thread-per-pair warp pays for a branch if ANY lane takes it,
-// and on the stacking list that is one or two iterations instead of sixteen.
-__device__ __forceinline__ bool t_overlap(const TFrame &fa, const double *hull, const double *q, uint32_t bmb,
-                                          double &zsel) {
+// and on the stacking list that is one or two iterations instead of sixteen.  An atom inside the disc of squared
+// radius r2in that the hull contains (c_tab.hull_r2in, tests/test_abi.py) is in without any half-plane test.
+__device__ __forceinline__ bool t_overlap(const TFrame &fa, const double *hull, double r2in, const double *q,
+                                          uint32_t bmb, double &zsel) {
     double zmin = 1e300, zmax = -1e300, best = 1e300;
     unsigned cand = 0;
+    bool inside = false;
     zsel = 0.0;
 #pragma unroll 4
     for (int a = 0; a < FR3D_BASE_SLOTS; ++a) {
@@ -74,10 +76,10 @@ __device__ __forceinline__ bool t_overlap(const TFrame &fa, const double *hull, 
         const double z = v0 * fa.u2 + v1 * fa.u5 + v2 * fa.u8;                // the z of translate_rotate_point
         const double r2 = (v0 * v0 + v1 * v1 + v2 * v2) - z * z;              // x^2 + y^2 (U is orthonormal)
         if (have && fabs(z) < 4.5 && r2 < 16.0 + 1e-6) cand |= 1u << a;
+        if (have && fabs(z) < 4.5 && r2 < r2in) inside = true;
         if (have && fabs(z) < best) { best = fabs(z); zsel = z; }
         if (have) { zmin = fmin(zmin, z); zmax = fmax(zmax, z); }
     }
-    bool inside = false;
     while (cand && !inside) {
         const int a = __ffs(cand) - 1;
         cand &= cand - 1;
@@ -552,8 +554,8 @@ classify_pairs_tpp_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, 
             bool stack_both = false;
             if ((cats & FR3D_CAT_STACKING) && par1 >= 0 && par2 >= 0) {
                 double z_2on1, z_1on2;
-                const bool nt2on1 = t_overlap(f1, s_hull + par1 * 21, base2, bm2, z_2on1);
-                const bool nt1on2 = t_overlap(f2, s_hull + par2 * 21, base1, bm1, z_1on2);
+                const bool nt2on1 = t_overlap(f1, s_hull + par1 * 21, c_tab.hull_r2in[par1], base2, bm2, z_2on1);
+                const bool nt1on2 = t_overlap(f2, s_hull + par2 * 21, c_tab.hull_r2in[par2], base1, bm1, z_1on2);
                 if ((nt2on1 || nt1on2) && !(fabs(nZ) < 0.5)) {
                     const bool reverse = nt1on2 && !nt2on1;
                     const double mvd = reverse ? z_1on2 : z_2on1;

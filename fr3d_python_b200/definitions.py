@@ -107,6 +107,9 @@ def load_ideal_basepair_hydrogen_bonds():
 # that are shipped (the tight values are 2.73 2.07 3.00 2.05 2.01 and 3.50 3.25 3.84 2.79 2.83).
 SCREEN_SO_RADIUS = {'A': 2.80, 'C': 2.15, 'G': 3.05, 'U': 2.10, 'DT': 2.10}
 SCREEN_HULL_RADIUS = {'A': 3.55, 'C': 3.30, 'G': 3.90, 'U': 2.85, 'DT': 2.90}
+# ... and the disc of this radius about the base centre lies INSIDE the hull (inscribed radii 1.956 1.471 1.885
+# 1.835 1.492): an atom within it (and |z| < 4.5) overlaps the base without evaluating the half planes.
+HULL_INNER_RADIUS = {'A': 1.93, 'C': 1.45, 'G': 1.86, 'U': 1.81, 'DT': 1.47}
 
 
 def static_tables():
@@ -115,6 +118,7 @@ def static_tables():
     for p, parent in enumerate(PARENTS):
         t.so_r2max[p] = SCREEN_SO_RADIUS[parent] ** 2
         t.hull_r2max[p] = SCREEN_HULL_RADIUS[parent] ** 2
+        t.hull_r2in[p] = HULL_INNER_RADIUS[parent] ** 2
     for p, parent in enumerate(PARENTS):
         names = SLOT_NAMES[parent]
         # standard coordinates of a DNA/RNA parent: RNA tables for A C G U, DT for DT

@@ -127,6 +127,7 @@ typedef struct {
      * the parent lies inside so_r2max, its convex hull inside hull_r2max (proved in tests/test_abi.py). */
     double so_r2max[FR3D_N_PARENTS];
     double hull_r2max[FR3D_N_PARENTS];
+    double hull_r2in[FR3D_N_PARENTS];      /* ... and the disc of this squared radius lies inside the hull */
 } fr3d_static_tables_t;
 
 /* One basepair cutoff box (class_limits_2023.py after focus_basepair_cutoffs, NA:88-136). 128 B. */

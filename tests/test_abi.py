@@ -127,3 +127,15 @@ def test_hulls_lie_inside_the_screen_disc(per_parent):
             inside0 = inside0 and c > 0
         assert not ok.any(), parent
         assert inside0, parent                      # the base centre is inside the hull
+
+
+def test_inner_disc_lies_inside_the_hull():
+    """The overlap tests accept an atom with x^2 + y^2 < definitions.HULL_INNER_RADIUS[parent]^2 without
+    evaluating the half planes: that disc must lie strictly inside the convex hull (every point of its boundary
+    circle, and therefore the whole disc, satisfies all half planes with room to spare)."""
+    ang = np.linspace(0, 2 * np.pi, 7200, endpoint=False)
+    for parent in defs.PARENTS:
+        radius = defs.HULL_INNER_RADIUS[parent] + 0.01
+        cx, cy = radius * np.cos(ang), radius * np.sin(ang)
+        for a, b, c in defs.PLANES["hull"][parent]:
+            assert (a * cx + b * cy + c > 0).all(), parent
