@@ -104,11 +104,6 @@ __device__ __forceinline__ double hb_angle_if_wide(const double *A, const double
     return 180.0 * atan2_once(sinang, cosang) / 3.141592653589793;
 }
 
-__device__ __forceinline__ double dist3(const double *a, const double *b) {
-    const double d0 = a[0] - b[0], d1 = a[1] - b[1], d2 = a[2] - b[2];
-    return sqrt(d0 * d0 + d1 * d1 + d2 * d2);
-}
-
 static constexpr int WARPS_PER_BLOCK = 4;
 
 // Per-warp staging area in shared memory: everything the rules read for one pair.
