@@ -102,7 +102,7 @@ int fr3d_frames_fit(const fr3d_nts_t *nts, int32_t *status, int place_h, void *s
     if (!nts) return fail(FR3D_E_ARG, "nts is NULL");
     if (!g_tables_loaded) return fail(FR3D_E_NOTABLES, "fr3d_upload_tables not called");
     if (nts->n_nt <= 0) return FR3D_OK;
-    const int block = 128;
+    const int block = fr3d::FRAMES_WARPS * 32;
     const int grid = (nts->n_nt + block - 1) / block;
     fr3d::frames_fit_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(*nts, status, place_h);
     CUDA_TRY(cudaGetLastError());

@@ -4,19 +4,28 @@
 // -> besttransformation (fr3d/geometry/superpositions.py:10-89) and the
 // arithmetic of infer_NA_hydrogens (components.py:452-462).
 //
-// Work per nt is tiny (<= 11 atoms): the kernel is latency bound; one thread
-// per nt keeps the 4x4 Jacobi in registers and the loads of the nt's
-// contiguous 16x3 slot block sequential per thread.
+// Work per nt is tiny (<= 11 atoms): one thread per nt keeps the 4x4 Jacobi in registers.  The 32 records of a
+// warp are one contiguous 12 KB block of base_xyz, so the warp first copies it into shared memory with coalesced
+// cp.async (a thread reading "its" record from global memory makes every load touch 32 cache lines) and each
+// thread then works in its own row (odd stride: no bank conflicts); the slots a thread may have written
+// (hydrogens, ideal-position copies) are copied back the same way.  The standard base coordinates are read
+// with a per-lane parent index, which would serialise constant-cache loads: they sit in shared memory too.
 #pragma once
 
+#include "classify_pm.cuh"
 #include "rotfit.cuh"
 #include "tables.cuh"
 
 namespace fr3d {
 
-__global__ void __launch_bounds__(128) frames_fit_kernel(fr3d_nts_t nts, int32_t *__restrict__ status, int place_h) {
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= nts.n_nt) return;
+constexpr int FRAMES_WARPS = 3;
+constexpr int FRAMES_STRIDE = FR3D_BASE_SLOTS * 3 + 1;     // 49 doubles per row
+
+// the fit of one nt; xyz = its 16 x 3 slot block (a shared-memory row), std_xyz = the standard base coordinates.
+// Returns true if a slot below 8 was written (ideal-position copies of a modified residue).
+__device__ __forceinline__ bool frames_fit_one(const fr3d_nts_t &nts, int32_t *__restrict__ status, int place_h, int n,
+                                               double *xyz, const double (*std_xyz)[FR3D_BASE_SLOTS][3]) {
+    bool wrote_low = false;
     const int parent = nts.meta[n * FR3D_META_INTS + 0];
     const int flags = nts.meta[n * FR3D_META_INTS + 1];
     const uint32_t mask_in = nts.base_mask[n];
@@ -25,18 +34,17 @@ __global__ void __launch_bounds__(128) frames_fit_kernel(fr3d_nts_t nts, int32_t
     // them again would not reproduce the frame, so a second pass leaves them alone
     if ((flags & FR3D_FLAG_DUP) && (mask_in & FR3D_MASK_HAS_FRAME)) {
         if (status) status[n] = 0;
-        return;
+        return false;
     }
     // bits 16-19: parent + 1, bits 20-23: flags (read by the classify kernel instead of meta)
     const uint32_t tag = ((uint32_t)(parent + 1) & 15u) << 16 | ((uint32_t)flags & 15u) << 20;
     if (parent < 0 || parent >= FR3D_N_PARENTS) {
         nts.base_mask[n] = mask;
         if (status) status[n] = -1;
-        return;
+        return false;
     }
     const int nh = c_tab.n_heavy[parent];
     const int ns = c_tab.n_slots[parent];
-    double *xyz = nts.base_xyz + (size_t)n * FR3D_BASE_SLOTS * 3;
 
     // means over the observed heavy atoms (superpositions.py:40-41)
     double mr[3] = {0, 0, 0}, ms[3] = {0, 0, 0};
@@ -44,8 +52,8 @@ __global__ void __launch_bounds__(128) frames_fit_kernel(fr3d_nts_t nts, int32_t
     for (int k = 0; k < nh; ++k) {
         if (mask >> k & 1u) {
             mr[0] += xyz[k * 3 + 0]; mr[1] += xyz[k * 3 + 1]; mr[2] += xyz[k * 3 + 2];
-            ms[0] += c_tab.std_xyz[parent][k][0]; ms[1] += c_tab.std_xyz[parent][k][1];
-            ms[2] += c_tab.std_xyz[parent][k][2];
+            ms[0] += std_xyz[parent][k][0]; ms[1] += std_xyz[parent][k][1];
+            ms[2] += std_xyz[parent][k][2];
             ++cnt;
         }
     }
@@ -55,7 +63,7 @@ __global__ void __launch_bounds__(128) frames_fit_kernel(fr3d_nts_t nts, int32_t
         // (components.py:324-337), and drops out of the cubes (NA:390,426).
         nts.base_mask[n] = mask | tag;
         if (status) status[n] = -2;
-        return;
+        return false;
     }
     const double inv = 1.0 / (double)cnt;
     mr[0] *= inv; mr[1] *= inv; mr[2] *= inv;
@@ -66,8 +74,8 @@ __global__ void __launch_bounds__(128) frames_fit_kernel(fr3d_nts_t nts, int32_t
     for (int k = 0; k < nh; ++k) {
         if (mask >> k & 1u) {
             const double a0 = xyz[k * 3 + 0] - mr[0], a1 = xyz[k * 3 + 1] - mr[1], a2 = xyz[k * 3 + 2] - mr[2];
-            const double b0 = c_tab.std_xyz[parent][k][0] - ms[0], b1 = c_tab.std_xyz[parent][k][1] - ms[1],
-                         b2 = c_tab.std_xyz[parent][k][2] - ms[2];
+            const double b0 = std_xyz[parent][k][0] - ms[0], b1 = std_xyz[parent][k][1] - ms[1],
+                         b2 = std_xyz[parent][k][2] - ms[2];
             M[0][0] += a0 * b0; M[0][1] += a0 * b1; M[0][2] += a0 * b2;
             M[1][0] += a1 * b0; M[1][1] += a1 * b1; M[1][2] += a1 * b2;
             M[2][0] += a2 * b0; M[2][1] += a2 * b1; M[2][2] += a2 * b2;
@@ -102,11 +110,12 @@ __global__ void __launch_bounds__(128) frames_fit_kernel(fr3d_nts_t nts, int32_t
         uint32_t twin = 0;
         for (int k = 0; k < ns; ++k) {
             if (dup >> k & 1u) {
-                const double h0 = c_tab.std_xyz[parent][k][0], h1 = c_tab.std_xyz[parent][k][1],
-                             h2 = c_tab.std_xyz[parent][k][2];
+                const double h0 = std_xyz[parent][k][0], h1 = std_xyz[parent][k][1],
+                             h2 = std_xyz[parent][k][2];
                 const double i0 = ctr[0] + (U[0][0] * h0 + U[0][1] * h1 + U[0][2] * h2);
                 const double i1 = ctr[1] + (U[1][0] * h0 + U[1][1] * h1 + U[1][2] * h2);
                 const double i2 = ctr[2] + (U[2][0] * h0 + U[2][1] * h1 + U[2][2] * h2);
+                if (k < 8) wrote_low = true;
                 if (mask >> k & 1u) {
                     xyz[k * 3 + 0] = (xyz[k * 3 + 0] + i0) / 2.0;
                     xyz[k * 3 + 1] = (xyz[k * 3 + 1] + i1) / 2.0;
@@ -123,8 +132,8 @@ __global__ void __launch_bounds__(128) frames_fit_kernel(fr3d_nts_t nts, int32_t
         // components.py:452-462: centre + U . h_std for every missing base hydrogen of a standard residue
         for (int k = nh; k < ns; ++k) {
             if (!(mask >> k & 1u)) {
-                const double h0 = c_tab.std_xyz[parent][k][0], h1 = c_tab.std_xyz[parent][k][1],
-                             h2 = c_tab.std_xyz[parent][k][2];
+                const double h0 = std_xyz[parent][k][0], h1 = std_xyz[parent][k][1],
+                             h2 = std_xyz[parent][k][2];
                 xyz[k * 3 + 0] = ctr[0] + (U[0][0] * h0 + U[0][1] * h1 + U[0][2] * h2);
                 xyz[k * 3 + 1] = ctr[1] + (U[1][0] * h0 + U[1][1] * h1 + U[1][2] * h2);
                 xyz[k * 3 + 2] = ctr[2] + (U[2][0] * h0 + U[2][1] * h1 + U[2][2] * h2);
@@ -134,6 +143,41 @@ __global__ void __launch_bounds__(128) frames_fit_kernel(fr3d_nts_t nts, int32_t
     }
     nts.base_mask[n] = mask | tag | FR3D_MASK_HAS_FRAME;
     if (status) status[n] = 0;
+    return wrote_low;
+}
+
+__global__ void __launch_bounds__(FRAMES_WARPS * 32) frames_fit_kernel(fr3d_nts_t nts, int32_t *__restrict__ status,
+                                                                       int place_h) {
+    __shared__ double s_std[FR3D_N_PARENTS][FR3D_BASE_SLOTS][3];
+    __shared__ double s_rows[FRAMES_WARPS][32 * FRAMES_STRIDE];
+    for (int item = threadIdx.x; item < FR3D_N_PARENTS * FR3D_BASE_SLOTS * 3; item += blockDim.x)
+        (&s_std[0][0][0])[item] = (&c_tab.std_xyz[0][0][0])[item];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n0 = (blockIdx.x * FRAMES_WARPS + warp) * 32;              // first nt of this warp
+    const int n = n0 + lane;
+    double *rows = s_rows[warp];
+    {   // stage the warp's records: items [0, 32 * 48) of the contiguous block, item t -> row t / 48, column t % 48
+        const long long total = (long long)min(32, max(0, nts.n_nt - n0)) * (FR3D_BASE_SLOTS * 3);
+        const double *src = nts.base_xyz + (size_t)n0 * FR3D_BASE_SLOTS * 3;
+#pragma unroll 4
+        for (int t = lane; t < 32 * FR3D_BASE_SLOTS * 3; t += 32)
+            if (t < total) cp_async8(rows + (t / (FR3D_BASE_SLOTS * 3)) * FRAMES_STRIDE + t % (FR3D_BASE_SLOTS * 3), src + t);
+        cp_async_wait_all();
+    }
+    __syncthreads();
+    bool wrote_low = false;                                               // wrote a slot below 8 (ideal-position copies)
+    if (n < nts.n_nt) wrote_low = frames_fit_one(nts, status, place_h, n, rows + lane * FRAMES_STRIDE, s_std);
+    __syncwarp();
+    // copy back slots 8..15 (every hydrogen slot lies there: the parents have 8 to 11 heavy atoms), or whole rows
+    // if some lane inserted ideal-position copies
+    const int first_col = __any_sync(0xFFFFFFFFu, wrote_low) ? 0 : 24;
+    const int width = FR3D_BASE_SLOTS * 3 - first_col;
+    const int rows_here = min(32, max(0, nts.n_nt - n0));
+    double *dstg = nts.base_xyz + (size_t)n0 * FR3D_BASE_SLOTS * 3;
+    for (int t = lane; t < rows_here * width; t += 32) {
+        const int r = t / width, c = first_col + t % width;
+        dstg[r * (FR3D_BASE_SLOTS * 3) + c] = rows[r * FRAMES_STRIDE + c];
+    }
 }
 
 }  // namespace fr3d
