@@ -38,8 +38,10 @@ def fit_component_frames(components, device=None):
     if not todo:
         return
     b = packing.NtBatch(len(todo))
-    for k, c in enumerate(todo):
-        packing._fill_atoms(b, k, packing._slot_maps(c.sequence), ((a.name, a.x, a.y, a.z) for a in c._atoms))
+    rows = packing._Rows()
+    for c in todo:
+        packing._fill_atoms(rows, packing._slot_maps(c.sequence), ((a.name, a.x, a.y, a.z) for a in c._atoms))
+    rows.flush(b)
     status = fit_batch_frames(b, place_h=False, device=device)
     for k, c in enumerate(todo):
         if status[k] == 0:

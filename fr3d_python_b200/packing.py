@@ -133,68 +133,114 @@ def _slot_maps(sequence):
     return res
 
 
-def _fill_atoms(batch, k, maps, atoms, frames_given=False):
-    """atoms: iterable of (name, x, y, z).  Duplicate names are averaged like AtomProxy
+_ZERO3 = [0.0, 0.0, 0.0]
+_ZERO_BASE = [0.0] * (3 * _lib.BASE_SLOTS)
+_ZERO_BB = [0.0] * (3 * _lib.BB_SLOTS)
+
+
+class _Rows(object):
+    """Per-nt records collected as plain Python lists while the atoms are walked, written to the numpy
+    arrays of the batch in one go (element-wise numpy writes dominated the packing time)."""
+
+    def __init__(self):
+        self.base, self.bb, self.bmask, self.bbmask = [], [], [], []
+        self.meta0, self.meta1, self.meta7 = [], [], []
+
+    def add_unknown(self):
+        self.base += _ZERO_BASE; self.bb += _ZERO_BB
+        self.bmask.append(0); self.bbmask.append(0)
+        self.meta0.append(-1); self.meta1.append(0); self.meta7.append(0)
+
+    def flush(self, batch):
+        if not batch.n:
+            return
+        batch.base_xyz[:] = np.array(self.base, dtype=np.float64).reshape(batch.n, _lib.BASE_SLOTS, 3)   # flat lists:
+        batch.bb_xyz[:] = np.array(self.bb, dtype=np.float64).reshape(batch.n, _lib.BB_SLOTS, 3)         # nested ones parse slowly
+        batch.base_mask[:] = np.array(self.bmask, dtype=np.uint32)
+        batch.bb_mask[:] = np.array(self.bbmask, dtype=np.uint32)
+        batch.meta[:, 0] = self.meta0
+        batch.meta[:, 1] = self.meta1
+        batch.meta[:, 7] = self.meta7
+
+
+def _fill_atoms(rows, maps, atoms, frames_given=False):
+    """Append one nt to rows.  atoms: iterable of (name, x, y, z).  Duplicate names are averaged like AtomProxy
     (fr3d/data/base.py:150-166).  Modified residues: see FR3D_FLAG_DUP in include/fr3d_b200.h."""
     pcode, flags, bslot, bbslot, dupmask = maps
-    bcount = {}
+    base = [None] * _lib.BASE_SLOTS          # slot -> [x, y, z, count]
+    bb = [None] * _lib.BB_SLOTS
     saw_h = False
     for name, x, y, z in atoms:
         if 'H' in name:
             saw_h = True
         s = bslot.get(name)
         if s is not None:
-            if batch.base_mask[k] >> s & 1:
-                c = bcount.get(s, 1)
-                batch.base_xyz[k, s] = (batch.base_xyz[k, s] * c + (x, y, z)) / (c + 1)
-                bcount[s] = c + 1
-            else:
-                batch.base_xyz[k, s] = (x, y, z)
-                batch.base_mask[k] |= np.uint32(1 << s)
-            continue
-        s = bbslot.get(name)
-        if s is not None:
-            if batch.bb_mask[k] >> s & 1:
-                c = bcount.get(100 + s, 1)
-                batch.bb_xyz[k, s] = (batch.bb_xyz[k, s] * c + (x, y, z)) / (c + 1)
-                bcount[100 + s] = c + 1
-            else:
-                batch.bb_xyz[k, s] = (x, y, z)
-                batch.bb_mask[k] |= np.uint32(1 << s)
+            tgt = base
+        else:
+            s = bbslot.get(name)
+            if s is None:
+                continue
+            tgt = bb
+        cur = tgt[s]
+        if cur is None:
+            tgt[s] = [x, y, z, 1]
+        else:
+            c = cur[3]
+            cur[0] = (cur[0] * c + x) / (c + 1)
+            cur[1] = (cur[1] * c + y) / (c + 1)
+            cur[2] = (cur[2] * c + z) / (c + 1)
+            cur[3] = c + 1
+    bmask = 0
+    bbmask = 0
+    for s_, cur in enumerate(base):
+        if cur is not None:
+            bmask |= 1 << s_
+    for s_, cur in enumerate(bb):
+        if cur is not None:
+            bbmask |= 1 << s_
+    meta7 = 0
     if flags & _lib.FLAG_MODIFIED:
         if frames_given:
             # Component objects of the reference already hold the ideal copies: twin slots are those seen twice
             twin = 0
-            for s_, c in bcount.items():
-                if s_ < 100 and c == 2:
+            for s_, cur in enumerate(base):
+                if cur is not None and cur[3] == 2:
                     twin |= 1 << s_
             if twin:
                 flags |= _lib.FLAG_DUP
-                batch.meta[k, 7] = twin << 16
+                meta7 = twin << 16
         elif not saw_h:
             flags |= _lib.FLAG_DUP
-            batch.meta[k, 7] = dupmask
-    batch.meta[k, 0] = pcode
-    batch.meta[k, 1] = flags
-    batch.base_mask[k] |= np.uint32(((pcode + 1) & 15) << 16 | (flags & 15) << 20)   # read by the classify kernel
+            meta7 = dupmask
+    flat = rows.base
+    for cur in base:
+        flat += cur[:3] if cur is not None else _ZERO3
+    flat = rows.bb
+    for cur in bb:
+        flat += cur[:3] if cur is not None else _ZERO3
+    rows.bmask.append(bmask | ((pcode + 1) & 15) << 16 | (flags & 15) << 20)      # tag read by the classify kernel
+    rows.bbmask.append(bbmask)
+    rows.meta0.append(pcode); rows.meta1.append(flags); rows.meta7.append(meta7)
 
 
-def _fix_amino_hydrogens(batch, k, parent):
-    """components.py:405-445: observed amino hydrogens are relabelled so that H62 / H42 / H22 is
-    the one nearer N7 / C5 / N1."""
+def _fix_amino_hydrogens(rows, parent):
+    """components.py:405-445, on the nt just appended to rows: observed amino hydrogens are relabelled so that
+    H62 / H42 / H22 is the one nearer N7 / C5 / N1."""
     if parent not in _AMINO:
         return
     heavy, h1, h2 = _AMINO[parent]
     so = defs.SLOT_OF[parent]
     sh, s1, s2 = so[heavy], so[h1], so[h2]
-    m = int(batch.base_mask[k])
+    m = rows.bmask[-1]
     if (m >> sh & 1) and (m >> s1 & 1) and (m >> s2 & 1):
-        d1 = np.sum((batch.base_xyz[k, sh] - batch.base_xyz[k, s1]) ** 2)
-        d2 = np.sum((batch.base_xyz[k, sh] - batch.base_xyz[k, s2]) ** 2)
+        flat = rows.base
+        o = len(flat) - 3 * _lib.BASE_SLOTS                  # the nt just appended
+        a, p1, p2 = flat[o + 3 * sh:o + 3 * sh + 3], flat[o + 3 * s1:o + 3 * s1 + 3], flat[o + 3 * s2:o + 3 * s2 + 3]
+        d1 = (a[0] - p1[0]) ** 2 + (a[1] - p1[1]) ** 2 + (a[2] - p1[2]) ** 2
+        d2 = (a[0] - p2[0]) ** 2 + (a[1] - p2[1]) ** 2 + (a[2] - p2[2]) ** 2
         if d1 < d2:
-            tmp = batch.base_xyz[k, s1].copy()
-            batch.base_xyz[k, s1] = batch.base_xyz[k, s2]
-            batch.base_xyz[k, s2] = tmp
+            flat[o + 3 * s1:o + 3 * s1 + 3] = p2
+            flat[o + 3 * s2:o + 3 * s2 + 3] = p1
 
 
 def _finish_identity(batch):
@@ -207,34 +253,41 @@ def _finish_identity(batch):
     any_alt = any(a is not None for a in batch.alt_id)
     resid = {}
     alts = {}
+    # plain Python lists inside the loops, one numpy write per column at the end
+    sof_l = sof.tolist()
+    m2, m3, m4, m5, m6 = [0] * n, [0] * n, [0] * n, [0] * n, [0] * n
     for k in range(n):
-        g = groups.setdefault((int(sof[k]), batch.model[k]), len(groups))
-        batch.meta[k, 2] = g
-        batch.meta[k, 3] = chain_rank[batch.chain[k]]
+        m2[k] = groups.setdefault((sof_l[k], batch.model[k]), len(groups))
+        m3[k] = chain_rank[batch.chain[k]]
         idx = batch.index[k]
-        batch.meta[k, 4] = 0 if idx is None else int(idx)
+        m4[k] = 0 if idx is None else int(idx)
         if any_alt:     # alt-id twins screen, NA:706-713
-            key = (int(sof[k]), batch.number[k], batch.sequence[k], batch.chain[k], batch.symmetry[k],
+            key = (sof_l[k], batch.number[k], batch.sequence[k], batch.chain[k], batch.symmetry[k],
                    batch.insertion_code[k])
-            batch.meta[k, 5] = resid.setdefault(key, len(resid))
-            batch.meta[k, 6] = alts.setdefault(batch.alt_id[k], len(alts))
+            m5[k] = resid.setdefault(key, len(resid))
+            m6[k] = alts.setdefault(batch.alt_id[k], len(alts))
         else:
-            batch.meta[k, 5] = k
-            batch.meta[k, 6] = 0
+            m5[k] = k
+    if n:
+        batch.meta[:, 2] = m2; batch.meta[:, 3] = m3; batch.meta[:, 4] = m4; batch.meta[:, 5] = m5; batch.meta[:, 6] = m6
     # previous O3'
     uid = batch.unit_ids()
+    has_o3 = ((batch.bb_mask >> 5) & 1).tolist()
+    model, symmetry, chain = batch.model, batch.symmetry, batch.chain
+    src, dst = [], []
     for s in range(batch.n_structures):
         lo, hi = int(batch.struct_off[s]), int(batch.struct_off[s + 1])
-        order = sorted(range(lo, hi), key=lambda k: (batch.model[k], batch.symmetry[k] or "", batch.chain[k],
-                                                     batch.meta[k, 4], uid[k]))
+        order = sorted(range(lo, hi), key=lambda k: (model[k], symmetry[k] or "", chain[k], m4[k], uid[k]))
         prev = None
         for k in order:
-            if prev is not None and batch.model[k] == batch.model[prev] and batch.symmetry[k] == batch.symmetry[prev] \
-                    and batch.chain[k] == batch.chain[prev] and batch.meta[k, 4] == batch.meta[prev, 4] + 1:
-                if batch.bb_mask[prev] >> 5 & 1:     # O3' of the previous nt
-                    batch.bb_xyz[k, defs.BB_PREV_O3] = batch.bb_xyz[prev, 5]
-                    batch.bb_mask[k] |= np.uint32(1 << defs.BB_PREV_O3)
+            if prev is not None and model[k] == model[prev] and symmetry[k] == symmetry[prev] \
+                    and chain[k] == chain[prev] and m4[k] == m4[prev] + 1:
+                if has_o3[prev]:                     # O3' of the previous nt
+                    src.append(prev); dst.append(k)
             prev = k
+    if dst:
+        batch.bb_xyz[dst, defs.BB_PREV_O3] = batch.bb_xyz[src, 5]
+        batch.bb_mask[dst] |= np.uint32(1 << defs.BB_PREV_O3)
 
 
 def pack_specs(specs):
@@ -244,6 +297,7 @@ def pack_specs(specs):
         specs = [specs]
     n = sum(len(s["nts"]) for s in specs)
     b = NtBatch(n)
+    rows = _Rows()
     off = [0]
     k = 0
     for spec in specs:
@@ -255,13 +309,14 @@ def pack_specs(specs):
             b.alt_id.append(nt.get("alt_id")); b.insertion_code.append(nt.get("insertion_code"))
             maps = _slot_maps(seq)
             if maps is None:
-                b.meta[k, 0] = -1
+                rows.add_unknown()
             else:
-                _fill_atoms(b, k, maps, nt["atoms"])
+                _fill_atoms(rows, maps, nt["atoms"])
                 if not (maps[1] & _lib.FLAG_MODIFIED):
-                    _fix_amino_hydrogens(b, k, defs.PARENTS[maps[0]])
+                    _fix_amino_hydrogens(rows, defs.PARENTS[maps[0]])
             k += 1
         off.append(k)
+    rows.flush(b)
     b.struct_off = np.array(off, dtype=np.int64)
     _finish_identity(b)
     return b
@@ -283,9 +338,11 @@ def pack_structures(structures, chains=None):
     n = sum(len(c) for c in comps_per)
     b = NtBatch(n)
     b.frames_given = True
+    rows = _Rows()
     off = [0]
     k = 0
     uids = []
+    framed, rots, ctrs = [], [], []
     for st, comps in zip(structures, comps_per):
         b.pdb.append(getattr(st, "pdb", None))
         for c in comps:
@@ -296,17 +353,22 @@ def pack_structures(structures, chains=None):
             uids.append(c.unit_id())
             maps = _slot_maps(seq)
             if maps is None:
-                b.meta[k, 0] = -1
+                rows.add_unknown()
             else:
-                _fill_atoms(b, k, maps, ((a.name, a.x, a.y, a.z) for a in c.atoms()), frames_given=True)
+                _fill_atoms(rows, maps, ((a.name, a.x, a.y, a.z) for a in c.atoms()), frames_given=True)
                 R = c.rotation_matrix
                 ctr = c.centers["base"]
                 if R is not None and len(ctr) == 3:
-                    b.rot[k] = np.asarray(R, dtype=float).reshape(9)
-                    b.center[k] = np.asarray(ctr, dtype=float)
-                    b.base_mask[k] |= np.uint32(_lib.MASK_HAS_FRAME)
+                    framed.append(k)
+                    rots.append(np.asarray(R, dtype=float).reshape(9))
+                    ctrs.append(np.asarray(ctr, dtype=float))
+                    rows.bmask[-1] |= _lib.MASK_HAS_FRAME
             k += 1
         off.append(k)
+    rows.flush(b)
+    if framed:
+        b.rot[framed] = np.array(rots)
+        b.center[framed] = np.array(ctrs)
     b.struct_off = np.array(off, dtype=np.int64)
     b._unit_ids = uids
     _finish_identity(b)
