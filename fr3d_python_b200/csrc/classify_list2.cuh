@@ -143,6 +143,8 @@ classify_list2_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, cons
             nx1 = pair_i[q]; nx2 = pair_j[q]; nxr = pair_rank[q];
         }
         if (!__any_sync(FULL, active)) continue;
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(nts.base_mask + nx1));     // next round's masks
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(nts.base_mask + nx2));
         // ---------------- phase A staging
         __syncwarp();                                       // everybody is done with the previous round's rows
 #pragma unroll 2

@@ -198,6 +198,24 @@ classify_screen_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, con
         const TFrame f1 = load_tframe(nts, n1);
         const double *A_base = nts.base_xyz + (size_t)n1 * FR3D_BASE_SLOTS * 3;     // nt1: mostly warp-uniform addresses
         const double *A_bb = nts.bb_xyz + (size_t)n1 * FR3D_BB_SLOTS * 3;
+        // pull nt1's lines towards L1 now, while the staging copies are in flight: the first touches further down
+        // (site atoms in a serial loop, the cylinder pass) otherwise each wait for L2
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(A_base));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(A_base + 16));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(A_base + 32));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(A_base + 47));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(A_bb));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(A_bb + 16));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(A_bb + 29));
+        {   // ... and the next round's nt1 frame and masks (their indices are already here)
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(nts.center + (size_t)nx1 * 3));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(nts.rot + (size_t)nx1 * 9));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(nts.rot + (size_t)nx1 * 9 + 8));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(nts.base_mask + nx1));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(nts.base_mask + nx2));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(nts.bb_mask + nx1));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(nts.bb_mask + nx2));
+        }
         cp_async_wait_all();
         __syncwarp();
         const double *R = rows + lane * SCR_STRIDE;
