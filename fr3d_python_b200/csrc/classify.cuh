@@ -1,6 +1,8 @@
 // K4 building blocks: helpers, the per-pair shared-memory scratch and the out-of-line rare paths of the
 // one-warp-per-pair rule engine.  The kernel itself is in classify_pm.cuh (the first, pair-major kernel
-// that lived here is in the git history; profiles/README.md has its ncu numbers).
+// that lived here is in the git history; profiles/README.md has its ncu numbers).  Since the screened pipeline
+// (classify_screen.cuh -> classify_tpp.cuh / classify_list2.cuh) that warp-per-pair kernel only serves callers
+// that pass no workspace; the geometric helpers below (left_of, in_hull, in_ellipse, hb_angle...) serve every kernel.
 //
 // Replaces, per pair (nt1, nt2), in the reference's own evaluation order
 // (NA = fr3d/classifiers/NA_pairwise_interactions.py):

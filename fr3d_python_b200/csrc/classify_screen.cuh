@@ -6,7 +6,7 @@
 // that a pure thread-per-pair kernel is divergence bound (7.8 of 32 lanes active) because the rare, long
 // tails serialise the warp.  So the work is split: this kernel evaluates, one THREAD per pair and fully
 // converged, the cheap NECESSARY condition of every rule family (the same predicates the warp-per-pair
-// kernel votes on) and compacts the pairs that can still produce something into two work lists:
+// kernel votes on) and compacts the pairs that can still produce something into four work lists:
 //   light list    -> classify_pairs_tpp_kernel  (sO, sugar-ribose)
 //   phosphate list-> classify_pairs_tpp_kernel  (base-phosphate / base-ribose)
 //   stacking list -> classify_list2_kernel      (base stacking)
@@ -29,8 +29,6 @@ namespace fr3d {
 #define SCR_BPH 16u
 #define SCR_CP 32u
 #define SCR_BP 64u
-#define SCR_DETAIL (SCR_SO12 | SCR_SO21 | SCR_SR | SCR_BPH)
-#define SCR_GEOM (SCR_STACK | SCR_CP | SCR_BP)
 
 // Shared-memory row of one nt2 record (doubles), staged in two phases that re-use the same buffer so that twice as
 // many warps fit on an SM:
