@@ -33,7 +33,7 @@ def as_plain(result):
 
 
 # ------------------------------------------------------------------ frames (K1)
-@pytest.mark.parametrize("name", ["1gid_full", "1s72_strand", "1s72_sarcin"])
+@pytest.mark.parametrize("name", ["1gid_full", "1s72_strand", "1s72_sarcin", "1gid_variants"])
 def test_frames_and_hydrogens_match_reference(golden, name):
     spec = golden("spec_%s.json.gz" % name)
     want = golden("frames_%s.json.gz" % name)
@@ -160,6 +160,8 @@ def test_capacity_overflow_is_retried_not_truncated(golden):
     ("spec_1gid_full.json.gz", "annot_1gid_full_all9.json.gz"),
     ("spec_1gid_base.json.gz", "annot_1gid_base_bp_stack_cp.json.gz"),
     ("spec_1gid_base.json.gz", "annot_1gid_base_bp.json.gz"),
+    # DNA, missing atoms, alt-id twins, insertion codes, a second model and a symmetry copy (tools/make_golden.py variants)
+    ("spec_1gid_variants.json.gz", "annot_1gid_variants_all9.json.gz"),
 ])
 def test_annotation_identical_to_reference(golden, spec_name, annot_name):
     spec = golden(spec_name)

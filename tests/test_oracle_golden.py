@@ -26,6 +26,8 @@ def _close_rows(a, b, tol=0.0):
     ("spec_1gid_full.json.gz", "annot_1gid_full_all9.json.gz"),
     ("spec_1gid_base.json.gz", "annot_1gid_base_bp_stack_cp.json.gz"),
     ("spec_1gid_base.json.gz", "annot_1gid_base_bp.json.gz"),
+    # DNA, missing atoms, alt-id twins, insertion codes, a second model and a symmetry copy (tools/make_golden.py variants)
+    ("spec_1gid_variants.json.gz", "annot_1gid_variants_all9.json.gz"),
 ])
 def test_annotation_matches_reference(golden, spec_name, annot_name):
     spec = golden(spec_name)
@@ -51,7 +53,7 @@ def test_1gid_probe_counts(golden):
     assert "Found 154" in g["found_line"]
 
 
-@pytest.mark.parametrize("name", ["1gid_full", "1s72_strand", "1s72_sarcin"])
+@pytest.mark.parametrize("name", ["1gid_full", "1s72_strand", "1s72_sarcin", "1gid_variants"])
 def test_frames_match_reference(golden, name):
     spec = golden("spec_%s.json.gz" % name)
     frames = golden("frames_%s.json.gz" % name)

@@ -416,5 +416,76 @@ def main():
     dump("annot_1gid_modified_all9.json.gz", annotate_with_traces(modified, ALL9))
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and len(sys.argv) == 1:
     main()
+
+
+def make_spec_variants(full_spec):
+    """1GID-full with the identity / completeness corner cases the reference handles on its way to the rules:
+    DNA residues (DA DC DG DT, no O2'), missing backbone / glycosidic / base atoms, alt-id twins (NA:706-713),
+    an insertion-code pair, a second model (separate cubes, NA:424-436) and a symmetry copy (same cubes)."""
+    import copy
+    spec = copy.deepcopy(full_spec)
+    comps = residues(rf.ref_structure_from_spec(full_spec))
+    from fr3d.definitions import NAbasecoordinates
+    nts = spec["nts"]
+    for k, nt in enumerate(nts[:120]):
+        if k % 3 == 0 and nt["sequence"] in ("A", "C", "G"):
+            nt["sequence"] = "D" + nt["sequence"]
+            nt["atoms"] = [a for a in nt["atoms"] if a[0] != "O2'"]
+        elif k % 3 == 1 and nt["sequence"] == "U":
+            nt["sequence"] = "DT"
+            U = np.asarray(comps[k].rotation_matrix)
+            c7 = np.asarray(comps[k].centers["base"]) + U @ np.array(NAbasecoordinates["DT"]["C7"])
+            nt["atoms"] = [a for a in nt["atoms"] if a[0] != "O2'"] + [["C7", float(c7[0]), float(c7[1]), float(c7[2])]]
+        elif k % 7 == 2:
+            nt["atoms"] = [a for a in nt["atoms"] if a[0] not in ("P", "OP1", "O4'", "C2'")]
+        elif k % 11 == 5:
+            nt["atoms"] = [a for a in nt["atoms"] if a[0] not in ("N9", "N1")]
+        elif k % 13 == 6:
+            nt["atoms"] = [a for a in nt["atoms"] if a[0] not in ("N3", "O2", "C5")]
+    out = []
+    for k, nt in enumerate(nts):
+        if k in (130, 131, 200):                       # alt-id twins: same residue, conformers A and B
+            a = copy.deepcopy(nt); a["alt_id"] = "A"
+            b = copy.deepcopy(nt); b["alt_id"] = "B"
+            b["atoms"] = [[n, x + 0.25, y - 0.15, z + 0.2] for n, x, y, z in b["atoms"]]
+            out += [a, b]
+        elif k == 150:                                 # insertion codes: 150A follows 150
+            a = copy.deepcopy(nt)
+            out.append(a)
+        elif k == 151:
+            a = copy.deepcopy(nt)
+            a["number"] = nts[150]["number"]
+            a["insertion_code"] = "A"
+            out.append(a)
+        else:
+            out.append(nt)
+    first_chain = nts[0]["chain"]
+    model2 = []
+    for nt in nts[:40]:                                # second model: same place, must not pair with model 1
+        a = copy.deepcopy(nt)
+        a["model"] = "2"
+        a["atoms"] = [[n, x + 0.4, y, z] for n, x, y, z in a["atoms"]]
+        model2.append(a)
+    sym = []
+    for nt in nts[60:90]:                              # symmetry copy next to the original: pairs across copies
+        a = copy.deepcopy(nt)
+        a["symmetry"] = "2_655"
+        a["atoms"] = [[n, x + 9.0, y + 4.0, z - 6.0] for n, x, y, z in a["atoms"]]
+        sym.append(a)
+    assert first_chain
+    return {"pdb": "1GID", "nts": out + model2 + sym}
+
+
+def main_variants():
+    with gzip.open(os.path.join(GOLD, "spec_1gid_full.json.gz"), "rt") as f:
+        full = json.load(f)
+    variants = make_spec_variants(full)
+    dump("spec_1gid_variants.json.gz", variants)
+    dump("frames_1gid_variants.json.gz", frames_golden(variants))
+    dump("annot_1gid_variants_all9.json.gz", annotate_with_traces(variants, ALL9))
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "variants":
+    main_variants()
