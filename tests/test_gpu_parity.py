@@ -449,3 +449,19 @@ def test_alternate_classify_paths_give_the_same_hits(mode, tmp_path):
         assert np.array_equal(a[f], b[f]), f
     for f in ("cutoff_distance", "max_gap"):          # the warp-per-pair kernel sums the box terms in another fma pattern
         assert np.abs(a[f] - b[f]).max() < 1e-12, f
+
+
+@pytest.mark.parametrize("case", ["detail", "focus_cww_ths_stacking", "focus_cww_coplanar_covalent"])
+def test_category_subsets_and_focused_interactions(golden, case):
+    """Category subsets (work lists of families that were not asked for are not launched) and focused
+    interaction lists (smaller cutoff-box tables) against rows produced by the unmodified reference."""
+    spec = golden("spec_1gid_full.json.gz")
+    gg = golden("annot_1gid_full_category_subsets.json.gz")
+    g, uid = gg[case], gg["unit_ids"]
+    want = {k: [(uid[a], uid[b], c) for a, b, c in v] for k, v in g["interaction_to_list_of_tuples"].items()}
+    wantc = {k: set(v) for k, v in g["category_to_interactions"].items()}
+    i2t, c2i = as_plain(NA.annotate_batch(spec, g["categories"])[0])
+    assert i2t == want and c2i == wantc
+    st = Structure.from_spec(spec)
+    r = NA.annotate_nt_nt_in_structure(st, g["categories"])
+    assert as_plain(r) == (want, wantc)

@@ -167,3 +167,15 @@ def test_modified_residues_match_reference(golden):
     _close_rows(tr["coplanar"], g["traces"]["coplanar"])
     _close_rows(tr["basepair"], g["traces"]["basepair"])
     assert {k: [list(t) for t in v] for k, v in out.items()} == g["interaction_to_list_of_tuples"]
+
+
+@pytest.mark.parametrize("case", ["detail", "focus_cww_ths_stacking", "focus_cww_coplanar_covalent"])
+def test_category_subsets_and_focused_interactions(golden, case):
+    """Category subsets and focused interaction lists (focus_basepair_cutoffs, NA:88-136) against the reference."""
+    spec = golden("spec_1gid_full.json.gz")
+    g = golden("annot_1gid_full_category_subsets.json.gz")[case]
+    out, c2i, tr = O.annotate(spec, g["categories"])
+    got = {k: [list(t) for t in v] for k, v in out.items()}
+    assert got == g["interaction_to_list_of_tuples"]
+    assert {k: sorted(v) for k, v in c2i.items()} == g["category_to_interactions"]
+    assert "Found %d nucleotide" % tr["count_pair"] in g["found_line"]

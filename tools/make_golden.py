@@ -489,3 +489,23 @@ def main_variants():
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "variants":
     main_variants()
+
+
+def main_category_subsets():
+    """Category subsets ('basepair' must always be a key: the reference indexes categories['basepair'], NA:1216) and
+    focused interaction lists (focus_basepair_cutoffs keeps only the listed families, NA:88-136)."""
+    with gzip.open(os.path.join(GOLD, "spec_1gid_full.json.gz"), "rt") as f:
+        full = json.load(f)
+    out = {}
+    for name, cats in [("detail", {'basepair': [], 'sO': [], 'backbone': [], 'sugar_ribose': []}),
+                       ("focus_cww_ths_stacking", {'basepair': ['cWW', 'tHS'], 'stacking': []}),
+                       ("focus_cww_coplanar_covalent", {'basepair': ['cWW'], 'coplanar': [], 'covalent': []})]:
+        g = annotate_with_traces(full, cats)
+        out[name] = {"categories": cats, "interaction_to_list_of_tuples": g["interaction_to_list_of_tuples"],
+                     "category_to_interactions": g["category_to_interactions"], "found_line": g["found_line"]}
+    out["unit_ids"] = g["unit_ids"]
+    dump("annot_1gid_full_category_subsets.json.gz", out)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "subsets":
+    main_category_subsets()
