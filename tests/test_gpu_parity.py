@@ -263,6 +263,12 @@ def test_custom_cutoff_tables_against_oracle(golden, only_largest):
     want, wc, _, _ = oracle_tuples(spec, ALL9, focused=focused)
     got = as_plain(NA.annotate_batch(spec, ALL9, focused_basepair_cutoffs=focused)[0])
     assert got == (want, wc)
+    # ... and against the rows the unmodified reference produced with the same table (tools/make_golden.py cutoffs)
+    gg = golden("annot_1gid_full_custom_cutoffs.json.gz")
+    g, uid = gg["only_largest" if only_largest else "all"], gg["unit_ids"]
+    ref = {k: [(uid[a], uid[b], c) for a, b, c in v] for k, v in g["interaction_to_list_of_tuples"].items() if v}
+    assert got[0] == ref
+    assert got[1] == {k: set(v) for k, v in g["category_to_interactions"].items() if v}
     if not only_largest:
         base_want, _, _, _ = oracle_tuples(spec, ALL9)
         assert want != base_want                   # the inflated table really changes the annotation

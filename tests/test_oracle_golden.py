@@ -179,3 +179,35 @@ def test_category_subsets_and_focused_interactions(golden, case):
     assert got == g["interaction_to_list_of_tuples"]
     assert {k: sorted(v) for k, v in c2i.items()} == g["category_to_interactions"]
     assert "Found %d nucleotide" % tr["count_pair"] in g["found_line"]
+
+
+def _inflated_cutoffs(only_largest):
+    """Same table as tools/make_golden.py::inflated_cutoffs, built from the oracle's copy of the shipped tables."""
+    import copy
+    focused = copy.deepcopy(O.focus_basepair_cutoffs(O.nt_nt_cutoffs(), []))
+    sizes = {(c, sg): sum(len(v) for v in focused[c][sg].values()) for c in focused for sg in focused[c]}
+    largest = max(sizes, key=sizes.get)
+    for c in focused:
+        for sg in focused[c]:
+            if only_largest and (c, sg) != largest:
+                continue
+            for inter, subs in focused[c][sg].items():
+                for sub in list(subs.keys()):
+                    box = dict(subs[sub])
+                    for k in ("xmin", "xmax", "ymin", "ymax"):
+                        box[k] = box[k] + 0.35
+                    box["gapmax"] = box.get("gapmax", 0.0) + 0.2
+                    subs[sub + 50] = box
+    return focused
+
+
+@pytest.mark.parametrize("only_largest", [True, False])
+def test_caller_supplied_cutoff_table(golden, only_largest):
+    """focused_basepair_cutoffs passed by the caller (third argument of annotate_nt_nt_in_structure, NA:1213)."""
+    spec = golden("spec_1gid_full.json.gz")
+    g = golden("annot_1gid_full_custom_cutoffs.json.gz")["only_largest" if only_largest else "all"]
+    categories = {k: [] for k in ("basepair", "basepair_detail", "stacking", "sO", "backbone", "coplanar",
+                                  "sugar_ribose", "covalent", "near")}
+    out, c2i, _ = O.annotate(spec, categories, focused=_inflated_cutoffs(only_largest))
+    assert {k: [list(t) for t in v] for k, v in out.items()} == g["interaction_to_list_of_tuples"]
+    assert {k: sorted(v) for k, v in c2i.items()} == g["category_to_interactions"]

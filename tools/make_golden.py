@@ -509,3 +509,48 @@ def main_category_subsets():
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "subsets":
     main_category_subsets()
+
+
+def inflated_cutoffs(NA, only_largest):
+    """The table of tests/test_gpu_parity.py::_inflated_cutoffs, built from the reference's own tables."""
+    import copy
+    focused = copy.deepcopy(NA.focus_basepair_cutoffs(NA.nt_nt_cutoffs, []))
+    sizes = {(c, sg): sum(len(v) for v in focused[c][sg].values()) for c in focused for sg in focused[c]}
+    largest = max(sizes, key=sizes.get)
+    for c in focused:
+        for sg in focused[c]:
+            if only_largest and (c, sg) != largest:
+                continue
+            for inter, subs in focused[c][sg].items():
+                for sub in list(subs.keys()):
+                    box = dict(subs[sub])
+                    for k in ("xmin", "xmax", "ymin", "ymax"):
+                        box[k] = box[k] + 0.35
+                    box["gapmax"] = box.get("gapmax", 0.0) + 0.2
+                    subs[sub + 50] = box
+    return focused
+
+
+def main_custom_cutoffs():
+    """Caller-supplied focused_basepair_cutoffs (third argument of annotate_nt_nt_in_structure)."""
+    from fr3d.classifiers import NA_pairwise_interactions as NA
+    with gzip.open(os.path.join(GOLD, "spec_1gid_full.json.gz"), "rt") as f:
+        full = json.load(f)
+    out = {}
+    for only_largest in (True, False):
+        structure = rf.ref_structure_from_spec(full)
+        comps = residues(structure)
+        idx = {c.unit_id(): k for k, c in enumerate(comps)}
+        focused = inflated_cutoffs(NA, only_largest)
+        with contextlib.redirect_stdout(io.StringIO()):
+            result = NA.annotate_nt_nt_in_structure(structure, ALL9, focused)
+        out["only_largest" if only_largest else "all"] = {
+            "interaction_to_list_of_tuples": {label: [[idx[a], idx[b], c] for a, b, c in lst]
+                                              for label, lst in result[0].items()},
+            "category_to_interactions": {cat: sorted(v) for cat, v in result[1].items()}}
+        out["unit_ids"] = [c.unit_id() for c in comps]
+    dump("annot_1gid_full_custom_cutoffs.json.gz", out)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "cutoffs":
+    main_custom_cutoffs()
