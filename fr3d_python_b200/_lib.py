@@ -112,7 +112,7 @@ def load():
         lib.fr3d_pair_search_workspace.argtypes = [i32]
         lib.fr3d_pair_search_workspace.restype = C.c_size_t
         lib.fr3d_pair_search.argtypes = [C.POINTER(NtsStruct), dbl, vp, C.c_size_t, vp, vp, vp, i64, vp, vp]
-        lib.fr3d_classify_workspace.argtypes = [i64]
+        lib.fr3d_classify_workspace.argtypes = [i64, i32]
         lib.fr3d_classify_workspace.restype = C.c_size_t
         lib.fr3d_classify_pairs.argtypes = [C.POINTER(NtsStruct), vp, vp, vp, vp, vp, i64, C.c_uint32, i32, vp,
                                             C.c_size_t, vp, i64, vp, vp]

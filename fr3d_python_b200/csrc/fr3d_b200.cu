@@ -16,6 +16,7 @@
 #include "classify_pm.cuh"
 #include "classify_tpp.cuh"
 #include "classify_screen.cuh"
+#include "classify_screen32.cuh"
 #include "classify_list2.cuh"
 #include "geometry.cuh"
 
@@ -82,6 +83,8 @@ int fr3d_init(int device) {
     // opt in to the large dynamic shared-memory carve-outs once per device (not on every call)
     CUDA_TRY(cudaFuncSetAttribute(fr3d::classify_screen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)fr3d::SCR_SMEM));
+    CUDA_TRY(cudaFuncSetAttribute(fr3d::classify_screen32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)fr3d::S32_SMEM));
     CUDA_TRY(cudaFuncSetAttribute(fr3d::classify_list2_kernel<false, fr3d::L2_WARPS_STACK>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)fr3d::l2_smem_bytes<false, fr3d::L2_WARPS_STACK>()));
@@ -146,9 +149,11 @@ int fr3d_pair_search(const fr3d_nts_t *nts, double cell_size, void *workspace, s
     return FR3D_OK;
 }
 
-size_t fr3d_classify_workspace(int64_t pair_cap) {
+size_t fr3d_classify_workspace(int64_t pair_cap, int32_t n_nt) {
     if (pair_cap < 0) pair_cap = 0;
-    return 4 * align_up(sizeof(int32_t) * (size_t)pair_cap, 256) + 256;
+    if (n_nt < 0) n_nt = 0;
+    return 4 * align_up(sizeof(int32_t) * (size_t)pair_cap, 256) +
+           align_up(sizeof(float) * fr3d::S32_REC * (size_t)n_nt, 256) + 256;
 }
 
 int fr3d_classify_pairs(const fr3d_nts_t *nts, const fr3d_box_t *boxes, const int32_t *box_index,
@@ -162,15 +167,17 @@ int fr3d_classify_pairs(const fr3d_nts_t *nts, const fr3d_box_t *boxes, const in
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // Tuning knobs (environment): FR3D_CLASSIFY_MODE 2 = screen + two work-list kernels (default when a
     // workspace is given), 1 = thread-per-pair kernel over all pairs, 0 = warp-per-pair kernel over all pairs.
-    static int mult = -1, mode = -1;
+    static int mult = -1, mode = -1, screen64 = 0;
     if (mult < 0) {
+        const char *s64 = getenv("FR3D_SCREEN");
+        screen64 = s64 && atoi(s64) == 64;
         const char *e = getenv("FR3D_CLASSIFY_GRID_MULT");
         mult = (e && atoi(e) > 0) ? atoi(e) : 0;
         const char *m = getenv("FR3D_CLASSIFY_MODE");
         mode = m ? atoi(m) : 2;
     }
     int use_mode = mode;
-    if (use_mode == 2 && (!workspace || workspace_bytes < fr3d_classify_workspace(pair_cap))) use_mode = 0;
+    if (use_mode == 2 && (!workspace || workspace_bytes < fr3d_classify_workspace(pair_cap, nts->n_nt))) use_mode = 0;
     const long long tpp_grid_max = (long long)g_sm_count * (mult ? mult : 4 * FR3D_TPP_MIN_BLOCKS);
     const long long pm_grid_max = (long long)g_sm_count * (mult ? mult : FR3D_CLASSIFY_MIN_BLOCKS);
     const long long per_block = (long long)fr3d::WARPS_PER_BLOCK * fr3d::PM_K;
@@ -184,11 +191,24 @@ int fr3d_classify_pairs(const fr3d_nts_t *nts, const fr3d_box_t *boxes, const in
         int32_t *wl_pair = reinterpret_cast<int32_t *>(wsp + 2 * list_bytes);
         int32_t *wl_bph = reinterpret_cast<int32_t *>(wsp + 3 * list_bytes);
         CUDA_TRY(cudaMemsetAsync(counters + 4, 0, 4 * sizeof(int64_t), st));
-        const int scr_threads = fr3d::SCR_WARPS * 32;
-        fr3d::classify_screen_kernel<<<clampg((pair_cap + scr_threads - 1) / scr_threads,
-                                              (long long)g_sm_count * (mult ? mult : 1)),
-                                       scr_threads, fr3d::SCR_SMEM, st>>>(
-            *nts, boxes, box_index, pair_i, pair_j, pair_cap, category_mask, wl_light, wl_stack, wl_pair, wl_bph, counters);
+        if (screen64) {          // the double-precision screen, kept for A/B runs
+            const int scr_threads = fr3d::SCR_WARPS * 32;
+            fr3d::classify_screen_kernel<<<clampg((pair_cap + scr_threads - 1) / scr_threads,
+                                                  (long long)g_sm_count * (mult ? mult : 1)),
+                                           scr_threads, fr3d::SCR_SMEM, st>>>(
+                *nts, boxes, box_index, pair_i, pair_j, pair_cap, category_mask, wl_light, wl_stack, wl_pair, wl_bph, counters);
+        } else {
+            // single-precision screen records (classify_screen32.cuh), then the screen itself on them
+            float *srec = reinterpret_cast<float *>(wsp + 4 * list_bytes);
+            if (nts->n_nt > 0)
+                fr3d::screen_records_kernel<<<(nts->n_nt + fr3d::SREC_NTS - 1) / fr3d::SREC_NTS, fr3d::SREC_THREADS, 0, st>>>(
+                *nts, srec, counters);
+            const int scr_threads = fr3d::S32_WARPS * 32;
+            fr3d::classify_screen32_kernel<<<clampg((pair_cap + scr_threads - 1) / scr_threads,
+                                                    (long long)g_sm_count * (mult ? mult : 1)),
+                                             scr_threads, fr3d::S32_SMEM, st>>>(
+                srec, boxes, box_index, pair_i, pair_j, pair_cap, category_mask, wl_light, wl_stack, wl_pair, wl_bph, counters);
+        }
         // one thread-per-pair launch per list, each instantiation compiled with its own rule families only
         const int tpp_grid = clampg((pair_cap + 127) / 128, tpp_grid_max);
         constexpr uint32_t LIGHT_CATS = FR3D_CAT_SO | FR3D_CAT_SUGAR_RIBOSE;

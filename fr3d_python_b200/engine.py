@@ -204,7 +204,7 @@ class Engine(object):
         p.pair_j = torch.empty(p.pair_cap, dtype=torch.int32, device=dev)
         p.pair_rank = torch.empty(p.pair_cap, dtype=torch.int32, device=dev)
         p.counters = torch.zeros(8, dtype=torch.int64, device=dev)
-        p.cws_bytes = int(self.lib.fr3d_classify_workspace(p.pair_cap))
+        p.cws_bytes = int(self.lib.fr3d_classify_workspace(p.pair_cap, n_nt))
         p.cws = torch.empty(p.cws_bytes, dtype=torch.uint8, device=dev)
         p.hits = torch.empty(p.hit_cap * HIT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
         p.status = torch.empty(max(n_nt, 1), dtype=torch.int32, device=dev)
@@ -236,9 +236,10 @@ class Engine(object):
                                                     int(index_offset), plan.cws.data_ptr(), plan.cws_bytes,
                                                     plan.hits.data_ptr(), plan.hit_cap, plan.counters.data_ptr(), st),
                        "fr3d_classify_pairs")
-            # screen + one thread-per-pair kernel per work list (lists of families that were not requested are skipped)
+            # screen records + screen + one thread-per-pair kernel per work list (lists of families that were not
+            # requested are skipped)
             cm = int(category_mask)
-            self.launches += 2 + (1 if cm & (_lib.CAT_SO | _lib.CAT_SUGAR_RIBOSE) else 0) + \
+            self.launches += 3 + (1 if cm & (_lib.CAT_SO | _lib.CAT_SUGAR_RIBOSE) else 0) + \
                 (1 if cm & _lib.CAT_BACKBONE else 0) + (1 if cm & _lib.CAT_STACKING else 0)
             if events is not None:
                 events["classify1"].record()

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define FR3D_ABI_VERSION 1
+#define FR3D_ABI_VERSION 2
 
 #define FR3D_OK 0
 #define FR3D_E_CUDA (-1)      /* a CUDA runtime call failed; see fr3d_last_error */
@@ -172,12 +172,14 @@ int fr3d_pair_search(const fr3d_nts_t *nts, double cell_size, void *workspace, s
  * hits compacted with a warp-aggregated atomic.
  * n_pairs is read from counters[0] on the device (clamped to pair_cap).  index_offset is added to the
  * nt indices (and 16 x to the rank) written into the hit records, so that chunks of a larger batch
- * produce globally indexed hits.  workspace (fr3d_classify_workspace(pair_cap) bytes, may be NULL): work lists
- * of the screen kernel; with it the call is five launches: a thread-per-pair screen of the cheap necessary
- * conditions of every rule family, then one thread-per-pair launch per work list (sO / sugar-ribose; BPh / BR;
- * stacking; coplanar / basepair) over the pairs that passed; without it one warp-per-pair launch over all
- * pairs. */
-size_t fr3d_classify_workspace(int64_t pair_cap);
+ * produce globally indexed hits.  workspace (fr3d_classify_workspace(pair_cap, n_nt) bytes, may be NULL): work
+ * lists of the screen kernel and its single-precision copy of the records (320 B per nt); with it the call is
+ * six launches: the screen records, a thread-per-pair single-precision screen of the cheap necessary conditions
+ * of every rule family (thresholds relaxed by margins far above fp32 rounding, so it is a superset), then one
+ * thread-per-pair fp64 launch per work list (sO / sugar-ribose; BPh / BR; stacking; coplanar / basepair) over the
+ * pairs that passed; without it one warp-per-pair launch over all pairs.  Every label and number in a hit record
+ * is decided in fp64.  Base centres must lie within +-32 000 A (else counters[2] != 0, FR3D_E_RANGE). */
+size_t fr3d_classify_workspace(int64_t pair_cap, int32_t n_nt);
 int fr3d_classify_pairs(const fr3d_nts_t *nts, const fr3d_box_t *boxes, const int32_t *box_index /*[25][2][2]*/,
                         const int32_t *pair_i, const int32_t *pair_j, const int32_t *pair_rank,
                         int64_t pair_cap, uint32_t category_mask, int32_t index_offset, void *workspace,

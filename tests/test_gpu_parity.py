@@ -438,7 +438,7 @@ def test_alternate_classify_paths_give_the_same_hits(mode, tmp_path):
         "from fr3d_python_b200 import synthetic\n"
         "from fr3d_python_b200.classifiers import NA_pairwise_interactions as NA\n"
         "from fr3d_python_b200.engine import Engine\n"
-        "batch = synthetic.make_structure_batch(synthetic.pack_base(), 5, seed0=77)\n"
+        "batch = synthetic.make_structure_batch(synthetic.pack_base(), 40, seed0=77)\n"
         "bt, _ = NA._box_table(NA._default_focused(ALL9['basepair']), NA.load_ideal_basepair_hydrogen_bonds())\n"
         "hits, n_pairs, _ = Engine.get().annotate_batch(batch, bt, NA.category_mask(ALL9))\n"
         "order = np.lexsort((hits['slot'], hits['j'], hits['i'], hits['rank']))\n"
@@ -450,11 +450,51 @@ def test_alternate_classify_paths_give_the_same_hits(mode, tmp_path):
         subprocess.run([sys.executable, "-c", code, out], check=True, env=env, cwd=root)
         outs.append(np.load(out))
     a, b = outs
-    assert len(a) > 1000 and len(a) == len(b)
+    assert len(a) > 20000 and len(a) == len(b)
     for f in ("i", "j", "rank", "slot", "code", "box"):
         assert np.array_equal(a[f], b[f]), f
     for f in ("cutoff_distance", "max_gap"):          # the warp-per-pair kernel sums the box terms in another fma pattern
         assert np.abs(a[f] - b[f]).max() < 1e-12, f
+
+
+@pytest.mark.parametrize("shift", [0.0, 24000.0])
+def test_single_precision_screen_is_a_superset(shift, tmp_path):
+    """The fp32 screen (classify_screen32.cuh) must let through every pair the fp64 screen lets through - so the
+    hit records (decided in fp64 by the list kernels) are bit-identical - also when the structures sit 24 000 A
+    from the origin, where a plain fp32 coordinate would carry 2e-3 A (the records hold fixed-point centres and
+    centre-relative coordinates instead).  FR3D_SCREEN is read once per process, hence the subprocess."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, numpy as np\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "from conftest import ALL9\n"
+        "from fr3d_python_b200 import synthetic\n"
+        "from fr3d_python_b200.classifiers import NA_pairwise_interactions as NA\n"
+        "from fr3d_python_b200.engine import Engine\n"
+        "batch = synthetic.make_structure_batch(synthetic.pack_base(), 120, seed0=9100)\n"
+        "batch.base_xyz += %r; batch.bb_xyz += %r\n"
+        "bt, _ = NA._box_table(NA._default_focused(ALL9['basepair']), NA.load_ideal_basepair_hydrogen_bonds())\n"
+        "hits, n_pairs, ex = Engine.get().annotate_batch(batch, bt, NA.category_mask(ALL9))\n"
+        "order = np.lexsort((hits['slot'], hits['j'], hits['i'], hits['rank']))\n"
+        "np.save(sys.argv[1], hits[order])\n"
+        "np.save(sys.argv[1] + '.lists.npy', ex['plan'].counters.cpu().numpy())\n"
+        % (root, os.path.join(root, "tests"), shift, shift))
+    outs, lists = [], []
+    for m in ("32", "64"):
+        out = str(tmp_path / ("hits_screen%s.npy" % m))
+        env = dict(os.environ, FR3D_SCREEN=m)
+        subprocess.run([sys.executable, "-c", code, out], check=True, env=env, cwd=root)
+        outs.append(np.load(out))
+        lists.append(np.load(out + ".lists.npy"))
+    a, b = outs
+    assert len(a) > 50000 and len(a) == len(b)
+    assert a.tobytes() == b.tobytes()
+    assert lists[0][0] == lists[1][0] and lists[0][1] == lists[1][1]            # pairs, hits
+    assert np.all(lists[0][4:8] >= lists[1][4:8])                               # every work list at least as long ...
+    assert np.all(lists[0][4:8] <= 1.02 * lists[1][4:8] + 16)                   # ... and the margins cost < 2 %
 
 
 @pytest.mark.parametrize("case", ["detail", "focus_cww_ths_stacking", "focus_cww_coplanar_covalent"])
