@@ -72,7 +72,7 @@ classify_list2_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, cons
                       const int32_t *__restrict__ pair_i, const int32_t *__restrict__ pair_j,
                       const int32_t *__restrict__ pair_rank, int64_t pair_cap, uint32_t cats, int32_t index_offset,
                       fr3d_hit_t *__restrict__ hits, int64_t hit_cap, int64_t *counters,
-                      const int32_t *__restrict__ worklist, int list_counter) {
+                      const int32_t *__restrict__ worklist, int list_counter, const int64_t *list_len = nullptr) {
     extern __shared__ double l2_smem[];
     __shared__ double s_hull[FR3D_N_PARENTS * 7 * 3];        // a per-lane parent index would serialise constant loads
     __shared__ double s_r2in[FR3D_N_PARENTS];
@@ -119,7 +119,7 @@ classify_list2_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, cons
     }
     const double *src_b0 = nts.base_xyz + lane, *src_b1 = nts.base_xyz + 32 + lane;
 
-    long long n_pairs = counters[list_counter];
+    long long n_pairs = list_len ? *list_len : counters[list_counter];       // (list_len: a length kept outside counters)
     if (n_pairs > pair_cap) n_pairs = pair_cap;
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long first = (long long)blockIdx.x * blockDim.x + threadIdx.x;

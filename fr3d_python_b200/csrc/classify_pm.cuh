@@ -17,6 +17,9 @@
 namespace fr3d {
 
 static constexpr int PM_K = 4;
+// internal category bit: skip the coplanar / basepair phases (the kernel then serves as the fp64 fallback of a single
+// rule family, e.g. the undecided pairs of the single-precision stacking kernel)
+#define PM_CAT_NO_PAIRING 0x80000000u
 #ifndef PM_UNROLL
 #define PM_UNROLL 1
 #endif
@@ -63,7 +66,7 @@ classify_pairs_pm_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, c
                          const int32_t *__restrict__ pair_i, const int32_t *__restrict__ pair_j,
                          const int32_t *__restrict__ pair_rank, int64_t pair_cap, uint32_t cats, int32_t index_offset,
                          fr3d_hit_t *__restrict__ hits, int64_t hit_cap, int64_t *counters,
-                         const int32_t *__restrict__ worklist) {
+                         const int32_t *__restrict__ worklist, const int64_t *list_len = nullptr) {
     __shared__ PairState s_state[WARPS_PER_BLOCK][PM_K];
 
     const int lane = threadIdx.x & 31;
@@ -71,7 +74,8 @@ classify_pairs_pm_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, c
     const long long warp0 = (long long)blockIdx.x * WARPS_PER_BLOCK + (threadIdx.x >> 5);
     const long long nwarps = (long long)gridDim.x * WARPS_PER_BLOCK;
     // with a work list (classify_screen.cuh) the kernel walks its entries instead of the whole pair list
-    long long n_pairs = worklist ? counters[5] : counters[0];
+    // (list_len: the length of a work list kept outside counters - the undecided pairs of classify_stack32.cuh)
+    long long n_pairs = list_len ? *list_len : (worklist ? counters[5] : counters[0]);
     if (n_pairs > pair_cap) n_pairs = pair_cap;
     const int half = lane >> 4;      // 0: atoms of nt2 seen from frame 1, 1: atoms of nt1 seen from frame 2
     const int a = lane & 15;
@@ -305,7 +309,7 @@ classify_pairs_pm_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, c
             const uint32_t bm1 = P.bm1, bm2 = P.bm2;
             const int par1 = (int)((bm1 >> 16) & 15u) - 1, par2 = (int)((bm2 >> 16) & 15u) - 1;
             const bool gly_ok = (bm1 & 1u) && (bm2 & 1u) && par1 >= 0 && par2 >= 0;   // NA:674, 834-837
-            if (!gly_ok) continue;
+            if (!gly_ok || (cats & PM_CAT_NO_PAIRING)) continue;
             unsigned ori_ok = 0, bp_live = 0;
             bool cp_frames = false;
             if (c_tab.combo_ok[par1 * FR3D_N_PARENTS + par2]) ori_ok |= 1u;

@@ -58,7 +58,8 @@ __global__ void __launch_bounds__(SREC_THREADS) screen_records_kernel(fr3d_nts_t
     const int cnt = min(SREC_NTS, nts.n_nt - n0);
     if (cnt <= 0) return;
     const int tid = threadIdx.x;
-    if (cnt == SREC_NTS) {        // full block: every plane segment starts on a 16-byte boundary (32 nts x an even count of doubles)
+    const bool aligned16 = (((size_t)nts.center | (size_t)nts.rot | (size_t)nts.bb_xyz | (size_t)nts.base_xyz) & 15) == 0;
+    if (cnt == SREC_NTS && aligned16) {   // every plane segment of a full block then starts on a 16-byte boundary
         for (int t = tid; t < SREC_NTS * 3 / 2; t += SREC_THREADS) cp_async16(sd + SREC_C + 2 * t, nts.center + (size_t)n0 * 3 + 2 * t);
         for (int t = tid; t < SREC_NTS * 9 / 2; t += SREC_THREADS) cp_async16(sd + SREC_U + 2 * t, nts.rot + (size_t)n0 * 9 + 2 * t);
         for (int t = tid; t < SREC_NTS * FR3D_BB_SLOTS * 3 / 2; t += SREC_THREADS)

@@ -18,6 +18,7 @@
 #include "classify_screen.cuh"
 #include "classify_screen32.cuh"
 #include "classify_list2.cuh"
+#include "classify_stack32.cuh"
 #include "geometry.cuh"
 
 namespace {
@@ -85,6 +86,8 @@ int fr3d_init(int device) {
                                   (int)fr3d::SCR_SMEM));
     CUDA_TRY(cudaFuncSetAttribute(fr3d::classify_screen32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)fr3d::S32_SMEM));
+    CUDA_TRY(cudaFuncSetAttribute(fr3d::classify_stack32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)fr3d::ST32_SMEM));
     CUDA_TRY(cudaFuncSetAttribute(fr3d::classify_list2_kernel<false, fr3d::L2_WARPS_STACK>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)fr3d::l2_smem_bytes<false, fr3d::L2_WARPS_STACK>()));
@@ -152,7 +155,7 @@ int fr3d_pair_search(const fr3d_nts_t *nts, double cell_size, void *workspace, s
 size_t fr3d_classify_workspace(int64_t pair_cap, int32_t n_nt) {
     if (pair_cap < 0) pair_cap = 0;
     if (n_nt < 0) n_nt = 0;
-    return 4 * align_up(sizeof(int32_t) * (size_t)pair_cap, 256) +
+    return 5 * align_up(sizeof(int32_t) * (size_t)pair_cap, 256) +
            align_up(sizeof(float) * fr3d::S32_REC * (size_t)n_nt, 256) + 256;
 }
 
@@ -167,10 +170,12 @@ int fr3d_classify_pairs(const fr3d_nts_t *nts, const fr3d_box_t *boxes, const in
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // Tuning knobs (environment): FR3D_CLASSIFY_MODE 2 = screen + two work-list kernels (default when a
     // workspace is given), 1 = thread-per-pair kernel over all pairs, 0 = warp-per-pair kernel over all pairs.
-    static int mult = -1, mode = -1, screen64 = 0;
+    static int mult = -1, mode = -1, screen64 = 0, stack64 = 0;
     if (mult < 0) {
         const char *s64 = getenv("FR3D_SCREEN");
         screen64 = s64 && atoi(s64) == 64;
+        const char *t64 = getenv("FR3D_STACK");
+        stack64 = screen64 || (t64 && atoi(t64) == 64);          // the fp32 stacking kernel reads the screen records
         const char *e = getenv("FR3D_CLASSIFY_GRID_MULT");
         mult = (e && atoi(e) > 0) ? atoi(e) : 0;
         const char *m = getenv("FR3D_CLASSIFY_MODE");
@@ -199,7 +204,7 @@ int fr3d_classify_pairs(const fr3d_nts_t *nts, const fr3d_box_t *boxes, const in
                 *nts, boxes, box_index, pair_i, pair_j, pair_cap, category_mask, wl_light, wl_stack, wl_pair, wl_bph, counters);
         } else {
             // single-precision screen records (classify_screen32.cuh), then the screen itself on them
-            float *srec = reinterpret_cast<float *>(wsp + 4 * list_bytes);
+            float *srec = reinterpret_cast<float *>(wsp + 5 * list_bytes);
             if (nts->n_nt > 0)
                 fr3d::screen_records_kernel<<<(nts->n_nt + fr3d::SREC_NTS - 1) / fr3d::SREC_NTS, fr3d::SREC_THREADS, 0, st>>>(
                 *nts, srec, counters);
@@ -224,11 +229,29 @@ int fr3d_classify_pairs(const fr3d_nts_t *nts, const fr3d_box_t *boxes, const in
         constexpr int ts = fr3d::L2_WARPS_STACK * 32, tp = fr3d::L2_WARPS_PAIR * 32;
         const int grid_s = clampg((pair_cap + ts - 1) / ts, (long long)g_sm_count * (mult ? mult : 1));
         const int grid_p = clampg((pair_cap + tp - 1) / tp, (long long)g_sm_count * (mult ? mult : 1));
-        if (category_mask & FR3D_CAT_STACKING)
+        if ((category_mask & FR3D_CAT_STACKING) && stack64) {
             fr3d::classify_list2_kernel<false, fr3d::L2_WARPS_STACK>
                 <<<grid_s, ts, fr3d::l2_smem_bytes<false, fr3d::L2_WARPS_STACK>(), st>>>(
                     *nts, boxes, box_index, pair_i, pair_j, pair_rank, pair_cap, FR3D_CAT_STACKING, index_offset, hits,
                     hit_cap, counters, wl_stack, 5);
+        } else if (category_mask & FR3D_CAT_STACKING) {
+            // single precision where every comparison is certain, the undecided pairs through the fp64 kernel
+            // (classify_stack32.cuh); the undecided list and its length live in the workspace
+            int32_t *wl_unc = reinterpret_cast<int32_t *>(wsp + 4 * list_bytes);
+            unsigned long long *unc_count = reinterpret_cast<unsigned long long *>(
+                wsp + 5 * list_bytes + align_up(sizeof(float) * fr3d::S32_REC * (size_t)nts->n_nt, 256));
+            CUDA_TRY(cudaMemsetAsync(unc_count, 0, sizeof(unsigned long long), st));
+            const float *srec = reinterpret_cast<const float *>(wsp + 5 * list_bytes);
+            constexpr int t32 = fr3d::ST32_WARPS * 32;
+            fr3d::classify_stack32_kernel<<<clampg((pair_cap + t32 - 1) / t32, (long long)g_sm_count * (mult ? mult : 1)),
+                                            t32, fr3d::ST32_SMEM, st>>>(
+                srec, pair_i, pair_j, pair_rank, pair_cap, index_offset, hits, hit_cap, counters, wl_stack, 5, wl_unc,
+                unc_count);
+            // few pairs: the warp-per-pair kernel has by far the shortest latency per pair
+            fr3d::classify_pairs_pm_kernel<<<g_sm_count * FR3D_CLASSIFY_MIN_BLOCKS, fr3d::WARPS_PER_BLOCK * 32, 0, st>>>(
+                *nts, boxes, box_index, pair_i, pair_j, pair_rank, pair_cap, FR3D_CAT_STACKING | PM_CAT_NO_PAIRING,
+                index_offset, hits, hit_cap, counters, wl_unc, reinterpret_cast<const int64_t *>(unc_count));
+        }
         fr3d::classify_list2_kernel<true, fr3d::L2_WARPS_PAIR>
             <<<grid_p, tp, fr3d::l2_smem_bytes<true, fr3d::L2_WARPS_PAIR>(), st>>>(
                 *nts, boxes, box_index, pair_i, pair_j, pair_rank, pair_cap, category_mask & FR3D_CAT_COPLANAR,

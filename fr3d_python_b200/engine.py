@@ -240,7 +240,7 @@ class Engine(object):
             # requested are skipped)
             cm = int(category_mask)
             self.launches += 3 + (1 if cm & (_lib.CAT_SO | _lib.CAT_SUGAR_RIBOSE) else 0) + \
-                (1 if cm & _lib.CAT_BACKBONE else 0) + (1 if cm & _lib.CAT_STACKING else 0)
+                (1 if cm & _lib.CAT_BACKBONE else 0) + (2 if cm & _lib.CAT_STACKING else 0)
             if events is not None:
                 events["classify1"].record()
 

@@ -459,8 +459,9 @@ def test_alternate_classify_paths_give_the_same_hits(mode, tmp_path):
 
 @pytest.mark.parametrize("shift", [0.0, 24000.0])
 def test_single_precision_screen_is_a_superset(shift, tmp_path):
-    """The fp32 screen (classify_screen32.cuh) must let through every pair the fp64 screen lets through - so the
-    hit records (decided in fp64 by the list kernels) are bit-identical - also when the structures sit 24 000 A
+    """The fp32 screen (classify_screen32.cuh) must let through every pair the fp64 screen lets through, and the
+    fp32 stacking kernel (classify_stack32.cuh) must hand every pair it cannot decide with certainty to the fp64
+    kernel - so the hit records are bit-identical to the all-fp64 path (FR3D_SCREEN=64) - also when the structures sit 24 000 A
     from the origin, where a plain fp32 coordinate would carry 2e-3 A (the records hold fixed-point centres and
     centre-relative coordinates instead).  FR3D_SCREEN is read once per process, hence the subprocess."""
     import os
@@ -481,6 +482,9 @@ def test_single_precision_screen_is_a_superset(shift, tmp_path):
         "order = np.lexsort((hits['slot'], hits['j'], hits['i'], hits['rank']))\n"
         "np.save(sys.argv[1], hits[order])\n"
         "np.save(sys.argv[1] + '.lists.npy', ex['plan'].counters.cpu().numpy())\n"
+        "plan = ex['plan']; al = lambda v: (v + 255) // 256 * 256\n"
+        "off = 5 * al(4 * plan.pair_cap) + al(320 * batch.n)\n"
+        "np.save(sys.argv[1] + '.unc.npy', plan.cws[off:off + 8].cpu().numpy().view(np.int64))\n"
         % (root, os.path.join(root, "tests"), shift, shift))
     outs, lists = [], []
     for m in ("32", "64"):
@@ -489,12 +493,16 @@ def test_single_precision_screen_is_a_superset(shift, tmp_path):
         subprocess.run([sys.executable, "-c", code, out], check=True, env=env, cwd=root)
         outs.append(np.load(out))
         lists.append(np.load(out + ".lists.npy"))
+        if m == "32":
+            undecided = int(np.load(out + ".unc.npy")[0])
     a, b = outs
     assert len(a) > 50000 and len(a) == len(b)
     assert a.tobytes() == b.tobytes()
     assert lists[0][0] == lists[1][0] and lists[0][1] == lists[1][1]            # pairs, hits
     assert np.all(lists[0][4:8] >= lists[1][4:8])                               # every work list at least as long ...
     assert np.all(lists[0][4:8] <= 1.02 * lists[1][4:8] + 16)                   # ... and the margins cost < 2 %
+    # stacking list: decided in single precision except where a comparison is within its margin (classify_stack32.cuh)
+    assert 0 < undecided < 0.05 * lists[0][5]
 
 
 @pytest.mark.parametrize("case", ["detail", "focus_cww_ths_stacking", "focus_cww_coplanar_covalent"])
