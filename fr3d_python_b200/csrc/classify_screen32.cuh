@@ -47,7 +47,7 @@ constexpr size_t S32_SMEM = sizeof(float) * (S32_FIXED + S32_WARPS * 32 * S32_ST
 // Builds the screen records: one block per 32 consecutive nts.  The four source planes of those nts are contiguous
 // in memory, so they are staged in shared memory with coalesced asynchronous copies (every load independent of
 // every other), then the 32 x 80 output words are written coalesced, each computed from the staged doubles.
-constexpr int SREC_NTS = 32, SREC_THREADS = 256;
+constexpr int SREC_NTS = 32, SREC_THREADS = 320;          // 320 = 4 x S32_REC
 constexpr int SREC_C = 0, SREC_U = SREC_C + SREC_NTS * 3, SREC_BB = SREC_U + SREC_NTS * 9,
               SREC_BASE = SREC_BB + SREC_NTS * FR3D_BB_SLOTS * 3, SREC_DOUBLES = SREC_BASE + SREC_NTS * FR3D_BASE_SLOTS * 3;
 
@@ -78,12 +78,21 @@ __global__ void __launch_bounds__(SREC_THREADS) screen_records_kernel(fr3d_nts_t
     else if (tid >= SREC_NTS && tid < SREC_NTS + cnt) cp_async4(sm + tid, nts.bb_mask + n0 + (tid - SREC_NTS));
     cp_async_wait_all();
     __syncthreads();
+    // each thread owns ONE word position w of the record (320 threads = 4 x 80) and walks the nts k = tid / 80, + 4, ...:
+    // what the word is made of is decided once, the loop body is two shared-memory loads, a subtract and a store
+    const int w = tid % S32_REC;
+    int src = 0, stride = 0, comp = -1;            // value = sd[src + k * stride] - (comp >= 0 ? centre[comp] : 0)
+    if (w < 3) { src = SREC_C + w; stride = 3; }
+    else if (w < 9) { src = SREC_U + ((w - 3) % 3) * 3 + (w < 6 ? 0 : 2); stride = 9; }
+    else if (w < S32_MASKS) {
+        const int b = (w - S32_BB) / 3;
+        comp = (w - S32_BB) - b * 3;
+        src = SREC_BB + (b == 6 ? 9 : b + 1) * 3 + comp; stride = FR3D_BB_SLOTS * 3;
+    } else if (w >= S32_BASE) { comp = (w - S32_BASE) % 3; src = SREC_BASE + (w - S32_BASE); stride = FR3D_BASE_SLOTS * 3; }
     float *out = rec + (size_t)n0 * S32_REC;
-    for (int t = tid; t < cnt * S32_REC; t += SREC_THREADS) {
-        const int k = t / S32_REC, w = t - k * S32_REC;
-        const double *c = sd + SREC_C + k * 3;
+    for (int k = tid / S32_REC; k < cnt; k += SREC_THREADS / S32_REC) {
         const uint32_t bm = sm[k];
-        float v = 0.f;
+        float v;
         if (w == S32_MASKS) {
             v = __uint_as_float(bm);
         } else if (w == S32_MASKS + 1) {
@@ -91,20 +100,14 @@ __global__ void __launch_bounds__(SREC_THREADS) screen_records_kernel(fr3d_nts_t
         } else if (!(bm & FR3D_MASK_HAS_FRAME)) {          // never on a candidate pair; only the masks are kept
             v = 0.f;
         } else if (w < 3) {
-            const double x = c[w];
+            const double x = sd[src + k * 3];
             if (!(fabs(x) < S32_RANGE)) atomicOr((unsigned long long *)&counters[2], 1ull);      // FR3D_E_RANGE
             v = __int_as_float((int)rint(fmax(-S32_RANGE, fmin(S32_RANGE, x)) * S32_FX));
-        } else if (w < 9) {
-            const int col = w < 6 ? 0 : 2, row = (w - 3) % 3;
-            v = (float)sd[SREC_U + k * 9 + row * 3 + col];
-        } else if (w < S32_MASKS) {
-            const int b = (w - S32_BB) / 3, comp = (w - S32_BB) - b * 3, slot = b == 6 ? 9 : b + 1;
-            v = (float)(sd[SREC_BB + k * (FR3D_BB_SLOTS * 3) + slot * 3 + comp] - c[comp]);
         } else {
-            const int q = w - S32_BASE;
-            v = (float)(sd[SREC_BASE + k * (FR3D_BASE_SLOTS * 3) + q] - c[q % 3]);
+            const double x = sd[src + k * stride];
+            v = (float)(comp >= 0 ? x - sd[SREC_C + k * 3 + comp] : x);
         }
-        out[t] = v;
+        out[k * S32_REC + w] = v;
     }
 }
 
