@@ -314,8 +314,9 @@ def main():
                 "gpu_launches": gpu_launches,
                 "kernel_ms": {"classify_pairs": classify_ms, "pair_search_5_kernels": search_ms,
                               "frames_fit_and_launch_gaps": ms_per_step - classify_ms - search_ms},
-                "roofline": {"kernel": "fr3d_classify_pairs = classify_screen_kernel + 2 x classify_pairs_tpp_kernel + "
-                                       "2 x classify_list2_kernel (one launch per work list)", "bound": "hbm", "achieved": achieved, "peak": peak,
+                "roofline": {"kernel": "fr3d_classify_pairs = screen_records + classify_screen32 + 2 x classify_pairs_tpp + "
+                                       "classify_stack32 (+ its fp64 fallback launch) + classify_list2 (eight launches: "
+                                       "screen, then one or two per work list)", "bound": "hbm", "achieved": achieved, "peak": peak,
                              "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                              "algorithmic_bytes_per_pair": PAIR_BYTES, "model": "gather: 2 x 760 B nt records + 12 B "
                              "pair + 32 B hit slot per candidate pair"},

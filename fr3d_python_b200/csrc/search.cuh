@@ -139,7 +139,13 @@ __constant__ int8_t c_half_stencil[14][3] = {{0, 0, 0}, {0, 0, 1}, {0, 1, 0}, {0
 // identity fields are staged in shared memory once; every nt1 of the cube then scans that list in full chunks of
 // 32 out of shared memory.  (One warp per nt1 repeated the probes and the gathers for each of the ~5 nts of a
 // cube, and an atomicAdd per ballot on the single append cursor made it atomic bound: 655 us -> 321 us -> this.)
-constexpr int SEARCH_CAP = 128;          // candidates staged per segment
+#ifndef FR3D_SEARCH_CAP
+#define FR3D_SEARCH_CAP 64
+#endif
+#ifndef FR3D_SEARCH_MINB
+#define FR3D_SEARCH_MINB 10      // A/B on the bench workload (cap, blocks): (128, 7) 254 us, (96, 9) 223, (64, 10) 214, (64, 12) 214
+#endif
+constexpr int SEARCH_CAP = FR3D_SEARCH_CAP;          // candidates staged per segment
 constexpr int SEARCH_CHUNKS = SEARCH_CAP / 32;
 constexpr int SEARCH_WARPS = 4;
 
@@ -153,7 +159,7 @@ struct SearchStage {
     unsigned kept[32][SEARCH_CHUNKS];    // ballots of (nt1, chunk)
 };
 
-__global__ void __launch_bounds__(SEARCH_WARPS * 32)
+__global__ void __launch_bounds__(SEARCH_WARPS * 32, FR3D_SEARCH_MINB)
 pair_search_kernel(fr3d_nts_t nts, SearchWs ws, double cutoff, int32_t *__restrict__ pair_i,
                    int32_t *__restrict__ pair_j, int32_t *__restrict__ pair_rank, int64_t pair_cap, int64_t *counters) {
     constexpr unsigned ALL = 0xFFFFFFFFu;
