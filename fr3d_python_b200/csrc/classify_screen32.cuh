@@ -169,7 +169,7 @@ classify_screen32_kernel(const float *__restrict__ rec, const fr3d_box_t *__rest
                          const int32_t *__restrict__ box_index, const int32_t *__restrict__ pair_i,
                          const int32_t *__restrict__ pair_j, int64_t pair_cap, uint32_t cats,
                          int32_t *__restrict__ wl_light, int32_t *__restrict__ wl_stack, int32_t *__restrict__ wl_pair,
-                         int32_t *__restrict__ wl_bph, int64_t *counters) {
+                         int32_t *__restrict__ wl_bph, uint32_t *__restrict__ wl_bph_combos, int64_t *counters) {
     extern __shared__ float s32_smem[];
     float *ubox = s32_smem;                                          // [SCR_UBOX][8] union boxes
     float *sbox = ubox + SCR_UBOX * 8;                               // [SCR_MAX_BOXES][SCR_BOX_STRIDE] mid, half
@@ -256,7 +256,7 @@ classify_screen32_kernel(const float *__restrict__ rec, const fr3d_box_t *__rest
         const uint32_t bm1 = __float_as_uint(A[S32_MASKS]), bb1 = __float_as_uint(A[S32_MASKS + 1]);
         const int par1 = (int)((bm1 >> 16) & 15u) - 1;
         const bool par1_ok = par1 >= 0 && par1 < FR3D_N_PARENTS;
-        unsigned fl = 0, live = 0;
+        unsigned fl = 0, live = 0, bph_combos = 0;
         float dX0 = 0, dY0 = 0, dZ0 = 0, dX1 = 0, dY1 = 0, dZ1 = 0, nZ = 0, ang0 = 0.f, ang1 = 0.f;
         int entry0 = 0, entry1 = 0;
         cp_async_wait_all();
@@ -289,8 +289,8 @@ classify_screen32_kernel(const float *__restrict__ rec, const fr3d_box_t *__rest
             }
             if ((cats & FR3D_CAT_BACKBONE) && par1_ok) {
                 // some massive atom of a base-phosphate site of nt1 within 4.5 A of a backbone oxygen of nt2
+                // (bit site * 6 + i of bph_combos, i in the order of the fp64 rule: O5' OP1 OP2 prevO3' O2' O4')
                 const int nsites = c_tab.n_sites[par1];
-                bool any = false;
 #pragma unroll 1
                 for (int s = 0; s < nsites; ++s) {
                     const int ms = c_tab.site_m[par1][s], hs = c_tab.site_h[par1][s];
@@ -313,11 +313,12 @@ classify_screen32_kernel(const float *__restrict__ rec, const fr3d_box_t *__rest
                             const float w0 = o0 - h0, w1 = o1 - h1, w2 = o2 - h2;
                             const float cs = u0 * w0 + u1 * w1 + u2 * w2;
                             const float x0 = u1 * w2 - u2 * w1, x1 = u2 * w0 - u0 * w2, x2 = u0 * w1 - u1 * w0;
-                            if (!(cs >= 1e-3f || x0 * x0 + x1 * x1 + x2 * x2 > 10.3f * 1.001f * cs * cs + 1e-3f)) any = true;
+                            if (!(cs >= 1e-3f || x0 * x0 + x1 * x1 + x2 * x2 > 10.3f * 1.001f * cs * cs + 1e-3f))
+                                bph_combos |= 1u << (s * 6 + ((0x345021 >> (4 * i)) & 15));
                         }
                     }
                 }
-                if (any) fl |= SCR_BPH;
+                if (bph_combos) fl |= SCR_BPH;
             }
         }
         // phase B: the base points of the 32 nt2 records take the place of the phase A rows
@@ -456,7 +457,10 @@ classify_screen32_kernel(const float *__restrict__ rec, const fr3d_box_t *__rest
         if (want_light) wl_light[base_l + __popc(bl & below)] = (int32_t)p;
         if (want_stack) wl_stack[base_s + __popc(bs & below)] = (int32_t)p;
         if (want_pair) wl_pair[base_p + __popc(bp & below)] = (int32_t)p;
-        if (want_bph) wl_bph[base_b + __popc(bb & below)] = (int32_t)p;
+        if (want_bph) {
+            wl_bph[base_b + __popc(bb & below)] = (int32_t)p;
+            wl_bph_combos[base_b + __popc(bb & below)] = bph_combos;
+        }
     }
 }
 

@@ -169,8 +169,14 @@ __device__ __noinline__ int t_sr_tail(const double *A, const double *B, const do
 
 // check_base_backbone_interactions (NA:1867-2049): nt1 base -> nt2 backbone, with the reference's own
 // sequential, sticky selection.  Returns bph | br << 8 (digit | near << 4; 0xFF none).
+// combos: bit site * 6 + i set = the (site, oxygen i) combination can yield a label (all ones: test every one).  The
+// single-precision screen (classify_screen32.cuh) hands over the combinations that pass its necessary conditions
+// (both site atoms and the oxygen present, massive atom within 4.5 A + margin, angle not certainly below 107 degrees),
+// so only those are evaluated here.  A site without such a combination changes none of the selection's inputs, and
+// the selection is idempotent (it only assigns values its inputs determine, or keeps a value already set), so
+// skipping it for those sites gives the reference's result.
 __device__ __noinline__ int t_backbone(const TFrame &f1, int par1, const double *A, const double *B, uint32_t bm1,
-                                       uint32_t bb2) {
+                                       uint32_t bb2, unsigned combos = 0xFFFFFFFFu) {
     int bph = -1, br = -1;
     bool use_ph = true;                    // P far from the plane of base 1: no BPh (NA:1915-1921)
     if (bb2 & 1u) {
@@ -192,13 +198,16 @@ __device__ __noinline__ int t_backbone(const TFrame &f1, int par1, const double 
     for (int s = 0; s < nsites; ++s) {
         const int carbon = c_tab.site_carbon[par1][s];
         const int digit = c_tab.site_digit[par1][s];
-        if (carbon == 1) { cutoff = 4.0; ncutoff = 4.5; }          // NA:1930-1935
+        if (carbon == 1) { cutoff = 4.0; ncutoff = 4.5; }          // NA:1930-1935 (sticky: a site with neither keeps the last)
         else if (carbon == 0) { cutoff = 3.5; ncutoff = 4.0; }
+        const unsigned site_combos = (combos >> (s * 6)) & 63u;
+        if (!site_combos) continue;
         const int hs = c_tab.site_h[par1][s], ms = c_tab.site_m[par1][s];
         if ((bm1 >> hs & 1u) && (bm1 >> ms & 1u)) {
             const double *H = A + hs * 3, *Mv = A + ms * 3;
 #pragma unroll 1
             for (int i = 0; i < 6; ++i) {
+                if (!((site_combos >> i) & 1u)) continue;
                 if (i < 4 && !use_ph) continue;
                 const int oslot = (0x469213 >> (4 * i)) & 15;       // O5' OP1 OP2 prevO3' | O2' O4'
                 if (!((bb2 >> oslot) & 1u)) continue;
@@ -499,7 +508,8 @@ classify_pairs_tpp_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, 
                           const int32_t *__restrict__ pair_i, const int32_t *__restrict__ pair_j,
                           const int32_t *__restrict__ pair_rank, int64_t pair_cap, uint32_t cats, int32_t index_offset,
                           fr3d_hit_t *__restrict__ hits, int64_t hit_cap, int64_t *counters,
-                          const int32_t *__restrict__ worklist, int list_counter, int do_bp_rt) {
+                          const int32_t *__restrict__ worklist, int list_counter, int do_bp_rt,
+                          const uint32_t *__restrict__ list_combos = nullptr) {
     cats &= CATS_CT;
     const bool do_bp = BP_CT && do_bp_rt;
     __shared__ double s_hull[FR3D_N_PARENTS * 7 * 3];        // a per-lane parent index would serialise constant loads
@@ -581,8 +591,11 @@ classify_pairs_tpp_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, 
                 }
             }
             // ---- base-phosphate / base-ribose, nt1 base -> nt2 backbone (NA:807-829)
-            if ((cats & FR3D_CAT_BACKBONE) && par1 >= 0 && t_backbone_possible(par1, base1, bbp2, bm1, bb2)) {
-                const int sel = t_backbone(f1, par1, base1, bbp2, bm1, bb2);
+            // (list_combos: the candidate (site, oxygen) combinations of each listed pair, from the screen)
+            const unsigned combos = list_combos ? list_combos[p] : 0xFFFFFFFFu;
+            if ((cats & FR3D_CAT_BACKBONE) && par1 >= 0 && combos &&
+                (list_combos || t_backbone_possible(par1, base1, bbp2, bm1, bb2))) {
+                const int sel = t_backbone(f1, par1, base1, bbp2, bm1, bb2, combos);
                 if ((sel & 0xFF) != 0xFF) { hmask |= 1u << FR3D_SLOT_BPH; c_bph = sel & 0xFF; }
                 if (((sel >> 8) & 0xFF) != 0xFF) { hmask |= 1u << FR3D_SLOT_BR; c_br = (sel >> 8) & 0xFF; }
             }

@@ -155,7 +155,7 @@ int fr3d_pair_search(const fr3d_nts_t *nts, double cell_size, void *workspace, s
 size_t fr3d_classify_workspace(int64_t pair_cap, int32_t n_nt) {
     if (pair_cap < 0) pair_cap = 0;
     if (n_nt < 0) n_nt = 0;
-    return 5 * align_up(sizeof(int32_t) * (size_t)pair_cap, 256) +
+    return 6 * align_up(sizeof(int32_t) * (size_t)pair_cap, 256) +
            align_up(sizeof(float) * fr3d::S32_REC * (size_t)n_nt, 256) + 256;
 }
 
@@ -195,6 +195,8 @@ int fr3d_classify_pairs(const fr3d_nts_t *nts, const fr3d_box_t *boxes, const in
         int32_t *wl_stack = reinterpret_cast<int32_t *>(wsp + list_bytes);
         int32_t *wl_pair = reinterpret_cast<int32_t *>(wsp + 2 * list_bytes);
         int32_t *wl_bph = reinterpret_cast<int32_t *>(wsp + 3 * list_bytes);
+        // [4] undecided stacking pairs, [5] candidate (site, oxygen) combinations of the base-phosphate list
+        uint32_t *wl_bph_combos = reinterpret_cast<uint32_t *>(wsp + 5 * list_bytes);
         CUDA_TRY(cudaMemsetAsync(counters + 4, 0, 4 * sizeof(int64_t), st));
         if (screen64) {          // the double-precision screen, kept for A/B runs
             const int scr_threads = fr3d::SCR_WARPS * 32;
@@ -204,7 +206,7 @@ int fr3d_classify_pairs(const fr3d_nts_t *nts, const fr3d_box_t *boxes, const in
                 *nts, boxes, box_index, pair_i, pair_j, pair_cap, category_mask, wl_light, wl_stack, wl_pair, wl_bph, counters);
         } else {
             // single-precision screen records (classify_screen32.cuh), then the screen itself on them
-            float *srec = reinterpret_cast<float *>(wsp + 5 * list_bytes);
+            float *srec = reinterpret_cast<float *>(wsp + 6 * list_bytes);
             if (nts->n_nt > 0)
                 fr3d::screen_records_kernel<<<(nts->n_nt + fr3d::SREC_NTS - 1) / fr3d::SREC_NTS, fr3d::SREC_THREADS, 0, st>>>(
                 *nts, srec, counters);
@@ -212,7 +214,8 @@ int fr3d_classify_pairs(const fr3d_nts_t *nts, const fr3d_box_t *boxes, const in
             fr3d::classify_screen32_kernel<<<clampg((pair_cap + scr_threads - 1) / scr_threads,
                                                     (long long)g_sm_count * (mult ? mult : 1)),
                                              scr_threads, fr3d::S32_SMEM, st>>>(
-                srec, boxes, box_index, pair_i, pair_j, pair_cap, category_mask, wl_light, wl_stack, wl_pair, wl_bph, counters);
+                srec, boxes, box_index, pair_i, pair_j, pair_cap, category_mask, wl_light, wl_stack, wl_pair, wl_bph,
+                wl_bph_combos, counters);
         }
         // one thread-per-pair launch per list, each instantiation compiled with its own rule families only
         const int tpp_grid = clampg((pair_cap + 127) / 128, tpp_grid_max);
@@ -224,7 +227,7 @@ int fr3d_classify_pairs(const fr3d_nts_t *nts, const fr3d_box_t *boxes, const in
         if (category_mask & FR3D_CAT_BACKBONE)
             fr3d::classify_pairs_tpp_kernel<4, FR3D_CAT_BACKBONE, false><<<tpp_grid, 128, 0, st>>>(
                 *nts, boxes, box_index, pair_i, pair_j, pair_rank, pair_cap, FR3D_CAT_BACKBONE, index_offset, hits,
-                hit_cap, counters, wl_bph, 7, 0);
+                hit_cap, counters, wl_bph, 7, 0, screen64 ? nullptr : wl_bph_combos);
         // stacking and pairing lists: records staged in shared memory in two phases (classify_list2.cuh)
         constexpr int ts = fr3d::L2_WARPS_STACK * 32, tp = fr3d::L2_WARPS_PAIR * 32;
         const int grid_s = clampg((pair_cap + ts - 1) / ts, (long long)g_sm_count * (mult ? mult : 1));
@@ -239,9 +242,9 @@ int fr3d_classify_pairs(const fr3d_nts_t *nts, const fr3d_box_t *boxes, const in
             // (classify_stack32.cuh); the undecided list and its length live in the workspace
             int32_t *wl_unc = reinterpret_cast<int32_t *>(wsp + 4 * list_bytes);
             unsigned long long *unc_count = reinterpret_cast<unsigned long long *>(
-                wsp + 5 * list_bytes + align_up(sizeof(float) * fr3d::S32_REC * (size_t)nts->n_nt, 256));
+                wsp + 6 * list_bytes + align_up(sizeof(float) * fr3d::S32_REC * (size_t)nts->n_nt, 256));
             CUDA_TRY(cudaMemsetAsync(unc_count, 0, sizeof(unsigned long long), st));
-            const float *srec = reinterpret_cast<const float *>(wsp + 5 * list_bytes);
+            const float *srec = reinterpret_cast<const float *>(wsp + 6 * list_bytes);
             constexpr int t32 = fr3d::ST32_WARPS * 32;
             fr3d::classify_stack32_kernel<<<clampg((pair_cap + t32 - 1) / t32, (long long)g_sm_count * (mult ? mult : 1)),
                                             t32, fr3d::ST32_SMEM, st>>>(

@@ -483,7 +483,7 @@ def test_single_precision_screen_is_a_superset(shift, tmp_path):
         "np.save(sys.argv[1], hits[order])\n"
         "np.save(sys.argv[1] + '.lists.npy', ex['plan'].counters.cpu().numpy())\n"
         "plan = ex['plan']; al = lambda v: (v + 255) // 256 * 256\n"
-        "off = 5 * al(4 * plan.pair_cap) + al(320 * batch.n)\n"
+        "off = 6 * al(4 * plan.pair_cap) + al(320 * batch.n)\n"
         "np.save(sys.argv[1] + '.unc.npy', plan.cws[off:off + 8].cpu().numpy().view(np.int64))\n"
         % (root, os.path.join(root, "tests"), shift, shift))
     outs, lists = [], []

@@ -1,6 +1,6 @@
 #!/bin/bash
-# A/B on the GPU box: pair_search occupancy variants (SEARCH_CAP candidates per staged segment, min blocks per SM),
-# each a separate build: lib/libfr3d_b200_s<cap>_<minb>.so
-for v in 64_10 96_9 64_12 128_7; do
-  FR3D_B200_LIB=$PWD/fr3d_python_b200/lib/libfr3d_b200_s$v.so python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/ab_search_$v.log 2>&1
+# A/B on the GPU box: warps per SM of the single-precision stacking kernel (separate builds, -DFR3D_ST32_WARPS=n)
+python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/ab_st_16.log 2>&1
+for v in 12 20 24; do
+  FR3D_B200_LIB=$PWD/fr3d_python_b200/lib/libfr3d_b200_st$v.so python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/ab_st_$v.log 2>&1
 done
