@@ -140,7 +140,7 @@ int fr3d_pair_search(const fr3d_nts_t *nts, double cell_size, void *workspace, s
     const int block = 256;
     fr3d::search_reset_kernel<<<(T + block - 1) / block, block, 0, st>>>(ws);
     fr3d::cell_assign_kernel<<<(nts->n_nt + block - 1) / block, block, 0, st>>>(*nts, ws, cell_size, counters);
-    fr3d::cell_offsets_kernel<<<(T + block - 1) / block, block, 0, st>>>(ws, counters);
+    fr3d::cell_offsets_kernel<<<(T + fr3d::CELL_OFFSETS_THREADS - 1) / fr3d::CELL_OFFSETS_THREADS, fr3d::CELL_OFFSETS_THREADS, 0, st>>>(ws, counters);
     fr3d::cell_fill_kernel<<<(nts->n_nt + block - 1) / block, block, 0, st>>>(*nts, ws);
     // one warp per occupied cube; the cube count lives on the device, so size the grid for the worst case
     // (a cube per nt) capped at a few resident waves - the kernel strides over the cube list

@@ -164,12 +164,15 @@ __global__ void __launch_bounds__(FRAMES_WARPS * 32) frames_fit_kernel(fr3d_nts_
     const int n0 = (blockIdx.x * FRAMES_WARPS + warp) * 32;              // first nt of this warp
     const int n = n0 + lane;
     double *rows = s_rows[warp];
-    {   // stage the warp's records: items [0, 32 * 48) of the contiguous block, item t -> row t / 48, column t % 48
-        const long long total = (long long)min(32, max(0, nts.n_nt - n0)) * (FR3D_BASE_SLOTS * 3);
-        const double *src = nts.base_xyz + (size_t)n0 * FR3D_BASE_SLOTS * 3;
+    const int rows_here = min(32, max(0, nts.n_nt - n0));
+    {   // stage the warp's records row by row (48 doubles each: lanes 0..31, then lanes 0..15 for the rest)
+        const double *src = nts.base_xyz + (size_t)n0 * FR3D_BASE_SLOTS * 3 + lane;
+        double *dst = rows + lane;
 #pragma unroll 4
-        for (int t = lane; t < 32 * FR3D_BASE_SLOTS * 3; t += 32)
-            if (t < total) cp_async8(rows + (t / (FR3D_BASE_SLOTS * 3)) * FRAMES_STRIDE + t % (FR3D_BASE_SLOTS * 3), src + t);
+        for (int r = 0; r < rows_here; ++r) {
+            cp_async8(dst + r * FRAMES_STRIDE, src + r * (FR3D_BASE_SLOTS * 3));
+            if (lane < FR3D_BASE_SLOTS * 3 - 32) cp_async8(dst + r * FRAMES_STRIDE + 32, src + r * (FR3D_BASE_SLOTS * 3) + 32);
+        }
         cp_async_wait_all();
     }
     __syncthreads();
@@ -178,13 +181,16 @@ __global__ void __launch_bounds__(FRAMES_WARPS * 32) frames_fit_kernel(fr3d_nts_
     __syncwarp();
     // copy back slots 8..15 (every hydrogen slot lies there: the parents have 8 to 11 heavy atoms), or whole rows
     // if some lane inserted ideal-position copies
-    const int first_col = __any_sync(0xFFFFFFFFu, wrote_low) ? 0 : 24;
-    const int width = FR3D_BASE_SLOTS * 3 - first_col;
-    const int rows_here = min(32, max(0, nts.n_nt - n0));
     double *dstg = nts.base_xyz + (size_t)n0 * FR3D_BASE_SLOTS * 3;
-    for (int t = lane; t < rows_here * width; t += 32) {
-        const int r = t / width, c = first_col + t % width;
-        dstg[r * (FR3D_BASE_SLOTS * 3) + c] = rows[r * FRAMES_STRIDE + c];
+    if (__any_sync(0xFFFFFFFFu, wrote_low)) {
+        for (int r = 0; r < rows_here; ++r) {
+            dstg[r * (FR3D_BASE_SLOTS * 3) + lane] = rows[r * FRAMES_STRIDE + lane];
+            if (lane < FR3D_BASE_SLOTS * 3 - 32) dstg[r * (FR3D_BASE_SLOTS * 3) + 32 + lane] = rows[r * FRAMES_STRIDE + 32 + lane];
+        }
+    } else {        // columns 24..47: 24 doubles per row, lanes 0..23
+#pragma unroll 4
+        for (int r = 0; r < rows_here; ++r)
+            if (lane < 24) dstg[r * (FR3D_BASE_SLOTS * 3) + 24 + lane] = rows[r * FRAMES_STRIDE + 24 + lane];
     }
 }
 

@@ -85,10 +85,15 @@ __global__ void cell_assign_kernel(fr3d_nts_t nts, SearchWs ws, double cell_size
     ws.cell_slot[n] = slot;
 }
 
-// member-list allocation: a warp scan of the cell counts and ONE atomicAdd per warp on the cursor
-__global__ void cell_offsets_kernel(SearchWs ws, int64_t *counters) {
+// member-list allocation: a block-wide scan of the cell counts (and of the occupied-cube flags) and ONE atomicAdd per
+// block on each of the two cursors (one per warp made this kernel atomic bound: ~28 k atomics on one address, 25 us)
+constexpr int CELL_OFFSETS_THREADS = 1024;
+__global__ void __launch_bounds__(CELL_OFFSETS_THREADS) cell_offsets_kernel(SearchWs ws, int64_t *counters) {
+    __shared__ int s_cnt[32], s_occ[32];
+    __shared__ long long s_base;
+    __shared__ int s_cbase;
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int c = (t <= ws.table_mask) ? ws.count[t] : 0;
     int incl = c;
 #pragma unroll
@@ -96,18 +101,30 @@ __global__ void cell_offsets_kernel(SearchWs ws, int64_t *counters) {
         const int v = __shfl_up_sync(0xFFFFFFFFu, incl, off);
         if (lane >= off) incl += v;
     }
-    const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-    if (!total) return;
-    long long base = 0;
-    if (lane == 31) base = (long long)atomicAdd((unsigned long long *)&counters[3], (unsigned long long)total);
-    base = __shfl_sync(0xFFFFFFFFu, base, 31);
-    if (c > 0) ws.start[t] = (int32_t)(base + incl - c);
-    // ... and the occupied cubes go on a compact list (the search runs one warp per cube)
     const unsigned occ = __ballot_sync(0xFFFFFFFFu, c > 0);
-    int cbase = 0;
-    if (lane == 0) cbase = atomicAdd(ws.n_cells, __popc(occ));
-    cbase = __shfl_sync(0xFFFFFFFFu, cbase, 0);
-    if (c > 0) ws.cell_list[cbase + __popc(occ & ((1u << lane) - 1u))] = (int32_t)t;
+    if (lane == 31) { s_cnt[warp] = incl; s_occ[warp] = __popc(occ); }
+    __syncthreads();
+    if (warp == 0) {                    // exclusive scan of the 32 warp totals
+        const int wc = s_cnt[lane], wo = s_occ[lane];
+        int ic = wc, io = wo;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int v = __shfl_up_sync(0xFFFFFFFFu, ic, off), u = __shfl_up_sync(0xFFFFFFFFu, io, off);
+            if (lane >= off) { ic += v; io += u; }
+        }
+        s_cnt[lane] = ic - wc;
+        s_occ[lane] = io - wo;
+        if (lane == 31) {
+            s_base = ic ? (long long)atomicAdd((unsigned long long *)&counters[3], (unsigned long long)ic) : 0;
+            s_cbase = io ? atomicAdd(ws.n_cells, io) : 0;
+        }
+    }
+    __syncthreads();
+    if (c > 0) {
+        ws.start[t] = (int32_t)(s_base + s_cnt[warp] + incl - c);
+        // ... and the occupied cubes go on a compact list (the search runs one warp per cube)
+        ws.cell_list[s_cbase + s_occ[warp] + __popc(occ & ((1u << lane) - 1u))] = (int32_t)t;
+    }
 }
 
 __global__ void cell_fill_kernel(fr3d_nts_t nts, SearchWs ws) {
