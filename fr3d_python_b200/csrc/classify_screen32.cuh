@@ -37,6 +37,7 @@ constexpr int S32_STRIDE = 49;                  // odd: "lane k reads its own ro
 constexpr int S32_BB = 9, S32_MASKS = 30, S32_BASE = 32;
 constexpr double S32_FX = 65536.0;
 constexpr double S32_RANGE = 32000.0;
+constexpr float S32_FAR = 512.f;
 #ifndef FR3D_S32_WARPS
 #define FR3D_S32_WARPS 32
 #endif
@@ -90,14 +91,18 @@ __global__ void __launch_bounds__(SREC_THREADS) screen_records_kernel(fr3d_nts_t
         src = SREC_BB + (b == 6 ? 9 : b + 1) * 3 + comp; stride = FR3D_BB_SLOTS * 3;
     } else if (w >= S32_BASE) { comp = (w - S32_BASE) % 3; src = SREC_BASE + (w - S32_BASE); stride = FR3D_BASE_SLOTS * 3; }
     float *out = rec + (size_t)n0 * S32_REC;
+    // The error bounds of the single-precision kernels assume atoms within S32_FAR of their base centre (real bases
+    // stay within 5 A).  A record with a present atom beyond that gets FR3D_FLAG_DUP's bit in ITS copy of base_mask,
+    // which sends its stacking pairs to the fp64 kernel (classify_stack32.cuh); the screens need no such guard: an
+    // atom that far cannot pass a proximity test by any margin.
+    __shared__ uint32_t s_far[SREC_NTS];
+    if (tid < SREC_NTS) s_far[tid] = 0;
+    __syncthreads();
     for (int k = tid / S32_REC; k < cnt; k += SREC_THREADS / S32_REC) {
         const uint32_t bm = sm[k];
         float v;
-        if (w == S32_MASKS) {
-            v = __uint_as_float(bm);
-        } else if (w == S32_MASKS + 1) {
-            v = __uint_as_float(sm[SREC_NTS + k]);
-        } else if (!(bm & FR3D_MASK_HAS_FRAME)) {          // never on a candidate pair; only the masks are kept
+        if (w >= S32_MASKS && w < S32_BASE) continue;     // the masks follow once the far flags are complete
+        if (!(bm & FR3D_MASK_HAS_FRAME)) {                // never on a candidate pair; only the masks are kept
             v = 0.f;
         } else if (w < 3) {
             const double x = sd[src + k * 3];
@@ -106,9 +111,13 @@ __global__ void __launch_bounds__(SREC_THREADS) screen_records_kernel(fr3d_nts_t
         } else {
             const double x = sd[src + k * stride];
             v = (float)(comp >= 0 ? x - sd[SREC_C + k * 3 + comp] : x);
+            if (w >= S32_BASE && ((bm >> ((w - S32_BASE) / 3)) & 1u) && !(fabsf(v) < S32_FAR)) atomicOr(&s_far[k], 1u << 22);
         }
         out[k * S32_REC + w] = v;
     }
+    __syncthreads();
+    if (tid < cnt) out[tid * S32_REC + S32_MASKS] = __uint_as_float(sm[tid] | s_far[tid]);
+    else if (tid >= SREC_NTS && tid < SREC_NTS + cnt) out[(tid - SREC_NTS) * S32_REC + S32_MASKS + 1] = __uint_as_float(sm[tid]);
 }
 
 struct SFrame {

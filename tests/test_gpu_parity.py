@@ -292,6 +292,24 @@ def test_observed_hydrogens_are_kept(golden):
             assert np.abs(b.base_xyz[k, defs.SLOT_OF[parent][n]] - (np.array(h[n]) + 0.05)).max() < 1e-12
 
 
+def test_atom_far_from_its_base_goes_through_fp64(golden):
+    """An observed hydrogen hundreds of Angstrom from its base (garbage input) is outside the error bounds of the
+    single-precision kernels: such a record is flagged (classify_screen32.cuh, S32_FAR) and its stacking pairs are
+    decided by the fp64 kernel.  Whatever the path, the result must be the oracle's."""
+    spec = copy.deepcopy(golden("spec_1gid_full.json.gz"))
+    moved = 0
+    for k, nt in enumerate(spec["nts"]):
+        if k % 17 == 3:
+            name = {"A": "H8", "G": "H8", "C": "H6", "U": "H6"}[nt["sequence"]]
+            heavy = np.array([a[1:] for a in nt["atoms"] if a[0] in ("C2", "C4", "C6")]).mean(axis=0)
+            nt["atoms"] = [a for a in nt["atoms"] if a[0] != name] + [[name] + list(heavy + np.array([0.0, 700.0, 0.004]))]
+            moved += 1
+    assert moved > 10
+    want, wc, _, _ = oracle_tuples(spec, ALL9)
+    got = as_plain(NA.annotate_batch(spec, ALL9)[0])
+    assert got == (want, wc)
+
+
 def test_s1s72_like_structure_against_oracle():
     """C2 stand-in: 9 rotated, noised copies of 1GID-full in ONE structure, 2 844 nt."""
     base = synthetic.pack_base()
