@@ -21,7 +21,10 @@
 namespace fr3d {
 
 constexpr int L2_ROW = 75;               // doubles per pair; odd: lane k reads row k without bank conflicts
-constexpr int L2_WARPS_STACK = 11, L2_WARPS_PAIR = 8;
+#ifndef FR3D_L2_WARPS_PAIR
+#define FR3D_L2_WARPS_PAIR 8
+#endif
+constexpr int L2_WARPS_STACK = 11, L2_WARPS_PAIR = FR3D_L2_WARPS_PAIR;
 // The pairing kernel also keeps the cutoff boxes in shared memory when there are at most L2_MAX_BOXES of them (the
 // shipped tables have 243): 16 doubles per box at a stride of 17 doubles, so that lanes reading the same field of
 // different boxes hit different banks.

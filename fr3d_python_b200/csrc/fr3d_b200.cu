@@ -21,6 +21,13 @@
 #include "classify_stack32.cuh"
 #include "geometry.cuh"
 
+#ifndef FR3D_BPH_MINB
+#define FR3D_BPH_MINB 6      // base-phosphate list kernel, min blocks per SM 3 / 4 / 6 / 8: classify 0.840 / 0.835 / 0.807 / 0.815 ms
+#endif
+#ifndef FR3D_LIGHT_MINB
+#define FR3D_LIGHT_MINB 4
+#endif
+
 namespace {
 
 thread_local char g_err[512] = "";
@@ -221,11 +228,11 @@ int fr3d_classify_pairs(const fr3d_nts_t *nts, const fr3d_box_t *boxes, const in
         const int tpp_grid = clampg((pair_cap + 127) / 128, tpp_grid_max);
         constexpr uint32_t LIGHT_CATS = FR3D_CAT_SO | FR3D_CAT_SUGAR_RIBOSE;
         if (category_mask & LIGHT_CATS)
-            fr3d::classify_pairs_tpp_kernel<4, LIGHT_CATS, false><<<tpp_grid, 128, 0, st>>>(
+            fr3d::classify_pairs_tpp_kernel<FR3D_LIGHT_MINB, LIGHT_CATS, false><<<tpp_grid, 128, 0, st>>>(
                 *nts, boxes, box_index, pair_i, pair_j, pair_rank, pair_cap, category_mask & LIGHT_CATS, index_offset, hits,
                 hit_cap, counters, wl_light, 4, 0);
         if (category_mask & FR3D_CAT_BACKBONE)
-            fr3d::classify_pairs_tpp_kernel<4, FR3D_CAT_BACKBONE, false><<<tpp_grid, 128, 0, st>>>(
+            fr3d::classify_pairs_tpp_kernel<FR3D_BPH_MINB, FR3D_CAT_BACKBONE, false><<<tpp_grid, 128, 0, st>>>(
                 *nts, boxes, box_index, pair_i, pair_j, pair_rank, pair_cap, FR3D_CAT_BACKBONE, index_offset, hits,
                 hit_cap, counters, wl_bph, 7, 0, screen64 ? nullptr : wl_bph_combos);
         // stacking and pairing lists: records staged in shared memory in two phases (classify_list2.cuh)

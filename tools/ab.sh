@@ -1,6 +1,6 @@
 #!/bin/bash
-# A/B on the GPU box: warps per SM of the single-precision stacking kernel (separate builds, -DFR3D_ST32_WARPS=n)
-python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/ab_st_16.log 2>&1
-for v in 12 20 24; do
-  FR3D_B200_LIB=$PWD/fr3d_python_b200/lib/libfr3d_b200_st$v.so python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/ab_st_$v.log 2>&1
+# A/B on the GPU box: min blocks per SM of the two thread-per-pair list kernels (separate builds)
+python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/ab_occ_default.log 2>&1
+for v in LIGHT_MINB_6 LIGHT_MINB_8 BPH_MINB_5 BPH_MINB_7; do
+  FR3D_B200_LIB=$PWD/fr3d_python_b200/lib/libfr3d_b200_$v.so python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/ab_occ_$v.log 2>&1
 done
