@@ -80,16 +80,18 @@ __global__ void __launch_bounds__(SREC_THREADS) screen_records_kernel(fr3d_nts_t
     cp_async_wait_all();
     __syncthreads();
     // each thread owns ONE word position w of the record (320 threads = 4 x 80) and walks the nts k = tid / 80, + 4, ...:
-    // what the word is made of is decided once, the loop body is two shared-memory loads, a subtract and a store
+    // what the word is made of is decided once, the loop body is two shared-memory loads, a subtract and a store.
+    // The five special words (fixed-point centre, masks) are written after the loop.
     const int w = tid % S32_REC;
-    int src = 0, stride = 0, comp = -1;            // value = sd[src + k * stride] - (comp >= 0 ? centre[comp] : 0)
-    if (w < 3) { src = SREC_C + w; stride = 3; }
-    else if (w < 9) { src = SREC_U + ((w - 3) % 3) * 3 + (w < 6 ? 0 : 2); stride = 9; }
-    else if (w < S32_MASKS) {
-        const int b = (w - S32_BB) / 3;
-        comp = (w - S32_BB) - b * 3;
-        src = SREC_BB + (b == 6 ? 9 : b + 1) * 3 + comp; stride = FR3D_BB_SLOTS * 3;
-    } else if (w >= S32_BASE) { comp = (w - S32_BASE) % 3; src = SREC_BASE + (w - S32_BASE); stride = FR3D_BASE_SLOTS * 3; }
+    int src = -1, stride = 0, csub = -1, slot = -1;    // value = sd[src + k * stride] - (csub >= 0 ? sd[csub + 3 k] : 0)
+    if (w >= 3 && w < 9) { src = SREC_U + ((w - 3) % 3) * 3 + (w < 6 ? 0 : 2); stride = 9; }
+    else if (w >= S32_BB && w < S32_MASKS) {
+        const int b = (w - S32_BB) / 3, comp = (w - S32_BB) - b * 3;
+        src = SREC_BB + (b == 6 ? 9 : b + 1) * 3 + comp; stride = FR3D_BB_SLOTS * 3; csub = SREC_C + comp;
+    } else if (w >= S32_BASE) {
+        src = SREC_BASE + (w - S32_BASE); stride = FR3D_BASE_SLOTS * 3; csub = SREC_C + (w - S32_BASE) % 3;
+        slot = (w - S32_BASE) / 3;
+    }
     float *out = rec + (size_t)n0 * S32_REC;
     // The error bounds of the single-precision kernels assume atoms within S32_FAR of their base centre (real bases
     // stay within 5 A).  A record with a present atom beyond that gets FR3D_FLAG_DUP's bit in ITS copy of base_mask,
@@ -98,26 +100,30 @@ __global__ void __launch_bounds__(SREC_THREADS) screen_records_kernel(fr3d_nts_t
     __shared__ uint32_t s_far[SREC_NTS];
     if (tid < SREC_NTS) s_far[tid] = 0;
     __syncthreads();
-    for (int k = tid / S32_REC; k < cnt; k += SREC_THREADS / S32_REC) {
-        const uint32_t bm = sm[k];
-        float v;
-        if (w >= S32_MASKS && w < S32_BASE) continue;     // the masks follow once the far flags are complete
-        if (!(bm & FR3D_MASK_HAS_FRAME)) {                // never on a candidate pair; only the masks are kept
-            v = 0.f;
-        } else if (w < 3) {
-            const double x = sd[src + k * 3];
-            if (!(fabs(x) < S32_RANGE)) atomicOr((unsigned long long *)&counters[2], 1ull);      // FR3D_E_RANGE
-            v = __int_as_float((int)rint(fmax(-S32_RANGE, fmin(S32_RANGE, x)) * S32_FX));
-        } else {
+    if (src >= 0) {
+#pragma unroll 4
+        for (int k = tid / S32_REC; k < cnt; k += SREC_THREADS / S32_REC) {
+            const uint32_t bm = sm[k];
             const double x = sd[src + k * stride];
-            v = (float)(comp >= 0 ? x - sd[SREC_C + k * 3 + comp] : x);
-            if (w >= S32_BASE && ((bm >> ((w - S32_BASE) / 3)) & 1u) && !(fabsf(v) < S32_FAR)) atomicOr(&s_far[k], 1u << 22);
+            float v = (float)(csub >= 0 ? x - sd[csub + k * 3] : x);
+            if (!(bm & FR3D_MASK_HAS_FRAME)) v = 0.f;          // never on a candidate pair; only the masks are kept
+            else if (slot >= 0 && ((bm >> slot) & 1u) && !(fabsf(v) < S32_FAR)) atomicOr(&s_far[k], 1u << 22);
+            out[k * S32_REC + w] = v;
         }
-        out[k * S32_REC + w] = v;
     }
     __syncthreads();
     if (tid < cnt) out[tid * S32_REC + S32_MASKS] = __uint_as_float(sm[tid] | s_far[tid]);
     else if (tid >= SREC_NTS && tid < SREC_NTS + cnt) out[(tid - SREC_NTS) * S32_REC + S32_MASKS + 1] = __uint_as_float(sm[tid]);
+    else if (tid >= 2 * SREC_NTS && tid < 2 * SREC_NTS + 3 * cnt) {        // the centre as 2^-16 A fixed point
+        const int t = tid - 2 * SREC_NTS, k = t / 3, comp = t - k * 3;
+        float v = 0.f;
+        if (sm[k] & FR3D_MASK_HAS_FRAME) {
+            const double x = sd[SREC_C + t];
+            if (!(fabs(x) < S32_RANGE)) atomicOr((unsigned long long *)&counters[2], 1ull);      // FR3D_E_RANGE
+            v = __int_as_float((int)rint(fmax(-S32_RANGE, fmin(S32_RANGE, x)) * S32_FX));
+        }
+        out[k * S32_REC + comp] = v;
+    }
 }
 
 struct SFrame {

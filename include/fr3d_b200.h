@@ -15,7 +15,9 @@
  *  - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
  *  - the library allocates nothing that outlives a call except the constant
  *    tables uploaded by fr3d_upload_tables.
- *  - all floating point is IEEE fp64.
+ *  - all floating point in the interface is IEEE fp64, and everything that reaches an output is decided in
+ *    fp64 (single precision is used internally only for superset screens and for comparisons that are certain
+ *    by a margin far above its rounding error; see fr3d_classify_pairs).
  */
 #ifndef FR3D_B200_H
 #define FR3D_B200_H
