@@ -33,16 +33,22 @@
 namespace fr3d {
 
 constexpr int S32_REC = 80;
+#ifdef FR3D_S32_SCALAR_ROWS
 constexpr int S32_STRIDE = 49;                  // odd: "lane k reads its own row" is bank-conflict free
+#else
+// rows are copied in 16-byte pieces and read with 128-bit loads: 13 x 16 B per row (odd: a quarter warp's 128-bit
+// reads of "its own rows" touch 8 different 16-byte bank groups)
+constexpr int S32_STRIDE = 52;
+#endif
 constexpr int S32_BB = 9, S32_MASKS = 30, S32_BASE = 32;
 constexpr double S32_FX = 65536.0;
 constexpr double S32_RANGE = 32000.0;
 constexpr float S32_FAR = 512.f;
 #ifndef FR3D_S32_WARPS
-#define FR3D_S32_WARPS 32
+#define FR3D_S32_WARPS 24      // 24 (80 registers, no spill) and 32 (64 registers) warps per SM measure the same
 #endif
 constexpr int S32_WARPS = FR3D_S32_WARPS;
-constexpr int S32_FIXED = SCR_UBOX * 8 + SCR_MAX_BOXES * SCR_BOX_STRIDE + SCR_HULL + SCR_UBOX * 2 + 2 * (FR3D_N_PARENTS + 1);
+constexpr int S32_FIXED = (SCR_UBOX * 8 + SCR_MAX_BOXES * SCR_BOX_STRIDE + SCR_HULL + SCR_UBOX * 2 + 2 * (FR3D_N_PARENTS + 1) + 3) / 4 * 4;
 constexpr size_t S32_SMEM = sizeof(float) * (S32_FIXED + S32_WARPS * 32 * S32_STRIDE);
 
 // Builds the screen records: one block per 32 consecutive nts.  The four source planes of those nts are contiguous
@@ -185,7 +191,7 @@ classify_screen32_kernel(const float *__restrict__ rec, const fr3d_box_t *__rest
                          const int32_t *__restrict__ pair_j, int64_t pair_cap, uint32_t cats,
                          int32_t *__restrict__ wl_light, int32_t *__restrict__ wl_stack, int32_t *__restrict__ wl_pair,
                          int32_t *__restrict__ wl_bph, uint32_t *__restrict__ wl_bph_combos, int64_t *counters) {
-    extern __shared__ float s32_smem[];
+    extern __shared__ __align__(16) float s32_smem[];
     float *ubox = s32_smem;                                          // [SCR_UBOX][8] union boxes
     float *sbox = ubox + SCR_UBOX * 8;                               // [SCR_MAX_BOXES][SCR_BOX_STRIDE] mid, half
     float *shull = sbox + SCR_MAX_BOXES * SCR_BOX_STRIDE;            // [parents][7][3], margin folded into [2]
@@ -253,11 +259,20 @@ classify_screen32_kernel(const float *__restrict__ rec, const fr3d_box_t *__rest
         if (!__any_sync(FULL, valid)) continue;
         // phase A: words 0..31 of the 32 nt2 records, one coalesced 128-byte copy per row (row k belongs to lane k)
         __syncwarp();
+#ifdef FR3D_S32_SCALAR_ROWS
 #pragma unroll 8
         for (int k = 0; k < 32; ++k) {
             const int nb = __shfl_sync(FULL, n2, k);
             cp_async4(rows + k * S32_STRIDE + lane, rec + (size_t)nb * S32_REC + lane);
         }
+#else
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {                       // 8 lanes x 16 B per row, four rows per instruction
+            const int row = j * 4 + (lane >> 3), piece = (lane & 7) * 4;
+            const int nb = __shfl_sync(FULL, n2, row);
+            cp_async16(rows + row * S32_STRIDE + piece, rec + (size_t)nb * S32_REC + piece);
+        }
+#endif
         // nt1: read directly (pairs come grouped by nt1, so these loads are near-broadcast)
         const float *A = rec + (size_t)n1 * S32_REC;
         asm volatile("prefetch.global.L1 [%0];" ::"l"(A + 32));
@@ -276,7 +291,19 @@ classify_screen32_kernel(const float *__restrict__ rec, const fr3d_box_t *__rest
         int entry0 = 0, entry1 = 0;
         cp_async_wait_all();
         __syncwarp();
+#ifdef FR3D_S32_SCALAR_ROWS
         const float *R = rows + lane * S32_STRIDE;
+#else
+        float R[S32_BASE];                                  // this lane's row in registers: eight 128-bit loads
+        {
+            const float4 *R4 = reinterpret_cast<const float4 *>(rows + lane * S32_STRIDE);
+#pragma unroll
+            for (int j = 0; j < S32_BASE / 4; ++j) {
+                const float4 t = R4[j];
+                R[4 * j] = t.x; R[4 * j + 1] = t.y; R[4 * j + 2] = t.z; R[4 * j + 3] = t.w;
+            }
+        }
+#endif
         SFrame f2;
         f2.a0 = f2.a1 = f2.a2 = f2.n0 = f2.n1 = f2.n2 = 0.f;
         float e0 = 0.f, e1 = 0.f, e2 = 0.f;
@@ -338,6 +365,7 @@ classify_screen32_kernel(const float *__restrict__ rec, const fr3d_box_t *__rest
         }
         // phase B: the base points of the 32 nt2 records take the place of the phase A rows
         __syncwarp();
+#ifdef FR3D_S32_SCALAR_ROWS
 #pragma unroll 8
         for (int k = 0; k < 32; ++k) {
             const int nb = __shfl_sync(FULL, n2, k);
@@ -346,14 +374,36 @@ classify_screen32_kernel(const float *__restrict__ rec, const fr3d_box_t *__rest
             cp_async4(dst, src);
             if (lane < 16) cp_async4(dst + 32, src + 32);
         }
+#else
+#pragma unroll
+        for (int j = 0; j < 12; ++j) {                      // 12 pieces per row: 4 lanes x 16 B on eight rows per instruction
+            const int row = (j & 3) * 8 + (lane >> 2), piece = ((j >> 2) * 4 + (lane & 3)) * 4;
+            const int nb = __shfl_sync(FULL, n2, row);
+            cp_async16(rows + row * S32_STRIDE + piece, rec + (size_t)nb * S32_REC + S32_BASE + piece);
+        }
+#endif
         cp_async_wait_all();
         __syncwarp();
         if (valid) {
+#ifdef FR3D_S32_SCALAR_ROWS
+            const float *RB = rows + lane * S32_STRIDE;
+#else
+            float RB[FR3D_BASE_SLOTS * 3];                  // nt2's 16 base points in registers: twelve 128-bit loads
+            {
+                const float4 *R4 = reinterpret_cast<const float4 *>(rows + lane * S32_STRIDE);
+#pragma unroll
+                for (int j = 0; j < FR3D_BASE_SLOTS * 3 / 4; ++j) {
+                    const float4 t = R4[j];
+                    RB[4 * j] = t.x; RB[4 * j + 1] = t.y; RB[4 * j + 2] = t.z; RB[4 * j + 3] = t.w;
+                }
+            }
+#endif
             const float *Ab = A + S32_BASE;
             if ((cats & FR3D_CAT_STACKING) && par1_ok && par2_ok) {
-                const unsigned c12 = s32_cylinder_mask(f1, R, e0, e1, e2, s_r2[FR3D_N_PARENTS + 2 + par1]) & bm2;
+                const unsigned c12 = s32_cylinder_mask(f1, RB, e0, e1, e2, s_r2[FR3D_N_PARENTS + 2 + par1]) & bm2;
                 const unsigned c21 = s32_cylinder_mask(f2, Ab, -e0, -e1, -e2, s_r2[FR3D_N_PARENTS + 2 + par2]) & bm1;
-                if (s32_hull_any(f1, shull + par1 * 21, R, e0, e1, e2, c12) ||
+                // (the hull test indexes the points with a run-time slot: it reads the shared-memory row)
+                if (s32_hull_any(f1, shull + par1 * 21, rows + lane * S32_STRIDE, e0, e1, e2, c12) ||
                     s32_hull_any(f2, shull + par2 * 21, Ab, -e0, -e1, -e2, c21)) fl |= SCR_STACK;
             }
             if ((bm1 & 1u) && (bm2 & 1u) && par1_ok && par2_ok) {
@@ -368,7 +418,7 @@ classify_screen32_kernel(const float *__restrict__ rec, const fr3d_box_t *__rest
                     if (d1 * d1 < lim && d2 * d2 < lim) fl |= SCR_CP;
                 }
                 // glycosidic atom of nt2 minus glycosidic atom of nt1
-                const float gd0 = (R[0] + e0) - Ab[0], gd1 = (R[1] + e1) - Ab[1], gd2 = (R[2] + e2) - Ab[2];
+                const float gd0 = (RB[0] + e0) - Ab[0], gd1 = (RB[1] + e1) - Ab[1], gd2 = (RB[2] + e2) - Ab[2];
                 const int sg = nZ > 0 ? 0 : 1;
                 entry0 = (par1 * FR3D_N_PARENTS + par2) * 2 + sg;
                 entry1 = (par2 * FR3D_N_PARENTS + par1) * 2 + sg;

@@ -174,6 +174,7 @@ int fr3d_classify_pairs(const fr3d_nts_t *nts, const fr3d_box_t *boxes, const in
         return fail(FR3D_E_ARG, "NULL argument");
     if (!g_tables_loaded) return fail(FR3D_E_NOTABLES, "fr3d_upload_tables not called");
     if (pair_cap <= 0) return FR3D_OK;
+    if (workspace && (reinterpret_cast<size_t>(workspace) & 15)) return fail(FR3D_E_ARG, "workspace must be 16-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // Tuning knobs (environment): FR3D_CLASSIFY_MODE 2 = screen + two work-list kernels (default when a
     // workspace is given), 1 = thread-per-pair kernel over all pairs, 0 = warp-per-pair kernel over all pairs.
