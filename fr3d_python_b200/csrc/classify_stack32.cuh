@@ -27,8 +27,8 @@ namespace fr3d {
 #define FR3D_ST32_WARPS 12      // 12 / 16 / 20 warps: classify 0.843 / 0.850 / 0.873 ms (fewer warps leave more L1 for nt1's records)
 #endif
 constexpr int ST32_WARPS = FR3D_ST32_WARPS;
-constexpr int ST32_STRIDE = 81;                  // odd: lane k reads its own row without bank conflicts
-constexpr int ST32_FIXED = SCR_HULL + FR3D_N_PARENTS * 7 + FR3D_N_PARENTS;        // hull planes, their margins, r2in
+constexpr int ST32_STRIDE = 84;                  // 21 x 16 B (odd): rows are copied in 16-byte pieces and read with 128-bit loads
+constexpr int ST32_FIXED = (SCR_HULL + FR3D_N_PARENTS * 7 + FR3D_N_PARENTS + 3) / 4 * 4;        // hull planes, their margins, r2in
 constexpr size_t ST32_SMEM = sizeof(float) * (ST32_FIXED + ST32_WARPS * 32 * ST32_STRIDE);
 constexpr float ST32_DZ = 2e-3f;                 // margin on heights and distances (A)
 
@@ -36,14 +36,16 @@ constexpr float ST32_DZ = 2e-3f;                 // margin on heights and distan
 // 0 certainly no overlap, 1 certainly overlap, 2 cannot tell in single precision.  zsel = height of the atom
 // closest to the plane (asel = its slot); when the result is 1 every atom is on zsel's side by more than the margin.
 __device__ __forceinline__ int st32_overlap(const SFrame &f, float b0, float b1, float b2, const float *hull,
-                                            const float *hmargin, float r2in_sure, const float *q, float e0, float e1,
-                                            float e2, uint32_t bm, float &zsel, int &asel) {
+                                            const float *hmargin, float r2in_sure, const float *q, const float *qdyn,
+                                            float e0, float e1, float e2, uint32_t bm, float &zsel, int &asel) {
+    // q: the points for the unrolled pass (may live in registers); qdyn: the same points in memory, for the hull loop
+    // that indexes them with a run-time slot
     unsigned cand = 0;
     bool in_sure = false;
     float best = 1e30f, zmin = 1e30f, zmax = -1e30f;
     zsel = 0.f;
     asel = 0;
-#pragma unroll 8
+#pragma unroll
     for (int a = 0; a < FR3D_BASE_SLOTS; ++a) {
         const bool have = (bm >> a) & 1u;
         const float v0 = q[a * 3] + e0, v1 = q[a * 3 + 1] + e1, v2 = q[a * 3 + 2] + e2;
@@ -61,7 +63,7 @@ __device__ __forceinline__ int st32_overlap(const SFrame &f, float b0, float b1,
     while (cand && !in_sure) {
         const int a = __ffs(cand) - 1;
         cand &= cand - 1;
-        const float v0 = q[a * 3] + e0, v1 = q[a * 3 + 1] + e1, v2 = q[a * 3 + 2] + e2;
+        const float v0 = qdyn[a * 3] + e0, v1 = qdyn[a * 3 + 1] + e1, v2 = qdyn[a * 3 + 2] + e2;
         const float x = v0 * f.a0 + v1 * f.a1 + v2 * f.a2, y = v0 * b0 + v1 * b1 + v2 * b2;
         const float az = fabsf(v0 * f.n0 + v1 * f.n1 + v2 * f.n2);
         bool sure = az < 4.5f - ST32_DZ, maybe = true;
@@ -98,7 +100,7 @@ classify_stack32_kernel(const float *__restrict__ rec, const int32_t *__restrict
                         int32_t index_offset, fr3d_hit_t *__restrict__ hits, int64_t hit_cap, int64_t *counters,
                         const int32_t *__restrict__ worklist, int list_counter, int32_t *__restrict__ wl_unc,
                         unsigned long long *unc_count) {
-    extern __shared__ float st32_smem[];
+    extern __shared__ __align__(16) float st32_smem[];
     float *shull = st32_smem;                               // [parents][7][3]
     float *smargin = shull + SCR_HULL;                      // [parents][7]
     float *sr2in = smargin + FR3D_N_PARENTS * 7;            // [parents], margin subtracted
@@ -136,14 +138,11 @@ classify_stack32_kernel(const float *__restrict__ rec, const int32_t *__restrict
         if (!__any_sync(FULL, active)) continue;
         // stage the 32 nt2 records (80 words each; row k belongs to lane k)
         __syncwarp();
-#pragma unroll 4
-        for (int k = 0; k < 32; ++k) {
-            const int nb = __shfl_sync(FULL, n2, k);
-            const float *src = rec + (size_t)nb * S32_REC + lane;
-            float *dst = rows + k * ST32_STRIDE + lane;
-            cp_async4(dst, src);
-            cp_async4(dst + 32, src + 32);
-            if (lane < S32_REC - 64) cp_async4(dst + 64, src + 64);
+#pragma unroll
+        for (int j = 0; j < 20; ++j) {                      // 20 pieces per row: 4 lanes x 16 B on eight rows per instruction
+            const int row = (j & 3) * 8 + (lane >> 2), piece = ((j >> 2) * 4 + (lane & 3)) * 4;
+            const int nb = __shfl_sync(FULL, n2, row);
+            cp_async16(rows + row * ST32_STRIDE + piece, rec + (size_t)nb * S32_REC + piece);
         }
         // nt1: read directly (the list keeps the pairs grouped by nt1, so these loads are near-broadcast)
         const float *A = rec + (size_t)n1 * S32_REC;
@@ -161,7 +160,16 @@ classify_stack32_kernel(const float *__restrict__ rec, const int32_t *__restrict
 
         int result = -1;                 // -1 no label, -2 undecided in single precision, else the hit code
         if (active) {
-            const float *R = rows + lane * ST32_STRIDE;
+            const float *Rs = rows + lane * ST32_STRIDE;     // this lane's row; its first 32 words go to registers
+            float R[S32_BASE];
+            {
+                const float4 *R4 = reinterpret_cast<const float4 *>(Rs);
+#pragma unroll
+                for (int j = 0; j < S32_BASE / 4; ++j) {
+                    const float4 t = R4[j];
+                    R[4 * j] = t.x; R[4 * j + 1] = t.y; R[4 * j + 2] = t.z; R[4 * j + 3] = t.w;
+                }
+            }
             const uint32_t bm2 = __float_as_uint(R[S32_MASKS]);
             const int par2 = (int)((bm2 >> 16) & 15u) - 1;
             if (par1 >= 0 && par1 < FR3D_N_PARENTS && par2 >= 0 && par2 < FR3D_N_PARENTS) {
@@ -181,13 +189,22 @@ classify_stack32_kernel(const float *__restrict__ rec, const int32_t *__restrict
                     const float e2 = (float)(__float_as_int(R[2]) - c1z) * INV_FX;
                     const float b10 = f1.n1 * f1.a2 - f1.n2 * f1.a1, b11 = f1.n2 * f1.a0 - f1.n0 * f1.a2, b12 = f1.n0 * f1.a1 - f1.n1 * f1.a0;
                     const float b20 = f2.n1 * f2.a2 - f2.n2 * f2.a1, b21 = f2.n2 * f2.a0 - f2.n0 * f2.a2, b22 = f2.n0 * f2.a1 - f2.n1 * f2.a0;
-                    const float *Q1 = A + S32_BASE, *Q2 = R + S32_BASE;
+                    const float *Q1 = A + S32_BASE;
+                    float Q2[FR3D_BASE_SLOTS * 3];              // nt2's base points in registers: twelve 128-bit loads
+                    {
+                        const float4 *R4 = reinterpret_cast<const float4 *>(Rs + S32_BASE);
+#pragma unroll
+                        for (int j = 0; j < FR3D_BASE_SLOTS * 3 / 4; ++j) {
+                            const float4 t = R4[j];
+                            Q2[4 * j] = t.x; Q2[4 * j + 1] = t.y; Q2[4 * j + 2] = t.z; Q2[4 * j + 3] = t.w;
+                        }
+                    }
                     float z21, z12;
                     int a21, a12;
                     const int o21 = st32_overlap(f1, b10, b11, b12, shull + par1 * 21, smargin + par1 * 7, sr2in[par1], Q2,
-                                                 e0, e1, e2, bm2, z21, a21);
+                                                 Rs + S32_BASE, e0, e1, e2, bm2, z21, a21);
                     const int o12 = st32_overlap(f2, b20, b21, b22, shull + par2 * 21, smargin + par2 * 7, sr2in[par2], Q1,
-                                                 -e0, -e1, -e2, bm1, z12, a12);
+                                                 Q1, -e0, -e1, -e2, bm1, z12, a12);
                     if (o21 == 2 || o12 == 2) {
                         result = -2;
                     } else if (o21 == 1 || o12 == 1) {
