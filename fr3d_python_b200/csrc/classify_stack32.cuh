@@ -10,7 +10,7 @@
 // with ideal-position copies) - is appended to a fallback list that an fp64 kernel then processes, so the labels are
 // exactly those of the fp64 path; about 0.5 % of the listed pairs go that way.
 // ncu on the fp64 kernel (profiles/step_r1n_*): 168 registers, 11 warps per SM, 38 % issue utilisation, fp64
-// dependency latency; here: fp32 latencies, half the shared memory per pair, 16 warps per SM.
+// dependency latency, 226 warp instructions per listed pair; here: fp32 latencies, 110 instructions, 12 warps per SM.
 //
 // The minimum distance (15 x 15 atom pairs) is needed only for "mind < 1" (no label) and, for a true stack,
 // "mind < 4".  "mind > 1" is certified without the pair loop from heights: every atom of nt2 is at least h2 = min |z|
