@@ -270,6 +270,14 @@ def main():
     sub = synthetic.packing.select_structures(batch, range(n_tail))
     NA.annotate_batch(sub, CATEGORIES)
     t_tail = time.perf_counter() - t0
+    # ... and the same public call on a larger slice with the tail in forked worker processes (rank 0, N = 1 only:
+    # the ranks of one box would share the host cores)
+    t_tail_mp, n_tail_mp, tail_cores = None, min(S, 600), os.cpu_count() or 1
+    if world == 1 and tail_cores > 1 and n_tail_mp >= 64:
+        sub_mp = synthetic.packing.select_structures(batch, range(n_tail_mp))
+        t0 = time.perf_counter()
+        NA.annotate_batch(sub_mp, CATEGORIES, tail_workers=0)
+        t_tail_mp = time.perf_counter() - t0
 
     clocks = sampler.stop() if sampler is not None else None
 
@@ -310,7 +318,9 @@ def main():
                                 "%d chunks on 3 streams" % args.chunks},
                 "host_tail": {"structures_per_s_one_process": n_tail / t_tail,
                               "what": "annotate_batch incl. packing-free host post-processing to reference tuples, "
-                                      "%d structures, single Python process" % n_tail},
+                                      "%d structures, single Python process" % n_tail,
+                              "structures_per_s_all_cores": (n_tail_mp / t_tail_mp) if t_tail_mp else None,
+                              "all_cores": "%d structures, tail_workers=0 (%d forked workers)" % (n_tail_mp, min(tail_cores, n_tail_mp // 8))},
                 "gpu_launches": gpu_launches,
                 "kernel_ms": {"classify_pairs": classify_ms, "pair_search_5_kernels": search_ms,
                               "frames_fit_and_launch_gaps": ms_per_step - classify_ms - search_ms},

@@ -131,12 +131,48 @@ def category_mask(categories):
 
 
 # ------------------------------------------------------------------ batched API --
+_TAIL_JOB = None        # (batch, hits, cuts, boxtable, box_atoms, categories) of the call in progress, read by forked workers
+
+
+def _tail_range(bounds):
+    batch, hits, cuts, bt, box_atoms, categories = _TAIL_JOB
+    return [postprocess.build_results(batch, s, hits[cuts[s]:cuts[s + 1]], bt, box_atoms, categories)
+            for s in range(bounds[0], bounds[1])]
+
+
+def _host_tail(batch, hits, cuts, bt, box_atoms, categories, workers):
+    """postprocess.build_results for every structure.  The tail is pure Python / numpy and independent per
+    structure (SURVEY §8 A8 keeps it on the host), so with workers > 1 it runs in forked worker processes: they
+    inherit the batch and the hit records copy-on-write and send back the result dicts.  The children never touch
+    CUDA."""
+    global _TAIL_JOB
+    S = batch.n_structures
+    if workers is None:
+        workers = int(os.environ.get("FR3D_TAIL_WORKERS", "1"))
+    if workers == 0:
+        workers = os.cpu_count() or 1
+    workers = max(1, min(workers, S // 8))
+    _TAIL_JOB = (batch, hits, cuts, bt, box_atoms, categories)
+    try:
+        if workers == 1:
+            return _tail_range((0, S))
+        import multiprocessing
+        n_jobs = min(S, workers * 4)                 # a few jobs per worker: structures differ in size
+        edges = [int(round(k * S / n_jobs)) for k in range(n_jobs + 1)]
+        with multiprocessing.get_context("fork").Pool(workers) as pool:
+            parts = pool.map(_tail_range, list(zip(edges[:-1], edges[1:])), chunksize=1)
+        return [r for part in parts for r in part]
+    finally:
+        _TAIL_JOB = None
+
+
 def annotate_batch(batch, categories, focused_basepair_cutoffs=None, ideal_hydrogen_bonds=None, device=None,
-                   pinned=None, return_raw=False):
+                   pinned=None, return_raw=False, tail_workers=None):
     """Annotate every structure of an NtBatch (or of a list of coordinate specs) in one pass:
     one H2D copy, K1 (if frames are not given), K2/K3, K4, one D2H copy of the hit records, then
-    the host tail per structure.  Returns a list of (interaction_to_list_of_tuples,
-    category_to_interactions) per structure; with return_raw also the sorted hit array and extras."""
+    the host tail per structure (tail_workers: processes for it; None = $FR3D_TAIL_WORKERS or 1, 0 = one per
+    host core).  Returns a list of (interaction_to_list_of_tuples, category_to_interactions) per structure; with
+    return_raw also the sorted hit array and extras."""
     if not isinstance(batch, packing.NtBatch):
         batch = packing.pack_specs(batch)
     if not focused_basepair_cutoffs:
@@ -150,11 +186,9 @@ def annotate_batch(batch, categories, focused_basepair_cutoffs=None, ideal_hydro
     hits = postprocess.sort_hits(hits)
     # hits are sorted by rank = first_seen * 16 + stencil and first_seen is a global nt index of the
     # same structure as nt1, so the sorted array is already grouped by structure, in order
-    results = []
     sidx = np.searchsorted(batch.struct_off, hits['i'], side='right') - 1
     cuts = np.searchsorted(sidx, np.arange(batch.n_structures + 1))
-    for s in range(batch.n_structures):
-        results.append(postprocess.build_results(batch, s, hits[cuts[s]:cuts[s + 1]], bt, box_atoms, categories))
+    results = _host_tail(batch, hits, cuts, bt, box_atoms, categories, tail_workers)
     if return_raw:
         extras["n_pairs"] = n_pairs
         extras["hits"] = hits

@@ -292,6 +292,17 @@ def test_observed_hydrogens_are_kept(golden):
             assert np.abs(b.base_xyz[k, defs.SLOT_OF[parent][n]] - (np.array(h[n]) + 0.05)).max() < 1e-12
 
 
+def test_host_tail_in_worker_processes_gives_the_same_results():
+    """annotate_batch(tail_workers=n): the per-structure host tail in forked worker processes."""
+    batch = synthetic.make_structure_batch(synthetic.pack_base(), 40, seed0=321)
+    one = NA.annotate_batch(batch, ALL9, tail_workers=1)
+    many = NA.annotate_batch(batch, ALL9, tail_workers=4)
+    assert len(one) == len(many) == 40
+    for a, b in zip(one, many):
+        assert list(a[0].keys()) == list(b[0].keys())            # same labels in the same order ...
+        assert as_plain(a) == as_plain(b)                        # ... with the same rows in the same order
+
+
 def test_atom_far_from_its_base_goes_through_fp64(golden):
     """An observed hydrogen hundreds of Angstrom from its base (garbage input) is outside the error bounds of the
     single-precision kernels: such a record is flagged (classify_screen32.cuh, S32_FAR) and its stacking pairs are
