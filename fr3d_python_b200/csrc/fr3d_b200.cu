@@ -20,6 +20,7 @@
 #include "classify_list2.cuh"
 #include "classify_stack32.cuh"
 #include "geometry.cuh"
+#include "unit_annotation.cuh"
 
 #ifndef FR3D_BPH_MINB
 #define FR3D_BPH_MINB 6      // base-phosphate list kernel, min blocks per SM 3 / 4 / 6 / 8: classify 0.840 / 0.835 / 0.807 / 0.815 ms
@@ -277,6 +278,22 @@ int fr3d_classify_pairs(const fr3d_nts_t *nts, const fr3d_box_t *boxes, const in
             *nts, boxes, box_index, pair_i, pair_j, pair_rank, pair_cap, category_mask, index_offset, hits, hit_cap,
             counters, nullptr);
     }
+    CUDA_TRY(cudaGetLastError());
+    return FR3D_OK;
+}
+
+int fr3d_bond_orientation(const fr3d_nts_t *nts, const int32_t *host_ring_slot, double *chi_degree, int32_t *orientation,
+                          void *stream) {
+    if (!nts || !host_ring_slot || !chi_degree || !orientation) return fail(FR3D_E_ARG, "NULL argument");
+    if (nts->n_nt <= 0) return FR3D_OK;
+    fr3d::RingSlots ring;
+    for (int p = 0; p < FR3D_N_PARENTS; ++p) {
+        if (host_ring_slot[p] < 0 || host_ring_slot[p] >= FR3D_BASE_SLOTS) return fail(FR3D_E_ARG, "ring slot out of range");
+        ring.s[p] = host_ring_slot[p];
+    }
+    const int block = 128;
+    fr3d::bond_orientation_kernel<<<(nts->n_nt + block - 1) / block, block, 0, static_cast<cudaStream_t>(stream)>>>(
+        *nts, ring, chi_degree, orientation);
     CUDA_TRY(cudaGetLastError());
     return FR3D_OK;
 }

@@ -187,6 +187,19 @@ int fr3d_classify_pairs(const fr3d_nts_t *nts, const fr3d_box_t *boxes, const in
                         int64_t pair_cap, uint32_t category_mask, int32_t index_offset, void *workspace,
                         size_t workspace_bytes, fr3d_hit_t *hits, int64_t hit_cap, int64_t *counters, void *stream);
 
+/* Glycosidic bond orientation.  Replaces the arithmetic of annotate_bond_orientation
+ * (fr3d/classifiers/NA_unit_annotation.py:48-171) for every nt in one launch: chi = O4'-C1'-N9-C4 (purines) /
+ * O4'-C1'-N1-C2 (pyrimidines) in degrees (NaN where an atom is missing or the residue has no parent) and
+ * orientation = 0 NA, 1 anti, 2 syn, 3 int_syn (:150-155).  host_ring_slot[FR3D_N_PARENTS]: base slot of C4 / C2 per
+ * parent (HOST pointer; N9 / N1 is slot 0).  Reads base_xyz, bb_xyz and the masks (for modified residues after
+ * fr3d_frames_fit, which inserts the ideal-position copies the reference averages in). */
+#define FR3D_ORIENT_NA 0
+#define FR3D_ORIENT_ANTI 1
+#define FR3D_ORIENT_SYN 2
+#define FR3D_ORIENT_INT_SYN 3
+int fr3d_bond_orientation(const fr3d_nts_t *nts, const int32_t *host_ring_slot, double *chi_degree, int32_t *orientation,
+                          void *stream);
+
 /* K5. Replaces besttransformation / besttransformation_weighted
  * (fr3d/geometry/superpositions.py:10-121) for n_prob independent problems.
  * Problem p uses rows off[p]..off[p+1]-1 of set1/set2/w (w may be NULL = unweighted).

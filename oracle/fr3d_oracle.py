@@ -1289,3 +1289,73 @@ def annotate(spec, categories, nts=None, focused=None):
     annotate_covalent_connections(nts, out, c2i)
     tr["count_pair"] = count_pair
     return out, c2i, tr
+
+
+# ---------------------------------------------------------------- glycosidic bond orientation (N4)
+def bond_orientation(spec, nts=None):
+    """annotate_bond_orientation, fr3d/classifiers/NA_unit_annotation.py:48-171: the glycosidic torsion chi
+    (O4'-C1'-N9-C4 for purines, O4'-C1'-N1-C2 for pyrimidines, IUPAC sign) and its class per nucleotide.
+    Returns the reference's rows: {'unit_id', 'orientation' ('anti' | 'syn' | 'int_syn' | 'NA'), 'chi_degree'
+    ('%0.3f' string or None)}."""
+    if nts is None:
+        nts = build_nts(spec)
+    rows = []
+    for nt in nts:
+        chi = None
+        classification = ""
+        N1N9 = np.array([])
+        C2C4 = np.array([])
+        if nt.sequence in ['A', 'G', 'DA', 'DG']:                      # :67-70
+            N1N9, C2C4 = nt.center("N9"), nt.center("C4")
+        elif nt.sequence in ['C', 'U', 'DC', 'DT']:                    # :71-74
+            N1N9, C2C4 = nt.center("N1"), nt.center("C2")
+        else:
+            parent = get_parent(nt.sequence)                           # :75-95
+            p2m = MODIFIED[nt.sequence]["parent_atom_to_modified"] if nt.sequence in MODIFIED else {}
+            if parent in ['A', 'G', 'DA', 'DG']:
+                if "N9" in p2m:
+                    N1N9 = nt.center(p2m["N9"])
+                if "C4" in p2m:
+                    C2C4 = nt.center(p2m["C4"])
+            elif parent in ['C', 'U', 'DC', 'DT']:
+                if "N1" in p2m:
+                    N1N9 = nt.center(p2m["N1"])
+                if "C2" in p2m:
+                    C2C4 = nt.center(p2m["C2"])
+            else:                                                      # :96-108 no identified parent
+                N1N9 = nt.center("N9")
+                if len(N1N9) == 3:
+                    C2C4 = nt.center("C4")
+                else:
+                    N1N9, C2C4 = nt.center("N1"), nt.center("C2")
+        if len(N1N9) == 3 and len(C2C4) == 3:
+            C1P, O4P = nt.center("C1'"), nt.center("O4'")
+            if len(C1P) == 3 and len(O4P) == 3:
+                O4P_C1P = C1P - O4P                                     # :115-117
+                N1N9_C1P = C1P - N1N9
+                C2C4_N1N9 = N1N9 - C2C4
+                perp_to_sugar = np.cross(O4P_C1P, N1N9_C1P)             # :123-126
+                norm_perp_to_sugar = np.linalg.norm(perp_to_sugar)
+                if norm_perp_to_sugar != 0:
+                    perp_to_sugar = perp_to_sugar / norm_perp_to_sugar
+                perp_to_base = np.cross(-N1N9_C1P, C2C4_N1N9)           # :128-130
+                perp_to_base = perp_to_base / np.linalg.norm(perp_to_base)
+                cross_cross_chi = np.cross(perp_to_base, perp_to_sugar)
+                cos_chi = np.dot(perp_to_sugar, perp_to_base)           # :138-142
+                if np.dot(cross_cross_chi, N1N9_C1P) > 0:
+                    sin_chi = np.linalg.norm(cross_cross_chi)
+                else:
+                    sin_chi = -np.linalg.norm(cross_cross_chi)
+                chi = 180 * math.atan2(sin_chi, cos_chi) / math.pi      # :147
+                if chi > -90 and chi < -45:                             # :150-155
+                    classification = 'int_syn'
+                elif chi >= -45 and chi < 90:
+                    classification = 'syn'
+                else:
+                    classification = 'anti'
+        if classification:
+            rows.append({'unit_id': nt.unit_id(), 'orientation': classification, 'chi_degree': "%0.3f" % chi,
+                         'chi': chi})
+        else:
+            rows.append({'unit_id': nt.unit_id(), 'orientation': 'NA', 'chi_degree': None, 'chi': None})
+    return rows

@@ -548,3 +548,40 @@ def test_category_subsets_and_focused_interactions(golden, case):
     st = Structure.from_spec(spec)
     r = NA.annotate_nt_nt_in_structure(st, g["categories"])
     assert as_plain(r) == (want, wantc)
+
+
+# ------------------------------------------------------------------ glycosidic bond orientation (N4)
+@pytest.mark.parametrize("name", ["1gid_full", "1gid_modified", "1gid_variants", "1s72_strand", "chi_sweep"])
+def test_bond_orientation_identical_to_reference(golden, name):
+    """fr3d_bond_orientation through the reference's entry point against the rows of the unmodified reference."""
+    from fr3d_python_b200.classifiers import NA_unit_annotation as UA
+    from fr3d_python_b200.data import Structure
+    g = golden("glycosidic.json.gz")[name]
+    spec = golden("spec_%s.json.gz" % name)
+    (rows, errors), = UA.annotate_bond_orientation_batch(spec, pipeline=True)
+    assert rows == g["rows"]
+    assert errors == g["errors"]
+    # ... the same through a Structure object, and the torsion itself against the oracle's double
+    rows2, errors2 = UA.annotate_bond_orientation(Structure.from_spec(spec), pipeline=True)
+    assert rows2 == g["rows"] and errors2 == g["errors"]
+    chi, cls = UA.bond_orientation_arrays(packing.pack_specs(spec))
+    want = O.bond_orientation(spec)
+    for k, w in enumerate(want):
+        assert UA.ORIENTATION[cls[k]] == w["orientation"]
+        if w["chi"] is not None:
+            assert abs(chi[k] - w["chi"]) < 1e-9
+        else:
+            assert np.isnan(chi[k])
+
+
+def test_bond_orientation_on_a_large_batch():
+    """1000 structures in one launch: classes consistent with chi, every nt with its four atoms gets a value."""
+    from fr3d_python_b200.classifiers import NA_unit_annotation as UA
+    batch = synthetic.make_structure_batch(synthetic.pack_base(), 1000, seed0=4000)
+    chi, cls = UA.bond_orientation_arrays(batch)
+    assert len(chi) == batch.n and not np.isnan(chi).any() and np.all(cls > 0)
+    want = np.where((chi > -90) & (chi < -45), 3, np.where((chi >= -45) & (chi < 90), 2, 1))
+    assert np.array_equal(cls, want)
+    one = UA.bond_orientation_arrays(packing.select_structures(batch, [517]))
+    lo, hi = batch.struct_off[517], batch.struct_off[518]
+    assert np.array_equal(one[0], chi[lo:hi]) and np.array_equal(one[1], cls[lo:hi])

@@ -211,3 +211,14 @@ def test_caller_supplied_cutoff_table(golden, only_largest):
     out, c2i, _ = O.annotate(spec, categories, focused=_inflated_cutoffs(only_largest))
     assert {k: [list(t) for t in v] for k, v in out.items()} == g["interaction_to_list_of_tuples"]
     assert {k: sorted(v) for k, v in c2i.items()} == g["category_to_interactions"]
+
+
+@pytest.mark.parametrize("name", ["1gid_full", "1gid_modified", "1gid_variants", "1s72_strand", "chi_sweep"])
+def test_bond_orientation_matches_reference(golden, name):
+    """annotate_bond_orientation (NA_unit_annotation.py:48-171): the unmodified reference function's rows
+    (tools/make_golden.py glycosidic) on the fixtures and on a 15-degree sweep of the glycosidic torsion."""
+    g = golden("glycosidic.json.gz")[name]
+    rows = O.bond_orientation(golden("spec_%s.json.gz" % name))
+    assert [{k: r[k] for k in ("unit_id", "orientation", "chi_degree")} for r in rows] == g["rows"]
+    if name == "chi_sweep":
+        assert {r["orientation"] for r in rows} == {"anti", "syn", "int_syn"}

@@ -554,3 +554,71 @@ def main_custom_cutoffs():
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "cutoffs":
     main_custom_cutoffs()
+
+
+def reference_bond_orientation():
+    """annotate_bond_orientation of fr3d/classifiers/NA_unit_annotation.py, UNMODIFIED.  The module cannot be imported
+    (its top imports fr3d.cif.reader -> pdbx, and bare `from NA_pairwise_interactions import ...`), so the function's
+    own source lines are compiled from the reference file with the four names it reads bound to the reference's
+    objects."""
+    import ast
+    import math
+    from fr3d.classifiers import NA_pairwise_interactions as NA
+    from fr3d.data.mapping import parent_atom_to_modified
+    path = os.path.join(rf.REF, "fr3d", "classifiers", "NA_unit_annotation.py")
+    with open(path) as f:
+        tree = ast.parse(f.read(), path)
+    fn = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "annotate_bond_orientation"]
+    mod = ast.Module(body=fn, type_ignores=[])
+    env = {"np": np, "math": math, "get_parent": NA.get_parent, "parent_atom_to_modified": parent_atom_to_modified}
+    exec(compile(mod, path, "exec"), env)
+    return env["annotate_bond_orientation"]
+
+
+def make_spec_chi_sweep(strand_spec):
+    """Four nts of the 1S72 strand (A C G U) with the base turned about the glycosidic bond in 15-degree steps, so
+    that every orientation class (anti, syn, int_syn) and the class boundaries' neighbourhoods occur."""
+    nts = []
+    picked = {}
+    for nt in strand_spec["nts"]:
+        picked.setdefault(nt["sequence"], nt)
+    k = 0
+    for seq in ("A", "C", "G", "U"):
+        nt = picked[seq]
+        xyz = {a[0]: np.array(a[1:], dtype=float) for a in nt["atoms"]}
+        n_name = "N9" if seq in ("A", "G") else "N1"
+        axis = xyz[n_name] - xyz["C1'"]
+        axis /= np.linalg.norm(axis)
+        for step in range(24):
+            R = _axis_angle(axis, np.deg2rad(15.0 * step))
+            atoms = []
+            for name, x, y, z in nt["atoms"]:
+                p = np.array([x, y, z], dtype=float)
+                if name not in BACKBONE:
+                    p = xyz[n_name] + R.dot(p - xyz[n_name])
+                atoms.append([name] + [float(v) for v in p + np.array([40.0 * k, 0.0, 0.0])])
+            k += 1
+            nts.append({"chain": "S", "sequence": seq, "number": str(k), "index": k, "model": nt["model"],
+                        "symmetry": nt["symmetry"], "alt_id": None, "insertion_code": None, "atoms": atoms})
+    return {"pdb": "CHI", "nts": nts}
+
+
+def main_glycosidic():
+    """chi / syn-anti annotation: the reference's rows on the full, modified and variant structures
+    and on a sweep of the glycosidic torsion."""
+    fn = reference_bond_orientation()
+    out = {}
+    with gzip.open(os.path.join(GOLD, "spec_1s72_strand.json.gz"), "rt") as f:
+        dump("spec_chi_sweep.json.gz", make_spec_chi_sweep(json.load(f)))
+    for name in ("1gid_full", "1gid_modified", "1gid_variants", "1s72_strand", "chi_sweep"):
+        with gzip.open(os.path.join(GOLD, "spec_%s.json.gz" % name), "rt") as f:
+            spec = json.load(f)
+        structure = rf.ref_structure_from_spec(spec)
+        with contextlib.redirect_stdout(io.StringIO()) as printed:
+            rows, errors = fn(structure, pipeline=True)
+        out[name] = {"rows": rows, "errors": errors, "printed": printed.getvalue()}
+    dump("glycosidic.json.gz", out)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "glycosidic":
+    main_glycosidic()
