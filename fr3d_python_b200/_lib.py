@@ -14,6 +14,7 @@ LIB_PATH = os.environ.get("FR3D_B200_LIB") or os.path.join(_HERE, "lib", "libfr3
 CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 
+ABI_VERSION = 2          # FR3D_ABI_VERSION of include/fr3d_b200.h
 BASE_SLOTS = 16
 BB_SLOTS = 10
 META_INTS = 8

@@ -32,7 +32,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert set(names) == set(_lib.EXPORTS), (names, _lib.EXPORTS)
     for n in names:
         assert hasattr(lib, n), n
-    assert lib.fr3d_version() == 2
+    assert lib.fr3d_version() == _lib.ABI_VERSION == 2
     assert lib.fr3d_last_error() is not None
     assert lib.fr3d_pair_search_workspace(1000) > 0
     out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
