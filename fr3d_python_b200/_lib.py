@@ -31,7 +31,7 @@ E_CUDA, E_ARG, E_CAPACITY, E_NOTABLES, E_RANGE = -1, -2, -3, -4, -5
 
 EXPORTS = ["fr3d_version", "fr3d_last_error", "fr3d_init", "fr3d_upload_tables", "fr3d_frames_fit",
            "fr3d_pair_search_workspace", "fr3d_pair_search", "fr3d_classify_workspace", "fr3d_classify_pairs", "fr3d_kabsch_batched",
-           "fr3d_bond_orientation",
+           "fr3d_bond_orientation", "fr3d_radius_search_workspace", "fr3d_radius_search",
            "fr3d_discrepancy_all_vs_all", "fr3d_discrepancy_one_vs_many"]
 
 
@@ -118,12 +118,16 @@ def load():
         lib.fr3d_classify_workspace.restype = C.c_size_t
         lib.fr3d_classify_pairs.argtypes = [C.POINTER(NtsStruct), vp, vp, vp, vp, vp, i64, C.c_uint32, i32, vp,
                                             C.c_size_t, vp, i64, vp, vp]
+        lib.fr3d_radius_search_workspace.argtypes = [i32]
+        lib.fr3d_radius_search_workspace.restype = C.c_size_t
+        lib.fr3d_radius_search.argtypes = [vp, vp, i32, dbl, vp, C.c_size_t, vp, vp, vp, vp, i64, vp, vp]
         lib.fr3d_bond_orientation.argtypes = [C.POINTER(NtsStruct), C.POINTER(C.c_int32), vp, vp, vp]
         lib.fr3d_kabsch_batched.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp]
         lib.fr3d_discrepancy_all_vs_all.argtypes = [vp, vp, vp, i32, i32, dbl, i32, i32, vp, vp]
         lib.fr3d_discrepancy_one_vs_many.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, dbl, dbl, vp, vp, vp]
         for name in EXPORTS:
-            if name not in ("fr3d_last_error", "fr3d_pair_search_workspace", "fr3d_classify_workspace"):
+            if name not in ("fr3d_last_error", "fr3d_pair_search_workspace", "fr3d_classify_workspace",
+                            "fr3d_radius_search_workspace"):
                 getattr(lib, name).restype = C.c_int
         _lib = lib
         return lib

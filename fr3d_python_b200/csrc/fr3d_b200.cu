@@ -21,6 +21,7 @@
 #include "classify_stack32.cuh"
 #include "geometry.cuh"
 #include "unit_annotation.cuh"
+#include "radius_search.cuh"
 
 #ifndef FR3D_BPH_MINB
 #define FR3D_BPH_MINB 6      // base-phosphate list kernel, min blocks per SM 3 / 4 / 6 / 8: classify 0.840 / 0.835 / 0.807 / 0.815 ms
@@ -278,6 +279,35 @@ int fr3d_classify_pairs(const fr3d_nts_t *nts, const fr3d_box_t *boxes, const in
             *nts, boxes, box_index, pair_i, pair_j, pair_rank, pair_cap, category_mask, index_offset, hits, hit_cap,
             counters, nullptr);
     }
+    CUDA_TRY(cudaGetLastError());
+    return FR3D_OK;
+}
+
+size_t fr3d_radius_search_workspace(int32_t n_points) { return fr3d_pair_search_workspace(n_points); }
+
+int fr3d_radius_search(const double *xyz, const int32_t *model, int32_t n_points, double max_cutoff, void *workspace,
+                       size_t workspace_bytes, int32_t *pair_a, int32_t *pair_b, int32_t *pair_rank, double *dist2,
+                       int64_t pair_cap, int64_t *counters, void *stream) {
+    if (!xyz || !model || !workspace || !pair_a || !pair_b || !pair_rank || !dist2 || !counters)
+        return fail(FR3D_E_ARG, "NULL argument");
+    if (!(max_cutoff > 0)) return fail(FR3D_E_ARG, "max_cutoff must be positive");
+    if (workspace_bytes < fr3d_radius_search_workspace(n_points)) return fail(FR3D_E_ARG, "workspace too small");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CUDA_TRY(cudaMemsetAsync(counters, 0, 8 * sizeof(int64_t), st));
+    if (n_points <= 0) return FR3D_OK;
+    fr3d::SearchWs ws = carve(workspace, n_points);
+    const uint32_t T = ws.table_mask + 1;
+    const int block = 256;
+    fr3d::search_reset_kernel<<<(T + block - 1) / block, block, 0, st>>>(ws);
+    fr3d::rs_assign_kernel<<<(n_points + block - 1) / block, block, 0, st>>>(xyz, model, n_points, max_cutoff, ws, counters);
+    fr3d::cell_offsets_kernel<<<(T + fr3d::CELL_OFFSETS_THREADS - 1) / fr3d::CELL_OFFSETS_THREADS, fr3d::CELL_OFFSETS_THREADS, 0, st>>>(ws, counters);
+    fr3d::rs_fill_kernel<<<(n_points + block - 1) / block, block, 0, st>>>(n_points, ws);
+    // one warp per (occupied cell, stencil entry); the cell count lives on the device: size for the worst case,
+    // capped at a few resident waves (the kernel strides over the tasks)
+    const long long want = ((long long)n_points * 14 + fr3d::RS_WARPS - 1) / fr3d::RS_WARPS;
+    const long long cap_blocks = (long long)g_sm_count * 32;
+    fr3d::rs_pairs_kernel<<<(int)(want < cap_blocks ? want : cap_blocks), fr3d::RS_WARPS * 32, 0, st>>>(
+        xyz, model, ws, max_cutoff * max_cutoff, pair_a, pair_b, pair_rank, dist2, pair_cap, counters);
     CUDA_TRY(cudaGetLastError());
     return FR3D_OK;
 }

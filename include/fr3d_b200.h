@@ -187,6 +187,19 @@ int fr3d_classify_pairs(const fr3d_nts_t *nts, const fr3d_box_t *boxes, const in
                         int64_t pair_cap, uint32_t category_mask, int32_t index_offset, void *workspace,
                         size_t workspace_bytes, fr3d_hit_t *hits, int64_t hit_cap, int64_t *counters, void *stream);
 
+/* FR3D search screening.  Replaces fixed_radius_search (fr3d/search/pair_processing.py:106-177),
+ * which get_pairlist (:7-104) calls once per search: every pair of points of the same model whose squared distance
+ * is below max_cutoff^2.  xyz [n][3] (a NaN coordinate = no centre, the point is skipped, :137), model [n] (integer
+ * ids of the reference's model strings).  Outputs, in arbitrary order: pair_a / pair_b = (pnt1, pnt2) in the
+ * reference's orientation, pair_rank = first point of pnt1's bucket * 16 + stencil entry (sorting by (rank, pnt1,
+ * pnt2) gives the reference's list order), dist2 = (x1-x2)^2 + (y1-y2)^2 + (z1-z2)^2 evaluated like the reference
+ * (no fma).  counters (device int64[8]): [0] number of pairs (may exceed pair_cap: compare after the sync and re-run),
+ * [2] != 0: a coordinate outside +-2046 cutoffs (FR3D_E_RANGE), [3] scratch. */
+size_t fr3d_radius_search_workspace(int32_t n_points);
+int fr3d_radius_search(const double *xyz, const int32_t *model, int32_t n_points, double max_cutoff, void *workspace,
+                       size_t workspace_bytes, int32_t *pair_a, int32_t *pair_b, int32_t *pair_rank, double *dist2,
+                       int64_t pair_cap, int64_t *counters, void *stream);
+
 /* Glycosidic bond orientation.  Replaces the arithmetic of annotate_bond_orientation
  * (fr3d/classifiers/NA_unit_annotation.py:48-171) for every nt in one launch: chi = O4'-C1'-N9-C4 (purines) /
  * O4'-C1'-N1-C2 (pyrimidines) in degrees (NaN where an atom is missing or the residue has no parent) and

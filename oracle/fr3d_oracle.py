@@ -1359,3 +1359,82 @@ def bond_orientation(spec, nts=None):
         else:
             rows.append({'unit_id': nt.unit_id(), 'orientation': 'NA', 'chi_degree': None, 'chi': None})
     return rows
+
+
+# ---------------------------------------------------------------- FR3D search screening (N3)
+def fixed_radius_search(num_points, models, positions, max_cutoff, square_size=None):
+    """fixed_radius_search, fr3d/search/pair_processing.py:106-177: every pair of points of the same model with
+    squared distance below max_cutoff^2, as (pnt1, pnt2, distance_squared) in the reference's orientation and list
+    order.  The reference finds them through buckets of side max_cutoff keyed by a linearised integer (:133-143;
+    square_size only sizes that linearisation - the points span less than it, so distinct cells never collide and
+    the keys can be the cell triples themselves); adjacent buckets are the 13 at the same z level or above
+    (:147-151), then the bucket itself with pnt1 < pnt2 (:168-174)."""
+    d = max_cutoff
+    buckets = {}
+    for i in range(num_points):
+        x, y, z = positions[i]
+        if not (np.isnan(x) or np.isnan(y) or np.isnan(z)):
+            buckets.setdefault((x // d, y // d, z // d, models[i]), []).append(i)
+    dx = [1, 0, -1, 1, 0, -1, 1, 0, -1, 1, 0, -1, 1]
+    dy = [1, 1, 1, 0, 0, 0, -1, -1, -1, 1, 1, 1, 0]
+    dz = [1, 1, 1, 1, 1, 1, 1, 1, 1, 0, 0, 0, 0]
+    out = []
+
+    def dist2(a, b):
+        pa, pb = positions[a], positions[b]
+        return (pa[0] - pb[0]) ** 2 + (pa[1] - pb[1]) ** 2 + (pa[2] - pb[2]) ** 2
+
+    for key, members in buckets.items():
+        for j in range(13):
+            other = buckets.get((key[0] + dx[j], key[1] + dy[j], key[2] + dz[j], key[3]))
+            if other is not None:
+                for a in members:
+                    for b in other:
+                        dd = dist2(a, b)
+                        if dd < d * d:
+                            out.append((a, b, dd))
+        for a in members:
+            for b in members:
+                if a < b:
+                    dd = dist2(a, b)
+                    if dd < d * d:
+                        out.append((a, b, dd))
+    return out
+
+
+def get_pairlist(Q, models, centers, alt_index=False):
+    """get_pairlist, fr3d/search/pair_processing.py:7-104: per pair of query positions, the (index, index) pairs
+    (both orders) whose distance lies in that pair's range, sliced out of the distance-sorted triples."""
+    pairlist = defaultdict(dict)
+    npos = Q['numpositions']
+    keys = [(i, j) for i in range(npos) for j in range(i + 1, npos)] if alt_index is False else \
+        [(i, j) for a, i in enumerate(alt_index) for j in alt_index[a + 1:]]
+    if Q["type"] not in ("mixed", "geometric"):
+        for i, j in keys:
+            pairlist[i][j] = "full"
+        return pairlist
+    if centers.size == 0:
+        return pairlist
+    triples = sorted(fixed_radius_search(len(centers), models, centers, Q["largestMaxRange"]), key=lambda t: t[2])
+    both = []
+    for a, b, _ in triples:
+        both.append((a, b))
+        both.append((b, a))
+    d2 = [t[2] for t in triples]
+    for i, j in keys:
+        qi, qj = (i, j) if alt_index is False else (alt_index.index(i), alt_index.index(j))
+        lo2 = Q["requireddistanceminimum"][qi][qj] ** 2
+        hi2 = Q["requireddistancemaximum"][qi][qj] ** 2
+        if alt_index is False:
+            # :44-75 - two bisections; the upper one never returns less than index 0 of a non-empty list
+            start = 0 if Q["requireddistanceminimum"][qi][qj] <= 0 else sum(1 for v in d2 if v <= lo2)
+            end = max(sum(1 for v in d2 if v < hi2) - 1, 0) if d2 else -1
+            pairlist[i][j] = both[2 * start:2 * end + 2]
+        else:
+            rows = []                                                # :78-88
+            for a, b, v in triples:
+                if v > lo2 and v < hi2:
+                    rows.append((alt_index[a], alt_index[b]))
+                    rows.append((alt_index[b], alt_index[a]))
+            pairlist[i][j] = rows
+    return pairlist

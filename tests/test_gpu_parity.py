@@ -585,3 +585,53 @@ def test_bond_orientation_on_a_large_batch():
     one = UA.bond_orientation_arrays(packing.select_structures(batch, [517]))
     lo, hi = batch.struct_off[517], batch.struct_off[518]
     assert np.array_equal(one[0], chi[lo:hi]) and np.array_equal(one[1], cls[lo:hi])
+
+
+# ------------------------------------------------------------------ FR3D search screening (N3)
+@pytest.mark.parametrize("name", ["1gid_full", "1gid_variants"])
+def test_search_screen_identical_to_reference(golden, name):
+    """fr3d_radius_search through the reference's entry points against the unmodified reference's output: same
+    triples in the same orientation and order; squared distances to the last bit or one (the reference squares
+    with libm's pow, the device multiplies)."""
+    from fr3d_python_b200.search import pair_processing as PP
+    case = golden("search_screen.json.gz")[name]
+    centers = np.array([[np.nan if v is None else v for v in c] for c in case["centers"]], dtype=float)
+    models = case["models"]
+    for cutoff, want in case["searches"].items():
+        got = PP.fixed_radius_search(len(centers), models, centers, float(cutoff), 100.0)
+        assert [(a, b) for a, b, _ in got] == [(a, b) for a, b, _ in want]
+        g, w = np.array([c for _, _, c in got]), np.array([c for _, _, c in want])
+        assert np.abs(g - w).max() <= 4e-16 * w.max()
+    pl = PP.get_pairlist(case["Q"], models, centers)
+    got = {"%d,%d" % (i, j): [list(p) for p in v] for i, d in pl.items() for j, v in d.items()}
+    assert got == case["pairlist"]
+    # the alt_index form (centres of the listed positions only, indices mapped through alt_index, :78-88) and the
+    # symbolic form against the oracle
+    alt = [7, 3, 5]
+    few = centers[np.isfinite(centers[:, 0])][:3]
+    want_alt = O.get_pairlist(case["Q"], models[:3], few, alt)
+    got_alt = PP.get_pairlist(case["Q"], models[:3], few, alt)
+    assert sum(len(v) for d in want_alt.values() for v in d.values()) > 0
+    assert {k: dict(v) for k, v in got_alt.items()} == {k: dict(v) for k, v in want_alt.items()}
+    assert PP.get_pairlist(dict(case["Q"], type="symbolic"), models, centers)[0][1] == "full"
+
+
+def test_search_screen_large_and_edge_cases():
+    """25 280 points (C3) against a brute-force count on a slice; empty input; all points without a centre."""
+    from fr3d_python_b200.search import pair_processing as PP
+    big = synthetic.make_tiled_structure(synthetic.pack_base(), 80, (5, 4, 4), seed=25000, pdb="C3")
+    gframes.fit_batch_frames(big)
+    a, b, dd = PP.radius_pairs(big.center, np.zeros(big.n, dtype=np.int32), 16.0)
+    assert len(a) > 100000 and dd.max() < 256.0 and np.all(a != b)
+    und = np.minimum(a, b).astype(np.int64) * big.n + np.maximum(a, b)
+    assert len(np.unique(und)) == len(und)                          # every unordered pair once
+    sub = big.center[:2000]
+    d2 = ((sub[:, None] - sub[None]) ** 2).sum(axis=2)
+    want = int((np.triu(d2 < 256.0, 1)).sum())
+    inside = (a < 2000) & (b < 2000)
+    assert int(inside.sum()) == want
+    assert np.abs(dd - ((big.center[a] - big.center[b]) ** 2).sum(axis=1)).max() < 1e-10
+    assert PP.fixed_radius_search(0, [], np.zeros((0, 3)), 10.0, 100.0) == []
+    assert PP.fixed_radius_search(5, ["1"] * 5, np.full((5, 3), np.nan), 10.0, 100.0) == []
+    two_models = PP.fixed_radius_search(4, ["1", "1", "2", "2"], np.array([[0., 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0]]), 5.0, 10.0)
+    assert sorted((a, b) for a, b, _ in two_models) == [(0, 1), (2, 3)]     # never across models

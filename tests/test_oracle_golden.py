@@ -222,3 +222,22 @@ def test_bond_orientation_matches_reference(golden, name):
     assert [{k: r[k] for k in ("unit_id", "orientation", "chi_degree")} for r in rows] == g["rows"]
     if name == "chi_sweep":
         assert {r["orientation"] for r in rows} == {"anti", "syn", "int_syn"}
+
+
+def _search_case(case):
+    centers = np.array([[np.nan if v is None else v for v in c] for c in case["centers"]], dtype=float)
+    return centers, case["models"]
+
+
+@pytest.mark.parametrize("name", ["1gid_full", "1gid_variants"])
+def test_search_screen_matches_reference(golden, name):
+    """fixed_radius_search / get_pairlist (fr3d/search/pair_processing.py), imported unmodified by
+    tools/make_golden.py search: same triples (orientation, order, squared distances bit for bit), same slices."""
+    case = golden("search_screen.json.gz")[name]
+    centers, models = _search_case(case)
+    for cutoff, want in case["searches"].items():
+        got = O.fixed_radius_search(len(centers), models, centers, float(cutoff))
+        assert [[a, b, c] for a, b, c in got] == want
+    pl = O.get_pairlist(case["Q"], models, centers)
+    got = {"%d,%d" % (i, j): [list(p) for p in v] for i, d in pl.items() for j, v in d.items()}
+    assert got == case["pairlist"]

@@ -622,3 +622,41 @@ def main_glycosidic():
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "glycosidic":
     main_glycosidic()
+
+
+def main_search_screen():
+    """FR3D search screening: fixed_radius_search and get_pairlist of
+    fr3d/search/pair_processing.py (imported unmodified: it only needs numpy) on the base centres of the full and the
+    variants structures (two models, some points without a centre)."""
+    sys.path.insert(0, os.path.join(rf.REF, "fr3d", "search"))
+    import pair_processing as pp
+    out = {}
+    for name in ("1gid_full", "1gid_variants"):
+        with gzip.open(os.path.join(GOLD, "frames_%s.json.gz" % name), "rt") as f:
+            frames = json.load(f)
+        with gzip.open(os.path.join(GOLD, "spec_%s.json.gz" % name), "rt") as f:
+            spec = json.load(f)
+        centers = np.array([fr["center"] for fr in frames], dtype=float)
+        models = [str(nt["model"]) for nt in spec["nts"]]
+        if name == "1gid_variants":
+            centers[5::41] = np.nan                      # units without a centre (pair_processing.py:137)
+            centers -= centers[np.isfinite(centers[:, 0])].mean(axis=0) * 1.7      # negative coordinates too
+        case = {"centers": [[None if np.isnan(v) else float(v) for v in c] for c in centers], "models": models,
+                "searches": {}}
+        mn, mx = np.nanmin(centers), np.nanmax(centers)
+        square_size = float(np.power(10, np.floor(np.log10(mx - mn))) * np.ceil((mx - mn) / np.power(10, np.floor(np.log10(mx - mn)))))
+        for cutoff in ((6.0, 12.0, 21.5) if name == "1gid_full" else (6.0, 12.0)):
+            pairs = pp.fixed_radius_search(len(centers), models, centers, cutoff, square_size)
+            case["searches"][str(cutoff)] = [[int(a), int(b), float(c)] for a, b, c in pairs]
+        Q = {"type": "geometric", "numpositions": 3, "largestMaxRange": 14.0,
+             "requireddistanceminimum": [[0, 0.0, 4.0], [0.0, 0, 7.5], [4.0, 7.5, 0]],
+             "requireddistancemaximum": [[0, 9.0, 14.0], [9.0, 0, 12.25], [14.0, 12.25, 0]]}
+        pl = pp.get_pairlist(Q, models, centers)
+        case["Q"] = Q
+        case["pairlist"] = {"%d,%d" % (i, j): [[int(a), int(b)] for a, b in v] for i, d in pl.items() for j, v in d.items()}
+        out[name] = case
+    dump("search_screen.json.gz", out)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "search":
+    main_search_screen()
