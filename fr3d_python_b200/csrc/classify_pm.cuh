@@ -107,9 +107,13 @@ classify_pairs_pm_kernel(fr3d_nts_t nts, const fr3d_box_t *__restrict__ boxes, c
     const size_t c4_stride = fe < 3 ? 24 : 72;
     const int c4_dst = off_fr + lane * 8;
 
+    // pairs per warp and round: PM_K, fewer when the list is short (the fp64 fallback of the stacking kernel hands
+    // over ~2 k pairs: one pair per warp on 1.8 k warps is a quarter of the latency of four pairs on 450)
+    const long long per_warp = (n_pairs + nwarps - 1) / nwarps;
+    const int kk = per_warp < 1 ? 1 : (per_warp < PM_K ? (int)per_warp : PM_K);
 #pragma unroll 1
-    for (long long p0 = warp0 * PM_K; p0 < n_pairs; p0 += nwarps * PM_K) {
-        const int nk = (int)((n_pairs - p0) < PM_K ? (n_pairs - p0) : PM_K);
+    for (long long p0 = warp0 * kk; p0 < n_pairs; p0 += nwarps * kk) {
+        const int nk = (int)((n_pairs - p0) < kk ? (n_pairs - p0) : kk);
 
         // ---------------- phase 0: indices, then every record of the PM_K pairs with cp.async
         __syncwarp();

@@ -229,9 +229,14 @@ pair_search_kernel(fr3d_nts_t nts, SearchWs ws, double cutoff, int32_t *__restri
                 for (int t0 = 0; t0 < seg; t0 += 32) {      // warp-uniform trip count: the shuffles need every lane
                     const int t = t0 + lane;
                     const int k = sb + t;
+                    // stencil entry of candidate k = number of cubes whose (inclusive, non-decreasing) prefix end is <= k:
+                    // a four-step bisection over the values held by lanes 0..12 (lanes 13.. hold the total)
                     int s = 0;
 #pragma unroll
-                    for (int j = 0; j < 13; ++j) s += (k >= __shfl_sync(ALL, end, j)) ? 1 : 0;
+                    for (int step = 8; step >= 1; step >>= 1) {
+                        const int e = __shfl_sync(ALL, end, min(s + step - 1, 13));
+                        if (s + step <= 13 && k >= e) s += step;
+                    }
                     const int sh = __shfl_sync(ALL, shift, s);
                     if (t < seg) {
                         const int n2 = ws.members[k + sh];
