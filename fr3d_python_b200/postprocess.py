@@ -12,6 +12,7 @@ reproduces the reference's cube-walk order exactly (SURVEY §7 hard part 1).
 """
 
 from collections import defaultdict
+from itertools import chain
 
 import numpy as np
 
@@ -187,8 +188,10 @@ def crossing_numbers(ident, i2p):
     if not labels:
         return out
     sizes = [len(i2p[l][0]) for l in labels]
-    A = np.fromiter((k for l in labels for k in i2p[l][0]), dtype=np.int64, count=sum(sizes))
-    B = np.fromiter((k for l in labels for k in i2p[l][1]), dtype=np.int64, count=sum(sizes))
+    A_l = list(chain.from_iterable(i2p[l][0] for l in labels))
+    B_l = list(chain.from_iterable(i2p[l][1] for l in labels))
+    A = np.array(A_l, dtype=np.int64)
+    B = np.array(B_l, dtype=np.int64)
     cross = np.zeros(len(A), dtype=np.int64)
     if nested:                                   # one broadcast per chain over the rows of ALL labels
         ca = chain_code[A]
@@ -202,8 +205,8 @@ def crossing_numbers(ident, i2p):
                     rows = np.nonzero(same & (ca == c))[0]
                     P, Q = nested[name]
                     cross[rows] = _crossing_counts(lo_[rows], hi_[rows], P, Q)
-    ua_all = [uid[k] for k in A.tolist()]
-    ub_all = [uid[k] for k in B.tolist()]
+    ua_all = [uid[k] for k in A_l]
+    ub_all = [uid[k] for k in B_l]
     cl_all = cross.tolist()
     pos = 0
     for inter, n in zip(labels, sizes):
