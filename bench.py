@@ -156,7 +156,7 @@ def main():
     ap.add_argument("--structures", type=int, default=1000, help="structures per GPU (weak scaling)")
     ap.add_argument("--cpu-structures", type=int, default=0, help="CPU baseline sample (0 = 2 per core, max 128)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--chunks", type=int, default=8, help="chunks of the e2e pipeline")
+    ap.add_argument("--chunks", type=int, default=8, help="chunks of the e2e pipeline (2 / 4 / 8 / 12 / 16: 4.06 / 3.82 / 3.71 / 3.72 / 3.88 ms)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

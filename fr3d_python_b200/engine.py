@@ -294,7 +294,8 @@ class Pipeline(object):
     independent, so the batch is cut into contiguous chunks of whole structures and chunk k+1's
     H2D copy overlaps chunk k's kernels and chunk k-1's D2H copy.  All device / pinned buffers are
     allocated once and re-used across calls.  Frames are always fitted on the device (K1), so the
-    centre / rotation planes are not uploaded."""
+    centre / rotation planes are not uploaded.  The input is fixed at construction: each chunk's planes are laid out
+    back to back in one pinned blob here, and run() uploads those blobs (build a new Pipeline for new coordinates)."""
 
     def __init__(self, engine, batch, pinned, boxtable, category_mask, n_chunks=4, pair_cap=None, hit_cap=None,
                  n_streams=3):
@@ -314,13 +315,34 @@ class Pipeline(object):
             ch = Plan()
             ch.lo, ch.hi, ch.n = lo, hi, n
             ch.stream = self.streams[k % len(self.streams)]
-            ch.dev = {name: torch.zeros((n,) + tuple(getattr(batch, name).shape[1:]),
-                                        dtype=pinned[name].dtype, device=dev) for name in _FIELDS}
+            # One host -> device copy per chunk: the chunk's slices of the uploaded planes sit back to back in ONE
+            # pinned blob (built here, once) and land in ONE device blob whose sub-ranges ARE the device planes
+            # (PCIe moves 40 MB pieces at ~55 GB/s but 2-10 MB pieces at ~36 GB/s, profiles/pcie_probe.json).  The
+            # compact base plane (slots 0..10) is widened to 16 slots on the device.
+            compact = pinned["base_xyz"].shape[1] < _lib.BASE_SLOTS
+            uploaded = [name for name in _FIELDS if name not in ("center", "rot")]
+            offs, total = {}, 0
+            for name in uploaded:
+                src = pinned[name][lo:hi]
+                offs[name] = (total, src.numel() * src.element_size(), src.dtype, tuple(src.shape))
+                total += (offs[name][1] + 255) // 256 * 256
+            ch.host_blob = torch.empty(max(total, 1), dtype=torch.uint8).pin_memory()
+            ch.dev_blob = torch.empty(max(total, 1), dtype=torch.uint8, device=dev)
+            ch.dev = {}
+            ch.base_stage = None
+            for name in uploaded:
+                o, nb, dt, shape = offs[name]
+                ch.host_blob[o:o + nb].view(dt).view(shape).copy_(pinned[name][lo:hi])
+                view = ch.dev_blob[o:o + nb].view(dt).view(shape)
+                if name == "base_xyz" and compact:
+                    ch.base_stage = view
+                    ch.dev[name] = torch.zeros((n, _lib.BASE_SLOTS, 3), dtype=dt, device=dev)
+                else:
+                    ch.dev[name] = view
+            for name in ("center", "rot"):
+                ch.dev[name] = torch.zeros((n,) + tuple(getattr(batch, name).shape[1:]), dtype=pinned[name].dtype,
+                                           device=dev)
             t = ch.dev
-            ch.base_stage = None                  # compact pinned base plane: land here, then widen on the device
-            if pinned["base_xyz"].shape[1] < _lib.BASE_SLOTS:
-                ch.base_stage = torch.empty((n,) + tuple(pinned["base_xyz"].shape[1:]), dtype=pinned["base_xyz"].dtype,
-                                            device=dev)
             ch.nts = _lib.NtsStruct(n_nt=n, reserved=0, center=t["center"].data_ptr(), rot=t["rot"].data_ptr(),
                                     base_xyz=t["base_xyz"].data_ptr(), bb_xyz=t["bb_xyz"].data_ptr(),
                                     base_mask=t["base_mask"].data_ptr(), bb_mask=t["bb_mask"].data_ptr(),
@@ -348,14 +370,9 @@ class Pipeline(object):
         for ch in self.chunks:
             ch.stream.wait_event(start)
             with torch.cuda.stream(ch.stream):
-                for name in _FIELDS:
-                    if name in ("center", "rot"):
-                        continue
-                    if name == "base_xyz" and ch.base_stage is not None:
-                        ch.base_stage.copy_(self.pinned[name][ch.lo:ch.hi], non_blocking=True)
-                        ch.dev[name][:, :ch.base_stage.shape[1]].copy_(ch.base_stage, non_blocking=True)
-                    else:
-                        ch.dev[name].copy_(self.pinned[name][ch.lo:ch.hi], non_blocking=True)
+                ch.dev_blob.copy_(ch.host_blob, non_blocking=True)
+                if ch.base_stage is not None:
+                    ch.dev["base_xyz"][:, :ch.base_stage.shape[1]].copy_(ch.base_stage, non_blocking=True)
                 eng.run_plan(ch, ch.plan, self.bt, self.mask, fit_frames=True, index_offset=ch.lo)
                 ch.counters_host.copy_(ch.plan.counters, non_blocking=True)
                 ch.ev.record(ch.stream)
