@@ -289,3 +289,36 @@ def test_product_does_not_import_oracle():
             if f.endswith(".py"):
                 text = open(os.path.join(d, f)).read()
                 assert not pat.search(text), os.path.join(d, f)
+
+
+def test_host_tail_in_forked_workers_equals_serial(golden):
+    """NA._host_tail (the per-structure tail of annotate_batch) with worker processes: 24 copies of the 1S72 strand
+    as one batch, hit records encoded from the oracle's traces with global nt indices, like the GPU's."""
+    spec = golden("spec_1s72_strand.json.gz")
+    cats = golden("annot_1s72_strand_all9.json.gz")["categories"]
+    _, _, tr = O.annotate(spec, cats)
+    focused = NA.focus_basepair_cutoffs(NA.nt_nt_cutoffs, cats["basepair"])
+    bt, atoms = NA._box_table(focused, NA.load_ideal_basepair_hydrogen_bonds())
+    one = traces_to_hits(spec, tr, bt)
+    S, n = 24, len(spec["nts"])
+    specs = [dict(spec, pdb="X%03d" % k) for k in range(S)]
+    batch = packing.pack_specs(specs)
+    parts = []
+    for k in range(S):
+        h = one.copy()
+        h["i"] += k * n
+        h["j"] += k * n
+        h["rank"] += 16 * k * n
+        parts.append(h)
+    hits = postprocess.sort_hits(np.concatenate(parts))
+    sidx = np.searchsorted(batch.struct_off, hits["i"], side="right") - 1
+    cuts = np.searchsorted(sidx, np.arange(S + 1))
+    serial = NA._host_tail(batch, hits, cuts, bt, atoms, cats, 1)
+    forked = NA._host_tail(batch, hits, cuts, bt, atoms, cats, 3)
+    assert len(serial) == len(forked) == S
+    for k, (a, b) in enumerate(zip(serial, forked)):
+        assert list(a[0].keys()) == list(b[0].keys())
+        assert {x: list(v) for x, v in a[0].items()} == {x: list(v) for x, v in b[0].items()}
+        assert {x: set(v) for x, v in a[1].items()} == {x: set(v) for x, v in b[1].items()}
+        assert all(u.startswith("X%03d|" % k) for v in a[0].values() for u, _, _ in v)
+    assert NA._TAIL_JOB is None
