@@ -234,6 +234,22 @@ _group_names = {}
 
 def covalent_connections(ident, out, c2i):
     """annotate_covalent_connections, NA:1181-1210."""
+    n = len(ident.index)
+    uid = ident.unit_id
+    # common case - one model, one symmetry operator, every (chain, index) used once: the sorted (group, index) keys
+    # are the nts ordered by (chain, index), and successive keys of one chain are linked
+    if n and len(set(ident.model)) == 1 and len(set(ident.symmetry)) == 1:
+        chain, index = ident.chain, ident.index.tolist()
+        keys = sorted(zip(chain, index, range(n)))
+        if all(keys[k][:2] != keys[k + 1][:2] for k in range(n - 1)):
+            prev_c, prev_i, prev_k = keys[0]
+            for c, i, k in keys[1:]:
+                if c == prev_c:
+                    inter = "p_" + str(i - prev_i)
+                    out[inter].append((uid[prev_k], uid[k], None))
+                    c2i["covalent"].add(inter)
+                prev_c, prev_i, prev_k = c, i, k
+            return
     groups = defaultdict(list)
     for k, (m, sy, ch, ix) in enumerate(zip(ident.model, ident.symmetry, ident.chain, ident.index.tolist())):
         key = (m, sy, ch)
