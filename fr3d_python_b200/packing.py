@@ -58,10 +58,21 @@ class NtBatch(object):
             if self._unit_id_fn is not None:
                 self._unit_ids = self._unit_id_fn()
             else:
-                sof = self.structure_of()
-                self._unit_ids = [encode_unit_id(self.pdb[sof[k]], self.model[k], self.chain[k], self.sequence[k],
-                                                 self.number[k], self.alt_id[k], self.insertion_code[k],
-                                                 self.symmetry[k]) for k in range(self.n)]
+                sof = self.structure_of().tolist()
+                pdb, model, chain, seq, num = self.pdb, self.model, self.chain, self.sequence, self.number
+                alt, ins, sym = self.alt_id, self.insertion_code, self.symmetry
+                out = []
+                for k in range(self.n):
+                    nk = num[k]
+                    # the common id: no alt id, no insertion code, identity operator, a residue number - nothing is
+                    # trimmed after the number, so the id is the first five fields joined (encode_unit_id)
+                    if not alt[k] and not ins[k] and (not sym[k] or sym[k] == '1_555') and nk is not None and nk != '':
+                        p_, m_, c_, s_ = pdb[sof[k]], model[k], chain[k], seq[k]
+                        out.append("%s|%s|%s|%s|%s" % ('' if p_ is None else p_, '' if m_ is None else m_,
+                                                       '' if c_ is None else c_, '' if s_ is None else s_, nk))
+                    else:
+                        out.append(encode_unit_id(pdb[sof[k]], model[k], chain[k], seq[k], nk, alt[k], ins[k], sym[k]))
+                self._unit_ids = out
         return self._unit_ids
 
     def nbytes_device(self):
@@ -371,5 +382,159 @@ def pack_structures(structures, chains=None):
         b.center[framed] = np.array(ctrs)
     b.struct_off = np.array(off, dtype=np.int64)
     b._unit_ids = uids
+    _finish_identity(b)
+    return b
+
+
+# ------------------------------------------------------------------ array-native ingest
+def specs_to_columns(specs):
+    """Column form of coordinate specs: what a columnar mmCIF atom_site reader yields after residues have been
+    delimited (the reference does that in fr3d/cif/reader.py:440-481).  Returns the arguments of pack_columns."""
+    if isinstance(specs, dict):
+        specs = [specs]
+    res = {k: [] for k in ("sequence", "chain", "number", "index", "model", "symmetry", "alt_id", "insertion_code")}
+    atom_res, atom_name, atom_xyz, off, pdb = [], [], [], [0], []
+    r = 0
+    for spec in specs:
+        pdb.append(spec["pdb"])
+        for nt in spec["nts"]:
+            for k in res:
+                res[k].append(nt.get(k))
+            for a in nt["atoms"]:
+                atom_res.append(r); atom_name.append(a[0]); atom_xyz.append(a[1:4])
+            r += 1
+        off.append(r)
+    return (np.array(atom_res, dtype=np.int64), np.array(atom_name, dtype=str),
+            np.array(atom_xyz, dtype=np.float64).reshape(-1, 3), res, pdb, np.array(off, dtype=np.int64))
+
+
+def pack_columns(atom_res, atom_name, atom_xyz, res, pdb, struct_off):
+    """pack_specs for column data, without a Python loop over atoms.
+
+    atom_res int[n_atoms]: residue (row of the residue table) of every atom, atom_name str[n_atoms], atom_xyz
+    float64[n_atoms, 3]; res: dict of per-residue columns (sequence, chain, number, index, model, symmetry, alt_id,
+    insertion_code); pdb: id per structure; struct_off: residue offsets of the structures.  Produces exactly the
+    NtBatch pack_specs produces (tests/test_host_logic.py compares every array): atom names are mapped to slots
+    through one (residue type x atom name) table, coordinates are scattered with one fancy assignment, masks with
+    bitwise-or reductions.  Residues in which a name occurs more than once (alternate conformers listed together;
+    AtomProxy averages them, base.py:150-166) take the per-atom path of pack_specs."""
+    atom_res = np.asarray(atom_res, dtype=np.int64)
+    atom_xyz = np.asarray(atom_xyz, dtype=np.float64).reshape(-1, 3)
+    names = np.asarray(atom_name)
+    if names.dtype.kind not in "US":
+        names = names.astype(str)
+    seqs = list(res["sequence"])
+    n = len(seqs)
+    b = NtBatch(n)
+    b.pdb = list(pdb)
+    b.struct_off = np.asarray(struct_off, dtype=np.int64)
+    b.model, b.chain, b.sequence = list(res["model"]), list(res["chain"]), seqs
+    b.number, b.index, b.symmetry = list(res["number"]), list(res["index"]), list(res["symmetry"])
+    b.alt_id = list(res.get("alt_id") or [None] * n)
+    b.insertion_code = list(res.get("insertion_code") or [None] * n)
+    if n == 0:
+        _finish_identity(b)
+        return b
+    # residue types and atom names as small integer codes
+    useq = sorted(set(seqs))
+    seq_code = {s: k for k, s in enumerate(useq)}
+    sc_res = np.fromiter((seq_code[s] for s in seqs), dtype=np.int64, count=n)
+    if len(names) == 0:
+        uname, nc = np.zeros(0, dtype=str), np.zeros(0, dtype=np.int64)
+    elif names.dtype.kind == "U" and names.dtype.itemsize <= 16:
+        # names of at most four characters (every PDB atom name): pack the code points into one uint64 per atom and
+        # find the distinct names on integers - sorting 7 k strings per structure was the largest single cost
+        cp = np.ascontiguousarray(names).view(np.uint32).reshape(len(names), -1).astype(np.uint64)
+        if cp.max() < 65536:
+            key = cp[:, 0].copy()
+            for c in range(1, cp.shape[1]):
+                key |= cp[:, c] << np.uint64(16 * c)
+            ukey, first, nc = np.unique(key, return_index=True, return_inverse=True)
+            uname = names[first].astype(str)
+        else:
+            uname, nc = np.unique(names, return_inverse=True)
+            uname = uname.astype(str)
+    else:
+        uname, nc = np.unique(names, return_inverse=True)
+        uname = uname.astype(str)
+    maps = [_slot_maps(s) for s in useq]
+    t_base = np.full((len(useq), max(len(uname), 1)), -1, dtype=np.int64)
+    t_bb = np.full((len(useq), max(len(uname), 1)), -1, dtype=np.int64)
+    name_code = {nm: k for k, nm in enumerate(uname.tolist())}
+    for k, m in enumerate(maps):
+        if m is None:
+            continue
+        for nm, slot in m[2].items():
+            if nm in name_code:
+                t_base[k, name_code[nm]] = slot
+        for nm, slot in m[3].items():
+            if nm in name_code and t_base[k, name_code[nm]] < 0:          # (_fill_atoms looks the base map up first)
+                t_bb[k, name_code[nm]] = slot
+    pcode = np.array([-1 if m is None else m[0] for m in maps], dtype=np.int64)[sc_res]
+    flags = np.array([0 if m is None else m[1] for m in maps], dtype=np.int64)[sc_res]
+    dupmask = np.array([0 if m is None else m[4] for m in maps], dtype=np.int64)[sc_res]
+    sc_atom = sc_res[atom_res]
+    sb = t_base[sc_atom, nc] if len(nc) else np.zeros(0, dtype=np.int64)
+    sk = t_bb[sc_atom, nc] if len(nc) else np.zeros(0, dtype=np.int64)
+    in_base, in_bb = sb >= 0, sk >= 0
+    # residues with a repeated (residue, slot): per-atom path afterwards
+    key = np.concatenate([atom_res[in_base] * 32 + sb[in_base], atom_res[in_bb] * 32 + 16 + sk[in_bb]])
+    uk, cnt = np.unique(key, return_counts=True)
+    slow = np.unique(uk[cnt > 1] // 32)
+    is_slow = np.zeros(n, dtype=bool)
+    is_slow[slow] = True
+    fast_b = in_base & ~is_slow[atom_res]
+    fast_k = in_bb & ~is_slow[atom_res]
+    b.base_xyz[atom_res[fast_b], sb[fast_b]] = atom_xyz[fast_b]
+    b.bb_xyz[atom_res[fast_k], sk[fast_k]] = atom_xyz[fast_k]
+    bmask = np.zeros(n, dtype=np.int64)
+    bbmask = np.zeros(n, dtype=np.int64)
+    np.bitwise_or.at(bmask, atom_res[fast_b], np.left_shift(1, sb[fast_b]))
+    np.bitwise_or.at(bbmask, atom_res[fast_k], np.left_shift(1, sk[fast_k]))
+    # modified residues without any observed hydrogen receive ideal-position copies (components.py:505-513)
+    has_h_name = np.array(['H' in nm for nm in uname.tolist()], dtype=bool)
+    saw_h = np.zeros(n, dtype=bool)
+    if len(nc):
+        np.logical_or.at(saw_h, atom_res, has_h_name[nc])
+    dup = ((flags & _lib.FLAG_MODIFIED) != 0) & ~saw_h & (pcode >= 0)
+    flags = np.where(dup, flags | _lib.FLAG_DUP, flags)
+    meta7 = np.where(dup, dupmask, 0)
+    # observed amino hydrogens: H62 / H42 / H22 is the one nearer N7 / C5 / N1 (components.py:405-445)
+    for parent, (heavy, h1, h2) in _AMINO.items():
+        so = defs.SLOT_OF[parent]
+        sh, s1, s2 = so[heavy], so[h1], so[h2]
+        need = (1 << sh) | (1 << s1) | (1 << s2)
+        rows = np.nonzero((pcode == defs.PARENT_CODE[parent]) & ((flags & _lib.FLAG_MODIFIED) == 0) &
+                          ((bmask & need) == need) & ~is_slow)[0]
+        if len(rows):
+            a, p1, p2 = b.base_xyz[rows, sh], b.base_xyz[rows, s1].copy(), b.base_xyz[rows, s2].copy()
+            d1 = ((a - p1) ** 2).sum(axis=1)        # same order of operations as _fix_amino_hydrogens
+            d2 = ((a - p2) ** 2).sum(axis=1)
+            swap = rows[d1 < d2]
+            b.base_xyz[swap, s1] = p2[d1 < d2]
+            b.base_xyz[swap, s2] = p1[d1 < d2]
+    known = pcode >= 0
+    b.base_mask[:] = np.where(known, bmask | (((pcode + 1) & 15) << 16) | ((flags & 15) << 20), 0).astype(np.uint32)
+    b.bb_mask[:] = np.where(known, bbmask, 0).astype(np.uint32)
+    b.meta[:, 0] = pcode
+    b.meta[:, 1] = np.where(known, flags, 0)
+    b.meta[:, 7] = np.where(known, meta7, 0)
+    if len(slow):                                    # the rare residues with repeated atom names
+        order = np.argsort(atom_res, kind="stable")
+        starts = np.searchsorted(atom_res[order], np.arange(n + 1))
+        for r_ in slow.tolist():
+            m = maps[sc_res[r_]]
+            if m is None:
+                continue
+            rows_ = _Rows()
+            idx = order[starts[r_]:starts[r_ + 1]]
+            _fill_atoms(rows_, m, [(str(names[i]), atom_xyz[i, 0], atom_xyz[i, 1], atom_xyz[i, 2]) for i in idx.tolist()])
+            if not (m[1] & _lib.FLAG_MODIFIED):
+                _fix_amino_hydrogens(rows_, defs.PARENTS[m[0]])
+            b.base_xyz[r_] = np.array(rows_.base, dtype=np.float64).reshape(_lib.BASE_SLOTS, 3)
+            b.bb_xyz[r_] = np.array(rows_.bb, dtype=np.float64).reshape(_lib.BB_SLOTS, 3)
+            b.base_mask[r_] = rows_.bmask[0]
+            b.bb_mask[r_] = rows_.bbmask[0]
+            b.meta[r_, 0], b.meta[r_, 1], b.meta[r_, 7] = rows_.meta0[0], rows_.meta1[0], rows_.meta7[0]
     _finish_identity(b)
     return b

@@ -2,6 +2,7 @@
 inputs) on CPU.  The GPU stage is replaced by hit records made from the oracle's per-rule
 traces, so the order-dependent tail is checked against the reference golden without a GPU."""
 
+import copy
 import os
 
 import numpy as np
@@ -322,3 +323,37 @@ def test_host_tail_in_forked_workers_equals_serial(golden):
         assert {x: set(v) for x, v in a[1].items()} == {x: set(v) for x, v in b[1].items()}
         assert all(u.startswith("X%03d|" % k) for v in a[0].values() for u, _, _ in v)
     assert NA._TAIL_JOB is None
+
+
+@pytest.mark.parametrize("name", ["1gid_full", "1gid_modified", "1gid_variants", "1s72_strand", "chi_sweep"])
+def test_array_native_packer_equals_pack_specs(golden, name):
+    """packing.pack_columns (no Python loop over atoms) against packing.pack_specs on every fixture: DNA, modified
+    residues with and without observed hydrogens, missing atoms, alt ids, two models, symmetry copies."""
+    spec = golden("spec_%s.json.gz" % name)
+    if name == "1s72_strand":                # observed (mislabelled) amino hydrogens and a repeated atom name
+        spec = copy.deepcopy(spec)
+        for nt in spec["nts"]:
+            xyz = {a[0]: a[1:] for a in nt["atoms"]}
+            if nt["sequence"] == "A":
+                nt["atoms"] += [["H61"] + [v + 0.9 for v in xyz["N6"]], ["H62"] + [v - 0.9 for v in xyz["N6"]]]
+            if nt["sequence"] == "U":
+                nt["atoms"] += [["O4"] + [v + 0.2 for v in xyz["O4"]]]
+    want = packing.pack_specs(spec)
+    got = packing.pack_columns(*packing.specs_to_columns(spec))
+    for field in ("center", "rot", "base_xyz", "bb_xyz", "base_mask", "bb_mask", "meta", "struct_off"):
+        assert np.array_equal(getattr(got, field), getattr(want, field)), field
+    for field in ("pdb", "model", "chain", "sequence", "number", "index", "symmetry", "alt_id", "insertion_code"):
+        assert getattr(got, field) == getattr(want, field), field
+    assert got.unit_ids() == want.unit_ids() and got.frames_given == want.frames_given
+
+
+def test_array_native_packer_on_a_batch_and_empty_input():
+    base = synthetic.pack_base()
+    batch = synthetic.make_structure_batch(base, 7, seed0=11)
+    specs = [synthetic.batch_to_spec(batch, s) for s in range(7)]
+    want = packing.pack_specs(specs)
+    got = packing.pack_columns(*packing.specs_to_columns(specs))
+    for field in ("base_xyz", "bb_xyz", "base_mask", "bb_mask", "meta", "struct_off"):
+        assert np.array_equal(getattr(got, field), getattr(want, field)), field
+    empty = packing.pack_columns(*packing.specs_to_columns([]))
+    assert empty.n == 0 and empty.n_structures == 0
