@@ -254,48 +254,61 @@ def _fix_amino_hydrogens(rows, parent):
             flat[o + 3 * s2:o + 3 * s2 + 3] = p1
 
 
+def _prev_o3_of_structure(lo, hi, model, symmetry, chain, m4, uid, has_o3, src, dst):
+    """map_unit_id_to_previous_O3 (NA:480-525) for one structure, any mix of models / operators / repeated positions:
+    walk the nts in (model, symmetry, chain, index, unit id) order, link successive indices of one chain."""
+    order = sorted(range(lo, hi), key=lambda k: (model[k], symmetry[k] or "", chain[k], m4[k], uid[k]))
+    prev = None
+    for k in order:
+        if prev is not None and model[k] == model[prev] and symmetry[k] == symmetry[prev] \
+                and chain[k] == chain[prev] and m4[k] == m4[prev] + 1:
+            if has_o3[prev]:                     # O3' of the previous nt
+                src.append(prev); dst.append(k)
+        prev = k
+
+
 def _finish_identity(batch):
     """group ids, chain ranks, alt-id keys and previous-O3' (map_unit_id_to_previous_O3, NA:480-525)."""
     n = batch.n
-    sof = batch.structure_of() if n else np.zeros(0, dtype=np.int64)
-    groups = {}
-    chains = sorted(set(batch.chain))
-    chain_rank = {c: r for r, c in enumerate(chains)}
-    any_alt = any(a is not None for a in batch.alt_id)
-    resid = {}
-    alts = {}
-    # plain Python lists inside the loops, one numpy write per column at the end
+    if not n:
+        return
+    sof = batch.structure_of()
     sof_l = sof.tolist()
-    m2, m3, m4, m5, m6 = [0] * n, [0] * n, [0] * n, [0] * n, [0] * n
-    for k in range(n):
-        m2[k] = groups.setdefault((sof_l[k], batch.model[k]), len(groups))
-        m3[k] = chain_rank[batch.chain[k]]
-        idx = batch.index[k]
-        m4[k] = 0 if idx is None else int(idx)
-        if any_alt:     # alt-id twins screen, NA:706-713
-            key = (sof_l[k], batch.number[k], batch.sequence[k], batch.chain[k], batch.symmetry[k],
-                   batch.insertion_code[k])
-            m5[k] = resid.setdefault(key, len(resid))
-            m6[k] = alts.setdefault(batch.alt_id[k], len(alts))
-        else:
-            m5[k] = k
-    if n:
-        batch.meta[:, 2] = m2; batch.meta[:, 3] = m3; batch.meta[:, 4] = m4; batch.meta[:, 5] = m5; batch.meta[:, 6] = m6
-    # previous O3'
-    uid = batch.unit_ids()
-    has_o3 = ((batch.bb_mask >> 5) & 1).tolist()
-    model, symmetry, chain = batch.model, batch.symmetry, batch.chain
-    src, dst = [], []
-    for s in range(batch.n_structures):
-        lo, hi = int(batch.struct_off[s]), int(batch.struct_off[s + 1])
-        order = sorted(range(lo, hi), key=lambda k: (model[k], symmetry[k] or "", chain[k], m4[k], uid[k]))
-        prev = None
-        for k in order:
-            if prev is not None and model[k] == model[prev] and symmetry[k] == symmetry[prev] \
-                    and chain[k] == chain[prev] and m4[k] == m4[prev] + 1:
-                if has_o3[prev]:                     # O3' of the previous nt
-                    src.append(prev); dst.append(k)
-            prev = k
+    chain_rank = {c: r for r, c in enumerate(sorted(set(batch.chain)))}
+    groups, resid, alts = {}, {}, {}
+    # one pass per column (list comprehensions), one numpy write per column
+    m2 = [groups.setdefault(key, len(groups)) for key in zip(sof_l, batch.model)]
+    m3 = [chain_rank[c] for c in batch.chain]
+    m4 = [0 if i is None else int(i) for i in batch.index]
+    if any(a is not None for a in batch.alt_id):     # alt-id twins screen, NA:706-713
+        m5 = [resid.setdefault(key, len(resid)) for key in zip(sof_l, batch.number, batch.sequence, batch.chain,
+                                                                batch.symmetry, batch.insertion_code)]
+        m6 = [alts.setdefault(a, len(alts)) for a in batch.alt_id]
+    else:
+        m5, m6 = np.arange(n), 0
+    batch.meta[:, 2] = m2; batch.meta[:, 3] = m3; batch.meta[:, 4] = m4; batch.meta[:, 5] = m5; batch.meta[:, 6] = m6
+    # previous O3'.  Structures with one model, one operator and no repeated (chain, index) - nearly all - are done
+    # together with numpy: sort by (structure, chain rank, index), link neighbours; the others one by one.
+    has_o3 = (batch.bb_mask >> 5) & 1
+    m3a, m4a = np.asarray(m3, dtype=np.int64), np.asarray(m4, dtype=np.int64)
+    codes = {}
+    ms = np.fromiter((codes.setdefault(key, len(codes)) for key in zip(batch.model, batch.symmetry)), dtype=np.int64, count=n)
+    starts = batch.struct_off[:-1][np.diff(batch.struct_off) > 0]
+    simple = np.zeros(batch.n_structures, dtype=bool)
+    nonempty = np.nonzero(np.diff(batch.struct_off) > 0)[0]
+    simple[nonempty] = np.minimum.reduceat(ms, starts) == np.maximum.reduceat(ms, starts)
+    order = np.lexsort((m4a, m3a, sof))
+    so, c3, c4 = sof[order], m3a[order], m4a[order]
+    tie = (so[1:] == so[:-1]) & (c3[1:] == c3[:-1]) & (c4[1:] == c4[:-1])
+    simple[so[1:][tie]] = False
+    link = (so[1:] == so[:-1]) & (c3[1:] == c3[:-1]) & (c4[1:] == c4[:-1] + 1) & simple[so[1:]] & (has_o3[order[:-1]] == 1)
+    src, dst = order[:-1][link].tolist(), order[1:][link].tolist()
+    if not simple.all():
+        uid = batch.unit_ids()
+        has_l = has_o3.tolist()
+        for s in np.nonzero(~simple)[0].tolist():
+            _prev_o3_of_structure(int(batch.struct_off[s]), int(batch.struct_off[s + 1]), batch.model, batch.symmetry,
+                                  batch.chain, m4, uid, has_l, src, dst)
     if dst:
         batch.bb_xyz[dst, defs.BB_PREV_O3] = batch.bb_xyz[src, 5]
         batch.bb_mask[dst] |= np.uint32(1 << defs.BB_PREV_O3)

@@ -357,3 +357,89 @@ def test_array_native_packer_on_a_batch_and_empty_input():
         assert np.array_equal(getattr(got, field), getattr(want, field)), field
     empty = packing.pack_columns(*packing.specs_to_columns([]))
     assert empty.n == 0 and empty.n_structures == 0
+
+
+# ---- the packer's identity bookkeeping: the first (loop per nt, sort per structure) implementation as the expected
+# ---- behaviour of the vectorised one
+def _finish_identity_v0(batch):
+    """group ids, chain ranks, alt-id keys and previous-O3' (map_unit_id_to_previous_O3, NA:480-525)."""
+    n = batch.n
+    sof = batch.structure_of() if n else np.zeros(0, dtype=np.int64)
+    groups = {}
+    chains = sorted(set(batch.chain))
+    chain_rank = {c: r for r, c in enumerate(chains)}
+    any_alt = any(a is not None for a in batch.alt_id)
+    resid = {}
+    alts = {}
+    # plain Python lists inside the loops, one numpy write per column at the end
+    sof_l = sof.tolist()
+    m2, m3, m4, m5, m6 = [0] * n, [0] * n, [0] * n, [0] * n, [0] * n
+    for k in range(n):
+        m2[k] = groups.setdefault((sof_l[k], batch.model[k]), len(groups))
+        m3[k] = chain_rank[batch.chain[k]]
+        idx = batch.index[k]
+        m4[k] = 0 if idx is None else int(idx)
+        if any_alt:     # alt-id twins screen, NA:706-713
+            key = (sof_l[k], batch.number[k], batch.sequence[k], batch.chain[k], batch.symmetry[k],
+                   batch.insertion_code[k])
+            m5[k] = resid.setdefault(key, len(resid))
+            m6[k] = alts.setdefault(batch.alt_id[k], len(alts))
+        else:
+            m5[k] = k
+    if n:
+        batch.meta[:, 2] = m2; batch.meta[:, 3] = m3; batch.meta[:, 4] = m4; batch.meta[:, 5] = m5; batch.meta[:, 6] = m6
+    # previous O3'
+    uid = batch.unit_ids()
+    has_o3 = ((batch.bb_mask >> 5) & 1).tolist()
+    model, symmetry, chain = batch.model, batch.symmetry, batch.chain
+    src, dst = [], []
+    for s in range(batch.n_structures):
+        lo, hi = int(batch.struct_off[s]), int(batch.struct_off[s + 1])
+        order = sorted(range(lo, hi), key=lambda k: (model[k], symmetry[k] or "", chain[k], m4[k], uid[k]))
+        prev = None
+        for k in order:
+            if prev is not None and model[k] == model[prev] and symmetry[k] == symmetry[prev] \
+                    and chain[k] == chain[prev] and m4[k] == m4[prev] + 1:
+                if has_o3[prev]:                     # O3' of the previous nt
+                    src.append(prev); dst.append(k)
+            prev = k
+    if dst:
+        batch.bb_xyz[dst, defs.BB_PREV_O3] = batch.bb_xyz[src, 5]
+        batch.bb_mask[dst] |= np.uint32(1 << defs.BB_PREV_O3)
+
+
+
+
+def _identity_fields(batch):
+    return batch.meta.copy(), batch.bb_xyz.copy(), batch.bb_mask.copy()
+
+
+@pytest.mark.parametrize("name", ["1gid_full", "1gid_modified", "1gid_variants", "1s72_strand", "chi_sweep", "shuffled"])
+def test_identity_bookkeeping_equals_first_implementation(golden, name):
+    from fr3d_python_b200 import definitions as defs  # noqa: F401
+    if name == "shuffled":            # several structures, nts out of order, repeated positions, missing O3', no index
+        spec = copy.deepcopy(golden("spec_1gid_variants.json.gz"))
+        rng = np.random.default_rng(5)
+        specs = []
+        for k in range(4):
+            nts = [copy.deepcopy(spec["nts"][i]) for i in rng.permutation(len(spec["nts"]))[:150 + 40 * k]]
+            for q, nt in enumerate(nts):
+                if q % 11 == 0:
+                    nt["atoms"] = [a for a in nt["atoms"] if a[0] != "O3'"]
+                if q % 29 == 0:
+                    nt["index"] = None
+            specs.append({"pdb": "SH%d" % k, "nts": nts})
+        specs.append({"pdb": "EMPTY", "nts": []})
+    else:
+        specs = [golden("spec_%s.json.gz" % name)]
+    b = packing.pack_specs(specs)
+    got = _identity_fields(b)
+    # undo the previous-O3' slot, then run the first implementation on the same batch
+    b.bb_xyz[:, defs.BB_PREV_O3] = 0.0
+    b.bb_mask &= ~np.uint32(1 << defs.BB_PREV_O3)
+    b.meta[:, 2:7] = -7
+    _finish_identity_v0(b)
+    want = _identity_fields(b)
+    for g, w, what in zip(got, want, ("meta", "bb_xyz", "bb_mask")):
+        assert np.array_equal(g, w), what
+    assert (got[2] >> defs.BB_PREV_O3 & 1).sum() > 0 or name == "chi_sweep"
