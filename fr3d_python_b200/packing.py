@@ -10,11 +10,14 @@ per-nt device record documented in include/fr3d_b200.h.  Two sources:
                                carry rotation_matrix / centers / inferred hydrogens
 """
 
+import operator
+
 import numpy as np
 
 from . import _lib
 from . import definitions as defs
 
+_ATOM_FIELDS = operator.attrgetter("name", "x", "y", "z")        # one C-level call per atom object
 _AMINO = {'A': ("N7", "H61", "H62"), 'C': ("C5", "H41", "H42"), 'G': ("N1", "H21", "H22")}  # components.py:410-428
 
 
@@ -379,7 +382,7 @@ def pack_structures(structures, chains=None):
             if maps is None:
                 rows.add_unknown()
             else:
-                _fill_atoms(rows, maps, ((a.name, a.x, a.y, a.z) for a in c.atoms()), frames_given=True)
+                _fill_atoms(rows, maps, map(_ATOM_FIELDS, c.atoms()), frames_given=True)
                 R = c.rotation_matrix
                 ctr = c.centers["base"]
                 if R is not None and len(ctr) == 3:
