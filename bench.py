@@ -308,6 +308,8 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, S),
+                "dtype_note": "every label / number of a hit record is decided in f64; f32 only screens (supersets) and "
+                              "decides stacking comparisons that are certain by a margin, f64 recomputation otherwise",
                 "structures_per_s": S * world * args.steps / (ms_total / 1000.0),
                 "pairs_per_step": pairs_all, "hits_per_step": hits_all,
                 "worklists_rank0": {"light_detail_pairs": int(wl[4]), "stacking_pairs": int(wl[5]),
