@@ -7,8 +7,8 @@
 // (bounds below), which keeps it a superset.  ncu on the fp64 screen (profiles/step_r1n_*): 16 warps per SM (the
 // 49-double rows fill shared memory, 128 registers per thread), 41 % issue utilisation, stalls = global loads of
 // nt1 and fp64 dependency chains.  The fp32 record is 320 B instead of 760 B (the 316 k records of the bench batch
-// are 101 MB: they stay in the 126 MB L2 between the kernel that writes them and this one), a staged row is 49
-// floats, and 24-32 warps fit on an SM.
+// are 101 MB: they mostly stay in the 126 MB L2 between the kernel that writes them and this one), a staged row is
+// 52 floats (copied in 16-byte pieces, read with 128-bit loads), and 24 warps run per SM at 80 registers.
 //
 // Screen record of one nt, 80 32-bit words (screen_records_kernel):
 //   0..2   base centre as fixed point, 2^-16 A (int32): e = c2 - c1 is an exact integer difference
@@ -18,8 +18,8 @@
 //   9..29  OP1 OP2 O5' O4' O3' O2' and the previous nt's O3' (backbone slots 1..6, 9) minus the centre
 //   30     base_mask   31  bb_mask
 //   32..79 the 16 base points minus the centre
-// Words 0..31 are staged for the sO / sugar-ribose / base-phosphate screens (exactly one copy instruction per
-// row), words 32..79 then take their place for the stacking / pairing screens.
+// Words 0..31 are staged for the sO / sugar-ribose / base-phosphate screens (eight 16-byte copies per row: one
+// instruction moves four rows), words 32..79 then take their place for the stacking / pairing screens.
 //
 // Error bounds (|coordinate| < 32 000 A is enforced by the fixed-point conversion, larger ones raise
 // FR3D_E_RANGE): centre-relative coordinates are below 16 A, so their fp32 images carry <= 1e-6 A; e carries
