@@ -635,3 +635,16 @@ def test_search_screen_large_and_edge_cases():
     assert PP.fixed_radius_search(5, ["1"] * 5, np.full((5, 3), np.nan), 10.0, 100.0) == []
     two_models = PP.fixed_radius_search(4, ["1", "1", "2", "2"], np.array([[0., 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0]]), 5.0, 10.0)
     assert sorted((a, b) for a, b, _ in two_models) == [(0, 1), (2, 3)]     # never across models
+
+
+def test_search_screen_capacity_overflow_is_rerun_not_truncated():
+    """A dense cloud yields more pairs than the first output capacity (64 n + 1024): the call is repeated with the
+    exact count (FR3D_E_CAPACITY semantics), nothing is dropped."""
+    from fr3d_python_b200.search import pair_processing as PP
+    rng = np.random.default_rng(3)
+    pts = rng.uniform(0.0, 9.0, size=(1500, 3))
+    a, b, dd = PP.radius_pairs(pts, np.zeros(len(pts), dtype=np.int32), 20.0)
+    assert len(a) == 1500 * 1499 // 2 > 64 * 1500 + 1024
+    und = np.minimum(a, b).astype(np.int64) * 1500 + np.maximum(a, b)
+    assert len(np.unique(und)) == len(und)
+    assert np.abs(dd - ((pts[a] - pts[b]) ** 2).sum(axis=1)).max() < 1e-12
