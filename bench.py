@@ -254,12 +254,13 @@ def main():
     from fr3d_python_b200.engine import Pipeline
     pipe = Pipeline(eng, batch, pinned, bt, mask, n_chunks=args.chunks, pair_cap=n_pairs, hit_cap=n_hits)
     for _ in range(2):
-        hits_p, n_pairs_p = pipe.run()
+        res_p = pipe.run()
+    hits_p, n_pairs_p = res_p.hits, res_p.n_pairs
     assert n_pairs_p == n_pairs and len(hits_p) == n_hits, "pipelined pass disagrees with the calibration pass"
     barrier()
     t0 = time.perf_counter()
     for k in range(args.steps):
-        hits_p, n_pairs_e = pipe.run()
+        res_p = pipe.run()
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
     barrier()

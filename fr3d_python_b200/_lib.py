@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("FR3D_B200_LIB") or os.path.join(_HERE, "lib", "libfr3
 CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 
-ABI_VERSION = 2          # FR3D_ABI_VERSION of include/fr3d_b200.h
+ABI_VERSION = 3          # FR3D_ABI_VERSION of include/fr3d_b200.h
 BASE_SLOTS = 16
 BB_SLOTS = 10
 META_INTS = 8
@@ -29,10 +29,15 @@ SLOT_SO12, SLOT_SO21, SLOT_STACK, SLOT_SR12, SLOT_SR21, SLOT_BPH, SLOT_BR, SLOT_
 
 E_CUDA, E_ARG, E_CAPACITY, E_NOTABLES, E_RANGE = -1, -2, -3, -4, -5
 
-EXPORTS = ["fr3d_version", "fr3d_last_error", "fr3d_init", "fr3d_upload_tables", "fr3d_frames_fit",
+EXPORTS = ["fr3d_version", "fr3d_last_error", "fr3d_init", "fr3d_upload_tables", "fr3d_frames_fit", "fr3d_frames_fit_from",
            "fr3d_pair_search_workspace", "fr3d_pair_search", "fr3d_classify_workspace", "fr3d_classify_pairs", "fr3d_kabsch_batched",
            "fr3d_bond_orientation", "fr3d_radius_search_workspace", "fr3d_radius_search",
-           "fr3d_discrepancy_all_vs_all", "fr3d_discrepancy_one_vs_many"]
+           "fr3d_discrepancy_all_vs_all", "fr3d_discrepancy_one_vs_many",
+           "fr3d_tail_workspace", "fr3d_annotation_tail"]
+LABEL_COVALENT = 0x40000000
+TAIL_MAX_LABELS = 1024
+TAIL_MAX_NT = 1 << 17
+TAIL_MAX_INDEX = 1 << 23
 
 
 class Fr3dError(RuntimeError):
@@ -63,23 +68,48 @@ class StaticTables(C.Structure):
                 ("hull_r2in", C.c_double * N_PARENTS)]
 
 
+class TailIdentStruct(C.Structure):
+    _fields_ = [("n_struct", C.c_int32), ("n_chains", C.c_int32), ("n_ends", C.c_int32), ("reserved", C.c_int32),
+                ("struct_off", C.c_void_p), ("struct_chain_off", C.c_void_p), ("chain_ends_off", C.c_void_p),
+                ("nt_chain", C.c_void_p), ("nt_cov", C.c_void_p)]
+
+
+class TailTablesStruct(C.Structure):
+    _fields_ = [("n_labels", C.c_int32), ("n_boxes", C.c_int32), ("labels", C.c_void_p), ("boxes", C.c_void_p),
+                ("slot_label", C.c_void_p), ("hydrogen_atoms", C.c_uint64)]
+
+
 _lock = threading.Lock()
 _lib = None
 
 
-def build(verbose=False):
-    """Compile csrc/fr3d_b200.cu for sm_100a into lib/libfr3d_b200.so (in-tree)."""
+def build(verbose=False, only_if_stale=False):
+    """Compile csrc/fr3d_b200.cu for sm_100a into lib/libfr3d_b200.so (in-tree).  Safe when several processes
+    (one per GPU) find the library stale at once: a file lock serialises them, the library is written under a
+    temporary name and renamed, and a process that waited for the lock skips the compile if it is fresh by then."""
+    import fcntl
     os.makedirs(os.path.dirname(LIB_PATH), exist_ok=True)
-    cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-           "-shared", "-Xcompiler", "-fPIC", "-cudart", "static", "-o", LIB_PATH,
-           os.path.join(CSRC, "fr3d_b200.cu")]
-    if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        raise Fr3dError("nvcc failed:\n" + res.stdout + res.stderr)
-    return res.stdout + res.stderr
+    with open(LIB_PATH + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if only_if_stale and not needs_build():          # another process compiled it while we waited
+                return ""
+            tmp = "%s.%d.tmp" % (LIB_PATH, os.getpid())
+            cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+                   "-shared", "-Xcompiler", "-fPIC", "-cudart", "static", "-o", tmp,
+                   os.path.join(CSRC, "fr3d_b200.cu")]
+            if verbose:
+                cmd.insert(1, "-Xptxas")
+                cmd.insert(2, "-v")
+            res = subprocess.run(cmd, capture_output=True, text=True)
+            if res.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise Fr3dError("nvcc failed:\n" + res.stdout + res.stderr)
+            os.replace(tmp, LIB_PATH)
+            return res.stdout + res.stderr
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
 
 
 def needs_build():
@@ -96,21 +126,31 @@ def load():
     with _lock:
         if _lib is not None:
             return _lib
-        if not os.path.exists(LIB_PATH):
-            # a fresh checkout: compile once with nvcc (sm_100a cross-compiles without a GPU)
+        if needs_build() and not os.environ.get("FR3D_B200_LIB"):
+            # a fresh checkout, or sources newer than the library (a stale .so would be dlopen'ed silently and e.g.
+            # receive a newer table struct): compile with nvcc (sm_100a cross-compiles without a GPU)
             try:
-                build()
+                build(only_if_stale=True)          # another rank may be compiling the same file right now
             except Exception as ex:
-                raise Fr3dError("libfr3d_b200.so is not built (%s) and building it failed: %s.  Run `python -c "
-                                "'import __graft_entry__ as g; g.build()'`.  There is no CPU fallback."
+                raise Fr3dError("libfr3d_b200.so is missing or older than its sources (%s) and building it failed: %s."
+                                "  Run `python -c 'import __graft_entry__ as g; g.build()'`.  There is no CPU fallback."
                                 % (LIB_PATH, ex))
         lib = C.CDLL(LIB_PATH)
+        missing = [name for name in EXPORTS if not hasattr(lib, name)]
+        if missing:
+            raise Fr3dError("%s does not export %s: rebuild it (python -c 'import __graft_entry__ as g; g.build()')"
+                            % (LIB_PATH, ", ".join(missing)))
+        lib.fr3d_version.restype = C.c_int
+        if lib.fr3d_version() != ABI_VERSION:
+            raise Fr3dError("%s has ABI version %d, this package needs %d: rebuild it"
+                            % (LIB_PATH, lib.fr3d_version(), ABI_VERSION))
         vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
         lib.fr3d_version.restype = C.c_int
         lib.fr3d_last_error.restype = C.c_char_p
         lib.fr3d_init.argtypes = [C.c_int]
         lib.fr3d_upload_tables.argtypes = [C.POINTER(StaticTables)]
         lib.fr3d_frames_fit.argtypes = [C.POINTER(NtsStruct), vp, C.c_int, vp]
+        lib.fr3d_frames_fit_from.argtypes = [C.POINTER(NtsStruct), vp, i32, vp, C.c_int, vp]
         lib.fr3d_pair_search_workspace.argtypes = [i32]
         lib.fr3d_pair_search_workspace.restype = C.c_size_t
         lib.fr3d_pair_search.argtypes = [C.POINTER(NtsStruct), dbl, vp, C.c_size_t, vp, vp, vp, i64, vp, vp]
@@ -125,9 +165,13 @@ def load():
         lib.fr3d_kabsch_batched.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp]
         lib.fr3d_discrepancy_all_vs_all.argtypes = [vp, vp, vp, i32, i32, dbl, i32, i32, vp, vp]
         lib.fr3d_discrepancy_one_vs_many.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, dbl, dbl, vp, vp, vp]
+        lib.fr3d_tail_workspace.argtypes = [i64, i32, i32, i64]
+        lib.fr3d_tail_workspace.restype = C.c_size_t
+        lib.fr3d_annotation_tail.argtypes = [C.POINTER(NtsStruct), C.POINTER(TailIdentStruct), C.POINTER(TailTablesStruct),
+                                             vp, i64, vp, i32, vp, C.c_size_t, vp, i64, vp, vp, vp, vp]
         for name in EXPORTS:
             if name not in ("fr3d_last_error", "fr3d_pair_search_workspace", "fr3d_classify_workspace",
-                            "fr3d_radius_search_workspace"):
+                            "fr3d_radius_search_workspace", "fr3d_tail_workspace"):
                 getattr(lib, name).restype = C.c_int
         _lib = lib
         return lib

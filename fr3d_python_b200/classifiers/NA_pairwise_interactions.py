@@ -13,9 +13,10 @@ plus the batched form the GPU wants:
 
   annotate_batch(batch_or_specs, categories, ...) -> list of per-structure result tuples
 
-The per-pair rules run in CUDA (csrc/classify.cuh); the order-dependent tail
-(same-edge cleanup, crossing numbers, covalent links, writers) is host Python
-(postprocess.py).  `get_datapoint=True` (rule-development diagnostics incl. hydrogen-bond
+The per-pair rules run in CUDA (csrc/classify*.cuh) and so does the order-dependent tail
+(same-edge cleanup, emission, crossing numbers, covalent links: csrc/tail.cuh); Python only
+turns the final integer rows into unit-id tuples, lazily.  postprocess.py is the host form of
+the tail (tail="host").  `get_datapoint=True` (rule-development diagnostics incl. hydrogen-bond
 checks, NA:2404-2536) is outside the accelerated path and raises.
 """
 
@@ -32,6 +33,7 @@ from .. import _lib
 from .. import definitions as defs
 from .. import packing
 from .. import postprocess
+from .. import tail as tailmod
 from ..engine import BoxTable, Engine, reverse_edges  # noqa: F401  (reverse_edges re-exported)
 
 nt_nt_screen_distance = 12        # NA:69
@@ -99,17 +101,22 @@ def myTimer(state, data={}):
 _box_cache = {}
 
 
-def _box_table(focused, hbonds):
+def _tables(focused, hbonds):
+    """(BoxTable, per-box hydrogen-bond atom sets, tail.LabelTable) of a focused cutoff table, cached."""
     key = (id(focused), id(hbonds))
     ent = _box_cache.get(key)
     if ent is None or ent[0] is not focused or ent[1] is not hbonds:
         bt = BoxTable(focused)
         atoms = postprocess.box_atom_sets(bt, bt.box_combo, hbonds)
-        ent = (focused, hbonds, bt, atoms)
+        ent = (focused, hbonds, bt, atoms, tailmod.LabelTable(bt, atoms))
         if len(_box_cache) > 16:
             _box_cache.clear()
         _box_cache[key] = ent
-    return ent[2], ent[3]
+    return ent[2], ent[3], ent[4]
+
+
+def _box_table(focused, hbonds):
+    return _tables(focused, hbonds)[:2]
 
 
 _default_focus = {}
@@ -167,20 +174,40 @@ def _host_tail(batch, hits, cuts, bt, box_atoms, categories, workers):
 
 
 def annotate_batch(batch, categories, focused_basepair_cutoffs=None, ideal_hydrogen_bonds=None, device=None,
-                   pinned=None, return_raw=False, tail_workers=None):
+                   pinned=None, return_raw=False, tail_workers=None, tail="device", as_arrays=False):
     """Annotate every structure of an NtBatch (or of a list of coordinate specs) in one pass:
-    one H2D copy, K1 (if frames are not given), K2/K3, K4, one D2H copy of the hit records, then
-    the host tail per structure (tail_workers: processes for it; None = $FR3D_TAIL_WORKERS or 1, 0 = one per
-    host core).  Returns a list of (interaction_to_list_of_tuples, category_to_interactions) per structure; with
-    return_raw also the sorted hit array and extras."""
+    one H2D copy, K1 (if frames are not given), K2/K3, K4, the order-dependent tail, one D2H copy.
+
+    tail="device" (default): same-edge cleanup, emission, crossing numbers and covalent links run on the GPU
+    (fr3d_annotation_tail); the result is a tail.BatchAnnotations - a sequence whose item s is the reference's
+    (interaction_to_list_of_tuples, category_to_interactions) of structure s, built from the row arrays on first
+    access.  as_arrays=True returns the same object; it says the caller will read .rows_of(s) / .rows (label id,
+    nt1, nt2, crossing; .labels.name(id)) and never needs the tuples.
+    tail="host": the round-1 path - hit records back, postprocess.build_results per structure in Python
+    (tail_workers: processes for it; None = $FR3D_TAIL_WORKERS or 1, 0 = one per host core); returns a list.
+    With return_raw also the extras dict (sorted hit array, candidate pairs, frames)."""
     if not isinstance(batch, packing.NtBatch):
         batch = packing.pack_specs(batch)
     if not focused_basepair_cutoffs:
         focused_basepair_cutoffs = _default_focused(categories.get('basepair', []))
     if not ideal_hydrogen_bonds:
         ideal_hydrogen_bonds = load_ideal_basepair_hydrogen_bonds()
-    bt, box_atoms = _box_table(focused_basepair_cutoffs, ideal_hydrogen_bonds)
+    bt, box_atoms, labels = _tables(focused_basepair_cutoffs, ideal_hydrogen_bonds)
     eng = Engine.get(device)
+    if tail == "device":
+        hits, n_pairs, extras = eng.annotate_batch(batch, bt, category_mask(categories), pinned=pinned,
+                                                   return_frames=return_raw, labels=labels, want_hits=return_raw)
+        results = tailmod.BatchAnnotations(batch, extras["rows"], extras["row_start"], extras["row_count"], labels,
+                                           n_pairs=n_pairs)
+        if return_raw:
+            extras["n_pairs"] = n_pairs
+            extras["hits"] = postprocess.sort_hits(hits)
+            return results, extras
+        return results
+    if tail != "host":
+        raise ValueError("tail must be 'device' or 'host'")
+    if as_arrays:
+        raise ValueError("as_arrays needs tail='device'")
     hits, n_pairs, extras = eng.annotate_batch(batch, bt, category_mask(categories), pinned=pinned,
                                                return_frames=return_raw)
     hits = postprocess.sort_hits(hits)

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #include "../../include/fr3d_b200.h"
 #include "tables.cuh"
@@ -22,6 +23,7 @@
 #include "geometry.cuh"
 #include "unit_annotation.cuh"
 #include "radius_search.cuh"
+#include "tail.cuh"
 
 #ifndef FR3D_BPH_MINB
 #define FR3D_BPH_MINB 6      // base-phosphate list kernel, min blocks per SM 3 / 4 / 6 / 8: classify 0.840 / 0.835 / 0.807 / 0.815 ms
@@ -33,7 +35,47 @@
 namespace {
 
 thread_local char g_err[512] = "";
-bool g_tables_loaded = false;
+
+// Per-device state: the __constant__ tables and the shared-memory opt-ins live per device, so "initialised" and
+// "tables uploaded" are tracked per device too (one thread per GPU in one process is a supported way to drive this
+// library).  Written under g_mu; read without it after the owning thread's fr3d_init returned.
+constexpr int MAX_DEVICES = 64;
+struct DeviceState {
+    bool initialised = false;
+    bool tables_loaded = false;
+    int sm_count = 148;
+};
+DeviceState g_dev[MAX_DEVICES];
+std::mutex g_mu;
+
+DeviceState *current_device_state() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= MAX_DEVICES) return nullptr;
+    return &g_dev[d];
+}
+
+// Tuning knobs (environment), read once per process:
+// FR3D_CLASSIFY_MODE 2 = screen + work-list kernels (default when a workspace is given), 1 = thread-per-pair kernel
+// over all pairs, 0 = warp-per-pair kernel over all pairs; FR3D_SCREEN=64 / FR3D_STACK=64: the fp64 screen / stacking
+// kernels (A/B runs); FR3D_CLASSIFY_GRID_MULT: blocks per SM.
+struct Knobs {
+    int mult = 0, mode = 2, screen64 = 0, stack64 = 0;
+};
+Knobs g_knobs;
+std::once_flag g_knobs_once;
+const Knobs &knobs() {
+    std::call_once(g_knobs_once, [] {
+        const char *s64 = getenv("FR3D_SCREEN");
+        g_knobs.screen64 = s64 && atoi(s64) == 64;
+        const char *t64 = getenv("FR3D_STACK");
+        g_knobs.stack64 = g_knobs.screen64 || (t64 && atoi(t64) == 64);   // the fp32 stacking kernel reads the screen records
+        const char *e = getenv("FR3D_CLASSIFY_GRID_MULT");
+        g_knobs.mult = (e && atoi(e) > 0) ? atoi(e) : 0;
+        const char *m = getenv("FR3D_CLASSIFY_MODE");
+        g_knobs.mode = m ? atoi(m) : 2;
+    });
+    return g_knobs;
+}
 
 int fail(int code, const char *what, cudaError_t e = cudaSuccess) {
     if (e != cudaSuccess) snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
@@ -74,7 +116,8 @@ fr3d::SearchWs carve(void *workspace, int32_t n_nt) {
     return ws;
 }
 
-int g_sm_count = 148;
+// rank = first nt * 16 + stencil (+ 16 * index_offset) is int32: nt indices must stay below 2^27
+constexpr long long MAX_NT_INDEX = 1ll << 27;
 
 }  // namespace
 
@@ -84,12 +127,11 @@ int fr3d_version(void) { return FR3D_ABI_VERSION; }
 
 const char *fr3d_last_error(void) { return g_err; }
 
-int fr3d_init(int device) {
-    CUDA_TRY(cudaSetDevice(device));
+static int init_current_device(int device) {
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
-    g_sm_count = prop.multiProcessorCount;
     if (prop.major < 10) return fail(FR3D_E_CUDA, "libfr3d_b200 is built for sm_100a only");
+    g_dev[device].sm_count = prop.multiProcessorCount;
     // opt in to the large dynamic shared-memory carve-outs once per device (not on every call)
     CUDA_TRY(cudaFuncSetAttribute(fr3d::classify_screen_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)fr3d::SCR_SMEM));
@@ -103,25 +145,62 @@ int fr3d_init(int device) {
     CUDA_TRY(cudaFuncSetAttribute(fr3d::classify_list2_kernel<true, fr3d::L2_WARPS_PAIR>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)fr3d::l2_smem_bytes<true, fr3d::L2_WARPS_PAIR>()));
+    CUDA_TRY(cudaFuncSetAttribute(fr3d::discrepancy_all_vs_all_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)fr3d::disc_smem_bytes(fr3d::DISC_MAXN)));
+    CUDA_TRY(cudaFuncSetAttribute(fr3d::tail_structure_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)fr3d::TAIL_SMEM));
+    g_dev[device].initialised = true;
     return FR3D_OK;
+}
+
+int fr3d_init(int device) {
+    if (device < 0 || device >= MAX_DEVICES) return fail(FR3D_E_ARG, "device out of range");
+    std::lock_guard<std::mutex> lock(g_mu);
+    int previous = -1;
+    CUDA_TRY(cudaGetDevice(&previous));          // the caller's current device is left as it was
+    CUDA_TRY(cudaSetDevice(device));
+    const int rc = init_current_device(device);
+    if (previous >= 0 && previous != device) cudaSetDevice(previous);
+    knobs();
+    return rc;
 }
 
 int fr3d_upload_tables(const fr3d_static_tables_t *host_tables) {
     if (!host_tables) return fail(FR3D_E_ARG, "host_tables is NULL");
+    DeviceState *ds = current_device_state();
+    if (!ds || !ds->initialised) return fail(FR3D_E_ARG, "fr3d_init has not been called for the current device");
+    std::lock_guard<std::mutex> lock(g_mu);
     CUDA_TRY(cudaMemcpyToSymbol(fr3d::c_tab, host_tables, sizeof(fr3d_static_tables_t)));
-    g_tables_loaded = true;
+    ds->tables_loaded = true;
+    return FR3D_OK;
+}
+
+// every compute entry point: the current device must have been initialised (and, where rule tables are read, loaded)
+static int require_device(bool tables, int *sm_count) {
+    DeviceState *ds = current_device_state();
+    if (!ds || !ds->initialised) return fail(FR3D_E_ARG, "fr3d_init has not been called for the current device");
+    if (tables && !ds->tables_loaded) return fail(FR3D_E_NOTABLES, "fr3d_upload_tables not called on the current device");
+    if (sm_count) *sm_count = ds->sm_count;
+    return FR3D_OK;
+}
+
+int fr3d_frames_fit_from(const fr3d_nts_t *nts, const double *compact_base_xyz, int32_t compact_slots, int32_t *status,
+                         int place_h, void *stream) {
+    if (!nts) return fail(FR3D_E_ARG, "nts is NULL");
+    if (compact_base_xyz && (compact_slots < 11 || compact_slots > FR3D_BASE_SLOTS))
+        return fail(FR3D_E_ARG, "compact_slots must be in [11, 16] (every heavy base atom lies in slots 0..10)");
+    if (int rc = require_device(true, nullptr)) return rc;
+    if (nts->n_nt <= 0) return FR3D_OK;
+    const int block = fr3d::FRAMES_WARPS * 32;
+    const int grid = (nts->n_nt + block - 1) / block;
+    fr3d::frames_fit_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(*nts, status, place_h, compact_base_xyz,
+                                                                                   compact_slots * 3);
+    CUDA_TRY(cudaGetLastError());
     return FR3D_OK;
 }
 
 int fr3d_frames_fit(const fr3d_nts_t *nts, int32_t *status, int place_h, void *stream) {
-    if (!nts) return fail(FR3D_E_ARG, "nts is NULL");
-    if (!g_tables_loaded) return fail(FR3D_E_NOTABLES, "fr3d_upload_tables not called");
-    if (nts->n_nt <= 0) return FR3D_OK;
-    const int block = fr3d::FRAMES_WARPS * 32;
-    const int grid = (nts->n_nt + block - 1) / block;
-    fr3d::frames_fit_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(*nts, status, place_h);
-    CUDA_TRY(cudaGetLastError());
-    return FR3D_OK;
+    return fr3d_frames_fit_from(nts, nullptr, FR3D_BASE_SLOTS, status, place_h, stream);
 }
 
 size_t fr3d_pair_search_workspace(int32_t n_nt) {
@@ -141,6 +220,9 @@ int fr3d_pair_search(const fr3d_nts_t *nts, double cell_size, void *workspace, s
     if (!nts || !workspace || !pair_i || !pair_j || !pair_rank || !counters) return fail(FR3D_E_ARG, "NULL argument");
     if (!(cell_size > 0)) return fail(FR3D_E_ARG, "cell_size must be positive");
     if (workspace_bytes < fr3d_pair_search_workspace(nts->n_nt)) return fail(FR3D_E_ARG, "workspace too small");
+    if ((long long)nts->n_nt >= MAX_NT_INDEX) return fail(FR3D_E_ARG, "more than 2^27 nts in one call (the visit-order rank is int32)");
+    int sm_count = 148;
+    if (int rc = require_device(false, &sm_count)) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CUDA_TRY(cudaMemsetAsync(counters, 0, 8 * sizeof(int64_t), st));
     if (nts->n_nt <= 0) return FR3D_OK;
@@ -154,7 +236,7 @@ int fr3d_pair_search(const fr3d_nts_t *nts, double cell_size, void *workspace, s
     // one warp per occupied cube; the cube count lives on the device, so size the grid for the worst case
     // (a cube per nt) capped at a few resident waves - the kernel strides over the cube list
     const long long want = ((long long)nts->n_nt + fr3d::SEARCH_WARPS - 1) / fr3d::SEARCH_WARPS;
-    const long long cap_blocks = (long long)g_sm_count * 32;
+    const long long cap_blocks = (long long)sm_count * 32;
     fr3d::pair_search_kernel<<<(int)(want < cap_blocks ? want : cap_blocks), fr3d::SEARCH_WARPS * 32, 0, st>>>(
         *nts, ws, cell_size, pair_i, pair_j, pair_rank, pair_cap, counters);
     CUDA_TRY(cudaGetLastError());
@@ -174,27 +256,19 @@ int fr3d_classify_pairs(const fr3d_nts_t *nts, const fr3d_box_t *boxes, const in
                         fr3d_hit_t *hits, int64_t hit_cap, int64_t *counters, void *stream) {
     if (!nts || !boxes || !box_index || !pair_i || !pair_j || !pair_rank || !hits || !counters)
         return fail(FR3D_E_ARG, "NULL argument");
-    if (!g_tables_loaded) return fail(FR3D_E_NOTABLES, "fr3d_upload_tables not called");
+    int sm_count = 148;
+    if (int rc = require_device(true, &sm_count)) return rc;
     if (pair_cap <= 0) return FR3D_OK;
     if (workspace && (reinterpret_cast<size_t>(workspace) & 15)) return fail(FR3D_E_ARG, "workspace must be 16-byte aligned");
+    if (index_offset < 0 || (long long)nts->n_nt + index_offset >= MAX_NT_INDEX)
+        return fail(FR3D_E_ARG, "nt index (with index_offset) reaches 2^27 (the visit-order rank is int32)");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    // Tuning knobs (environment): FR3D_CLASSIFY_MODE 2 = screen + two work-list kernels (default when a
-    // workspace is given), 1 = thread-per-pair kernel over all pairs, 0 = warp-per-pair kernel over all pairs.
-    static int mult = -1, mode = -1, screen64 = 0, stack64 = 0;
-    if (mult < 0) {
-        const char *s64 = getenv("FR3D_SCREEN");
-        screen64 = s64 && atoi(s64) == 64;
-        const char *t64 = getenv("FR3D_STACK");
-        stack64 = screen64 || (t64 && atoi(t64) == 64);          // the fp32 stacking kernel reads the screen records
-        const char *e = getenv("FR3D_CLASSIFY_GRID_MULT");
-        mult = (e && atoi(e) > 0) ? atoi(e) : 0;
-        const char *m = getenv("FR3D_CLASSIFY_MODE");
-        mode = m ? atoi(m) : 2;
-    }
+    const Knobs &kn = knobs();
+    const int mult = kn.mult, mode = kn.mode, screen64 = kn.screen64, stack64 = kn.stack64;
     int use_mode = mode;
     if (use_mode == 2 && (!workspace || workspace_bytes < fr3d_classify_workspace(pair_cap, nts->n_nt))) use_mode = 0;
-    const long long tpp_grid_max = (long long)g_sm_count * (mult ? mult : 4 * FR3D_TPP_MIN_BLOCKS);
-    const long long pm_grid_max = (long long)g_sm_count * (mult ? mult : FR3D_CLASSIFY_MIN_BLOCKS);
+    const long long tpp_grid_max = (long long)sm_count * (mult ? mult : 4 * FR3D_TPP_MIN_BLOCKS);
+    const long long pm_grid_max = (long long)sm_count * (mult ? mult : FR3D_CLASSIFY_MIN_BLOCKS);
     const long long per_block = (long long)fr3d::WARPS_PER_BLOCK * fr3d::PM_K;
     auto clampg = [](long long want, long long mx) { long long g = want < mx ? want : mx; return (int)(g < 1 ? 1 : g); };
     if (use_mode == 2) {
@@ -211,7 +285,7 @@ int fr3d_classify_pairs(const fr3d_nts_t *nts, const fr3d_box_t *boxes, const in
         if (screen64) {          // the double-precision screen, kept for A/B runs
             const int scr_threads = fr3d::SCR_WARPS * 32;
             fr3d::classify_screen_kernel<<<clampg((pair_cap + scr_threads - 1) / scr_threads,
-                                                  (long long)g_sm_count * (mult ? mult : 1)),
+                                                  (long long)sm_count * (mult ? mult : 1)),
                                            scr_threads, fr3d::SCR_SMEM, st>>>(
                 *nts, boxes, box_index, pair_i, pair_j, pair_cap, category_mask, wl_light, wl_stack, wl_pair, wl_bph, counters);
         } else {
@@ -222,7 +296,7 @@ int fr3d_classify_pairs(const fr3d_nts_t *nts, const fr3d_box_t *boxes, const in
                 *nts, srec, counters);
             const int scr_threads = fr3d::S32_WARPS * 32;
             fr3d::classify_screen32_kernel<<<clampg((pair_cap + scr_threads - 1) / scr_threads,
-                                                    (long long)g_sm_count * (mult ? mult : 1)),
+                                                    (long long)sm_count * (mult ? mult : 1)),
                                              scr_threads, fr3d::S32_SMEM, st>>>(
                 srec, boxes, box_index, pair_i, pair_j, pair_cap, category_mask, wl_light, wl_stack, wl_pair, wl_bph,
                 wl_bph_combos, counters);
@@ -240,8 +314,8 @@ int fr3d_classify_pairs(const fr3d_nts_t *nts, const fr3d_box_t *boxes, const in
                 hit_cap, counters, wl_bph, 7, 0, screen64 ? nullptr : wl_bph_combos);
         // stacking and pairing lists: records staged in shared memory in two phases (classify_list2.cuh)
         constexpr int ts = fr3d::L2_WARPS_STACK * 32, tp = fr3d::L2_WARPS_PAIR * 32;
-        const int grid_s = clampg((pair_cap + ts - 1) / ts, (long long)g_sm_count * (mult ? mult : 1));
-        const int grid_p = clampg((pair_cap + tp - 1) / tp, (long long)g_sm_count * (mult ? mult : 1));
+        const int grid_s = clampg((pair_cap + ts - 1) / ts, (long long)sm_count * (mult ? mult : 1));
+        const int grid_p = clampg((pair_cap + tp - 1) / tp, (long long)sm_count * (mult ? mult : 1));
         if ((category_mask & FR3D_CAT_STACKING) && stack64) {
             fr3d::classify_list2_kernel<false, fr3d::L2_WARPS_STACK>
                 <<<grid_s, ts, fr3d::l2_smem_bytes<false, fr3d::L2_WARPS_STACK>(), st>>>(
@@ -256,12 +330,12 @@ int fr3d_classify_pairs(const fr3d_nts_t *nts, const fr3d_box_t *boxes, const in
             CUDA_TRY(cudaMemsetAsync(unc_count, 0, sizeof(unsigned long long), st));
             const float *srec = reinterpret_cast<const float *>(wsp + 6 * list_bytes);
             constexpr int t32 = fr3d::ST32_WARPS * 32;
-            fr3d::classify_stack32_kernel<<<clampg((pair_cap + t32 - 1) / t32, (long long)g_sm_count * (mult ? mult : 1)),
+            fr3d::classify_stack32_kernel<<<clampg((pair_cap + t32 - 1) / t32, (long long)sm_count * (mult ? mult : 1)),
                                             t32, fr3d::ST32_SMEM, st>>>(
                 srec, pair_i, pair_j, pair_rank, pair_cap, index_offset, hits, hit_cap, counters, wl_stack, 5, wl_unc,
                 unc_count);
             // few pairs: the warp-per-pair kernel has by far the shortest latency per pair
-            fr3d::classify_pairs_pm_kernel<<<g_sm_count * FR3D_CLASSIFY_MIN_BLOCKS, fr3d::WARPS_PER_BLOCK * 32, 0, st>>>(
+            fr3d::classify_pairs_pm_kernel<<<sm_count * FR3D_CLASSIFY_MIN_BLOCKS, fr3d::WARPS_PER_BLOCK * 32, 0, st>>>(
                 *nts, boxes, box_index, pair_i, pair_j, pair_rank, pair_cap, FR3D_CAT_STACKING | PM_CAT_NO_PAIRING,
                 index_offset, hits, hit_cap, counters, wl_unc, reinterpret_cast<const int64_t *>(unc_count));
         }
@@ -283,6 +357,87 @@ int fr3d_classify_pairs(const fr3d_nts_t *nts, const fr3d_box_t *boxes, const in
     return FR3D_OK;
 }
 
+namespace {
+struct TailCarve {
+    fr3d::TailWs ws;
+    size_t bytes;
+};
+TailCarve carve_tail(void *workspace, int64_t hit_cap, int32_t n_nt, int32_t n_struct, int64_t n_ends) {
+    TailCarve c;
+    char *p = static_cast<char *>(workspace);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { char *q = p ? p + off : nullptr; off += align_up(bytes ? bytes : 1, 256); return q; };
+    const size_t H = (size_t)(hit_cap > 0 ? hit_cap : 0), n = (size_t)(n_nt > 0 ? n_nt : 0), S = (size_t)(n_struct > 0 ? n_struct : 0);
+    fr3d::TailWs &w = c.ws;
+    w.seg_cnt = reinterpret_cast<int32_t *>(take(4 * S));
+    w.seg_off = reinterpret_cast<int32_t *>(take(4 * (S + 1)));
+    w.seg_cur = reinterpret_cast<int32_t *>(take(4 * S));
+    w.hkey = reinterpret_cast<unsigned long long *>(take(8 * H));
+    w.hval = reinterpret_cast<uint32_t *>(take(4 * H));
+    w.ekey = reinterpret_cast<unsigned long long *>(take(16 * H));
+    w.eval = reinterpret_cast<uint32_t *>(take(8 * H));
+    w.e_u = reinterpret_cast<int32_t *>(take(8 * H));
+    w.e_v = reinterpret_cast<int32_t *>(take(8 * H));
+    w.e_lab = reinterpret_cast<int32_t *>(take(8 * H));
+    w.e_flag = reinterpret_cast<uint8_t *>(take(2 * H));
+    w.akey = reinterpret_cast<unsigned long long *>(take(16 * H));
+    w.aval = reinterpret_cast<uint32_t *>(take(8 * H));
+    w.alab = reinterpret_cast<int32_t *>(take(8 * H));
+    w.aa = reinterpret_cast<int32_t *>(take(8 * H));
+    w.ab = reinterpret_cast<int32_t *>(take(8 * H));
+    w.aseq = reinterpret_cast<uint32_t *>(take(8 * H));
+    w.across = reinterpret_cast<int32_t *>(take(8 * H));
+    w.first = reinterpret_cast<uint32_t *>(take(4 * n));
+    w.gstart = reinterpret_cast<int32_t *>(take(4 * n));
+    w.gcount = reinterpret_cast<int32_t *>(take(4 * n));
+    w.ckey = reinterpret_cast<unsigned long long *>(take(8 * n));
+    w.cval = reinterpret_cast<uint32_t *>(take(4 * n));
+    w.ends = reinterpret_cast<int32_t *>(take(4 * (size_t)(n_ends > 0 ? n_ends : 0)));
+    c.bytes = off;
+    return c;
+}
+}  // namespace
+
+size_t fr3d_tail_workspace(int64_t hit_cap, int32_t n_nt, int32_t n_struct, int64_t n_ends) {
+    return carve_tail(nullptr, hit_cap, n_nt, n_struct, n_ends).bytes;
+}
+
+int fr3d_annotation_tail(const fr3d_nts_t *nts, const fr3d_tail_ident_t *ident, const fr3d_tail_tables_t *tables,
+                         const fr3d_hit_t *hits, int64_t hit_cap, const int64_t *counters, int32_t index_offset,
+                         void *workspace, size_t workspace_bytes, fr3d_row_t *rows, int64_t row_cap,
+                         int32_t *row_start, int32_t *row_count, int64_t *tail_counters, void *stream) {
+    if (!nts || !ident || !tables || !hits || !counters || !workspace || !rows || !row_start || !row_count || !tail_counters)
+        return fail(FR3D_E_ARG, "NULL argument");
+    if (!ident->struct_off || !ident->struct_chain_off || !ident->chain_ends_off || !ident->nt_chain || !ident->nt_cov ||
+        !tables->labels || !tables->boxes || !tables->slot_label)
+        return fail(FR3D_E_ARG, "NULL table pointer");
+    if (tables->n_labels <= 0 || tables->n_labels > fr3d::TAIL_MAX_LABELS) return fail(FR3D_E_ARG, "n_labels must be in [1, 1024]");
+    if (hit_cap < 0 || row_cap < 0 || ident->n_struct < 0) return fail(FR3D_E_ARG, "negative size");
+    if (2 * hit_cap >= (1ll << 31)) return fail(FR3D_E_ARG, "hit_cap must stay below 2^30 per call (split the batch)");
+    int sm_count = 148;
+    if (int rc = require_device(false, &sm_count)) return rc;
+    if (ident->n_ends < 0 || ident->n_chains < 0) return fail(FR3D_E_ARG, "negative size");
+    if (workspace_bytes < fr3d_tail_workspace(hit_cap, nts->n_nt, ident->n_struct, ident->n_ends))
+        return fail(FR3D_E_ARG, "workspace too small");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    fr3d::TailWs ws = carve_tail(workspace, hit_cap, nts->n_nt, ident->n_struct, ident->n_ends).ws;
+    const int S = ident->n_struct;
+    fr3d::tail_reset_kernel<<<(S + 256) / 256, 256, 0, st>>>(ws, S, tail_counters);
+    if (S > 0) {
+        const long long want = (hit_cap + 255) / 256;
+        const long long cap_blocks = (long long)sm_count * 8;
+        const int grid = (int)(want < 1 ? 1 : (want < cap_blocks ? want : cap_blocks));
+        fr3d::tail_count_kernel<<<grid, 256, 0, st>>>(hits, hit_cap, counters, index_offset, *ident, ws);
+        fr3d::tail_scan_kernel<<<1, 1024, 0, st>>>(ws, S);
+        fr3d::tail_scatter_kernel<<<grid, 256, 0, st>>>(hits, hit_cap, counters, index_offset, *ident, ws, tail_counters);
+        const int blocks = S < sm_count * 7 ? S : sm_count * 7;
+        fr3d::tail_structure_kernel<<<blocks, fr3d::TAIL_THREADS, fr3d::TAIL_SMEM, st>>>(
+            *nts, *ident, *tables, hits, index_offset, ws, rows, row_cap, row_start, row_count, tail_counters);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return FR3D_OK;
+}
+
 size_t fr3d_radius_search_workspace(int32_t n_points) { return fr3d_pair_search_workspace(n_points); }
 
 int fr3d_radius_search(const double *xyz, const int32_t *model, int32_t n_points, double max_cutoff, void *workspace,
@@ -292,6 +447,9 @@ int fr3d_radius_search(const double *xyz, const int32_t *model, int32_t n_points
         return fail(FR3D_E_ARG, "NULL argument");
     if (!(max_cutoff > 0)) return fail(FR3D_E_ARG, "max_cutoff must be positive");
     if (workspace_bytes < fr3d_radius_search_workspace(n_points)) return fail(FR3D_E_ARG, "workspace too small");
+    if ((long long)n_points >= MAX_NT_INDEX) return fail(FR3D_E_ARG, "more than 2^27 points in one call (the list-order rank is int32)");
+    int sm_count = 148;
+    if (int rc = require_device(false, &sm_count)) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     CUDA_TRY(cudaMemsetAsync(counters, 0, 8 * sizeof(int64_t), st));
     if (n_points <= 0) return FR3D_OK;
@@ -305,7 +463,7 @@ int fr3d_radius_search(const double *xyz, const int32_t *model, int32_t n_points
     // one warp per (occupied cell, stencil entry); the cell count lives on the device: size for the worst case,
     // capped at a few resident waves (the kernel strides over the tasks)
     const long long want = ((long long)n_points * 14 + fr3d::RS_WARPS - 1) / fr3d::RS_WARPS;
-    const long long cap_blocks = (long long)g_sm_count * 32;
+    const long long cap_blocks = (long long)sm_count * 32;
     fr3d::rs_pairs_kernel<<<(int)(want < cap_blocks ? want : cap_blocks), fr3d::RS_WARPS * 32, 0, st>>>(
         xyz, model, ws, max_cutoff * max_cutoff, pair_a, pair_b, pair_rank, dist2, pair_cap, counters);
     CUDA_TRY(cudaGetLastError());
@@ -315,6 +473,7 @@ int fr3d_radius_search(const double *xyz, const int32_t *model, int32_t n_points
 int fr3d_bond_orientation(const fr3d_nts_t *nts, const int32_t *host_ring_slot, double *chi_degree, int32_t *orientation,
                           void *stream) {
     if (!nts || !host_ring_slot || !chi_degree || !orientation) return fail(FR3D_E_ARG, "NULL argument");
+    if (int rc = require_device(false, nullptr)) return rc;
     if (nts->n_nt <= 0) return FR3D_OK;
     fr3d::RingSlots ring;
     for (int p = 0; p < FR3D_N_PARENTS; ++p) {
@@ -331,7 +490,8 @@ int fr3d_bond_orientation(const fr3d_nts_t *nts, const int32_t *host_ring_slot, 
 int fr3d_kabsch_batched(const double *set1, const double *set2, const double *w, const int32_t *off, int32_t n_prob,
                         double *U, double *mean1, double *mean2, double *rmsd, double *sse, double *new1,
                         void *stream) {
-    if (!set1 || !set2 || !off) return fail(FR3D_E_ARG, "NULL argument");
+    if (!set1 || !set2 || !off) return fail(FR3D_E_ARG, "NULL argument");      // every output may be NULL
+    if (int rc = require_device(false, nullptr)) return rc;
     if (n_prob <= 0) return FR3D_OK;
     const int block = 128;
     fr3d::kabsch_batched_kernel<<<(n_prob + block - 1) / block, block, 0, static_cast<cudaStream_t>(stream)>>>(
@@ -346,11 +506,9 @@ int fr3d_discrepancy_all_vs_all(const double *centers, const double *rots, const
     if (!centers || !rots || !out) return fail(FR3D_E_ARG, "NULL argument");
     if (n < 2 || n > fr3d::DISC_MAXN) return fail(FR3D_E_ARG, "n must be in [2, 16]");
     if (row0 < 0 || row1 > N || row0 > row1) return fail(FR3D_E_ARG, "bad row range");
+    if (int rc = require_device(false, nullptr)) return rc;
     if (row0 == row1 || N == 0) return FR3D_OK;
-    const size_t smem = (size_t)fr3d::DISC_TILE * (size_t)n * 12 * 2 * sizeof(double) + 2 * fr3d::DISC_TILE * fr3d::DISC_MAXN +
-                        (size_t)fr3d::DISC_TILE * (fr3d::DISC_TILE + 1) * sizeof(double);
-    CUDA_TRY(cudaFuncSetAttribute(fr3d::discrepancy_all_vs_all_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem));
+    const size_t smem = fr3d::disc_smem_bytes(n);        // opted in for n = DISC_MAXN by fr3d_init
     dim3 block(32, 8);
     dim3 grid((N + fr3d::DISC_TILE - 1) / fr3d::DISC_TILE, (row1 - row0 + fr3d::DISC_TILE - 1) / fr3d::DISC_TILE);
     fr3d::discrepancy_all_vs_all_kernel<<<grid, block, smem, static_cast<cudaStream_t>(stream)>>>(
@@ -365,6 +523,7 @@ int fr3d_discrepancy_one_vs_many(const double *q_centers, const double *q_rots, 
                                  double *out, void *stream) {
     if (!q_centers || !q_rots || !centers || !rots || !out) return fail(FR3D_E_ARG, "NULL argument");
     if (n < 2 || n > fr3d::DISC_MAXN) return fail(FR3D_E_ARG, "n must be in [2, 16]");
+    if (int rc = require_device(false, nullptr)) return rc;
     if (M <= 0) return FR3D_OK;
     const int block = 128;
     fr3d::discrepancy_one_vs_many_kernel<<<(M + block - 1) / block, block, 0, static_cast<cudaStream_t>(stream)>>>(

@@ -154,8 +154,12 @@ __device__ __forceinline__ bool frames_fit_one(const fr3d_nts_t &nts, int32_t *_
     return wrote_low;
 }
 
+// src / src_cols: where the observed atoms are read from - nts.base_xyz itself (src == nullptr), or a compact plane
+// [n][src_cols / 3][3] holding only the first slots of every record (the upload keeps slots 0..10 when no hydrogen
+// is observed: they are placed here anyway); the full 16-slot record is then written to nts.base_xyz.
 __global__ void __launch_bounds__(FRAMES_WARPS * 32) frames_fit_kernel(fr3d_nts_t nts, int32_t *__restrict__ status,
-                                                                       int place_h) {
+                                                                       int place_h, const double *__restrict__ src_plane,
+                                                                       int src_cols) {
     __shared__ double s_std[FR3D_N_PARENTS][FR3D_BASE_SLOTS][3];
     __shared__ double s_rows[FRAMES_WARPS][32 * FRAMES_STRIDE];
     for (int item = threadIdx.x; item < FR3D_N_PARENTS * FR3D_BASE_SLOTS * 3; item += blockDim.x)
@@ -165,13 +169,16 @@ __global__ void __launch_bounds__(FRAMES_WARPS * 32) frames_fit_kernel(fr3d_nts_
     const int n = n0 + lane;
     double *rows = s_rows[warp];
     const int rows_here = min(32, max(0, nts.n_nt - n0));
-    {   // stage the warp's records row by row (48 doubles each: lanes 0..31, then lanes 0..15 for the rest)
-        const double *src = nts.base_xyz + (size_t)n0 * FR3D_BASE_SLOTS * 3 + lane;
+    const bool compact = src_plane != nullptr;
+    const int cols = compact ? src_cols : FR3D_BASE_SLOTS * 3;
+    {   // stage the warp's records row by row (cols doubles each: lanes 0..31, then the first lanes for the rest)
+        const double *src = (compact ? src_plane : nts.base_xyz) + (size_t)n0 * cols + lane;
         double *dst = rows + lane;
 #pragma unroll 4
         for (int r = 0; r < rows_here; ++r) {
-            cp_async8(dst + r * FRAMES_STRIDE, src + r * (FR3D_BASE_SLOTS * 3));
-            if (lane < FR3D_BASE_SLOTS * 3 - 32) cp_async8(dst + r * FRAMES_STRIDE + 32, src + r * (FR3D_BASE_SLOTS * 3) + 32);
+            if (lane < cols) cp_async8(dst + r * FRAMES_STRIDE, src + (size_t)r * cols);
+            if (lane < cols - 32) cp_async8(dst + r * FRAMES_STRIDE + 32, src + (size_t)r * cols + 32);
+            if (compact && lane >= cols - 32 && lane < FR3D_BASE_SLOTS * 3 - 32) dst[r * FRAMES_STRIDE + 32] = 0.0;
         }
         cp_async_wait_all();
     }
@@ -180,9 +187,9 @@ __global__ void __launch_bounds__(FRAMES_WARPS * 32) frames_fit_kernel(fr3d_nts_
     if (n < nts.n_nt) wrote_low = frames_fit_one(nts, status, place_h, n, rows + lane * FRAMES_STRIDE, s_std);
     __syncwarp();
     // copy back slots 8..15 (every hydrogen slot lies there: the parents have 8 to 11 heavy atoms), or whole rows
-    // if some lane inserted ideal-position copies
+    // if some lane inserted ideal-position copies or the records came from a compact plane
     double *dstg = nts.base_xyz + (size_t)n0 * FR3D_BASE_SLOTS * 3;
-    if (__any_sync(0xFFFFFFFFu, wrote_low)) {
+    if (compact || __any_sync(0xFFFFFFFFu, wrote_low)) {
         for (int r = 0; r < rows_here; ++r) {
             dstg[r * (FR3D_BASE_SLOTS * 3) + lane] = rows[r * FRAMES_STRIDE + lane];
             if (lane < FR3D_BASE_SLOTS * 3 - 32) dstg[r * (FR3D_BASE_SLOTS * 3) + 32 + lane] = rows[r * FRAMES_STRIDE + 32 + lane];

@@ -173,6 +173,12 @@ __device__ __forceinline__ double discrepancy_pair2(const double *c1, const doub
 static constexpr int DISC_TILE = 32;
 static constexpr int DISC_MAXN = 16;      // positions per instance supported by the tiled kernel
 
+// dynamic shared memory of discrepancy_all_vs_all_kernel for n positions (the opt-in in fr3d_init uses n = DISC_MAXN)
+constexpr size_t disc_smem_bytes(int n) {
+    return (size_t)DISC_TILE * (size_t)n * 12 * 2 * sizeof(double) + 2 * DISC_TILE * DISC_MAXN +
+           (size_t)DISC_TILE * (DISC_TILE + 1) * sizeof(double);
+}
+
 // grid: (ceil(N/32), ceil(rows/32)); block 32x8 threads, each thread 4 rows of the tile.
 __global__ void __launch_bounds__(256)
 discrepancy_all_vs_all_kernel(const double *__restrict__ centers, const double *__restrict__ rots,

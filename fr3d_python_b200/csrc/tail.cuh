@@ -1,0 +1,603 @@
+// A8 on the device: the order-dependent tail of annotate_nt_nt_interactions for every structure of a batch.
+//
+// Replaces (fr3d/classifiers/NA_pairwise_interactions.py)
+//   the visit-order recording of per-pair results                 NA:758-1013
+//   check_for_two_interactions_on_same_edge                       NA:528-632
+//   the emission of the surviving basepairs                       NA:1026-1044
+//   calculate_crossing_numbers                                    NA:1057-1179
+//   annotate_covalent_connections                                 NA:1181-1210
+//
+// Hit records arrive unordered (K4 appends them with atomics).  Three small kernels bin them by structure
+// (count -> scan -> scatter, with the sort key (rank, nt1, nt2, slot) that reproduces the reference's cube walk);
+// then ONE thread block per structure does everything else on integer ids:
+//   sort the structure's hits                       -> the order in which the reference records results
+//   walk them: non-basepair hits append (label, a, b) rows; basepair hits add one entry to each partner's list
+//   sort the entries by (first appearance of the nt, sequence) = the iteration order of unit_id_to_basepairs
+//   same-edge cleanup (sequential by construction, but only over nts with two or more basepairs), emission
+//   nested-cWW selection per chain id (greedy over pairs sorted by span; one warp per chain), crossing numbers
+//   rank the labels by first appearance, sort the rows by (label rank, sequence), expand the reversed duplicates
+//   covalent links: sort the nts by (model symmetry chain, index), link successive keys
+// and writes the final rows (label id, nt1, nt2, crossing) in the reference's append order.
+// Sorting is a bitonic network in shared memory (<= TAIL_SORT_CAP elements) or in the global workspace (large
+// structures); all keys are unique, so the result is deterministic.
+#pragma once
+
+#include "tables.cuh"
+
+namespace fr3d {
+
+constexpr int TAIL_THREADS = 256;
+constexpr int TAIL_SORT_CAP = 2048;      // elements sorted in shared memory (24 KB)
+constexpr int TAIL_MAX_LABELS = 1024;
+constexpr int TAIL_MAX_NT_BITS = 17;     // structures of up to 131 072 nts
+constexpr int TAIL_INDEX_BITS = 23;
+constexpr uint32_t TAIL_NONE = 0xFFFFFFFFu;
+constexpr int TAIL_F_REMOVED = 1, TAIL_F_NEAR = 2;
+constexpr size_t TAIL_SMEM = (size_t)TAIL_SORT_CAP * (sizeof(unsigned long long) + sizeof(uint32_t));
+
+struct TailWs {
+    int32_t *seg_cnt;             // [S]     hits per structure
+    int32_t *seg_off;             // [S + 1]
+    int32_t *seg_cur;             // [S]
+    unsigned long long *hkey;     // [H]     hits of a structure: sort key; later the nested-cWW candidates
+    uint32_t *hval;               // [H]     hit index
+    unsigned long long *ekey;     // [2H]    basepair entries: (first appearance of u, sequence)
+    uint32_t *eval;               // [2H]    hit index * 2 + (1: the entry recorded for u2)
+    int32_t *e_u, *e_v, *e_lab;   // [2H]    entries in iteration order
+    uint8_t *e_flag;              // [2H]
+    unsigned long long *akey;     // [2H]    appended rows: (label rank, sequence)
+    uint32_t *aval;               // [2H]
+    int32_t *alab, *aa, *ab;      // [2H]
+    uint32_t *aseq;               // [2H]
+    int32_t *across;              // [2H]
+    uint32_t *first;              // [n]     first appearance of the nt in unit_id_to_basepairs
+    int32_t *gstart, *gcount;     // [n]     its entries
+    unsigned long long *ckey;     // [n]     covalent sort
+    uint32_t *cval;               // [n]
+    int32_t *ends;                // [n_ends] nested_cWW_endpoints of every chain
+};
+
+typedef unsigned long long tail_u64;
+
+__device__ __forceinline__ int tail_find_struct(const int32_t *__restrict__ off, int n_struct, int nt) {
+    int lo = 0, hi = n_struct;                    // largest s with off[s] <= nt
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (off[mid] <= nt) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void tail_reset_kernel(TailWs ws, int n_struct, int64_t *tc) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n_struct) { ws.seg_cnt[t] = 0; ws.seg_cur[t] = 0; }
+    if (t == 0) { tc[0] = 0; tc[1] = 0; tc[2] = 0; tc[3] = 0; }
+}
+
+__global__ void tail_count_kernel(const fr3d_hit_t *__restrict__ hits, int64_t hit_cap, const int64_t *counters,
+                                  int32_t index_offset, fr3d_tail_ident_t id, TailWs ws) {
+    const long long n_hits = min((long long)counters[1], (long long)hit_cap);
+    for (long long h = (long long)blockIdx.x * blockDim.x + threadIdx.x; h < n_hits; h += (long long)gridDim.x * blockDim.x) {
+        const int s = tail_find_struct(id.struct_off, id.n_struct, hits[h].i - index_offset);
+        atomicAdd(&ws.seg_cnt[s], 1);
+    }
+}
+
+// exclusive scan of the per-structure hit counts (one block; the structure count is small next to the hit count)
+__global__ void __launch_bounds__(1024) tail_scan_kernel(TailWs ws, int n_struct) {
+    __shared__ int s_w[32];
+    __shared__ int s_run;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_run = 0;
+    __syncthreads();
+    for (int base = 0; base < n_struct; base += 1024) {
+        const int t = base + threadIdx.x;
+        const int c = t < n_struct ? ws.seg_cnt[t] : 0;
+        int incl = c;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int v = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+            if (lane >= off) incl += v;
+        }
+        if (lane == 31) s_w[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const int w = s_w[lane];
+            int iw = w;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const int v = __shfl_up_sync(0xFFFFFFFFu, iw, off);
+                if (lane >= off) iw += v;
+            }
+            s_w[lane] = iw - w;
+        }
+        __syncthreads();
+        const int run = s_run;
+        if (t < n_struct) ws.seg_off[t] = run + s_w[warp] + incl - c;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_run = run + s_w[warp] + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) ws.seg_off[n_struct] = s_run;
+}
+
+__global__ void tail_scatter_kernel(const fr3d_hit_t *__restrict__ hits, int64_t hit_cap, const int64_t *counters,
+                                    int32_t index_offset, fr3d_tail_ident_t id, TailWs ws, int64_t *tc) {
+    const long long n_hits = min((long long)counters[1], (long long)hit_cap);
+    for (long long h = (long long)blockIdx.x * blockDim.x + threadIdx.x; h < n_hits; h += (long long)gridDim.x * blockDim.x) {
+        const fr3d_hit_t hit = hits[h];
+        const int i = hit.i - index_offset, j = hit.j - index_offset;
+        const int s = tail_find_struct(id.struct_off, id.n_struct, i);
+        const int lo = id.struct_off[s];
+        const int n = id.struct_off[s + 1] - lo;
+        if (n > (1 << TAIL_MAX_NT_BITS)) { atomicOr((tail_u64 *)&tc[2], 1ull); continue; }
+        // (rank, nt1, nt2, slot): rank = first nt of nt1's cube * 16 + stencil entry (search.cuh), all local to the structure
+        const tail_u64 rank = (tail_u64)(uint32_t)(hit.rank - 16 * index_offset - 16 * lo);
+        const tail_u64 key = (rank << (2 * TAIL_MAX_NT_BITS + 4)) | ((tail_u64)(uint32_t)(i - lo) << (TAIL_MAX_NT_BITS + 4)) |
+                             ((tail_u64)(uint32_t)(j - lo) << 4) | (tail_u64)hit.slot;
+        const int pos = ws.seg_off[s] + atomicAdd(&ws.seg_cur[s], 1);
+        ws.hkey[pos] = key;
+        ws.hval[pos] = (uint32_t)h;
+    }
+}
+
+// ---- block-wide primitives -----------------------------------------------------------------------------------------
+// exclusive scan of one value per thread; every thread gets the block total too
+__device__ __forceinline__ int tail_block_scan(int v, int *s_w, int &total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int u = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+        if (lane >= off) incl += u;
+    }
+    __syncthreads();                         // s_w may still be read from the previous call
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    int before = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < TAIL_THREADS / 32; ++w) {
+        const int x = s_w[w];
+        if (w < warp) before += x;
+        tot += x;
+    }
+    total = tot;
+    return before + incl - v;
+}
+
+__device__ __forceinline__ void tail_cmpswap(tail_u64 *K, uint32_t *V, int lo, int hi) {
+    const tail_u64 a = K[lo], b = K[hi];
+    if (a > b) {
+        K[lo] = b; K[hi] = a;
+        const uint32_t x = V[lo]; V[lo] = V[hi]; V[hi] = x;
+    }
+}
+
+// Ascending sort of n (key, value) pairs by one block: a bitonic network in which every comparator puts the larger
+// key at the higher index, so positions >= n behave as +infinity that never moves and their comparators are skipped
+// (n need not be a power of two).  In shared memory when it fits, else in place in global memory.
+__device__ void tail_block_sort(tail_u64 *keys, uint32_t *vals, int n, tail_u64 *s_key, uint32_t *s_val) {
+    __syncthreads();
+    if (n <= 1) return;
+    int P = 2;
+    while (P < n) P <<= 1;
+    tail_u64 *K = keys;
+    uint32_t *V = vals;
+    const bool staged = P <= TAIL_SORT_CAP;
+    if (staged) {
+        for (int i = threadIdx.x; i < n; i += TAIL_THREADS) { s_key[i] = keys[i]; s_val[i] = vals[i]; }
+        K = s_key; V = s_val;
+        __syncthreads();
+    }
+    const int half_p = P >> 1;
+    for (int k = 2; k <= P; k <<= 1) {
+        const int hk = k >> 1;
+        for (int i = threadIdx.x; i < half_p; i += TAIL_THREADS) {          // flip: i <-> mirror inside blocks of k
+            const int blk = i / hk, off = i - blk * hk;
+            const int lo = blk * k + off, hi = blk * k + k - 1 - off;
+            if (hi < n) tail_cmpswap(K, V, lo, hi);
+        }
+        __syncthreads();
+        for (int j = hk >> 1; j >= 1; j >>= 1) {
+            for (int i = threadIdx.x; i < half_p; i += TAIL_THREADS) {
+                const int lo = 2 * j * (i / j) + (i % j), hi = lo + j;
+                if (hi < n) tail_cmpswap(K, V, lo, hi);
+            }
+            __syncthreads();
+        }
+    }
+    if (staged) {
+        for (int i = threadIdx.x; i < n; i += TAIL_THREADS) { keys[i] = s_key[i]; vals[i] = s_val[i]; }
+        __syncthreads();
+    }
+}
+
+struct TailEntrySrc {      // what one basepair hit says about the entry recorded for u1 (d = 0) or u2 (d = 1)
+    int u, v, lab;
+};
+
+__device__ __forceinline__ TailEntrySrc tail_entry_of(const fr3d_hit_t &h, int d, int base, const fr3d_tail_tables_t &tb) {
+    const int a = h.i - base, b = h.j - base;
+    const int near = h.code & 1;
+    const int u1 = (h.code & 2) ? b : a, u2 = (h.code & 2) ? a : b;      // orientation 21 was used: nt2 is u1 (NA:981)
+    TailEntrySrc e;
+    e.u = d ? u2 : u1;
+    e.v = d ? u1 : u2;
+    e.lab = tb.boxes[h.box].label[d][near];
+    return e;
+}
+
+// One block per structure (dynamic assignment through tc[1]).
+__global__ void __launch_bounds__(TAIL_THREADS)
+tail_structure_kernel(fr3d_nts_t nts, fr3d_tail_ident_t id, fr3d_tail_tables_t tb, const fr3d_hit_t *__restrict__ hits,
+                      int32_t index_offset, TailWs ws, fr3d_row_t *__restrict__ rows, int64_t row_cap,
+                      int32_t *__restrict__ row_start, int32_t *__restrict__ row_count, int64_t *tc) {
+    extern __shared__ __align__(16) unsigned char tail_smem[];
+    tail_u64 *s_key = reinterpret_cast<tail_u64 *>(tail_smem);
+    uint32_t *s_val = reinterpret_cast<uint32_t *>(s_key + TAIL_SORT_CAP);
+    __shared__ uint32_t s_lfirst[TAIL_MAX_LABELS];
+    __shared__ uint16_t s_lrank[TAIL_MAX_LABELS];
+    __shared__ int s_w[TAIL_THREADS / 32];
+    __shared__ int s_struct, s_nent, s_napp, s_nnest, s_nmulti, s_err;
+    __shared__ long long s_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int T = TAIL_THREADS;
+    const int n_labels = tb.n_labels;
+
+    while (true) {
+        __syncthreads();
+        if (tid == 0) {
+            s_struct = (int)atomicAdd((tail_u64 *)&tc[1], 1ull);
+            s_nent = 0; s_napp = 0; s_nnest = 0; s_nmulti = 0; s_err = 0;
+        }
+        __syncthreads();
+        const int s = s_struct;
+        if (s >= id.n_struct) break;
+        const int lo = id.struct_off[s], n = id.struct_off[s + 1] - lo;
+        const int hb = ws.seg_off[s], H = ws.seg_off[s + 1] - hb;
+        const int base = index_offset + lo;                                  // hit.i - base = position in the structure
+        if (n > (1 << TAIL_MAX_NT_BITS)) {                                   // flagged by the scatter kernel
+            if (tid == 0) { row_start[s] = -1; row_count[s] = 0; }
+            continue;
+        }
+        tail_u64 *hkey = ws.hkey + hb;
+        uint32_t *hval = ws.hval + hb;
+        const size_t eb = 2 * (size_t)hb;
+        tail_u64 *ekey = ws.ekey + eb, *akey = ws.akey + eb;
+        uint32_t *eval = ws.eval + eb, *aval = ws.aval + eb, *aseq = ws.aseq + eb;
+        int32_t *e_u = ws.e_u + eb, *e_v = ws.e_v + eb, *e_lab = ws.e_lab + eb;
+        uint8_t *e_flag = ws.e_flag + eb;
+        int32_t *alab = ws.alab + eb, *aa = ws.aa + eb, *ab = ws.ab + eb, *across = ws.across + eb;
+        uint32_t *first = ws.first + lo;
+        int32_t *gstart = ws.gstart + lo, *gcount = ws.gcount + lo;
+        const int32_t *meta = nts.meta + (size_t)lo * FR3D_META_INTS;
+        const int32_t *nt_chain = id.nt_chain + lo;
+
+        // ---- init, and the ranges the keys below rely on
+        const int c_lo = id.struct_chain_off[s], c_hi = id.struct_chain_off[s + 1];
+        if (c_hi - c_lo > 65536 || n_labels > TAIL_MAX_LABELS) s_err = 1;
+        for (int u = tid; u < n; u += T) {
+            first[u] = TAIL_NONE; gcount[u] = 0;
+            const int ix = meta[(size_t)u * FR3D_META_INTS + 4], cov = id.nt_cov[lo + u], ch = nt_chain[u];
+            if (ix < 0 || ix >= (1 << TAIL_INDEX_BITS) || cov < 0 || cov >= (1 << 23) || ch < c_lo || ch >= c_hi) s_err = 1;
+            else if (ix >= id.chain_ends_off[ch + 1] - id.chain_ends_off[ch]) s_err = 1;
+        }
+        for (int l = tid; l < min(n_labels, TAIL_MAX_LABELS); l += T) s_lfirst[l] = TAIL_NONE;
+        __syncthreads();
+        if (s_err) {
+            if (tid == 0) { row_start[s] = -1; row_count[s] = 0; atomicOr((tail_u64 *)&tc[2], 2ull); }
+            continue;
+        }
+        for (int c = c_lo; c < c_hi; ++c) {                                  // nested_cWW_endpoints: identity (NA:1106)
+            const int eo = id.chain_ends_off[c], len = id.chain_ends_off[c + 1] - eo;
+            for (int i = tid; i < len; i += T) ws.ends[eo + i] = i;
+        }
+
+        // ---- the reference's visit order
+        tail_block_sort(hkey, hval, H, s_key, s_val);
+
+        // ---- walk: sequence number 2p + k for the k-th thing hit p records
+        for (int p = tid; p < H; p += T) {
+            const uint32_t hidx = hval[p];
+            const fr3d_hit_t h = hits[hidx];
+            if (h.slot == FR3D_SLOT_BP) {
+                const TailEntrySrc e0 = tail_entry_of(h, 0, base, tb);
+                const int e = atomicAdd(&s_nent, 2);
+                ekey[e] = ((tail_u64)(uint32_t)e0.u << 32) | (uint32_t)(2 * p);           // u for now; first[u] below
+                ekey[e + 1] = ((tail_u64)(uint32_t)e0.v << 32) | (uint32_t)(2 * p + 1);
+                eval[e] = hidx * 2u;
+                eval[e + 1] = hidx * 2u + 1u;
+                atomicMin(&first[e0.u], (uint32_t)(2 * p));
+                atomicMin(&first[e0.v], (uint32_t)(2 * p + 1));
+                atomicAdd(&gcount[e0.u], 1);
+                atomicAdd(&gcount[e0.v], 1);
+            } else if (h.slot < FR3D_SLOT_BP) {
+                const int a = h.i - base, b = h.j - base;
+                const int32_t *sl = tb.slot_label + ((int)h.slot * 32 + (h.code & 31)) * 2;
+                const int l0 = sl[0], l1 = sl[1];
+                const bool swap = h.slot == FR3D_SLOT_SO21 || h.slot == FR3D_SLOT_SR21;  // recorded for (nt2, nt1)
+                if (l0 < 0 || l0 >= n_labels || l1 >= n_labels) { s_err = 1; continue; }
+                const int cnt = l1 >= 0 ? 2 : 1;
+                const int k = atomicAdd(&s_napp, cnt);
+                alab[k] = l0; aa[k] = swap ? b : a; ab[k] = swap ? a : b; aseq[k] = (uint32_t)(2 * p);
+                atomicMin(&s_lfirst[l0], (uint32_t)(2 * p));
+                if (l1 >= 0) {                                                            // NA:765 / NA:775
+                    alab[k + 1] = l1; aa[k + 1] = swap ? a : b; ab[k + 1] = swap ? b : a; aseq[k + 1] = (uint32_t)(2 * p + 1);
+                    atomicMin(&s_lfirst[l1], (uint32_t)(2 * p + 1));
+                }
+            }
+        }
+        __syncthreads();
+        const int nent = s_nent;
+
+        // ---- unit_id_to_basepairs in iteration order: nts by first appearance, entries by sequence (NA:1001-1013)
+        for (int e = tid; e < nent; e += T) {
+            const tail_u64 k = ekey[e];
+            ekey[e] = ((tail_u64)first[(int)(k >> 32)] << 32) | (k & 0xFFFFFFFFull);
+        }
+        tail_block_sort(ekey, eval, nent, s_key, s_val);
+        for (int q = tid; q < nent; q += T) {
+            const uint32_t ev = eval[q];
+            const TailEntrySrc e = tail_entry_of(hits[ev >> 1], (int)(ev & 1u), base, tb);
+            e_u[q] = e.u; e_v[q] = e.v; e_lab[q] = e.lab; e_flag[q] = 0;
+            if (e.lab < 0 || e.lab >= n_labels) s_err = 1;
+        }
+        __syncthreads();
+        // group starts, and the list of nts with two or more basepairs (in iteration order) in the low half of akey
+        int32_t *multi = reinterpret_cast<int32_t *>(akey);
+        {
+            int running = 0;
+            for (int q0 = 0; q0 < nent; q0 += T) {
+                const int q = q0 + tid;
+                int flag = 0;
+                if (q < nent) {
+                    const int u = e_u[q];
+                    if (q == 0 || e_u[q - 1] != u) {
+                        gstart[u] = q;
+                        flag = gcount[u] >= 2;
+                    }
+                }
+                int total;
+                const int ex = tail_block_scan(flag, s_w, total);
+                if (flag) multi[running + ex] = q;
+                running += total;
+            }
+            if (tid == 0) s_nmulti = running;
+        }
+        __syncthreads();
+
+        // ---- check_for_two_interactions_on_same_edge (NA:528-632): order dependent, one thread, conflicts are rare
+        if (tid == 0 && !s_err) {
+            const int nmulti = s_nmulti;
+            for (int m = 0; m < nmulti; ++m) {
+                const int g0 = multi[m];
+                const int u = e_u[g0];
+                const int len = gcount[u];
+                for (int i = g0; i < g0 + len - 1; ++i) {
+                    if (e_flag[i] & TAIL_F_REMOVED) continue;                              // NA:545
+                    const int lab1 = e_lab[i], v1 = e_v[i];
+                    const uint32_t f1 = tb.labels[lab1].flags;
+                    const fr3d_hit_t *h1 = hits + (eval[i] >> 1);
+                    const tail_u64 at1 = (eval[i] & 1u) ? tb.boxes[h1->box].atoms2 : tb.boxes[h1->box].atoms1;
+                    const double cd1 = h1->cutoff_distance, gap1 = h1->max_gap;
+                    for (int j = i + 1; j < g0 + len; ++j) {
+                        if (e_flag[j] & (TAIL_F_REMOVED | TAIL_F_NEAR)) continue;          // NA:551-557
+                        const int lab2 = e_lab[j], v2 = e_v[j];
+                        const uint32_t f2 = tb.labels[lab2].flags;
+                        if (((f1 >> 8) & 0xFF) != ((f2 >> 8) & 0xFF)) continue;            // different edges
+                        const fr3d_hit_t *h2 = hits + (eval[j] >> 1);
+                        const tail_u64 at2 = (eval[j] & 1u) ? tb.boxes[h2->box].atoms2 : tb.boxes[h2->box].atoms1;
+                        const tail_u64 common = at1 & at2;
+                        if (!common) continue;
+                        if (!((common & tb.hydrogen_atoms) || __popcll(common) > 1)) continue;
+                        const double cd2 = h2->cutoff_distance, gap2 = h2->max_gap;
+                        const bool n1 = f1 & 2u, n2 = f2 & 2u;
+                        int flag = 0, target = -1;                                          // partner whose pair is marked
+                        if (n1 && n2) {
+                            if (cd1 < cd2) { if (cd2 > 0.5) { flag = TAIL_F_REMOVED; target = v2; } }
+                            else if (cd1 > 0.5) { flag = TAIL_F_REMOVED; target = v1; }
+                        } else if (!n1 && !n2) {
+                            flag = TAIL_F_NEAR;
+                            target = gap1 < gap2 ? v2 : v1;
+                        } else {
+                            if (cd2 > 0.5) { flag = TAIL_F_REMOVED; target = v2; }
+                            else if (cd1 > 0.5) { flag = TAIL_F_REMOVED; target = v1; }
+                        }
+                        if (flag) {         // the sets hold (u, target) and (target, u): every entry with either key
+                            for (int q = g0; q < g0 + len; ++q)
+                                if (e_v[q] == target) e_flag[q] |= (uint8_t)flag;
+                            const int t0 = gstart[target], tl = gcount[target];
+                            for (int q = t0; q < t0 + tl; ++q)
+                                if (e_v[q] == u) e_flag[q] |= (uint8_t)flag;
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- emission (NA:1026-1044): the first entry of an unordered pair in iteration order, unless removed
+        for (int q = tid; q < nent; q += T) {
+            const int fl = e_flag[q];
+            if (fl & TAIL_F_REMOVED) continue;
+            const int u = e_u[q], v = e_v[q];
+            bool is_first = true;
+            for (int q2 = gstart[u]; q2 < q; ++q2)
+                if (e_v[q2] == v) is_first = false;
+            const int t0 = gstart[v], t1 = t0 + gcount[v];
+            for (int q2 = t0; q2 < t1 && q2 < q; ++q2)
+                if (e_v[q2] == u) is_first = false;
+            if (!is_first) continue;
+            int lab = e_lab[q];
+            if (lab < 0 || lab >= n_labels) continue;
+            if (fl & TAIL_F_NEAR) {
+                lab = tb.labels[lab].near;
+                if (lab < 0 || lab >= n_labels) { s_err = 1; continue; }
+            }
+            const int k = atomicAdd(&s_napp, 1);
+            alab[k] = lab; aa[k] = u; ab[k] = v; aseq[k] = (uint32_t)(2 * H + q);
+            atomicMin(&s_lfirst[lab], (uint32_t)(2 * H + q));
+        }
+        __syncthreads();
+        const int napp = s_napp;
+
+        // ---- nested cWW pairs (NA:1077-1131): candidates keyed (chain, span, start), greedy in that order per chain
+        tail_u64 *nkey = hkey;           // the hit keys are no longer needed
+        uint32_t *nval = hval;
+        for (int k = tid; k < napp; k += T) {
+            if (!(tb.labels[alab[k]].flags & 4u)) continue;
+            const int a = aa[k], b = ab[k];
+            if (nt_chain[a] != nt_chain[b]) continue;
+            const int pa = meta[(size_t)a * FR3D_META_INTS], pb = meta[(size_t)b * FR3D_META_INTS];
+            // AU UA CG GC GU UG (NA:1089); parents A C G U = 0 1 2 3
+            const bool ok = (pa == 0 && pb == 3) || (pa == 3 && pb == 0) || (pa == 1 && pb == 2) || (pa == 2 && pb == 1) ||
+                            (pa == 2 && pb == 3) || (pa == 3 && pb == 2);
+            if (!ok) continue;
+            const int ia = meta[(size_t)a * FR3D_META_INTS + 4], ib = meta[(size_t)b * FR3D_META_INTS + 4];
+            const int i1 = min(ia, ib), i2 = max(ia, ib);
+            const int x = atomicAdd(&s_nnest, 1);
+            nkey[x] = ((tail_u64)(uint32_t)(nt_chain[a] - c_lo) << 48) | ((tail_u64)(uint32_t)(i2 - i1) << 24) | (tail_u64)(uint32_t)i1;
+            nval[x] = 0;
+        }
+        __syncthreads();
+        const int nnest = s_nnest;
+        tail_block_sort(nkey, nval, nnest, s_key, s_val);
+        // one warp per chain: its candidates are contiguous in the sorted list
+        if (nnest > 0) {
+            for (int c = warp; c < c_hi - c_lo; c += T / 32) {
+                int b0 = 0, b1 = nnest;                              // first candidate with chain >= c
+                while (b0 < b1) {
+                    const int mid = (b0 + b1) >> 1;
+                    if ((int)(nkey[mid] >> 48) < c) b0 = mid + 1; else b1 = mid;
+                }
+                int32_t *ends = ws.ends + id.chain_ends_off[c_lo + c];
+                for (int x = b0; x < nnest && (int)(nkey[x] >> 48) == c; ++x) {
+                    const tail_u64 k = nkey[x];
+                    const int i1 = (int)(k & 0xFFFFFFull), i2 = i1 + (int)((k >> 24) & 0xFFFFFFull);
+                    bool nested = i2 > i1;                           // span 0: never nested (NA:1112-1116)
+                    for (int i0 = i1 + 1; i0 < i2 && nested; i0 += 32) {
+                        const int i = i0 + lane;
+                        bool bad = false;
+                        if (i < i2) { const int e = ends[i]; bad = !(e > i1 && e < i2); }
+                        if (__any_sync(0xFFFFFFFFu, bad)) nested = false;
+                    }
+                    if (nested && lane == 0) { ends[i1] = i2; ends[i2] = i1; }
+                    __syncwarp();
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- crossing numbers (NA:1146-1169) and row counts
+        int my_rows = 0;
+        for (int k = tid; k < napp; k += T) {
+            const int a = aa[k], b = ab[k];
+            int crossing = 0;
+            const int ca = nt_chain[a];
+            if (ca == nt_chain[b]) {
+                const int ia = meta[(size_t)a * FR3D_META_INTS + 4], ib = meta[(size_t)b * FR3D_META_INTS + 4];
+                const int i1 = min(ia, ib), i2 = max(ia, ib);
+                const int32_t *ends = ws.ends + id.chain_ends_off[ca];
+                for (int i = i1 + 1; i < i2; ++i) {
+                    const int e = ends[i];
+                    crossing += (e < i1 || e > i2);
+                }
+            }
+            across[k] = crossing;
+            my_rows += 1 + (int)(tb.labels[alab[k]].flags & 1u);
+        }
+        // ---- label ranks by first appearance, then the rows in append order
+        for (int l = tid; l < n_labels; l += T) {
+            const uint32_t f = s_lfirst[l];
+            int r = 0;
+            if (f != TAIL_NONE)
+                for (int m = 0; m < n_labels; ++m) r += s_lfirst[m] < f;
+            s_lrank[l] = (uint16_t)r;
+        }
+        __syncthreads();
+        for (int k = tid; k < napp; k += T) {
+            akey[k] = ((tail_u64)s_lrank[alab[k]] << 32) | aseq[k];
+            aval[k] = (uint32_t)k;
+        }
+        tail_block_sort(akey, aval, napp, s_key, s_val);
+
+        // ---- covalent links (NA:1181-1210): nts by (model symmetry chain, index), successive keys of one string
+        tail_u64 *ckey = ws.ckey + lo;
+        uint32_t *cval = ws.cval + lo;
+        for (int u = tid; u < n; u += T) {
+            const int ix = meta[(size_t)u * FR3D_META_INTS + 4];
+            ckey[u] = ((tail_u64)(uint32_t)id.nt_cov[lo + u] << (TAIL_INDEX_BITS + TAIL_MAX_NT_BITS)) |
+                      ((tail_u64)(uint32_t)ix << TAIL_MAX_NT_BITS) | (tail_u64)u;
+            cval[u] = (uint32_t)u;
+        }
+        tail_block_sort(ckey, cval, n, s_key, s_val);
+        for (int r = tid; r < n; r += T) {                   // rows of sorted position r = members of the next key
+            const tail_u64 kr = ckey[r] >> TAIL_MAX_NT_BITS;
+            int e = r + 1;
+            while (e < n && (ckey[e] >> TAIL_MAX_NT_BITS) == kr) ++e;
+            int cnt = 0;
+            if (e < n && (ckey[e] >> (TAIL_INDEX_BITS + TAIL_MAX_NT_BITS)) == (kr >> TAIL_INDEX_BITS)) {
+                const tail_u64 ke = ckey[e] >> TAIL_MAX_NT_BITS;
+                int f = e + 1;
+                while (f < n && (ckey[f] >> TAIL_MAX_NT_BITS) == ke) ++f;
+                cnt = f - e;
+            }
+            gcount[r] = cnt;                                 // the per-nt arrays are free again
+            gstart[r] = e;
+            my_rows += cnt;
+        }
+        int total_rows;
+        tail_block_scan(my_rows, s_w, total_rows);
+        __syncthreads();
+        if (tid == 0) {
+            if (s_err) { atomicOr((tail_u64 *)&tc[2], 2ull); total_rows = 0; }
+            const long long b = (long long)atomicAdd((tail_u64 *)&tc[0], (tail_u64)total_rows);
+            s_base = b;
+            const bool fits = b + total_rows <= (long long)row_cap;
+            row_start[s] = fits ? (int32_t)b : -1;
+            row_count[s] = s_err ? 0 : total_rows;
+            if (!fits) s_err = 1;                            // nothing is written; the host re-runs with the count
+        }
+        __syncthreads();
+        if (s_err) continue;
+        fr3d_row_t *out = rows + s_base;
+        int running = 0;
+        for (int r0 = 0; r0 < napp; r0 += T) {
+            const int r = r0 + tid;
+            int k = 0, lab = 0, cnt = 0;
+            if (r < napp) { k = (int)aval[r]; lab = alab[k]; cnt = 1 + (int)(tb.labels[lab].flags & 1u); }
+            int total;
+            const int ex = tail_block_scan(cnt, s_w, total);
+            if (r < napp) {
+                fr3d_row_t row;
+                row.label = lab; row.nt1 = aa[k] + base; row.nt2 = ab[k] + base; row.crossing = across[k];
+                out[running + ex] = row;
+                if (cnt == 2) {                                                          // NA:1171-1177
+                    row.label = tb.labels[lab].rev; row.nt1 = ab[k] + base; row.nt2 = aa[k] + base;
+                    out[running + ex + 1] = row;
+                }
+            }
+            running += total;
+        }
+        for (int r0 = 0; r0 < n; r0 += T) {
+            const int r = r0 + tid;
+            const int cnt = r < n ? gcount[r] : 0;
+            int total;
+            const int ex = tail_block_scan(cnt, s_w, total);
+            if (cnt) {
+                const int u1 = (int)cval[r], e = gstart[r];
+                const int i1 = meta[(size_t)u1 * FR3D_META_INTS + 4];
+                for (int x = 0; x < cnt; ++x) {
+                    const int u2 = (int)cval[e + x];
+                    fr3d_row_t row;
+                    row.label = FR3D_LABEL_COVALENT | (meta[(size_t)u2 * FR3D_META_INTS + 4] - i1);
+                    row.nt1 = u1 + base; row.nt2 = u2 + base; row.crossing = -1;
+                    out[running + ex + x] = row;
+                }
+            }
+            running += total;
+        }
+    }
+}
+
+}  // namespace fr3d

@@ -105,12 +105,14 @@ class DeviceBatch(object):
 
     def __init__(self, torch, device, batch, pinned=None):
         self.n = batch.n
+        self.compact_base = None
         t = {}
         for name in ("center", "rot", "base_xyz", "bb_xyz", "base_mask", "bb_mask", "meta"):
             src = pinned[name] if pinned is not None else torch.from_numpy(_as_signed(getattr(batch, name)))
-            if name == "base_xyz" and src.shape[1] < _lib.BASE_SLOTS:       # compact pinned form, see pin_batch
-                t[name] = torch.zeros((batch.n, _lib.BASE_SLOTS, 3), dtype=src.dtype, device=device)
-                t[name][:, :src.shape[1]].copy_(src.to(device, non_blocking=True))
+            if name == "base_xyz" and src.shape[1] < _lib.BASE_SLOTS:       # compact pinned form, see pin_batch:
+                # K1 reads the compact plane and writes the full 16-slot records (fr3d_frames_fit_from)
+                self.compact_base = (src.to(device, non_blocking=True), int(src.shape[1]))
+                t[name] = torch.empty((batch.n, _lib.BASE_SLOTS, 3), dtype=src.dtype, device=device)
             else:
                 t[name] = src.to(device, non_blocking=True)
         self.t = t
@@ -177,19 +179,28 @@ class Engine(object):
         return C.c_void_p(self.torch.cuda.current_stream(self.device).cuda_stream)
 
     # ---------------------------------------------------------------- K1
+    def _frames_fit(self, dbatch, status_ptr, place_h, st):
+        compact = getattr(dbatch, "compact_base", None)
+        if compact is not None:
+            _lib.check(self.lib.fr3d_frames_fit_from(C.byref(dbatch.nts), compact[0].data_ptr(), compact[1], status_ptr,
+                                                     1 if place_h else 0, st), "fr3d_frames_fit_from")
+        else:
+            _lib.check(self.lib.fr3d_frames_fit(C.byref(dbatch.nts), status_ptr, 1 if place_h else 0, st),
+                       "fr3d_frames_fit")
+        self.launches += 1
+
     def fit_frames(self, dbatch, place_h=True):
         torch = self.torch
         status = torch.empty(dbatch.n, dtype=torch.int32, device=self.device)
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.fr3d_frames_fit(C.byref(dbatch.nts), status.data_ptr(), 1 if place_h else 0,
-                                                self.stream_ptr()), "fr3d_frames_fit")
-        self.launches += 1
+            self._frames_fit(dbatch, status.data_ptr(), place_h, self.stream_ptr())
         return status
 
     # ---------------------------------------------------------------- plans
-    def make_plan(self, n_nt, pair_cap=None, hit_cap=None):
+    def make_plan(self, n_nt, pair_cap=None, hit_cap=None, tail=None, row_cap=None):
         """Pre-allocate every device buffer one pass over an n_nt batch needs, so that the pass
-        itself is launches only (no allocation, no host sync)."""
+        itself is launches only (no allocation, no host sync).  tail = (n_struct, n_ends): also the buffers of the
+        device tail (fr3d_annotation_tail)."""
         torch = self.torch
         if pair_cap is None:
             pair_cap = 12 * n_nt + 1024        # ~6.3 candidate pairs per nt on RNA (SURVEY §6)
@@ -207,20 +218,35 @@ class Engine(object):
         p.cws_bytes = int(self.lib.fr3d_classify_workspace(p.pair_cap, n_nt))
         p.cws = torch.empty(p.cws_bytes, dtype=torch.uint8, device=dev)
         p.hits = torch.empty(p.hit_cap * HIT_DTYPE.itemsize, dtype=torch.uint8, device=dev)
-        p.status = torch.empty(max(n_nt, 1), dtype=torch.int32, device=dev)
+        p.status = torch.zeros(max(n_nt, 1), dtype=torch.int32, device=dev)
+        p.tail = None
+        if tail is not None:
+            self.add_tail_buffers(p, tail[0], tail[1], row_cap)
         return p
 
-    def run_plan(self, dbatch, plan, boxtable, category_mask, fit_frames=True, events=None, index_offset=0):
-        """K1 -> K2/K3 -> K4 on the current stream, asynchronously.  `events` (dict) receives
-        torch CUDA events around the classify launch for per-kernel timing."""
+    def add_tail_buffers(self, p, n_struct, n_ends, row_cap=None):
+        torch, dev = self.torch, self.device
+        if row_cap is None:
+            row_cap = 3 * p.hit_cap + 2 * p.n_nt + 1024      # ~2.2 rows per hit + one covalent row per nt
+        p.tail = (int(n_struct), int(n_ends))
+        p.row_cap = int(row_cap)
+        p.tws_bytes = int(self.lib.fr3d_tail_workspace(p.hit_cap, p.n_nt, p.tail[0], p.tail[1]))
+        p.tws = torch.empty(p.tws_bytes, dtype=torch.uint8, device=dev)
+        p.rows = torch.empty(p.row_cap * 16, dtype=torch.uint8, device=dev)
+        p.row_start = torch.empty(max(p.tail[0], 1), dtype=torch.int32, device=dev)
+        p.row_count = torch.empty(max(p.tail[0], 1), dtype=torch.int32, device=dev)
+        p.tcounters = torch.zeros(4, dtype=torch.int64, device=dev)
+
+    def run_plan(self, dbatch, plan, boxtable, category_mask, fit_frames=True, events=None, index_offset=0, tail=None):
+        """K1 -> K2/K3 -> K4 [-> device tail] on the current stream, asynchronously.  `events` (dict) receives
+        torch CUDA events around the classify launch for per-kernel timing.  tail = (DeviceIdent, LabelTable): also
+        run fr3d_annotation_tail into the plan's row buffers."""
         torch = self.torch
         bx, ix = boxtable.device(torch, self.device)
         st = self.stream_ptr()
         with torch.cuda.device(self.device):
             if fit_frames:
-                _lib.check(self.lib.fr3d_frames_fit(C.byref(dbatch.nts), plan.status.data_ptr(), 1, st),
-                           "fr3d_frames_fit")
-                self.launches += 1
+                self._frames_fit(dbatch, plan.status.data_ptr(), True, st)
             if events is not None:
                 events["search0"].record()
             _lib.check(self.lib.fr3d_pair_search(C.byref(dbatch.nts), 12.0, plan.ws.data_ptr(), plan.ws_bytes,
@@ -243,6 +269,24 @@ class Engine(object):
                 (1 if cm & _lib.CAT_BACKBONE else 0) + (2 if cm & _lib.CAT_STACKING else 0)
             if events is not None:
                 events["classify1"].record()
+            if tail is not None:
+                self.run_tail(dbatch, plan, tail, index_offset, st)
+                if events is not None and "tail1" in events:
+                    events["tail1"].record()
+
+    def run_tail(self, dbatch, plan, tail, index_offset=0, st=None):
+        """fr3d_annotation_tail on the hit records of `plan` (5 launches)."""
+        ident, labels = tail
+        tables, _keep = labels.device(self.torch, self.device)
+        if st is None:
+            st = self.stream_ptr()
+        _lib.check(self.lib.fr3d_annotation_tail(C.byref(dbatch.nts), C.byref(ident.struct), C.byref(tables),
+                                                 plan.hits.data_ptr(), plan.hit_cap, plan.counters.data_ptr(),
+                                                 int(index_offset), plan.tws.data_ptr(), plan.tws_bytes,
+                                                 plan.rows.data_ptr(), plan.row_cap, plan.row_start.data_ptr(),
+                                                 plan.row_count.data_ptr(), plan.tcounters.data_ptr(), st),
+                   "fr3d_annotation_tail")
+        self.launches += 5 if ident.n_struct > 0 else 1
 
     def read_counts(self, plan):
         """(n_pairs, n_hits) after a sync; raises on range errors; None if a capacity was exceeded."""
@@ -252,34 +296,105 @@ class Engine(object):
         return int(cnt[0]), int(cnt[1])
 
     # ---------------------------------------------------------------- whole path
-    def annotate_batch(self, batch, boxtable, category_mask, pinned=None, return_frames=False, plan=None):
-        """H2D -> [K1] -> K2/K3 -> K4 -> D2H.  Returns (hits structured array, n_pairs, extras).
-        Capacity overflow (FR3D_E_CAPACITY) re-runs with the exact counts; nothing is truncated."""
+    def annotate_batch(self, batch, boxtable, category_mask, pinned=None, return_frames=False, plan=None,
+                       labels=None, want_hits=True):
+        """H2D -> [K1] -> K2/K3 -> K4 [-> device tail] -> D2H.  Returns (hits structured array, n_pairs, extras).
+        With `labels` (a tail.LabelTable) the device tail runs too and extras["rows"], ["row_start"], ["row_count"]
+        hold the final rows (hits are then only copied back if want_hits).  Capacity overflow (FR3D_E_CAPACITY)
+        re-runs with the exact counts; nothing is truncated."""
         torch = self.torch
         with torch.cuda.device(self.device):
             db = DeviceBatch(torch, self.device, batch, pinned)
+            tail = None
+            if labels is not None:
+                from . import tail as tailmod
+                ident = DeviceIdent(torch, self.device, tailmod.tail_ident(batch))
+                tail = (ident, labels)
             if plan is None or plan.n_nt != batch.n:
                 plan = self.make_plan(batch.n)
+            if tail is not None and plan.tail != (ident.n_struct, ident.n_ends):
+                self.add_tail_buffers(plan, ident.n_struct, ident.n_ends)
             fit = not batch.frames_given
+            status = None
             while True:
-                self.run_plan(db, plan, boxtable, category_mask, fit_frames=fit)
+                self.run_plan(db, plan, boxtable, category_mask, fit_frames=fit, tail=tail)
+                if fit:
+                    status = plan.status        # K1 ran in this pass: its status survives capacity re-runs
                 n_pairs, n_hits = self.read_counts(plan)
                 if n_pairs <= plan.pair_cap and n_hits <= plan.hit_cap:
                     break
                 fit = False          # frames are already in place in the device batch
                 plan = self.make_plan(batch.n, max(n_pairs, plan.pair_cap) + 1024,
-                                      max(n_hits, 2 * max(n_pairs, 1)) + 1024)
-            hits = plan.hits[: n_hits * HIT_DTYPE.itemsize].cpu().numpy().view(HIT_DTYPE)
+                                      max(n_hits, 2 * max(n_pairs, 1)) + 1024,
+                                      tail=(ident.n_struct, ident.n_ends) if tail is not None else None)
             extras = {"plan": plan}
+            if tail is not None:
+                while True:
+                    n_rows = self.read_tail_counts(plan)
+                    if n_rows <= plan.row_cap:
+                        break
+                    self.add_tail_buffers(plan, ident.n_struct, ident.n_ends, row_cap=n_rows + 1024)
+                    self.run_tail(db, plan, tail)
+                from .tail import ROW_DTYPE
+                extras["rows"] = plan.rows[: n_rows * 16].cpu().numpy().view(ROW_DTYPE)
+                extras["row_start"] = plan.row_start[:ident.n_struct].cpu().numpy()
+                extras["row_count"] = plan.row_count[:ident.n_struct].cpu().numpy()
+            if want_hits or tail is None:
+                hits = plan.hits[: n_hits * HIT_DTYPE.itemsize].cpu().numpy().view(HIT_DTYPE)
+            else:
+                hits = None
+            extras["n_hits"] = n_hits
             if return_frames:
                 extras["center"] = db.t["center"].cpu().numpy()
                 extras["rot"] = db.t["rot"].cpu().numpy()
                 extras["base_xyz"] = db.t["base_xyz"].cpu().numpy()
                 extras["base_mask"] = db.t["base_mask"].cpu().numpy().view(np.uint32)
-                extras["status"] = plan.status[:batch.n].cpu().numpy() if not batch.frames_given else None
+                extras["status"] = status[:batch.n].cpu().numpy() if status is not None else None
                 extras["pairs"] = (plan.pair_i[:n_pairs].cpu().numpy(), plan.pair_j[:n_pairs].cpu().numpy(),
                                    plan.pair_rank[:n_pairs].cpu().numpy())
         return hits, n_pairs, extras
+
+    def read_tail_counts(self, plan):
+        """Total rows after a sync; raises when a structure is outside the ranges the device tail supports."""
+        tc = plan.tcounters.cpu()
+        if int(tc[2]) != 0:
+            raise _lib.Fr3dError("fr3d_annotation_tail: a structure is outside the supported ranges (more than 131 072 "
+                                 "nts, an index outside [0, 2^23), or a label without its table entry): FR3D_E_RANGE")
+        return int(tc[0])
+
+
+class DeviceIdent(object):
+    """The fr3d_tail_ident_t arrays of a batch (or of structures s0..s1-1 of it) in HBM."""
+
+    def __init__(self, torch, device, ident, s0=0, s1=None, pinned=False):
+        if s1 is None:
+            s1 = ident.n_struct
+        arrays = ident.chunk(s0, s1)
+        self.n_struct, self.n_chains, self.n_ends = s1 - s0, arrays[5], arrays[6]
+        self.host = arrays[:5]
+        offs, total = [], 0
+        for a in self.host:
+            offs.append(total)
+            total += (a.nbytes + 255) // 256 * 256
+        self.offs = offs
+        blob = np.zeros(max(total, 1), dtype=np.uint8)
+        for o, a in zip(offs, self.host):
+            blob[o:o + a.nbytes] = a.view(np.uint8).reshape(-1)
+        self.host_blob = torch.from_numpy(blob)
+        if pinned:
+            self.host_blob = self.host_blob.pin_memory()
+        self.dev_blob = None
+        if device is not None:
+            self.bind(self.host_blob.to(device, non_blocking=pinned))
+
+    def bind(self, dev_blob):
+        """Point the struct at a device copy of host_blob (the pipeline uploads it with the nt records)."""
+        self.dev_blob = dev_blob
+        base = dev_blob.data_ptr()
+        o = self.offs
+        self.struct = _lib.TailIdentStruct(n_struct=self.n_struct, n_chains=self.n_chains, n_ends=self.n_ends, reserved=0,
+                                           struct_off=base + o[0], struct_chain_off=base + o[1],
+                                           chain_ends_off=base + o[2], nt_chain=base + o[3], nt_cov=base + o[4])
 
 
 class Plan(object):
@@ -295,30 +410,42 @@ class Pipeline(object):
     H2D copy overlaps chunk k's kernels and chunk k-1's D2H copy.  All device / pinned buffers are
     allocated once and re-used across calls.  Frames are always fitted on the device (K1), so the
     centre / rotation planes are not uploaded.  The input is fixed at construction: each chunk's planes are laid out
-    back to back in one pinned blob here, and run() uploads those blobs (build a new Pipeline for new coordinates)."""
+    back to back in one pinned blob here, and run() uploads those blobs (build a new Pipeline for new coordinates).
+
+    With `labels` (a tail.LabelTable) every chunk also runs the device tail and run() returns the final rows;
+    the hit records are then only copied back when want_hits is set."""
 
     def __init__(self, engine, batch, pinned, boxtable, category_mask, n_chunks=4, pair_cap=None, hit_cap=None,
-                 n_streams=3):
+                 n_streams=3, labels=None, want_hits=None, row_cap=None):
         torch = engine.torch
         self.eng, self.batch, self.pinned, self.bt, self.mask = engine, batch, pinned, boxtable, category_mask
+        self.labels = labels
+        self.want_hits = (labels is None) if want_hits is None else bool(want_hits)
         if batch.frames_given:
             raise _lib.Fr3dError("Pipeline uploads observed atoms only; frames are fitted on the device")
+        ident = None
+        if labels is not None:
+            from . import tail as tailmod
+            ident = tailmod.tail_ident(batch)
         S = batch.n_structures
         n_chunks = max(1, min(n_chunks, S))
         bounds = [int(round(k * S / n_chunks)) for k in range(n_chunks + 1)]
         self.chunks = []
         dev = engine.device
         self.streams = [torch.cuda.Stream(device=dev) for _ in range(min(n_streams, n_chunks))]
+        self.h2d_bytes = 0
         for k in range(n_chunks):
             lo, hi = int(batch.struct_off[bounds[k]]), int(batch.struct_off[bounds[k + 1]])
             n = hi - lo
             ch = Plan()
             ch.lo, ch.hi, ch.n = lo, hi, n
+            ch.s0, ch.s1 = bounds[k], bounds[k + 1]
             ch.stream = self.streams[k % len(self.streams)]
-            # One host -> device copy per chunk: the chunk's slices of the uploaded planes sit back to back in ONE
-            # pinned blob (built here, once) and land in ONE device blob whose sub-ranges ARE the device planes
-            # (PCIe moves 40 MB pieces at ~55 GB/s but 2-10 MB pieces at ~36 GB/s, profiles/pcie_probe.json).  The
-            # compact base plane (slots 0..10) is widened to 16 slots on the device.
+            # One host -> device copy per chunk: the chunk's slices of the uploaded planes (and the identity arrays
+            # of the tail) sit back to back in ONE pinned blob (built here, once) and land in ONE device blob whose
+            # sub-ranges ARE the device planes (PCIe moves 40 MB pieces at ~55 GB/s but 2-10 MB pieces at ~36 GB/s,
+            # profiles/pcie_probe.json).  A compact base plane (slots 0..10) is read by K1 directly, which writes
+            # the full 16-slot records.
             compact = pinned["base_xyz"].shape[1] < _lib.BASE_SLOTS
             uploaded = [name for name in _FIELDS if name not in ("center", "rot")]
             offs, total = {}, 0
@@ -326,19 +453,29 @@ class Pipeline(object):
                 src = pinned[name][lo:hi]
                 offs[name] = (total, src.numel() * src.element_size(), src.dtype, tuple(src.shape))
                 total += (offs[name][1] + 255) // 256 * 256
+            ch.ident = None
+            if ident is not None:
+                ch.ident = DeviceIdent(torch, None, ident, ch.s0, ch.s1)
+                ident_off = total
+                total += (ch.ident.host_blob.numel() + 255) // 256 * 256
             ch.host_blob = torch.empty(max(total, 1), dtype=torch.uint8).pin_memory()
             ch.dev_blob = torch.empty(max(total, 1), dtype=torch.uint8, device=dev)
+            self.h2d_bytes += total
             ch.dev = {}
-            ch.base_stage = None
+            ch.compact_base = None
             for name in uploaded:
                 o, nb, dt, shape = offs[name]
                 ch.host_blob[o:o + nb].view(dt).view(shape).copy_(pinned[name][lo:hi])
                 view = ch.dev_blob[o:o + nb].view(dt).view(shape)
                 if name == "base_xyz" and compact:
-                    ch.base_stage = view
-                    ch.dev[name] = torch.zeros((n, _lib.BASE_SLOTS, 3), dtype=dt, device=dev)
+                    ch.compact_base = (view, int(shape[1]))
+                    ch.dev[name] = torch.empty((n, _lib.BASE_SLOTS, 3), dtype=dt, device=dev)
                 else:
                     ch.dev[name] = view
+            if ch.ident is not None:
+                nb = ch.ident.host_blob.numel()
+                ch.host_blob[ident_off:ident_off + nb].copy_(ch.ident.host_blob)
+                ch.ident.bind(ch.dev_blob[ident_off:ident_off + nb])
             for name in ("center", "rot"):
                 ch.dev[name] = torch.zeros((n,) + tuple(getattr(batch, name).shape[1:]), dtype=pinned[name].dtype,
                                            device=dev)
@@ -350,19 +487,42 @@ class Pipeline(object):
             frac = n / max(batch.n, 1)
             pc = int((pair_cap or (12 * batch.n + 1024)) * frac * 1.15) + 4096
             hc = int((hit_cap or (12 * batch.n + 1024)) * frac * 1.15) + 4096
-            ch.plan = engine.make_plan(n, pc, hc)
-            ch.counters_host = torch.zeros(8, dtype=torch.int64).pin_memory()
+            rc = (int(row_cap * frac * 1.15) + 4096) if row_cap else None
+            ch.plan = engine.make_plan(n, pc, hc, tail=(ch.ident.n_struct, ch.ident.n_ends) if ch.ident else None,
+                                       row_cap=rc)
+            ch.counters_host = torch.zeros(12, dtype=torch.int64).pin_memory()
             ch.ev = torch.cuda.Event()
             self.chunks.append(ch)
-        total_hc = sum(ch.plan.hit_cap for ch in self.chunks)
-        self.hits_host = torch.empty(total_hc * HIT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
-        self.hits_np = self.hits_host.numpy()
-        self.h2d_bytes = sum(int(pinned[name][0:1].element_size()) * int(np.prod(pinned[name].shape))
-                             for name in _FIELDS if name not in ("center", "rot"))
+        self._alloc_results()
+
+    def _alloc_results(self):
+        torch = self.eng.torch
+        self.hits_host = None
+        if self.want_hits:
+            total_hc = sum(ch.plan.hit_cap for ch in self.chunks)
+            self.hits_host = torch.empty(total_hc * HIT_DTYPE.itemsize, dtype=torch.uint8).pin_memory()
+        self.rows_host = None
+        if self.labels is not None:
+            total_rc = sum(ch.plan.row_cap for ch in self.chunks)
+            S = self.batch.n_structures
+            self.rows_host = torch.empty(total_rc * 16, dtype=torch.uint8).pin_memory()
+            self.row_start_host = torch.empty(max(S, 1), dtype=torch.int32).pin_memory()
+            self.row_count_host = torch.empty(max(S, 1), dtype=torch.int32).pin_memory()
+
+    def _launch(self, ch):
+        eng = self.eng
+        tail = (ch.ident, self.labels) if ch.ident is not None else None
+        eng.run_plan(ch, ch.plan, self.bt, self.mask, fit_frames=True, index_offset=ch.lo, tail=tail)
+        ch.counters_host[:8].copy_(ch.plan.counters, non_blocking=True)
+        if tail is not None:
+            ch.counters_host[8:].copy_(ch.plan.tcounters, non_blocking=True)
+        ch.ev.record(ch.stream)
 
     def run(self):
-        """One pass.  Returns (hits, n_pairs): hits is a structured-array VIEW of the pipeline's pinned
-        result buffer with GLOBAL nt indices (valid until the next run())."""
+        """One pass.  Returns a PipelineResult: n_pairs, n_hits, and (with labels) rows / row_start / row_count -
+        structured-array VIEWS of the pipeline's pinned result buffers with GLOBAL nt indices, valid until the
+        next run(); .hits when the pipeline copies hit records back.  A chunk whose capacities turn out too small
+        is re-run with the exact counts (nothing is truncated)."""
         eng, torch = self.eng, self.eng.torch
         main = torch.cuda.current_stream(eng.device)
         start = torch.cuda.Event()
@@ -371,28 +531,70 @@ class Pipeline(object):
             ch.stream.wait_event(start)
             with torch.cuda.stream(ch.stream):
                 ch.dev_blob.copy_(ch.host_blob, non_blocking=True)
-                if ch.base_stage is not None:
-                    ch.dev["base_xyz"][:, :ch.base_stage.shape[1]].copy_(ch.base_stage, non_blocking=True)
-                eng.run_plan(ch, ch.plan, self.bt, self.mask, fit_frames=True, index_offset=ch.lo)
-                ch.counters_host.copy_(ch.plan.counters, non_blocking=True)
-                ch.ev.record(ch.stream)
-        n_pairs = 0
-        off = 0
+                self._launch(ch)
+        n_pairs = n_hits = 0
+        hoff = roff = 0
+        regrow = False
         for ch in self.chunks:
-            ch.ev.synchronize()
-            cnt = ch.counters_host
-            if int(cnt[2]) != 0:
-                raise _lib.Fr3dError("fr3d_pair_search: base centre outside the spatial-hash range (FR3D_E_RANGE)")
-            npairs, nhits = int(cnt[0]), int(cnt[1])
-            if npairs > ch.plan.pair_cap or nhits > ch.plan.hit_cap:
-                raise _lib.Fr3dError("pipeline chunk capacity exceeded (pairs %d/%d, hits %d/%d): rebuild the "
-                                     "Pipeline with larger capacities" % (npairs, ch.plan.pair_cap, nhits,
-                                                                          ch.plan.hit_cap))
+            while True:
+                ch.ev.synchronize()
+                cnt = ch.counters_host
+                if int(cnt[2]) != 0:
+                    raise _lib.Fr3dError("fr3d_pair_search: base centre outside the spatial-hash range (FR3D_E_RANGE)")
+                npairs, nhits = int(cnt[0]), int(cnt[1])
+                nrows = int(cnt[8]) if ch.ident is not None else 0
+                if ch.ident is not None and int(cnt[10]) != 0 and npairs <= ch.plan.pair_cap and nhits <= ch.plan.hit_cap:
+                    raise _lib.Fr3dError("fr3d_annotation_tail: a structure is outside the supported ranges (FR3D_E_RANGE)")
+                over = npairs > ch.plan.pair_cap or nhits > ch.plan.hit_cap
+                if not over and (ch.ident is None or nrows <= ch.plan.row_cap):
+                    break
+                # capacity exceeded: new buffers with the exact counts, this chunk again (its input is still on the device)
+                regrow = True
+                tail = (ch.ident.n_struct, ch.ident.n_ends) if ch.ident is not None else None
+                if over:
+                    ch.plan = eng.make_plan(ch.n, max(npairs, ch.plan.pair_cap) + 1024,
+                                            max(nhits, 2 * npairs if nhits > ch.plan.hit_cap else ch.plan.hit_cap) + 1024,
+                                            tail=tail, row_cap=None)
+                else:
+                    eng.add_tail_buffers(ch.plan, tail[0], tail[1], row_cap=nrows + 1024)
+                with torch.cuda.stream(ch.stream):
+                    self._launch(ch)
+            ch.n_hits, ch.n_rows = nhits, nrows
             n_pairs += npairs
-            nb = nhits * HIT_DTYPE.itemsize
+            n_hits += nhits
+        if regrow:
+            self._alloc_results()
+        for ch in self.chunks:
             with torch.cuda.stream(ch.stream):
-                self.hits_host[off:off + nb].copy_(ch.plan.hits[:nb], non_blocking=True)
-            off += nb
+                if self.hits_host is not None:
+                    nb = ch.n_hits * HIT_DTYPE.itemsize
+                    self.hits_host[hoff:hoff + nb].copy_(ch.plan.hits[:nb], non_blocking=True)
+                    hoff += nb
+                if ch.ident is not None:
+                    nb = ch.n_rows * 16
+                    self.rows_host[roff:roff + nb].copy_(ch.plan.rows[:nb], non_blocking=True)
+                    ns = ch.s1 - ch.s0
+                    self.row_start_host[ch.s0:ch.s1].copy_(ch.plan.row_start[:ns], non_blocking=True)
+                    self.row_count_host[ch.s0:ch.s1].copy_(ch.plan.row_count[:ns], non_blocking=True)
+                    ch.row_off = roff // 16
+                    roff += nb
         for st in self.streams:
             st.synchronize()
-        return self.hits_np[:off].view(HIT_DTYPE), n_pairs
+        res = PipelineResult()
+        res.n_pairs, res.n_hits = n_pairs, n_hits
+        res.hits = self.hits_host.numpy()[:hoff].view(HIT_DTYPE) if self.hits_host is not None else None
+        res.rows = res.row_start = res.row_count = None
+        if self.labels is not None:
+            from .tail import ROW_DTYPE
+            S = self.batch.n_structures
+            res.rows = self.rows_host.numpy()[:roff].view(ROW_DTYPE)
+            res.row_start = self.row_start_host.numpy()[:S]
+            res.row_count = self.row_count_host.numpy()[:S]
+            for ch in self.chunks:               # the chunks' row blocks follow one another in the result buffer
+                if ch.row_off:
+                    res.row_start[ch.s0:ch.s1] += ch.row_off
+        return res
+
+
+class PipelineResult(object):
+    pass

@@ -78,6 +78,27 @@ class NtBatch(object):
                 self._unit_ids = out
         return self._unit_ids
 
+    def unit_ids_of(self, s):
+        """Unit ids of structure s only (list; position = nt - struct_off[s])."""
+        lo, hi = int(self.struct_off[s]), int(self.struct_off[s + 1])
+        if self._unit_ids is not None:
+            return self._unit_ids[lo:hi]
+        if self._unit_id_fn is not None:
+            return self.unit_ids()[lo:hi]
+        pdb, model, chain, seq, num = self.pdb[s], self.model, self.chain, self.sequence, self.number
+        alt, ins, sym = self.alt_id, self.insertion_code, self.symmetry
+        p_ = '' if pdb is None else pdb
+        out = []
+        for k in range(lo, hi):
+            nk = num[k]
+            if not alt[k] and not ins[k] and (not sym[k] or sym[k] == '1_555') and nk is not None and nk != '':
+                m_, c_, s_ = model[k], chain[k], seq[k]
+                out.append("%s|%s|%s|%s|%s" % (p_, '' if m_ is None else m_, '' if c_ is None else c_,
+                                               '' if s_ is None else s_, nk))
+            else:
+                out.append(encode_unit_id(pdb, model[k], chain[k], seq[k], nk, alt[k], ins[k], sym[k]))
+        return out
+
     def nbytes_device(self):
         return sum(a.nbytes for a in (self.center, self.rot, self.base_xyz, self.bb_xyz, self.base_mask,
                                       self.bb_mask, self.meta))

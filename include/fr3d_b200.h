@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define FR3D_ABI_VERSION 2
+#define FR3D_ABI_VERSION 3
 
 #define FR3D_OK 0
 #define FR3D_E_CUDA (-1)      /* a CUDA runtime call failed; see fr3d_last_error */
@@ -147,9 +147,12 @@ typedef struct {
 /* ---- library ------------------------------------------------------------ */
 int fr3d_version(void);
 const char *fr3d_last_error(void);
-int fr3d_init(int device);   /* REQUIRED once per process and device before any other call: selects the device,
-                                  checks sm_100, opts the kernels in to their shared-memory carve-outs */
-int fr3d_upload_tables(const fr3d_static_tables_t *host_tables);
+int fr3d_init(int device);   /* REQUIRED once per process and device before any other call: checks sm_100 and opts
+                                  the kernels in to their shared-memory carve-outs on that device.  The caller's
+                                  current device is left unchanged.  State is kept per device, so one thread per GPU
+                                  in one process works; every other entry point acts on the CURRENT device and fails
+                                  with FR3D_E_ARG if that device was not initialised. */
+int fr3d_upload_tables(const fr3d_static_tables_t *host_tables);   /* to the current device (FR3D_E_NOTABLES without) */
 
 /* K1. Replaces Component.calculate_rotation_matrix (fr3d/data/components.py:273-349) +
  * besttransformation (fr3d/geometry/superpositions.py:10-89) for every nt in one launch, and
@@ -157,6 +160,11 @@ int fr3d_upload_tables(const fr3d_static_tables_t *host_tables);
  * place_h != 0.  Reads base_xyz/base_mask/meta; writes center, rot, missing hydrogen slots,
  * base_mask (hydrogen bits + FR3D_MASK_HAS_FRAME) and status[n] (0 ok, -1 no parent, -2 <3 atoms). */
 int fr3d_frames_fit(const fr3d_nts_t *nts, int32_t *status, int place_h, void *stream);
+/* Same, with the observed base atoms read from a compact plane [n][compact_slots][3] (11 <= compact_slots <= 16:
+ * the first slots of every record; an upload that carries no observed hydrogens keeps slots 0..10 only) instead of
+ * nts->base_xyz, to which the full 16-slot records are written.  compact_base_xyz == NULL: fr3d_frames_fit. */
+int fr3d_frames_fit_from(const fr3d_nts_t *nts, const double *compact_base_xyz, int32_t compact_slots, int32_t *status,
+                         int place_h, void *stream);
 
 /* K2+K3. Replaces make_nt_cubes_half (NA:410-443) and the loop/screens of
  * annotate_nt_nt_interactions (NA:661-724): oriented candidate pairs with 2 <= d <= 12.
@@ -186,6 +194,78 @@ int fr3d_classify_pairs(const fr3d_nts_t *nts, const fr3d_box_t *boxes, const in
                         const int32_t *pair_i, const int32_t *pair_j, const int32_t *pair_rank,
                         int64_t pair_cap, uint32_t category_mask, int32_t index_offset, void *workspace,
                         size_t workspace_bytes, fr3d_hit_t *hits, int64_t hit_cap, int64_t *counters, void *stream);
+
+/* A8 on the device.  Replaces, for every structure of the batch in one call, the order-dependent
+ * tail of annotate_nt_nt_interactions: the visit-order recording of the per-pair results (NA:758-1013),
+ * check_for_two_interactions_on_same_edge (NA:528-632), the emission of the surviving basepairs (NA:1026-1044),
+ * calculate_crossing_numbers (NA:1057-1179) and annotate_covalent_connections (NA:1181-1210).
+ *
+ * Output: one 16-byte row per tuple the reference appends to interaction_to_list_of_tuples, per structure in the
+ * reference's own append order (so a stable grouping of a structure's rows by label gives the reference's dict:
+ * same keys in the same order, same lists in the same order).  Labels are integer ids; the id space belongs to
+ * the caller, who supplies the tables below (strings never reach the device). */
+typedef struct {
+    int32_t label;    /* label id; FR3D_LABEL_COVALENT | d for "p_<d>" */
+    int32_t nt1;      /* global nt index (index_offset added) */
+    int32_t nt2;
+    int32_t crossing; /* crossing number, -1 = None (covalent rows) */
+} fr3d_row_t;
+
+#define FR3D_LABEL_COVALENT 0x40000000
+
+/* Per label id. */
+typedef struct {
+    int32_t rev;   /* id of reverse_edges(label) (NA:446-465), -1 if not needed */
+    int32_t near;  /* id of "n" + label (NA:1031-1032), -1 if not needed */
+    uint32_t flags;/* bit0: rows are duplicated in reversed order (NA:1171-1177); bit1: label starts with "n";
+                      bit2: label is one of cWW cWw cwW acWW acWw acwW (NA:1077); bits 8-15: the edge letter
+                      label.replace("n","")[1].lower() (NA:543) */
+    int32_t pad;
+} fr3d_tail_label_t;
+
+/* Per cutoff box (same indexing as the fr3d_box_t table). */
+typedef struct {
+    int32_t label[2][2]; /* [recorded for u2 ? 1 : 0][near]: the box name / "n" + name, and reverse_edges of it */
+    uint64_t atoms1;     /* quality['atoms1'] / ['atoms2'] of store_basepair_quality (NA:2345-2361) as bit sets over */
+    uint64_t atoms2;     /* the caller's numbering of the hydrogen-bond atom names */
+} fr3d_tail_box_t;
+
+typedef struct {
+    int32_t n_labels;
+    int32_t n_boxes;
+    const fr3d_tail_label_t *labels;
+    const fr3d_tail_box_t *boxes;
+    const int32_t *slot_label; /* [8][32][2]: label ids of hit slot 0..7 and code: [0] the label recorded for
+                                  (nt1, nt2) (for FR3D_SLOT_SO21 / SR21: for (nt2, nt1)), [1] the second label of
+                                  the sO slots (interaction_reversed, NA:765,775), -1 elsewhere */
+    uint64_t hydrogen_atoms;   /* bits of the atom names that contain "H" (NA:581-582) */
+} fr3d_tail_tables_t;
+
+/* Identity of the nts, as far as the tail reads it (index and parent come from nts->meta). */
+typedef struct {
+    int32_t n_struct;
+    int32_t n_chains;
+    int32_t n_ends;                  /* chain_ends_off[n_chains], known to the host (sizes the workspace) */
+    int32_t reserved;
+    const int32_t *struct_off;       /* [n_struct + 1] first nt of each structure */
+    const int32_t *struct_chain_off; /* [n_struct + 1] first chain-table entry of each structure */
+    const int32_t *chain_ends_off;   /* [n_chains + 1] offset of the chain's nested-cWW endpoint array in the workspace;
+                                        its length is the chain's largest index + 1 (NA:1106) */
+    const int32_t *nt_chain;         /* [n_nt] chain-table entry = (structure, chain id): crossing numbers key chains by
+                                        id only (NA:1068-1072) */
+    const int32_t *nt_cov;           /* [n_nt] rank of the string model + " " + symmetry + " " + chain (NA:1192) */
+} fr3d_tail_ident_t;
+
+/* tail_counters (device int64[4]): [0] total rows (may exceed row_cap: compare after the sync and re-run),
+ * [1] scratch, [2] != 0: a structure outside the supported ranges (more than 131 072 nts, an index outside
+ * [0, 2^23), more than 65 536 chains or a label without the table entry it needs: FR3D_E_RANGE), [3] scratch.
+ * n_hits is read from counters[1] on the device (clamped to hit_cap).  row_start / row_count [n_struct]: the rows of
+ * structure s are rows[row_start[s] .. + row_count[s]) (the structures' blocks sit in no particular order). */
+size_t fr3d_tail_workspace(int64_t hit_cap, int32_t n_nt, int32_t n_struct, int64_t n_ends);
+int fr3d_annotation_tail(const fr3d_nts_t *nts, const fr3d_tail_ident_t *ident, const fr3d_tail_tables_t *tables,
+                         const fr3d_hit_t *hits, int64_t hit_cap, const int64_t *counters, int32_t index_offset,
+                         void *workspace, size_t workspace_bytes, fr3d_row_t *rows, int64_t row_cap,
+                         int32_t *row_start, int32_t *row_count, int64_t *tail_counters, void *stream);
 
 /* FR3D search screening.  Replaces fixed_radius_search (fr3d/search/pair_processing.py:106-177),
  * which get_pairlist (:7-104) calls once per search: every pair of points of the same model whose squared distance

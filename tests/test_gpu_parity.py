@@ -170,8 +170,12 @@ def test_annotation_identical_to_reference(golden, spec_name, annot_name):
     want = {k: [(uid[a], uid[b], c) for a, b, c in v] for k, v in g["interaction_to_list_of_tuples"].items()}
     wantc = {k: set(v) for k, v in g["category_to_interactions"].items()}
     # batched entry point, frames fitted on the GPU
-    i2t, c2i = as_plain(NA.annotate_batch(spec, g["categories"])[0])
+    res = NA.annotate_batch(spec, g["categories"])[0]
+    i2t, c2i = as_plain(res)
     assert i2t == want and c2i == wantc                 # same rows, same order as fr3d-python
+    assert list(res[0].keys()) == [k for k, v in g["interaction_to_list_of_tuples"].items() if v]   # same dict order
+    # the host form of the tail (postprocess.py) gives the same
+    assert as_plain(NA.annotate_batch(spec, g["categories"], tail="host")[0]) == (want, wantc)
     # reference entry point on Structure / Component objects
     st = Structure.from_spec(spec)
     r = NA.annotate_nt_nt_in_structure(st, g["categories"])
@@ -295,8 +299,8 @@ def test_observed_hydrogens_are_kept(golden):
 def test_host_tail_in_worker_processes_gives_the_same_results():
     """annotate_batch(tail_workers=n): the per-structure host tail in forked worker processes."""
     batch = synthetic.make_structure_batch(synthetic.pack_base(), 40, seed0=321)
-    one = NA.annotate_batch(batch, ALL9, tail_workers=1)
-    many = NA.annotate_batch(batch, ALL9, tail_workers=4)
+    one = NA.annotate_batch(batch, ALL9, tail_workers=1, tail="host")
+    many = NA.annotate_batch(batch, ALL9, tail_workers=4, tail="host")
     assert len(one) == len(many) == 40
     for a, b in zip(one, many):
         assert list(a[0].keys()) == list(b[0].keys())            # same labels in the same order ...
@@ -378,6 +382,116 @@ def test_full_size_batch_properties():
     assert np.all(hb['slot'] <= 8)
 
 
+# ------------------------------------------------------------------ device tail (N1)
+def _rows_by_structure(res, s):
+    r = res.rows_of(s)
+    return [(res.labels.name(l), a, b, c) for l, a, b, c in zip(r['label'].tolist(), r['nt1'].tolist(), r['nt2'].tolist(),
+                                                                 r['crossing'].tolist())]
+
+
+def test_device_tail_equals_host_tail_and_oracle():
+    """fr3d_annotation_tail (same-edge cleanup, emission, crossing numbers, covalent links on the GPU) against the
+    host form of the tail on 64 structures at three noise levels - rows, row order AND dict key order - and
+    against the oracle on 16 of them."""
+    base = synthetic.pack_base()
+    for sigma, seed0, n_oracle in ((0.10, 4000, 6), (0.50, 7000, 5), (1.0, 9000, 5)):
+        batch = synthetic.make_structure_batch(base, 64 if sigma == 0.10 else 24, seed0=seed0, sigma=sigma)
+        dev = NA.annotate_batch(batch, ALL9)
+        host = NA.annotate_batch(batch, ALL9, tail="host")
+        assert len(dev) == len(host) == batch.n_structures
+        for s in range(batch.n_structures):
+            assert list(dev[s][0].keys()) == list(host[s][0].keys()), "structure %d, sigma %g" % (s, sigma)
+            assert as_plain(dev[s]) == as_plain(host[s]), "structure %d, sigma %g" % (s, sigma)
+        rng = np.random.default_rng(seed0)
+        for s in rng.choice(batch.n_structures, n_oracle, replace=False).tolist():
+            want, wc, _, _ = oracle_tuples(synthetic.batch_to_spec(batch, s), ALL9)
+            assert as_plain(dev[s]) == (want, wc), "structure %d, sigma %g" % (s, sigma)
+
+
+def test_full_size_batch_random_structures_against_oracle():
+    """C4 at bench size (1000 structures in one pass, device tail): 16 random structures against the oracle, row
+    arrays consistent, every structure's block in bounds."""
+    base = synthetic.pack_base()
+    batch = synthetic.make_structure_batch(base, 1000, seed0=4000)
+    res = NA.annotate_batch(batch, ALL9, as_arrays=True)
+    assert len(res) == 1000 and res.n_rows == len(res.rows)
+    ends = np.sort(res.row_start.astype(np.int64) + res.row_count)
+    starts = np.sort(res.row_start.astype(np.int64))
+    assert starts[0] == 0 and np.array_equal(starts[1:], ends[:-1]) and ends[-1] == len(res.rows)     # a partition
+    sid1 = np.searchsorted(batch.struct_off, res.rows['nt1'], side='right') - 1
+    sid2 = np.searchsorted(batch.struct_off, res.rows['nt2'], side='right') - 1
+    assert np.array_equal(sid1, sid2)
+    for s in np.random.default_rng(5).choice(1000, 16, replace=False).tolist():
+        assert np.all(sid1[res.row_start[s]:res.row_start[s] + res.row_count[s]] == s)
+        want, wc, _, _ = oracle_tuples(synthetic.batch_to_spec(batch, s), ALL9)
+        assert as_plain(res[s]) == (want, wc), "structure %d" % s
+
+
+def test_device_tail_row_order_is_the_append_order(golden):
+    """The flat row array lists the tuples in the order the reference appends them: grouping it by label (stable)
+    gives the golden lists, and the first occurrences give the golden dict order."""
+    spec = golden("spec_1gid_variants.json.gz")
+    g = golden("annot_1gid_variants_all9.json.gz")
+    res = NA.annotate_batch(spec, g["categories"], as_arrays=True)
+    rows = _rows_by_structure(res, 0)
+    grouped = {}
+    for l, a, b, c in rows:
+        grouped.setdefault(l, []).append([a, b, None if c < 0 else c])
+    want = {k: v for k, v in g["interaction_to_list_of_tuples"].items() if v}
+    assert list(grouped.keys()) == list(want.keys())
+    assert grouped == want
+
+
+def test_device_tail_in_the_pipeline_and_capacity_reruns():
+    """engine.Pipeline with the device tail: rows of every chunking equal the single pass; a pipeline built with
+    far too small capacities re-runs its chunks instead of raising or truncating."""
+    import torch
+    from fr3d_python_b200.engine import Pipeline, pin_batch
+    base = synthetic.pack_base()
+    batch = synthetic.make_structure_batch(base, 37, seed0=900)
+    eng = Engine.get()
+    bt, atoms, labels = NA._tables(NA._default_focused(ALL9['basepair']), NA.load_ideal_basepair_hydrogen_bonds())
+    mask = NA.category_mask(ALL9)
+    ref = NA.annotate_batch(batch, ALL9, as_arrays=True)
+    pinned = pin_batch(torch, batch)
+    for chunks, caps in ((1, None), (5, None), (37, None), (3, (100, 100, 50))):
+        kw = {} if caps is None else {"pair_cap": caps[0], "hit_cap": caps[1], "row_cap": caps[2]}
+        pipe = Pipeline(eng, batch, pinned, bt, mask, n_chunks=chunks, labels=labels, **kw)
+        for _ in range(2):
+            out = pipe.run()
+        assert out.n_pairs == ref.n_pairs and out.hits is None
+        for s in range(batch.n_structures):
+            got = out.rows[out.row_start[s]:out.row_start[s] + out.row_count[s]]
+            assert np.array_equal(got, ref.rows_of(s)), "chunks %d structure %d" % (chunks, s)
+    # the single-pass entry point re-runs too
+    tiny = eng.make_plan(batch.n, pair_cap=100, hit_cap=10)
+    hits, n_pairs, ex = eng.annotate_batch(batch, bt, mask, plan=tiny, labels=labels)
+    assert n_pairs == ref.n_pairs and len(ex["rows"]) == ref.n_rows
+
+
+def test_device_tail_edge_cases(golden):
+    """Empty structures inside a batch, a structure without any hit, multi-model / symmetry / insertion-code
+    identities (covalent links per model + operator + chain), and the ranges the device tail refuses."""
+    strand = golden("spec_1s72_strand.json.gz")
+    variants = golden("spec_1gid_variants.json.gz")
+    far = copy.deepcopy(strand)
+    far["pdb"] = "FAR"
+    far["nts"] = far["nts"][:1]                                  # one nt: no pair, no covalent link
+    specs = [{"pdb": "E0", "nts": []}, strand, far, {"pdb": "E1", "nts": []}, variants]
+    dev = NA.annotate_batch(specs, ALL9)
+    host = NA.annotate_batch(specs, ALL9, tail="host")
+    assert len(dev) == 5
+    for s in range(5):
+        assert list(dev[s][0].keys()) == list(host[s][0].keys())
+        assert as_plain(dev[s]) == as_plain(host[s])
+    assert as_plain(dev[0]) == ({}, {}) and as_plain(dev[2]) == ({}, {})
+    bad = copy.deepcopy(strand)
+    bad["nts"][3]["index"] = -4
+    with pytest.raises(_lib.Fr3dError):
+        NA.annotate_batch(bad, ALL9)
+    assert len(NA.annotate_batch(bad, ALL9, tail="host")) == 1      # the host tail has no such limit
+
+
 def postprocess_subset(batch, hits, bt, atoms, which):
     from fr3d_python_b200 import postprocess
     hits = postprocess.sort_hits(hits)
@@ -410,7 +524,8 @@ def test_pipelined_path_equals_single_pass(observed_h):
     for chunks in (1, 5, 37):
         pipe = Pipeline(eng, batch, pinned, bt, mask, n_chunks=chunks, pair_cap=n_pairs, hit_cap=len(hits))
         for _ in range(2):
-            h2, np2 = pipe.run()
+            res = pipe.run()
+        h2, np2 = res.hits, res.n_pairs
         key = lambda h: np.lexsort((h['slot'], h['j'], h['i'], h['rank']))
         assert np2 == n_pairs and np.array_equal(hits[key(hits)], h2[key(h2)])
 
