@@ -1,18 +1,28 @@
 #!/usr/bin/env python
-"""Benchmark of the hot path: nt-pairs classified/sec on the 1000-structure synthetic batch
-(BASELINE.json configs[3]), one process per GPU, weak scaling.
+"""Benchmark of the hot path (BASELINE.json metric: nt-pairs classified/sec & structures/sec vs host-CPU reference).
 
-  python bench.py --gpus 1 --steps K --warmup W            our arm (CUDA)
-  python bench.py --impl reference ...                      the reference's CPU algorithm (oracle
-                                                            port, all host cores, bounded sample)
+  python bench.py --gpus N --steps K --warmup W                  our arm (CUDA), workload C4
+  python bench.py --workload c5 ...                              all-vs-all discrepancy of 20 000 motif instances
+  python bench.py --impl reference ...                           the UNMODIFIED reference (baseline/_ref/fr3d, a copy
+                                                                 of /root/reference/fr3d made by build()) on all host
+                                                                 cores, bounded sample; the oracle port if absent
 
-A step = one pass of the hot path (K1 frames -> K2/K3 search -> K4 classify) over the rank's batch.
-`value` is timed with inputs resident in HBM; `e2e` is the same pass through the Python/C-ABI
-call with pinned HOST buffers (H2D of the nt records and D2H of the hit records inside the timed
-region).  One JSON line is printed by rank 0.
+C4 = BASELINE configs[3]: a 1000-structure synthetic batch (perturbed 1GID-scale structures), all nine categories.
+A step = one pass of the whole annotator over the batch: K1 frames -> K2/K3 search -> K4 classify -> device tail
+(same-edge cleanup, emission, crossing numbers, covalent links) -> final rows in the reference's order.
+
+  value   inputs resident in HBM, rows left in HBM (N > 1, strong scaling: gathered to rank 0's HBM with NCCL)
+  e2e     packed HOST records in (pinned) -> H2D -> K1..K4 + tail -> final rows on the HOST of rank 0 (N > 1: ONE batch
+          sharded by LPT over the ranks, rows gathered with a tensor collective inside the timed region)
+  N = 1: scaling "weak" is moot; N > 1: "strong" by default (the one batch of configs[3] sharded over N GPUs), and the
+  weak-scaling numbers (every rank its own 1000-structure batch, no exchange) are reported under "weak".
+
+One JSON line is printed by rank 0.
 """
 
 import argparse
+import contextlib
+import io
 import json
 import multiprocessing as mp
 import os
@@ -33,43 +43,90 @@ CATEGORIES = {'basepair': ['cWW', 'cSS', 'cHH', 'cHS', 'cHW', 'cSH', 'cSW', 'cWH
 RECORD_BYTES = 760          # per-nt device record (include/fr3d_b200.h)
 PAIR_BYTES = 2 * RECORD_BYTES + 12 + 32   # gather model: two nt records + (i, j, rank) + one hit slot
 METRIC = "nt_pairs_classified_per_sec"
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")
 
 
-def load_peaks():
+def load_peaks(key="hbm_gbs", fallback=6650.0, what="B200_PROFILING.md 6.65 TB/s"):
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         with open(path) as f:
-            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+            d = json.load(f)
+        if key in d:
+            return float(d[key]), "measured (MEASURED_PEAKS.json %s)" % key
+    return fallback, "fallback (%s)" % what
 
 
 # ------------------------------------------------------------------ CPU legs --
-def _oracle_one(args):
-    """Annotate one synthetic structure with the oracle port; returns candidate-pair count."""
-    import contextlib
-    import io
-    seed, n_struct_unused = args
+def reference_available():
+    return os.path.isdir(os.path.join(REF_DIR, "fr3d", "classifiers"))
+
+
+def _spec_of_seed(seed):
     from fr3d_python_b200 import synthetic
-    from oracle import fr3d_oracle as O
     base = synthetic.pack_base()
     tb = synthetic.make_structure_batch(base, 1, seed0=seed)
-    spec = synthetic.batch_to_spec(tb, 0)
+    return synthetic.batch_to_spec(tb, 0)
+
+
+def _reference_one(seed):
+    """One structure of the batch through the UNMODIFIED reference: Component construction (frame fit + hydrogens,
+    fr3d/data/components.py) and annotate_nt_nt_in_structure (all nine categories).  Returns its candidate pairs."""
+    sys.dont_write_bytecode = True
+    if REF_DIR not in sys.path:
+        sys.path.insert(0, REF_DIR)
+    spec = _spec_of_seed(seed)
+    with contextlib.redirect_stdout(io.StringIO()):
+        from fr3d.classifiers import NA_pairwise_interactions as RNA
+        from fr3d.data import Atom, Component, Structure
+        comps = []
+        for nt in spec["nts"]:
+            atoms = [Atom(pdb=spec["pdb"], model=nt["model"], chain=nt["chain"], component_id=nt["sequence"],
+                          component_number=nt["number"], component_index=nt["index"], x=a[1], y=a[2], z=a[3],
+                          name=a[0], symmetry=nt["symmetry"], polymeric=True, type=a[0][0]) for a in nt["atoms"]]
+            comps.append(Component(atoms, pdb=spec["pdb"], model=nt["model"], type="RNA linking", chain=nt["chain"],
+                                   symmetry=nt["symmetry"], sequence=nt["sequence"], number=nt["number"],
+                                   index=nt["index"], polymeric=True))
+        st = Structure(comps, pdb=spec["pdb"])
+        RNA.annotate_nt_nt_in_structure(st, CATEGORIES)
+    c = np.array([x.centers["base"] for x in comps])
+    d = np.linalg.norm(c[:, None] - c[None], axis=2)
+    return int(np.triu((d >= 2.0) & (d <= 12.0), 1).sum())
+
+
+def _oracle_one(seed):
+    """Same through the oracle port (fallback when baseline/_ref is absent)."""
+    from oracle import fr3d_oracle as O
+    spec = _spec_of_seed(seed)
     with contextlib.redirect_stdout(io.StringIO()):
         out, c2i, tr = O.annotate(spec, CATEGORIES)
     return len(tr["candidates"])
 
 
 def cpu_sample_run(pool, seeds):
+    fn = _reference_one if reference_available() else _oracle_one
     t0 = time.perf_counter()
-    counts = pool.map(_oracle_one, [(s, 0) for s in seeds], chunksize=1)
+    counts = pool.map(fn, seeds, chunksize=1)
     dt = time.perf_counter() - t0
     return sum(counts), dt
+
+
+def cpu_kind():
+    return "reference" if reference_available() else "port"
+
+
+def cpu_what():
+    if reference_available():
+        return "unmodified fr3d-python (baseline/_ref/fr3d): Component construction + annotate_nt_nt_in_structure"
+    return "oracle/fr3d_oracle.py (port; baseline/_ref absent)"
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.workload == "c5":
+        import bench_c5
+        return bench_c5.run_reference_arm(args)
     cores = os.cpu_count() or 1
     procs = min(cores, 64)
     n_sample = procs               # one structure per worker per step
@@ -79,27 +136,32 @@ def run_reference_arm(args):
             cpu_sample_run(pool, [4000 + k for k in range(n_sample)])
         t_total, pairs_total = 0.0, 0
         for k in range(args.steps):
-            pairs, dt = cpu_sample_run(pool, [4000 + k * n_sample + q for q in range(n_sample)])
+            pairs, dt = cpu_sample_run(pool, [4000 + (k * n_sample + q) % args.structures for q in range(n_sample)])
             pairs_total += pairs
             t_total += dt
     value = pairs_total / t_total
-    sample = "%d structures (316 nt each) of the 1000-structure batch per step, one per worker" % n_sample
+    sample = "%d structures (316 nt each) of the 1000-structure batch per step, one per worker; %s" % (n_sample, cpu_what())
+    scaling = args.scaling or ("strong" if args.gpus > 1 else "weak")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * t_total / max(args.steps, 1),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, args.structures),
-            "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": procs, "kind": "port", "sample": sample},
+            "higher_is_better": True, "scaling": scaling if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_config(args, args.structures, args.gpus, scaling),
+            "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": procs, "kind": cpu_kind(), "sample": sample},
             "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "structures_per_s": n_sample * args.steps / t_total, "gpu_launches": 0}
     print(json.dumps(line))
 
 
-def workload_config(args, structures):
+def workload_config(args, structures, world, scaling=None):
+    weak = scaling == "weak" and world > 1
     return {"workload": "C4: synthetic batch of perturbed 1GID-scale structures (316 nt, seed 4000+k, sigma 0.10 A), "
-                        "all nine annotation categories",
-            "structures_per_gpu": structures, "nt_per_structure": 316,
-            "l2_policy": "inputs larger than L2 (240 MB of nt records per pass vs 126 MB L2)",
-            "parallelism": "structures sharded by rank, no data-path collective"}
+                        "all nine annotation categories, final rows in the reference's order (device tail included)",
+            "structures": structures * world if weak else structures,
+            "structures_per_gpu": structures if weak else structures / max(world, 1),
+            "nt_per_structure": 316,
+            "l2_policy": "inputs larger than L2 at N = 1 (240 MB of nt records per pass vs 126 MB L2); a per-GPU shard "
+                         "smaller than 200 MB (strong scaling at N > 1) gets a 256 MB buffer written between timed steps",
+            "parallelism": "structures sharded by rank (LPT on nt count), no data-path collective; rows gathered to rank 0"}
 
 
 # ------------------------------------------------------------------ clocks --
@@ -146,6 +208,40 @@ class ClockSampler(object):
                 "samples_under_load": len(sm)}
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this process (and the pinned host memory it allocates from now on) to the CPUs next to its GPU, so that the
+    ranks of one box do not all stage through one NUMA node.  Best effort; returns what it did."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        n_words = ((os.cpu_count() or 64) + 63) // 64
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if word >> b & 1]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return "cpus %d-%d (%d)" % (min(cpus), max(cpus), len(cpus))
+    except Exception as ex:          # no NVML / no permission: stay unbound
+        return "unbound (%s)" % type(ex).__name__
+    return "unbound"
+
+
+def init_distributed(torch, dist, local_rank):
+    """NCCL prints its version banner on stdout at communicator creation; the contract is ONE JSON line on stdout,
+    so stdout is pointed at stderr while the communicator is built."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.barrier()
+        torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+
+
 # ------------------------------------------------------------------ our arm --
 def main():
     ap = argparse.ArgumentParser()
@@ -153,19 +249,27 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--structures", type=int, default=1000, help="structures per GPU (weak scaling)")
+    ap.add_argument("--workload", default="c4", choices=["c4", "c5"])
+    ap.add_argument("--scaling", default=None, choices=["strong", "weak"],
+                    help="N > 1: strong (default) = ONE batch of --structures sharded over the ranks; weak = own batch per rank")
+    ap.add_argument("--structures", type=int, default=1000, help="structures of the batch (per GPU under weak scaling)")
+    ap.add_argument("--instances", type=int, default=20000, help="c5: motif instances")
     ap.add_argument("--cpu-structures", type=int, default=0, help="CPU baseline sample (0 = 2 per core, max 128)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--chunks", type=int, default=8, help="chunks of the e2e pipeline (2 / 4 / 8 / 12 / 16: 4.06 / 3.82 / 3.71 / 3.72 / 3.88 ms)")
+    ap.add_argument("--chunks", type=int, default=8, help="chunks of the e2e pipeline per GPU")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         run_reference_arm(args)
         return
+    if args.workload == "c5":
+        import bench_c5
+        return bench_c5.main(args)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    scaling = args.scaling or ("strong" if world > 1 else "weak")
 
     # CPU baseline first (fork pool before any CUDA context exists): rank 0, N = 1 only
     cpu_baseline = None
@@ -176,168 +280,275 @@ def main():
         ctx = mp.get_context("fork")
         with ctx.Pool(procs) as pool:
             pairs, dt = cpu_sample_run(pool, [4000 + k for k in range(n_sample)])
-        cpu_baseline = {"value": pairs / dt, "unit": "pairs/s", "cores": procs, "kind": "port",
-                        "sample": "first %d structures of the batch (%d candidate pairs) through oracle/fr3d_oracle.py "
-                                  "with a %d-process pool, %.1f s" % (n_sample, pairs, procs, dt),
+        cpu_baseline = {"value": pairs / dt, "unit": "pairs/s", "cores": procs, "kind": cpu_kind(),
+                        "sample": "first %d structures of the batch (%d candidate pairs), %s, %d-process pool, %.1f s"
+                                  % (n_sample, pairs, cpu_what(), procs, dt),
                         "structures_per_s": n_sample / dt}
 
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else "single rank: unbound"
     import torch
     import torch.distributed as dist
-    from fr3d_python_b200 import _lib, synthetic
+    from fr3d_python_b200 import packing, parallel, synthetic
+    from fr3d_python_b200 import tail as tailmod
     from fr3d_python_b200.classifiers import NA_pairwise_interactions as NA
-    from fr3d_python_b200.engine import DeviceBatch, Engine, HIT_DTYPE, pin_batch
+    from fr3d_python_b200.engine import DeviceBatch, DeviceIdent, Engine, Pipeline, pin_batch
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        # NCCL prints its version banner on stdout at communicator creation; the contract is ONE JSON
-        # line on stdout, so stdout is pointed at stderr while the communicator is built
-        sys.stdout.flush()
-        saved = os.dup(1)
-        os.dup2(2, 1)
-        try:
-            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-            dist.barrier()
-            torch.cuda.synchronize()
-        finally:
-            sys.stdout.flush()
-            os.dup2(saved, 1)
-            os.close(saved)
+        init_distributed(torch, dist, local_rank)
     sampler = ClockSampler(local_rank) if rank == 0 else None
 
     eng = Engine.get(local_rank)
+    dev = eng.device
     base = synthetic.pack_base()
     S = args.structures
-    batch = synthetic.make_structure_batch(base, S, seed0=4000 + rank * S)
     focused = NA._default_focused(CATEGORIES['basepair'])
-    bt, box_atoms = NA._box_table(focused, NA.load_ideal_basepair_hydrogen_bonds())
+    bt, box_atoms, labels = NA._tables(focused, NA.load_ideal_basepair_hydrogen_bonds())
     mask = NA.category_mask(CATEGORIES)
-    pinned = pin_batch(torch, batch)
-
-    # calibration pass through the public call (also sizes the plan exactly)
-    hits, n_pairs, extras = eng.annotate_batch(batch, bt, mask, pinned=pinned)
-    n_hits = len(hits)
-    plan = eng.make_plan(batch.n, pair_cap=n_pairs + 4096, hit_cap=n_hits + 4096)
+    l2_buf = torch.zeros(64 * 1024 * 1024, dtype=torch.float32, device=dev)         # 256 MB > 126 MB L2
+    shared = {"full_batch": None, "rows_expected": None}
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- resident: inputs already in HBM
-    db = DeviceBatch(torch, eng.device, batch, pinned)
-    torch.cuda.synchronize()
-    for _ in range(args.warmup):
-        eng.run_plan(db, plan, bt, mask, fit_frames=True)
-    torch.cuda.synchronize()
-    launches0 = eng.launches
-    evs = [{k: torch.cuda.Event(enable_timing=True) for k in ("search0", "classify0", "classify1")}
-           for _ in range(args.steps)]
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for k in range(args.steps):
-        eng.run_plan(db, plan, bt, mask, fit_frames=True, events=evs[k])
-    e1.record()
-    barrier()
-    gpu_launches = eng.launches - launches0
-    ms_total = e0.elapsed_time(e1)
-    np_chk, nh_chk = eng.read_counts(plan)
-    wl = plan.counters.cpu().tolist()
-    assert np_chk == n_pairs and nh_chk == n_hits, "resident pass disagrees with the calibration pass"
-    classify_ms = float(np.mean([ev["classify0"].elapsed_time(ev["classify1"]) for ev in evs]))
-    search_ms = float(np.mean([ev["search0"].elapsed_time(ev["classify0"]) for ev in evs]))
+    def measure(batch_local, mine, n_structures_total, gather):
+        """Resident and end-to-end timing of one sharding of the work.  batch_local: this rank's structures;
+        gather: rows go to rank 0 inside the timed regions (strong scaling).  Returns a dict of local measurements."""
+        out = {}
+        pinned = pin_batch(torch, batch_local)
+        ident = DeviceIdent(torch, dev, tailmod.tail_ident(batch_local))
+        tail = (ident, labels)
+        # calibration pass through the public call (also sizes the plan exactly)
+        hits, n_pairs, extras = eng.annotate_batch(batch_local, bt, mask, pinned=pinned, labels=labels, want_hits=True)
+        n_hits, n_rows = len(hits), len(extras["rows"])
+        plan = eng.make_plan(batch_local.n, pair_cap=n_pairs + 4096, hit_cap=n_hits + 4096,
+                             tail=(ident.n_struct, ident.n_ends), row_cap=n_rows + 4096)
+        out.update(n_pairs=n_pairs, n_hits=n_hits, n_rows=n_rows)
+        mine_l = list(mine)
+        db = DeviceBatch(torch, dev, batch_local, pinned)
 
-    # ---------------- e2e: pinned host buffers in, hit records out (per step)
-    # Engine's chunked pipeline: H2D of chunk k+1 overlaps the kernels of chunk k and the D2H of k-1
-    from fr3d_python_b200.engine import Pipeline
-    pipe = Pipeline(eng, batch, pinned, bt, mask, n_chunks=args.chunks, pair_cap=n_pairs, hit_cap=n_hits)
-    for _ in range(2):
-        res_p = pipe.run()
-    hits_p, n_pairs_p = res_p.hits, res_p.n_pairs
-    assert n_pairs_p == n_pairs and len(hits_p) == n_hits, "pipelined pass disagrees with the calibration pass"
-    barrier()
-    t0 = time.perf_counter()
-    for k in range(args.steps):
-        res_p = pipe.run()
-    torch.cuda.synchronize()
-    t_e2e = time.perf_counter() - t0
-    barrier()
+        def resident_step(events=None):
+            eng.run_plan(db, plan, bt, mask, fit_frames=True, events=events, tail=tail)
+            if gather:
+                rows = plan.rows[:n_rows * 16].view(torch.int32).view(-1, 4)
+                parallel.gather_rows(rows, plan.row_start[:ident.n_struct], plan.row_count[:ident.n_struct], mine_l,
+                                     n_structures_total, rank, world, scalars=(n_pairs,))
 
-    # host tail on a sample: hit records -> reference-format tuples (informational)
-    t0 = time.perf_counter()
-    n_tail = min(S, 50)
-    sub = synthetic.packing.select_structures(batch, range(n_tail))
-    NA.annotate_batch(sub, CATEGORIES)
-    t_tail = time.perf_counter() - t0
-    # ... and the same public call on a larger slice with the tail in forked worker processes (rank 0, N = 1 only:
-    # the ranks of one box would share the host cores)
-    t_tail_mp, n_tail_mp, tail_cores = None, min(S, 600), os.cpu_count() or 1
-    if world == 1 and tail_cores > 1 and n_tail_mp >= 64:
-        sub_mp = synthetic.packing.select_structures(batch, range(n_tail_mp))
+        # ---------------- resident: inputs already in HBM
+        torch.cuda.synchronize()
+        for _ in range(args.warmup):
+            resident_step()
+        torch.cuda.synchronize()
+        launches0 = eng.launches
+        names = ("search0", "classify0", "classify1", "tail1")
+        evs = [{k: torch.cuda.Event(enable_timing=True) for k in names} for _ in range(args.steps)]
+        small = batch_local.nbytes_device() < 200e6                # shard not much larger than L2: flush between steps
+        step_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        barrier()
+        for k in range(args.steps):
+            if small:
+                l2_buf.add_(1)
+            step_ev[k][0].record()
+            resident_step(events=evs[k])
+            step_ev[k][1].record()
+        barrier()
+        out["gpu_launches"] = eng.launches - launches0
+        out["ms_total"] = float(sum(a.elapsed_time(b) for a, b in step_ev))
+        np_chk, nh_chk = eng.read_counts(plan)
+        assert np_chk == n_pairs and nh_chk == n_hits and eng.read_tail_counts(plan) == n_rows, \
+            "resident pass disagrees with the calibration pass"
+        out["worklists"] = plan.counters.cpu().tolist()
+        out["classify_ms"] = float(np.mean([ev["classify0"].elapsed_time(ev["classify1"]) for ev in evs]))
+        out["search_ms"] = float(np.mean([ev["search0"].elapsed_time(ev["classify0"]) for ev in evs]))
+        out["tail_ms"] = float(np.mean([ev["classify1"].elapsed_time(ev["tail1"]) for ev in evs]))
+        out["l2_flush_between_steps"] = bool(small)
+
+        # ---------------- e2e: pinned host buffers in, final rows on the host of rank 0 out (per step)
+        if gather:
+            chunks = max(1, args.chunks // world)
+            sh = parallel.ShardedAnnotator(shared["full_batch"], CATEGORIES, rank=rank, world_size=world,
+                                           device=local_rank, n_chunks=chunks)
+            for _ in range(2):
+                res = sh.run()
+            if rank == 0:
+                assert res.n_rows == shared["rows_expected"], "sharded pass disagrees with the single-GPU row count"
+            barrier()
+            t0 = time.perf_counter()
+            for k in range(args.steps):
+                res = sh.run()
+            torch.cuda.synchronize()
+            out["t_e2e"] = time.perf_counter() - t0
+            barrier()
+            out["h2d"] = sh.pipe.h2d_bytes if sh.pipe is not None else 0
+            out["d2h"] = (res.n_rows * 16 + 8 * n_structures_total) if rank == 0 else 0
+            out["e2e_what"] = "parallel.ShardedAnnotator.run: LPT shard -> per rank pinned records -> H2D -> K1..K4 + " \
+                              "device tail (%d chunks) -> NCCL gather of the rows to rank 0 -> one D2H" % chunks
+            out["sharded_result"] = res
+        else:
+            pipe = Pipeline(eng, batch_local, pinned, bt, mask, n_chunks=args.chunks, pair_cap=n_pairs, hit_cap=n_hits,
+                            labels=labels, row_cap=n_rows)
+            for _ in range(2):
+                res = pipe.run()
+            assert res.n_pairs == n_pairs and len(res.rows) == n_rows, "pipelined pass disagrees with the calibration pass"
+            barrier()
+            t0 = time.perf_counter()
+            for k in range(args.steps):
+                res = pipe.run()
+            torch.cuda.synchronize()
+            out["t_e2e"] = time.perf_counter() - t0
+            barrier()
+            out["h2d"] = pipe.h2d_bytes
+            out["d2h"] = n_rows * 16 + 8 * batch_local.n_structures + 96 * len(pipe.chunks)
+            out["e2e_what"] = "engine.Pipeline.run: pinned host nt records -> H2D -> K1..K4 + device tail -> D2H of the " \
+                              "final rows (label id, nt1, nt2, crossing; reference order), %d chunks on 3 streams" % args.chunks
+        return out
+
+    def reduce_max_sum(vals):
+        t = torch.tensor(vals, dtype=torch.float64, device=dev)
+        if world > 1:
+            mx, sm = t.clone(), t.clone()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+            return mx.tolist(), sm.tolist()
+        return t.tolist(), t.tolist()
+
+    results = {}
+    if world == 1 or scaling == "strong":
+        # ONE batch of S structures; N > 1: sharded by LPT, rows gathered to rank 0
+        full_batch = synthetic.make_structure_batch(base, S, seed0=4000)
+        shared["full_batch"] = full_batch
+        parts = parallel.lpt_partition(np.diff(full_batch.struct_off).astype(int).tolist(), world)
+        mine = parts[rank]
+        local = packing.select_structures(full_batch, mine) if world > 1 else full_batch
+        ref = None
+        if world > 1 and rank == 0:          # the single-GPU answer the sharded run must reproduce
+            ref = NA.annotate_batch(full_batch, CATEGORIES, as_arrays=True)
+            shared["rows_expected"] = ref.n_rows
+        m = measure(local, mine, S, gather=(world > 1))
+        got = m.pop("sharded_result", None)
+        if ref is not None:
+            same = all(np.array_equal(got.rows_of(s), ref.rows_of(s)) for s in range(S))
+            assert same, "rank-0 result of the sharded run differs from the single-GPU run"
+            m["sharded_equals_single_gpu"] = True
+        results["main"] = m
+    if world > 1:
+        # weak scaling: every rank its own S-structure batch, nothing exchanged
+        own = synthetic.make_structure_batch(base, S, seed0=4000 + rank * S)
+        results["weak"] = measure(own, list(range(S)), S, gather=False)
+        if scaling == "weak":
+            results["main"] = results["weak"]
+
+    # ---------------- through the public API (rank 0, N = 1): array API and tuples; packing included
+    api = None
+    if world == 1 and rank == 0:
+        batch = shared["full_batch"]
+        pinned = pin_batch(torch, batch)
+        NA.annotate_batch(batch, CATEGORIES, pinned=pinned, as_arrays=True)
         t0 = time.perf_counter()
-        NA.annotate_batch(sub_mp, CATEGORIES, tail_workers=0)
-        t_tail_mp = time.perf_counter() - t0
+        reps = 3
+        for _ in range(reps):
+            res = NA.annotate_batch(batch, CATEGORIES, pinned=pinned, as_arrays=True)
+        t_arr = (time.perf_counter() - t0) / reps
+        n_t = min(S, 200)
+        t0 = time.perf_counter()
+        for s in range(n_t):
+            res[s]
+        t_tuples = (time.perf_counter() - t0) / n_t
+        # Structure-level input: column data (what an atom_site reader yields) -> pack_columns -> pipeline
+        n_in = min(S, 100)
+        specs = [synthetic.batch_to_spec(batch, s) for s in range(n_in)]
+        cols = packing.specs_to_columns(specs)
+        t0 = time.perf_counter()
+        b_in = packing.pack_columns(*cols)
+        t_pack = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        NA.annotate_batch(b_in, CATEGORIES, as_arrays=True)
+        t_ann = time.perf_counter() - t0
+        api = {"annotate_batch_array_api_structures_per_s": S / t_arr,
+               "annotate_batch_array_api_what": "NA.annotate_batch(batch, categories, pinned=..., as_arrays=True): one "
+                                                "un-pipelined pass incl. buffer allocation, %d structures" % S,
+               "tuples_structures_per_s_one_process": 1.0 / (t_arr / S + t_tuples),
+               "tuples_what": "array API + materialising the reference's dict of unit-id tuples for every structure "
+                              "(%.3f ms per structure in Python, measured on %d)" % (1e3 * t_tuples, n_t),
+               "e2e_structure_in": {"structures_per_s": n_in / (t_pack + t_ann), "pack_ms_per_structure": 1e3 * t_pack / n_in,
+                                    "what": "atom columns of %d structures -> packing.pack_columns (host numpy) -> "
+                                            "annotate_batch array API; packing included" % n_in}}
 
     clocks = sampler.stop() if sampler is not None else None
 
     # ---------------- reduce over ranks
-    vals = torch.tensor([ms_total, t_e2e, float(n_pairs), float(n_hits)], dtype=torch.float64, device=eng.device)
-    if world > 1:
-        mx = vals.clone()
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        sm = vals.clone()
-        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        ms_total, t_e2e = float(mx[0]), float(mx[1])
-        pairs_all, hits_all = float(sm[2]), float(sm[3])
-    else:
-        pairs_all, hits_all = float(n_pairs), float(n_hits)
+    def summarise(m, S_total):
+        mx, sm = reduce_max_sum([m["ms_total"], m["t_e2e"], float(m["n_pairs"]), float(m["n_hits"]), float(m["n_rows"]),
+                                 float(m["h2d"]), float(m["d2h"]), m["classify_ms"], m["search_ms"], m["tail_ms"],
+                                 float(m["gpu_launches"])])
+        ms_total, t_e2e = mx[0], mx[1]
+        pairs_all, hits_all, rows_all = sm[2], sm[3], sm[4]
+        return {"ms_per_step": ms_total / args.steps, "value": pairs_all * args.steps / (ms_total / 1000.0),
+                "structures_per_s": S_total * args.steps / (ms_total / 1000.0),
+                "e2e_value": pairs_all * args.steps / t_e2e, "e2e_structures_per_s": S_total * args.steps / t_e2e,
+                "e2e_ms_per_step": 1000.0 * t_e2e / args.steps, "pairs": pairs_all, "hits": hits_all, "rows": rows_all,
+                "h2d": sm[5], "d2h": sm[6], "classify_ms_max": mx[7], "search_ms_max": mx[8], "tail_ms_max": mx[9],
+                "gpu_launches": int(sm[10])}
+
+    strong = world == 1 or scaling == "strong"
+    main_s = summarise(results["main"], S if strong else S * world)
+    weak_s = summarise(results["weak"], S * world) if ("weak" in results and scaling == "strong") else None
     if rank == 0:
-        ms_per_step = ms_total / args.steps
-        value = pairs_all * args.steps / (ms_total / 1000.0)
-        e2e_value = pairs_all * args.steps / t_e2e
+        m = results["main"]
         peak, peak_src = load_peaks()
-        achieved = n_pairs * PAIR_BYTES / (classify_ms / 1000.0) / 1e9
+        achieved = m["n_pairs"] * PAIR_BYTES / (m["classify_ms"] / 1000.0) / 1e9
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "classify_traffic.json")
         if os.path.exists(tpath):
             with open(tpath) as f:
                 traffic = json.load(f).get("dram_bytes_per_launch")
-        h2d = pipe.h2d_bytes
-        d2h = n_hits * HIT_DTYPE.itemsize + 32
-        line = {"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, S),
+        wl = m["worklists"]
+        line = {"metric": METRIC, "value": main_s["value"], "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": main_s["ms_per_step"], "higher_is_better": True,
+                "scaling": scaling if world > 1 else "weak",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, S, world, scaling),
                 "dtype_note": "every label / number of a hit record is decided in f64; f32 only screens (supersets) and "
-                              "decides stacking comparisons that are certain by a margin, f64 recomputation otherwise",
-                "structures_per_s": S * world * args.steps / (ms_total / 1000.0),
-                "pairs_per_step": pairs_all, "hits_per_step": hits_all,
+                              "decides stacking comparisons that are certain by a margin, f64 recomputation otherwise; "
+                              "the tail is integer work",
+                "structures_per_s": main_s["structures_per_s"],
+                "pairs_per_step": main_s["pairs"], "hits_per_step": main_s["hits"], "rows_per_step": main_s["rows"],
                 "worklists_rank0": {"light_detail_pairs": int(wl[4]), "stacking_pairs": int(wl[5]),
                                     "pairing_pairs": int(wl[6]), "base_phosphate_pairs": int(wl[7])},
-                "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "structures_per_s": S * world * args.steps / t_e2e, "ms_per_step": 1000.0 * t_e2e / args.steps,
-                        "what": "engine.Pipeline.run: pinned host nt records -> H2D -> K1..K4 -> D2H hit records, "
-                                "%d chunks on 3 streams" % args.chunks},
-                "host_tail": {"structures_per_s_one_process": n_tail / t_tail,
-                              "what": "annotate_batch incl. packing-free host post-processing to reference tuples, "
-                                      "%d structures, single Python process" % n_tail,
-                              "structures_per_s_all_cores": (n_tail_mp / t_tail_mp) if t_tail_mp else None,
-                              "all_cores": "%d structures, tail_workers=0 (%d forked workers)" % (n_tail_mp, min(tail_cores, n_tail_mp // 8))},
-                "gpu_launches": gpu_launches,
-                "kernel_ms": {"classify_pairs": classify_ms, "pair_search_5_kernels": search_ms,
-                              "frames_fit_and_launch_gaps": ms_per_step - classify_ms - search_ms},
+                "e2e": {"value": main_s["e2e_value"], "unit": "pairs/s", "h2d_bytes_per_step": int(main_s["h2d"]),
+                        "d2h_bytes_per_step": int(main_s["d2h"]), "structures_per_s": main_s["e2e_structures_per_s"],
+                        "ms_per_step": main_s["e2e_ms_per_step"], "what": m["e2e_what"]},
+                "gpu_launches": main_s["gpu_launches"],
+                "kernel_ms": {"classify_pairs": m["classify_ms"], "pair_search_5_kernels": m["search_ms"],
+                              "device_tail_5_kernels": m["tail_ms"],
+                              "frames_fit_gather_and_launch_gaps": main_s["ms_per_step"] - m["classify_ms"] - m["search_ms"] - m["tail_ms"]},
                 "roofline": {"kernel": "fr3d_classify_pairs = screen_records + classify_screen32 + 2 x classify_pairs_tpp + "
                                        "classify_stack32 (+ its fp64 fallback launch) + classify_list2 (eight launches: "
-                                       "screen, then one or two per work list)", "bound": "hbm", "achieved": achieved, "peak": peak,
-                             "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                             "algorithmic_bytes_per_pair": PAIR_BYTES, "model": "gather: 2 x 760 B nt records + 12 B "
-                             "pair + 32 B hit slot per candidate pair"},
-                "clocks": clocks}
+                                       "screen, then one or two per work list), rank 0", "bound": "hbm", "achieved": achieved,
+                             "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                             "peak_source": peak_src, "algorithmic_bytes_per_pair": PAIR_BYTES,
+                             "model": "gather: 2 x 760 B nt records + 12 B pair + 32 B hit slot per candidate pair"},
+                "l2_flush_between_steps": m["l2_flush_between_steps"],
+                "numa_binding_rank0": numa, "clocks": clocks}
+        if m.get("sharded_equals_single_gpu"):
+            line["sharded_equals_single_gpu"] = True
+        if weak_s is not None:
+            line["weak"] = {"value": weak_s["value"], "ms_per_step": weak_s["ms_per_step"],
+                            "structures_per_s": weak_s["structures_per_s"], "structures_per_gpu": S,
+                            "e2e": {"value": weak_s["e2e_value"], "ms_per_step": weak_s["e2e_ms_per_step"],
+                                    "structures_per_s": weak_s["e2e_structures_per_s"],
+                                    "h2d_bytes_per_step": int(weak_s["h2d"]), "d2h_bytes_per_step": int(weak_s["d2h"])},
+                            "what": "weak scaling: every rank its own %d-structure batch, nothing exchanged" % S}
+        if api is not None:
+            line["api"] = api
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

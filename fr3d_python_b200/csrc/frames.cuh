@@ -23,12 +23,16 @@ constexpr int FRAMES_STRIDE = FR3D_BASE_SLOTS * 3 + 1;     // 49 doubles per row
 
 // the fit of one nt; xyz = its 16 x 3 slot block (a shared-memory row), std_xyz = the standard base coordinates.
 // Returns true if a slot below 8 was written (ideal-position copies of a modified residue).
+// keep_mask: bits of the incoming base_mask that are believed (all of them, or - when the atoms come from a compact
+// plane - only the slots that plane holds: the fit is then a pure function of the uploaded plane, also on a second
+// pass over records whose masks a first pass has already extended).
 __device__ __forceinline__ bool frames_fit_one(const fr3d_nts_t &nts, int32_t *__restrict__ status, int place_h, int n,
-                                               double *xyz, const double (*std_xyz)[FR3D_BASE_SLOTS][3]) {
+                                               double *xyz, const double (*std_xyz)[FR3D_BASE_SLOTS][3],
+                                               uint32_t keep_mask) {
     bool wrote_low = false;
     const int parent = nts.meta[n * FR3D_META_INTS + 0];
     const int flags = nts.meta[n * FR3D_META_INTS + 1];
-    const uint32_t mask_in = nts.base_mask[n];
+    const uint32_t mask_in = nts.base_mask[n] & keep_mask;
     uint32_t mask = mask_in & 0xFFFFu;
     // residues that already received their ideal-position copies hold averaged coordinates: fitting
     // them again would not reproduce the frame, so a second pass leaves them alone
@@ -184,7 +188,8 @@ __global__ void __launch_bounds__(FRAMES_WARPS * 32) frames_fit_kernel(fr3d_nts_
     }
     __syncthreads();
     bool wrote_low = false;                                               // wrote a slot below 8 (ideal-position copies)
-    if (n < nts.n_nt) wrote_low = frames_fit_one(nts, status, place_h, n, rows + lane * FRAMES_STRIDE, s_std);
+    const uint32_t keep_mask = compact ? ((1u << (cols / 3)) - 1u) : 0xFFFFFFFFu;
+    if (n < nts.n_nt) wrote_low = frames_fit_one(nts, status, place_h, n, rows + lane * FRAMES_STRIDE, s_std, keep_mask);
     __syncwarp();
     // copy back slots 8..15 (every hydrogen slot lies there: the parents have 8 to 11 heavy atoms), or whole rows
     // if some lane inserted ideal-position copies or the records came from a compact plane

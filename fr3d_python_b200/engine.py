@@ -518,11 +518,14 @@ class Pipeline(object):
             ch.counters_host[8:].copy_(ch.plan.tcounters, non_blocking=True)
         ch.ev.record(ch.stream)
 
-    def run(self):
+    def run(self, to_host=True):
         """One pass.  Returns a PipelineResult: n_pairs, n_hits, and (with labels) rows / row_start / row_count -
         structured-array VIEWS of the pipeline's pinned result buffers with GLOBAL nt indices, valid until the
         next run(); .hits when the pipeline copies hit records back.  A chunk whose capacities turn out too small
-        is re-run with the exact counts (nothing is truncated)."""
+        is re-run with the exact counts (nothing is truncated).
+        to_host=False (needs labels): nothing is copied back; the result holds DEVICE tensors instead - rows_dev
+        int32 [n_rows, 4] (the chunks' blocks concatenated), row_start_dev / row_count_dev int32 [n_structures] -
+        for a collective to pick up (parallel.ShardedAnnotator)."""
         eng, torch = self.eng, self.eng.torch
         main = torch.cuda.current_stream(eng.device)
         start = torch.cuda.Event()
@@ -558,12 +561,30 @@ class Pipeline(object):
                 else:
                     eng.add_tail_buffers(ch.plan, tail[0], tail[1], row_cap=nrows + 1024)
                 with torch.cuda.stream(ch.stream):
+                    ch.dev_blob.copy_(ch.host_blob, non_blocking=True)     # K1 has extended the masks in place
                     self._launch(ch)
             ch.n_hits, ch.n_rows = nhits, nrows
             n_pairs += npairs
             n_hits += nhits
         if regrow:
             self._alloc_results()
+        if not to_host:
+            if self.labels is None:
+                raise _lib.Fr3dError("Pipeline.run(to_host=False) needs the device tail (labels)")
+            res = PipelineResult()
+            res.n_pairs, res.n_hits = n_pairs, n_hits
+            parts, starts, counts, off = [], [], [], 0
+            for ch in self.chunks:                # all chunk kernels have finished (events), so any stream may read
+                ns = ch.s1 - ch.s0
+                parts.append(ch.plan.rows[:ch.n_rows * 16].view(torch.int32).view(-1, 4))
+                starts.append(ch.plan.row_start[:ns] + off)
+                counts.append(ch.plan.row_count[:ns])
+                off += ch.n_rows
+            res.rows_dev = torch.cat(parts) if parts else torch.zeros((0, 4), dtype=torch.int32, device=eng.device)
+            res.row_start_dev = torch.cat(starts) if starts else torch.zeros(0, dtype=torch.int32, device=eng.device)
+            res.row_count_dev = torch.cat(counts) if counts else torch.zeros(0, dtype=torch.int32, device=eng.device)
+            res.n_rows = off
+            return res
         for ch in self.chunks:
             with torch.cuda.stream(ch.stream):
                 if self.hits_host is not None:

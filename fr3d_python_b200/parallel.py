@@ -1,6 +1,14 @@
 """Multi-GPU: the path shards by structure (annotator) and by matrix row block (discrepancy);
 there is no exchange step, so no collective runs on the data path.  One process per GPU
-(torch.distributed, NCCL on GPUs / gloo in the CPU tests); results are gathered to rank 0 once.
+(torch.distributed, NCCL on GPUs / gloo in the CPU tests); results are gathered to rank 0 once,
+with tensor collectives (padded row arrays / matrix slabs), never pickled objects.
+
+  lpt_partition, cyclic_row_blocks, triangle_blocks     who owns what
+  gather_rows                                           per-rank row arrays -> rank 0 (any backend)
+  ShardedAnnotator                                      ONE batch sharded over the ranks (BASELINE configs[3]):
+                                                        LPT shard -> engine.Pipeline with the device tail per rank ->
+                                                        rows gathered on the device -> one D2H on rank 0
+  gather_slabs                                          discrepancy row blocks -> the N x N matrix on rank 0
 """
 
 import numpy as np
@@ -36,16 +44,144 @@ def _dist():
     return dist
 
 
-def annotate_batch_sharded(batch, categories, annotate_fn, rank=None, world_size=None, gather=True):
-    """Shard the structures of `batch` over ranks (LPT on nt count), run `annotate_fn(sub_batch,
-    categories) -> list of per-structure results` on the local shard and gather the per-structure
-    results to rank 0 in the original structure order.  Returns the full list on rank 0, the
-    local list elsewhere (or everywhere when gather=False)."""
+def _rank_world(rank, world_size):
     dist = _dist()
     if rank is None:
         rank = dist.get_rank() if dist.is_initialized() else 0
     if world_size is None:
         world_size = dist.get_world_size() if dist.is_initialized() else 1
+    return rank, world_size
+
+
+def gather_rows(rows, row_start, row_count, mine, n_structures, rank=None, world_size=None, scalars=()):
+    """Gather every rank's final rows to rank 0 with tensor collectives.
+
+    rows int32 [n_rows, 4] (label, nt1, nt2, crossing), row_start / row_count int32 [len(mine)] for the structures
+    `mine` (indices into the whole batch) - torch tensors on the device the process group works on (CUDA for NCCL,
+    CPU for gloo).  scalars: extra int64 values summed over ranks (e.g. candidate pairs).
+    Returns on rank 0 (rows [total, 4], row_start [n_structures], row_count [n_structures], summed scalars) as
+    tensors on that device, with row_start pointing into the concatenated array; None elsewhere.
+    Collectives: one all_gather of (n_rows, n_structures, scalars...) - its result sizes the padded buffers -
+    then one gather of the rows and one of the per-structure (start, count, structure index) table."""
+    import torch
+    dist = _dist()
+    rank, world_size = _rank_world(rank, world_size)
+    dev = rows.device
+    mine_t = torch.as_tensor(np.asarray(mine, dtype=np.int32), device=dev)
+    if world_size == 1:
+        rs = torch.zeros(n_structures, dtype=torch.int32, device=dev)
+        rc = torch.zeros(n_structures, dtype=torch.int32, device=dev)
+        rs[mine_t.long()] = row_start
+        rc[mine_t.long()] = row_count
+        return rows, rs, rc, [int(v) for v in scalars]
+    head = torch.tensor([int(rows.shape[0]), len(mine)] + [int(v) for v in scalars], dtype=torch.int64, device=dev)
+    heads = torch.empty((world_size, head.numel()), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(heads.view(-1), head)
+    heads_h = heads.cpu()
+    max_rows, max_structs = int(heads_h[:, 0].max()), int(heads_h[:, 1].max())
+    rows_pad = torch.zeros((max(max_rows, 1), 4), dtype=torch.int32, device=dev)
+    rows_pad[:rows.shape[0]] = rows
+    table = torch.zeros((max(max_structs, 1), 3), dtype=torch.int32, device=dev)
+    table[:len(mine), 0] = row_start
+    table[:len(mine), 1] = row_count
+    table[:len(mine), 2] = mine_t
+    if rank == 0:
+        rows_all = [torch.empty_like(rows_pad) for _ in range(world_size)]
+        table_all = [torch.empty_like(table) for _ in range(world_size)]
+        dist.gather(rows_pad, rows_all, dst=0)
+        dist.gather(table, table_all, dst=0)
+    else:
+        dist.gather(rows_pad, None, dst=0)
+        dist.gather(table, None, dst=0)
+        return None
+    out_rows, off = [], 0
+    rs = torch.zeros(n_structures, dtype=torch.int32, device=dev)
+    rc = torch.zeros(n_structures, dtype=torch.int32, device=dev)
+    for r in range(world_size):
+        nr, ns = int(heads_h[r, 0]), int(heads_h[r, 1])
+        out_rows.append(rows_all[r][:nr])
+        t = table_all[r][:ns]
+        idx = t[:, 2].long()
+        rs[idx] = t[:, 0] + off
+        rc[idx] = t[:, 1]
+        off += nr
+    return torch.cat(out_rows), rs, rc, [int(v) for v in heads_h[:, 2:].sum(dim=0)]
+
+
+class ShardedAnnotator(object):
+    """ONE batch annotated by all ranks (BASELINE configs[3]): structures are dealt to the ranks by LPT on their nt
+    count, every rank runs engine.Pipeline (K1..K4 + device tail) on its shard, the final rows are gathered on the
+    devices (NCCL) and rank 0 copies them to the host once.  All buffers are set up in the constructor; run() is
+    one pass and returns a tail.BatchAnnotations over the WHOLE batch on rank 0 (None elsewhere)."""
+
+    def __init__(self, batch, categories, focused_basepair_cutoffs=None, ideal_hydrogen_bonds=None, rank=None,
+                 world_size=None, device=None, n_chunks=2):
+        import torch
+        from .classifiers import NA_pairwise_interactions as NA
+        from .engine import Engine, Pipeline, pin_batch
+        self.rank, self.world = _rank_world(rank, world_size)
+        self.batch = batch
+        if not focused_basepair_cutoffs:
+            focused_basepair_cutoffs = NA._default_focused(categories.get('basepair', []))
+        if not ideal_hydrogen_bonds:
+            ideal_hydrogen_bonds = NA.load_ideal_basepair_hydrogen_bonds()
+        bt, _atoms, self.labels = NA._tables(focused_basepair_cutoffs, ideal_hydrogen_bonds)
+        weights = np.diff(batch.struct_off).astype(int).tolist()
+        self.parts = lpt_partition(weights, self.world)
+        self.mine = self.parts[self.rank]
+        self.sub = packing.select_structures(batch, self.mine)
+        self.eng = Engine.get(device)
+        self.torch = torch
+        mask = NA.category_mask(categories)
+        self.pinned = pin_batch(torch, self.sub)
+        self.pipe = Pipeline(self.eng, self.sub, self.pinned, bt, mask, n_chunks=max(1, min(n_chunks, len(self.mine))),
+                             labels=self.labels, want_hits=False) if len(self.mine) else None
+        # global nt index of every local nt (rows carry shard-local indices)
+        self.nt_map = torch.as_tensor(np.concatenate(
+            [np.arange(batch.struct_off[s], batch.struct_off[s + 1]) for s in self.mine] or [np.zeros(0, dtype=np.int64)]
+        ).astype(np.int32), device=self.eng.device)
+        self.rows_host = None
+
+    def run(self):
+        torch, dev = self.torch, self.eng.device
+        if self.pipe is not None:
+            out = self.pipe.run(to_host=False)
+            rows = out.rows_dev.clone()
+            if rows.shape[0]:                                  # shard-local nt indices -> indices of the whole batch
+                rows[:, 1] = self.nt_map[rows[:, 1].long()]
+                rows[:, 2] = self.nt_map[rows[:, 2].long()]
+            rs, rc, n_pairs = out.row_start_dev, out.row_count_dev, out.n_pairs
+        else:
+            rows = torch.zeros((0, 4), dtype=torch.int32, device=dev)
+            rs = rc = torch.zeros(0, dtype=torch.int32, device=dev)
+            n_pairs = 0
+        got = gather_rows(rows, rs, rc, self.mine, self.batch.n_structures, self.rank, self.world, scalars=(n_pairs,))
+        if got is None:
+            return None
+        rows_all, rs_all, rc_all, (pairs_all,) = got
+        from .tail import BatchAnnotations, ROW_DTYPE
+        nb = rows_all.shape[0]
+        if self.rows_host is None or self.rows_host.shape[0] < nb:
+            self.rows_host = torch.empty((int(nb * 1.2) + 1024, 4), dtype=torch.int32).pin_memory()
+        self.rows_host[:nb].copy_(rows_all, non_blocking=True)
+        rs_h, rc_h = rs_all.cpu(), rc_all.cpu()               # synchronises the stream the copies are on
+        torch.cuda.current_stream(dev).synchronize()
+        return BatchAnnotations(self.batch, self.rows_host[:nb].numpy().view(ROW_DTYPE).reshape(-1), rs_h.numpy(),
+                                rc_h.numpy(), self.labels, n_pairs=pairs_all)
+
+
+def annotate_batch_sharded(batch, categories, annotate_fn=None, rank=None, world_size=None, gather=True, **kw):
+    """Shard the structures of `batch` over the ranks (LPT on nt count), annotate the local shard, gather to rank 0.
+
+    Default (annotate_fn None): ShardedAnnotator - device pipeline per rank, rows gathered with NCCL; returns a
+    tail.BatchAnnotations over the whole batch on rank 0, None elsewhere.
+    With annotate_fn(sub_batch, categories) -> list of per-structure results (the host-side protocol, used by the
+    CPU tests with gloo): the per-structure results are gathered with gather_object in the original structure order;
+    rank 0 returns the full list, the others their local list (everyone the local list when gather=False)."""
+    if annotate_fn is None:
+        return ShardedAnnotator(batch, categories, rank=rank, world_size=world_size, **kw).run()
+    dist = _dist()
+    rank, world_size = _rank_world(rank, world_size)
     weights = np.diff(batch.struct_off).astype(int).tolist()
     parts = lpt_partition(weights, world_size)
     mine = parts[rank]
@@ -64,15 +200,34 @@ def annotate_batch_sharded(batch, categories, annotate_fn, rank=None, world_size
     return out
 
 
+# ------------------------------------------------------------------ discrepancy (C5)
+def triangle_blocks(N, n_parts, block=256):
+    """Ownership of the upper triangle of the N x N discrepancy matrix: row blocks of `block` rows dealt to the ranks
+    so that every rank gets the same number of tiles ON OR ABOVE the diagonal (row block b has ~ (nb - b) of them):
+    blocks are taken in pairs (b, nb - 1 - b), dealt cyclically.  A rank evaluates only the part of its row blocks
+    at or right of the diagonal (fr3d_discrepancy_all_vs_all with col0 = row0); the lower triangle is the mirror
+    (FR3D.py:439-441).  Returns per rank a list of (row0, row1)."""
+    nb = (N + block - 1) // block
+    parts = [[] for _ in range(n_parts)]
+    k = 0
+    lo, hi = 0, nb - 1
+    while lo <= hi:
+        r = k % n_parts
+        parts[r].append((lo * block, min(N, (lo + 1) * block)))
+        if hi != lo:
+            parts[r].append((hi * block, min(N, (hi + 1) * block)))
+        lo += 1
+        hi -= 1
+        k += 1
+    return [sorted(p) for p in parts]
+
+
 def all_vs_all_sharded(centers, rotations, compute_rows, rank=None, world_size=None, block=256):
-    """Row-block sharded all-vs-all discrepancy: `compute_rows(row0, row1) -> (row1-row0, N)` array is
-    called for this rank's blocks; slabs are gathered to rank 0 and assembled.  Rank 0 returns the
-    N x N matrix, others None."""
+    """Row-block sharded all-vs-all discrepancy (host protocol, used by the CPU tests): `compute_rows(row0, row1) ->
+    (row1-row0, N)` array is called for this rank's blocks; slabs are gathered to rank 0 and assembled.  Rank 0
+    returns the N x N matrix, others None.  The device form is geometry.discrepancy.all_vs_all_multi_gpu."""
     dist = _dist()
-    if rank is None:
-        rank = dist.get_rank() if dist.is_initialized() else 0
-    if world_size is None:
-        world_size = dist.get_world_size() if dist.is_initialized() else 1
+    rank, world_size = _rank_world(rank, world_size)
     N = len(centers)
     blocks = cyclic_row_blocks(N, world_size, block)
     slabs = [(r0, r1, np.asarray(compute_rows(r0, r1))) for r0, r1 in blocks[rank]]
