@@ -359,8 +359,10 @@ def main():
         out["gpu_launches"] = eng.launches - launches0
         out["ms_total"] = float(sum(a.elapsed_time(b) for a, b in step_ev))
         np_chk, nh_chk = eng.read_counts(plan)
-        assert np_chk == n_pairs and nh_chk == n_hits and eng.read_tail_counts(plan) == n_rows, \
-            "resident pass disagrees with the calibration pass"
+        nr_chk = eng.read_tail_counts(plan)
+        assert (np_chk, nh_chk, nr_chk) == (n_pairs, n_hits, n_rows), \
+            "resident pass (pairs, hits, rows) = %r disagrees with the calibration pass %r" % (
+                (np_chk, nh_chk, nr_chk), (n_pairs, n_hits, n_rows))
         out["worklists"] = plan.counters.cpu().tolist()
         out["classify_ms"] = float(np.mean([ev["classify0"].elapsed_time(ev["classify1"]) for ev in evs]))
         out["search_ms"] = float(np.mean([ev["search0"].elapsed_time(ev["classify0"]) for ev in evs]))

@@ -150,7 +150,7 @@ def load():
         lib.fr3d_init.argtypes = [C.c_int]
         lib.fr3d_upload_tables.argtypes = [C.POINTER(StaticTables)]
         lib.fr3d_frames_fit.argtypes = [C.POINTER(NtsStruct), vp, C.c_int, vp]
-        lib.fr3d_frames_fit_from.argtypes = [C.POINTER(NtsStruct), vp, i32, vp, C.c_int, vp]
+        lib.fr3d_frames_fit_from.argtypes = [C.POINTER(NtsStruct), vp, i32, vp, vp, C.c_int, vp]
         lib.fr3d_pair_search_workspace.argtypes = [i32]
         lib.fr3d_pair_search_workspace.restype = C.c_size_t
         lib.fr3d_pair_search.argtypes = [C.POINTER(NtsStruct), dbl, vp, C.c_size_t, vp, vp, vp, i64, vp, vp]

@@ -184,23 +184,26 @@ static int require_device(bool tables, int *sm_count) {
     return FR3D_OK;
 }
 
-int fr3d_frames_fit_from(const fr3d_nts_t *nts, const double *compact_base_xyz, int32_t compact_slots, int32_t *status,
-                         int place_h, void *stream) {
+int fr3d_frames_fit_from(const fr3d_nts_t *nts, const double *compact_base_xyz, int32_t compact_slots,
+                         const uint32_t *observed_mask, int32_t *status, int place_h, void *stream) {
     if (!nts) return fail(FR3D_E_ARG, "nts is NULL");
     if (compact_base_xyz && (compact_slots < 11 || compact_slots > FR3D_BASE_SLOTS))
         return fail(FR3D_E_ARG, "compact_slots must be in [11, 16] (every heavy base atom lies in slots 0..10)");
+    if (compact_base_xyz && (!observed_mask || observed_mask == nts->base_mask))
+        return fail(FR3D_E_ARG, "a compact plane needs its own observed_mask plane (not nts->base_mask, which is written)");
+    if (!compact_base_xyz) observed_mask = nullptr;
     if (int rc = require_device(true, nullptr)) return rc;
     if (nts->n_nt <= 0) return FR3D_OK;
     const int block = fr3d::FRAMES_WARPS * 32;
     const int grid = (nts->n_nt + block - 1) / block;
     fr3d::frames_fit_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(*nts, status, place_h, compact_base_xyz,
-                                                                                   compact_slots * 3);
+                                                                                   compact_slots * 3, observed_mask);
     CUDA_TRY(cudaGetLastError());
     return FR3D_OK;
 }
 
 int fr3d_frames_fit(const fr3d_nts_t *nts, int32_t *status, int place_h, void *stream) {
-    return fr3d_frames_fit_from(nts, nullptr, FR3D_BASE_SLOTS, status, place_h, stream);
+    return fr3d_frames_fit_from(nts, nullptr, FR3D_BASE_SLOTS, nullptr, status, place_h, stream);
 }
 
 size_t fr3d_pair_search_workspace(int32_t n_nt) {

@@ -23,16 +23,15 @@ constexpr int FRAMES_STRIDE = FR3D_BASE_SLOTS * 3 + 1;     // 49 doubles per row
 
 // the fit of one nt; xyz = its 16 x 3 slot block (a shared-memory row), std_xyz = the standard base coordinates.
 // Returns true if a slot below 8 was written (ideal-position copies of a modified residue).
-// keep_mask: bits of the incoming base_mask that are believed (all of them, or - when the atoms come from a compact
-// plane - only the slots that plane holds: the fit is then a pure function of the uploaded plane, also on a second
-// pass over records whose masks a first pass has already extended).
+// mask_in: the observed-atom mask the fit starts from - the record's own base_mask, or (atoms read from a compact
+// plane) the uploaded mask plane, which is never written: the fit is then a pure function of the upload and can be
+// repeated on records a first pass has already completed.
 __device__ __forceinline__ bool frames_fit_one(const fr3d_nts_t &nts, int32_t *__restrict__ status, int place_h, int n,
                                                double *xyz, const double (*std_xyz)[FR3D_BASE_SLOTS][3],
-                                               uint32_t keep_mask) {
+                                               uint32_t mask_in) {
     bool wrote_low = false;
     const int parent = nts.meta[n * FR3D_META_INTS + 0];
     const int flags = nts.meta[n * FR3D_META_INTS + 1];
-    const uint32_t mask_in = nts.base_mask[n] & keep_mask;
     uint32_t mask = mask_in & 0xFFFFu;
     // residues that already received their ideal-position copies hold averaged coordinates: fitting
     // them again would not reproduce the frame, so a second pass leaves them alone
@@ -158,12 +157,13 @@ __device__ __forceinline__ bool frames_fit_one(const fr3d_nts_t &nts, int32_t *_
     return wrote_low;
 }
 
-// src / src_cols: where the observed atoms are read from - nts.base_xyz itself (src == nullptr), or a compact plane
-// [n][src_cols / 3][3] holding only the first slots of every record (the upload keeps slots 0..10 when no hydrogen
-// is observed: they are placed here anyway); the full 16-slot record is then written to nts.base_xyz.
+// src_plane / src_cols / src_mask: where the observed atoms are read from - nts.base_xyz and nts.base_mask themselves
+// (nullptr), or a compact plane [n][src_cols / 3][3] holding only the first slots of every record (the upload keeps
+// slots 0..10 when no hydrogen sits beyond them: they are placed here anyway) with its own mask plane; the full
+// 16-slot record and the completed mask are then written to nts.base_xyz / nts.base_mask.
 __global__ void __launch_bounds__(FRAMES_WARPS * 32) frames_fit_kernel(fr3d_nts_t nts, int32_t *__restrict__ status,
                                                                        int place_h, const double *__restrict__ src_plane,
-                                                                       int src_cols) {
+                                                                       int src_cols, const uint32_t *__restrict__ src_mask) {
     __shared__ double s_std[FR3D_N_PARENTS][FR3D_BASE_SLOTS][3];
     __shared__ double s_rows[FRAMES_WARPS][32 * FRAMES_STRIDE];
     for (int item = threadIdx.x; item < FR3D_N_PARENTS * FR3D_BASE_SLOTS * 3; item += blockDim.x)
@@ -188,8 +188,9 @@ __global__ void __launch_bounds__(FRAMES_WARPS * 32) frames_fit_kernel(fr3d_nts_
     }
     __syncthreads();
     bool wrote_low = false;                                               // wrote a slot below 8 (ideal-position copies)
-    const uint32_t keep_mask = compact ? ((1u << (cols / 3)) - 1u) : 0xFFFFFFFFu;
-    if (n < nts.n_nt) wrote_low = frames_fit_one(nts, status, place_h, n, rows + lane * FRAMES_STRIDE, s_std, keep_mask);
+    if (n < nts.n_nt)
+        wrote_low = frames_fit_one(nts, status, place_h, n, rows + lane * FRAMES_STRIDE, s_std,
+                                   src_mask ? src_mask[n] : nts.base_mask[n]);
     __syncwarp();
     // copy back slots 8..15 (every hydrogen slot lies there: the parents have 8 to 11 heavy atoms), or whole rows
     // if some lane inserted ideal-position copies or the records came from a compact plane

@@ -111,10 +111,13 @@ class DeviceBatch(object):
             src = pinned[name] if pinned is not None else torch.from_numpy(_as_signed(getattr(batch, name)))
             if name == "base_xyz" and src.shape[1] < _lib.BASE_SLOTS:       # compact pinned form, see pin_batch:
                 # K1 reads the compact plane and writes the full 16-slot records (fr3d_frames_fit_from)
-                self.compact_base = (src.to(device, non_blocking=True), int(src.shape[1]))
+                self.compact_base = [src.to(device, non_blocking=True), int(src.shape[1]), None]
                 t[name] = torch.empty((batch.n, _lib.BASE_SLOTS, 3), dtype=src.dtype, device=device)
             else:
                 t[name] = src.to(device, non_blocking=True)
+        if self.compact_base is not None:        # the uploaded mask plane stays as it is; K1 writes the record's mask
+            self.compact_base[2] = t["base_mask"]
+            t["base_mask"] = torch.empty_like(t["base_mask"])
         self.t = t
         self.nts = _lib.NtsStruct(n_nt=batch.n, reserved=0, center=t["center"].data_ptr(), rot=t["rot"].data_ptr(),
                                   base_xyz=t["base_xyz"].data_ptr(), bb_xyz=t["bb_xyz"].data_ptr(),
@@ -182,8 +185,9 @@ class Engine(object):
     def _frames_fit(self, dbatch, status_ptr, place_h, st):
         compact = getattr(dbatch, "compact_base", None)
         if compact is not None:
-            _lib.check(self.lib.fr3d_frames_fit_from(C.byref(dbatch.nts), compact[0].data_ptr(), compact[1], status_ptr,
-                                                     1 if place_h else 0, st), "fr3d_frames_fit_from")
+            _lib.check(self.lib.fr3d_frames_fit_from(C.byref(dbatch.nts), compact[0].data_ptr(), compact[1],
+                                                     compact[2].data_ptr(), status_ptr, 1 if place_h else 0, st),
+                       "fr3d_frames_fit_from")
         else:
             _lib.check(self.lib.fr3d_frames_fit(C.byref(dbatch.nts), status_ptr, 1 if place_h else 0, st),
                        "fr3d_frames_fit")
@@ -468,8 +472,11 @@ class Pipeline(object):
                 ch.host_blob[o:o + nb].view(dt).view(shape).copy_(pinned[name][lo:hi])
                 view = ch.dev_blob[o:o + nb].view(dt).view(shape)
                 if name == "base_xyz" and compact:
-                    ch.compact_base = (view, int(shape[1]))
+                    ch.compact_base = [view, int(shape[1]), None]
                     ch.dev[name] = torch.empty((n, _lib.BASE_SLOTS, 3), dtype=dt, device=dev)
+                elif name == "base_mask" and compact:
+                    ch.compact_base[2] = view          # the uploaded (observed) masks; K1 writes the record's own
+                    ch.dev[name] = torch.empty((n,), dtype=dt, device=dev)
                 else:
                     ch.dev[name] = view
             if ch.ident is not None:
@@ -561,7 +568,8 @@ class Pipeline(object):
                 else:
                     eng.add_tail_buffers(ch.plan, tail[0], tail[1], row_cap=nrows + 1024)
                 with torch.cuda.stream(ch.stream):
-                    ch.dev_blob.copy_(ch.host_blob, non_blocking=True)     # K1 has extended the masks in place
+                    if ch.compact_base is None:
+                        ch.dev_blob.copy_(ch.host_blob, non_blocking=True)     # K1 has completed the records in place
                     self._launch(ch)
             ch.n_hits, ch.n_rows = nhits, nrows
             n_pairs += npairs

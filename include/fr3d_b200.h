@@ -161,10 +161,12 @@ int fr3d_upload_tables(const fr3d_static_tables_t *host_tables);   /* to the cur
  * base_mask (hydrogen bits + FR3D_MASK_HAS_FRAME) and status[n] (0 ok, -1 no parent, -2 <3 atoms). */
 int fr3d_frames_fit(const fr3d_nts_t *nts, int32_t *status, int place_h, void *stream);
 /* Same, with the observed base atoms read from a compact plane [n][compact_slots][3] (11 <= compact_slots <= 16:
- * the first slots of every record; an upload that carries no observed hydrogens keeps slots 0..10 only) instead of
- * nts->base_xyz, to which the full 16-slot records are written.  compact_base_xyz == NULL: fr3d_frames_fit. */
-int fr3d_frames_fit_from(const fr3d_nts_t *nts, const double *compact_base_xyz, int32_t compact_slots, int32_t *status,
-                         int place_h, void *stream);
+ * the first slots of every record; an upload without atoms in slots 11..15 keeps slots 0..10 only) and their
+ * presence bits from observed_mask [n] (same bit layout as base_mask; a plane of its own, never written) instead of
+ * nts->base_xyz / nts->base_mask, to which the full 16-slot records and the completed masks are written: a pure
+ * function of the upload, repeatable.  compact_base_xyz == NULL: fr3d_frames_fit. */
+int fr3d_frames_fit_from(const fr3d_nts_t *nts, const double *compact_base_xyz, int32_t compact_slots,
+                         const uint32_t *observed_mask, int32_t *status, int place_h, void *stream);
 
 /* K2+K3. Replaces make_nt_cubes_half (NA:410-443) and the loop/screens of
  * annotate_nt_nt_interactions (NA:661-724): oriented candidate pairs with 2 <= d <= 12.

@@ -382,6 +382,17 @@ def glycosidic(nt):
     return np.array([])
 
 
+# Adversarial-test support (tests/adversarial.py): when PROBE is a list, every threshold comparison of the rules
+# appends (name, value - threshold), so that a decision boundary found by bisection can be attributed to the
+# threshold whose margin changes sign there.  Recording only; no rule reads it.
+PROBE = None
+
+
+def _probe(name, margin):
+    if PROBE is not None:
+        PROBE.append((name, float(margin)))
+
+
 def translate_rotate_point(nt, point):
     """NA:1263-1275: (point - centre) . U as a row vector."""
     return list(np.dot(np.subtract(point, nt.base_center), nt.rotation))
@@ -436,6 +447,7 @@ def candidate_pairs(nts, cutoff=nt_nt_screen_distance):
                     if len(nt2.center("base")) < 3:
                         continue
                     displacement = abs(nt2.base_center - nt1.base_center)
+                    _probe("search |dx|,|dy|,|dz| vs 12", max(displacement) - cutoff)
                     if displacement[0] > cutoff or displacement[1] > cutoff or displacement[2] > cutoff:
                         continue
                     if nt1.number == nt2.number and nt1.sequence == nt2.sequence and nt1.chain == nt2.chain \
@@ -443,6 +455,8 @@ def candidate_pairs(nts, cutoff=nt_nt_screen_distance):
                             and nt1.alt_id != nt2.alt_id:
                         continue
                     d = np.linalg.norm(displacement)
+                    _probe("search d vs 12", d - cutoff)
+                    _probe("search d vs 2", d - 2)
                     if d > cutoff:
                         continue
                     if d < 2:
@@ -453,8 +467,10 @@ def candidate_pairs(nts, cutoff=nt_nt_screen_distance):
 
 # ----------------------------------------------------------------- rules ----
 
-def _inside(lines, x, y):
+def _inside(lines, x, y, what=None):
     for a, b, c in lines:
+        if what is not None:
+            _probe(what, a * x + b * y + c)
         if not (a * x + b * y + c > 0):
             return False
     return True
@@ -486,6 +502,9 @@ def check_base_oxygen_stack_rings(nt1, nt2, parent1):
         if len(p) == 3:
             x, y, z = translate_rotate_point(nt1, p)
             oxygen_points.append([x, y, z, oxygen])
+            _probe("sO |z| vs 2", abs(z) - 2)
+            _probe("sO |z| vs 3.6", abs(z) - near_z_cutoff)
+            _probe("sO |z| vs 3.5", abs(z) - true_z_cutoff)
             if abs(z) < 2:
                 continue
             ring5 = False
@@ -493,12 +512,13 @@ def check_base_oxygen_stack_rings(nt1, nt2, parent1):
             if abs(z) < near_z_cutoff and rings is not None:
                 if rings["divider"] is not None:
                     a, b, c = rings["divider"]
+                    _probe("sO ring divider", a * x + b * y + c)
                     if a * x + b * y + c > 0:
-                        ring5 = _inside(rings["ring5"], x, y)
+                        ring5 = _inside(rings["ring5"], x, y, "sO ring5 line")
                     else:
-                        ring6 = _inside(rings["ring6"], x, y)
+                        ring6 = _inside(rings["ring6"], x, y, "sO ring6 line")
                 else:
-                    ring6 = _inside(rings["ring6"], x, y)
+                    ring6 = _inside(rings["ring6"], x, y, "sO ring6 line")
             if ring5 or ring6:
                 if abs(z) < true_z_cutoff:
                     true_found = True
@@ -554,16 +574,18 @@ def check_base_oxygen_stack_rings(nt1, nt2, parent1):
 
 def _in_ellipse(e, x, y):
     a, b, cx, cy, r = e
+    _probe("sO near-ring ellipse", a * (x - cx) ** 2 + b * (x - cx) * (y - cy) + (y - cy) ** 2 - r)
     return a * (x - cx) ** 2 + b * (x - cx) * (y - cy) + (y - cy) ** 2 < r
 
 
 def check_convex_hull_atoms(x, y, z, parent):
     """NA:1475-1528."""
+    _probe("stacking atom |z| vs 4.5", abs(z) - 4.5)
     if abs(z) < 4.5:
         hull = PLANES["hull"].get(_ring_parent(parent))
         if hull is None:
             return False
-        return _inside(hull, x, y)
+        return _inside(hull, x, y, "stacking hull line")
     return False
 
 
@@ -588,6 +610,8 @@ def return_overlap(atom_names, nt1, nt2, parent):
                 maxz = z
             if inside:
                 overlap = True
+    _probe("stacking atoms on both sides (max z)", maxz)
+    _probe("stacking atoms on both sides (min z)", minz)
     if maxz > 0 and minz < 0:
         return False, [-100, -100, -100]
     if overlap:
@@ -645,6 +669,12 @@ def check_base_base_stacking(nt1, nt2, parent1, parent2):
         if reverse:
             interaction, interaction_reversed = interaction_reversed, interaction
         min_distance = calculate_base_min_distances(nt1, nt2)
+        _probe("stacking min distance vs 4", abs(min_distance) - true_z_cutoff)
+        _probe("stacking min distance vs 1", abs(min_distance) - 1)
+        _probe("stacking |normal_Z| vs 0.6", abs(normal_Z) - 0.6)
+        _probe("stacking |normal_Z| vs 0.5", abs(normal_Z) - 0.5)
+        _probe("stacking normal_Z sign", normal_Z)
+        _probe("stacking vertical offset sign", mvd)
         if abs(min_distance) < true_z_cutoff and abs(min_distance) > 1 and abs(normal_Z) > 0.6 \
                 and nt2on1 and nt1on2:
             interaction = interaction.replace("n", "")
@@ -675,6 +705,7 @@ def check_sugar_ribose(nt1, nt2, parent1):
     o2 = nt2.center(nt2.mapped("O2'"))
     if not len(o2) == 3:
         return ""
+    _probe("SR O2'-O2' vs 3.8", np.linalg.norm(np.subtract(o1, o2)) - 3.8)
     if np.linalg.norm(np.subtract(o1, o2)) > 3.8:
         return ""
     if parent1 in ['A', 'G']:
@@ -686,15 +717,18 @@ def check_sugar_ribose(nt1, nt2, parent1):
     if not len(base_point) == 3:
         return ""
     displ = np.subtract(base_point, o2)
+    _probe("SR base atom-O2' vs 3.8", np.linalg.norm(displ) - 3.8)
     if np.linalg.norm(displ) > 3.8:
         return ""
     z = abs(float(np.dot(displ, nt1.rotation[:, 2])))
+    _probe("SR height vs 2.0", z - 2.0)
     if z > 2.0:
         return ""
     p0, p1 = nt1.center(nt1.mapped("C1'")), nt1.center(nt1.mapped("C2'"))
     p2, p3 = nt2.center(nt2.mapped("C2'")), nt2.center(nt2.mapped("C1'"))
     if len(p0) == 3 and len(p1) == 3 and len(p2) == 3 and len(p3) == 3:
         angle = torsion_angle(p0, p1, p2, p3)
+        _probe("SR |torsion| vs 90", abs(angle) - 90)
         return 'cSR' if abs(angle) > 90 else 'tSR'
     return ""
 
@@ -743,6 +777,7 @@ def check_base_backbone_interactions(nt1, nt2, previousO3, parent1):
         ph_ox.append(previousO3)
     P = nt2.center(nt2.mapped("P"))
     if P.any():
+        _probe("BPh P off-plane vs 4.5", abs(translate_rotate_point(nt1, P)[2]) - 4.5)
         if abs(translate_rotate_point(nt1, P)[2]) > 4.5:
             ph_ox = []
     cutoff = nCutoff = None
@@ -759,6 +794,10 @@ def check_base_backbone_interactions(nt1, nt2, previousO3, parent1):
                 if ang:
                     dist = float(np.linalg.norm(np.subtract(M, ox)))
                     if dist:
+                        _probe("BPh angle vs 130", ang - angleLimit)
+                        _probe("BPh angle vs 110", ang - nAngleLimit)
+                        _probe("BPh distance vs 4.0 (C) / 3.5 (N)", dist - cutoff)
+                        _probe("BPh distance vs 4.5 (C) / 4.0 (N)", dist - nCutoff)
                         if ang > angleLimit and dist < cutoff:
                             q = (cutoff - dist) + (ang - angleLimit) / 20.0
                             true_ph.append((-q, site[2], i))
@@ -772,6 +811,10 @@ def check_base_backbone_interactions(nt1, nt2, previousO3, parent1):
                 if ang:
                     dist = float(np.linalg.norm(np.subtract(M, ox)))
                     if dist:
+                        _probe("BR angle vs 130", ang - angleLimit)
+                        _probe("BR angle vs 110", ang - nAngleLimit)
+                        _probe("BR distance vs 4.0 (C) / 3.5 (N)", dist - cutoff)
+                        _probe("BR distance vs 4.5 (C) / 4.0 (N)", dist - nCutoff)
                         if ang > angleLimit and dist < cutoff:
                             q = (cutoff - dist) + (ang - angleLimit) / 20.0
                             true_r.append((-q, site[3]))
@@ -830,10 +873,13 @@ def check_coplanar(nt1, nt2, pair_data):
     pair_data["coplanar_value"] = None
     gap12 = calculate_basepair_gap(nt1, nt2)
     pair_data["gap12"] = gap12
+    _probe("coplanar gap12 vs 1.5179", gap12 - 1.5179)
     if gap12 >= 1.5179:
         return pair_data
     min_distance = calculate_base_min_distances(nt1, nt2)
     pair_data["min_distance"] = min_distance
+    _probe("coplanar min distance vs 3.4589", min_distance - 3.4589)
+    _probe("coplanar min distance vs 2.4589", min_distance - 2.4589)
     if min_distance >= 3.4589:
         return pair_data
     if min_distance >= 2.4589 and nt1.sequence in ['A', 'C', 'G', 'U'] and nt2.sequence in ['A', 'C', 'G', 'U']:
@@ -841,15 +887,19 @@ def check_coplanar(nt1, nt2, pair_data):
     cd = np.subtract(nt1.base_center, nt2.base_center)
     cd = cd / np.linalg.norm(cd)
     dot1 = abs(float(np.dot(cd, nt1.rotation[:, 2])))
+    _probe("coplanar |c.n1| vs 0.3381", dot1 - 0.3381)
     if dot1 >= 0.3381:
         return pair_data
     dot2 = abs(float(np.dot(cd, nt2.rotation[:, 2])))
+    _probe("coplanar |c.n2| vs 0.3381", dot2 - 0.3381)
     if dot2 >= 0.3381:
         return pair_data
     dot3 = abs(float(np.dot(nt1.rotation[:, 2], nt2.rotation[:, 2])))
+    _probe("coplanar |n1.n2| vs 0.7757", dot3 - 0.7757)
     if dot3 <= 0.7757:
         return pair_data
     gap21 = calculate_basepair_gap(nt2, nt1)
+    _probe("coplanar gap21 vs 1.5179 (value only)", gap21 - 1.5179)
     # note: the reference does NOT store gap21 into pair_data here (NA:2115), so
     # check_basepair_cutoffs recomputes it (same value).
 
@@ -915,10 +965,12 @@ def check_basepair_cutoffs(nt1, nt2, pair_data, cutoffs, hydrogen_bonds):
     """NA:2364-2759 with datapoint = None.  Returns (LW, subcategory, quality)."""
     displ = pair_data["displ12"]
     quality = {}
+    _probe("basepair |z| vs 3.6", abs(displ[2]) - 3.6)
     if abs(displ[2]) > 3.6:
         return "", "", quality
     M = np.dot(nt1.rotation.T, nt2.rotation)
     normal_Z = M[2, 2]
+    _probe("basepair normal_Z sign", normal_Z)
     sgn = 1 if normal_Z > 0 else -1
     cmax = near_discrepancy_cutoff
     ok = []
@@ -945,6 +997,11 @@ def check_basepair_cutoffs(nt1, nt2, pair_data, cutoffs, hydrogen_bonds):
                 continue
             cd += 3 * max(0, cut['normalmin'] - normal_Z)
             cd += 3 * max(0, normal_Z - cut['normalmax'])
+            _probe("basepair box, cutoff_distance vs 1.0 (before angle)", cd - cmax)
+            if PROBE is not None:
+                for nm, v in (("x", displ[0]), ("y", displ[1]), ("z", displ[2]), ("normal", normal_Z)):
+                    _probe("basepair box edge %smin" % nm, v - cut[nm + 'min'])
+                    _probe("basepair box edge %smax" % nm, v - cut[nm + 'max'])
             if cd < cmax:
                 ok.append((inter, sub, cut, cd))
     if len(ok) == 0:
@@ -959,6 +1016,9 @@ def check_basepair_cutoffs(nt1, nt2, pair_data, cutoffs, hydrogen_bonds):
             cd += 0.05 * max(0, angle - cut['anglemax'])
         else:
             cd += 0.05 * min(max(0, cut["anglemin"] - angle), max(0, angle - cut["anglemax"]))
+        _probe("basepair box, cutoff_distance vs 1.0 (with angle)", cd - cmax)
+        _probe("basepair box angle min", angle - cut['anglemin'])
+        _probe("basepair box angle max", angle - cut['anglemax'])
         if cd < cmax:
             ok2.append((inter, sub, cut, cd))
     if len(ok2) == 0:
@@ -974,6 +1034,10 @@ def check_basepair_cutoffs(nt1, nt2, pair_data, cutoffs, hydrogen_bonds):
     for inter, sub, cut, cd in ok2:
         if cut['gapmax'] > 0.1:
             cd += 4 * max(0, max(pair_data["gap12"], pair_data["gap21"]) - cut['gapmax'])
+            _probe("basepair gap vs gapmax", max(pair_data["gap12"], pair_data["gap21"]) - cut['gapmax'])
+        _probe("basepair cutoff_distance vs 1.0 (with gap)", cd - near_discrepancy_cutoff)
+        _probe("basepair min distance vs 4.1", pair_data['min_distance'] - 4.1)
+        _probe("basepair min distance vs 3.75", pair_data['min_distance'] - 3.75)
         one_hbond = False
         if inter == 'cSs' and pair_data['parent2'] in ['C', 'U']:
             one_hbond = True

@@ -469,6 +469,37 @@ def test_device_tail_in_the_pipeline_and_capacity_reruns():
     assert n_pairs == ref.n_pairs and len(ex["rows"]) == ref.n_rows
 
 
+def test_repeated_passes_over_resident_records_are_identical():
+    """bench.py's resident loop: K1..K4 + tail run again and again over the same device records.  K1 reads the
+    uploaded compact base plane and its observed-mask plane and writes the full records elsewhere, so every pass
+    must reproduce the first one bit for bit (a K1 that took its own placed hydrogens for observed ones would not)."""
+    import torch
+    from fr3d_python_b200 import tail as tailmod
+    from fr3d_python_b200.engine import DeviceBatch, DeviceIdent, HIT_DTYPE, pin_batch
+    batch = synthetic.make_structure_batch(synthetic.pack_base(), 50, seed0=4000)
+    eng = Engine.get()
+    bt, atoms, labels = NA._tables(NA._default_focused(ALL9['basepair']), NA.load_ideal_basepair_hydrogen_bonds())
+    mask = NA.category_mask(ALL9)
+    pinned = pin_batch(torch, batch)
+    assert pinned["base_xyz"].shape[1] == 11
+    ident = DeviceIdent(torch, eng.device, tailmod.tail_ident(batch))
+    plan = eng.make_plan(batch.n, tail=(ident.n_struct, ident.n_ends))
+    db = DeviceBatch(torch, eng.device, batch, pinned)
+    key = lambda h: np.lexsort((h['slot'], h['j'], h['i'], h['rank']))
+    first = None
+    for it in range(3):
+        eng.run_plan(db, plan, bt, mask, fit_frames=True, tail=(ident, labels))
+        n_pairs, n_hits = eng.read_counts(plan)
+        h = plan.hits[:n_hits * 32].cpu().numpy().view(HIT_DTYPE)
+        state = (n_pairs, h[key(h)].tobytes(), eng.read_tail_counts(plan), db.t["base_xyz"].cpu().numpy().tobytes(),
+                 db.t["base_mask"].cpu().numpy().tobytes())
+        if first is None:
+            first = state
+        assert state == first, "pass %d differs from the first" % it
+    ref_hits, ref_pairs, _ = eng.annotate_batch(batch, bt, mask)
+    assert ref_pairs == first[0] and ref_hits[key(ref_hits)].tobytes() == first[1]
+
+
 def test_device_tail_edge_cases(golden):
     """Empty structures inside a batch, a structure without any hit, multi-model / symmetry / insertion-code
     identities (covalent links per model + operator + chain), and the ranges the device tail refuses."""
