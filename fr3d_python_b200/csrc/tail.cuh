@@ -59,6 +59,21 @@ struct TailWs {
 
 typedef unsigned long long tail_u64;
 
+// -DFR3D_TAIL_PROFILE: thread 0 of every block adds the cycles of each phase to tc[8 + phase] (tools/profile_tail.py)
+#ifdef FR3D_TAIL_PROFILE
+#define TAIL_PHASE(k)                                                                 \
+    do {                                                                              \
+        __syncthreads();                                                              \
+        if (threadIdx.x == 0) {                                                       \
+            const long long now_ = clock64();                                         \
+            atomicAdd((tail_u64 *)&tc[8 + (k)], (tail_u64)(now_ - phase_t0));         \
+            phase_t0 = now_;                                                          \
+        }                                                                             \
+    } while (0)
+#else
+#define TAIL_PHASE(k)
+#endif
+
 __device__ __forceinline__ int tail_find_struct(const int32_t *__restrict__ off, int n_struct, int nt) {
     int lo = 0, hi = n_struct;                    // largest s with off[s] <= nt
     while (hi - lo > 1) {
@@ -253,6 +268,9 @@ tail_structure_kernel(fr3d_nts_t nts, fr3d_tail_ident_t id, fr3d_tail_tables_t t
         __syncthreads();
         const int s = s_struct;
         if (s >= id.n_struct) break;
+#ifdef FR3D_TAIL_PROFILE
+        long long phase_t0 = clock64();
+#endif
         const int lo = id.struct_off[s], n = id.struct_off[s + 1] - lo;
         const int hb = ws.seg_off[s], H = ws.seg_off[s + 1] - hb;
         const int base = index_offset + lo;                                  // hit.i - base = position in the structure
@@ -293,9 +311,11 @@ tail_structure_kernel(fr3d_nts_t nts, fr3d_tail_ident_t id, fr3d_tail_tables_t t
             for (int i = tid; i < len; i += T) ws.ends[eo + i] = i;
         }
 
+        TAIL_PHASE(0);
         // ---- the reference's visit order
         tail_block_sort(hkey, hval, H, s_key, s_val);
 
+        TAIL_PHASE(1);
         // ---- walk: sequence number 2p + k for the k-th thing hit p records
         for (int p = tid; p < H; p += T) {
             const uint32_t hidx = hval[p];
@@ -330,6 +350,7 @@ tail_structure_kernel(fr3d_nts_t nts, fr3d_tail_ident_t id, fr3d_tail_tables_t t
         __syncthreads();
         const int nent = s_nent;
 
+        TAIL_PHASE(2);
         // ---- unit_id_to_basepairs in iteration order: nts by first appearance, entries by sequence (NA:1001-1013)
         for (int e = tid; e < nent; e += T) {
             const tail_u64 k = ekey[e];
@@ -366,6 +387,7 @@ tail_structure_kernel(fr3d_nts_t nts, fr3d_tail_ident_t id, fr3d_tail_tables_t t
         }
         __syncthreads();
 
+        TAIL_PHASE(3);
         // ---- check_for_two_interactions_on_same_edge (NA:528-632): order dependent, one thread, conflicts are rare
         if (tid == 0 && !s_err) {
             const int nmulti = s_nmulti;
@@ -416,6 +438,7 @@ tail_structure_kernel(fr3d_nts_t nts, fr3d_tail_ident_t id, fr3d_tail_tables_t t
         }
         __syncthreads();
 
+        TAIL_PHASE(4);
         // ---- emission (NA:1026-1044): the first entry of an unordered pair in iteration order, unless removed
         for (int q = tid; q < nent; q += T) {
             const int fl = e_flag[q];
@@ -441,6 +464,7 @@ tail_structure_kernel(fr3d_nts_t nts, fr3d_tail_ident_t id, fr3d_tail_tables_t t
         __syncthreads();
         const int napp = s_napp;
 
+        TAIL_PHASE(5);
         // ---- nested cWW pairs (NA:1077-1131): candidates keyed (chain, span, start), greedy in that order per chain
         tail_u64 *nkey = hkey;           // the hit keys are no longer needed
         uint32_t *nval = hval;
@@ -488,6 +512,7 @@ tail_structure_kernel(fr3d_nts_t nts, fr3d_tail_ident_t id, fr3d_tail_tables_t t
         }
         __syncthreads();
 
+        TAIL_PHASE(6);
         // ---- crossing numbers (NA:1146-1169) and row counts
         int my_rows = 0;
         for (int k = tid; k < napp; k += T) {
@@ -506,6 +531,7 @@ tail_structure_kernel(fr3d_nts_t nts, fr3d_tail_ident_t id, fr3d_tail_tables_t t
             across[k] = crossing;
             my_rows += 1 + (int)(tb.labels[alab[k]].flags & 1u);
         }
+        TAIL_PHASE(7);
         // ---- label ranks by first appearance, then the rows in append order
         for (int l = tid; l < n_labels; l += T) {
             const uint32_t f = s_lfirst[l];
@@ -521,6 +547,7 @@ tail_structure_kernel(fr3d_nts_t nts, fr3d_tail_ident_t id, fr3d_tail_tables_t t
         }
         tail_block_sort(akey, aval, napp, s_key, s_val);
 
+        TAIL_PHASE(8);
         // ---- covalent links (NA:1181-1210): nts by (model symmetry chain, index), successive keys of one string
         tail_u64 *ckey = ws.ckey + lo;
         uint32_t *cval = ws.cval + lo;
@@ -546,6 +573,7 @@ tail_structure_kernel(fr3d_nts_t nts, fr3d_tail_ident_t id, fr3d_tail_tables_t t
             gstart[r] = e;
             my_rows += cnt;
         }
+        TAIL_PHASE(9);
         int total_rows;
         tail_block_scan(my_rows, s_w, total_rows);
         __syncthreads();
@@ -597,6 +625,7 @@ tail_structure_kernel(fr3d_nts_t nts, fr3d_tail_ident_t id, fr3d_tail_tables_t t
             }
             running += total;
         }
+        TAIL_PHASE(10);
     }
 }
 

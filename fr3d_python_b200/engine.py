@@ -201,7 +201,7 @@ class Engine(object):
         return status
 
     # ---------------------------------------------------------------- plans
-    def make_plan(self, n_nt, pair_cap=None, hit_cap=None, tail=None, row_cap=None):
+    def make_plan(self, n_nt, pair_cap=None, hit_cap=None, tail=None, row_cap=None, row_out=None):
         """Pre-allocate every device buffer one pass over an n_nt batch needs, so that the pass
         itself is launches only (no allocation, no host sync).  tail = (n_struct, n_ends): also the buffers of the
         device tail (fr3d_annotation_tail)."""
@@ -225,10 +225,12 @@ class Engine(object):
         p.status = torch.zeros(max(n_nt, 1), dtype=torch.int32, device=dev)
         p.tail = None
         if tail is not None:
-            self.add_tail_buffers(p, tail[0], tail[1], row_cap)
+            self.add_tail_buffers(p, tail[0], tail[1], row_cap, out=row_out)
         return p
 
-    def add_tail_buffers(self, p, n_struct, n_ends, row_cap=None):
+    def add_tail_buffers(self, p, n_struct, n_ends, row_cap=None, out=None):
+        """out = (rows uint8 [16 row_cap], row_start int32 [n_struct], row_count int32 [n_struct], tcounters int64
+        [32]): caller-owned output tensors (e.g. views of a buffer a collective sends) instead of new ones."""
         torch, dev = self.torch, self.device
         if row_cap is None:
             row_cap = 3 * p.hit_cap + 2 * p.n_nt + 1024      # ~2.2 rows per hit + one covalent row per nt
@@ -236,10 +238,15 @@ class Engine(object):
         p.row_cap = int(row_cap)
         p.tws_bytes = int(self.lib.fr3d_tail_workspace(p.hit_cap, p.n_nt, p.tail[0], p.tail[1]))
         p.tws = torch.empty(p.tws_bytes, dtype=torch.uint8, device=dev)
+        p.external_rows = out is not None
+        if out is not None:
+            p.rows, p.row_start, p.row_count, p.tcounters = out
+            assert p.rows.numel() >= 16 * p.row_cap and p.row_start.numel() >= p.tail[0] and p.tcounters.numel() >= 32
+            return
         p.rows = torch.empty(p.row_cap * 16, dtype=torch.uint8, device=dev)
         p.row_start = torch.empty(max(p.tail[0], 1), dtype=torch.int32, device=dev)
         p.row_count = torch.empty(max(p.tail[0], 1), dtype=torch.int32, device=dev)
-        p.tcounters = torch.zeros(4, dtype=torch.int64, device=dev)
+        p.tcounters = torch.zeros(32, dtype=torch.int64, device=dev)      # [0..3] see fr3d_annotation_tail; the rest: profiling builds
 
     def run_plan(self, dbatch, plan, boxtable, category_mask, fit_frames=True, events=None, index_offset=0, tail=None):
         """K1 -> K2/K3 -> K4 [-> device tail] on the current stream, asynchronously.  `events` (dict) receives
@@ -420,7 +427,10 @@ class Pipeline(object):
     the hit records are then only copied back when want_hits is set."""
 
     def __init__(self, engine, batch, pinned, boxtable, category_mask, n_chunks=4, pair_cap=None, hit_cap=None,
-                 n_streams=3, labels=None, want_hits=None, row_cap=None):
+                 n_streams=3, labels=None, want_hits=None, row_cap=None, chunk_caps=None, row_out=None):
+        """chunk_caps: per chunk (pair_cap, hit_cap, row_cap) instead of the proportional split of pair_cap / hit_cap /
+        row_cap; row_out(k, n_struct, row_cap) -> (rows, row_start, row_count, tcounters): caller-owned output tensors
+        of chunk k (see Engine.add_tail_buffers), for enqueue() + a collective."""
         torch = engine.torch
         self.eng, self.batch, self.pinned, self.bt, self.mask = engine, batch, pinned, boxtable, category_mask
         self.labels = labels
@@ -495,8 +505,11 @@ class Pipeline(object):
             pc = int((pair_cap or (12 * batch.n + 1024)) * frac * 1.15) + 4096
             hc = int((hit_cap or (12 * batch.n + 1024)) * frac * 1.15) + 4096
             rc = (int(row_cap * frac * 1.15) + 4096) if row_cap else None
+            if chunk_caps is not None:
+                pc, hc, rc = chunk_caps[k]
+            ro = row_out(k, ch.ident.n_struct, rc) if (row_out is not None and ch.ident is not None) else None
             ch.plan = engine.make_plan(n, pc, hc, tail=(ch.ident.n_struct, ch.ident.n_ends) if ch.ident else None,
-                                       row_cap=rc)
+                                       row_cap=rc, row_out=ro)
             ch.counters_host = torch.zeros(12, dtype=torch.int64).pin_memory()
             ch.ev = torch.cuda.Event()
             self.chunks.append(ch)
@@ -522,8 +535,28 @@ class Pipeline(object):
         eng.run_plan(ch, ch.plan, self.bt, self.mask, fit_frames=True, index_offset=ch.lo, tail=tail)
         ch.counters_host[:8].copy_(ch.plan.counters, non_blocking=True)
         if tail is not None:
-            ch.counters_host[8:].copy_(ch.plan.tcounters, non_blocking=True)
+            ch.counters_host[8:].copy_(ch.plan.tcounters[:4], non_blocking=True)
         ch.ev.record(ch.stream)
+
+    def enqueue(self, upload=True):
+        """Issue one pass - per chunk: H2D (unless upload is False: the records of the previous pass are still in
+        HBM), K1..K4, tail - on the chunk streams and make the CURRENT stream wait for
+        all of it; no host synchronisation, nothing copied back.  For callers that own the output buffers (row_out)
+        and follow up with a collective on the current stream; capacities are theirs to check (plan.counters,
+        plan.tcounters travel with the results)."""
+        eng, torch = self.eng, self.eng.torch
+        main = torch.cuda.current_stream(eng.device)
+        start = torch.cuda.Event()
+        start.record(main)
+        for ch in self.chunks:
+            ch.stream.wait_event(start)
+            with torch.cuda.stream(ch.stream):
+                if upload or (ch.compact_base is None):        # in-place records are completed by K1: always re-upload
+                    ch.dev_blob.copy_(ch.host_blob, non_blocking=True)
+                tail = (ch.ident, self.labels) if ch.ident is not None else None
+                eng.run_plan(ch, ch.plan, self.bt, self.mask, fit_frames=True, index_offset=ch.lo, tail=tail)
+                ch.ev.record(ch.stream)
+            main.wait_event(ch.ev)
 
     def run(self, to_host=True):
         """One pass.  Returns a PipelineResult: n_pairs, n_hits, and (with labels) rows / row_start / row_count -
@@ -559,6 +592,10 @@ class Pipeline(object):
                 if not over and (ch.ident is None or nrows <= ch.plan.row_cap):
                     break
                 # capacity exceeded: new buffers with the exact counts, this chunk again (its input is still on the device)
+                if getattr(ch.plan, "external_rows", False):
+                    raise _lib.Fr3dError("pipeline chunk capacity exceeded (pairs %d/%d, hits %d/%d, rows %d/%d) with "
+                                         "caller-owned row buffers" % (npairs, ch.plan.pair_cap, nhits, ch.plan.hit_cap,
+                                                                       nrows, ch.plan.row_cap))
                 regrow = True
                 tail = (ch.ident.n_struct, ch.ident.n_ends) if ch.ident is not None else None
                 if over:

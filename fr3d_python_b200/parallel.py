@@ -108,17 +108,27 @@ def gather_rows(rows, row_start, row_count, mine, n_structures, rank=None, world
     return torch.cat(out_rows), rs, rc, [int(v) for v in heads_h[:, 2:].sum(dim=0)]
 
 
+HDR_INTS = 64          # per chunk block: 32 int64 of tail counters; [4..11] hold a copy of the search / classify counters
+
+
 class ShardedAnnotator(object):
     """ONE batch annotated by all ranks (BASELINE configs[3]): structures are dealt to the ranks by LPT on their nt
     count, every rank runs engine.Pipeline (K1..K4 + device tail) on its shard, the final rows are gathered on the
-    devices (NCCL) and rank 0 copies them to the host once.  All buffers are set up in the constructor; run() is
-    one pass and returns a tail.BatchAnnotations over the WHOLE batch on rank 0 (None elsewhere)."""
+    devices (one NCCL gather of a fixed-size block per rank) and rank 0 copies them to the host once.
+
+    Every rank owns ONE device block laid out per pipeline chunk as [counters | row_start | row_count | rows]; the
+    tail kernels write their output straight into it (no packing pass), the block is the send buffer of the gather,
+    and rank 0's receive buffer goes to pinned host memory in one copy, where the result object indexes it in place.
+    Block sizes are agreed once in the constructor (a calibration pass + one all_reduce(MAX)), so a pass needs no
+    host synchronisation before the final copy.  run() returns a tail.BatchAnnotations over the WHOLE batch on
+    rank 0 (None elsewhere)."""
 
     def __init__(self, batch, categories, focused_basepair_cutoffs=None, ideal_hydrogen_bonds=None, rank=None,
                  world_size=None, device=None, n_chunks=2):
         import torch
         from .classifiers import NA_pairwise_interactions as NA
         from .engine import Engine, Pipeline, pin_batch
+        dist = _dist()
         self.rank, self.world = _rank_world(rank, world_size)
         self.batch = batch
         if not focused_basepair_cutoffs:
@@ -132,42 +142,114 @@ class ShardedAnnotator(object):
         self.sub = packing.select_structures(batch, self.mine)
         self.eng = Engine.get(device)
         self.torch = torch
+        dev = self.eng.device
         mask = NA.category_mask(categories)
         self.pinned = pin_batch(torch, self.sub)
-        self.pipe = Pipeline(self.eng, self.sub, self.pinned, bt, mask, n_chunks=max(1, min(n_chunks, len(self.mine))),
-                             labels=self.labels, want_hits=False) if len(self.mine) else None
-        # global nt index of every local nt (rows carry shard-local indices)
-        self.nt_map = torch.as_tensor(np.concatenate(
-            [np.arange(batch.struct_off[s], batch.struct_off[s + 1]) for s in self.mine] or [np.zeros(0, dtype=np.int64)]
-        ).astype(np.int32), device=self.eng.device)
-        self.rows_host = None
+        # every rank uses the same number of chunks (the block layout is common); a rank with fewer structures than
+        # chunks still has that many (possibly empty) chunk blocks
+        K = self.n_chunks = max(1, min(n_chunks, min(len(p) for p in self.parts) or 1))
+        # calibration: a pass with self-growing buffers tells the counts of every chunk
+        need = np.zeros((K, 4), dtype=np.int64)            # pairs, hits, rows, structures per chunk
+        if len(self.mine):
+            cal = Pipeline(self.eng, self.sub, self.pinned, bt, mask, n_chunks=K, labels=self.labels, want_hits=False)
+            cal.run()
+            for k, ch in enumerate(cal.chunks):
+                need[k] = (int(ch.counters_host[0]), ch.n_hits, ch.n_rows, ch.s1 - ch.s0)
+            del cal
+        need_t = torch.as_tensor(need, device=dev)
+        if self.world > 1:
+            dist.all_reduce(need_t, op=dist.ReduceOp.MAX)
+        need = need_t.cpu().numpy()
+        self.caps = [(int(p * 1.02) + 1024, int(h * 1.02) + 1024, int(r * 1.02) + 1024) for p, h, r, _ in need]
+        self.s_max = [int(x) for x in need[:, 3]]
+        # block layout (int32 units), every region a multiple of 4 so that the rows region is 16-byte aligned
+        self.off = []
+        total = 0
+        for k in range(K):
+            sm = (self.s_max[k] + 3) // 4 * 4
+            hdr, rs, rc, rows = total, total + HDR_INTS, total + HDR_INTS + sm, total + HDR_INTS + 2 * sm
+            total = rows + 4 * self.caps[k][2]
+            self.off.append((hdr, rs, rc, rows))
+        self.block_ints = total
+        self.block = torch.zeros(total, dtype=torch.int32, device=dev)
+        self.recv = torch.empty((self.world, total), dtype=torch.int32, device=dev) if self.rank == 0 else None
+        self.host = torch.empty((self.world, total), dtype=torch.int32).pin_memory() if self.rank == 0 else None
 
-    def run(self):
-        torch, dev = self.torch, self.eng.device
+        def row_out(k, n_struct, row_cap):
+            hdr, rs, rc, rows = self.off[k]
+            b = self.block
+            return (b[rows:rows + 4 * self.caps[k][2]].view(torch.uint8), b[rs:rs + max(n_struct, 1)],
+                    b[rc:rc + max(n_struct, 1)], b[hdr:hdr + HDR_INTS].view(torch.int64))
+
+        self.pipe = Pipeline(self.eng, self.sub, self.pinned, bt, mask, n_chunks=K, labels=self.labels, want_hits=False,
+                             chunk_caps=self.caps, row_out=row_out) if len(self.mine) else None
+        if self.pipe is not None and len(self.pipe.chunks) != K:
+            raise RuntimeError("chunk count mismatch")
+        # where the structures of every rank's chunks sit (the chunking of Pipeline: contiguous, even split)
+        self.layout = []
+        for r in range(self.world):
+            S_r = len(self.parts[r])
+            kk = max(1, min(K, S_r)) if S_r else 0
+            bounds = [int(round(q * S_r / kk)) for q in range(kk + 1)] if kk else [0]
+            self.layout.append(bounds)
+        sub_off = {r: np.concatenate([[0], np.cumsum([weights[s] for s in self.parts[r]])]) for r in range(self.world)}
+        self.sub_off = sub_off
+
+    def enqueue(self, upload=True):
+        """The device part of a pass, asynchronously on the current stream: shard pipeline (upload=False: on the
+        records already in HBM), counters into the block headers, NCCL gather of the blocks into rank 0's HBM."""
+        torch = self.torch
+        dist = _dist()
         if self.pipe is not None:
-            out = self.pipe.run(to_host=False)
-            rows = out.rows_dev.clone()
-            if rows.shape[0]:                                  # shard-local nt indices -> indices of the whole batch
-                rows[:, 1] = self.nt_map[rows[:, 1].long()]
-                rows[:, 2] = self.nt_map[rows[:, 2].long()]
-            rs, rc, n_pairs = out.row_start_dev, out.row_count_dev, out.n_pairs
-        else:
-            rows = torch.zeros((0, 4), dtype=torch.int32, device=dev)
-            rs = rc = torch.zeros(0, dtype=torch.int32, device=dev)
-            n_pairs = 0
-        got = gather_rows(rows, rs, rc, self.mine, self.batch.n_structures, self.rank, self.world, scalars=(n_pairs,))
-        if got is None:
+            self.pipe.enqueue(upload=upload)
+            for k, ch in enumerate(self.pipe.chunks):      # the search / classify counters travel in the header
+                hdr = self.off[k][0]
+                self.block[hdr:hdr + HDR_INTS].view(torch.int64)[4:12].copy_(ch.plan.counters, non_blocking=True)
+        if self.world > 1:
+            if self.rank == 0:
+                dist.gather(self.block, list(self.recv.unbind(0)), dst=0)
+            else:
+                dist.gather(self.block, None, dst=0)
+
+    def run(self, upload=True):
+        torch, dev = self.torch, self.eng.device
+        self.enqueue(upload=upload)
+        if self.rank != 0:
             return None
-        rows_all, rs_all, rc_all, (pairs_all,) = got
-        from .tail import BatchAnnotations, ROW_DTYPE
-        nb = rows_all.shape[0]
-        if self.rows_host is None or self.rows_host.shape[0] < nb:
-            self.rows_host = torch.empty((int(nb * 1.2) + 1024, 4), dtype=torch.int32).pin_memory()
-        self.rows_host[:nb].copy_(rows_all, non_blocking=True)
-        rs_h, rc_h = rs_all.cpu(), rc_all.cpu()               # synchronises the stream the copies are on
+        src = self.recv if self.world > 1 else self.block.view(1, -1)
+        self.host.copy_(src, non_blocking=True)
         torch.cuda.current_stream(dev).synchronize()
-        return BatchAnnotations(self.batch, self.rows_host[:nb].numpy().view(ROW_DTYPE).reshape(-1), rs_h.numpy(),
-                                rc_h.numpy(), self.labels, n_pairs=pairs_all)
+        return self._assemble()
+
+    def _assemble(self):
+        from . import _lib
+        from .tail import BatchAnnotations, ROW_DTYPE
+        host = self.host.numpy()
+        S = self.batch.n_structures
+        row_start = np.zeros(S, dtype=np.int64)
+        row_count = np.zeros(S, dtype=np.int32)
+        nt_base = np.zeros(S, dtype=np.int64)
+        n_pairs = 0
+        for r in range(self.world):
+            bounds = self.layout[r]
+            mine = self.parts[r]
+            for k in range(len(bounds) - 1):
+                hdr, rs, rc, rows = self.off[k]
+                cnt = host[r, hdr:hdr + HDR_INTS].view(np.int64)
+                pairs, hits, nrows = int(cnt[4]), int(cnt[5]), int(cnt[0])
+                if int(cnt[6]) != 0 or int(cnt[2]) != 0:
+                    raise _lib.Fr3dError("rank %d chunk %d: coordinates or a structure outside the supported ranges (FR3D_E_RANGE)" % (r, k))
+                if pairs > self.caps[k][0] or hits > self.caps[k][1] or nrows > self.caps[k][2]:
+                    raise _lib.Fr3dError("rank %d chunk %d: capacity exceeded (pairs %d, hits %d, rows %d > %r)"
+                                         % (r, k, pairs, hits, nrows, self.caps[k]))
+                n_pairs += pairs
+                ns = bounds[k + 1] - bounds[k]
+                ids = mine[bounds[k]:bounds[k + 1]]
+                row_start[ids] = host[r, rs:rs + ns].astype(np.int64) + (r * self.block_ints + rows) // 4
+                row_count[ids] = host[r, rc:rc + ns]
+                nt_base[ids] = self.sub_off[r][bounds[k]:bounds[k + 1]]
+        rows_all = host.reshape(-1).view(ROW_DTYPE)
+        return BatchAnnotations(self.batch, rows_all, row_start, row_count, self.labels, n_pairs=n_pairs, nt_base=nt_base)
 
 
 def annotate_batch_sharded(batch, categories, annotate_fn=None, rank=None, world_size=None, gather=True, **kw):

@@ -240,17 +240,29 @@ class BatchAnnotations(object):
     annotate_nt_nt_in_structure returns them (built on first access, cached); result.rows_of(s) -> the structured
     row array (label id, nt1, nt2, crossing) with GLOBAL nt indices of the batch; result.labels.name(id) -> str."""
 
-    def __init__(self, batch, rows, row_start, row_count, labels, n_pairs=None):
+    def __init__(self, batch, rows, row_start, row_count, labels, n_pairs=None, nt_base=None):
+        """rows[row_start[s] : row_start[s] + row_count[s]] are the rows of structure s; their nt fields count from
+        nt_base[s] for the first nt of the structure (default batch.struct_off: global indices of the batch; a
+        sharded run delivers shard-local ones)."""
         self.batch, self.rows, self.row_start, self.row_count, self.labels = batch, rows, row_start, row_count, labels
         self.n_pairs = n_pairs
+        self.nt_base = nt_base
         self._cache = {}
 
     def __len__(self):
         return len(self.row_start)
 
     def rows_of(self, s):
+        """Rows of structure s with GLOBAL nt indices of the batch (a view when the stored rows already are)."""
         a = int(self.row_start[s])
-        return self.rows[a:a + int(self.row_count[s])]
+        r = self.rows[a:a + int(self.row_count[s])]
+        if self.nt_base is not None:
+            shift = int(self.batch.struct_off[s]) - int(self.nt_base[s])
+            if shift:
+                r = r.copy()
+                r['nt1'] += shift
+                r['nt2'] += shift
+        return r
 
     @property
     def n_rows(self):

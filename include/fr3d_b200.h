@@ -258,7 +258,7 @@ typedef struct {
     const int32_t *nt_cov;           /* [n_nt] rank of the string model + " " + symmetry + " " + chain (NA:1192) */
 } fr3d_tail_ident_t;
 
-/* tail_counters (device int64[4]): [0] total rows (may exceed row_cap: compare after the sync and re-run),
+/* tail_counters (device int64[32]; [4..31] are written by profiling builds only): [0] total rows (may exceed row_cap: compare after the sync and re-run),
  * [1] scratch, [2] != 0: a structure outside the supported ranges (more than 131 072 nts, an index outside
  * [0, 2^23), more than 65 536 chains or a label without the table entry it needs: FR3D_E_RANGE), [3] scratch.
  * n_hits is read from counters[1] on the device (clamped to hit_cap).  row_start / row_count [n_struct]: the rows of

@@ -469,6 +469,36 @@ def test_device_tail_in_the_pipeline_and_capacity_reruns():
     assert n_pairs == ref.n_pairs and len(ex["rows"]) == ref.n_rows
 
 
+def test_sharded_annotator_single_rank_equals_annotate_batch():
+    """parallel.ShardedAnnotator (what bench.py runs under torchrun) with one rank: tail kernels write into the
+    rank's send block, the block goes to the host in one copy and is indexed in place - same rows as annotate_batch;
+    structures of different sizes exercise the LPT order and the chunk layout."""
+    from fr3d_python_b200 import parallel
+    base = synthetic.pack_base()
+    small = packing.pack_specs(synthetic.load_golden_spec("spec_1s72_strand"))
+    specs = []
+    a = synthetic.make_structure_batch(base, 9, seed0=50)
+    b = synthetic.make_structure_batch(small, 7, seed0=70, sigma=0.05)
+    for k in range(9):
+        specs.append(synthetic.batch_to_spec(a, k))
+        if k < 7:
+            specs.append(synthetic.batch_to_spec(b, k))
+    for k, sp in enumerate(specs):
+        sp["pdb"] = "M%02d" % k
+    batch = packing.pack_specs(specs)
+    ref = NA.annotate_batch(batch, ALL9, as_arrays=True)
+    for chunks in (1, 3):
+        sh = parallel.ShardedAnnotator(batch, ALL9, rank=0, world_size=1, n_chunks=chunks)
+        for _ in range(2):
+            got = sh.run()
+        assert got.n_rows == ref.n_rows and got.n_pairs == ref.n_pairs
+        for s in range(batch.n_structures):
+            assert np.array_equal(got.rows_of(s), ref.rows_of(s)), "chunks %d structure %d" % (chunks, s)
+        assert as_plain(got[3]) == as_plain(ref[3])
+        again = sh.run(upload=False)                      # on the records already in HBM (bench.py's resident loop)
+        assert all(np.array_equal(again.rows_of(s), ref.rows_of(s)) for s in range(batch.n_structures))
+
+
 def test_repeated_passes_over_resident_records_are_identical():
     """bench.py's resident loop: K1..K4 + tail run again and again over the same device records.  K1 reads the
     uploaded compact base plane and its observed-mask plane and writes the full records elsewhere, so every pass
