@@ -26,6 +26,9 @@
 
 namespace fr3d {
 
+#ifndef FR3D_TAIL_MINB
+#define FR3D_TAIL_MINB 4             // blocks per SM the structure kernel is compiled for (4: 64 registers, no spills)
+#endif
 constexpr int TAIL_THREADS = 256;
 constexpr int TAIL_SORT_CAP = 2048;      // elements sorted in shared memory (24 KB)
 constexpr int TAIL_MAX_LABELS = 1024;
@@ -188,43 +191,106 @@ __device__ __forceinline__ void tail_cmpswap(tail_u64 *K, uint32_t *V, int lo, i
     }
 }
 
-// Ascending sort of n (key, value) pairs by one block: a bitonic network in which every comparator puts the larger
-// key at the higher index, so positions >= n behave as +infinity that never moves and their comparators are skipped
-// (n need not be a power of two).  In shared memory when it fits, else in place in global memory.
+// Bitonic sort of up to 256 * E (key, value) pairs held in registers, E per thread, element i = tid * E + e.
+// Compare distance j < E: inside the thread; E <= j < 32 E: with a lane of the own warp (shuffles); larger: through
+// shared memory.  All loops have compile-time bounds, so the E elements never leave the registers.  Missing elements
+// (i >= n) are +infinity.  (The first version kept everything in shared memory with one comparator per thread and
+// step: ~120 instructions per comparator step and thread, 87 k cycles per 1 k-element sort with seven blocks per SM.)
+template <int E>
+__device__ __forceinline__ void tail_sort_regs(tail_u64 *keys, uint32_t *vals, int n, tail_u64 *s_key, uint32_t *s_val) {
+    constexpr int P = TAIL_THREADS * E;
+    constexpr unsigned ALL = 0xFFFFFFFFu;
+    const int tid = threadIdx.x;
+    tail_u64 k[E];
+    uint32_t v[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int i = tid * E + e;
+        k[e] = i < n ? keys[i] : ~0ull;
+        v[e] = i < n ? vals[i] : 0u;
+    }
+#pragma unroll
+    for (int size = 2; size <= P; size <<= 1) {
+#pragma unroll
+        for (int j = size >> 1; j >= 1; j >>= 1) {
+            if (j >= 32 * E) {
+                __syncthreads();
+#pragma unroll
+                for (int e = 0; e < E; ++e) { s_key[tid * E + e] = k[e]; s_val[tid * E + e] = v[e]; }
+                __syncthreads();
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const int i = tid * E + e;
+                    const tail_u64 pk = s_key[i ^ j];
+                    const uint32_t pv = s_val[i ^ j];
+                    const bool take_min = ((i & j) == 0) == ((i & size) == 0);
+                    if (take_min ? pk < k[e] : pk > k[e]) { k[e] = pk; v[e] = pv; }
+                }
+            } else if (j >= E) {
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const int i = tid * E + e;
+                    const tail_u64 pk = __shfl_xor_sync(ALL, k[e], j / E);
+                    const uint32_t pv = __shfl_xor_sync(ALL, v[e], j / E);
+                    const bool take_min = ((i & j) == 0) == ((i & size) == 0);
+                    if (take_min ? pk < k[e] : pk > k[e]) { k[e] = pk; v[e] = pv; }
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    if ((e & j) == 0) {
+                        const int i = tid * E + e;
+                        const bool asc = (i & size) == 0;
+                        if ((k[e] > k[e | j]) == asc) {
+                            const tail_u64 tk = k[e]; k[e] = k[e | j]; k[e | j] = tk;
+                            const uint32_t tv = v[e]; v[e] = v[e | j]; v[e | j] = tv;
+                        }
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int i = tid * E + e;
+        if (i < n) { keys[i] = k[e]; vals[i] = v[e]; }
+    }
+}
+
+// Ascending sort of n (key, value) pairs by one block, in place in global memory.  Up to TAIL_SORT_CAP elements: in
+// registers (tail_sort_regs).  More (large structures): a bitonic network over the global arrays in which every
+// comparator puts the larger key at the higher index, so positions >= n behave as +infinity that never moves and
+// their comparators are skipped (n need not be a power of two).
 __device__ void tail_block_sort(tail_u64 *keys, uint32_t *vals, int n, tail_u64 *s_key, uint32_t *s_val) {
     __syncthreads();
     if (n <= 1) return;
-    int P = 2;
-    while (P < n) P <<= 1;
-    tail_u64 *K = keys;
-    uint32_t *V = vals;
-    const bool staged = P <= TAIL_SORT_CAP;
-    if (staged) {
-        for (int i = threadIdx.x; i < n; i += TAIL_THREADS) { s_key[i] = keys[i]; s_val[i] = vals[i]; }
-        K = s_key; V = s_val;
-        __syncthreads();
-    }
-    const int half_p = P >> 1;
-    for (int k = 2; k <= P; k <<= 1) {
-        const int hk = k >> 1;
-        for (int i = threadIdx.x; i < half_p; i += TAIL_THREADS) {          // flip: i <-> mirror inside blocks of k
-            const int blk = i / hk, off = i - blk * hk;
-            const int lo = blk * k + off, hi = blk * k + k - 1 - off;
-            if (hi < n) tail_cmpswap(K, V, lo, hi);
-        }
-        __syncthreads();
-        for (int j = hk >> 1; j >= 1; j >>= 1) {
-            for (int i = threadIdx.x; i < half_p; i += TAIL_THREADS) {
-                const int lo = 2 * j * (i / j) + (i % j), hi = lo + j;
-                if (hi < n) tail_cmpswap(K, V, lo, hi);
+    if (n <= TAIL_THREADS) tail_sort_regs<1>(keys, vals, n, s_key, s_val);
+    else if (n <= 2 * TAIL_THREADS) tail_sort_regs<2>(keys, vals, n, s_key, s_val);
+    else if (n <= 4 * TAIL_THREADS) tail_sort_regs<4>(keys, vals, n, s_key, s_val);
+    else if (n <= 8 * TAIL_THREADS) tail_sort_regs<8>(keys, vals, n, s_key, s_val);
+    else {
+        int lp = 1;
+        while ((1 << lp) < n) ++lp;
+        const int half_p = 1 << (lp - 1);
+        for (int lk = 1; lk <= lp; ++lk) {
+            const int k = 1 << lk, hk = k >> 1;
+            for (int i = threadIdx.x; i < half_p; i += TAIL_THREADS) {      // flip: i <-> mirror inside blocks of k
+                const int blk = i >> (lk - 1), off = i & (hk - 1);
+                const int lo = blk * k + off, hi = blk * k + k - 1 - off;
+                if (hi < n) tail_cmpswap(keys, vals, lo, hi);
             }
             __syncthreads();
+            for (int lj = lk - 2; lj >= 0; --lj) {
+                const int j = 1 << lj;
+                for (int i = threadIdx.x; i < half_p; i += TAIL_THREADS) {
+                    const int lo = ((i >> lj) << (lj + 1)) + (i & (j - 1)), hi = lo + j;
+                    if (hi < n) tail_cmpswap(keys, vals, lo, hi);
+                }
+                __syncthreads();
+            }
         }
     }
-    if (staged) {
-        for (int i = threadIdx.x; i < n; i += TAIL_THREADS) { keys[i] = s_key[i]; vals[i] = s_val[i]; }
-        __syncthreads();
-    }
+    __syncthreads();
 }
 
 struct TailEntrySrc {      // what one basepair hit says about the entry recorded for u1 (d = 0) or u2 (d = 1)
@@ -243,7 +309,7 @@ __device__ __forceinline__ TailEntrySrc tail_entry_of(const fr3d_hit_t &h, int d
 }
 
 // One block per structure (dynamic assignment through tc[1]).
-__global__ void __launch_bounds__(TAIL_THREADS)
+__global__ void __launch_bounds__(TAIL_THREADS, FR3D_TAIL_MINB)
 tail_structure_kernel(fr3d_nts_t nts, fr3d_tail_ident_t id, fr3d_tail_tables_t tb, const fr3d_hit_t *__restrict__ hits,
                       int32_t index_offset, TailWs ws, fr3d_row_t *__restrict__ rows, int64_t row_cap,
                       int32_t *__restrict__ row_start, int32_t *__restrict__ row_count, int64_t *tc) {
@@ -306,10 +372,12 @@ tail_structure_kernel(fr3d_nts_t nts, fr3d_tail_ident_t id, fr3d_tail_tables_t t
             if (tid == 0) { row_start[s] = -1; row_count[s] = 0; atomicOr((tail_u64 *)&tc[2], 2ull); }
             continue;
         }
-        for (int c = c_lo; c < c_hi; ++c) {                                  // nested_cWW_endpoints: identity (NA:1106)
-            const int eo = id.chain_ends_off[c], len = id.chain_ends_off[c + 1] - eo;
-            for (int i = tid; i < len; i += T) ws.ends[eo + i] = i;
-        }
+        // nested_cWW_endpoints of the structure's chains (NA:1106): in shared memory (the sort buffer, free between the
+        // nested-cWW sort and the final sort) when they fit, else in the global workspace
+        const int ends_lo = id.chain_ends_off[c_lo];
+        const int ends_len = id.chain_ends_off[c_hi] - ends_lo;
+        const bool ends_shared = ends_len <= (int)(TAIL_SMEM / sizeof(int32_t));
+        int32_t *ends_base = ends_shared ? reinterpret_cast<int32_t *>(tail_smem) : ws.ends + ends_lo;
 
         TAIL_PHASE(0);
         // ---- the reference's visit order
@@ -364,7 +432,10 @@ tail_structure_kernel(fr3d_nts_t nts, fr3d_tail_ident_t id, fr3d_tail_tables_t t
             if (e.lab < 0 || e.lab >= n_labels) s_err = 1;
         }
         __syncthreads();
-        // group starts, and the list of nts with two or more basepairs (in iteration order) in the low half of akey
+        // group starts, and the list (in iteration order, in the low half of akey) of the nts whose basepairs can
+        // conflict at all: two entries on the same edge sharing hydrogen-bond atoms.  That test ignores the marks made
+        // so far, which can only suppress comparisons, so an nt that fails it never marks anything - and it runs in
+        // parallel, one thread per nt, while the order-dependent pass below only visits the nts that pass.
         int32_t *multi = reinterpret_cast<int32_t *>(akey);
         {
             int running = 0;
@@ -375,7 +446,19 @@ tail_structure_kernel(fr3d_nts_t nts, fr3d_tail_ident_t id, fr3d_tail_tables_t t
                     const int u = e_u[q];
                     if (q == 0 || e_u[q - 1] != u) {
                         gstart[u] = q;
-                        flag = gcount[u] >= 2;
+                        const int len = gcount[u];
+                        for (int i = q; i < q + len - 1 && !flag; ++i) {
+                            const uint32_t f1 = tb.labels[e_lab[i]].flags;
+                            const fr3d_hit_t *h1 = hits + (eval[i] >> 1);
+                            const tail_u64 at1 = (eval[i] & 1u) ? tb.boxes[h1->box].atoms2 : tb.boxes[h1->box].atoms1;
+                            for (int j = i + 1; j < q + len; ++j) {
+                                const uint32_t f2 = tb.labels[e_lab[j]].flags;
+                                if (((f1 >> 8) & 0xFF) != ((f2 >> 8) & 0xFF)) continue;
+                                const fr3d_hit_t *h2 = hits + (eval[j] >> 1);
+                                const tail_u64 common = at1 & ((eval[j] & 1u) ? tb.boxes[h2->box].atoms2 : tb.boxes[h2->box].atoms1);
+                                if (common && ((common & tb.hydrogen_atoms) || __popcll(common) > 1)) { flag = 1; break; }
+                            }
+                        }
                     }
                 }
                 int total;
@@ -486,6 +569,11 @@ tail_structure_kernel(fr3d_nts_t nts, fr3d_tail_ident_t id, fr3d_tail_tables_t t
         __syncthreads();
         const int nnest = s_nnest;
         tail_block_sort(nkey, nval, nnest, s_key, s_val);
+        for (int c = c_lo; c < c_hi; ++c) {                                  // identity: every index maps to itself
+            const int eo = id.chain_ends_off[c] - ends_lo, len = id.chain_ends_off[c + 1] - id.chain_ends_off[c];
+            for (int i = tid; i < len; i += T) ends_base[eo + i] = i;
+        }
+        __syncthreads();
         // one warp per chain: its candidates are contiguous in the sorted list
         if (nnest > 0) {
             for (int c = warp; c < c_hi - c_lo; c += T / 32) {
@@ -494,9 +582,10 @@ tail_structure_kernel(fr3d_nts_t nts, fr3d_tail_ident_t id, fr3d_tail_tables_t t
                     const int mid = (b0 + b1) >> 1;
                     if ((int)(nkey[mid] >> 48) < c) b0 = mid + 1; else b1 = mid;
                 }
-                int32_t *ends = ws.ends + id.chain_ends_off[c_lo + c];
-                for (int x = b0; x < nnest && (int)(nkey[x] >> 48) == c; ++x) {
+                int32_t *ends = ends_base + (id.chain_ends_off[c_lo + c] - ends_lo);
+                for (int x = b0; x < nnest; ++x) {
                     const tail_u64 k = nkey[x];
+                    if ((int)(k >> 48) != c) break;
                     const int i1 = (int)(k & 0xFFFFFFull), i2 = i1 + (int)((k >> 24) & 0xFFFFFFull);
                     bool nested = i2 > i1;                           // span 0: never nested (NA:1112-1116)
                     for (int i0 = i1 + 1; i0 < i2 && nested; i0 += 32) {
@@ -522,7 +611,7 @@ tail_structure_kernel(fr3d_nts_t nts, fr3d_tail_ident_t id, fr3d_tail_tables_t t
             if (ca == nt_chain[b]) {
                 const int ia = meta[(size_t)a * FR3D_META_INTS + 4], ib = meta[(size_t)b * FR3D_META_INTS + 4];
                 const int i1 = min(ia, ib), i2 = max(ia, ib);
-                const int32_t *ends = ws.ends + id.chain_ends_off[ca];
+                const int32_t *ends = ends_base + (id.chain_ends_off[ca] - ends_lo);
                 for (int i = i1 + 1; i < i2; ++i) {
                     const int e = ends[i];
                     crossing += (e < i1 || e > i2);

@@ -129,3 +129,48 @@ def checksum(spec):
 def rows_to_unit_ids(rows, spec):
     nts = O.build_nts(spec)
     return {k: [(nts[a].unit_id(), nts[b].unit_id(), c) for a, b, c in v] for k, v in rows.items()}
+
+
+# ------------------------------------------------------------------ shared by the tests and tools/adversarial_report.py
+def load_cases(golden, spec):
+    """Every probe point of the golden file as (key, spec, reference rows, reference candidate count, case, point);
+    key = (kind, case index, point index).  The coordinates are regenerated from (pair, motion, t)."""
+    out = []
+    for ci, c in enumerate(golden["cases"]):
+        pc = PairCase(spec, c["i"], c["j"])
+        for pi, p in enumerate(c["points"]):
+            sp = pc.moved(c["motion"], p["t"])
+            sp["pdb"] = "B%03d%02d" % (ci, pi)
+            out.append((("boundary", ci, pi), sp, p["rows"], p["n_candidates"], c, p))
+    for ci, c in enumerate(golden["cells"]):
+        pc = PairCase(spec, c["i"], c["j"])
+        for pi, p in enumerate(c["points"]):
+            sp = pc.moved("z", 0.0, shift=np.array(p["shift"]))
+            sp["pdb"] = "C%03d%02d" % (ci, pi)
+            out.append((("cell", ci, pi), sp, p["rows"], p["n_candidates"], c, p))
+    return out
+
+
+def rows_as_positions(i2t, spec):
+    """A result dict with unit-id tuples -> {label: [[pos1, pos2, crossing], ...]} without covalent links."""
+    pos = {nt.unit_id(): k for k, nt in enumerate(O.build_nts(spec))}
+    return {k: [[pos[a], pos[b], c] for a, b, c in v] for k, v in i2t.items() if v and not k.startswith("p_")}
+
+
+def disagreements(points, got_rows, got_ncand, categories):
+    """Compare per point; for every difference report the threshold the boundary belongs to and the margin of that
+    threshold at the point (oracle.PROBE).  Returns a list of dicts."""
+    out = []
+    for (key, sp, want_rows, want_ncand, case, p), rows, ncand in zip(points, got_rows, got_ncand):
+        if rows == want_rows and ncand == want_ncand:
+            continue
+        margin = None
+        name = case.get("threshold", "cube boundary")
+        if key[0] == "boundary" and name != "unattributed":
+            _, margins = annotate_oracle(sp, categories, probe=True)
+            margin = margin_at(margins, name, case["occurrence"])
+        out.append({"key": key, "pair": (case["i"], case["j"]), "motion": case.get("motion", "shift"), "threshold": name,
+                    "delta": p["delta"], "margin": margin,
+                    "labels": sorted(set(rows) ^ set(want_rows)) or sorted(k for k in rows if rows[k] != want_rows.get(k)),
+                    "candidates": (ncand, want_ncand)})
+    return out
