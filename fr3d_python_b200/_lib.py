@@ -33,7 +33,8 @@ EXPORTS = ["fr3d_version", "fr3d_last_error", "fr3d_init", "fr3d_upload_tables",
            "fr3d_pair_search_workspace", "fr3d_pair_search", "fr3d_classify_workspace", "fr3d_classify_pairs", "fr3d_kabsch_batched",
            "fr3d_bond_orientation", "fr3d_radius_search_workspace", "fr3d_radius_search",
            "fr3d_discrepancy_all_vs_all", "fr3d_discrepancy_one_vs_many",
-           "fr3d_tail_workspace", "fr3d_annotation_tail"]
+           "fr3d_tail_workspace", "fr3d_annotation_tail", "fr3d_discrepancy_rows_upper", "fr3d_discrepancy_assemble",
+           "fr3d_fp64_fma_probe"]
 LABEL_COVALENT = 0x40000000
 TAIL_MAX_LABELS = 1024
 TAIL_MAX_NT = 1 << 17
@@ -164,6 +165,9 @@ def load():
         lib.fr3d_bond_orientation.argtypes = [C.POINTER(NtsStruct), C.POINTER(C.c_int32), vp, vp, vp]
         lib.fr3d_kabsch_batched.argtypes = [vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp]
         lib.fr3d_discrepancy_all_vs_all.argtypes = [vp, vp, vp, i32, i32, dbl, i32, i32, vp, vp]
+        lib.fr3d_discrepancy_rows_upper.argtypes = [vp, vp, vp, i32, i32, dbl, i32, i32, vp, vp]
+        lib.fr3d_discrepancy_assemble.argtypes = [vp, i32, i32, i32, vp, vp]
+        lib.fr3d_fp64_fma_probe.argtypes = [i64, vp, C.POINTER(C.c_int64), vp]
         lib.fr3d_discrepancy_one_vs_many.argtypes = [vp, vp, vp, vp, vp, vp, i32, i32, dbl, dbl, vp, vp, vp]
         lib.fr3d_tail_workspace.argtypes = [i64, i32, i32, i64]
         lib.fr3d_tail_workspace.restype = C.c_size_t

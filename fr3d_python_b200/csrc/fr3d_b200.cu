@@ -503,20 +503,58 @@ int fr3d_kabsch_batched(const double *set1, const double *set2, const double *w,
     return FR3D_OK;
 }
 
-int fr3d_discrepancy_all_vs_all(const double *centers, const double *rots, const uint8_t *has_rot, int32_t N,
-                                int32_t n, double angle_weight, int32_t row0, int32_t row1, double *out,
-                                void *stream) {
+static int launch_all_vs_all(const double *centers, const double *rots, const uint8_t *has_rot, int32_t N, int32_t n,
+                             double angle_weight, int32_t row0, int32_t row1, int32_t col0, int32_t ld, double *out,
+                             void *stream) {
     if (!centers || !rots || !out) return fail(FR3D_E_ARG, "NULL argument");
     if (n < 2 || n > fr3d::DISC_MAXN) return fail(FR3D_E_ARG, "n must be in [2, 16]");
     if (row0 < 0 || row1 > N || row0 > row1) return fail(FR3D_E_ARG, "bad row range");
+    if (col0 < 0 || col0 % fr3d::DISC_TILE) return fail(FR3D_E_ARG, "the first column must be a multiple of 32");
     if (int rc = require_device(false, nullptr)) return rc;
-    if (row0 == row1 || N == 0) return FR3D_OK;
+    if (row0 == row1 || N == 0 || col0 >= N) return FR3D_OK;
     const size_t smem = fr3d::disc_smem_bytes(n);        // opted in for n = DISC_MAXN by fr3d_init
     dim3 block(32, 8);
-    dim3 grid((N + fr3d::DISC_TILE - 1) / fr3d::DISC_TILE, (row1 - row0 + fr3d::DISC_TILE - 1) / fr3d::DISC_TILE);
+    dim3 grid((N - col0 + fr3d::DISC_TILE - 1) / fr3d::DISC_TILE, (row1 - row0 + fr3d::DISC_TILE - 1) / fr3d::DISC_TILE);
     fr3d::discrepancy_all_vs_all_kernel<<<grid, block, smem, static_cast<cudaStream_t>(stream)>>>(
-        centers, rots, has_rot, N, n, angle_weight, row0, row1, out);
+        centers, rots, has_rot, N, n, angle_weight, row0, row1, col0, ld, out);
     CUDA_TRY(cudaGetLastError());
+    return FR3D_OK;
+}
+
+int fr3d_discrepancy_all_vs_all(const double *centers, const double *rots, const uint8_t *has_rot, int32_t N,
+                                int32_t n, double angle_weight, int32_t row0, int32_t row1, double *out,
+                                void *stream) {
+    return launch_all_vs_all(centers, rots, has_rot, N, n, angle_weight, row0, row1, 0, N, out, stream);
+}
+
+int fr3d_discrepancy_rows_upper(const double *centers, const double *rots, const uint8_t *has_rot, int32_t N,
+                                int32_t n, double angle_weight, int32_t row0, int32_t row1, double *out,
+                                void *stream) {
+    if (row0 % fr3d::DISC_TILE) return fail(FR3D_E_ARG, "row0 must be a multiple of 32");
+    return launch_all_vs_all(centers, rots, has_rot, N, n, angle_weight, row0, row1, row0, N - row0, out, stream);
+}
+
+int fr3d_discrepancy_assemble(const double *block_upper, int32_t N, int32_t row0, int32_t row1, double *matrix,
+                              void *stream) {
+    if (!block_upper || !matrix) return fail(FR3D_E_ARG, "NULL argument");
+    if (row0 < 0 || row1 > N || row0 > row1 || row0 % fr3d::DISC_TILE) return fail(FR3D_E_ARG, "bad row range");
+    if (int rc = require_device(false, nullptr)) return rc;
+    if (row0 == row1) return FR3D_OK;
+    dim3 block(32, 8);
+    dim3 grid((N - row0 + fr3d::DISC_TILE - 1) / fr3d::DISC_TILE, (row1 - row0 + fr3d::DISC_TILE - 1) / fr3d::DISC_TILE);
+    fr3d::discrepancy_assemble_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(block_upper, N, row0, row1, matrix);
+    CUDA_TRY(cudaGetLastError());
+    return FR3D_OK;
+}
+
+int fr3d_fp64_fma_probe(int64_t iters, double *sink, int64_t *flops, void *stream) {
+    if (!sink || !flops || iters <= 0) return fail(FR3D_E_ARG, "bad argument");
+    int sm_count = 148;
+    if (int rc = require_device(false, &sm_count)) return rc;
+    const int blocks = sm_count * 8;
+    fr3d::fp64_fma_probe_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(iters, 1.0, sink);
+    CUDA_TRY(cudaGetLastError());
+    *flops = (int64_t)blocks * 256 * iters * 16;
     return FR3D_OK;
 }
 

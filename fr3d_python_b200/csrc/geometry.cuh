@@ -179,11 +179,14 @@ constexpr size_t disc_smem_bytes(int n) {
            (size_t)DISC_TILE * (DISC_TILE + 1) * sizeof(double);
 }
 
-// grid: (ceil(N/32), ceil(rows/32)); block 32x8 threads, each thread 4 rows of the tile.
+// grid: (ceil((N - col0)/32), ceil(rows/32)); block 32x8 threads, each thread 4 rows of the tile.
+// Writes out[(r - row0) * ld + (c - col0)] for row0 <= r < row1, col0 <= c < N (col0 a multiple of 32).  col0 = 0,
+// ld = N: whole rows; col0 = row0, ld = N - row0: only the part of a row block at or right of the diagonal (the
+// multi-GPU split of the upper triangle, parallel.triangle_blocks; the mirror is fr3d_discrepancy_assemble).
 __global__ void __launch_bounds__(256)
 discrepancy_all_vs_all_kernel(const double *__restrict__ centers, const double *__restrict__ rots,
                               const uint8_t *__restrict__ has_rot, int N, int n, double angle_weight, int row0,
-                              int row1, double *__restrict__ out) {
+                              int row1, int col0, int ld, double *__restrict__ out) {
     extern __shared__ double smem[];
     // layout: rowc[32][n*3] rowr[32][n*9] colc[32][n*3] colr[32][n*9] + flags
     const int cs = n * 3, rs = n * 9;
@@ -197,10 +200,10 @@ discrepancy_all_vs_all_kernel(const double *__restrict__ centers, const double *
 
     const int tid = threadIdx.y * 32 + threadIdx.x;
     const int rbase = row0 + blockIdx.y * DISC_TILE;
-    const int cbase = blockIdx.x * DISC_TILE;
+    const int cbase = col0 + blockIdx.x * DISC_TILE;
     // full-matrix launches compute only tiles on or above the diagonal and mirror them: the reference
     // fills both triangles from one evaluation as well (FR3D.py:439-441)
-    const bool mirror = (row0 == 0 && row1 == N);
+    const bool mirror = (row0 == 0 && row1 == N && col0 == 0);
     if (mirror && blockIdx.x < blockIdx.y) return;
 
     // stage: raw centres, rotations (coalesced: consecutive threads read consecutive doubles)
@@ -251,7 +254,7 @@ discrepancy_all_vs_all_kernel(const double *__restrict__ centers, const double *
             if (n > 2) d = discrepancy_pair<DISC_MAXN>(ca, ra, ha, cb, rb, hb, n, angle_weight, nullptr, -1.0);
             else d = discrepancy_pair2(ca, ra, cb, rb, angle_weight);
         }
-        out[(size_t)(r - row0) * N + c] = d;
+        out[(size_t)(r - row0) * ld + (c - col0)] = d;
         if (mirror && blockIdx.x > blockIdx.y) tile[threadIdx.x * (DISC_TILE + 1) + rr] = d;
     }
     if (mirror && blockIdx.x > blockIdx.y) {
@@ -263,6 +266,45 @@ discrepancy_all_vs_all_kernel(const double *__restrict__ centers, const double *
             if (cg < N && rg < N) out[(size_t)cg * N + rg] = tile[cc * (DISC_TILE + 1) + threadIdx.x];
         }
     }
+}
+
+// Place one upper row block blk [(r1 - r0)][N - r0] (the output of a col0 = row0 launch) into the N x N matrix D and
+// mirror it: D[r][c] = D[c][r] = blk[r - r0][c - r0] for r0 <= r < r1, c >= r0 (FR3D.py:439-441).  32 x 32 tiles
+// through shared memory so that both the row-wise and the transposed writes are coalesced.
+__global__ void __launch_bounds__(256)
+discrepancy_assemble_kernel(const double *__restrict__ blk, int N, int r0, int r1, double *__restrict__ D) {
+    __shared__ double tile[DISC_TILE][DISC_TILE + 1];
+    const int cbase = r0 + blockIdx.x * DISC_TILE, rbase = r0 + blockIdx.y * DISC_TILE;
+    const int ld = N - r0;
+    for (int rr = threadIdx.y; rr < DISC_TILE; rr += 8) {
+        const int r = rbase + rr, c = cbase + threadIdx.x;
+        double v = 0.0;
+        if (r < r1 && c < N) {
+            v = blk[(size_t)(r - r0) * ld + (c - r0)];
+            D[(size_t)r * N + c] = v;
+        }
+        tile[rr][threadIdx.x] = v;
+    }
+    __syncthreads();
+    if (cbase >= r1) {                       // right of the block's own diagonal square (which holds both triangles)
+        for (int cc = threadIdx.y; cc < DISC_TILE; cc += 8) {
+            const int c = cbase + cc, r = rbase + threadIdx.x;
+            if (c < N && r < r1) D[(size_t)c * N + r] = tile[threadIdx.x][cc];
+        }
+    }
+}
+
+// FP64 peak probe: 8 independent fused multiply-add chains per thread, `iters` rounds; 2 * 8 * iters flops per thread.
+// Timed by the caller (bench.py) to get the DFMA throughput the discrepancy roofline is quoted against.
+__global__ void __launch_bounds__(256) fp64_fma_probe_kernel(long long iters, double seed, double *__restrict__ sink) {
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 1.0000001, b = 1e-9;
+    for (long long k = 0; k < iters; ++k) {
+        a0 = fma(a0, m, b); a1 = fma(a1, m, b); a2 = fma(a2, m, b); a3 = fma(a3, m, b);
+        a4 = fma(a4, m, b); a5 = fma(a5, m, b); a6 = fma(a6, m, b); a7 = fma(a7, m, b);
+    }
+    const double total = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (total == 123.456) sink[0] = total;          // never true: keeps the chains alive
 }
 
 // one query against M candidates, one thread per candidate (search.py:1073-1085)

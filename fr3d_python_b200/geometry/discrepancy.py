@@ -136,3 +136,135 @@ def discrepancy(ntlist1, ntlist2, centers=['base'], base_weights=1.0, P_weights=
     c2 = [nt.centers['base'] for nt in ntlist2]
     r2 = [np.asarray(nt.rotation_matrix) for nt in ntlist2]
     return matrix_discrepancy(c1, r1, c2, r2, angle_weight=angleweight)
+
+
+def fp64_peak_tflops(device=None, iters=20000, reps=5):
+    """Measured DFMA throughput of the device (fr3d_fp64_fma_probe timed with CUDA events; best of reps), in
+    TFLOP/s with an FMA counted as two flops.  The roofline denominator of K5 / K6."""
+    import ctypes as C
+    eng = Engine.get(device)
+    torch = eng.torch
+    with torch.cuda.device(eng.device):
+        sink = torch.zeros(8, dtype=torch.float64, device=eng.device)
+        flops = C.c_int64(0)
+        best = 0.0
+        for _ in range(reps + 1):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            _lib.check(eng.lib.fr3d_fp64_fma_probe(int(iters), sink.data_ptr(), C.byref(flops), eng.stream_ptr()),
+                       "fr3d_fp64_fma_probe")
+            e1.record()
+            torch.cuda.synchronize()
+            best = max(best, flops.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+        eng.launches += reps + 1
+    return best
+
+
+class AllVsAllSharded(object):
+    """The N x N discrepancy matrix on several GPUs (BASELINE configs[4]): the instances are replicated,
+    the UPPER triangle is dealt to the ranks in row blocks with equal tile counts (parallel.triangle_blocks), every
+    rank evaluates only its blocks' part at or right of the diagonal (fr3d_discrepancy_rows_upper) into one packed
+    buffer, the buffers are gathered to rank 0 with one NCCL gather (padded to the largest share), and rank 0
+    places and mirrors the blocks into the matrix (fr3d_discrepancy_assemble).  No exchange between the ranks.
+    run() returns the matrix as a DEVICE tensor on rank 0 (None elsewhere); to_host() copies it out."""
+
+    def __init__(self, centers, rotations, has_rot=None, angle_weight=1.0, rank=0, world_size=1, device=None, block=256):
+        from .. import parallel
+        self.eng = Engine.get(device)
+        torch = self.torch = self.eng.torch
+        dev = self.eng.device
+        self.rank, self.world = rank, world_size
+        centers = np.ascontiguousarray(centers, dtype=np.float64)
+        self.N, self.n = centers.shape[0], centers.shape[1]
+        rots = np.ascontiguousarray(rotations, dtype=np.float64).reshape(self.N, self.n, 9)
+        self.aw = float(angle_weight)
+        self.host_in = (torch.from_numpy(centers).pin_memory(), torch.from_numpy(rots).pin_memory())
+        self.dc = torch.empty_like(self.host_in[0], device=dev)
+        self.dr = torch.empty_like(self.host_in[1], device=dev)
+        self.dh = torch.from_numpy(np.ascontiguousarray(has_rot, dtype=np.uint8)).to(dev) if has_rot is not None else None
+        self.parts = parallel.triangle_blocks(self.N, world_size, block)
+        self.offsets = []          # per rank: [(row0, row1, offset in doubles)]
+        sizes = []
+        for part in self.parts:
+            off, lst = 0, []
+            for r0, r1 in part:
+                lst.append((r0, r1, off))
+                off += (r1 - r0) * (self.N - r0)
+            self.offsets.append(lst)
+            sizes.append(off)
+        self.share = max(sizes + [1])
+        self.buf = torch.empty(self.share, dtype=torch.float64, device=dev)
+        self.recv = torch.empty((world_size, self.share), dtype=torch.float64, device=dev) if (rank == 0 and world_size > 1) else None
+        self.D = torch.zeros((self.N, self.N), dtype=torch.float64, device=dev) if rank == 0 else None
+        self.host_out = None
+        self.in_bytes = centers.nbytes + rots.nbytes
+
+    def upload(self):
+        self.dc.copy_(self.host_in[0], non_blocking=True)
+        self.dr.copy_(self.host_in[1], non_blocking=True)
+
+    def run(self, upload=False):
+        eng, torch = self.eng, self.torch
+        import torch.distributed as dist
+        with torch.cuda.device(eng.device):
+            if upload:
+                self.upload()
+            st = eng.stream_ptr()
+            hp = self.dh.data_ptr() if self.dh is not None else None
+            if self.world == 1:          # one GPU: tiles on or above the diagonal, mirrored inside the kernel
+                self.evaluate_share()
+                return self.D
+            for r0, r1, off in self.offsets[self.rank]:
+                _lib.check(eng.lib.fr3d_discrepancy_rows_upper(self.dc.data_ptr(), self.dr.data_ptr(), hp, self.N, self.n,
+                                                               self.aw, r0, r1, self.buf[off:].data_ptr(), st),
+                           "fr3d_discrepancy_rows_upper")
+                eng.launches += 1
+            if self.world > 1:
+                if self.rank == 0:
+                    dist.gather(self.buf, list(self.recv.unbind(0)), dst=0)
+                else:
+                    dist.gather(self.buf, None, dst=0)
+                    return None
+            for r in range(self.world):
+                src = self.recv[r] if self.world > 1 else self.buf
+                for r0, r1, off in self.offsets[r]:
+                    _lib.check(eng.lib.fr3d_discrepancy_assemble(src[off:].data_ptr(), self.N, r0, r1, self.D.data_ptr(), st),
+                               "fr3d_discrepancy_assemble")
+                    eng.launches += 1
+        return self.D
+
+    def evaluate_share(self):
+        """Only the evaluation launches of this rank (no gather, no assembly): what the roofline figure times."""
+        eng = self.eng
+        st = eng.stream_ptr()
+        hp = self.dh.data_ptr() if self.dh is not None else None
+        if self.world == 1:
+            _lib.check(eng.lib.fr3d_discrepancy_all_vs_all(self.dc.data_ptr(), self.dr.data_ptr(), hp, self.N, self.n,
+                                                           self.aw, 0, self.N, self.D.data_ptr(), st),
+                       "fr3d_discrepancy_all_vs_all")
+            eng.launches += 1
+            return
+        for r0, r1, off in self.offsets[self.rank]:
+            _lib.check(eng.lib.fr3d_discrepancy_rows_upper(self.dc.data_ptr(), self.dr.data_ptr(), hp, self.N, self.n,
+                                                           self.aw, r0, r1, self.buf[off:].data_ptr(), st),
+                       "fr3d_discrepancy_rows_upper")
+            eng.launches += 1
+
+    def to_host(self):
+        torch = self.torch
+        if self.host_out is None:
+            self.host_out = torch.empty((self.N, self.N), dtype=torch.float64).pin_memory()
+        self.host_out.copy_(self.D, non_blocking=True)
+        torch.cuda.current_stream(self.eng.device).synchronize()
+        return self.host_out.numpy()
+
+
+def all_vs_all_multi_gpu(centers, rotations, has_rot=None, angle_weight=1.0, device=None):
+    """all_vs_all() over the ranks of the initialised torch.distributed group (one process per GPU): rank 0 gets
+    the N x N matrix (numpy), the others None.  Works without a group as a single rank."""
+    import torch.distributed as dist
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    sh = AllVsAllSharded(centers, rotations, has_rot, angle_weight, rank, world, device)
+    D = sh.run(upload=True)
+    return sh.to_host() if D is not None else None

@@ -311,6 +311,21 @@ int fr3d_discrepancy_all_vs_all(const double *centers, const double *rots, const
                                 int32_t N, int32_t n, double angle_weight, int32_t row0, int32_t row1,
                                 double *out, void *stream);
 
+/* The same for the multi-GPU split of the matrix: the upper triangle is dealt to the ranks in row blocks
+ * (row0 a multiple of 32); a rank evaluates only the part of its block at or right of the diagonal,
+ * out[(r - row0) * (N - row0) + (c - row0)] for row0 <= r < row1, row0 <= c < N - half the work of whole rows - and
+ * fr3d_discrepancy_assemble places such a block into the N x N matrix and mirrors it (FR3D.py:439-441: the reference
+ * fills both triangles from one evaluation too), on the rank that gathers the blocks. */
+int fr3d_discrepancy_rows_upper(const double *centers, const double *rots, const uint8_t *has_rot, int32_t N,
+                                int32_t n, double angle_weight, int32_t row0, int32_t row1, double *out, void *stream);
+int fr3d_discrepancy_assemble(const double *block_upper, int32_t N, int32_t row0, int32_t row1, double *matrix,
+                              void *stream);
+
+/* Measurement aid (no reference counterpart): launches (SMs x 8) blocks of 256 threads that each run `iters` rounds of
+ * 8 independent fp64 fused multiply-adds; *host_flops = the flops of the launch.  bench.py times it with CUDA events to
+ * get the DFMA peak the discrepancy kernels' roofline is quoted against (MEASURED_PEAKS.json has no fp64 figure). */
+int fr3d_fp64_fma_probe(int64_t iters, double *sink, int64_t *host_flops, void *stream);
+
 /* Replaces matrix_discrepancy_cutoff (discrepancy.py:235-313) of one query against M candidates
  * (fr3d/search/search.py:1073-1085). out[m] = NaN where the reference returns None. */
 int fr3d_discrepancy_one_vs_many(const double *q_centers, const double *q_rots, const uint8_t *q_has_rot,

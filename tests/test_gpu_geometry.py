@@ -172,3 +172,39 @@ def test_argument_checks():
     R = np.tile(np.eye(3), (4, 17, 1, 1))
     with pytest.raises(_lib.Fr3dError):
         disc.all_vs_all(C, R)                     # more than 16 positions
+
+
+def test_upper_triangle_row_blocks_and_assembly_equal_the_full_launch(golden):
+    """The multi-GPU split of the matrix (parallel.triangle_blocks + fr3d_discrepancy_rows_upper +
+    fr3d_discrepancy_assemble, here with 3 emulated ranks on one GPU) gives the bits of the full launch."""
+    import torch
+    from fr3d_python_b200 import _lib, parallel, synthetic
+    from fr3d_python_b200.engine import Engine
+    from fr3d_python_b200.geometry import discrepancy as disc
+    av = golden("geometry.json.gz")["all_vs_all"]
+    N = 1000
+    C, R = synthetic.make_instances(av["base_centers"], av["base_rotations"], N, 77)
+    n = C.shape[1]
+    full = disc.all_vs_all(C, R)
+    eng = Engine.get()
+    dc = torch.from_numpy(C).to(eng.device)
+    dr = torch.from_numpy(R.reshape(N, n, 9)).to(eng.device)
+    D = torch.zeros((N, N), dtype=torch.float64, device=eng.device)
+    parts = parallel.triangle_blocks(N, 3, 128)
+    assert sorted(b for p in parts for b in p) == [(r, min(N, r + 128)) for r in range(0, N, 128)]
+    for part in parts:
+        for r0, r1 in part:
+            blk = torch.full(((r1 - r0) * (N - r0),), -1.0, dtype=torch.float64, device=eng.device)
+            _lib.check(eng.lib.fr3d_discrepancy_rows_upper(dc.data_ptr(), dr.data_ptr(), None, N, n, 1.0, r0, r1,
+                                                           blk.data_ptr(), eng.stream_ptr()), "rows_upper")
+            assert float(blk.min()) >= 0.0                              # every entry of the block was written
+            _lib.check(eng.lib.fr3d_discrepancy_assemble(blk.data_ptr(), N, r0, r1, D.data_ptr(), eng.stream_ptr()),
+                       "assemble")
+    got = D.cpu().numpy()
+    assert np.array_equal(got, full) and np.array_equal(got, got.T) and np.all(np.diag(got) == 0)
+    # the class bench.py uses, single rank
+    sh = disc.AllVsAllSharded(C, R)
+    sh.upload()
+    assert np.array_equal(sh.run().cpu().numpy(), full)
+    assert np.array_equal(disc.all_vs_all_multi_gpu(C, R), full)
+    assert disc.fp64_peak_tflops() > 5.0
