@@ -824,3 +824,60 @@ def test_search_screen_capacity_overflow_is_rerun_not_truncated():
     und = np.minimum(a, b).astype(np.int64) * 1500 + np.maximum(a, b)
     assert len(np.unique(und)) == len(und)
     assert np.abs(dd - ((pts[a] - pts[b]) ** 2).sum(axis=1)).max() < 1e-12
+
+
+def test_two_devices_from_two_threads_of_one_process():
+    """The header's multi-device promise (state is kept per device): two threads, one per GPU, annotate different
+    batches at the same time; each result equals the single-device answer.  Needs two visible GPUs."""
+    import threading
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    base = synthetic.pack_base()
+    batches = [synthetic.make_structure_batch(base, 12, seed0=300 + 100 * d) for d in range(2)]
+    want = [NA.annotate_batch(b, ALL9, device=0, as_arrays=True) for b in batches]
+    got, errors = [None, None], []
+
+    def work(d):
+        try:
+            torch.cuda.set_device(d)
+            for _ in range(3):
+                got[d] = NA.annotate_batch(batches[d], ALL9, device=d, as_arrays=True)
+        except Exception as ex:          # surfaced in the main thread
+            errors.append((d, repr(ex)))
+
+    threads = [threading.Thread(target=work, args=(d,)) for d in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for d in range(2):
+        assert got[d].n_pairs == want[d].n_pairs
+        for s in range(12):
+            assert np.array_equal(got[d].rows_of(s), want[d].rows_of(s)), (d, s)
+    # a device that was never initialised is refused, not served with another device's tables
+    from fr3d_python_b200 import _lib as L
+    lib = L.load()
+    if torch.cuda.device_count() > 2:
+        with torch.cuda.device(2):
+            assert lib.fr3d_pair_search_workspace(10) > 0                      # pure size query: fine anywhere
+            rc = lib.fr3d_frames_fit(None, None, 0, None)
+            assert rc == L.E_ARG
+
+
+def test_cif_text_to_annotations(golden):
+    """mmCIF text in, reference-format annotations out: the CIF scenario (DNA, modified residues, alternate conformers,
+    two models, three symmetry operators) through cif.reader -> annotate_batch equals the oracle on the residues the
+    unmodified reference reader produced from the same file."""
+    import gzip
+    import os
+    from conftest import GOLD
+    from fr3d_python_b200.cif import reader
+    with gzip.open(os.path.join(GOLD, "cif_scenario.cif.gz"), "rt") as f:
+        text = f.read()
+    ref_spec = golden("cif_scenario_reference_reader.json.gz")
+    want, wc, _, _ = oracle_tuples(ref_spec, ALL9)
+    got = NA.annotate_batch(reader.cif_to_batch(text), ALL9)
+    assert as_plain(got[0]) == (want, wc)
+    assert sum(len(v) for v in want.values()) > 500

@@ -660,3 +660,91 @@ def main_search_screen():
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "search":
     main_search_screen()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# mmCIF ingest: what the UNMODIFIED fr3d.cif.reader makes of a CIF text.  The reference needs the
+# `pdbx` package, which is not installed: tools/pdbx_shim provides the few classes it uses (dev container only).
+def make_cif_scenario():
+    """A small mmCIF file with the cases the reader's residue delimitation has to get right (reader.py:440-629):
+    DNA residues, missing atoms, modified residues, alternate conformers with common atoms, an insertion code, a
+    second model, two extra symmetry operators on one chain, hetero / water / peptide residues to be filtered out."""
+    import copy
+    with gzip.open(os.path.join(GOLD, "spec_1gid_variants.json.gz"), "rt") as f:
+        variants = json.load(f)
+    with gzip.open(os.path.join(GOLD, "spec_1gid_modified.json.gz"), "rt") as f:
+        modified = json.load(f)
+    pool = [nt for nt in variants["nts"] if nt["symmetry"] == "1_555"]
+    m1 = [nt for nt in pool if nt["model"] == "1"]
+    keep = m1[:40] + [nt for nt in m1 if nt["chain"] == "A" and 226 <= int(nt["number"]) <= 256]
+    keep += [nt for nt in m1 if nt["chain"] == "B"][:14]
+    keep += [nt for nt in pool if nt["model"] == "2"][:10]
+    nts = copy.deepcopy(keep)
+    mod = {(nt["chain"], nt["number"]): nt for nt in modified["nts"] if nt["sequence"] not in "ACGU"}
+    swapped = 0
+    for k, nt in enumerate(nts):                   # a few modified residues (PSU, 5MC, OMG, ...)
+        key = (nt["chain"], nt["number"])
+        if key in mod and nt["model"] == "1" and not nt.get("alt_id") and swapped < 4 and nt["sequence"] in "ACGU":
+            nts[k] = copy.deepcopy(mod[key])
+            swapped += 1
+    # alternate conformers: the phosphate of conformer A becomes common to both (alt '.'), conformer B loses it
+    for nt in nts:
+        if nt.get("alt_id") == "A":
+            nt["atom_alt"] = [None if a[0] in ("P", "OP1", "OP2") else "A" for a in nt["atoms"]]
+        elif nt.get("alt_id") == "B":
+            nt["atoms"] = [a for a in nt["atoms"] if a[0] not in ("P", "OP1", "OP2")]
+    for nt in nts:
+        nt["atoms"] = [[a[0], round(a[1], 3), round(a[2], 3), round(a[3], 3)] for a in nt["atoms"]]
+    hetero = [
+        {"chain": "A", "sequence": "MG", "number": "901", "index": None, "model": "1", "group": "HETATM", "entity": 2,
+         "atoms": [["MG", 52.104, 48.331, 87.25]]},
+        {"chain": "A", "sequence": "HOH", "number": "902", "index": None, "model": "1", "group": "HETATM", "entity": 3,
+         "atoms": [["O", 50.0, 47.5, 86.125]]},
+        {"chain": "C", "sequence": "ALA", "number": "5", "index": 5, "model": "1", "group": "ATOM", "entity": 4,
+         "atoms": [["N", 40.0, 40.5, 80.25], ["CA", 41.2, 40.9, 80.75], ["C", 42.0, 39.8, 81.5], ["O", 41.7, 38.6, 81.375]]},
+    ]
+    c, s = np.cos(np.pi / 6), np.sin(np.pi / 6)
+    operators = [
+        {"id": "1", "name": "1_555", "matrix": [[1, 0, 0], [0, 1, 0], [0, 0, 1]], "vector": [0, 0, 0]},
+        {"id": "2", "name": "2_655", "matrix": [[-1, 0, 0], [0, -1, 0], [0, 0, 1]], "vector": [104.5, 110.25, 3.5]},
+        {"id": "3", "name": "?", "matrix": [[c, -s, 0], [s, c, 0], [0, 0, 1]], "vector": [12.125, -7.5, 20.0]},
+    ]
+    assembly = [("1,2,3", "A"), ("1", "B,C")]
+    return {"pdb": "1GID", "nts": nts}, hetero, operators, assembly
+
+
+def main_cif():
+    sys.path.insert(0, os.path.join(HERE, "pdbx_shim"))
+    sys.path.insert(0, os.path.dirname(HERE))
+    import contextlib
+    import io
+    from fr3d.cif.reader import Cif
+    from fr3d_python_b200.cif import writer
+    spec, hetero, operators, assembly = make_cif_scenario()
+    text = writer.spec_to_cif(spec, operators=operators, assembly=assembly, hetero=hetero,
+                              extra_chem={"MG": "non-polymer", "HOH": "non-polymer", "ALA": "L-peptide linking"})
+    with contextlib.redirect_stdout(io.StringIO()):
+        st = Cif(io.StringIO(text)).structure()
+    out = []
+    for r in residues(st):
+        # the atoms the reader read: Component.__init__ appends inferred hydrogens (and, for modified residues without
+        # hydrogens, ideal-position copies of every mapped base atom) AFTER them - keep the first atom of each name
+        seen, atoms = set(), []
+        for a in r.atoms():
+            if a.name.startswith("H") or a.name in seen:
+                continue
+            seen.add(a.name)
+            atoms.append([a.name, float(a.x), float(a.y), float(a.z)])
+        out.append({"unit_id": r.unit_id(), "chain": r.chain, "sequence": r.sequence, "number": r.number, "index": r.index,
+                    "model": r.model, "symmetry": r.symmetry, "alt_id": r.alt_id, "insertion_code": r.insertion_code,
+                    "atoms": atoms})
+    with gzip.GzipFile(os.path.join(GOLD, "cif_scenario.cif.gz"), "wb", mtime=0) as f:
+        f.write(text.encode())
+    print("wrote cif_scenario.cif.gz (%d bytes of text)" % len(text))
+    dump("cif_scenario_reference_reader.json.gz", {"pdb": st.pdb, "nts": out})
+    print("residues: %d nucleotides; symmetries %s; models %s" % (len(out), sorted(set(o["symmetry"] for o in out)),
+                                                                  sorted(set(o["model"] for o in out))))
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "cif":
+    main_cif()
