@@ -34,7 +34,8 @@ EXPORTS = ["fr3d_version", "fr3d_last_error", "fr3d_init", "fr3d_upload_tables",
            "fr3d_bond_orientation", "fr3d_radius_search_workspace", "fr3d_radius_search",
            "fr3d_discrepancy_all_vs_all", "fr3d_discrepancy_one_vs_many",
            "fr3d_tail_workspace", "fr3d_annotation_tail", "fr3d_discrepancy_rows_upper", "fr3d_discrepancy_assemble",
-           "fr3d_fp64_fma_probe"]
+           "fr3d_fp64_fma_probe", "fr3d_ingest_last_error", "fr3d_ingest_tables", "fr3d_cif_parse", "fr3d_ingest_sizes",
+           "fr3d_ingest_fill", "fr3d_ingest_free"]
 LABEL_COVALENT = 0x40000000
 TAIL_MAX_LABELS = 1024
 TAIL_MAX_NT = 1 << 17
@@ -98,7 +99,7 @@ def build(verbose=False, only_if_stale=False):
             tmp = "%s.%d.tmp" % (LIB_PATH, os.getpid())
             cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
                    "-shared", "-Xcompiler", "-fPIC", "-cudart", "static", "-o", tmp,
-                   os.path.join(CSRC, "fr3d_b200.cu")]
+                   os.path.join(CSRC, "fr3d_b200.cu"), os.path.join(CSRC, "ingest.cpp")]
             if verbose:
                 cmd.insert(1, "-Xptxas")
                 cmd.insert(2, "-v")
@@ -173,9 +174,17 @@ def load():
         lib.fr3d_tail_workspace.restype = C.c_size_t
         lib.fr3d_annotation_tail.argtypes = [C.POINTER(NtsStruct), C.POINTER(TailIdentStruct), C.POINTER(TailTablesStruct),
                                              vp, i64, vp, i32, vp, C.c_size_t, vp, i64, vp, vp, vp, vp]
+        lib.fr3d_ingest_last_error.restype = C.c_char_p
+        lib.fr3d_ingest_tables.argtypes = [C.c_char_p, C.c_size_t]
+        lib.fr3d_cif_parse.argtypes = [C.POINTER(C.c_char_p), C.POINTER(C.c_int64), i32, i32, C.POINTER(vp)]
+        lib.fr3d_ingest_sizes.argtypes = [vp, C.POINTER(C.c_int64)]
+        lib.fr3d_ingest_fill.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(vp)]
+        lib.fr3d_ingest_free.argtypes = [vp]
+        lib.fr3d_ingest_free.restype = None
         for name in EXPORTS:
             if name not in ("fr3d_last_error", "fr3d_pair_search_workspace", "fr3d_classify_workspace",
-                            "fr3d_radius_search_workspace", "fr3d_tail_workspace"):
+                            "fr3d_radius_search_workspace", "fr3d_tail_workspace", "fr3d_ingest_last_error",
+                            "fr3d_ingest_free"):
                 getattr(lib, name).restype = C.c_int
         _lib = lib
         return lib

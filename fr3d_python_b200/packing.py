@@ -149,7 +149,10 @@ def _slot_maps(sequence):
     if sequence in _slot_cache:
         return _slot_cache[sequence]
     parent = defs.get_parent(sequence)
-    if parent is None:
+    if parent is None or parent not in defs.PARENT_CODE:
+        # unknown residue, or a modified residue whose parent is DA / DC / DG: the reference gives those the parent
+        # "DA" ... (NA:1257), for which it has planes but no cutoff boxes; they are left without a frame here and drop
+        # out of the annotation instead of being paired as their RNA counterparts
         res = None
     elif sequence in defs.SEQ_TO_PARENT:
         flags = _lib.FLAG_STD_RNA if sequence in ('A', 'C', 'G', 'U') else 0

@@ -333,6 +333,29 @@ int fr3d_discrepancy_one_vs_many(const double *q_centers, const double *q_rots, 
                                  int32_t M, int32_t n, double cutoff /* < 0: no cutoff */, double angle_weight,
                                  const double *center_weight /* [n] or NULL */, double *out, void *stream);
 
+/* ---- native mmCIF ingest (host code) -------------------------------------------------------------
+ * Replaces, for the nucleotides of a file, fr3d.cif.reader.Cif(handle).structure() (fr3d/cif/reader.py:440-629: operators,
+ * one atom per (operator, atom_site row), residues by stable sort + group, alternate conformers) and the flattening of
+ * the resulting Components into nt records (fr3d/data/components.py:118-202, base.py:150-166; previous O3' of
+ * NA_pairwise_interactions.py:480-525) for many files at once, one thread per file.  Everything here is HOST memory. */
+typedef struct fr3d_ingest fr3d_ingest_t;
+const char *fr3d_ingest_last_error(void);
+/* Slot tables, once per process: tab-separated lines "S seq parent flags dupmask", then "B atom slot" / "K atom slot" (base /
+ * backbone map of that residue type), and "A parent heavy h1 h2" (amino-hydrogen slots); built by the Python layer. */
+int fr3d_ingest_tables(const char *host_blob, size_t len);
+/* Parse n_texts CIF texts with n_threads workers (0 = one per core).  *out must be released with fr3d_ingest_free. */
+int fr3d_cif_parse(const char *const *host_texts, const int64_t *lengths, int32_t n_texts, int32_t n_threads,
+                   fr3d_ingest_t **out);
+/* sizes[0] = nts, [1] = structures, [2..8] = bytes of the string columns model, chain, sequence, symmetry, alt_id,
+ * insertion_code (per nt) and pdb (per structure); values are NUL-terminated, "\1" stands for None. */
+int fr3d_ingest_sizes(const fr3d_ingest_t *h, int64_t *sizes);
+/* Fill caller-owned HOST buffers (pinned memory works): the fr3d_nts_t planes base_xyz [n][16][3], bb_xyz [n][10][3],
+ * base_mask, bb_mask [n], meta [n][8]; struct_off [S + 1]; number, index [n] (index INT64_MIN = None); the seven string
+ * columns (any may be NULL). */
+int fr3d_ingest_fill(const fr3d_ingest_t *h, double *base_xyz, double *bb_xyz, uint32_t *base_mask, uint32_t *bb_mask,
+                     int32_t *meta, int64_t *struct_off, int64_t *number, int64_t *index, char *const *string_columns);
+void fr3d_ingest_free(fr3d_ingest_t *h);
+
 #ifdef __cplusplus
 }
 #endif

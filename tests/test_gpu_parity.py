@@ -881,3 +881,17 @@ def test_cif_text_to_annotations(golden):
     got = NA.annotate_batch(reader.cif_to_batch(text), ALL9)
     assert as_plain(got[0]) == (want, wc)
     assert sum(len(v) for v in want.values()) > 500
+
+
+def test_native_cif_ingest_to_annotations(golden):
+    """The C++ ingest in front of the GPU path: same annotations as the Python reader in front of it."""
+    import gzip
+    import os
+    from conftest import GOLD
+    from fr3d_python_b200.cif import native, reader
+    with gzip.open(os.path.join(GOLD, "cif_scenario.cif.gz"), "rt") as f:
+        text = f.read()
+    a = NA.annotate_batch(native.cif_to_batch([text, text], n_threads=2), ALL9)
+    b = NA.annotate_batch(reader.cif_to_batch(text), ALL9)
+    assert len(a) == 2
+    assert as_plain(a[0]) == as_plain(b[0]) == as_plain(a[1])
