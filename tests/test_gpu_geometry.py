@@ -208,3 +208,36 @@ def test_upper_triangle_row_blocks_and_assembly_equal_the_full_launch(golden):
     assert np.array_equal(sh.run().cpu().numpy(), full)
     assert np.array_equal(disc.all_vs_all_multi_gpu(C, R), full)
     assert disc.fp64_peak_tflops() > 5.0
+
+
+def test_possibility_screen_of_the_fr3d_search(golden):
+    """search.possibility_discrepancies (one launch) against the loop of fr3d/search/search.py:1067-1085 restated with
+    the oracle's matrix_discrepancy_cutoff: same keys in the same order, values within 1e-9; one unit without a
+    rotation matrix (NA_protein_annotation.py:1705-1714 style)."""
+    from fr3d_python_b200 import synthetic
+    from fr3d_python_b200.search import search as S
+    from oracle import fr3d_oracle as O
+    av = golden("geometry.json.gz")["all_vs_all"]
+    C, R = synthetic.make_instances(av["base_centers"], av["base_rotations"], 60, 11)
+    n = C.shape[1]
+    units = []
+    for k in range(60):
+        for p in range(n):
+            units.append({"centers": C[k, p], "rotations": R[k, p]})
+    units[5]["rotations"] = np.array([])
+    rng = np.random.default_rng(2)
+    possibilities = [tuple(range(k * n, (k + 1) * n)) for k in range(60)]
+    possibilities += [tuple(rng.choice(len(units), n, replace=False).tolist()) for _ in range(200)]
+    qc = [C[0, p] + 0.05 for p in range(n)]
+    qr = [R[0, p] for p in range(n)]
+    cutoff = 1.2
+    want = {}
+    for poss in possibilities:
+        d = O.matrix_discrepancy_cutoff(qc, qr, [units[i]["centers"] for i in poss], [units[i]["rotations"] for i in poss], cutoff)
+        if d is not None and d < cutoff:
+            want[poss] = d
+    got = S.possibility_discrepancies(qc, qr, units, possibilities, cutoff)
+    assert list(got.keys()) == list(want.keys()) and 5 < len(want) < len(possibilities)
+    for k in want:
+        assert abs(got[k] - want[k]) < 1e-9
+    assert S.possibility_discrepancies(qc, qr, units, [], cutoff) == {}
