@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <atomic>
 #include <charconv>
+#include <chrono>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -39,11 +40,35 @@ int ifail(const char *msg) {
 }
 
 // ---------------------------------------------------------------- slot tables (from packing._slot_maps) ----
+// atom names (at most 8 bytes in every table we ship; checked when the tables are loaded) packed into one integer
+inline bool pack_name(std::string_view s, uint64_t &key) {
+    if (s.size() > 8) return false;
+    key = 0;
+    memcpy(&key, s.data(), s.size());
+    return true;
+}
+
+struct SlotMap {                       // ~ 25 entries: a linear scan over packed names beats hashing strings
+    std::vector<uint64_t> keys;
+    std::vector<int> slots;
+    void set(uint64_t k, int slot) {
+        for (size_t q = 0; q < keys.size(); ++q)
+            if (keys[q] == k) { slots[q] = slot; return; }
+        keys.push_back(k);
+        slots.push_back(slot);
+    }
+    int find(uint64_t k) const {
+        for (size_t q = 0; q < keys.size(); ++q)
+            if (keys[q] == k) return slots[q];
+        return -1;
+    }
+};
+
 struct SeqInfo {
     int pcode = -1;
     int flags = 0;
     uint32_t dup = 0;
-    std::unordered_map<std::string, int> base, bb;
+    SlotMap base, bb;
 };
 std::unordered_map<std::string, SeqInfo> g_seq;
 struct Amino { int heavy, h1, h2; };
@@ -68,14 +93,32 @@ struct Tokens {
     std::map<std::string, Table> tables;
 };
 
-inline bool is_ws(char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\n'; }
+struct WsTable {
+    bool t[256];
+    constexpr WsTable() : t() { t[(unsigned char)' '] = t[(unsigned char)'\t'] = t[(unsigned char)'\r'] = t[(unsigned char)'\n'] = true; }
+};
+constexpr WsTable g_ws;
+inline bool is_ws(char c) { return g_ws.t[(unsigned char)c]; }
 
-// general mmCIF tokenizer: data_ / loop_ / _names / values (quoted, ;-text fields, # comments)
+// general mmCIF tokenizer: data_ / loop_ / _names / values (quoted, ;-text fields, # comments), streamed straight into
+// the tables (no intermediate token list: nearly all tokens of a file are atom_site values)
 void tokenize(sv text, Tokens &out) {
-    enum Kind { DATA, LOOP, NAME, VALUE };
-    struct Tok { Kind k; sv v; };
-    std::vector<Tok> toks;
-    toks.reserve(text.size() / 6);
+    enum State { NONE, LOOP_NAMES, LOOP_VALUES, KV_VALUE };
+    State state = NONE;
+    Table *cur = nullptr;
+    auto close_loop = [&]() {
+        if (state == LOOP_VALUES && cur && cur->width()) cur->vals.resize(cur->vals.size() / cur->width() * cur->width());
+        if (state == KV_VALUE && cur) cur->vals.push_back(sv("?"));
+    };
+    auto on_value = [&](sv v) {
+        if ((state == LOOP_NAMES || state == LOOP_VALUES) && cur) { state = LOOP_VALUES; cur->vals.push_back(v); }
+        else if (state == KV_VALUE && cur) { cur->vals.push_back(v); state = NONE; }
+    };
+    auto table_of = [&](sv nm, sv &attr) -> Table * {
+        const size_t d = nm.find('.');
+        attr = d == sv::npos ? nm : nm.substr(d + 1);
+        return &out.tables[std::string(nm.substr(1, d == sv::npos ? sv::npos : d - 1))];
+    };
     size_t i = 0, n = text.size();
     bool line_start = true;
     while (i < n) {
@@ -92,7 +135,7 @@ void tokenize(sv text, Tokens &out) {
             sv v = text.substr(i + 1, (end == n ? n : end) - (i + 1));
             while (!v.empty() && is_ws(v.front())) v.remove_prefix(1);
             while (!v.empty() && is_ws(v.back())) v.remove_suffix(1);
-            toks.push_back({VALUE, v});
+            on_value(v);
             i = j;
             line_start = false;
             continue;
@@ -106,54 +149,49 @@ void tokenize(sv text, Tokens &out) {
         if (c == '\'' || c == '"') {
             size_t j = i + 1;
             while (j < n && text[j] != '\n' && !(text[j] == c && (j + 1 == n || is_ws(text[j + 1])))) ++j;
-            toks.push_back({VALUE, text.substr(i + 1, j - i - 1)});
+            on_value(text.substr(i + 1, j - i - 1));
             i = (j < n && text[j] == c) ? j + 1 : j;
             continue;
         }
-        size_t j = i;
-        while (j < n && !is_ws(text[j])) ++j;
-        sv t = text.substr(i, j - i);
-        if (t.size() >= 5 && (t[0] == 'd' || t[0] == 'D') && strncasecmp(t.data(), "data_", 5) == 0) toks.push_back({DATA, t.substr(5)});
-        else if (t.size() == 5 && strncasecmp(t.data(), "loop_", 5) == 0) toks.push_back({LOOP, sv()});
-        else if (t[0] == '_') toks.push_back({NAME, t});
-        else toks.push_back({VALUE, t});
+        size_t j = i + 1;
+        const char *p = text.data();
+        while (j < n && !g_ws.t[(unsigned char)p[j]]) ++j;
+        const sv t(p + i, j - i);
         i = j;
-    }
-    size_t k = 0;
-    while (k < toks.size()) {
-        if (toks[k].k == DATA) {
-            if (!out.have_name) { out.name = std::string(toks[k].v); out.have_name = true; }
-            ++k;
-        } else if (toks[k].k == LOOP) {
-            ++k;
-            std::vector<sv> names;
-            while (k < toks.size() && toks[k].k == NAME) names.push_back(toks[k++].v);
-            const size_t v0 = k;
-            while (k < toks.size() && toks[k].k == VALUE) ++k;
-            if (!names.empty()) {
-                const size_t dot = names[0].find('.');
-                Table &t = out.tables[std::string(names[0].substr(1, dot == sv::npos ? sv::npos : dot - 1))];
-                t.cols.clear();
-                t.vals.clear();
-                for (sv nm : names) {
-                    const size_t d = nm.find('.');
-                    t.cols.emplace_back(d == sv::npos ? nm : nm.substr(d + 1));
+        if (c != '_' && c != 'l' && c != 'L' && c != 'd' && c != 'D') {      // the common case: a plain value
+            on_value(t);
+        } else if (t[0] == '_') {
+            sv attr;
+            if (state == LOOP_NAMES) {
+                Table *tb = table_of(t, attr);
+                if (!cur) {
+                    cur = tb;
+                    cur->cols.clear();
+                    cur->vals.clear();
+                    // atom_site holds nearly every token of a file (about one per 3.5 bytes): no regrowth
+                    if (t.size() > 11 && t.compare(0, 11, "_atom_site.") == 0) cur->vals.reserve((text.size() - i) / 3 + 64);
                 }
-                const size_t w = names.size(), cnt = (k - v0) / w * w;
-                t.vals.reserve(cnt);
-                for (size_t q = 0; q < cnt; ++q) t.vals.push_back(toks[v0 + q].v);
+                cur->cols.emplace_back(attr);
+            } else {
+                close_loop();
+                cur = table_of(t, attr);
+                cur->cols.emplace_back(attr);
+                state = KV_VALUE;
             }
-        } else if (toks[k].k == NAME) {
-            const sv nm = toks[k].v;
-            const size_t d = nm.find('.');
-            Table &t = out.tables[std::string(nm.substr(1, d == sv::npos ? sv::npos : d - 1))];
-            t.cols.emplace_back(d == sv::npos ? nm : nm.substr(d + 1));
-            t.vals.push_back(k + 1 < toks.size() && toks[k + 1].k == VALUE ? toks[k + 1].v : sv("?"));
-            k += 2;
+        } else if (t.size() == 5 && strncasecmp(t.data(), "loop_", 5) == 0) {
+            close_loop();
+            state = LOOP_NAMES;
+            cur = nullptr;
+        } else if (t.size() >= 5 && (t[0] == 'd' || t[0] == 'D') && strncasecmp(t.data(), "data_", 5) == 0) {
+            close_loop();
+            state = NONE;
+            cur = nullptr;
+            if (!out.have_name) { out.name = std::string(t.substr(5)); out.have_name = true; }
         } else {
-            ++k;
+            on_value(t);
         }
     }
+    close_loop();
 }
 
 bool parse_double(sv s, double &v) {
@@ -183,6 +221,7 @@ struct NtOut {
     double base[FR3D_BASE_SLOTS][3] = {}, bb[FR3D_BB_SLOTS][3] = {};
     uint32_t bmask = 0, bbmask = 0;
     int meta0 = -1, meta1 = 0, meta7 = 0;
+    int prev = -1;                                        // nt of the structure whose O3' is this nt's previous O3'
     std::string uid;
 };
 
@@ -237,20 +276,19 @@ void fill_atoms(NtOut &nt, const SeqInfo &si, const std::vector<std::pair<sv, co
     double b[FR3D_BASE_SLOTS][4] = {}, k[FR3D_BB_SLOTS][4] = {};
     bool hb[FR3D_BASE_SLOTS] = {}, hk[FR3D_BB_SLOTS] = {};
     bool saw_h = false;
-    std::string key;
     for (const auto &a : atoms) {
         const sv name = a.first;
         if (name.find('H') != sv::npos) saw_h = true;
-        key.assign(name);
+        uint64_t key;
+        if (!pack_name(name, key)) continue;
         double(*tgt)[4];
         bool *has;
-        int s;
-        auto it = si.base.find(key);
-        if (it != si.base.end()) { s = it->second; tgt = b; has = hb; }
+        int s = si.base.find(key);
+        if (s >= 0) { tgt = b; has = hb; }
         else {
-            auto jt = si.bb.find(key);
-            if (jt == si.bb.end()) continue;
-            s = jt->second; tgt = k; has = hk;
+            s = si.bb.find(key);
+            if (s < 0) continue;
+            tgt = k; has = hk;
         }
         const GenAtom *g = a.second;
         if (!has[s]) { tgt[s][0] = g->x; tgt[s][1] = g->y; tgt[s][2] = g->z; tgt[s][3] = 1; has[s] = true; }
@@ -306,9 +344,19 @@ std::string unit_id(const std::string &pdb, const NtOut &nt) {          // packi
     return o;
 }
 
+#ifdef FR3D_INGEST_TIMING
+#define TICK(label) do { auto now_ = std::chrono::steady_clock::now(); fprintf(stderr, "  %-22s %.3f ms\n", label, std::chrono::duration<double, std::milli>(now_ - tick_).count()); tick_ = now_; } while (0)
+#else
+#define TICK(label)
+#endif
+
 void parse_structure(sv text, StructOut &out) {
+#ifdef FR3D_INGEST_TIMING
+    auto tick_ = std::chrono::steady_clock::now();
+#endif
     Tokens T;
     tokenize(text, T);
+    TICK("tokenize");
     out.pdb = T.name;
     auto at = T.tables.find("atom_site");
     if (at == T.tables.end() || at->second.rows() == 0) return;
@@ -436,6 +484,7 @@ void parse_structure(sv text, StructOut &out) {
         }
     }
     if (base_rows.empty()) return;
+    TICK("tables, operators, rows");
     const Op ident = identity_op();
     std::vector<std::string> sym_names;
     auto sym_index = [&](const Op *o) {
@@ -470,6 +519,7 @@ void parse_structure(sv text, StructOut &out) {
     const sv one("1"), qm("?"), dot(".");
     auto model_of = [&](uint32_t r) { return c_model >= 0 ? V(r, c_model) : one; };
     auto ins_of = [&](uint32_t r) { sv v = c_ins >= 0 ? V(r, c_ins) : qm; return v == qm ? sv() : v; };
+    TICK("numbers");
     // Runs: maximal stretches of consecutive nucleotide rows with one residue key (and one label_asym_id, which picks
     // the operators).  Atoms of a run stay together and in file order under the reference's STABLE sort by residue key,
     // so sorting (operator index, run) pairs is the same as sorting the atoms - a few hundred keys instead of thousands.
@@ -519,6 +569,7 @@ void parse_structure(sv text, StructOut &out) {
         return sym_names[gen[a].sym].compare(sym_names[gen[b].sym]);
     };
     std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return cmp_key(a, b) < 0; });
+    TICK("runs + sort");
     // groups -> conformers -> nucleotides
     std::string key;
     std::vector<GenAtom> atoms_buf;
@@ -591,6 +642,32 @@ void parse_structure(sv text, StructOut &out) {
         }
         a0 = a1;
     }
+    TICK("residues + slots");
+    // previous O3' (map_unit_id_to_previous_O3, NA:480-525; packing._prev_o3_of_structure): the nts of the structure in
+    // (model, symmetry, chain, index, unit id) order, successive indices of one chain are linked
+    std::vector<int> ord(out.nts.size());
+    for (size_t q = 0; q < ord.size(); ++q) ord[q] = (int)q;
+    std::sort(ord.begin(), ord.end(), [&](int a, int b) {
+        const NtOut &x = out.nts[a], &y = out.nts[b];
+        int c = x.model.compare(y.model);
+        if (c) return c < 0;
+        c = x.sym.compare(y.sym);
+        if (c) return c < 0;
+        c = x.chain.compare(y.chain);
+        if (c) return c < 0;
+        const long long ix = x.has_index ? x.index : 0, iy = y.has_index ? y.index : 0;
+        if (ix != iy) return ix < iy;
+        c = x.uid.compare(y.uid);
+        if (c) return c < 0;
+        return a < b;
+    });
+    for (size_t q = 1; q < ord.size(); ++q) {
+        const NtOut &x = out.nts[ord[q - 1]];
+        NtOut &y = out.nts[ord[q]];
+        const long long ix = x.has_index ? x.index : 0, iy = y.has_index ? y.index : 0;
+        if (x.model == y.model && x.sym == y.sym && x.chain == y.chain && iy == ix + 1 && x.meta0 >= 0 && (x.bbmask >> 5 & 1u))
+            y.prev = ord[q - 1];
+    }
 }
 
 }  // namespace
@@ -627,7 +704,9 @@ int fr3d_ingest_tables(const char *blob, size_t len) {
         } else if ((f[0] == "B" || f[0] == "K") && f.size() == 3 && cur) {
             long long s;
             if (!parse_int(f[2], s)) return ifail("bad map line");
-            (f[0] == "B" ? cur->base : cur->bb)[std::string(f[1])] = (int)s;
+            uint64_t key;
+            if (!pack_name(f[1], key)) return ifail("atom name longer than 8 bytes in the slot tables");
+            (f[0] == "B" ? cur->base : cur->bb).set(key, (int)s);
         } else if (f[0] == "A" && f.size() == 5) {
             long long p, h, h1, h2;
             if (!parse_int(f[1], p) || !parse_int(f[2], h) || !parse_int(f[3], h1) || !parse_int(f[4], h2)) return ifail("bad A line");
@@ -731,7 +810,10 @@ int fr3d_ingest_fill(const fr3d_ingest *h, double *base_xyz, double *bb_xyz, uin
     bool any_alt = false;
     for (auto *nt : nts) any_alt = any_alt || nt->has_alt;
     std::map<std::pair<int, std::string>, int> groups;
-    std::map<std::string, int> resid, alts;
+    std::unordered_map<std::string, int> resid, alts;
+    int last_sof = -1, last_group = 0;
+    const std::string *last_model = nullptr, *last_chain = nullptr;
+    int last_chain_rank = 0;
     std::string key;
     for (int64_t k = 0; k < n; ++k) {
         const NtOut &nt = *nts[k];
@@ -741,11 +823,15 @@ int fr3d_ingest_fill(const fr3d_ingest *h, double *base_xyz, double *bb_xyz, uin
         bb_mask[k] = nt.meta0 >= 0 ? nt.bbmask : 0;
         int32_t *m = meta + k * FR3D_META_INTS;
         m[0] = nt.meta0; m[1] = nt.meta1; m[7] = nt.meta7;
-        auto gk = std::make_pair(sof[k], nt.model);
-        auto gi = groups.find(gk);
-        if (gi == groups.end()) gi = groups.emplace(gk, (int)groups.size()).first;
-        m[2] = gi->second;
-        m[3] = chain_rank[nt.chain];
+        if (!(last_sof == sof[k] && last_model && *last_model == nt.model)) {      // consecutive nts mostly share both
+            auto gk = std::make_pair(sof[k], nt.model);
+            auto gi = groups.find(gk);
+            if (gi == groups.end()) gi = groups.emplace(gk, (int)groups.size()).first;
+            last_group = gi->second; last_sof = sof[k]; last_model = &nt.model;
+        }
+        m[2] = last_group;
+        if (!(last_chain && *last_chain == nt.chain)) { last_chain_rank = chain_rank[nt.chain]; last_chain = &nt.chain; }
+        m[3] = last_chain_rank;
         m[4] = nt.has_index ? (int32_t)nt.index : 0;
         if (any_alt) {
             key = std::to_string(sof[k]) + "\x1f" + std::to_string(nt.number) + "\x1f" + nt.seq + "\x1f" + nt.chain + "\x1f" + nt.sym +
@@ -764,33 +850,13 @@ int fr3d_ingest_fill(const fr3d_ingest *h, double *base_xyz, double *bb_xyz, uin
         number[k] = nt.number;
         index[k] = nt.has_index ? nt.index : INT64_MIN;
     }
-    // previous O3' (NA:480-525): per structure, nts in (model, symmetry, chain, index, unit id) order
-    for (size_t s = 0; s < h->structs.size(); ++s) {
-        const int64_t lo = struct_off[s], hi = struct_off[s + 1];
-        std::vector<int64_t> ord(hi - lo);
-        for (int64_t q = 0; q < hi - lo; ++q) ord[q] = lo + q;
-        std::sort(ord.begin(), ord.end(), [&](int64_t a, int64_t b) {
-            const NtOut &x = *nts[a], &y = *nts[b];
-            int c = x.model.compare(y.model);
-            if (c) return c < 0;
-            c = x.sym.compare(y.sym);
-            if (c) return c < 0;
-            c = x.chain.compare(y.chain);
-            if (c) return c < 0;
-            const long long ix = x.has_index ? x.index : 0, iy = y.has_index ? y.index : 0;
-            if (ix != iy) return ix < iy;
-            c = x.uid.compare(y.uid);
-            if (c) return c < 0;
-            return a < b;
-        });
-        for (size_t q = 1; q < ord.size(); ++q) {
-            const int64_t p = ord[q - 1], k = ord[q];
-            const NtOut &x = *nts[p], &y = *nts[k];
-            const long long ix = x.has_index ? x.index : 0, iy = y.has_index ? y.index : 0;
-            if (x.model == y.model && x.sym == y.sym && x.chain == y.chain && iy == ix + 1 && x.meta0 >= 0 && (x.bbmask >> 5 & 1u)) {
-                memcpy(bb_xyz + (k * FR3D_BB_SLOTS + 9) * 3, x.bb[5], 3 * sizeof(double));
-                bb_mask[k] |= 1u << 9;
-            }
+    // previous O3' (found per structure by the parsing threads)
+    for (int64_t k = 0; k < n; ++k) {
+        const NtOut &nt = *nts[k];
+        if (nt.prev >= 0) {
+            const NtOut &x = h->structs[sof[k]].nts[nt.prev];
+            memcpy(bb_xyz + (k * FR3D_BB_SLOTS + 9) * 3, x.bb[5], 3 * sizeof(double));
+            bb_mask[k] |= 1u << 9;
         }
     }
     return FR3D_OK;

@@ -108,7 +108,11 @@ class DeviceBatch(object):
         self.compact_base = None
         t = {}
         for name in ("center", "rot", "base_xyz", "bb_xyz", "base_mask", "bb_mask", "meta"):
-            src = pinned[name] if pinned is not None else torch.from_numpy(_as_signed(getattr(batch, name)))
+            if name in ("center", "rot") and not batch.frames_given:        # K1 writes them: nothing to upload
+                shape = getattr(batch, name).shape
+                t[name] = torch.empty(shape, dtype=torch.float64, device=device)
+                continue
+            src = pinned[name] if (pinned is not None and name in pinned) else torch.from_numpy(_as_signed(getattr(batch, name)))
             if name == "base_xyz" and src.shape[1] < _lib.BASE_SLOTS:       # compact pinned form, see pin_batch:
                 # K1 reads the compact plane and writes the full 16-slot records (fr3d_frames_fit_from)
                 self.compact_base = [src.to(device, non_blocking=True), int(src.shape[1]), None]
@@ -133,6 +137,18 @@ def _as_signed(a):
 
 
 HEAVY_SLOTS = 11        # the most heavy base atoms any parent has (G); slots from here on only ever hold hydrogens
+
+
+def pinned_planes(batch):
+    """The pinned torch tensors behind the record planes of a batch whose arrays already live in pinned memory
+    (cif.native.cif_to_batch(..., pinned=True)), in the form Engine.annotate_batch(pinned=...) takes; None otherwise."""
+    out = {}
+    for name in ("base_xyz", "bb_xyz", "base_mask", "bb_mask", "meta"):
+        t = getattr(batch, "_pin_" + name, None)
+        if t is None:
+            return None
+        out[name] = t
+    return out
 
 
 def pin_batch(torch, batch):
