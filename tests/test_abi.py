@@ -34,9 +34,7 @@ def test_library_builds_and_exports_every_declared_symbol():
         assert hasattr(lib, n), n
     header_version = int(re.search(r"#define FR3D_ABI_VERSION (\d+)", open(HEADER).read()).group(1))
     assert lib.fr3d_version() == _lib.ABI_VERSION == header_version
-    import __graft_entry__
-    __graft_entry__.build()                       # the driver's build check itself
-    assert lib.fr3d_last_error() is not None
+    assert lib.fr3d_last_error() is not None          # (the driver runs __graft_entry__.build() itself each round)
     assert lib.fr3d_pair_search_workspace(1000) > 0
     out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
     exported = set(re.findall(r" T (fr3d_[a-z_0-9]+)", out))
