@@ -257,6 +257,7 @@ def main():
     ap.add_argument("--cpu-structures", type=int, default=0, help="CPU baseline sample (0 = 2 per core, max 128)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--chunks", type=int, default=8, help="chunks of the e2e pipeline per GPU")
+    ap.add_argument("--no-graph", action="store_true", help="time Pipeline.run (one Python launch per kernel) instead of the CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
@@ -400,17 +401,35 @@ def main():
             for _ in range(2):
                 res = pipe.run()
             assert res.n_pairs == n_pairs and len(res.rows) == n_rows, "pipelined pass disagrees with the calibration pass"
+            use_graph = not args.no_graph
+            if use_graph:
+                try:
+                    res = pipe.run_graph()
+                    assert res.n_pairs == n_pairs and res.n_rows == n_rows, "graph replay disagrees with the calibration pass"
+                except Exception as ex:                     # capture not possible here: the plain pipeline is timed
+                    sys.stderr.write("CUDA graph capture failed (%r); timing Pipeline.run instead\n" % (ex,))
+                    use_graph = False
+            step = pipe.run_graph if use_graph else pipe.run
             barrier()
             t0 = time.perf_counter()
             for k in range(args.steps):
-                res = pipe.run()
+                res = step()
             torch.cuda.synchronize()
             out["t_e2e"] = time.perf_counter() - t0
             barrier()
             out["h2d"] = pipe.h2d_bytes
-            out["d2h"] = n_rows * 16 + 8 * batch_local.n_structures + 96 * len(pipe.chunks)
-            out["e2e_what"] = "engine.Pipeline.run: pinned host nt records -> H2D -> K1..K4 + device tail -> D2H of the " \
-                              "final rows (label id, nt1, nt2, crossing; reference order), %d chunks on 3 streams" % args.chunks
+            out["d2h"] = pipe.graph_d2h_bytes if use_graph else (n_rows * 16 + 8 * batch_local.n_structures + 96 * len(pipe.chunks))
+            out["e2e_what"] = "engine.Pipeline.%s: pinned host nt records -> H2D -> K1..K4 + device tail -> D2H of the final rows " \
+                              "(label id, nt1, nt2, crossing; reference order), %d chunks on 3 streams%s" % (
+                                  "run_graph" if use_graph else "run", args.chunks,
+                                  ", the whole pass captured in ONE CUDA graph and replayed" if use_graph else "")
+            if use_graph:          # the plain pipeline beside it
+                barrier()
+                t0 = time.perf_counter()
+                for k in range(args.steps):
+                    pipe.run()
+                torch.cuda.synchronize()
+                out["t_e2e_no_graph"] = time.perf_counter() - t0
         return out
 
     def reduce_max_sum(vals):
@@ -548,6 +567,7 @@ def main():
                 "e2e": {"value": main_s["e2e_value"], "unit": "pairs/s", "h2d_bytes_per_step": int(main_s["h2d"]),
                         "d2h_bytes_per_step": int(main_s["d2h"]), "structures_per_s": main_s["e2e_structures_per_s"],
                         "ms_per_step": main_s["e2e_ms_per_step"], "what": m["e2e_what"]},
+                "e2e_without_cuda_graph_ms_per_step": (1000.0 * m["t_e2e_no_graph"] / args.steps) if "t_e2e_no_graph" in m else None,
                 "gpu_launches": main_s["gpu_launches"],
                 "kernel_ms": {"classify_pairs": m["classify_ms"], "pair_search_5_kernels": m["search_ms"],
                               "device_tail_5_kernels": m["tail_ms"],

@@ -554,6 +554,81 @@ class Pipeline(object):
             ch.counters_host[8:].copy_(ch.plan.tcounters[:4], non_blocking=True)
         ch.ev.record(ch.stream)
 
+    def build_graph(self):
+        """Capture one whole pass - for every chunk: H2D, K1..K7, counters, and the D2H of its row block at full
+        capacity into a fixed region of the pinned result buffer, chunks forked onto their streams and joined -
+        into ONE CUDA graph, so that a pass costs one graph launch instead of ~30 launches and copies per chunk from
+        Python (the pipeline is launch-bound on the host once the kernels are fast).  Needs the device tail."""
+        eng, torch = self.eng, self.eng.torch
+        if self.labels is None:
+            raise _lib.Fr3dError("Pipeline.build_graph needs the device tail (labels)")
+        self.run()                                   # warm-up; also grows any capacity that was too small
+        self._alloc_results()
+        side = torch.cuda.Stream(device=eng.device)
+        g = torch.cuda.CUDAGraph()
+        launches0 = eng.launches
+        torch.cuda.synchronize(eng.device)
+        with torch.cuda.graph(g, stream=side):
+            main = torch.cuda.current_stream(eng.device)
+            start = torch.cuda.Event()
+            start.record(main)
+            roff = 0
+            for ch in self.chunks:
+                ch.stream.wait_event(start)
+                with torch.cuda.stream(ch.stream):
+                    ch.dev_blob.copy_(ch.host_blob, non_blocking=True)
+                    self._launch(ch)
+                    nb = ch.plan.row_cap * 16
+                    ns = ch.s1 - ch.s0
+                    self.rows_host[roff:roff + nb].copy_(ch.plan.rows[:nb], non_blocking=True)
+                    self.row_start_host[ch.s0:ch.s1].copy_(ch.plan.row_start[:ns], non_blocking=True)
+                    self.row_count_host[ch.s0:ch.s1].copy_(ch.plan.row_count[:ns], non_blocking=True)
+                    ch.graph_row_off = roff // 16
+                    done = torch.cuda.Event()
+                    done.record(ch.stream)
+                main.wait_event(done)
+                roff += nb
+        self.graph = g
+        self.graph_launches = eng.launches - launches0
+        self.graph_d2h_bytes = roff + 8 * self.batch.n_structures + 96 * len(self.chunks)
+        return g
+
+    def run_graph(self):
+        """One pass by replaying the captured graph (build_graph() on first use).  Same result object as run(); the
+        row array has one capacity-sized region per chunk (row_start points into it)."""
+        eng, torch = self.eng, self.eng.torch
+        if getattr(self, "graph", None) is None:
+            self.build_graph()
+        self.graph.replay()
+        torch.cuda.current_stream(eng.device).synchronize()
+        eng.launches += self.graph_launches
+        n_pairs = n_hits = 0
+        for ch in self.chunks:
+            cnt = ch.counters_host
+            if int(cnt[2]) != 0:
+                raise _lib.Fr3dError("fr3d_pair_search: base centre outside the spatial-hash range (FR3D_E_RANGE)")
+            npairs, nhits, nrows = int(cnt[0]), int(cnt[1]), int(cnt[8])
+            if npairs > ch.plan.pair_cap or nhits > ch.plan.hit_cap or nrows > ch.plan.row_cap:
+                self.graph = None                    # capacities of the captured buffers: grow them (run) and re-capture
+                self.build_graph()
+                return self.run_graph()
+            if int(cnt[10]) != 0:
+                raise _lib.Fr3dError("fr3d_annotation_tail: a structure is outside the supported ranges (FR3D_E_RANGE)")
+            ch.n_hits, ch.n_rows = nhits, nrows
+            n_pairs += npairs
+            n_hits += nhits
+        from .tail import ROW_DTYPE
+        S = self.batch.n_structures
+        res = PipelineResult()
+        res.n_pairs, res.n_hits, res.hits = n_pairs, n_hits, None
+        res.rows = self.rows_host.numpy().view(ROW_DTYPE)
+        res.row_start = self.row_start_host.numpy()[:S].astype(np.int64)
+        res.row_count = self.row_count_host.numpy()[:S]
+        res.n_rows = int(sum(ch.n_rows for ch in self.chunks))
+        for ch in self.chunks:
+            res.row_start[ch.s0:ch.s1] += ch.graph_row_off
+        return res
+
     def enqueue(self, upload=True):
         """Issue one pass - per chunk: H2D (unless upload is False: the records of the previous pass are still in
         HBM), K1..K4, tail - on the chunk streams and make the CURRENT stream wait for

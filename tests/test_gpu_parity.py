@@ -463,6 +463,14 @@ def test_device_tail_in_the_pipeline_and_capacity_reruns():
         for s in range(batch.n_structures):
             got = out.rows[out.row_start[s]:out.row_start[s] + out.row_count[s]]
             assert np.array_equal(got, ref.rows_of(s)), "chunks %d structure %d" % (chunks, s)
+    # one CUDA graph per pass (what bench.py's e2e replays): same rows, repeatedly
+    pipe = Pipeline(eng, batch, pinned, bt, mask, n_chunks=4, labels=labels)
+    for _ in range(3):
+        out = pipe.run_graph()
+        assert out.n_pairs == ref.n_pairs and out.n_rows == ref.n_rows
+        for s in range(batch.n_structures):
+            got = out.rows[out.row_start[s]:out.row_start[s] + out.row_count[s]]
+            assert np.array_equal(got, ref.rows_of(s)), "graph, structure %d" % s
     # the single-pass entry point re-runs too
     tiny = eng.make_plan(batch.n, pair_cap=100, hit_cap=10)
     hits, n_pairs, ex = eng.annotate_batch(batch, bt, mask, plan=tiny, labels=labels)
