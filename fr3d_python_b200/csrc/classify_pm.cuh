@@ -56,6 +56,41 @@ __device__ __forceinline__ void cp_async4(void *smem_dst, const void *gmem_src) 
 
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 
+// ---- bulk asynchronous copies (TMA, non-tensor form) completing on an mbarrier: one instruction moves a whole record
+// row (a multiple of 16 bytes, 16-byte aligned on both sides) instead of one cp.async per 16-byte piece and lane.
+__device__ __forceinline__ uint32_t smem_addr_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int arrivals) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr_u32(bar)), "r"(arrivals) : "memory");
+}
+
+// orders generic-proxy accesses to shared memory (the mbarrier init, the lanes' reads of a row buffer) before later
+// async-proxy ones (the bulk copy engine's writes into the same buffer)
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr_u32(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void bulk_copy_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_addr_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_addr_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait_parity(unsigned long long *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "MBAR_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@!p bra MBAR_WAIT_%=;\n"
+        "}\n" ::"r"(smem_addr_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
 #define PM_C1(k) (S.fr[(k)])
 #define PM_U1(k) (S.fr[3 + (k)])
 #define PM_C2(k) (S.fr[12 + (k)])

@@ -44,6 +44,13 @@ constexpr int S32_BB = 9, S32_MASKS = 30, S32_BASE = 32;
 constexpr double S32_FX = 65536.0;
 constexpr double S32_RANGE = 32000.0;
 constexpr float S32_FAR = 512.f;
+#ifndef FR3D_S32_BULK
+// 1: every lane stages its row with ONE bulk copy (cp.async.bulk.shared.global + the warp's mbarrier, 128 B then 192 B)
+// instead of 8 + 12 16-byte cp.async and as many shuffles.  Correct (same hits) but measured SLOWER on the bench
+// workload - classify 0.775 vs 0.759 ms (profiles/ab_bulk_copy_r2.log): the copy engine's per-request cost outweighs
+// the ~35 issue slots saved per pair when a request is only 128-192 bytes.  Kept as a build option, default off.
+#define FR3D_S32_BULK 0
+#endif
 #ifndef FR3D_S32_WARPS
 #define FR3D_S32_WARPS 24      // 24 (80 registers, no spill) and 32 (64 registers) warps per SM measure the same
 #endif
@@ -200,6 +207,12 @@ classify_screen32_kernel(const float *__restrict__ rec, const fr3d_box_t *__rest
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float *rows = s32_smem + S32_FIXED + warp * 32 * S32_STRIDE;
     __shared__ int s_nboxes;
+#if FR3D_S32_BULK && !defined(FR3D_S32_SCALAR_ROWS)
+    __shared__ __align__(8) unsigned long long s_bar[S32_WARPS];       // one mbarrier per warp: its rows are private
+    if (lane == 0) mbar_init(&s_bar[warp], 1);
+    fence_proxy_async_smem();
+    uint32_t bar_parity = 0;
+#endif
     if (threadIdx.x == 0) s_nboxes = 0;
     if (threadIdx.x <= FR3D_N_PARENTS) {
         const int p = (int)threadIdx.x - 1;
@@ -265,6 +278,11 @@ classify_screen32_kernel(const float *__restrict__ rec, const fr3d_box_t *__rest
             const int nb = __shfl_sync(FULL, n2, k);
             cp_async4(rows + k * S32_STRIDE + lane, rec + (size_t)nb * S32_REC + lane);
         }
+#elif FR3D_S32_BULK
+        // every lane fetches ITS row with one bulk copy (128 B); the warp's mbarrier counts the 32 x 128 bytes
+        fence_proxy_async_smem();
+        if (lane == 0) mbar_arrive_expect_tx(&s_bar[warp], 32u * 128u);
+        bulk_copy_g2s(rows + lane * S32_STRIDE, rec + (size_t)n2 * S32_REC, 128u, &s_bar[warp]);
 #else
 #pragma unroll
         for (int j = 0; j < 8; ++j) {                       // 8 lanes x 16 B per row, four rows per instruction
@@ -289,8 +307,13 @@ classify_screen32_kernel(const float *__restrict__ rec, const fr3d_box_t *__rest
         unsigned fl = 0, live = 0, bph_combos = 0;
         float dX0 = 0, dY0 = 0, dZ0 = 0, dX1 = 0, dY1 = 0, dZ1 = 0, nZ = 0, ang0 = 0.f, ang1 = 0.f;
         int entry0 = 0, entry1 = 0;
+#if FR3D_S32_BULK && !defined(FR3D_S32_SCALAR_ROWS)
+        mbar_wait_parity(&s_bar[warp], bar_parity);
+        bar_parity ^= 1u;
+#else
         cp_async_wait_all();
         __syncwarp();
+#endif
 #ifdef FR3D_S32_SCALAR_ROWS
         const float *R = rows + lane * S32_STRIDE;
 #else
@@ -374,6 +397,12 @@ classify_screen32_kernel(const float *__restrict__ rec, const fr3d_box_t *__rest
             cp_async4(dst, src);
             if (lane < 16) cp_async4(dst + 32, src + 32);
         }
+#elif FR3D_S32_BULK
+        fence_proxy_async_smem();                           // the lanes have read their phase A rows (__syncwarp above)
+        if (lane == 0) mbar_arrive_expect_tx(&s_bar[warp], 32u * 192u);
+        bulk_copy_g2s(rows + lane * S32_STRIDE, rec + (size_t)n2 * S32_REC + S32_BASE, 192u, &s_bar[warp]);
+        mbar_wait_parity(&s_bar[warp], bar_parity);
+        bar_parity ^= 1u;
 #else
 #pragma unroll
         for (int j = 0; j < 12; ++j) {                      // 12 pieces per row: 4 lanes x 16 B on eight rows per instruction
@@ -382,8 +411,10 @@ classify_screen32_kernel(const float *__restrict__ rec, const fr3d_box_t *__rest
             cp_async16(rows + row * S32_STRIDE + piece, rec + (size_t)nb * S32_REC + S32_BASE + piece);
         }
 #endif
+#if !(FR3D_S32_BULK && !defined(FR3D_S32_SCALAR_ROWS))
         cp_async_wait_all();
         __syncwarp();
+#endif
         if (valid) {
 #ifdef FR3D_S32_SCALAR_ROWS
             const float *RB = rows + lane * S32_STRIDE;

@@ -388,13 +388,11 @@ TailCarve carve_tail(void *workspace, int64_t hit_cap, int32_t n_nt, int32_t n_s
     w.alab = reinterpret_cast<int32_t *>(take(8 * H));
     w.aa = reinterpret_cast<int32_t *>(take(8 * H));
     w.ab = reinterpret_cast<int32_t *>(take(8 * H));
-    w.aseq = reinterpret_cast<uint32_t *>(take(8 * H));
     w.across = reinterpret_cast<int32_t *>(take(8 * H));
     w.first = reinterpret_cast<uint32_t *>(take(4 * n));
     w.gstart = reinterpret_cast<int32_t *>(take(4 * n));
     w.gcount = reinterpret_cast<int32_t *>(take(4 * n));
     w.ckey = reinterpret_cast<unsigned long long *>(take(8 * n));
-    w.cval = reinterpret_cast<uint32_t *>(take(4 * n));
     w.ends = reinterpret_cast<int32_t *>(take(4 * (size_t)(n_ends > 0 ? n_ends : 0)));
     c.bytes = off;
     return c;

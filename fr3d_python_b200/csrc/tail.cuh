@@ -30,13 +30,13 @@ namespace fr3d {
 #define FR3D_TAIL_MINB 4             // blocks per SM the structure kernel is compiled for (4: 64 registers, no spills)
 #endif
 constexpr int TAIL_THREADS = 256;
-constexpr int TAIL_SORT_CAP = 2048;      // elements sorted in shared memory (24 KB)
+constexpr int TAIL_SORT_CAP = 2048;      // elements sorted in registers (exchange buffer: 16 KB of shared memory)
 constexpr int TAIL_MAX_LABELS = 1024;
 constexpr int TAIL_MAX_NT_BITS = 17;     // structures of up to 131 072 nts
 constexpr int TAIL_INDEX_BITS = 23;
 constexpr uint32_t TAIL_NONE = 0xFFFFFFFFu;
 constexpr int TAIL_F_REMOVED = 1, TAIL_F_NEAR = 2;
-constexpr size_t TAIL_SMEM = (size_t)TAIL_SORT_CAP * (sizeof(unsigned long long) + sizeof(uint32_t));
+constexpr size_t TAIL_SMEM = (size_t)TAIL_SORT_CAP * sizeof(unsigned long long);
 
 struct TailWs {
     int32_t *seg_cnt;             // [S]     hits per structure
@@ -48,15 +48,13 @@ struct TailWs {
     uint32_t *eval;               // [2H]    hit index * 2 + (1: the entry recorded for u2)
     int32_t *e_u, *e_v, *e_lab;   // [2H]    entries in iteration order
     uint8_t *e_flag;              // [2H]
-    unsigned long long *akey;     // [2H]    appended rows: (label rank, sequence)
-    uint32_t *aval;               // [2H]
+    unsigned long long *akey;     // [2H]    appended rows: sort keys (label rank, append index)
+    uint32_t *aval;               // [2H]    scratch: entries in recording order
     int32_t *alab, *aa, *ab;      // [2H]
-    uint32_t *aseq;               // [2H]
     int32_t *across;              // [2H]
     uint32_t *first;              // [n]     first appearance of the nt in unit_id_to_basepairs
     int32_t *gstart, *gcount;     // [n]     its entries
     unsigned long long *ckey;     // [n]     covalent sort
-    uint32_t *cval;               // [n]
     int32_t *ends;                // [n_ends] nested_cWW_endpoints of every chain
 };
 
@@ -191,23 +189,22 @@ __device__ __forceinline__ void tail_cmpswap(tail_u64 *K, uint32_t *V, int lo, i
     }
 }
 
-// Bitonic sort of up to 256 * E (key, value) pairs held in registers, E per thread, element i = tid * E + e.
-// Compare distance j < E: inside the thread; E <= j < 32 E: with a lane of the own warp (shuffles); larger: through
-// shared memory.  All loops have compile-time bounds, so the E elements never leave the registers.  Missing elements
-// (i >= n) are +infinity.  (The first version kept everything in shared memory with one comparator per thread and
-// step: ~120 instructions per comparator step and thread, 87 k cycles per 1 k-element sort with seven blocks per SM.)
-template <int E>
-__device__ __forceinline__ void tail_sort_regs(tail_u64 *keys, uint32_t *vals, int n, tail_u64 *s_key, uint32_t *s_val) {
+// Bitonic sort of up to 256 * E keys held in registers, E per thread, element i = tid * E + e; the payload rides in the
+// low bits of the key (32- or 64-bit keys).  Compare distance j < E: inside the thread; E <= j < 32 E: with a lane of
+// the own warp (shuffles); larger: through shared memory.  All loops have compile-time bounds, so the E elements never
+// leave the registers.  Missing elements (i >= n) are +infinity.  (The first version kept (key, value) pairs in shared
+// memory with one comparator per thread and step: ~120 instructions per comparator step and thread, 87 k cycles per
+// 1 k-element sort with seven blocks per SM; registers + shuffles: 47 k; key-only with narrow keys: see profiles/.)
+template <int E, typename K>
+__device__ __forceinline__ void tail_sort_keys_regs(K *keys, int n, K *s_buf) {
     constexpr int P = TAIL_THREADS * E;
     constexpr unsigned ALL = 0xFFFFFFFFu;
     const int tid = threadIdx.x;
-    tail_u64 k[E];
-    uint32_t v[E];
+    K k[E];
 #pragma unroll
     for (int e = 0; e < E; ++e) {
         const int i = tid * E + e;
-        k[e] = i < n ? keys[i] : ~0ull;
-        v[e] = i < n ? vals[i] : 0u;
+        k[e] = i < n ? keys[i] : (K)~(K)0;
     }
 #pragma unroll
     for (int size = 2; size <= P; size <<= 1) {
@@ -216,24 +213,22 @@ __device__ __forceinline__ void tail_sort_regs(tail_u64 *keys, uint32_t *vals, i
             if (j >= 32 * E) {
                 __syncthreads();
 #pragma unroll
-                for (int e = 0; e < E; ++e) { s_key[tid * E + e] = k[e]; s_val[tid * E + e] = v[e]; }
+                for (int e = 0; e < E; ++e) s_buf[tid * E + e] = k[e];
                 __syncthreads();
 #pragma unroll
                 for (int e = 0; e < E; ++e) {
                     const int i = tid * E + e;
-                    const tail_u64 pk = s_key[i ^ j];
-                    const uint32_t pv = s_val[i ^ j];
+                    const K pk = s_buf[i ^ j];
                     const bool take_min = ((i & j) == 0) == ((i & size) == 0);
-                    if (take_min ? pk < k[e] : pk > k[e]) { k[e] = pk; v[e] = pv; }
+                    if (take_min ? pk < k[e] : pk > k[e]) k[e] = pk;
                 }
             } else if (j >= E) {
 #pragma unroll
                 for (int e = 0; e < E; ++e) {
                     const int i = tid * E + e;
-                    const tail_u64 pk = __shfl_xor_sync(ALL, k[e], j / E);
-                    const uint32_t pv = __shfl_xor_sync(ALL, v[e], j / E);
+                    const K pk = __shfl_xor_sync(ALL, k[e], j / E);
                     const bool take_min = ((i & j) == 0) == ((i & size) == 0);
-                    if (take_min ? pk < k[e] : pk > k[e]) { k[e] = pk; v[e] = pv; }
+                    if (take_min ? pk < k[e] : pk > k[e]) k[e] = pk;
                 }
             } else {
 #pragma unroll
@@ -241,10 +236,7 @@ __device__ __forceinline__ void tail_sort_regs(tail_u64 *keys, uint32_t *vals, i
                     if ((e & j) == 0) {
                         const int i = tid * E + e;
                         const bool asc = (i & size) == 0;
-                        if ((k[e] > k[e | j]) == asc) {
-                            const tail_u64 tk = k[e]; k[e] = k[e | j]; k[e | j] = tk;
-                            const uint32_t tv = v[e]; v[e] = v[e | j]; v[e | j] = tv;
-                        }
+                        if ((k[e] > k[e | j]) == asc) { const K t = k[e]; k[e] = k[e | j]; k[e | j] = t; }
                     }
                 }
             }
@@ -253,41 +245,69 @@ __device__ __forceinline__ void tail_sort_regs(tail_u64 *keys, uint32_t *vals, i
 #pragma unroll
     for (int e = 0; e < E; ++e) {
         const int i = tid * E + e;
-        if (i < n) { keys[i] = k[e]; vals[i] = v[e]; }
+        if (i < n) keys[i] = k[e];
     }
 }
 
-// Ascending sort of n (key, value) pairs by one block, in place in global memory.  Up to TAIL_SORT_CAP elements: in
-// registers (tail_sort_regs).  More (large structures): a bitonic network over the global arrays in which every
-// comparator puts the larger key at the higher index, so positions >= n behave as +infinity that never moves and
-// their comparators are skipped (n need not be a power of two).
-__device__ void tail_block_sort(tail_u64 *keys, uint32_t *vals, int n, tail_u64 *s_key, uint32_t *s_val) {
+template <typename K>
+__device__ void tail_block_sort_keys(K *keys, int n, void *smem) {
     __syncthreads();
     if (n <= 1) return;
-    if (n <= TAIL_THREADS) tail_sort_regs<1>(keys, vals, n, s_key, s_val);
-    else if (n <= 2 * TAIL_THREADS) tail_sort_regs<2>(keys, vals, n, s_key, s_val);
-    else if (n <= 4 * TAIL_THREADS) tail_sort_regs<4>(keys, vals, n, s_key, s_val);
-    else if (n <= 8 * TAIL_THREADS) tail_sort_regs<8>(keys, vals, n, s_key, s_val);
-    else {
+    K *s_buf = reinterpret_cast<K *>(smem);
+    if (n <= TAIL_THREADS) tail_sort_keys_regs<1, K>(keys, n, s_buf);
+    else if (n <= 2 * TAIL_THREADS) tail_sort_keys_regs<2, K>(keys, n, s_buf);
+    else if (n <= 4 * TAIL_THREADS) tail_sort_keys_regs<4, K>(keys, n, s_buf);
+    else if (n <= 8 * TAIL_THREADS) tail_sort_keys_regs<8, K>(keys, n, s_buf);
+    else {                                           // large structures: the all-ascending network over global memory
         int lp = 1;
         while ((1 << lp) < n) ++lp;
         const int half_p = 1 << (lp - 1);
         for (int lk = 1; lk <= lp; ++lk) {
-            const int k = 1 << lk, hk = k >> 1;
-            for (int i = threadIdx.x; i < half_p; i += TAIL_THREADS) {      // flip: i <-> mirror inside blocks of k
+            const int kk = 1 << lk, hk = kk >> 1;
+            for (int i = threadIdx.x; i < half_p; i += TAIL_THREADS) {
                 const int blk = i >> (lk - 1), off = i & (hk - 1);
-                const int lo = blk * k + off, hi = blk * k + k - 1 - off;
-                if (hi < n) tail_cmpswap(keys, vals, lo, hi);
+                const int lo = blk * kk + off, hi = blk * kk + kk - 1 - off;
+                if (hi < n) { const K a = keys[lo], b = keys[hi]; if (a > b) { keys[lo] = b; keys[hi] = a; } }
             }
             __syncthreads();
             for (int lj = lk - 2; lj >= 0; --lj) {
                 const int j = 1 << lj;
                 for (int i = threadIdx.x; i < half_p; i += TAIL_THREADS) {
                     const int lo = ((i >> lj) << (lj + 1)) + (i & (j - 1)), hi = lo + j;
-                    if (hi < n) tail_cmpswap(keys, vals, lo, hi);
+                    if (hi < n) { const K a = keys[lo], b = keys[hi]; if (a > b) { keys[lo] = b; keys[hi] = a; } }
                 }
                 __syncthreads();
             }
+        }
+    }
+    __syncthreads();
+}
+
+// Ascending sort of n (key, value) pairs by one block, in place in global memory: the fallback for structures whose
+// packed hit key does not fit 64 bits (more than ~100 k nts AND many hits).  A bitonic network in which every comparator
+// puts the larger key at the higher index, so positions >= n behave as +infinity that never moves and their comparators
+// are skipped (n need not be a power of two).
+__device__ void tail_block_sort(tail_u64 *keys, uint32_t *vals, int n) {
+    __syncthreads();
+    if (n <= 1) return;
+    int lp = 1;
+    while ((1 << lp) < n) ++lp;
+    const int half_p = 1 << (lp - 1);
+    for (int lk = 1; lk <= lp; ++lk) {
+        const int k = 1 << lk, hk = k >> 1;
+        for (int i = threadIdx.x; i < half_p; i += TAIL_THREADS) {      // flip: i <-> mirror inside blocks of k
+            const int blk = i >> (lk - 1), off = i & (hk - 1);
+            const int lo = blk * k + off, hi = blk * k + k - 1 - off;
+            if (hi < n) tail_cmpswap(keys, vals, lo, hi);
+        }
+        __syncthreads();
+        for (int lj = lk - 2; lj >= 0; --lj) {
+            const int j = 1 << lj;
+            for (int i = threadIdx.x; i < half_p; i += TAIL_THREADS) {
+                const int lo = ((i >> lj) << (lj + 1)) + (i & (j - 1)), hi = lo + j;
+                if (hi < n) tail_cmpswap(keys, vals, lo, hi);
+            }
+            __syncthreads();
         }
     }
     __syncthreads();
@@ -314,8 +334,6 @@ tail_structure_kernel(fr3d_nts_t nts, fr3d_tail_ident_t id, fr3d_tail_tables_t t
                       int32_t index_offset, TailWs ws, fr3d_row_t *__restrict__ rows, int64_t row_cap,
                       int32_t *__restrict__ row_start, int32_t *__restrict__ row_count, int64_t *tc) {
     extern __shared__ __align__(16) unsigned char tail_smem[];
-    tail_u64 *s_key = reinterpret_cast<tail_u64 *>(tail_smem);
-    uint32_t *s_val = reinterpret_cast<uint32_t *>(s_key + TAIL_SORT_CAP);
     __shared__ uint32_t s_lfirst[TAIL_MAX_LABELS];
     __shared__ uint16_t s_lrank[TAIL_MAX_LABELS];
     __shared__ int s_w[TAIL_THREADS / 32];
@@ -348,7 +366,7 @@ tail_structure_kernel(fr3d_nts_t nts, fr3d_tail_ident_t id, fr3d_tail_tables_t t
         uint32_t *hval = ws.hval + hb;
         const size_t eb = 2 * (size_t)hb;
         tail_u64 *ekey = ws.ekey + eb, *akey = ws.akey + eb;
-        uint32_t *eval = ws.eval + eb, *aval = ws.aval + eb, *aseq = ws.aseq + eb;
+        uint32_t *eval = ws.eval + eb, *aval = ws.aval + eb;
         int32_t *e_u = ws.e_u + eb, *e_v = ws.e_v + eb, *e_lab = ws.e_lab + eb;
         uint8_t *e_flag = ws.e_flag + eb;
         int32_t *alab = ws.alab + eb, *aa = ws.aa + eb, *ab = ws.ab + eb, *across = ws.across + eb;
@@ -380,53 +398,96 @@ tail_structure_kernel(fr3d_nts_t nts, fr3d_tail_ident_t id, fr3d_tail_tables_t t
         int32_t *ends_base = ends_shared ? reinterpret_cast<int32_t *>(tail_smem) : ws.ends + ends_lo;
 
         TAIL_PHASE(0);
-        // ---- the reference's visit order
-        tail_block_sort(hkey, hval, H, s_key, s_val);
+        // ---- the reference's visit order.  When the bits allow (always, for structures whose hits fit the register
+        // sort) the key is re-packed as (rank, nt1, nt2, slot, position in the segment) with field widths from n and H,
+        // and sorted WITHOUT a value array: half the shuffles and selects of a (key, value) sort.
+        int nb = 1;
+        while ((1 << nb) < n) ++nb;
+        int hbits = 1;
+        while ((1 << hbits) < H) ++hbits;
+        const bool packed = 3 * nb + 8 + hbits <= 64;
+        const tail_u64 hmask = (1ull << hbits) - 1ull;
+        if (packed) {
+            const tail_u64 fm = (1ull << TAIL_MAX_NT_BITS) - 1ull;
+            for (int t = tid; t < H; t += T) {
+                const tail_u64 k = hkey[t];              // (rank : nt1 : nt2 : slot) in fixed 17-bit fields (tail_scatter_kernel)
+                const tail_u64 slot = k & 15ull, j = (k >> 4) & fm, i = (k >> (TAIL_MAX_NT_BITS + 4)) & fm,
+                               rank = k >> (2 * TAIL_MAX_NT_BITS + 4);
+                hkey[t] = ((((rank << nb | i) << nb | j) << 4 | slot) << hbits) | (tail_u64)t;
+            }
+            tail_block_sort_keys<tail_u64>(hkey, H, tail_smem);
+        } else {
+            tail_block_sort(hkey, hval, H);
+        }
+        // hit index of sorted position p
+#define TAIL_HIT_OF(p) (packed ? hval[(int)(hkey[p] & hmask)] : hval[p])
 
         TAIL_PHASE(1);
-        // ---- walk: sequence number 2p + k for the k-th thing hit p records
-        for (int p = tid; p < H; p += T) {
-            const uint32_t hidx = hval[p];
-            const fr3d_hit_t h = hits[hidx];
-            if (h.slot == FR3D_SLOT_BP) {
-                const TailEntrySrc e0 = tail_entry_of(h, 0, base, tb);
-                const int e = atomicAdd(&s_nent, 2);
-                ekey[e] = ((tail_u64)(uint32_t)e0.u << 32) | (uint32_t)(2 * p);           // u for now; first[u] below
-                ekey[e + 1] = ((tail_u64)(uint32_t)e0.v << 32) | (uint32_t)(2 * p + 1);
-                eval[e] = hidx * 2u;
-                eval[e + 1] = hidx * 2u + 1u;
-                atomicMin(&first[e0.u], (uint32_t)(2 * p));
-                atomicMin(&first[e0.v], (uint32_t)(2 * p + 1));
-                atomicAdd(&gcount[e0.u], 1);
-                atomicAdd(&gcount[e0.v], 1);
-            } else if (h.slot < FR3D_SLOT_BP) {
-                const int a = h.i - base, b = h.j - base;
-                const int32_t *sl = tb.slot_label + ((int)h.slot * 32 + (h.code & 31)) * 2;
-                const int l0 = sl[0], l1 = sl[1];
-                const bool swap = h.slot == FR3D_SLOT_SO21 || h.slot == FR3D_SLOT_SR21;  // recorded for (nt2, nt1)
-                if (l0 < 0 || l0 >= n_labels || l1 >= n_labels) { s_err = 1; continue; }
-                const int cnt = l1 >= 0 ? 2 : 1;
-                const int k = atomicAdd(&s_napp, cnt);
-                alab[k] = l0; aa[k] = swap ? b : a; ab[k] = swap ? a : b; aseq[k] = (uint32_t)(2 * p);
-                atomicMin(&s_lfirst[l0], (uint32_t)(2 * p));
-                if (l1 >= 0) {                                                            // NA:765 / NA:775
-                    alab[k + 1] = l1; aa[k + 1] = swap ? a : b; ab[k + 1] = swap ? b : a; aseq[k + 1] = (uint32_t)(2 * p + 1);
-                    atomicMin(&s_lfirst[l1], (uint32_t)(2 * p + 1));
+        // ---- walk: positions by block scans, so that the appended rows and the basepair entries come out in the
+        // reference's recording order (their index IS their sequence number)
+        uint32_t *ent_hit = aval;                        // entry e (recording order) -> hit index * 2 + (1: recorded for u2)
+        {
+            int run_app = 0, run_ent = 0;
+            for (int p0 = 0; p0 < H; p0 += T) {
+                const int p = p0 + tid;
+                int cnt_app = 0, cnt_ent = 0, l0 = -1, l1 = -1, a = 0, b = 0;
+                uint32_t hidx = 0;
+                bool swap = false;
+                TailEntrySrc e0 = {0, 0, 0};
+                if (p < H) {
+                    hidx = TAIL_HIT_OF(p);
+                    const fr3d_hit_t h = hits[hidx];
+                    a = h.i - base; b = h.j - base;
+                    if (h.slot == FR3D_SLOT_BP) {
+                        e0 = tail_entry_of(h, 0, base, tb);
+                        cnt_ent = 2;
+                    } else if (h.slot < FR3D_SLOT_BP) {
+                        const int32_t *sl = tb.slot_label + ((int)h.slot * 32 + (h.code & 31)) * 2;
+                        l0 = sl[0]; l1 = sl[1];
+                        swap = h.slot == FR3D_SLOT_SO21 || h.slot == FR3D_SLOT_SR21;       // recorded for (nt2, nt1)
+                        if (l0 < 0 || l0 >= n_labels || l1 >= n_labels) { s_err = 1; l0 = -1; }
+                        else cnt_app = l1 >= 0 ? 2 : 1;
+                    }
                 }
+                int total;
+                const int ex = tail_block_scan(cnt_app | (cnt_ent << 16), s_w, total);
+                if (cnt_app) {
+                    const int k = run_app + (ex & 0xFFFF);
+                    alab[k] = l0; aa[k] = swap ? b : a; ab[k] = swap ? a : b;
+                    atomicMin(&s_lfirst[l0], (uint32_t)k);
+                    if (cnt_app == 2) {                                                       // NA:765 / NA:775
+                        alab[k + 1] = l1; aa[k + 1] = swap ? a : b; ab[k + 1] = swap ? b : a;
+                        atomicMin(&s_lfirst[l1], (uint32_t)(k + 1));
+                    }
+                }
+                if (cnt_ent) {
+                    const int e = run_ent + (ex >> 16);
+                    ent_hit[e] = hidx * 2u;
+                    ent_hit[e + 1] = hidx * 2u + 1u;
+                    ekey[e] = (tail_u64)(uint32_t)e0.u;                   // the nt for now; its first appearance below
+                    ekey[e + 1] = (tail_u64)(uint32_t)e0.v;
+                    atomicMin(&first[e0.u], (uint32_t)e);
+                    atomicMin(&first[e0.v], (uint32_t)(e + 1));
+                    atomicAdd(&gcount[e0.u], 1);
+                    atomicAdd(&gcount[e0.v], 1);
+                }
+                run_app += total & 0xFFFF;
+                run_ent += total >> 16;
             }
+            if (tid == 0) { s_napp = run_app; s_nent = run_ent; }
         }
         __syncthreads();
         const int nent = s_nent;
+        const int napp_walk = s_napp;
 
         TAIL_PHASE(2);
-        // ---- unit_id_to_basepairs in iteration order: nts by first appearance, entries by sequence (NA:1001-1013)
-        for (int e = tid; e < nent; e += T) {
-            const tail_u64 k = ekey[e];
-            ekey[e] = ((tail_u64)first[(int)(k >> 32)] << 32) | (k & 0xFFFFFFFFull);
-        }
-        tail_block_sort(ekey, eval, nent, s_key, s_val);
+        // ---- unit_id_to_basepairs in iteration order: nts by first appearance, entries by sequence (NA:1001-1013);
+        // key = (entry index of the nt's first entry, entry index), sorted without values
+        for (int e = tid; e < nent; e += T) ekey[e] = ((tail_u64)first[(int)ekey[e]] << 32) | (tail_u64)(uint32_t)e;
+        tail_block_sort_keys<tail_u64>(ekey, nent, tail_smem);
         for (int q = tid; q < nent; q += T) {
-            const uint32_t ev = eval[q];
+            const uint32_t ev = ent_hit[(int)(ekey[q] & 0xFFFFFFFFull)];
+            eval[q] = ev;
             const TailEntrySrc e = tail_entry_of(hits[ev >> 1], (int)(ev & 1u), base, tb);
             e_u[q] = e.u; e_v[q] = e.v; e_lab[q] = e.lab; e_flag[q] = 0;
             if (e.lab < 0 || e.lab >= n_labels) s_err = 1;
@@ -522,27 +583,43 @@ tail_structure_kernel(fr3d_nts_t nts, fr3d_tail_ident_t id, fr3d_tail_tables_t t
         __syncthreads();
 
         TAIL_PHASE(4);
-        // ---- emission (NA:1026-1044): the first entry of an unordered pair in iteration order, unless removed
-        for (int q = tid; q < nent; q += T) {
-            const int fl = e_flag[q];
-            if (fl & TAIL_F_REMOVED) continue;
-            const int u = e_u[q], v = e_v[q];
-            bool is_first = true;
-            for (int q2 = gstart[u]; q2 < q; ++q2)
-                if (e_v[q2] == v) is_first = false;
-            const int t0 = gstart[v], t1 = t0 + gcount[v];
-            for (int q2 = t0; q2 < t1 && q2 < q; ++q2)
-                if (e_v[q2] == u) is_first = false;
-            if (!is_first) continue;
-            int lab = e_lab[q];
-            if (lab < 0 || lab >= n_labels) continue;
-            if (fl & TAIL_F_NEAR) {
-                lab = tb.labels[lab].near;
-                if (lab < 0 || lab >= n_labels) { s_err = 1; continue; }
+        // ---- emission (NA:1026-1044): the first entry of an unordered pair in iteration order, unless removed; the
+        // emitted rows follow the walk's rows in entry order (block scan)
+        {
+            int running = napp_walk;
+            for (int q0 = 0; q0 < nent; q0 += T) {
+                const int q = q0 + tid;
+                int lab = -1, u = 0, v = 0;
+                if (q < nent) {
+                    const int fl = e_flag[q];
+                    if (!(fl & TAIL_F_REMOVED)) {
+                        u = e_u[q]; v = e_v[q];
+                        bool is_first = true;
+                        for (int q2 = gstart[u]; q2 < q; ++q2)
+                            if (e_v[q2] == v) is_first = false;
+                        const int t0 = gstart[v], t1 = t0 + gcount[v];
+                        for (int q2 = t0; q2 < t1 && q2 < q; ++q2)
+                            if (e_v[q2] == u) is_first = false;
+                        if (is_first) {
+                            lab = e_lab[q];
+                            if (lab >= 0 && lab < n_labels && (fl & TAIL_F_NEAR)) {
+                                lab = tb.labels[lab].near;
+                                if (lab < 0 || lab >= n_labels) s_err = 1;
+                            }
+                            if (lab < 0 || lab >= n_labels) lab = -1;
+                        }
+                    }
+                }
+                int total;
+                const int ex = tail_block_scan(lab >= 0 ? 1 : 0, s_w, total);
+                if (lab >= 0) {
+                    const int k = running + ex;
+                    alab[k] = lab; aa[k] = u; ab[k] = v;
+                    atomicMin(&s_lfirst[lab], (uint32_t)k);
+                }
+                running += total;
             }
-            const int k = atomicAdd(&s_napp, 1);
-            alab[k] = lab; aa[k] = u; ab[k] = v; aseq[k] = (uint32_t)(2 * H + q);
-            atomicMin(&s_lfirst[lab], (uint32_t)(2 * H + q));
+            if (tid == 0) s_napp = running;
         }
         __syncthreads();
         const int napp = s_napp;
@@ -550,7 +627,6 @@ tail_structure_kernel(fr3d_nts_t nts, fr3d_tail_ident_t id, fr3d_tail_tables_t t
         TAIL_PHASE(5);
         // ---- nested cWW pairs (NA:1077-1131): candidates keyed (chain, span, start), greedy in that order per chain
         tail_u64 *nkey = hkey;           // the hit keys are no longer needed
-        uint32_t *nval = hval;
         for (int k = tid; k < napp; k += T) {
             if (!(tb.labels[alab[k]].flags & 4u)) continue;
             const int a = aa[k], b = ab[k];
@@ -564,11 +640,10 @@ tail_structure_kernel(fr3d_nts_t nts, fr3d_tail_ident_t id, fr3d_tail_tables_t t
             const int i1 = min(ia, ib), i2 = max(ia, ib);
             const int x = atomicAdd(&s_nnest, 1);
             nkey[x] = ((tail_u64)(uint32_t)(nt_chain[a] - c_lo) << 48) | ((tail_u64)(uint32_t)(i2 - i1) << 24) | (tail_u64)(uint32_t)i1;
-            nval[x] = 0;
         }
         __syncthreads();
         const int nnest = s_nnest;
-        tail_block_sort(nkey, nval, nnest, s_key, s_val);
+        tail_block_sort_keys<tail_u64>(nkey, nnest, tail_smem);
         for (int c = c_lo; c < c_hi; ++c) {                                  // identity: every index maps to itself
             const int eo = id.chain_ends_off[c] - ends_lo, len = id.chain_ends_off[c + 1] - id.chain_ends_off[c];
             for (int i = tid; i < len; i += T) ends_base[eo + i] = i;
@@ -630,23 +705,34 @@ tail_structure_kernel(fr3d_nts_t nts, fr3d_tail_ident_t id, fr3d_tail_tables_t t
             s_lrank[l] = (uint16_t)r;
         }
         __syncthreads();
-        for (int k = tid; k < napp; k += T) {
-            akey[k] = ((tail_u64)s_lrank[alab[k]] << 32) | aseq[k];
-            aval[k] = (uint32_t)k;
+        // rows ordered by (label rank, append index): the append index is the payload, in the low bits of the key -
+        // 32-bit keys (10 + 22 bits) unless the structure has more than four million rows
+        const bool keys32 = napp < (1 << 22);
+        uint32_t *akey32 = reinterpret_cast<uint32_t *>(akey);
+        if (keys32) {
+            for (int k = tid; k < napp; k += T) akey32[k] = ((uint32_t)s_lrank[alab[k]] << 22) | (uint32_t)k;
+            tail_block_sort_keys<uint32_t>(akey32, napp, tail_smem);
+        } else {
+            for (int k = tid; k < napp; k += T) akey[k] = ((tail_u64)s_lrank[alab[k]] << 32) | (tail_u64)(uint32_t)k;
+            tail_block_sort_keys<tail_u64>(akey, napp, tail_smem);
         }
-        tail_block_sort(akey, aval, napp, s_key, s_val);
+#define TAIL_ROW_OF(r) (keys32 ? (int)(akey32[r] & ((1u << 22) - 1u)) : (int)(akey[r] & 0xFFFFFFFFull))
 
         TAIL_PHASE(8);
         // ---- covalent links (NA:1181-1210): nts by (model symmetry chain, index), successive keys of one string
         tail_u64 *ckey = ws.ckey + lo;
-        uint32_t *cval = ws.cval + lo;
         for (int u = tid; u < n; u += T) {
             const int ix = meta[(size_t)u * FR3D_META_INTS + 4];
             ckey[u] = ((tail_u64)(uint32_t)id.nt_cov[lo + u] << (TAIL_INDEX_BITS + TAIL_MAX_NT_BITS)) |
                       ((tail_u64)(uint32_t)ix << TAIL_MAX_NT_BITS) | (tail_u64)u;
-            cval[u] = (uint32_t)u;
         }
-        tail_block_sort(ckey, cval, n, s_key, s_val);
+        __syncthreads();
+        {       // files usually list the nts of a chain in sequence order: then the keys are sorted already
+            int unsorted = 0;
+            for (int u = tid; u + 1 < n; u += T) unsorted |= ckey[u] > ckey[u + 1];
+            if (__syncthreads_or(unsorted)) tail_block_sort_keys<tail_u64>(ckey, n, tail_smem);
+        }
+#define TAIL_COV_NT(r) ((int)(ckey[r] & ((1ull << TAIL_MAX_NT_BITS) - 1ull)))
         for (int r = tid; r < n; r += T) {                   // rows of sorted position r = members of the next key
             const tail_u64 kr = ckey[r] >> TAIL_MAX_NT_BITS;
             int e = r + 1;
@@ -682,7 +768,7 @@ tail_structure_kernel(fr3d_nts_t nts, fr3d_tail_ident_t id, fr3d_tail_tables_t t
         for (int r0 = 0; r0 < napp; r0 += T) {
             const int r = r0 + tid;
             int k = 0, lab = 0, cnt = 0;
-            if (r < napp) { k = (int)aval[r]; lab = alab[k]; cnt = 1 + (int)(tb.labels[lab].flags & 1u); }
+            if (r < napp) { k = TAIL_ROW_OF(r); lab = alab[k]; cnt = 1 + (int)(tb.labels[lab].flags & 1u); }
             int total;
             const int ex = tail_block_scan(cnt, s_w, total);
             if (r < napp) {
@@ -702,10 +788,10 @@ tail_structure_kernel(fr3d_nts_t nts, fr3d_tail_ident_t id, fr3d_tail_tables_t t
             int total;
             const int ex = tail_block_scan(cnt, s_w, total);
             if (cnt) {
-                const int u1 = (int)cval[r], e = gstart[r];
+                const int u1 = TAIL_COV_NT(r), e = gstart[r];
                 const int i1 = meta[(size_t)u1 * FR3D_META_INTS + 4];
                 for (int x = 0; x < cnt; ++x) {
-                    const int u2 = (int)cval[e + x];
+                    const int u2 = TAIL_COV_NT(e + x);
                     fr3d_row_t row;
                     row.label = FR3D_LABEL_COVALENT | (meta[(size_t)u2 * FR3D_META_INTS + 4] - i1);
                     row.nt1 = u1 + base; row.nt2 = u2 + base; row.crossing = -1;
@@ -716,6 +802,9 @@ tail_structure_kernel(fr3d_nts_t nts, fr3d_tail_ident_t id, fr3d_tail_tables_t t
         }
         TAIL_PHASE(10);
     }
+#undef TAIL_HIT_OF
+#undef TAIL_ROW_OF
+#undef TAIL_COV_NT
 }
 
 }  // namespace fr3d
