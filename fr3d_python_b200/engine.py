@@ -629,6 +629,38 @@ class Pipeline(object):
             res.row_start[ch.s0:ch.s1] += ch.graph_row_off
         return res
 
+    def enqueue_graph(self, upload=True, extra=None):
+        """enqueue() as ONE CUDA graph launch on the current stream (captured on first use, one graph per value of
+        `upload`); extra(): more work on the current stream to capture behind the chunks (e.g. copying counters into
+        a send block).  Falls back to plain enqueue() + extra() if the capture fails."""
+        eng, torch = self.eng, self.eng.torch
+        graphs = self.__dict__.setdefault("_enqueue_graphs", {})
+        key = bool(upload)
+        if key not in graphs:
+            self.enqueue(upload=upload)                     # warm-up outside the capture
+            if extra is not None:
+                extra()
+            torch.cuda.synchronize(eng.device)
+            launches0 = eng.launches
+            try:
+                g = torch.cuda.CUDAGraph()
+                side = torch.cuda.Stream(device=eng.device)
+                with torch.cuda.graph(g, stream=side):
+                    self.enqueue(upload=upload)
+                    if extra is not None:
+                        extra()
+                graphs[key] = (g, eng.launches - launches0)
+            except Exception:
+                graphs[key] = None
+        ent = graphs[key]
+        if ent is None:
+            self.enqueue(upload=upload)
+            if extra is not None:
+                extra()
+            return
+        ent[0].replay()
+        eng.launches += ent[1]
+
     def enqueue(self, upload=True):
         """Issue one pass - per chunk: H2D (unless upload is False: the records of the previous pass are still in
         HBM), K1..K4, tail - on the chunk streams and make the CURRENT stream wait for

@@ -124,8 +124,9 @@ class ShardedAnnotator(object):
     rank 0 (None elsewhere)."""
 
     def __init__(self, batch, categories, focused_basepair_cutoffs=None, ideal_hydrogen_bonds=None, rank=None,
-                 world_size=None, device=None, n_chunks=2):
+                 world_size=None, device=None, n_chunks=2, use_graph=True):
         import torch
+        self.use_graph = use_graph
         from .classifiers import NA_pairwise_interactions as NA
         from .engine import Engine, Pipeline, pin_batch
         dist = _dist()
@@ -201,10 +202,15 @@ class ShardedAnnotator(object):
         torch = self.torch
         dist = _dist()
         if self.pipe is not None:
-            self.pipe.enqueue(upload=upload)
-            for k, ch in enumerate(self.pipe.chunks):      # the search / classify counters travel in the header
-                hdr = self.off[k][0]
-                self.block[hdr:hdr + HDR_INTS].view(torch.int64)[4:12].copy_(ch.plan.counters, non_blocking=True)
+            def headers():                                 # the search / classify counters travel in the header
+                for k, ch in enumerate(self.pipe.chunks):
+                    hdr = self.off[k][0]
+                    self.block[hdr:hdr + HDR_INTS].view(torch.int64)[4:12].copy_(ch.plan.counters, non_blocking=True)
+            if self.use_graph:
+                self.pipe.enqueue_graph(upload=upload, extra=headers)      # the rank's whole pass: one graph launch
+            else:
+                self.pipe.enqueue(upload=upload)
+                headers()
         if self.world > 1:
             if self.rank == 0:
                 dist.gather(self.block, list(self.recv.unbind(0)), dst=0)

@@ -505,6 +505,10 @@ def test_sharded_annotator_single_rank_equals_annotate_batch():
         assert as_plain(got[3]) == as_plain(ref[3])
         again = sh.run(upload=False)                      # on the records already in HBM (bench.py's resident loop)
         assert all(np.array_equal(again.rows_of(s), ref.rows_of(s)) for s in range(batch.n_structures))
+        for _ in range(2):                                # graph replays (captured above) keep giving the same rows
+            assert all(np.array_equal(sh.run().rows_of(s), ref.rows_of(s)) for s in range(batch.n_structures))
+    plain = parallel.ShardedAnnotator(batch, ALL9, rank=0, world_size=1, n_chunks=2, use_graph=False).run()
+    assert all(np.array_equal(plain.rows_of(s), ref.rows_of(s)) for s in range(batch.n_structures))
 
 
 def test_repeated_passes_over_resident_records_are_identical():
