@@ -907,3 +907,22 @@ def test_native_cif_ingest_to_annotations(golden):
     b = NA.annotate_batch(reader.cif_to_batch(text), ALL9)
     assert len(a) == 2
     assert as_plain(a[0]) == as_plain(b[0]) == as_plain(a[1])
+
+
+def test_large_structures_device_tail_equals_host_tail():
+    """The tail's large-structure paths: S_1S72_like (2 844 nt, ~7 k hits: key-only network over the global workspace)
+    and C3 (25 280 nt in ONE structure, ~63 k hits: the packed hit key no longer fits 64 bits, so the (key, value)
+    network runs; 160 chains) against the host form of the tail - rows, order, dict key order."""
+    import time
+    base = synthetic.pack_base()
+    for copies, lattice, seed in ((9, (3, 3, 1), 1072), (80, (5, 4, 4), 25000)):
+        big = synthetic.make_tiled_structure(base, copies, lattice, seed=seed, pdb="BIG%d" % copies)
+        t0 = time.perf_counter()
+        dev = NA.annotate_batch(big, ALL9, as_arrays=True)
+        t_dev = time.perf_counter() - t0
+        host = NA.annotate_batch(big, ALL9, tail="host")
+        d = dev[0]
+        assert list(d[0].keys()) == list(host[0][0].keys())
+        assert as_plain(d) == as_plain(host[0])
+        assert dev.n_rows > 5 * big.n
+        print("%d nt: device path %.1f ms, %d rows" % (big.n, 1e3 * t_dev, dev.n_rows))
