@@ -100,6 +100,34 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
+def time_ordering(torch, D, N, with_cpu):
+    """The step that follows the matrix in fr3d/search/FR3D.py:446-467: treePenalizedPathLength(matrix, 100, 59) of the
+    search copy + reorderSymmetricMatrix, on leading blocks of the matrix that is already in HBM (K8).  The reference
+    caps this at 300 candidates (MAXCANDIDATESHEATMAP); its algorithm (oracle port, pinned) is timed at that size."""
+    from fr3d_python_b200.search import orderBySimilarity as sobs
+    out = {"what": "search/orderBySimilarity.treePenalizedPathLength(block, 100, 59) + reorderSymmetricMatrix on the leading "
+                   "n x n block of the resident matrix (tree penalty by average linkage, 100 greedy insertions, one CTA each)",
+           "sizes": {}}
+    for n in (300, 1000, 3000):
+        if n > N:
+            break
+        block = D[:n, :n].contiguous()
+        sobs.treePenalizedPathLength(block, 100, 59)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        order = sobs.treePenalizedPathLength(block, 100, 59)
+        sobs.reorderSymmetricMatrix(block, order)
+        torch.cuda.synchronize()
+        out["sizes"][str(n)] = {"ms": 1e3 * (time.perf_counter() - t0)}
+        if n == 300 and with_cpu:
+            from oracle import ordering_oracle as oo
+            host = block.cpu().numpy()
+            t0 = time.perf_counter()
+            ref = oo.treePenalizedPathLength_search(host, 100, 59)
+            out["sizes"]["300"].update({"cpu_port_ms": 1e3 * (time.perf_counter() - t0), "equal_to_cpu_port": bool(ref == order)})
+    return out
+
+
 def main(args):
     import bench
     rank = int(os.environ.get("RANK", "0"))
@@ -183,6 +211,9 @@ def main(args):
         sub = Dh[:64, :64]
         chk = {"symmetric": bool(np.array_equal(Dh[:512, :512], Dh[:512, :512].T)), "diagonal_zero": bool(np.all(np.diag(sub) == 0)),
                "sum_first_1024x1024": float(Dh[:1024, :1024].sum())}
+    ordering = None
+    if rank == 0 and world == 1 and D is not None:
+        ordering = time_ordering(torch, D, N, not args.no_cpu_baseline)
     clocks = sampler.stop() if sampler is not None else None
     vals = torch.tensor([ms_total, t_e2e, kernel_ms], dtype=torch.float64, device=eng.device)
     if world > 1:
@@ -210,6 +241,8 @@ def main(args):
                              "algorithmic_flops_per_pair": flop_pair, "model": "154 n + 600 flop per instance pair, FMA = 2 "
                              "(SURVEY §8(d)); the kernel executes more (Newton on the quartic, two adjugates)"},
                 "matrix_check": chk, "clocks": clocks}
+        if ordering is not None:
+            line["ordering"] = ordering
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
         print(json.dumps(line))

@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("FR3D_B200_LIB") or os.path.join(_HERE, "lib", "libfr3
 CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 
-ABI_VERSION = 3          # FR3D_ABI_VERSION of include/fr3d_b200.h
+ABI_VERSION = 4          # FR3D_ABI_VERSION of include/fr3d_b200.h
 BASE_SLOTS = 16
 BB_SLOTS = 10
 META_INTS = 8
@@ -35,7 +35,8 @@ EXPORTS = ["fr3d_version", "fr3d_last_error", "fr3d_init", "fr3d_upload_tables",
            "fr3d_discrepancy_all_vs_all", "fr3d_discrepancy_one_vs_many",
            "fr3d_tail_workspace", "fr3d_annotation_tail", "fr3d_discrepancy_rows_upper", "fr3d_discrepancy_assemble",
            "fr3d_fp64_fma_probe", "fr3d_ingest_last_error", "fr3d_ingest_tables", "fr3d_cif_parse", "fr3d_ingest_sizes",
-           "fr3d_ingest_fill", "fr3d_ingest_free"]
+           "fr3d_ingest_fill", "fr3d_ingest_free",
+           "fr3d_order_workspace", "fr3d_tree_penalty", "fr3d_penalized_distance", "fr3d_order_paths", "fr3d_reorder_symmetric"]
 LABEL_COVALENT = 0x40000000
 TAIL_MAX_LABELS = 1024
 TAIL_MAX_NT = 1 << 17
@@ -174,6 +175,12 @@ def load():
         lib.fr3d_tail_workspace.restype = C.c_size_t
         lib.fr3d_annotation_tail.argtypes = [C.POINTER(NtsStruct), C.POINTER(TailIdentStruct), C.POINTER(TailTablesStruct),
                                              vp, i64, vp, i32, vp, C.c_size_t, vp, i64, vp, vp, vp, vp]
+        lib.fr3d_order_workspace.argtypes = [i32, i32]
+        lib.fr3d_order_workspace.restype = C.c_size_t
+        lib.fr3d_tree_penalty.argtypes = [vp, i32, vp, vp, vp, C.c_size_t, vp]
+        lib.fr3d_penalized_distance.argtypes = [vp, vp, i32, i32, dbl, vp, vp, vp]
+        lib.fr3d_order_paths.argtypes = [vp, i32, vp, i32, i32, vp, vp, vp, vp, C.c_size_t, vp]
+        lib.fr3d_reorder_symmetric.argtypes = [vp, i32, vp, i32, vp, vp]
         lib.fr3d_ingest_last_error.restype = C.c_char_p
         lib.fr3d_ingest_tables.argtypes = [C.c_char_p, C.c_size_t]
         lib.fr3d_cif_parse.argtypes = [C.POINTER(C.c_char_p), C.POINTER(C.c_int64), i32, i32, C.POINTER(vp)]
@@ -183,7 +190,7 @@ def load():
         lib.fr3d_ingest_free.restype = None
         for name in EXPORTS:
             if name not in ("fr3d_last_error", "fr3d_pair_search_workspace", "fr3d_classify_workspace",
-                            "fr3d_radius_search_workspace", "fr3d_tail_workspace", "fr3d_ingest_last_error",
+                            "fr3d_radius_search_workspace", "fr3d_tail_workspace", "fr3d_order_workspace", "fr3d_ingest_last_error",
                             "fr3d_ingest_free"):
                 getattr(lib, name).restype = C.c_int
         _lib = lib

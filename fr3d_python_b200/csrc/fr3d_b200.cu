@@ -24,6 +24,7 @@
 #include "unit_annotation.cuh"
 #include "radius_search.cuh"
 #include "tail.cuh"
+#include "ordering.cuh"
 
 #ifndef FR3D_BPH_MINB
 #define FR3D_BPH_MINB 6      // base-phosphate list kernel, min blocks per SM 3 / 4 / 6 / 8: classify 0.840 / 0.835 / 0.807 / 0.815 ms
@@ -567,6 +568,98 @@ int fr3d_discrepancy_one_vs_many(const double *q_centers, const double *q_rots, 
     const int block = 128;
     fr3d::discrepancy_one_vs_many_kernel<<<(M + block - 1) / block, block, 0, static_cast<cudaStream_t>(stream)>>>(
         q_centers, q_rots, q_has_rot, centers, rots, has_rot, M, n, cutoff, angle_weight, center_weight, out);
+    CUDA_TRY(cudaGetLastError());
+    return FR3D_OK;
+}
+
+// ---- K8: ordering by similarity (csrc/ordering.cuh) ----------------------------------------------------------------
+namespace {
+struct OrderCarve { fr3d::LinkWs link; fr3d::PathWs path; size_t bytes; };
+OrderCarve carve_order(void *workspace, int32_t n, int32_t reps) {
+    OrderCarve c;
+    size_t off = 0;
+    char *base = static_cast<char *>(workspace);
+    auto take = [&](size_t bytes) { char *p = base ? base + off : nullptr; off += align_up(bytes, 256); return p; };
+    const size_t N = (size_t)(n > 0 ? n : 0), R = (size_t)(reps > 0 ? reps : 0);
+    c.link.W = reinterpret_cast<double *>(take(8 * N * N));
+    c.link.m_h = reinterpret_cast<double *>(take(8 * N));
+    int32_t **ints[] = {&c.link.size, &c.link.chain, &c.link.next, &c.link.head, &c.link.tail, &c.link.m_head,
+                        &c.link.m_nx, &c.link.m_ny, &c.link.leaf, &c.link.pos};
+    for (int32_t **p : ints) *p = reinterpret_cast<int32_t *>(take(4 * N));
+    c.path.edge = reinterpret_cast<double *>(take(8 * 2 * N * R));
+    c.path.path = reinterpret_cast<int32_t *>(take(4 * 2 * N * R));
+    c.bytes = off;
+    return c;
+}
+}  // namespace
+
+size_t fr3d_order_workspace(int32_t n, int32_t reps) { return carve_order(nullptr, n, reps).bytes; }
+
+int fr3d_tree_penalty(const double *distance, int32_t n, double *penalty, int32_t *flags, void *workspace,
+                      size_t workspace_bytes, void *stream) {
+    if (!distance || !penalty || !flags || !workspace) return fail(FR3D_E_ARG, "NULL argument");
+    if (n < 0 || n > 46340) return fail(FR3D_E_ARG, "n must be in [0, 46340]");
+    if (workspace_bytes < fr3d_order_workspace(n, 0)) return fail(FR3D_E_ARG, "workspace too small");
+    int sm_count = 148;
+    if (int rc = require_device(false, &sm_count)) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CUDA_TRY(cudaMemsetAsync(flags, 0, sizeof(int32_t), st));
+    if (n == 0) return FR3D_OK;
+    CUDA_TRY(cudaMemsetAsync(penalty, 0, sizeof(double) * (size_t)n * n, st));
+    if (n == 1) return FR3D_OK;
+    fr3d::LinkWs ws = carve_order(workspace, n, 0).link;
+    const long long total = (long long)n * n;
+    const long long want = (total + 255) / 256;
+    fr3d::linkage_prepare_kernel<<<(int)(want < sm_count * 8 ? want : sm_count * 8), 256, 0, st>>>(distance, n, ws.W, flags);
+    fr3d::linkage_chain_kernel<<<1, fr3d::ORD_THREADS, 0, st>>>(ws, n, flags);
+    const int slices = n >= 2048 ? 64 : (n >= 256 ? 8 : 1);
+    fr3d::cophenetic_fill_kernel<<<dim3(n - 1, slices), 256, 0, st>>>(ws, n, penalty, flags);
+    CUDA_TRY(cudaGetLastError());
+    return FR3D_OK;
+}
+
+int fr3d_penalized_distance(const double *distance, const double *penalty, int32_t n, int32_t mode, double strength,
+                            double *sums, double *out, void *stream) {
+    if (!distance || !penalty || !sums || !out) return fail(FR3D_E_ARG, "NULL argument");
+    if (n < 0 || n > 46340 || mode < 0 || mode > 2) return fail(FR3D_E_ARG, "bad n or mode");
+    int sm_count = 148;
+    if (int rc = require_device(false, &sm_count)) return rc;
+    if (n == 0) return FR3D_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long total = (long long)n * n;
+    if (mode >= 1) fr3d::sequential_sum_kernel<<<2, 256, 0, st>>>(distance, penalty, total, sums);
+    const long long want = (total + 255) / 256;
+    fr3d::penalized_distance_kernel<<<(int)(want < sm_count * 8 ? want : sm_count * 8), 256, 0, st>>>(
+        distance, penalty, total, mode, strength, sums, out);
+    CUDA_TRY(cudaGetLastError());
+    return FR3D_OK;
+}
+
+int fr3d_order_paths(const double *distance, int32_t n, const int32_t *start_orders, int32_t reps, int32_t mode,
+                     int32_t *orders, double *scores, double *reductions, void *workspace, size_t workspace_bytes,
+                     void *stream) {
+    if (!distance || !start_orders || !orders || !scores || !reductions || !workspace) return fail(FR3D_E_ARG, "NULL argument");
+    if (n < 2 || n > 46340) return fail(FR3D_E_ARG, "n must be in [2, 46340]");
+    if (reps < 1 || mode < 1 || mode > 3) return fail(FR3D_E_ARG, "reps >= 1 and mode in {1 greedy, 2 two-opt, 3 both}");
+    if (workspace_bytes < fr3d_order_workspace(n, reps)) return fail(FR3D_E_ARG, "workspace too small");
+    if (int rc = require_device(false, nullptr)) return rc;
+    fr3d::PathWs ws = carve_order(workspace, n, reps).path;
+    fr3d::order_paths_kernel<<<reps, fr3d::ORD_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(
+        distance, n, start_orders, mode, ws, orders, scores, reductions);
+    CUDA_TRY(cudaGetLastError());
+    return FR3D_OK;
+}
+
+int fr3d_reorder_symmetric(const double *distance, int32_t n, const int32_t *order, int32_t zero_diagonal, double *out,
+                           void *stream) {
+    if (!distance || !order || !out) return fail(FR3D_E_ARG, "NULL argument");
+    if (n < 0 || n > 46340) return fail(FR3D_E_ARG, "n must be in [0, 46340]");
+    int sm_count = 148;
+    if (int rc = require_device(false, &sm_count)) return rc;
+    if (n == 0) return FR3D_OK;
+    const long long want = ((long long)n * n + 255) / 256;
+    fr3d::reorder_symmetric_kernel<<<(int)(want < sm_count * 8 ? want : sm_count * 8), 256, 0,
+                                     static_cast<cudaStream_t>(stream)>>>(distance, n, order, zero_diagonal, out);
     CUDA_TRY(cudaGetLastError());
     return FR3D_OK;
 }

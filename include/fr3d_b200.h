@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define FR3D_ABI_VERSION 3
+#define FR3D_ABI_VERSION 4
 
 #define FR3D_OK 0
 #define FR3D_E_CUDA (-1)      /* a CUDA runtime call failed; see fr3d_last_error */
@@ -332,6 +332,35 @@ int fr3d_discrepancy_one_vs_many(const double *q_centers, const double *q_rots, 
                                  const double *centers, const double *rots, const uint8_t *has_rot,
                                  int32_t M, int32_t n, double cutoff /* < 0: no cutoff */, double angle_weight,
                                  const double *center_weight /* [n] or NULL */, double *out, void *stream);
+
+/* ---- K8: ordering by similarity of the all-vs-all matrix ---------------------------------------
+ * Replaces treePenalizedPathLength and its parts in both copies of the reference, fr3d/ordering/orderBySimilarity.py
+ * (:10-41 treePenalty, :43-64 normalizePenaltyMatrix, :66-80 twoOptSwap, :82-115 greedyInsertionPathLength, :131-186,
+ * :237-245) and fr3d/search/orderBySimilarity.py (:9-113; called at fr3d/search/FR3D.py:463), on a matrix resident in
+ * HBM (e.g. the output of fr3d_discrepancy_all_vs_all).  All matrices are device double [n][n], row major; results are
+ * bit-identical to the reference's floats (explicitly rounded operations in its operation order).  The starting orders
+ * (random.shuffle of the GLOBAL Python generator) come from the caller. */
+size_t fr3d_order_workspace(int32_t n, int32_t reps);   /* reps = 0: enough for fr3d_tree_penalty */
+/* treePenalty: penalty[i][j] = height of the average-linkage merge (scipy linkage(squareform(d), "average"), restated as
+ * its nearest-neighbour chain) that joins i and j.  flags (device int32[1]): 1 = not symmetric, 2 = non-zero diagonal,
+ * 4 = non-finite entry - the inputs scipy refuses with ValueError; penalty is undefined then. */
+int fr3d_tree_penalty(const double *distance, int32_t n, double *penalty, int32_t *flags, void *workspace,
+                      size_t workspace_bytes, void *stream);
+/* mode 0: out = distance + strength * penalty (search copy, strength 5); mode 1: penalty first scaled by
+ * sum(distance) / sum(penalty) when that sum is positive (normalizePenaltyMatrix; the two sums run sequentially over the
+ * rows like the reference's loops and are left in sums[0], sums[1], device double[2]); mode 2: out = the scaled penalty
+ * alone. */
+int fr3d_penalized_distance(const double *distance, const double *penalty, int32_t n, int32_t mode, double strength,
+                            double *sums, double *out, void *stream);
+/* One repetition per CTA.  mode bit 0: greedy insertion of start_orders[r][2..] into the path start_orders[r][0..1];
+ * bit 1: twoOptSwap of the result (or of start_orders[r] itself when bit 0 is clear).  orders [reps][n], scores [reps]
+ * (path score of the greedy insertion, 0 without it), reductions [reps] (the 2-opt's distance_reduction). */
+int fr3d_order_paths(const double *distance, int32_t n, const int32_t *start_orders, int32_t reps, int32_t mode,
+                     int32_t *orders, double *scores, double *reductions, void *workspace, size_t workspace_bytes,
+                     void *stream);
+/* reorderSymmetricMatrix: out[i][j] = out[j][i] = distance[order[i]][order[j]], j >= i (zero_diagonal: j > i, search copy). */
+int fr3d_reorder_symmetric(const double *distance, int32_t n, const int32_t *order, int32_t zero_diagonal, double *out,
+                           void *stream);
 
 /* ---- native mmCIF ingest (host code) -------------------------------------------------------------
  * Replaces, for the nucleotides of a file, fr3d.cif.reader.Cif(handle).structure() (fr3d/cif/reader.py:440-629: operators,

@@ -748,3 +748,82 @@ def main_cif():
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "cif":
     main_cif()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Ordering by similarity (last part): the UNMODIFIED fr3d/ordering/orderBySimilarity.py and
+# fr3d/search/orderBySimilarity.py (the copy search/FR3D.py:463 calls) on seeded matrices.
+def ordering_matrices():
+    rng = np.random.Generator(np.random.PCG64(8165))
+    mats = {}
+    for n in (3, 4, 5, 6, 7, 17, 60, 150):
+        pts = rng.uniform(0, 1, (n, 3))
+        if n >= 60:                                   # clustered points: the case the penalty is made for
+            pts = rng.uniform(0, 1, (6, 3))[rng.integers(0, 6, n)] + rng.normal(0, 0.05, (n, 3))
+        mats["points_%d" % n] = np.sqrt(((pts[:, None, :] - pts[None, :, :]) ** 2).sum(-1))
+    for n in (12, 40):                                # tie-laden: L1 distances of small-integer grid points
+        pts = rng.integers(0, 4, (n, 2)).astype(float)
+        mats["ties_%d" % n] = np.abs(pts[:, None, :] - pts[None, :, :]).sum(-1)
+    mats["zeros_5"] = np.zeros((5, 5))
+    # discrepancies of perturbed sarcin-ricin instances (what FR3D.py:433-442 feeds the ordering)
+    from fr3d.geometry.discrepancy import matrix_discrepancy
+    with gzip.open(os.path.join(GOLD, "frames_1s72_sarcin.json.gz"), "rt") as f:
+        frames = json.load(f)
+    base_c = np.array([fr["center"] for fr in frames][:7])
+    base_r = np.array([fr["rotation"] for fr in frames][:7])
+    cen, rot = make_instances(base_c, base_r, 40, 5001)
+    with contextlib.redirect_stdout(io.StringIO()):
+        d = np.zeros((40, 40))
+        for i in range(40):
+            for j in range(i + 1, 40):
+                d[i][j] = d[j][i] = matrix_discrepancy(list(cen[i]), list(rot[i]), list(cen[j]), list(rot[j]))
+    mats["sarcin_40"] = d
+    for k in mats:
+        np.fill_diagonal(mats[k], 0.0)
+        mats[k] = (mats[k] + mats[k].T) / 2
+    return mats
+
+
+def main_ordering():
+    import importlib.util
+    import random
+    from fr3d.ordering import orderBySimilarity as obs
+    sys.path.insert(0, os.path.join(rf.REF, "fr3d", "search"))
+    spec = importlib.util.spec_from_file_location("search_orderBySimilarity",
+                                                  os.path.join(rf.REF, "fr3d", "search", "orderBySimilarity.py"))
+    sobs = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(sobs)
+    out = {}
+    for name, d in ordering_matrices().items():
+        n = d.shape[0]
+        case = {"distance": d.tolist()}
+        pen = obs.treePenalty(d)
+        assert np.array_equal(pen, sobs.treePenalty(d))
+        case["penalty"] = pen.tolist()
+        case["normalized"] = np.asarray(obs.normalizePenaltyMatrix(d, pen)).tolist()
+        random.seed(n + 100)
+        start = list(range(n))
+        random.shuffle(start)
+        path, score = obs.greedyInsertionPathLength(d, list(start))
+        swapped, reduction = obs.twoOptSwap(d, list(path))
+        case["start"] = start
+        case["greedy"] = [[int(v) for v in path], float(score)]
+        case["twoopt"] = [[int(v) for v in swapped], float(reduction)]
+        swapped2, reduction2 = obs.twoOptSwap(d, list(start))          # 2-opt from a random order: many swaps
+        case["twoopt_from_start"] = [[int(v) for v in swapped2], float(reduction2)]
+        case["tppl"] = {}
+        for reps, seed, strength in ((10, 1, 0.5), (5, 7, 1.0), (3, 2, 0.0)):
+            order = obs.treePenalizedPathLength(d, reps, seed, strength)
+            case["tppl"]["%d,%d,%g" % (reps, seed, strength)] = {
+                "order": [int(v) for v in order],
+                "standard": [int(v) for v in obs.standardOrder(d, list(order))]}
+        case["tppl_search"] = {}
+        for reps, seed in ((100, 59), (7, 3)):
+            case["tppl_search"]["%d,%d" % (reps, seed)] = [int(v) for v in sobs.treePenalizedPathLength(d, reps, seed)]
+        case["reordered"] = np.asarray(obs.reorderSymmetricMatrix(d, case["tppl"]["10,1,0.5"]["order"])).tolist()
+        out[name] = case
+    dump("ordering.json.gz", out)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "ordering":
+    main_ordering()
