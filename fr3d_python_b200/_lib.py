@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("FR3D_B200_LIB") or os.path.join(_HERE, "lib", "libfr3
 CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 
-ABI_VERSION = 4          # FR3D_ABI_VERSION of include/fr3d_b200.h
+ABI_VERSION = 5          # FR3D_ABI_VERSION of include/fr3d_b200.h
 BASE_SLOTS = 16
 BB_SLOTS = 10
 META_INTS = 8
@@ -36,7 +36,8 @@ EXPORTS = ["fr3d_version", "fr3d_last_error", "fr3d_init", "fr3d_upload_tables",
            "fr3d_tail_workspace", "fr3d_annotation_tail", "fr3d_discrepancy_rows_upper", "fr3d_discrepancy_assemble",
            "fr3d_fp64_fma_probe", "fr3d_ingest_last_error", "fr3d_ingest_tables", "fr3d_cif_parse", "fr3d_ingest_sizes",
            "fr3d_ingest_fill", "fr3d_ingest_free",
-           "fr3d_order_workspace", "fr3d_tree_penalty", "fr3d_penalized_distance", "fr3d_order_paths", "fr3d_reorder_symmetric"]
+           "fr3d_order_workspace", "fr3d_tree_penalty", "fr3d_penalized_distance", "fr3d_order_paths", "fr3d_reorder_symmetric",
+           "fr3d_possibilities_first", "fr3d_possibilities_extend"]
 LABEL_COVALENT = 0x40000000
 TAIL_MAX_LABELS = 1024
 TAIL_MAX_NT = 1 << 17
@@ -69,6 +70,18 @@ class StaticTables(C.Structure):
                 ("so_r2max", C.c_double * N_PARENTS),
                 ("hull_r2max", C.c_double * N_PARENTS),
                 ("hull_r2in", C.c_double * N_PARENTS)]
+
+
+SEARCH_MAX_POSITIONS = 16
+
+
+class SearchQueryStruct(C.Structure):
+    _fields_ = [("n_positions", C.c_int32), ("n_units", C.c_int32), ("symbolic", C.c_int32), ("reserved", C.c_int32),
+                ("rowptr", C.c_void_p * (SEARCH_MAX_POSITIONS * SEARCH_MAX_POSITIONS)),
+                ("cols", C.c_void_p * (SEARCH_MAX_POSITIONS * SEARCH_MAX_POSITIONS)),
+                ("universe", C.c_void_p * SEARCH_MAX_POSITIONS), ("centers", C.c_void_p),
+                ("perm_dist", C.c_double * (SEARCH_MAX_POSITIONS * SEARCH_MAX_POSITIONS)),
+                ("cutoff", C.c_double * SEARCH_MAX_POSITIONS)]
 
 
 class TailIdentStruct(C.Structure):
@@ -181,6 +194,8 @@ def load():
         lib.fr3d_penalized_distance.argtypes = [vp, vp, i32, i32, dbl, vp, vp, vp]
         lib.fr3d_order_paths.argtypes = [vp, i32, vp, i32, i32, vp, vp, vp, vp, C.c_size_t, vp]
         lib.fr3d_reorder_symmetric.argtypes = [vp, i32, vp, i32, vp, vp]
+        lib.fr3d_possibilities_first.argtypes = [vp, vp, i64, i32, vp, vp, vp, i64, vp]
+        lib.fr3d_possibilities_extend.argtypes = [vp, i32, vp, vp, i64, i32, vp, vp, vp, i64, vp, vp]
         lib.fr3d_ingest_last_error.restype = C.c_char_p
         lib.fr3d_ingest_tables.argtypes = [C.c_char_p, C.c_size_t]
         lib.fr3d_cif_parse.argtypes = [C.POINTER(C.c_char_p), C.POINTER(C.c_int64), i32, i32, C.POINTER(vp)]

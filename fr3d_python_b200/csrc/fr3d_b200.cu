@@ -25,6 +25,7 @@
 #include "radius_search.cuh"
 #include "tail.cuh"
 #include "ordering.cuh"
+#include "possibilities.cuh"
 
 #ifndef FR3D_BPH_MINB
 #define FR3D_BPH_MINB 6      // base-phosphate list kernel, min blocks per SM 3 / 4 / 6 / 8: classify 0.840 / 0.835 / 0.807 / 0.815 ms
@@ -660,6 +661,52 @@ int fr3d_reorder_symmetric(const double *distance, int32_t n, const int32_t *ord
     const long long want = ((long long)n * n + 255) / 256;
     fr3d::reorder_symmetric_kernel<<<(int)(want < sm_count * 8 ? want : sm_count * 8), 256, 0,
                                      static_cast<cudaStream_t>(stream)>>>(distance, n, order, zero_diagonal, out);
+    CUDA_TRY(cudaGetLastError());
+    return FR3D_OK;
+}
+
+// ---- K9: FR3D search, constraint intersection (csrc/possibilities.cuh) ---------------------------------------------
+int fr3d_possibilities_first(const fr3d_search_query_t *dev_query, const int32_t *pairs, int64_t n_pairs, int32_t emit,
+                             int64_t *counts, int32_t *out_frags, double *out_errs, int64_t out_cap, void *stream) {
+    if (!dev_query || !counts || (n_pairs > 0 && !pairs)) return fail(FR3D_E_ARG, "NULL argument");
+    if (n_pairs < 0 || (emit && (!out_frags || out_cap < 0))) return fail(FR3D_E_ARG, "bad size or NULL output");
+    int sm_count = 148;
+    if (int rc = require_device(false, &sm_count)) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long want = (n_pairs + 255) / 256;
+    const int grid = (int)(want < 1 ? 1 : (want < sm_count * 8 ? want : sm_count * 8));
+    static_assert(sizeof(long long) == sizeof(int64_t), "int64");
+    long long *cnt = reinterpret_cast<long long *>(counts);
+    if (!emit) {
+        fr3d::poss_first_pairs_kernel<<<grid, 256, 0, st>>>(dev_query, pairs, n_pairs, cnt);
+        fr3d::poss_scan_kernel<<<1, 1024, 0, st>>>(cnt, n_pairs);
+    } else {
+        fr3d::poss_first_emit_kernel<<<grid, 256, 0, st>>>(dev_query, pairs, n_pairs, cnt, out_frags, out_errs, out_cap);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return FR3D_OK;
+}
+
+int fr3d_possibilities_extend(const fr3d_search_query_t *dev_query, int32_t level, const int32_t *frags, const double *errs,
+                              int64_t n_frags, int32_t emit, int64_t *counts, int32_t *out_frags, double *out_errs,
+                              int64_t out_cap, int32_t *flags, void *stream) {
+    if (!dev_query || !counts || !flags || (n_frags > 0 && !frags)) return fail(FR3D_E_ARG, "NULL argument");
+    if (level < 1 || level >= FR3D_SEARCH_MAX_POSITIONS - 1) return fail(FR3D_E_ARG, "level must be in [1, 14]");
+    if (n_frags < 0 || (emit && (!out_frags || out_cap < 0))) return fail(FR3D_E_ARG, "bad size or NULL output");
+    int sm_count = 148;
+    if (int rc = require_device(false, &sm_count)) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long want = (n_frags + fr3d::POSS_WARPS - 1) / fr3d::POSS_WARPS;
+    const int grid = (int)(want < 1 ? 1 : (want < sm_count * 16 ? want : sm_count * 16));
+    long long *cnt = reinterpret_cast<long long *>(counts);
+    if (!emit) {
+        fr3d::poss_extend_kernel<false><<<grid, fr3d::POSS_WARPS * 32, 0, st>>>(dev_query, level, frags, errs, n_frags, cnt,
+                                                                                nullptr, nullptr, 0, flags);
+        fr3d::poss_scan_kernel<<<1, 1024, 0, st>>>(cnt, n_frags);
+    } else {
+        fr3d::poss_extend_kernel<true><<<grid, fr3d::POSS_WARPS * 32, 0, st>>>(dev_query, level, frags, errs, n_frags, cnt,
+                                                                               out_frags, out_errs, out_cap, flags);
+    }
     CUDA_TRY(cudaGetLastError());
     return FR3D_OK;
 }

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define FR3D_ABI_VERSION 4
+#define FR3D_ABI_VERSION 5
 
 #define FR3D_OK 0
 #define FR3D_E_CUDA (-1)      /* a CUDA runtime call failed; see fr3d_last_error */
@@ -361,6 +361,35 @@ int fr3d_order_paths(const double *distance, int32_t n, const int32_t *start_ord
 /* reorderSymmetricMatrix: out[i][j] = out[j][i] = distance[order[i]][order[j]], j >= i (zero_diagonal: j > i, search copy). */
 int fr3d_reorder_symmetric(const double *distance, int32_t n, const int32_t *order, int32_t zero_diagonal, double *out,
                            void *stream);
+
+/* ---- K9: FR3D search, intersection of the pairwise constraint lists (VERDICT round 1, N3 second half) ------------------
+ * Replaces getPossibilities / extendFragment (fr3d/search/search.py:263-375) over buildSecondElementList (:377-398): the
+ * possibilities are grown one position per call, breadth first, one warp per fragment; output fragments are in
+ * lexicographic order (the reference's order is that of Python set iteration; the SET is the same).
+ * The query lives in DEVICE memory (the caller uploads this struct); [a][b] tables are indexed a * 16 + b, a < b. */
+#define FR3D_SEARCH_MAX_POSITIONS 16
+typedef struct {
+    int32_t n_positions, n_units, symbolic /* Q["type"] == "symbolic" */, reserved;
+    const int32_t *rowptr[FR3D_SEARCH_MAX_POSITIONS * FR3D_SEARCH_MAX_POSITIONS]; /* CSR of listOfPairs[a][b] by first element:
+                                                  [n_units + 1]; NULL = "full" */
+    const int32_t *cols[FR3D_SEARCH_MAX_POSITIONS * FR3D_SEARCH_MAX_POSITIONS];   /* second elements, ascending, unique */
+    const uint8_t *universe[FR3D_SEARCH_MAX_POSITIONS];   /* [n_units] membership of universe[a]; needed where a list [a][b] is full */
+    const double *centers;                                /* [n_units][3] units[u]["centers"]; geometric / mixed only */
+    double perm_dist[FR3D_SEARCH_MAX_POSITIONS * FR3D_SEARCH_MAX_POSITIONS];      /* Q["permutedDistance"] */
+    double cutoff[FR3D_SEARCH_MAX_POSITIONS];             /* Q["cutoff"][m] */
+} fr3d_search_query_t;
+/* The first pairs (search.py:351-366): pairs [n_pairs][2] = listOfPairs[0][1], sorted.  emit = 0: counts[i] (device
+ * int64 [n_pairs + 1]) = exclusive prefix of "pair i starts a fragment", counts[n_pairs] = their number; emit = 1 (same
+ * counts): out_frags [total][2], out_errs [total] (geometric / mixed: the pair's distance error; NULL for symbolic). */
+int fr3d_possibilities_first(const fr3d_search_query_t *dev_query, const int32_t *pairs, int64_t n_pairs, int32_t emit,
+                             int64_t *counts, int32_t *out_frags, double *out_errs, int64_t out_cap, void *stream);
+/* One step of extendFragment for all fragments at once: frags [n_frags][level + 1] -> out_frags [total][level + 2] (position
+ * level + 1 added), errs / out_errs the running distance errors.  emit = 0 counts (counts [n_frags + 1] as above), emit = 1
+ * writes (nothing if counts[n_frags] > out_cap).  flags (device int32[1]) bit 0: the position has only "full" lists -
+ * "Query is underspecified" (search.py:295-300). */
+int fr3d_possibilities_extend(const fr3d_search_query_t *dev_query, int32_t level, const int32_t *frags, const double *errs,
+                              int64_t n_frags, int32_t emit, int64_t *counts, int32_t *out_frags, double *out_errs,
+                              int64_t out_cap, int32_t *flags, void *stream);
 
 /* ---- native mmCIF ingest (host code) -------------------------------------------------------------
  * Replaces, for the nucleotides of a file, fr3d.cif.reader.Cif(handle).structure() (fr3d/cif/reader.py:440-629: operators,

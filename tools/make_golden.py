@@ -827,3 +827,122 @@ def main_ordering():
 
 if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "ordering":
     main_ordering()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# FR3D search, constraint intersection (search.py:263-398).  fr3d/search/search.py is imported UNMODIFIED; its
+# `from query_processing import synonym` cannot work (query_processing.py has an IndentationError under Python 3), so that
+# one module is stubbed - none of the functions used here touches it.
+def import_reference_search():
+    import types
+    sys.path.insert(0, os.path.join(rf.REF, "fr3d", "search"))
+    if "query_processing" not in sys.modules:
+        stub = types.ModuleType("query_processing")
+        stub.synonym = {}
+        sys.modules["query_processing"] = stub
+    import search as ref_search
+    return ref_search
+
+
+def possibility_scenarios():
+    """Inputs of the intersection: (Q, listOfPairs, universe, centers) per scenario, before reorderPositions."""
+    import pair_processing as pp
+    with gzip.open(os.path.join(GOLD, "frames_1gid_full.json.gz"), "rt") as f:
+        frames = json.load(f)
+    centers = np.array([fr["center"] for fr in frames], dtype=float)
+    models = ["1"] * len(centers)
+    n_units = len(centers)
+    out = {}
+    # geometric queries: a unit and its nearest neighbours as the query motif (query_processing.py:886-914, :1113-1121)
+    for name, seed_unit, k, disc in (("geometric_4", 20, 4, 0.6), ("geometric_5", 150, 5, 0.5), ("geometric_3", 77, 3, 0.8),
+                                     ("geometric_2", 5, 2, 0.5)):
+        d = np.linalg.norm(centers - centers[seed_unit], axis=1)
+        motif = [int(v) for v in np.argsort(d)[:k]]
+        Q = {"type": "geometric", "numpositions": k, "discrepancy": disc, "locationWeight": [1.0] * k,
+             "centers": [centers[u] for u in motif]}
+        Q["requireddistanceminimum"] = {i: {} for i in range(k)}
+        Q["requireddistancemaximum"] = {i: {} for i in range(k)}
+        Q["SSCutoff"] = [None] * k
+        Q["largestMaxRange"] = 0
+        Q["distance"] = np.zeros((k, k))
+        s = 0
+        for i in range(k):
+            s = s + Q["locationWeight"][i]
+            Q["SSCutoff"][i] = (k ** 2) * (disc ** 2) * s
+            for j in range(i + 1, k):
+                Q["distance"][i][j] = Q["distance"][j][i] = np.linalg.norm(Q["centers"][i] - Q["centers"][j])
+                delta = (np.sqrt(2.0) if k > 2 else 1.0) * k * disc
+                for a, b in ((i, j), (j, i)):
+                    Q["requireddistanceminimum"][a][b] = Q["distance"][i][j] - delta
+                    Q["requireddistancemaximum"][a][b] = Q["distance"][i][j] + delta
+                Q["largestMaxRange"] = max(Q["largestMaxRange"], Q["distance"][i][j] + delta)
+        Q["cutoff"] = [float(v) for v in Q["SSCutoff"]]
+        pl = pp.get_pairlist(Q, models, centers)
+        listOfPairs = {i: {j: list(pl[i][j]) for j in range(i + 1, k)} for i in range(k - 1)}
+        universe = [set(range(n_units)) for _ in range(k)]
+        out[name] = (Q, listOfPairs, universe, centers, motif)
+    # a mixed query: the geometric lists of geometric_4 with one list thinned like an interaction constraint would
+    Q, lop, uni, cen, motif = out["geometric_4"]
+    rng = np.random.Generator(np.random.PCG64(263))
+    lop2 = {i: {j: list(v) for j, v in d.items()} for i, d in lop.items()}
+    keep = rng.random(len(lop2[1][2])) < 0.4
+    lop2[1][2] = [p for p, kp in zip(lop2[1][2], keep) if kp]
+    Q2 = dict(Q)
+    Q2["type"] = "mixed"
+    out["mixed_4"] = (Q2, lop2, uni, cen, motif)
+    # symbolic queries on random pair lists, with "full" lists and universes that do not contain every unit
+    def rand_pairs(n):
+        a = rng.integers(0, 120, n)
+        b = rng.integers(0, 120, n)
+        return sorted(set((int(x), int(y)) for x, y in zip(a, b) if x != y))
+    for name, k, full in (("symbolic_4_full", 4, ((0, 2), (0, 3), (1, 3))), ("symbolic_5", 5, ((0, 4), (1, 3))),
+                          ("symbolic_reordered", 4, ((0, 2), (1, 2), (0, 3))), ("symbolic_halt_3", 3, ((0, 2), (1, 2))),
+                          ("symbolic_halt_2", 2, ((0, 1),))):
+        lop = {i: {} for i in range(k - 1)}
+        for i in range(k - 1):
+            for j in range(i + 1, k):
+                lop[i][j] = "full" if (i, j) in full else rand_pairs(900)
+        universe = [set(int(v) for v in rng.choice(120, 100, replace=False)) for _ in range(k)]
+        Q = {"type": "symbolic", "numpositions": k}
+        out[name] = (Q, lop, universe, None, None)
+    return out
+
+
+def main_possibilities():
+    rs = import_reference_search()
+    out = {}
+    for name, (Q, listOfPairs, universe, centers, motif) in possibility_scenarios().items():
+        k = Q["numpositions"]
+        case = {"type": Q["type"], "numpositions": k, "motif": motif,
+                "listOfPairs": {"%d,%d" % (i, j): (v if v == "full" else [[int(a), int(b)] for a, b in v])
+                                for i, d in listOfPairs.items() for j, v in d.items()},
+                "universe": [sorted(int(v) for v in u) for u in universe]}
+        if centers is not None:
+            case["centers"] = centers.tolist()
+            case["distance"] = Q["distance"].tolist()
+            case["cutoff"] = Q["cutoff"]
+        ifedata = {"units": [{"centers": c} for c in centers]} if centers is not None else {"units": []}
+        Q.update({"MAXTIME": 1e9, "CPUTimeUsed": 0, "errorMessage": [], "halt": False})
+        with contextlib.redirect_stdout(io.StringIO()):
+            if k > 2 or listOfPairs[0][1] != "full":
+                lop, uni, perm = rs.reorderPositions(listOfPairs, universe)
+            else:
+                lop, uni, perm = listOfPairs, universe, list(range(k))
+            if Q["type"] != "symbolic":
+                Q["permutedDistance"] = np.zeros((k, k))
+                for i in range(k):
+                    for j in range(k):
+                        Q["permutedDistance"][i][j] = Q["distance"][perm[i]][perm[j]]
+            sel = rs.buildSecondElementList(Q, lop, uni, ifedata)
+            Q, poss = rs.getPossibilities(Q, ifedata, perm, sel, k, lop)
+        case["perm"] = [int(p) for p in perm]
+        case["possibilities_sorted"] = sorted([int(v) for v in p] for p in poss)
+        case["halt"] = bool(Q["halt"])
+        case["errorMessage"] = list(Q["errorMessage"][:1])
+        print(name, "perm", perm, "possibilities", len(poss), "halt", Q["halt"])
+        out[name] = case
+    dump("possibilities.json.gz", out)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "possibilities":
+    main_possibilities()
