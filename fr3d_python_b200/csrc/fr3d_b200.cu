@@ -377,6 +377,8 @@ TailCarve carve_tail(void *workspace, int64_t hit_cap, int32_t n_nt, int32_t n_s
     w.seg_cnt = reinterpret_cast<int32_t *>(take(4 * S));
     w.seg_off = reinterpret_cast<int32_t *>(take(4 * (S + 1)));
     w.seg_cur = reinterpret_cast<int32_t *>(take(4 * S));
+    w.nt_struct = reinterpret_cast<int32_t *>(take(4 * n));
+    w.overflow = reinterpret_cast<int32_t *>(take(4));
     w.hkey = reinterpret_cast<unsigned long long *>(take(8 * H));
     w.hval = reinterpret_cast<uint32_t *>(take(4 * H));
     w.ekey = reinterpret_cast<unsigned long long *>(take(16 * H));
@@ -425,13 +427,14 @@ int fr3d_annotation_tail(const fr3d_nts_t *nts, const fr3d_tail_ident_t *ident, 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     fr3d::TailWs ws = carve_tail(workspace, hit_cap, nts->n_nt, ident->n_struct, ident->n_ends).ws;
     const int S = ident->n_struct;
-    fr3d::tail_reset_kernel<<<(S + 256) / 256, 256, 0, st>>>(ws, S, tail_counters);
+    const int reset_threads = (S + 1 > nts->n_nt ? S + 1 : nts->n_nt);
+    fr3d::tail_reset_kernel<<<(reset_threads + 255) / 256, 256, 0, st>>>(ws, *ident, nts->n_nt, hit_cap, tail_counters);
     if (S > 0) {
         const long long want = (hit_cap + 255) / 256;
         const long long cap_blocks = (long long)sm_count * 8;
         const int grid = (int)(want < 1 ? 1 : (want < cap_blocks ? want : cap_blocks));
-        fr3d::tail_count_kernel<<<grid, 256, 0, st>>>(hits, hit_cap, counters, index_offset, *ident, ws);
-        fr3d::tail_scan_kernel<<<1, 1024, 0, st>>>(ws, S);
+        fr3d::tail_bin_kernel<<<grid, 256, 0, st>>>(hits, hit_cap, counters, index_offset, *ident, ws, tail_counters);
+        fr3d::tail_scan_kernel<<<1, 1024, 0, st>>>(ws, S);                        // both return at once unless a structure
         fr3d::tail_scatter_kernel<<<grid, 256, 0, st>>>(hits, hit_cap, counters, index_offset, *ident, ws, tail_counters);
         const int blocks = S < sm_count * 7 ? S : sm_count * 7;
         fr3d::tail_structure_kernel<<<blocks, fr3d::TAIL_THREADS, fr3d::TAIL_SMEM, st>>>(

@@ -7,8 +7,10 @@
 //   calculate_crossing_numbers                                    NA:1057-1179
 //   annotate_covalent_connections                                 NA:1181-1210
 //
-// Hit records arrive unordered (K4 appends them with atomics).  Three small kernels bin them by structure
-// (count -> scan -> scatter, with the sort key (rank, nt1, nt2, slot) that reproduces the reference's cube walk);
+// Hit records arrive unordered (K4 appends them with atomics).  They are binned by structure with the sort key
+// (rank, nt1, nt2, slot) that reproduces the reference's cube walk - in ONE pass into segments whose capacity is the
+// structure's share of hit_cap by nt count (tail_bin_kernel, one atomic per warp and structure); only when a structure
+// has more hits than its share do the exact scan -> scatter kernels run (they return at once otherwise);
 // then ONE thread block per structure does everything else on integer ids:
 //   sort the structure's hits                       -> the order in which the reference records results
 //   walk them: non-basepair hits append (label, a, b) rows; basepair hits add one entry to each partner's list
@@ -41,7 +43,9 @@ constexpr size_t TAIL_SMEM = (size_t)TAIL_SORT_CAP * sizeof(unsigned long long);
 struct TailWs {
     int32_t *seg_cnt;             // [S]     hits per structure
     int32_t *seg_off;             // [S + 1]
-    int32_t *seg_cur;             // [S]
+    int32_t *seg_cur;             // [S]     = the structure's hit count after tail_bin_kernel
+    int32_t *nt_struct;           // [n]     structure of every nt
+    int32_t *overflow;            // [1]     a structure's hits did not fit its share: exact scan + scatter take over
     unsigned long long *hkey;     // [H]     hits of a structure: sort key; later the nested-cWW candidates
     uint32_t *hval;               // [H]     hit index
     unsigned long long *ekey;     // [2H]    basepair entries: (first appearance of u, sequence)
@@ -84,18 +88,57 @@ __device__ __forceinline__ int tail_find_struct(const int32_t *__restrict__ off,
     return lo;
 }
 
-__global__ void tail_reset_kernel(TailWs ws, int n_struct, int64_t *tc) {
+// per structure: zero cursors, segment = the structure's share of hit_cap by nt count; per nt: its structure
+__global__ void tail_reset_kernel(TailWs ws, fr3d_tail_ident_t id, int n_nt, int64_t hit_cap, int64_t *tc) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < n_struct) { ws.seg_cnt[t] = 0; ws.seg_cur[t] = 0; }
-    if (t == 0) { tc[0] = 0; tc[1] = 0; tc[2] = 0; tc[3] = 0; }
+    const int n_struct = id.n_struct;
+    if (t <= n_struct) {
+        if (t < n_struct) { ws.seg_cnt[t] = 0; ws.seg_cur[t] = 0; }
+        const long long total = id.struct_off[n_struct];
+        ws.seg_off[t] = total > 0 ? (int32_t)((hit_cap * (long long)id.struct_off[t]) / total) : 0;
+    }
+    if (t < n_nt) ws.nt_struct[t] = n_struct > 0 ? tail_find_struct(id.struct_off, n_struct, t) : 0;
+    if (t == 0) { tc[0] = 0; tc[1] = 0; tc[2] = 0; tc[3] = 0; *ws.overflow = 0; }
 }
 
-__global__ void tail_count_kernel(const fr3d_hit_t *__restrict__ hits, int64_t hit_cap, const int64_t *counters,
-                                  int32_t index_offset, fr3d_tail_ident_t id, TailWs ws) {
+__device__ __forceinline__ tail_u64 tail_hit_key(const fr3d_hit_t &hit, int32_t index_offset, int lo) {
+    // (rank, nt1, nt2, slot): rank = first nt of nt1's cube * 16 + stencil entry (search.cuh), all local to the structure
+    const int i = hit.i - index_offset, j = hit.j - index_offset;
+    const tail_u64 rank = (tail_u64)(uint32_t)(hit.rank - 16 * index_offset - 16 * lo);
+    return (rank << (2 * TAIL_MAX_NT_BITS + 4)) | ((tail_u64)(uint32_t)(i - lo) << (TAIL_MAX_NT_BITS + 4)) |
+           ((tail_u64)(uint32_t)(j - lo) << 4) | (tail_u64)hit.slot;
+}
+
+// One pass: hit -> its structure's segment.  Hits of one cube sit next to each other in the stream, so the lanes of a
+// warp mostly agree on the structure: one atomicAdd per (warp, structure).  seg_cur[s] ends as the exact hit count of
+// the structure whether or not its hits fitted.
+__global__ void tail_bin_kernel(const fr3d_hit_t *__restrict__ hits, int64_t hit_cap, const int64_t *counters,
+                                int32_t index_offset, fr3d_tail_ident_t id, TailWs ws, int64_t *tc) {
     const long long n_hits = min((long long)counters[1], (long long)hit_cap);
-    for (long long h = (long long)blockIdx.x * blockDim.x + threadIdx.x; h < n_hits; h += (long long)gridDim.x * blockDim.x) {
-        const int s = tail_find_struct(id.struct_off, id.n_struct, hits[h].i - index_offset);
-        atomicAdd(&ws.seg_cnt[s], 1);
+    const int lane = threadIdx.x & 31;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long h0 = (long long)blockIdx.x * blockDim.x + threadIdx.x - lane; h0 < n_hits; h0 += stride) {
+        const long long h = h0 + lane;
+        const bool live = h < n_hits;
+        fr3d_hit_t hit;
+        int s = -1 - lane;                                   // idle lanes: a group of their own
+        if (live) {
+            hit = hits[h];
+            s = ws.nt_struct[hit.i - index_offset];
+        }
+        const unsigned peers = __match_any_sync(0xFFFFFFFFu, s);
+        if (!live) continue;
+        const int leader = __ffs(peers) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(&ws.seg_cur[s], __popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        const int at = base + __popc(peers & ((1u << lane) - 1u));
+        const int lo = id.struct_off[s];
+        if (id.struct_off[s + 1] - lo > (1 << TAIL_MAX_NT_BITS)) { atomicOr((tail_u64 *)&tc[2], 1ull); continue; }
+        const int seg = ws.seg_off[s];
+        if (at >= ws.seg_off[s + 1] - seg) { *ws.overflow = 1; continue; }
+        ws.hkey[seg + at] = tail_hit_key(hit, index_offset, lo);
+        ws.hval[seg + at] = (uint32_t)h;
     }
 }
 
@@ -103,12 +146,13 @@ __global__ void tail_count_kernel(const fr3d_hit_t *__restrict__ hits, int64_t h
 __global__ void __launch_bounds__(1024) tail_scan_kernel(TailWs ws, int n_struct) {
     __shared__ int s_w[32];
     __shared__ int s_run;
+    if (!*ws.overflow) return;                   // every structure fitted its share: the segments stand as they are
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) s_run = 0;
     __syncthreads();
     for (int base = 0; base < n_struct; base += 1024) {
         const int t = base + threadIdx.x;
-        const int c = t < n_struct ? ws.seg_cnt[t] : 0;
+        const int c = t < n_struct ? ws.seg_cur[t] : 0;      // exact counts left by tail_bin_kernel
         int incl = c;
 #pragma unroll
         for (int off = 1; off < 32; off <<= 1) {
@@ -139,20 +183,15 @@ __global__ void __launch_bounds__(1024) tail_scan_kernel(TailWs ws, int n_struct
 
 __global__ void tail_scatter_kernel(const fr3d_hit_t *__restrict__ hits, int64_t hit_cap, const int64_t *counters,
                                     int32_t index_offset, fr3d_tail_ident_t id, TailWs ws, int64_t *tc) {
+    if (!*ws.overflow) return;
     const long long n_hits = min((long long)counters[1], (long long)hit_cap);
     for (long long h = (long long)blockIdx.x * blockDim.x + threadIdx.x; h < n_hits; h += (long long)gridDim.x * blockDim.x) {
         const fr3d_hit_t hit = hits[h];
-        const int i = hit.i - index_offset, j = hit.j - index_offset;
-        const int s = tail_find_struct(id.struct_off, id.n_struct, i);
+        const int s = ws.nt_struct[hit.i - index_offset];
         const int lo = id.struct_off[s];
-        const int n = id.struct_off[s + 1] - lo;
-        if (n > (1 << TAIL_MAX_NT_BITS)) { atomicOr((tail_u64 *)&tc[2], 1ull); continue; }
-        // (rank, nt1, nt2, slot): rank = first nt of nt1's cube * 16 + stencil entry (search.cuh), all local to the structure
-        const tail_u64 rank = (tail_u64)(uint32_t)(hit.rank - 16 * index_offset - 16 * lo);
-        const tail_u64 key = (rank << (2 * TAIL_MAX_NT_BITS + 4)) | ((tail_u64)(uint32_t)(i - lo) << (TAIL_MAX_NT_BITS + 4)) |
-                             ((tail_u64)(uint32_t)(j - lo) << 4) | (tail_u64)hit.slot;
-        const int pos = ws.seg_off[s] + atomicAdd(&ws.seg_cur[s], 1);
-        ws.hkey[pos] = key;
+        if (id.struct_off[s + 1] - lo > (1 << TAIL_MAX_NT_BITS)) continue;        // flagged by tail_bin_kernel
+        const int pos = ws.seg_off[s] + atomicAdd(&ws.seg_cnt[s], 1);
+        ws.hkey[pos] = tail_hit_key(hit, index_offset, lo);
         ws.hval[pos] = (uint32_t)h;
     }
 }
@@ -356,7 +395,7 @@ tail_structure_kernel(fr3d_nts_t nts, fr3d_tail_ident_t id, fr3d_tail_tables_t t
         long long phase_t0 = clock64();
 #endif
         const int lo = id.struct_off[s], n = id.struct_off[s + 1] - lo;
-        const int hb = ws.seg_off[s], H = ws.seg_off[s + 1] - hb;
+        const int hb = ws.seg_off[s], H = ws.seg_cur[s];
         const int base = index_offset + lo;                                  // hit.i - base = position in the structure
         if (n > (1 << TAIL_MAX_NT_BITS)) {                                   // flagged by the scatter kernel
             if (tid == 0) { row_start[s] = -1; row_count[s] = 0; }
