@@ -454,7 +454,11 @@ def test_device_tail_in_the_pipeline_and_capacity_reruns():
     mask = NA.category_mask(ALL9)
     ref = NA.annotate_batch(batch, ALL9, as_arrays=True)
     pinned = pin_batch(torch, batch)
-    for chunks, caps in ((1, None), (5, None), (37, None), (3, (100, 100, 50))):
+    n_hits = len(eng.annotate_batch(batch, bt, mask)[0])
+    # (hit_cap = the exact hit count: the tail's one-pass binning by proportional shares overflows for every structure
+    # with more hits than the average and the exact scan + scatter path takes over)
+    for chunks, caps in ((1, None), (5, None), (37, None), (3, (100, 100, 50)), (1, (ref.n_pairs, n_hits, ref.n_rows)),
+                         (2, (ref.n_pairs, n_hits, ref.n_rows))):
         kw = {} if caps is None else {"pair_cap": caps[0], "hit_cap": caps[1], "row_cap": caps[2]}
         pipe = Pipeline(eng, batch, pinned, bt, mask, n_chunks=chunks, labels=labels, **kw)
         for _ in range(2):
