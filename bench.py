@@ -154,11 +154,14 @@ def run_reference_arm(args):
 
 def workload_config(args, structures, world, scaling=None):
     weak = scaling == "weak" and world > 1
-    return {"workload": "C4: synthetic batch of perturbed 1GID-scale structures (316 nt, seed 4000+k, sigma 0.10 A), "
-                        "all nine annotation categories, final rows in the reference's order (device tail included)",
+    heavy = getattr(args, "heavy", False)
+    return {"workload": ("C4 heavy variant: synthetic batch of perturbed S_1S72_like structures (9 tiled 1GID copies, 2 844 nt, "
+                         "seed 4000+k, sigma 0.10 A)" if heavy else
+                         "C4: synthetic batch of perturbed 1GID-scale structures (316 nt, seed 4000+k, sigma 0.10 A)") +
+                        ", all nine annotation categories, final rows in the reference's order (device tail included)",
             "structures": structures * world if weak else structures,
             "structures_per_gpu": structures if weak else structures / max(world, 1),
-            "nt_per_structure": 316,
+            "nt_per_structure": 2844 if heavy else 316,
             "l2_policy": "inputs larger than L2 at N = 1 (240 MB of nt records per pass vs 126 MB L2); a per-GPU shard "
                          "smaller than 200 MB (strong scaling at N > 1) gets a 256 MB buffer written between timed steps",
             "parallelism": "structures sharded by rank (LPT on nt count), no data-path collective; rows gathered to rank 0"}
@@ -256,6 +259,9 @@ def main():
     ap.add_argument("--instances", type=int, default=20000, help="c5: motif instances")
     ap.add_argument("--cpu-structures", type=int, default=0, help="CPU baseline sample (0 = 2 per core, max 128)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--heavy", action="store_true",
+                    help="C4 heavy variant (SURVEY §8(d)): every structure is S_1S72_like, 9 tiled copies = 2 844 nt (implies "
+                         "--no-cpu-baseline; not the headline configuration)")
     ap.add_argument("--chunks", type=int, default=8, help="chunks of the e2e pipeline per GPU")
     ap.add_argument("--no-graph", action="store_true", help="time Pipeline.run (one Python launch per kernel) instead of the CUDA graph")
     args = ap.parse_args()
@@ -263,6 +269,8 @@ def main():
     if args.impl == "reference":
         run_reference_arm(args)
         return
+    if args.heavy:
+        args.no_cpu_baseline = True
     if args.workload == "c5":
         import bench_c5
         return bench_c5.main(args)
@@ -304,6 +312,8 @@ def main():
     eng = Engine.get(local_rank)
     dev = eng.device
     base = synthetic.pack_base()
+    if args.heavy:
+        base = synthetic.make_tiled_structure(base, 9, (3, 3, 1), seed=1072, pdb="S1S72")
     S = args.structures
     focused = NA._default_focused(CATEGORIES['basepair'])
     bt, box_atoms, labels = NA._tables(focused, NA.load_ideal_basepair_hydrogen_bonds())
@@ -477,7 +487,7 @@ def main():
 
     # ---------------- through the public API (rank 0, N = 1): array API and tuples; packing included
     api = None
-    if world == 1 and rank == 0:
+    if world == 1 and rank == 0 and not args.heavy:
         batch = shared["full_batch"]
         pinned = pin_batch(torch, batch)
         NA.annotate_batch(batch, CATEGORIES, pinned=pinned, as_arrays=True)

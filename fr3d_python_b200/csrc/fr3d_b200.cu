@@ -114,6 +114,8 @@ fr3d::SearchWs carve(void *workspace, int32_t n_nt) {
     ws.cell_xyz = reinterpret_cast<int32_t *>(p); p += align_up(sizeof(int32_t) * 3 * (size_t)n_nt, 256);
     ws.cell_list = reinterpret_cast<int32_t *>(p); p += align_up(sizeof(int32_t) * (size_t)n_nt, 256);
     ws.n_cells = reinterpret_cast<int32_t *>(p); p += 256;
+    ws.cell_info = reinterpret_cast<int4 *>(p); p += align_up(sizeof(int4) * T, 256);
+    ws.sorted = reinterpret_cast<double2 *>(p); p += align_up(sizeof(double2) * 3 * (size_t)n_nt, 256);
     ws.table_mask = T - 1;
     return ws;
 }
@@ -216,6 +218,8 @@ size_t fr3d_pair_search_workspace(int32_t n_nt) {
     b += 4 * align_up(sizeof(int32_t) * T, 256);
     b += 3 * align_up(sizeof(int32_t) * (size_t)n_nt, 256);
     b += align_up(sizeof(int32_t) * 3 * (size_t)n_nt, 256);
+    b += align_up(sizeof(int4) * T, 256);                   // cell_info
+    b += align_up(sizeof(double2) * 3 * (size_t)n_nt, 256); // sorted
     return b + 512;
 }
 

@@ -31,6 +31,9 @@ struct SearchWs {
     int32_t *cell_xyz;         // [n][3]
     int32_t *cell_list;        // [n] table slots of the occupied cubes (any order)
     int32_t *n_cells;          // [1]
+    int4 *cell_info;           // [T] (cx, cy, cz, group) of the cube in the slot (written by the nt that claimed it)
+    double2 *sorted;           // [n][3] the search's view of an nt, in member order (cube by cube): (x, y), (z, n | glycosidic
+                               //        atom present), (chain, index, residue id, alt id) - 48 contiguous bytes per candidate
     uint32_t table_mask;       // T - 1
 };
 
@@ -74,6 +77,7 @@ __global__ void cell_assign_kernel(fr3d_nts_t nts, SearchWs ws, double cell_size
             uint32_t h = hash64(key) & ws.table_mask;
             while (true) {
                 const unsigned long long prev = atomicCAS(&ws.keys[h], HASH_EMPTY, key);
+                if (prev == HASH_EMPTY) ws.cell_info[h] = make_int4(cx, cy, cz, group);
                 if (prev == HASH_EMPTY || prev == key) break;
                 h = (h + 1) & ws.table_mask;
             }
@@ -134,6 +138,16 @@ __global__ void cell_fill_kernel(fr3d_nts_t nts, SearchWs ws) {
     if (slot >= 0) {
         const int pos = ws.start[slot] + atomicAdd(&ws.cursor[slot], 1);
         ws.members[pos] = n;
+        // the record the pair search reads: the members of a cube are neighbours in memory, so a warp's 32 candidates are
+        // a handful of contiguous runs instead of 32 scattered centre / meta rows (it was L2-sector bound on those gathers)
+        const int4 *m = reinterpret_cast<const int4 *>(nts.meta + (size_t)n * FR3D_META_INTS);
+        const int4 lo = m[0], hi = m[1];                    // meta[3..6] = chain, index, residue id, alt id
+        double2 *rec = ws.sorted + (size_t)pos * 3;
+        rec[0] = make_double2(nts.center[(size_t)n * 3 + 0], nts.center[(size_t)n * 3 + 1]);
+        rec[1] = make_double2(nts.center[(size_t)n * 3 + 2],
+                              __hiloint2double((nts.base_mask[n] & 1u) ? 1 : 0, n));
+        const int4 key = make_int4(lo.w, hi.x, hi.y, hi.z);
+        rec[2] = *reinterpret_cast<const double2 *>(&key);
     }
 }
 
@@ -152,46 +166,45 @@ __constant__ int8_t c_half_stencil[14][3] = {{0, 0, 0}, {0, 0, 1}, {0, 1, 0}, {0
                                              {1, 0, -1}, {1, 1, 0}, {1, 1, 1}, {1, 1, -1}, {1, -1, 0}, {1, -1, 1}, {1, -1, -1}};
 
 // One warp per occupied cube.  The 14 cube lookups of the half stencil (hash probe, count, start) are done once per
-// cube by 14 lanes, the member lists are concatenated into ONE candidate list, and the candidates' centre and
-// identity fields are staged in shared memory once; every nt1 of the cube then scans that list in full chunks of
-// 32 out of shared memory.  (One warp per nt1 repeated the probes and the gathers for each of the ~5 nts of a
-// cube, and an atomicAdd per ballot on the single append cursor made it atomic bound: 655 us -> 321 us -> this.)
-#ifndef FR3D_SEARCH_CAP
-#define FR3D_SEARCH_CAP 64
-#endif
+// cube by 14 lanes and the member lists are treated as ONE candidate list.  The nt1 of the cube (a batch of up to 32)
+// wait in shared memory; the candidates are taken 32 at a time, one per lane, and stay in REGISTERS while the lane
+// tests its candidate against every nt1 of the batch (four broadcast shared-memory loads per nt1) and collects the
+// accepting nt1 as a bit mask.  One atomicAdd per (batch, 32 candidates) places the pairs, written grouped by nt1.
+// History on the bench workload: one warp per nt1 655 us -> one append per warp 321 us -> one warp per cube with the
+// candidates staged in shared memory and a ballot per (nt1, 32 candidates) 166 us -> this (see profiles/README.md).
 #ifndef FR3D_SEARCH_MINB
-#define FR3D_SEARCH_MINB 10      // A/B on the bench workload (cap, blocks): (128, 7) 254 us, (96, 9) 223, (64, 10) 214, (64, 12) 214
+#define FR3D_SEARCH_MINB 8
 #endif
-constexpr int SEARCH_CAP = FR3D_SEARCH_CAP;          // candidates staged per segment
-constexpr int SEARCH_CHUNKS = SEARCH_CAP / 32;
 constexpr int SEARCH_WARPS = 4;
+#ifndef FR3D_SEARCH_GROUP
+#define FR3D_SEARCH_GROUP 1      // 2 / 4 x 32 candidates per atomicAdd were slower (0.183 / 0.188 vs 0.177 ms, profiles/ab_search_r2.log)
+#endif
+constexpr int SEARCH_GROUP = FR3D_SEARCH_GROUP;      // x 32 candidates per append
 
-struct SearchStage {
-    double xyz[SEARCH_CAP][3];           // candidates (nt2)
-    int32_t n2[SEARCH_CAP];
-    int32_t chain[SEARCH_CAP], index[SEARCH_CAP], resid[SEARCH_CAP], alt[SEARCH_CAP];
-    uint8_t s[SEARCH_CAP];
-    double q_xyz[32][3];                 // a batch of up to 32 nt1 of the cube
-    int32_t q_n1[32], q_chain[32], q_index[32], q_resid[32], q_alt[32];
-    unsigned kept[32][SEARCH_CHUNKS];    // ballots of (nt1, chunk)
+struct SearchBatch {                     // the nt1 of a cube, per warp
+    double xy[32][2];
+    double z[32];
+    int4 key[32];                        // chain, index, residue id, alt id
+    int32_t n1[32];                      // -1: no glycosidic atom (NA:674)
 };
 
 __global__ void __launch_bounds__(SEARCH_WARPS * 32, FR3D_SEARCH_MINB)
 pair_search_kernel(fr3d_nts_t nts, SearchWs ws, double cutoff, int32_t *__restrict__ pair_i,
                    int32_t *__restrict__ pair_j, int32_t *__restrict__ pair_rank, int64_t pair_cap, int64_t *counters) {
     constexpr unsigned ALL = 0xFFFFFFFFu;
-    __shared__ SearchStage stage[SEARCH_WARPS];
-    SearchStage &S = stage[threadIdx.x >> 5];
+    __shared__ __align__(16) SearchBatch batch[SEARCH_WARPS];
+    SearchBatch &Q = batch[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     const int n_cells = *ws.n_cells;
     const int warps_total = gridDim.x * SEARCH_WARPS;
+    const double c2 = cutoff * cutoff;
+    const double c2_hi = c2 * (1.0 + 1e-12), c2_lo = c2 * (1.0 - 1e-12), four_hi = 4.0 * (1.0 + 1e-12), four_lo = 4.0 * (1.0 - 1e-12);
     for (int w = blockIdx.x * SEARCH_WARPS + (threadIdx.x >> 5); w < n_cells; w += warps_total) {
         const int slot1 = ws.cell_list[w];
         const int cnt1 = ws.count[slot1], beg1 = ws.start[slot1];
         const int first1 = ws.first[slot1];
-        const int rep = ws.members[beg1];                   // any member: the cube's coordinates and group
-        const int cx = ws.cell_xyz[rep * 3 + 0], cy = ws.cell_xyz[rep * 3 + 1], cz = ws.cell_xyz[rep * 3 + 2];
-        const int group = nts.meta[(size_t)rep * FR3D_META_INTS + 2];
+        const int4 info = ws.cell_info[slot1];              // the cube's coordinates and group: one load, no walk
+        const int cx = info.x, cy = info.y, cz = info.z, group = info.w;
         // lane s < 14: the cube of stencil entry s (a cube that was never made has no members, NA:663)
         int cnt = 0, beg = 0;
         if (lane < 14) {
@@ -210,25 +223,32 @@ pair_search_kernel(fr3d_nts_t nts, SearchWs ws, double cutoff, int32_t *__restri
         const int shift = beg - (end - cnt);                // member index = candidate index + shift
 
         for (int m0 = 0; m0 < cnt1; m0 += 32) {
-            // a batch of nt1: lane l loads member m0 + l (n1 = -1: no glycosidic atom, NA:674)
+            // a batch of nt1: lane l loads member m0 + l
             const int mm = min(32, cnt1 - m0);
             __syncwarp();
             if (lane < mm) {
-                const int n1 = ws.members[beg1 + m0 + lane];
-                const int32_t *m1 = nts.meta + (size_t)n1 * FR3D_META_INTS;
-                S.q_n1[lane] = (nts.base_mask[n1] & 1u) ? n1 : -1;
-                S.q_chain[lane] = m1[3]; S.q_index[lane] = m1[4]; S.q_resid[lane] = m1[5]; S.q_alt[lane] = m1[6];
-                S.q_xyz[lane][0] = nts.center[(size_t)n1 * 3 + 0];
-                S.q_xyz[lane][1] = nts.center[(size_t)n1 * 3 + 1];
-                S.q_xyz[lane][2] = nts.center[(size_t)n1 * 3 + 2];
+                const double2 *rec = ws.sorted + (size_t)(beg1 + m0 + lane) * 3;
+                const double2 xy = rec[0], zn = rec[1], kk = rec[2];
+                Q.n1[lane] = __double2hiint(zn.y) ? __double2loint(zn.y) : -1;
+                Q.key[lane] = *reinterpret_cast<const int4 *>(&kk);
+                Q.xy[lane][0] = xy.x;
+                Q.xy[lane][1] = xy.y;
+                Q.z[lane] = zn.x;
             }
-            for (int sb = 0; sb < total; sb += SEARCH_CAP) {
-                const int seg = min(SEARCH_CAP, total - sb);
-                // stage the segment's candidates
-                __syncwarp();
-                for (int t0 = 0; t0 < seg; t0 += 32) {      // warp-uniform trip count: the shuffles need every lane
-                    const int t = t0 + lane;
-                    const int k = sb + t;
+            __syncwarp();
+            // the candidates in groups of SEARCH_GROUP x 32 (a cube's whole stencil fits one group on RNA): ONE atomicAdd per
+            // group - ncu showed the kernel waiting on same-address atomics with one per 32 candidates (45 % of the stall
+            // samples, ~0.5 atomics per clock on one L2 address)
+            for (int sb = 0; sb < total; sb += 32 * SEARCH_GROUP) {
+                unsigned accept[SEARCH_GROUP];              // bit m: nt1 m of the batch pairs with this lane's candidate c
+                int n2[SEARCH_GROUP], st[SEARCH_GROUP];
+                int mine = 0;
+#pragma unroll
+                for (int c = 0; c < SEARCH_GROUP; ++c) {
+                    accept[c] = 0; n2[c] = 0; st[c] = 0;
+                    if (sb + 32 * c >= total) continue;     // warp uniform
+                    const int k = sb + 32 * c + lane;
+                    const bool valid = k < total;
                     // stencil entry of candidate k = number of cubes whose (inclusive, non-decreasing) prefix end is <= k:
                     // a four-step bisection over the values held by lanes 0..12 (lanes 13.. hold the total)
                     int s = 0;
@@ -238,83 +258,67 @@ pair_search_kernel(fr3d_nts_t nts, SearchWs ws, double cutoff, int32_t *__restri
                         if (s + step <= 13 && k >= e) s += step;
                     }
                     const int sh = __shfl_sync(ALL, shift, s);
-                    if (t < seg) {
-                        const int n2 = ws.members[k + sh];
-                        const int32_t *m2 = nts.meta + (size_t)n2 * FR3D_META_INTS;
-                        S.s[t] = (uint8_t)s;
-                        S.n2[t] = n2;
-                        S.chain[t] = m2[3]; S.index[t] = m2[4]; S.resid[t] = m2[5]; S.alt[t] = m2[6];
-                        S.xyz[t][0] = nts.center[(size_t)n2 * 3 + 0];
-                        S.xyz[t][1] = nts.center[(size_t)n2 * 3 + 1];
-                        S.xyz[t][2] = nts.center[(size_t)n2 * 3 + 2];
+                    int4 k2 = make_int4(0, 0, 0, 0);
+                    double x2 = 0.0, y2 = 0.0, z2 = 0.0;
+                    if (valid) {
+                        const double2 *rec = ws.sorted + (size_t)(k + sh) * 3;
+                        const double2 xy = rec[0], zn = rec[1], kk = rec[2];
+                        n2[c] = __double2loint(zn.y);
+                        k2 = *reinterpret_cast<const int4 *>(&kk);
+                        x2 = xy.x; y2 = xy.y; z2 = zn.x;
                     }
-                }
-                __syncwarp();
-                // pass 1: every nt1 of the batch scans the staged candidates; ballots go to shared memory
-                int nkept = 0;
-                for (int m = 0; m < mm; ++m) {
-                    const int n1 = S.q_n1[m];
-                    const int chain1 = S.q_chain[m], index1 = S.q_index[m], resid1 = S.q_resid[m], alt1 = S.q_alt[m];
-                    const double c1x = S.q_xyz[m][0], c1y = S.q_xyz[m][1], c1z = S.q_xyz[m][2];
-#pragma unroll
-                    for (int c = 0; c < SEARCH_CHUNKS; ++c) {
-                        if (c * 32 >= seg) {                 // warp uniform: no candidates in this chunk
-                            if (lane == 0) S.kept[m][c] = 0;
-                            continue;
-                        }
-                        const int t = c * 32 + lane;
-                        bool keep = false;
-                        if (n1 >= 0 && t < seg) {
-                            keep = true;
-                            if (S.s[t] == 0) {              // NA:684-688
-                                const int chain2 = S.chain[t];
-                                if (chain1 > chain2) keep = false;
-                                else if (chain1 == chain2 && index1 > S.index[t]) keep = false;
-                            }
-                            if (keep) {
-                                const double dx = fabs(S.xyz[t][0] - c1x);
-                                const double dy = fabs(S.xyz[t][1] - c1y);
-                                const double dz = fabs(S.xyz[t][2] - c1z);
-                                if (dx > cutoff || dy > cutoff || dz > cutoff) keep = false;         // NA:699-702
-                                else if (resid1 == S.resid[t] && alt1 != S.alt[t]) keep = false;     // NA:706-713
-                                else {
-                                    // d = sqrt(d2) against the cutoff and 2.0 (NA:716-724): decided on d2 unless it is
-                                    // within rounding of a threshold, where the reference's own sqrt decides
-                                    const double d2 = dx * dx + dy * dy + dz * dz, c2 = cutoff * cutoff;
-                                    if (d2 > c2 * (1.0 + 1e-12) || d2 < 4.0 * (1.0 - 1e-12)) keep = false;
-                                    else if (!(d2 < c2 * (1.0 - 1e-12) && d2 > 4.0 * (1.0 + 1e-12))) {
-                                        const double d = sqrt(d2);
-                                        if (d > cutoff || d < 2.0) keep = false;
-                                    }
-                                }
-                            }
-                        }
-                        const unsigned b = __ballot_sync(ALL, keep);
-                        if (lane == 0) S.kept[m][c] = b;
-                        nkept += __popc(b);
+                    st[c] = s;
+                    // The test of one (nt1, candidate): branch-free, decided on the squared distance; a pair whose d2 is
+                    // within rounding of a threshold goes on the `band` mask and is settled below by the reference's own
+                    // sqrt comparison (NA:716-724).  The per-axis screen of NA:699-702 is implied: |dx| > cutoff gives
+                    // d >= |dx| > cutoff (sqrt(x * x) == |x| in IEEE arithmetic), so the distance test rejects the pair too.
+                    unsigned acc = 0, band = 0;
+                    for (int m = 0; m < mm; ++m) {
+                        const int n1 = Q.n1[m];
+                        const int4 k1 = Q.key[m];
+                        const double2 xy1 = *reinterpret_cast<const double2 *>(Q.xy[m]);
+                        const double z1 = Q.z[m];
+                        const double dx = x2 - xy1.x, dy = y2 - xy1.y, dz = z2 - z1;
+                        const double d2 = dx * dx + dy * dy + dz * dz;
+                        const bool order_ok = (s != 0) | (k1.x < k2.x) | ((k1.x == k2.x) & (k1.y <= k2.y));   // NA:684-688
+                        const bool alt_ok = (k1.z != k2.z) | (k1.w == k2.w);                                   // NA:706-713
+                        const bool maybe = valid & (n1 >= 0) & order_ok & alt_ok & (d2 <= c2_hi) & (d2 >= four_lo);
+                        const bool sure = (d2 < c2_lo) & (d2 > four_hi);
+                        acc |= ((maybe & sure) ? 1u : 0u) << m;
+                        band |= ((maybe & !sure) ? 1u : 0u) << m;
                     }
+                    while (band) {                          // rare: within 1e-12 (relative) of 2 A or of the cutoff
+                        const int m = __ffs(band) - 1;
+                        band &= band - 1;
+                        const double dx = x2 - Q.xy[m][0], dy = y2 - Q.xy[m][1], dz = z2 - Q.z[m];
+                        const double d = sqrt(dx * dx + dy * dy + dz * dz);
+                        if (!(d > cutoff || d < 2.0)) acc |= 1u << m;
+                    }
+                    accept[c] = acc;
+                    mine += __popc(acc);
                 }
+                // the pairs are written grouped by nt1 (the screen kernel of K4 reads the nt1 record from global memory: runs
+                // of one nt1 stay in L1 - candidate-major order made that kernel 3 % slower, profiles/ab_search_r2.log)
+                const int nkept = __reduce_add_sync(ALL, mine);
                 if (!nkept) continue;
-                // one append for the whole (batch, segment), then pass 2 writes the pairs grouped by nt1
-                long long basepos = 0;
-                if (lane == 0) basepos = (long long)atomicAdd((unsigned long long *)&counters[0], (unsigned long long)nkept);
-                basepos = __shfl_sync(ALL, basepos, 0);
-                __syncwarp();
+                long long pos = 0;
+                if (lane == 0) pos = (long long)atomicAdd((unsigned long long *)&counters[0], (unsigned long long)nkept);
+                pos = __shfl_sync(ALL, pos, 0);
                 for (int m = 0; m < mm; ++m) {
-                    const int n1 = S.q_n1[m];
+                    const int n1 = Q.n1[m];
 #pragma unroll
-                    for (int c = 0; c < SEARCH_CHUNKS; ++c) {
-                        const unsigned b = S.kept[m][c];
-                        if ((b >> lane) & 1u) {
-                            const int t = c * 32 + lane;
-                            const long long pos = basepos + __popc(b & ((1u << lane) - 1u));
-                            if (pos < pair_cap) {
-                                pair_i[pos] = n1;
-                                pair_j[pos] = S.n2[t];
-                                pair_rank[pos] = first1 * 16 + (int)S.s[t];
+                    for (int c = 0; c < SEARCH_GROUP; ++c) {
+                        if (sb + 32 * c >= total) continue;
+                        const unsigned bm = __ballot_sync(ALL, (accept[c] >> m) & 1u);
+                        if ((bm >> lane) & 1u) {
+                            const long long at = pos + __popc(bm & ((1u << lane) - 1u));
+                            if (at < pair_cap) {
+                                pair_i[at] = n1;
+                                pair_j[at] = n2[c];
+                                pair_rank[at] = first1 * 16 + st[c];
                             }
                         }
-                        basepos += __popc(b);
+                        pos += __popc(bm);
                     }
                 }
             }
