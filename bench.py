@@ -61,8 +61,31 @@ def reference_available():
     return os.path.isdir(os.path.join(REF_DIR, "fr3d", "classifiers"))
 
 
+SINGLE = {"c1": ("C1: S_1GID_full, one structure of 316 nt (the 1GID bases of the reference's Matlab golden file + template "
+                 "backbone)", 1, None, None),
+          "c2": ("C2: S_1S72_like, one structure of 2 844 nt (9 copies of S_1GID_full on a 3 x 3 x 1 lattice, random rotations, "
+                 "sigma 0.10 A, seed 1072; no 1S72.cif exists offline)", 9, (3, 3, 1), 1072),
+          "c3": ("C3: one assembly of 25 280 nt (80 copies of S_1GID_full on a 5 x 4 x 4 lattice, sigma 0.10 A, seed 25000)",
+                 80, (5, 4, 4), 25000)}
+_SINGLE_WORKLOAD = [None]          # set by main(): the CPU arm then times (a sample of) that one structure
+
+
+def single_structure(workload):
+    from fr3d_python_b200 import synthetic
+    base = synthetic.pack_base()
+    name, copies, lattice, seed = SINGLE[workload]
+    if copies == 1:
+        return base
+    return synthetic.make_tiled_structure(base, copies, lattice, seed=seed, pdb=workload.upper())
+
+
 def _spec_of_seed(seed):
     from fr3d_python_b200 import synthetic
+    if _SINGLE_WORKLOAD[0] is not None:
+        # the CPU sample of a single-structure workload: its first 316 nt (one tile copy), whatever the seed
+        spec = synthetic.batch_to_spec(single_structure(_SINGLE_WORKLOAD[0]), 0)
+        spec["nts"] = spec["nts"][:316]
+        return spec
     base = synthetic.pack_base()
     tb = synthetic.make_structure_batch(base, 1, seed0=seed)
     return synthetic.batch_to_spec(tb, 0)
@@ -129,6 +152,9 @@ def run_reference_arm(args):
         return bench_c5.run_reference_arm(args)
     cores = os.cpu_count() or 1
     procs = min(cores, 64)
+    if args.workload in SINGLE:    # one structure = one reference process (annotate_nt_nt_in_structure is serial)
+        _SINGLE_WORKLOAD[0] = args.workload
+        procs = 1
     n_sample = procs               # one structure per worker per step
     ctx = mp.get_context("fork")
     with ctx.Pool(procs) as pool:
@@ -141,6 +167,8 @@ def run_reference_arm(args):
             t_total += dt
     value = pairs_total / t_total
     sample = "%d structures (316 nt each) of the 1000-structure batch per step, one per worker; %s" % (n_sample, cpu_what())
+    if args.workload in SINGLE:
+        sample = "the first 316 nt (one tile copy) of the structure per step, one process; %s" % cpu_what()
     scaling = args.scaling or ("strong" if args.gpus > 1 else "weak")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * t_total / max(args.steps, 1),
@@ -155,6 +183,12 @@ def run_reference_arm(args):
 def workload_config(args, structures, world, scaling=None):
     weak = scaling == "weak" and world > 1
     heavy = getattr(args, "heavy", False)
+    if args.workload in SINGLE:
+        return {"workload": SINGLE[args.workload][0] + ", all nine annotation categories, final rows in the reference's order "
+                            "(device tail included); a step = the whole structure",
+                "structures": 1, "nt_per_structure": {"c1": 316, "c2": 2844, "c3": 25280}[args.workload],
+                "l2_policy": "a 256 MB buffer is written between timed steps (the structure's records fit in L2)",
+                "parallelism": "one structure runs on one GPU (SURVEY \u00a78(e)); N > 1 is not defined for this workload"}
     return {"workload": ("C4 heavy variant: synthetic batch of perturbed S_1S72_like structures (9 tiled 1GID copies, 2 844 nt, "
                          "seed 4000+k, sigma 0.10 A)" if heavy else
                          "C4: synthetic batch of perturbed 1GID-scale structures (316 nt, seed 4000+k, sigma 0.10 A)") +
@@ -252,7 +286,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c4", choices=["c4", "c5"])
+    ap.add_argument("--workload", default="c4", choices=["c4", "c5", "c1", "c2", "c3"],
+                    help="c4 (default, the headline batch), c5 (discrepancy matrix), c1 / c2 / c3: ONE structure of 316 / 2 844 / "
+                         "25 280 nt (BASELINE configs[0..2]; single GPU)")
     ap.add_argument("--scaling", default=None, choices=["strong", "weak"],
                     help="N > 1: strong (default) = ONE batch of --structures sharded over the ranks; weak = own batch per rank")
     ap.add_argument("--structures", type=int, default=1000, help="structures of the batch (per GPU under weak scaling)")
@@ -271,6 +307,13 @@ def main():
         return
     if args.heavy:
         args.no_cpu_baseline = True
+    if args.workload in SINGLE:
+        if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+            if int(os.environ.get("RANK", "0")) == 0:
+                print(json.dumps({"metric": METRIC, "workload": args.workload, "unavailable": "a single structure runs on one GPU"}))
+            return
+        _SINGLE_WORKLOAD[0] = args.workload
+        args.structures, args.chunks, args.cpu_structures = 1, 1, 1
     if args.workload == "c5":
         import bench_c5
         return bench_c5.main(args)
@@ -284,13 +327,15 @@ def main():
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        procs = min(cores, 64)
+        procs = 1 if args.workload in SINGLE else min(cores, 64)
         n_sample = args.cpu_structures or min(2 * procs, 128)
         ctx = mp.get_context("fork")
         with ctx.Pool(procs) as pool:
             pairs, dt = cpu_sample_run(pool, [4000 + k for k in range(n_sample)])
         cpu_baseline = {"value": pairs / dt, "unit": "pairs/s", "cores": procs, "kind": cpu_kind(),
-                        "sample": "first %d structures of the batch (%d candidate pairs), %s, %d-process pool, %.1f s"
+                        "sample": ("the first 316 nt (one tile copy, %d candidate pairs) of the structure, %s, one process, %.1f s"
+                                   % (pairs, cpu_what(), dt)) if args.workload in SINGLE else
+                                  "first %d structures of the batch (%d candidate pairs), %s, %d-process pool, %.1f s"
                                   % (n_sample, pairs, cpu_what(), procs, dt),
                         "structures_per_s": n_sample / dt}
 
@@ -462,7 +507,8 @@ def main():
     results = {}
     if world == 1 or scaling == "strong":
         # ONE batch of S structures; N > 1: sharded by LPT, rows gathered to rank 0
-        full_batch = synthetic.make_structure_batch(base, S, seed0=4000)
+        full_batch = single_structure(args.workload) if args.workload in SINGLE else \
+            synthetic.make_structure_batch(base, S, seed0=4000)
         shared["full_batch"] = full_batch
         parts = parallel.lpt_partition(np.diff(full_batch.struct_off).astype(int).tolist(), world)
         mine = parts[rank]
@@ -487,7 +533,7 @@ def main():
 
     # ---------------- through the public API (rank 0, N = 1): array API and tuples; packing included
     api = None
-    if world == 1 and rank == 0 and not args.heavy:
+    if world == 1 and rank == 0 and not args.heavy and args.workload not in SINGLE:
         batch = shared["full_batch"]
         pinned = pin_batch(torch, batch)
         NA.annotate_batch(batch, CATEGORIES, pinned=pinned, as_arrays=True)

@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("FR3D_B200_LIB") or os.path.join(_HERE, "lib", "libfr3
 CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 
-ABI_VERSION = 5          # FR3D_ABI_VERSION of include/fr3d_b200.h
+ABI_VERSION = 6          # FR3D_ABI_VERSION of include/fr3d_b200.h
 BASE_SLOTS = 16
 BB_SLOTS = 10
 META_INTS = 8
@@ -85,7 +85,7 @@ class SearchQueryStruct(C.Structure):
 
 
 class TailIdentStruct(C.Structure):
-    _fields_ = [("n_struct", C.c_int32), ("n_chains", C.c_int32), ("n_ends", C.c_int32), ("reserved", C.c_int32),
+    _fields_ = [("n_struct", C.c_int32), ("n_chains", C.c_int32), ("n_ends", C.c_int32), ("max_struct_nt", C.c_int32),
                 ("struct_off", C.c_void_p), ("struct_chain_off", C.c_void_p), ("chain_ends_off", C.c_void_p),
                 ("nt_chain", C.c_void_p), ("nt_cov", C.c_void_p)]
 

@@ -151,8 +151,11 @@ static int init_current_device(int device) {
                                   (int)fr3d::l2_smem_bytes<true, fr3d::L2_WARPS_PAIR>()));
     CUDA_TRY(cudaFuncSetAttribute(fr3d::discrepancy_all_vs_all_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)fr3d::disc_smem_bytes(fr3d::DISC_MAXN)));
-    CUDA_TRY(cudaFuncSetAttribute(fr3d::tail_structure_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)fr3d::TAIL_SMEM));
+    CUDA_TRY(cudaFuncSetAttribute(fr3d::tail_structure_kernel<fr3d::TAIL_THREADS, FR3D_TAIL_MINB, false>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fr3d::TAIL_SMEM));
+    CUDA_TRY(cudaFuncSetAttribute(fr3d::tail_structure_kernel<fr3d::TAIL_THREADS_BIG, 1, true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)fr3d::tail_smem_bytes<fr3d::TAIL_THREADS_BIG>()));
     g_dev[device].initialised = true;
     return FR3D_OK;
 }
@@ -441,8 +444,15 @@ int fr3d_annotation_tail(const fr3d_nts_t *nts, const fr3d_tail_ident_t *ident, 
         fr3d::tail_scan_kernel<<<1, 1024, 0, st>>>(ws, S);                        // both return at once unless a structure
         fr3d::tail_scatter_kernel<<<grid, 256, 0, st>>>(hits, hit_cap, counters, index_offset, *ident, ws, tail_counters);
         const int blocks = S < sm_count * 7 ? S : sm_count * 7;
-        fr3d::tail_structure_kernel<<<blocks, fr3d::TAIL_THREADS, fr3d::TAIL_SMEM, st>>>(
-            *nts, *ident, *tables, hits, index_offset, ws, rows, row_cap, row_start, row_count, tail_counters);
+        fr3d::tail_structure_kernel<fr3d::TAIL_THREADS, FR3D_TAIL_MINB, false>
+            <<<blocks, fr3d::TAIL_THREADS, fr3d::TAIL_SMEM, st>>>(*nts, *ident, *tables, hits, index_offset, ws, rows, row_cap,
+                                                                  row_start, row_count, tail_counters);
+        if (ident->max_struct_nt >= fr3d::TAIL_BIG_NT) {                          // the large structures: 1024-thread blocks
+            const int big_blocks = S < sm_count ? S : sm_count;
+            fr3d::tail_structure_kernel<fr3d::TAIL_THREADS_BIG, 1, true>
+                <<<big_blocks, fr3d::TAIL_THREADS_BIG, fr3d::tail_smem_bytes<fr3d::TAIL_THREADS_BIG>(), st>>>(
+                    *nts, *ident, *tables, hits, index_offset, ws, rows, row_cap, row_start, row_count, tail_counters);
+        }
     }
     CUDA_TRY(cudaGetLastError());
     return FR3D_OK;

@@ -31,14 +31,18 @@ namespace fr3d {
 #ifndef FR3D_TAIL_MINB
 #define FR3D_TAIL_MINB 4             // blocks per SM the structure kernel is compiled for (4: 64 registers, no spills)
 #endif
-constexpr int TAIL_THREADS = 256;
-constexpr int TAIL_SORT_CAP = 2048;      // elements sorted in registers (exchange buffer: 16 KB of shared memory)
+constexpr int TAIL_THREADS = 256;        // block size for ordinary structures (four blocks per SM)
+constexpr int TAIL_THREADS_BIG = 1024;   // ... for structures of TAIL_BIG_NT nts and more: one block per SM, four times the lanes
+constexpr int TAIL_BIG_NT = 1024;
+constexpr int TAIL_SORT_CAP = 2048;      // elements sorted in registers by 256 threads (exchange buffer: 16 KB of shared memory)
 constexpr int TAIL_MAX_LABELS = 1024;
 constexpr int TAIL_MAX_NT_BITS = 17;     // structures of up to 131 072 nts
 constexpr int TAIL_INDEX_BITS = 23;
 constexpr uint32_t TAIL_NONE = 0xFFFFFFFFu;
 constexpr int TAIL_F_REMOVED = 1, TAIL_F_NEAR = 2;
-constexpr size_t TAIL_SMEM = (size_t)TAIL_SORT_CAP * sizeof(unsigned long long);
+template <int TT>
+__host__ __device__ constexpr size_t tail_smem_bytes() { return (size_t)8 * TT * sizeof(unsigned long long); }
+constexpr size_t TAIL_SMEM = tail_smem_bytes<TAIL_THREADS>();
 
 struct TailWs {
     int32_t *seg_cnt;             // [S]     hits per structure
@@ -198,6 +202,7 @@ __global__ void tail_scatter_kernel(const fr3d_hit_t *__restrict__ hits, int64_t
 
 // ---- block-wide primitives -----------------------------------------------------------------------------------------
 // exclusive scan of one value per thread; every thread gets the block total too
+template <int TT>
 __device__ __forceinline__ int tail_block_scan(int v, int *s_w, int &total) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int incl = v;
@@ -211,7 +216,7 @@ __device__ __forceinline__ int tail_block_scan(int v, int *s_w, int &total) {
     __syncthreads();
     int before = 0, tot = 0;
 #pragma unroll
-    for (int w = 0; w < TAIL_THREADS / 32; ++w) {
+    for (int w = 0; w < TT / 32; ++w) {
         const int x = s_w[w];
         if (w < warp) before += x;
         tot += x;
@@ -234,9 +239,11 @@ __device__ __forceinline__ void tail_cmpswap(tail_u64 *K, uint32_t *V, int lo, i
 // leave the registers.  Missing elements (i >= n) are +infinity.  (The first version kept (key, value) pairs in shared
 // memory with one comparator per thread and step: ~120 instructions per comparator step and thread, 87 k cycles per
 // 1 k-element sort with seven blocks per SM; registers + shuffles: 47 k; key-only with narrow keys: see profiles/.)
-template <int E, typename K>
+// WHOLE = false: only the last merge (size = P, all ascending): the input is a bitonic sequence / the output of the stride-P/2
+// half cleaner of a larger all-ascending network (see tail_block_sort_keys).
+template <int TT, int E, typename K, bool WHOLE = true>
 __device__ __forceinline__ void tail_sort_keys_regs(K *keys, int n, K *s_buf) {
-    constexpr int P = TAIL_THREADS * E;
+    constexpr int P = TT * E;
     constexpr unsigned ALL = 0xFFFFFFFFu;
     const int tid = threadIdx.x;
     K k[E];
@@ -246,7 +253,7 @@ __device__ __forceinline__ void tail_sort_keys_regs(K *keys, int n, K *s_buf) {
         k[e] = i < n ? keys[i] : (K)~(K)0;
     }
 #pragma unroll
-    for (int size = 2; size <= P; size <<= 1) {
+    for (int size = WHOLE ? 2 : P; size <= P; size <<= 1) {
 #pragma unroll
         for (int j = size >> 1; j >= 1; j >>= 1) {
             if (j >= 32 * E) {
@@ -288,64 +295,171 @@ __device__ __forceinline__ void tail_sort_keys_regs(K *keys, int n, K *s_buf) {
     }
 }
 
-template <typename K>
-__device__ void tail_block_sort_keys(K *keys, int n, void *smem) {
-    __syncthreads();
-    if (n <= 1) return;
-    K *s_buf = reinterpret_cast<K *>(smem);
-    if (n <= TAIL_THREADS) tail_sort_keys_regs<1, K>(keys, n, s_buf);
-    else if (n <= 2 * TAIL_THREADS) tail_sort_keys_regs<2, K>(keys, n, s_buf);
-    else if (n <= 4 * TAIL_THREADS) tail_sort_keys_regs<4, K>(keys, n, s_buf);
-    else if (n <= 8 * TAIL_THREADS) tail_sort_keys_regs<8, K>(keys, n, s_buf);
-    else {                                           // large structures: the all-ascending network over global memory
-        int lp = 1;
-        while ((1 << lp) < n) ++lp;
-        const int half_p = 1 << (lp - 1);
-        for (int lk = 1; lk <= lp; ++lk) {
-            const int kk = 1 << lk, hk = kk >> 1;
-            for (int i = threadIdx.x; i < half_p; i += TAIL_THREADS) {
-                const int blk = i >> (lk - 1), off = i & (hk - 1);
-                const int lo = blk * kk + off, hi = blk * kk + kk - 1 - off;
-                if (hi < n) { const K a = keys[lo], b = keys[hi]; if (a > b) { keys[lo] = b; keys[hi] = a; } }
-            }
-            __syncthreads();
-            for (int lj = lk - 2; lj >= 0; --lj) {
-                const int j = 1 << lj;
-                for (int i = threadIdx.x; i < half_p; i += TAIL_THREADS) {
-                    const int lo = ((i >> lj) << (lj + 1)) + (i & (j - 1)), hi = lo + j;
-                    if (hi < n) { const K a = keys[lo], b = keys[hi]; if (a > b) { keys[lo] = b; keys[hi] = a; } }
-                }
-                __syncthreads();
-            }
-        }
+// Large structures (more keys than the block sorts in its registers): out of line, one copy per key type.
+template <int TT, typename K>
+__device__ __noinline__ void tail_block_sort_keys_large(K *keys, int n, K *s_buf) {
+    // Large structures: the all-ascending bitonic network (every comparator puts the larger key at the higher index, so
+    // the positions >= n behave as +infinity that never moves and n need not be a power of two) - but only the
+    // comparators at distance >= TILE touch global memory one by one; everything below runs tile by tile in the
+    // registers: first each tile is sorted, then after the long-distance steps of every stage each tile is finished
+    // by the register merge.  (All 136 steps of a 64 k sort through global memory: 9.3 ms of the 18.9 ms tail of the
+    // 25 280-nt structure; tiled: see profiles/tail_phases_r2d_*.txt.)
+    constexpr int TILE = 8 * TT, LOG_TILE = TT == 256 ? 11 : 13;
+    static_assert(TILE == (1 << LOG_TILE), "tile size");
+    for (int t0 = 0; t0 < n; t0 += TILE) {
+        tail_sort_keys_regs<TT, 8, K>(keys + t0, min(TILE, n - t0), s_buf);
+        __syncthreads();
     }
-    __syncthreads();
-}
-
-// Ascending sort of n (key, value) pairs by one block, in place in global memory: the fallback for structures whose
-// packed hit key does not fit 64 bits (more than ~100 k nts AND many hits).  A bitonic network in which every comparator
-// puts the larger key at the higher index, so positions >= n behave as +infinity that never moves and their comparators
-// are skipped (n need not be a power of two).
-__device__ void tail_block_sort(tail_u64 *keys, uint32_t *vals, int n) {
-    __syncthreads();
-    if (n <= 1) return;
     int lp = 1;
     while ((1 << lp) < n) ++lp;
     const int half_p = 1 << (lp - 1);
-    for (int lk = 1; lk <= lp; ++lk) {
+    for (int lk = LOG_TILE + 1; lk <= lp; ++lk) {
+        const int kk = 1 << lk, hk = kk >> 1;
+        for (int i = threadIdx.x; i < half_p; i += TT) {      // flip: i <-> mirror inside blocks of kk
+            const int blk = i >> (lk - 1), off = i & (hk - 1);
+            const int lo = blk * kk + off, hi = blk * kk + kk - 1 - off;
+            if (hi < n) { const K a = keys[lo], b = keys[hi]; if (a > b) { keys[lo] = b; keys[hi] = a; } }
+        }
+        __syncthreads();
+        for (int lj = lk - 2; lj >= LOG_TILE; --lj) {                  // half cleaners at distance >= TILE
+            const int j = 1 << lj;
+            for (int i = threadIdx.x; i < half_p; i += TT) {
+                const int lo = ((i >> lj) << (lj + 1)) + (i & (j - 1)), hi = lo + j;
+                if (hi < n) { const K a = keys[lo], b = keys[hi]; if (a > b) { keys[lo] = b; keys[hi] = a; } }
+            }
+            __syncthreads();
+        }
+        for (int t0 = 0; t0 < n; t0 += TILE) {                         // distances TILE / 2 .. 1: in the registers
+            tail_sort_keys_regs<TT, 8, K, false>(keys + t0, min(TILE, n - t0), s_buf);
+            __syncthreads();
+        }
+    }
+}
+
+template <int TT, typename K>
+__device__ __forceinline__ void tail_block_sort_keys_inline(K *keys, int n, void *smem) {
+    __syncthreads();
+    if (n <= 1) return;
+    K *s_buf = reinterpret_cast<K *>(smem);
+    if (n <= TT) tail_sort_keys_regs<TT, 1, K>(keys, n, s_buf);
+    else if (n <= 2 * TT) tail_sort_keys_regs<TT, 2, K>(keys, n, s_buf);
+    else if (n <= 4 * TT) tail_sort_keys_regs<TT, 4, K>(keys, n, s_buf);
+    else if (n <= 8 * TT) tail_sort_keys_regs<TT, 8, K>(keys, n, s_buf);
+    else tail_block_sort_keys_large<TT, K>(keys, n, s_buf);
+    __syncthreads();
+}
+
+template <int TT, typename K>
+__device__ __noinline__ void tail_block_sort_keys_outline(K *keys, int n, void *smem) {
+    tail_block_sort_keys_inline<TT, K>(keys, n, smem);
+}
+
+// 256-thread blocks (the common case, where the time goes): inlined at every call site as before; 1024-thread blocks:
+// one out-of-line copy per key type (the compile time of twenty more unrolled networks is not worth a call's overhead)
+template <int TT, typename K>
+__device__ __forceinline__ void tail_block_sort_keys(K *keys, int n, void *smem) {
+    if (TT == TAIL_THREADS) tail_block_sort_keys_inline<TT, K>(keys, n, smem);
+    else tail_block_sort_keys_outline<TT, K>(keys, n, smem);
+}
+
+// The same network for (key, value) pairs: 4 pairs per thread, tiles of 1024.
+template <int TT, bool WHOLE>
+__device__ __forceinline__ void tail_sort_kv_regs(tail_u64 *keys, uint32_t *vals, int n, tail_u64 *s_k, uint32_t *s_v) {
+    constexpr int E = 4, P = TT * E;
+    constexpr unsigned ALL = 0xFFFFFFFFu;
+    const int tid = threadIdx.x;
+    tail_u64 k[E];
+    uint32_t v[E];
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int i = tid * E + e;
+        k[e] = i < n ? keys[i] : ~0ull;
+        v[e] = i < n ? vals[i] : 0u;
+    }
+#pragma unroll
+    for (int size = WHOLE ? 2 : P; size <= P; size <<= 1) {
+#pragma unroll
+        for (int j = size >> 1; j >= 1; j >>= 1) {
+            if (j >= 32 * E) {
+                __syncthreads();
+#pragma unroll
+                for (int e = 0; e < E; ++e) { s_k[tid * E + e] = k[e]; s_v[tid * E + e] = v[e]; }
+                __syncthreads();
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const int i = tid * E + e;
+                    const tail_u64 pk = s_k[i ^ j];
+                    const uint32_t pv = s_v[i ^ j];
+                    const bool take_min = ((i & j) == 0) == ((i & size) == 0);
+                    if (take_min ? pk < k[e] : pk > k[e]) { k[e] = pk; v[e] = pv; }
+                }
+            } else if (j >= E) {
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const int i = tid * E + e;
+                    const tail_u64 pk = __shfl_xor_sync(ALL, k[e], j / E);
+                    const uint32_t pv = __shfl_xor_sync(ALL, v[e], j / E);
+                    const bool take_min = ((i & j) == 0) == ((i & size) == 0);
+                    if (take_min ? pk < k[e] : pk > k[e]) { k[e] = pk; v[e] = pv; }
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    if ((e & j) == 0) {
+                        const int i = tid * E + e;
+                        const bool asc = (i & size) == 0;
+                        if ((k[e] > k[e | j]) == asc) {
+                            const tail_u64 t = k[e]; k[e] = k[e | j]; k[e | j] = t;
+                            const uint32_t u = v[e]; v[e] = v[e | j]; v[e | j] = u;
+                        }
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        const int i = tid * E + e;
+        if (i < n) { keys[i] = k[e]; vals[i] = v[e]; }
+    }
+}
+
+// Ascending sort of n (key, value) pairs by one block, in place in global memory: for structures whose packed hit key
+// does not fit 64 bits (~25 k nts and more).  The all-ascending network of tail_block_sort_keys with tiles of 1024 pairs
+// (keys are unique, so the result does not depend on the network).
+template <int TT>
+__device__ __noinline__ void tail_block_sort(tail_u64 *keys, uint32_t *vals, int n, void *smem) {
+    __syncthreads();
+    if (n <= 1) return;
+    constexpr int TILE = 4 * TT, LOG_TILE = TT == 256 ? 10 : 12;
+    static_assert(TILE == (1 << LOG_TILE), "tile size");
+    tail_u64 *s_k = reinterpret_cast<tail_u64 *>(smem);
+    uint32_t *s_v = reinterpret_cast<uint32_t *>(s_k + TILE);
+    for (int t0 = 0; t0 < n; t0 += TILE) {
+        tail_sort_kv_regs<TT, true>(keys + t0, vals + t0, min(TILE, n - t0), s_k, s_v);
+        __syncthreads();
+    }
+    int lp = 1;
+    while ((1 << lp) < n) ++lp;
+    const int half_p = 1 << (lp - 1);
+    for (int lk = LOG_TILE + 1; lk <= lp; ++lk) {
         const int k = 1 << lk, hk = k >> 1;
-        for (int i = threadIdx.x; i < half_p; i += TAIL_THREADS) {      // flip: i <-> mirror inside blocks of k
+        for (int i = threadIdx.x; i < half_p; i += TT) {      // flip: i <-> mirror inside blocks of k
             const int blk = i >> (lk - 1), off = i & (hk - 1);
             const int lo = blk * k + off, hi = blk * k + k - 1 - off;
             if (hi < n) tail_cmpswap(keys, vals, lo, hi);
         }
         __syncthreads();
-        for (int lj = lk - 2; lj >= 0; --lj) {
+        for (int lj = lk - 2; lj >= LOG_TILE; --lj) {
             const int j = 1 << lj;
-            for (int i = threadIdx.x; i < half_p; i += TAIL_THREADS) {
+            for (int i = threadIdx.x; i < half_p; i += TT) {
                 const int lo = ((i >> lj) << (lj + 1)) + (i & (j - 1)), hi = lo + j;
                 if (hi < n) tail_cmpswap(keys, vals, lo, hi);
             }
+            __syncthreads();
+        }
+        for (int t0 = 0; t0 < n; t0 += TILE) {
+            tail_sort_kv_regs<TT, false>(keys + t0, vals + t0, min(TILE, n - t0), s_k, s_v);
             __syncthreads();
         }
     }
@@ -367,25 +481,30 @@ __device__ __forceinline__ TailEntrySrc tail_entry_of(const fr3d_hit_t &h, int d
     return e;
 }
 
-// One block per structure (dynamic assignment through tc[1]).
-__global__ void __launch_bounds__(TAIL_THREADS, FR3D_TAIL_MINB)
+// One block per structure (dynamic assignment through tc[1] / tc[3]).  BIG = false: blocks of 256 threads, four per SM, take
+// the structures below TAIL_BIG_NT nts (all of them when the caller does not announce large ones); BIG = true: blocks of
+// 1024 threads, one per SM, take the others - the phases are block-wide networks and scans whose time falls with the lane
+// count, and a large structure has nobody to share the SM with anyway.
+template <int TT, int MINB, bool BIG>
+__global__ void __launch_bounds__(TT, MINB)
 tail_structure_kernel(fr3d_nts_t nts, fr3d_tail_ident_t id, fr3d_tail_tables_t tb, const fr3d_hit_t *__restrict__ hits,
                       int32_t index_offset, TailWs ws, fr3d_row_t *__restrict__ rows, int64_t row_cap,
                       int32_t *__restrict__ row_start, int32_t *__restrict__ row_count, int64_t *tc) {
     extern __shared__ __align__(16) unsigned char tail_smem[];
     __shared__ uint32_t s_lfirst[TAIL_MAX_LABELS];
     __shared__ uint16_t s_lrank[TAIL_MAX_LABELS];
-    __shared__ int s_w[TAIL_THREADS / 32];
+    __shared__ int s_w[TT / 32];
     __shared__ int s_struct, s_nent, s_napp, s_nnest, s_nmulti, s_err;
     __shared__ long long s_base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int T = TAIL_THREADS;
+    constexpr int T = TT;
+    constexpr size_t SMEM_BYTES = tail_smem_bytes<TT>();
     const int n_labels = tb.n_labels;
 
     while (true) {
         __syncthreads();
         if (tid == 0) {
-            s_struct = (int)atomicAdd((tail_u64 *)&tc[1], 1ull);
+            s_struct = (int)atomicAdd((tail_u64 *)&tc[BIG ? 3 : 1], 1ull);
             s_nent = 0; s_napp = 0; s_nnest = 0; s_nmulti = 0; s_err = 0;
         }
         __syncthreads();
@@ -395,6 +514,7 @@ tail_structure_kernel(fr3d_nts_t nts, fr3d_tail_ident_t id, fr3d_tail_tables_t t
         long long phase_t0 = clock64();
 #endif
         const int lo = id.struct_off[s], n = id.struct_off[s + 1] - lo;
+        if (id.max_struct_nt >= TAIL_BIG_NT && (n >= TAIL_BIG_NT) != BIG) continue;      // the other kernel's structure
         const int hb = ws.seg_off[s], H = ws.seg_cur[s];
         const int base = index_offset + lo;                                  // hit.i - base = position in the structure
         if (n > (1 << TAIL_MAX_NT_BITS)) {                                   // flagged by the scatter kernel
@@ -433,7 +553,7 @@ tail_structure_kernel(fr3d_nts_t nts, fr3d_tail_ident_t id, fr3d_tail_tables_t t
         // nested-cWW sort and the final sort) when they fit, else in the global workspace
         const int ends_lo = id.chain_ends_off[c_lo];
         const int ends_len = id.chain_ends_off[c_hi] - ends_lo;
-        const bool ends_shared = ends_len <= (int)(TAIL_SMEM / sizeof(int32_t));
+        const bool ends_shared = ends_len <= (int)(SMEM_BYTES / sizeof(int32_t));
         int32_t *ends_base = ends_shared ? reinterpret_cast<int32_t *>(tail_smem) : ws.ends + ends_lo;
 
         TAIL_PHASE(0);
@@ -454,9 +574,9 @@ tail_structure_kernel(fr3d_nts_t nts, fr3d_tail_ident_t id, fr3d_tail_tables_t t
                                rank = k >> (2 * TAIL_MAX_NT_BITS + 4);
                 hkey[t] = ((((rank << nb | i) << nb | j) << 4 | slot) << hbits) | (tail_u64)t;
             }
-            tail_block_sort_keys<tail_u64>(hkey, H, tail_smem);
+            tail_block_sort_keys<TT, tail_u64>(hkey, H, tail_smem);
         } else {
-            tail_block_sort(hkey, hval, H);
+            tail_block_sort<TT>(hkey, hval, H, tail_smem);
         }
         // hit index of sorted position p
 #define TAIL_HIT_OF(p) (packed ? hval[(int)(hkey[p] & hmask)] : hval[p])
@@ -489,7 +609,7 @@ tail_structure_kernel(fr3d_nts_t nts, fr3d_tail_ident_t id, fr3d_tail_tables_t t
                     }
                 }
                 int total;
-                const int ex = tail_block_scan(cnt_app | (cnt_ent << 16), s_w, total);
+                const int ex = tail_block_scan<TT>(cnt_app | (cnt_ent << 16), s_w, total);
                 if (cnt_app) {
                     const int k = run_app + (ex & 0xFFFF);
                     alab[k] = l0; aa[k] = swap ? b : a; ab[k] = swap ? a : b;
@@ -523,7 +643,7 @@ tail_structure_kernel(fr3d_nts_t nts, fr3d_tail_ident_t id, fr3d_tail_tables_t t
         // ---- unit_id_to_basepairs in iteration order: nts by first appearance, entries by sequence (NA:1001-1013);
         // key = (entry index of the nt's first entry, entry index), sorted without values
         for (int e = tid; e < nent; e += T) ekey[e] = ((tail_u64)first[(int)ekey[e]] << 32) | (tail_u64)(uint32_t)e;
-        tail_block_sort_keys<tail_u64>(ekey, nent, tail_smem);
+        tail_block_sort_keys<TT, tail_u64>(ekey, nent, tail_smem);
         for (int q = tid; q < nent; q += T) {
             const uint32_t ev = ent_hit[(int)(ekey[q] & 0xFFFFFFFFull)];
             eval[q] = ev;
@@ -562,7 +682,7 @@ tail_structure_kernel(fr3d_nts_t nts, fr3d_tail_ident_t id, fr3d_tail_tables_t t
                     }
                 }
                 int total;
-                const int ex = tail_block_scan(flag, s_w, total);
+                const int ex = tail_block_scan<TT>(flag, s_w, total);
                 if (flag) multi[running + ex] = q;
                 running += total;
             }
@@ -650,7 +770,7 @@ tail_structure_kernel(fr3d_nts_t nts, fr3d_tail_ident_t id, fr3d_tail_tables_t t
                     }
                 }
                 int total;
-                const int ex = tail_block_scan(lab >= 0 ? 1 : 0, s_w, total);
+                const int ex = tail_block_scan<TT>(lab >= 0 ? 1 : 0, s_w, total);
                 if (lab >= 0) {
                     const int k = running + ex;
                     alab[k] = lab; aa[k] = u; ab[k] = v;
@@ -682,7 +802,7 @@ tail_structure_kernel(fr3d_nts_t nts, fr3d_tail_ident_t id, fr3d_tail_tables_t t
         }
         __syncthreads();
         const int nnest = s_nnest;
-        tail_block_sort_keys<tail_u64>(nkey, nnest, tail_smem);
+        tail_block_sort_keys<TT, tail_u64>(nkey, nnest, tail_smem);
         for (int c = c_lo; c < c_hi; ++c) {                                  // identity: every index maps to itself
             const int eo = id.chain_ends_off[c] - ends_lo, len = id.chain_ends_off[c + 1] - id.chain_ends_off[c];
             for (int i = tid; i < len; i += T) ends_base[eo + i] = i;
@@ -750,10 +870,10 @@ tail_structure_kernel(fr3d_nts_t nts, fr3d_tail_ident_t id, fr3d_tail_tables_t t
         uint32_t *akey32 = reinterpret_cast<uint32_t *>(akey);
         if (keys32) {
             for (int k = tid; k < napp; k += T) akey32[k] = ((uint32_t)s_lrank[alab[k]] << 22) | (uint32_t)k;
-            tail_block_sort_keys<uint32_t>(akey32, napp, tail_smem);
+            tail_block_sort_keys<TT, uint32_t>(akey32, napp, tail_smem);
         } else {
             for (int k = tid; k < napp; k += T) akey[k] = ((tail_u64)s_lrank[alab[k]] << 32) | (tail_u64)(uint32_t)k;
-            tail_block_sort_keys<tail_u64>(akey, napp, tail_smem);
+            tail_block_sort_keys<TT, tail_u64>(akey, napp, tail_smem);
         }
 #define TAIL_ROW_OF(r) (keys32 ? (int)(akey32[r] & ((1u << 22) - 1u)) : (int)(akey[r] & 0xFFFFFFFFull))
 
@@ -769,7 +889,7 @@ tail_structure_kernel(fr3d_nts_t nts, fr3d_tail_ident_t id, fr3d_tail_tables_t t
         {       // files usually list the nts of a chain in sequence order: then the keys are sorted already
             int unsorted = 0;
             for (int u = tid; u + 1 < n; u += T) unsorted |= ckey[u] > ckey[u + 1];
-            if (__syncthreads_or(unsorted)) tail_block_sort_keys<tail_u64>(ckey, n, tail_smem);
+            if (__syncthreads_or(unsorted)) tail_block_sort_keys<TT, tail_u64>(ckey, n, tail_smem);
         }
 #define TAIL_COV_NT(r) ((int)(ckey[r] & ((1ull << TAIL_MAX_NT_BITS) - 1ull)))
         for (int r = tid; r < n; r += T) {                   // rows of sorted position r = members of the next key
@@ -789,7 +909,7 @@ tail_structure_kernel(fr3d_nts_t nts, fr3d_tail_ident_t id, fr3d_tail_tables_t t
         }
         TAIL_PHASE(9);
         int total_rows;
-        tail_block_scan(my_rows, s_w, total_rows);
+        tail_block_scan<TT>(my_rows, s_w, total_rows);
         __syncthreads();
         if (tid == 0) {
             if (s_err) { atomicOr((tail_u64 *)&tc[2], 2ull); total_rows = 0; }
@@ -809,7 +929,7 @@ tail_structure_kernel(fr3d_nts_t nts, fr3d_tail_ident_t id, fr3d_tail_tables_t t
             int k = 0, lab = 0, cnt = 0;
             if (r < napp) { k = TAIL_ROW_OF(r); lab = alab[k]; cnt = 1 + (int)(tb.labels[lab].flags & 1u); }
             int total;
-            const int ex = tail_block_scan(cnt, s_w, total);
+            const int ex = tail_block_scan<TT>(cnt, s_w, total);
             if (r < napp) {
                 fr3d_row_t row;
                 row.label = lab; row.nt1 = aa[k] + base; row.nt2 = ab[k] + base; row.crossing = across[k];
@@ -825,7 +945,7 @@ tail_structure_kernel(fr3d_nts_t nts, fr3d_tail_ident_t id, fr3d_tail_tables_t t
             const int r = r0 + tid;
             const int cnt = r < n ? gcount[r] : 0;
             int total;
-            const int ex = tail_block_scan(cnt, s_w, total);
+            const int ex = tail_block_scan<TT>(cnt, s_w, total);
             if (cnt) {
                 const int u1 = TAIL_COV_NT(r), e = gstart[r];
                 const int i1 = meta[(size_t)u1 * FR3D_META_INTS + 4];

@@ -399,6 +399,7 @@ class DeviceIdent(object):
         arrays = ident.chunk(s0, s1)
         self.n_struct, self.n_chains, self.n_ends = s1 - s0, arrays[5], arrays[6]
         self.host = arrays[:5]
+        self.max_struct_nt = int(np.diff(arrays[0]).max()) if s1 > s0 else 0     # large structures get their own tail kernel
         offs, total = [], 0
         for a in self.host:
             offs.append(total)
@@ -419,8 +420,8 @@ class DeviceIdent(object):
         self.dev_blob = dev_blob
         base = dev_blob.data_ptr()
         o = self.offs
-        self.struct = _lib.TailIdentStruct(n_struct=self.n_struct, n_chains=self.n_chains, n_ends=self.n_ends, reserved=0,
-                                           struct_off=base + o[0], struct_chain_off=base + o[1],
+        self.struct = _lib.TailIdentStruct(n_struct=self.n_struct, n_chains=self.n_chains, n_ends=self.n_ends,
+                                           max_struct_nt=self.max_struct_nt, struct_off=base + o[0], struct_chain_off=base + o[1],
                                            chain_ends_off=base + o[2], nt_chain=base + o[3], nt_cov=base + o[4])
 
 

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define FR3D_ABI_VERSION 5
+#define FR3D_ABI_VERSION 6
 
 #define FR3D_OK 0
 #define FR3D_E_CUDA (-1)      /* a CUDA runtime call failed; see fr3d_last_error */
@@ -248,7 +248,8 @@ typedef struct {
     int32_t n_struct;
     int32_t n_chains;
     int32_t n_ends;                  /* chain_ends_off[n_chains], known to the host (sizes the workspace) */
-    int32_t reserved;
+    int32_t max_struct_nt;           /* nts of the largest structure, known to the host; 0 = not announced.  From 1 024 nts the
+                                        tail launches a second kernel with 1 024-thread blocks for the large structures */
     const int32_t *struct_off;       /* [n_struct + 1] first nt of each structure */
     const int32_t *struct_chain_off; /* [n_struct + 1] first chain-table entry of each structure */
     const int32_t *chain_ends_off;   /* [n_chains + 1] offset of the chain's nested-cWW endpoint array in the workspace;
@@ -259,7 +260,7 @@ typedef struct {
 } fr3d_tail_ident_t;
 
 /* tail_counters (device int64[32]; [4..31] are written by profiling builds only): [0] total rows (may exceed row_cap: compare after the sync and re-run),
- * [1] scratch, [2] != 0: a structure outside the supported ranges (more than 131 072 nts, an index outside
+ * [1], [3] scratch, [2] != 0: a structure outside the supported ranges (more than 131 072 nts, an index outside
  * [0, 2^23), more than 65 536 chains or a label without the table entry it needs: FR3D_E_RANGE), [3] scratch.
  * n_hits is read from counters[1] on the device (clamped to hit_cap).  row_start / row_count [n_struct]: the rows of
  * structure s are rows[row_start[s] .. + row_count[s]) (the structures' blocks sit in no particular order). */

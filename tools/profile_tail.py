@@ -1,5 +1,5 @@
 """Per-phase cycle counts of tail_structure_kernel (needs a library built with -DFR3D_TAIL_PROFILE:
-   FR3D_B200_LIB=/path/to/profile.so python tools/profile_tail.py [structures])."""
+   FR3D_B200_LIB=/path/to/profile.so python tools/profile_tail.py [structures [c2|c3]])."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -9,7 +9,12 @@ from fr3d_python_b200 import synthetic, tail as tailmod
 from fr3d_python_b200.classifiers import NA_pairwise_interactions as NA
 from fr3d_python_b200.engine import Engine, DeviceBatch, DeviceIdent, pin_batch
 S = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
-batch = synthetic.make_structure_batch(synthetic.pack_base(), S, seed0=4000)
+if len(sys.argv) > 2:       # one tiled structure instead of the batch: c2 (2 844 nt) or c3 (25 280 nt)
+    copies, lattice, seed = {"c2": (9, (3, 3, 1), 1072), "c3": (80, (5, 4, 4), 25000)}[sys.argv[2]]
+    batch = synthetic.make_tiled_structure(synthetic.pack_base(), copies, lattice, seed=seed, pdb=sys.argv[2].upper())
+    S = 1
+else:
+    batch = synthetic.make_structure_batch(synthetic.pack_base(), S, seed0=4000)
 eng = Engine.get()
 bt, atoms, labels = NA._tables(NA._default_focused(ALL9['basepair']), NA.load_ideal_basepair_hydrogen_bonds())
 mask = NA.category_mask(ALL9)
