@@ -385,6 +385,9 @@ TailCarve carve_tail(void *workspace, int64_t hit_cap, int32_t n_nt, int32_t n_s
     w.seg_off = reinterpret_cast<int32_t *>(take(4 * (S + 1)));
     w.seg_cur = reinterpret_cast<int32_t *>(take(4 * S));
     w.nt_struct = reinterpret_cast<int32_t *>(take(4 * n));
+    w.tmpk = reinterpret_cast<unsigned long long *>(take(16 * H));
+    w.tmpv = reinterpret_cast<uint32_t *>(take(8 * H));
+    w.tmpc = reinterpret_cast<unsigned long long *>(take(8 * n));
     w.overflow = reinterpret_cast<int32_t *>(take(4));
     w.hkey = reinterpret_cast<unsigned long long *>(take(8 * H));
     w.hval = reinterpret_cast<uint32_t *>(take(4 * H));

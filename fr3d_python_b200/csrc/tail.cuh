@@ -20,8 +20,9 @@
 //   rank the labels by first appearance, sort the rows by (label rank, sequence), expand the reversed duplicates
 //   covalent links: sort the nts by (model symmetry chain, index), link successive keys
 // and writes the final rows (label id, nt1, nt2, crossing) in the reference's append order.
-// Sorting is a bitonic network in shared memory (<= TAIL_SORT_CAP elements) or in the global workspace (large
-// structures); all keys are unique, so the result is deterministic.
+// Sorting: a bitonic network with the keys in registers (<= TAIL_SORT_CAP keys, 256-thread blocks) or a block-wide LSD radix
+// sort (everything larger, and the 1024-thread blocks of the large structures); all keys are unique, so the result is
+// deterministic.
 #pragma once
 
 #include "tables.cuh"
@@ -49,6 +50,9 @@ struct TailWs {
     int32_t *seg_off;             // [S + 1]
     int32_t *seg_cur;             // [S]     = the structure's hit count after tail_bin_kernel
     int32_t *nt_struct;           // [n]     structure of every nt
+    unsigned long long *tmpk;     // [2H]    radix sort: the other buffer of the ping-pong (keys)
+    uint32_t *tmpv;               // [2H]    ... (values)
+    unsigned long long *tmpc;     // [n]     ... for the covalent keys (one per nt)
     int32_t *overflow;            // [1]     a structure's hits did not fit its share: exact scan + scatter take over
     unsigned long long *hkey;     // [H]     hits of a structure: sort key; later the nested-cWW candidates
     uint32_t *hval;               // [H]     hit index
@@ -225,23 +229,13 @@ __device__ __forceinline__ int tail_block_scan(int v, int *s_w, int &total) {
     return before + incl - v;
 }
 
-__device__ __forceinline__ void tail_cmpswap(tail_u64 *K, uint32_t *V, int lo, int hi) {
-    const tail_u64 a = K[lo], b = K[hi];
-    if (a > b) {
-        K[lo] = b; K[hi] = a;
-        const uint32_t x = V[lo]; V[lo] = V[hi]; V[hi] = x;
-    }
-}
-
 // Bitonic sort of up to 256 * E keys held in registers, E per thread, element i = tid * E + e; the payload rides in the
 // low bits of the key (32- or 64-bit keys).  Compare distance j < E: inside the thread; E <= j < 32 E: with a lane of
 // the own warp (shuffles); larger: through shared memory.  All loops have compile-time bounds, so the E elements never
 // leave the registers.  Missing elements (i >= n) are +infinity.  (The first version kept (key, value) pairs in shared
 // memory with one comparator per thread and step: ~120 instructions per comparator step and thread, 87 k cycles per
 // 1 k-element sort with seven blocks per SM; registers + shuffles: 47 k; key-only with narrow keys: see profiles/.)
-// WHOLE = false: only the last merge (size = P, all ascending): the input is a bitonic sequence / the output of the stride-P/2
-// half cleaner of a larger all-ascending network (see tail_block_sort_keys).
-template <int TT, int E, typename K, bool WHOLE = true>
+template <int TT, int E, typename K>
 __device__ __forceinline__ void tail_sort_keys_regs(K *keys, int n, K *s_buf) {
     constexpr int P = TT * E;
     constexpr unsigned ALL = 0xFFFFFFFFu;
@@ -253,7 +247,7 @@ __device__ __forceinline__ void tail_sort_keys_regs(K *keys, int n, K *s_buf) {
         k[e] = i < n ? keys[i] : (K)~(K)0;
     }
 #pragma unroll
-    for (int size = WHOLE ? 2 : P; size <= P; size <<= 1) {
+    for (int size = 2; size <= P; size <<= 1) {
 #pragma unroll
         for (int j = size >> 1; j >= 1; j >>= 1) {
             if (j >= 32 * E) {
@@ -295,175 +289,121 @@ __device__ __forceinline__ void tail_sort_keys_regs(K *keys, int n, K *s_buf) {
     }
 }
 
-// Large structures (more keys than the block sorts in its registers): out of line, one copy per key type.
-template <int TT, typename K>
-__device__ __noinline__ void tail_block_sort_keys_large(K *keys, int n, K *s_buf) {
-    // Large structures: the all-ascending bitonic network (every comparator puts the larger key at the higher index, so
-    // the positions >= n behave as +infinity that never moves and n need not be a power of two) - but only the
-    // comparators at distance >= TILE touch global memory one by one; everything below runs tile by tile in the
-    // registers: first each tile is sorted, then after the long-distance steps of every stage each tile is finished
-    // by the register merge.  (All 136 steps of a 64 k sort through global memory: 9.3 ms of the 18.9 ms tail of the
-    // 25 280-nt structure; tiled: see profiles/tail_phases_r2d_*.txt.)
-    constexpr int TILE = 8 * TT, LOG_TILE = TT == 256 ? 11 : 13;
-    static_assert(TILE == (1 << LOG_TILE), "tile size");
-    for (int t0 = 0; t0 < n; t0 += TILE) {
-        tail_sort_keys_regs<TT, 8, K>(keys + t0, min(TILE, n - t0), s_buf);
-        __syncthreads();
-    }
-    int lp = 1;
-    while ((1 << lp) < n) ++lp;
-    const int half_p = 1 << (lp - 1);
-    for (int lk = LOG_TILE + 1; lk <= lp; ++lk) {
-        const int kk = 1 << lk, hk = kk >> 1;
-        for (int i = threadIdx.x; i < half_p; i += TT) {      // flip: i <-> mirror inside blocks of kk
-            const int blk = i >> (lk - 1), off = i & (hk - 1);
-            const int lo = blk * kk + off, hi = blk * kk + kk - 1 - off;
-            if (hi < n) { const K a = keys[lo], b = keys[hi]; if (a > b) { keys[lo] = b; keys[hi] = a; } }
-        }
-        __syncthreads();
-        for (int lj = lk - 2; lj >= LOG_TILE; --lj) {                  // half cleaners at distance >= TILE
-            const int j = 1 << lj;
-            for (int i = threadIdx.x; i < half_p; i += TT) {
-                const int lo = ((i >> lj) << (lj + 1)) + (i & (j - 1)), hi = lo + j;
-                if (hi < n) { const K a = keys[lo], b = keys[hi]; if (a > b) { keys[lo] = b; keys[hi] = a; } }
-            }
-            __syncthreads();
-        }
-        for (int t0 = 0; t0 < n; t0 += TILE) {                         // distances TILE / 2 .. 1: in the registers
-            tail_sort_keys_regs<TT, 8, K, false>(keys + t0, min(TILE, n - t0), s_buf);
-            __syncthreads();
-        }
-    }
-}
-
-template <int TT, typename K>
-__device__ __forceinline__ void tail_block_sort_keys_inline(K *keys, int n, void *smem) {
-    __syncthreads();
-    if (n <= 1) return;
-    K *s_buf = reinterpret_cast<K *>(smem);
-    if (n <= TT) tail_sort_keys_regs<TT, 1, K>(keys, n, s_buf);
-    else if (n <= 2 * TT) tail_sort_keys_regs<TT, 2, K>(keys, n, s_buf);
-    else if (n <= 4 * TT) tail_sort_keys_regs<TT, 4, K>(keys, n, s_buf);
-    else if (n <= 8 * TT) tail_sort_keys_regs<TT, 8, K>(keys, n, s_buf);
-    else tail_block_sort_keys_large<TT, K>(keys, n, s_buf);
-    __syncthreads();
-}
-
-template <int TT, typename K>
-__device__ __noinline__ void tail_block_sort_keys_outline(K *keys, int n, void *smem) {
-    tail_block_sort_keys_inline<TT, K>(keys, n, smem);
-}
-
-// 256-thread blocks (the common case, where the time goes): inlined at every call site as before; 1024-thread blocks:
-// one out-of-line copy per key type (the compile time of twenty more unrolled networks is not worth a call's overhead)
-template <int TT, typename K>
-__device__ __forceinline__ void tail_block_sort_keys(K *keys, int n, void *smem) {
-    if (TT == TAIL_THREADS) tail_block_sort_keys_inline<TT, K>(keys, n, smem);
-    else tail_block_sort_keys_outline<TT, K>(keys, n, smem);
-}
-
-// The same network for (key, value) pairs: 4 pairs per thread, tiles of 1024.
-template <int TT, bool WHOLE>
-__device__ __forceinline__ void tail_sort_kv_regs(tail_u64 *keys, uint32_t *vals, int n, tail_u64 *s_k, uint32_t *s_v) {
-    constexpr int E = 4, P = TT * E;
+// ---- block-wide LSD radix sort (8-bit digits, stable) ------------------------------------------------------------------
+// The sorts of the tail have short keys (22 to ~57 significant bits: label rank | sequence, rank | nt1 | nt2 | slot | position
+// ...), so three to eight counting passes beat the O(n log^2 n) comparator network even at n ~ 800, and by an order of
+// magnitude for the large structures.  Stability comes from giving every WARP a contiguous segment of the input: per-warp
+// digit counts (s_hist[warp][digit], no atomics: a warp's leaders of distinct digits write distinct words), one exclusive
+// scan in (digit, warp) order, then each warp scatters its segment in order, 32 keys at a time, the lanes of equal digit
+// ranked by __match_any_sync.  Keys ping-pong between `keys` and `tmp` in global memory (L2-resident); the number of passes
+// comes from the OR of all keys.  s_hist: (TT / 32) * 256 ints of the dynamic shared memory (8 KB / 32 KB).
+template <int TT, typename K, bool KV>
+__device__ __noinline__ void tail_radix_sort(K *keys, uint32_t *vals, K *tmpk, uint32_t *tmpv, int n, void *smem,
+                                             int skip_low = 0) {      // skip_low: payload bits that need no ordering
     constexpr unsigned ALL = 0xFFFFFFFFu;
-    const int tid = threadIdx.x;
-    tail_u64 k[E];
-    uint32_t v[E];
-#pragma unroll
-    for (int e = 0; e < E; ++e) {
-        const int i = tid * E + e;
-        k[e] = i < n ? keys[i] : ~0ull;
-        v[e] = i < n ? vals[i] : 0u;
-    }
-#pragma unroll
-    for (int size = WHOLE ? 2 : P; size <= P; size <<= 1) {
-#pragma unroll
-        for (int j = size >> 1; j >= 1; j >>= 1) {
-            if (j >= 32 * E) {
-                __syncthreads();
-#pragma unroll
-                for (int e = 0; e < E; ++e) { s_k[tid * E + e] = k[e]; s_v[tid * E + e] = v[e]; }
-                __syncthreads();
-#pragma unroll
-                for (int e = 0; e < E; ++e) {
-                    const int i = tid * E + e;
-                    const tail_u64 pk = s_k[i ^ j];
-                    const uint32_t pv = s_v[i ^ j];
-                    const bool take_min = ((i & j) == 0) == ((i & size) == 0);
-                    if (take_min ? pk < k[e] : pk > k[e]) { k[e] = pk; v[e] = pv; }
-                }
-            } else if (j >= E) {
-#pragma unroll
-                for (int e = 0; e < E; ++e) {
-                    const int i = tid * E + e;
-                    const tail_u64 pk = __shfl_xor_sync(ALL, k[e], j / E);
-                    const uint32_t pv = __shfl_xor_sync(ALL, v[e], j / E);
-                    const bool take_min = ((i & j) == 0) == ((i & size) == 0);
-                    if (take_min ? pk < k[e] : pk > k[e]) { k[e] = pk; v[e] = pv; }
-                }
-            } else {
-#pragma unroll
-                for (int e = 0; e < E; ++e) {
-                    if ((e & j) == 0) {
-                        const int i = tid * E + e;
-                        const bool asc = (i & size) == 0;
-                        if ((k[e] > k[e | j]) == asc) {
-                            const tail_u64 t = k[e]; k[e] = k[e | j]; k[e | j] = t;
-                            const uint32_t u = v[e]; v[e] = v[e | j]; v[e | j] = u;
-                        }
-                    }
-                }
-            }
-        }
-    }
-#pragma unroll
-    for (int e = 0; e < E; ++e) {
-        const int i = tid * E + e;
-        if (i < n) { keys[i] = k[e]; vals[i] = v[e]; }
-    }
-}
-
-// Ascending sort of n (key, value) pairs by one block, in place in global memory: for structures whose packed hit key
-// does not fit 64 bits (~25 k nts and more).  The all-ascending network of tail_block_sort_keys with tiles of 1024 pairs
-// (keys are unique, so the result does not depend on the network).
-template <int TT>
-__device__ __noinline__ void tail_block_sort(tail_u64 *keys, uint32_t *vals, int n, void *smem) {
+    constexpr int W = TT / 32;
+    __shared__ unsigned s_or[2];
+    __shared__ int s_scan[W];
+    int *s_hist = reinterpret_cast<int *>(smem);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     __syncthreads();
     if (n <= 1) return;
-    constexpr int TILE = 4 * TT, LOG_TILE = TT == 256 ? 10 : 12;
-    static_assert(TILE == (1 << LOG_TILE), "tile size");
-    tail_u64 *s_k = reinterpret_cast<tail_u64 *>(smem);
-    uint32_t *s_v = reinterpret_cast<uint32_t *>(s_k + TILE);
-    for (int t0 = 0; t0 < n; t0 += TILE) {
-        tail_sort_kv_regs<TT, true>(keys + t0, vals + t0, min(TILE, n - t0), s_k, s_v);
-        __syncthreads();
-    }
-    int lp = 1;
-    while ((1 << lp) < n) ++lp;
-    const int half_p = 1 << (lp - 1);
-    for (int lk = LOG_TILE + 1; lk <= lp; ++lk) {
-        const int k = 1 << lk, hk = k >> 1;
-        for (int i = threadIdx.x; i < half_p; i += TT) {      // flip: i <-> mirror inside blocks of k
-            const int blk = i >> (lk - 1), off = i & (hk - 1);
-            const int lo = blk * k + off, hi = blk * k + k - 1 - off;
-            if (hi < n) tail_cmpswap(keys, vals, lo, hi);
-        }
-        __syncthreads();
-        for (int lj = lk - 2; lj >= LOG_TILE; --lj) {
-            const int j = 1 << lj;
-            for (int i = threadIdx.x; i < half_p; i += TT) {
-                const int lo = ((i >> lj) << (lj + 1)) + (i & (j - 1)), hi = lo + j;
-                if (hi < n) tail_cmpswap(keys, vals, lo, hi);
-            }
-            __syncthreads();
-        }
-        for (int t0 = 0; t0 < n; t0 += TILE) {
-            tail_sort_kv_regs<TT, false>(keys + t0, vals + t0, min(TILE, n - t0), s_k, s_v);
-            __syncthreads();
-        }
+    if (tid < 2) s_or[tid] = 0;
+    __syncthreads();
+    {
+        unsigned lo = 0, hi = 0;
+        for (int i = tid; i < n; i += TT) { const unsigned long long k = (unsigned long long)keys[i]; lo |= (unsigned)k; hi |= (unsigned)(k >> 32); }
+        lo = __reduce_or_sync(ALL, lo); hi = __reduce_or_sync(ALL, hi);
+        if (lane == 0) { if (lo) atomicOr(&s_or[0], lo); if (hi) atomicOr(&s_or[1], hi); }
     }
     __syncthreads();
+    const int bits = s_or[1] ? 64 - __clz(s_or[1]) : (s_or[0] ? 32 - __clz(s_or[0]) : 0);
+    const int passes = bits > skip_low ? (bits - skip_low + 7) >> 3 : 0;
+    const int seg = (n + W - 1) / W;                       // warp w owns [w * seg, (w + 1) * seg)
+    const int w_lo = warp * seg, w_hi = min(n, w_lo + seg);
+    K *src = keys, *dst = tmpk;
+    uint32_t *vsrc = vals, *vdst = tmpv;
+    for (int pass = 0; pass < passes; ++pass) {
+        const int shift = skip_low + pass * 8;
+        for (int e = tid; e < W * 256; e += TT) s_hist[e] = 0;
+        __syncthreads();
+        // (the key of the next step is loaded one step ahead: the steps of a warp are serial, the loads need not be)
+        K knext = w_lo + lane < w_hi ? src[w_lo + lane] : (K)0;
+        for (int i0 = w_lo; i0 < w_hi; i0 += 32) {
+            const int i = i0 + lane;
+            const K k = knext;
+            if (i + 32 < w_hi) knext = src[i + 32];
+            const int d = i < w_hi ? (int)((k >> shift) & 255) : -1 - lane;
+            const unsigned peers = __match_any_sync(ALL, d);
+            if (d >= 0 && lane == __ffs(peers) - 1) s_hist[warp * 256 + d] += __popc(peers);
+            __syncwarp();
+        }
+        __syncthreads();
+        // exclusive scan in (digit, warp) order: entry e = digit * W + warp; thread t owns the 8 entries 8t .. 8t + 7
+        int run[8], tot = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int e = tid * 8 + q;
+            run[q] = tot;
+            tot += s_hist[(e % W) * 256 + e / W];
+        }
+        int block_total;
+        const int before = tail_block_scan<TT>(tot, s_scan, block_total);
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int e = tid * 8 + q;
+            s_hist[(e % W) * 256 + e / W] = before + run[q];
+        }
+        __syncthreads();
+        knext = w_lo + lane < w_hi ? src[w_lo + lane] : (K)0;
+        uint32_t vnext = 0;
+        if (KV && w_lo + lane < w_hi) vnext = vsrc[w_lo + lane];
+        for (int i0 = w_lo; i0 < w_hi; i0 += 32) {
+            const int i = i0 + lane;
+            const bool live = i < w_hi;
+            const K k = knext;
+            const uint32_t v = vnext;
+            if (i + 32 < w_hi) { knext = src[i + 32]; if (KV) vnext = vsrc[i + 32]; }
+            const int d = live ? (int)((k >> shift) & 255) : -1 - lane;
+            const unsigned peers = __match_any_sync(ALL, d);
+            if (live) {
+                const int at = s_hist[warp * 256 + d] + __popc(peers & ((1u << lane) - 1u));
+                dst[at] = k;
+                if (KV) vdst[at] = v;
+            }
+            __syncwarp();
+            if (live && lane == __ffs(peers) - 1) s_hist[warp * 256 + d] += __popc(peers);
+            __syncwarp();
+        }
+        __syncthreads();
+        { K *t = src; src = dst; dst = t; }
+        { uint32_t *t = vsrc; vsrc = vdst; vdst = t; }
+    }
+    if (src != keys) {
+        for (int i = tid; i < n; i += TT) { keys[i] = src[i]; if (KV) vals[i] = vsrc[i]; }
+    }
+    __syncthreads();
+}
+
+// Up to 2 048 keys in a 256-thread block: the register network (no memory traffic at all; the radix sort's passes cost
+// more there: sort hits 43 k -> 58 k cycles per 316-nt structure, profiles/tail_phases_r2e_c4_radix_everywhere.txt).
+// Everything larger, and everything in the 1 024-thread blocks of the large structures: the radix sort (C3: 64 k hits in
+// 0.3 M cycles instead of 17.7 M through the global-memory network, 3.4 M with register tiles).
+template <int TT, typename K>
+__device__ __forceinline__ void tail_block_sort_keys(K *keys, int n, void *smem, void *tmp, int skip_low = 0) {
+    if (TT == TAIL_THREADS && n <= 8 * TT) {
+        __syncthreads();
+        if (n <= 1) return;
+        K *s_buf = reinterpret_cast<K *>(smem);
+        if (n <= TT) tail_sort_keys_regs<TT, 1, K>(keys, n, s_buf);
+        else if (n <= 2 * TT) tail_sort_keys_regs<TT, 2, K>(keys, n, s_buf);
+        else if (n <= 4 * TT) tail_sort_keys_regs<TT, 4, K>(keys, n, s_buf);
+        else tail_sort_keys_regs<TT, 8, K>(keys, n, s_buf);
+        __syncthreads();
+    } else {
+        tail_radix_sort<TT, K, false>(keys, nullptr, reinterpret_cast<K *>(tmp), nullptr, n, smem, skip_low);
+    }
 }
 
 struct TailEntrySrc {      // what one basepair hit says about the entry recorded for u1 (d = 0) or u2 (d = 1)
@@ -574,9 +514,9 @@ tail_structure_kernel(fr3d_nts_t nts, fr3d_tail_ident_t id, fr3d_tail_tables_t t
                                rank = k >> (2 * TAIL_MAX_NT_BITS + 4);
                 hkey[t] = ((((rank << nb | i) << nb | j) << 4 | slot) << hbits) | (tail_u64)t;
             }
-            tail_block_sort_keys<TT, tail_u64>(hkey, H, tail_smem);
+            tail_block_sort_keys<TT, tail_u64>(hkey, H, tail_smem, ws.tmpk + eb, hbits);      // (the position is payload)
         } else {
-            tail_block_sort<TT>(hkey, hval, H, tail_smem);
+            tail_radix_sort<TT, tail_u64, true>(hkey, hval, ws.tmpk + eb, ws.tmpv + eb, H, tail_smem);
         }
         // hit index of sorted position p
 #define TAIL_HIT_OF(p) (packed ? hval[(int)(hkey[p] & hmask)] : hval[p])
@@ -643,7 +583,7 @@ tail_structure_kernel(fr3d_nts_t nts, fr3d_tail_ident_t id, fr3d_tail_tables_t t
         // ---- unit_id_to_basepairs in iteration order: nts by first appearance, entries by sequence (NA:1001-1013);
         // key = (entry index of the nt's first entry, entry index), sorted without values
         for (int e = tid; e < nent; e += T) ekey[e] = ((tail_u64)first[(int)ekey[e]] << 32) | (tail_u64)(uint32_t)e;
-        tail_block_sort_keys<TT, tail_u64>(ekey, nent, tail_smem);
+        tail_block_sort_keys<TT, tail_u64>(ekey, nent, tail_smem, ws.tmpk + eb);
         for (int q = tid; q < nent; q += T) {
             const uint32_t ev = ent_hit[(int)(ekey[q] & 0xFFFFFFFFull)];
             eval[q] = ev;
@@ -802,7 +742,7 @@ tail_structure_kernel(fr3d_nts_t nts, fr3d_tail_ident_t id, fr3d_tail_tables_t t
         }
         __syncthreads();
         const int nnest = s_nnest;
-        tail_block_sort_keys<TT, tail_u64>(nkey, nnest, tail_smem);
+        tail_block_sort_keys<TT, tail_u64>(nkey, nnest, tail_smem, ws.tmpk + eb);
         for (int c = c_lo; c < c_hi; ++c) {                                  // identity: every index maps to itself
             const int eo = id.chain_ends_off[c] - ends_lo, len = id.chain_ends_off[c + 1] - id.chain_ends_off[c];
             for (int i = tid; i < len; i += T) ends_base[eo + i] = i;
@@ -870,10 +810,10 @@ tail_structure_kernel(fr3d_nts_t nts, fr3d_tail_ident_t id, fr3d_tail_tables_t t
         uint32_t *akey32 = reinterpret_cast<uint32_t *>(akey);
         if (keys32) {
             for (int k = tid; k < napp; k += T) akey32[k] = ((uint32_t)s_lrank[alab[k]] << 22) | (uint32_t)k;
-            tail_block_sort_keys<TT, uint32_t>(akey32, napp, tail_smem);
+            tail_block_sort_keys<TT, uint32_t>(akey32, napp, tail_smem, ws.tmpk + eb);
         } else {
             for (int k = tid; k < napp; k += T) akey[k] = ((tail_u64)s_lrank[alab[k]] << 32) | (tail_u64)(uint32_t)k;
-            tail_block_sort_keys<TT, tail_u64>(akey, napp, tail_smem);
+            tail_block_sort_keys<TT, tail_u64>(akey, napp, tail_smem, ws.tmpk + eb);
         }
 #define TAIL_ROW_OF(r) (keys32 ? (int)(akey32[r] & ((1u << 22) - 1u)) : (int)(akey[r] & 0xFFFFFFFFull))
 
@@ -889,7 +829,7 @@ tail_structure_kernel(fr3d_nts_t nts, fr3d_tail_ident_t id, fr3d_tail_tables_t t
         {       // files usually list the nts of a chain in sequence order: then the keys are sorted already
             int unsorted = 0;
             for (int u = tid; u + 1 < n; u += T) unsorted |= ckey[u] > ckey[u + 1];
-            if (__syncthreads_or(unsorted)) tail_block_sort_keys<TT, tail_u64>(ckey, n, tail_smem);
+            if (__syncthreads_or(unsorted)) tail_block_sort_keys<TT, tail_u64>(ckey, n, tail_smem, ws.tmpc + lo);
         }
 #define TAIL_COV_NT(r) ((int)(ckey[r] & ((1ull << TAIL_MAX_NT_BITS) - 1ull)))
         for (int r = tid; r < n; r += T) {                   // rows of sorted position r = members of the next key
