@@ -930,3 +930,20 @@ def test_large_structures_device_tail_equals_host_tail():
         assert as_plain(d) == as_plain(host[0])
         assert dev.n_rows > 5 * big.n
         print("%d nt: device path %.1f ms, %d rows" % (big.n, 1e3 * t_dev, dev.n_rows))
+
+
+def test_mixed_batch_of_small_and_large_structures():
+    """Small structures (256-thread blocks of the tail) and large ones (>= 1 024 nts: the 1 024-thread instantiation with the
+    radix sorts) in ONE batch: every structure's rows equal those of the structure annotated alone with the host tail."""
+    base = synthetic.pack_base()
+    small = synthetic.make_structure_batch(base, 3, seed0=7100)
+    big = synthetic.make_tiled_structure(base, 9, (3, 3, 1), seed=1072, pdb="BIGM")
+    mid = synthetic.make_tiled_structure(base, 4, (2, 2, 1), seed=77, pdb="MIDM")          # 1 264 nt: just above the split
+    specs = [synthetic.batch_to_spec(small, 0), synthetic.batch_to_spec(big, 0), synthetic.batch_to_spec(small, 1),
+             synthetic.batch_to_spec(mid, 0), synthetic.batch_to_spec(small, 2)]
+    got = NA.annotate_batch(specs, ALL9, as_arrays=True)
+    assert len(got) == 5
+    for s, spec in enumerate(specs):
+        alone = NA.annotate_batch([spec], ALL9, tail="host")
+        assert list(got[s][0].keys()) == list(alone[0][0].keys()), s
+        assert as_plain(got[s]) == as_plain(alone[0]), s
