@@ -297,6 +297,18 @@ __device__ __forceinline__ void tail_sort_keys_regs(K *keys, int n, K *s_buf) {
 // scan in (digit, warp) order, then each warp scatters its segment in order, 32 keys at a time, the lanes of equal digit
 // ranked by __match_any_sync.  Keys ping-pong between `keys` and `tmp` in global memory (L2-resident); the number of passes
 // comes from the OR of all keys.  s_hist: (TT / 32) * 256 ints of the dynamic shared memory (8 KB / 32 KB).
+// the lanes holding the same 8-bit digit as this one (live lanes only): eight ballots - __match_any_sync takes one hardware
+// step per DISTINCT value, up to 32 with random digits
+__device__ __forceinline__ unsigned tail_digit_peers(int d, bool live) {
+    unsigned peers = __ballot_sync(0xFFFFFFFFu, live);
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+        const unsigned vote = __ballot_sync(0xFFFFFFFFu, (d >> b) & 1);
+        peers &= ((d >> b) & 1) ? vote : ~vote;
+    }
+    return peers;
+}
+
 template <int TT, typename K, bool KV>
 __device__ __noinline__ void tail_radix_sort(K *keys, uint32_t *vals, K *tmpk, uint32_t *tmpv, int n, void *smem,
                                              int skip_low = 0) {      // skip_low: payload bits that need no ordering
@@ -333,9 +345,10 @@ __device__ __noinline__ void tail_radix_sort(K *keys, uint32_t *vals, K *tmpk, u
             const int i = i0 + lane;
             const K k = knext;
             if (i + 32 < w_hi) knext = src[i + 32];
-            const int d = i < w_hi ? (int)((k >> shift) & 255) : -1 - lane;
-            const unsigned peers = __match_any_sync(ALL, d);
-            if (d >= 0 && lane == __ffs(peers) - 1) s_hist[warp * 256 + d] += __popc(peers);
+            const bool live = i < w_hi;
+            const int d = (int)((k >> shift) & 255);
+            const unsigned peers = tail_digit_peers(d, live);
+            if (live && lane == __ffs(peers) - 1) s_hist[warp * 256 + d] += __popc(peers);
             __syncwarp();
         }
         __syncthreads();
@@ -365,8 +378,8 @@ __device__ __noinline__ void tail_radix_sort(K *keys, uint32_t *vals, K *tmpk, u
             const K k = knext;
             const uint32_t v = vnext;
             if (i + 32 < w_hi) { knext = src[i + 32]; if (KV) vnext = vsrc[i + 32]; }
-            const int d = live ? (int)((k >> shift) & 255) : -1 - lane;
-            const unsigned peers = __match_any_sync(ALL, d);
+            const int d = (int)((k >> shift) & 255);
+            const unsigned peers = tail_digit_peers(d, live);
             if (live) {
                 const int at = s_hist[warp * 256 + d] + __popc(peers & ((1u << lane) - 1u));
                 dst[at] = k;
@@ -386,13 +399,16 @@ __device__ __noinline__ void tail_radix_sort(K *keys, uint32_t *vals, K *tmpk, u
     __syncthreads();
 }
 
+#ifndef FR3D_TAIL_RADIX_ALWAYS
+#define FR3D_TAIL_RADIX_ALWAYS 0     // A/B: 1 = no register network at all
+#endif
 // Up to 2 048 keys in a 256-thread block: the register network (no memory traffic at all; the radix sort's passes cost
-// more there: sort hits 43 k -> 58 k cycles per 316-nt structure, profiles/tail_phases_r2e_c4_radix_everywhere.txt).
+// more there: sort hits 43 k -> 53 k cycles per 316-nt structure, profiles/tail_phases_r2e_c4_radix_everywhere.txt).
 // Everything larger, and everything in the 1 024-thread blocks of the large structures: the radix sort (C3: 64 k hits in
 // 0.3 M cycles instead of 17.7 M through the global-memory network, 3.4 M with register tiles).
 template <int TT, typename K>
 __device__ __forceinline__ void tail_block_sort_keys(K *keys, int n, void *smem, void *tmp, int skip_low = 0) {
-    if (TT == TAIL_THREADS && n <= 8 * TT) {
+    if (TT == TAIL_THREADS && n <= 8 * TT && !FR3D_TAIL_RADIX_ALWAYS) {
         __syncthreads();
         if (n <= 1) return;
         K *s_buf = reinterpret_cast<K *>(smem);
