@@ -284,17 +284,32 @@ class BatchAnnotations(object):
         return res
 
     def _build(self, s):
+        """The reference's (interaction_to_list_of_tuples, category_to_interactions) of structure s.  The rows arrive grouped
+        by label (append order = label by label), so every run of one label becomes its list with C-level map / zip:
+        one tuple allocation per row and no Python bytecode per row."""
         r = self.rows_of(s)
         lo = int(self.batch.struct_off[s])
         uid = self.batch.unit_ids_of(s)
-        names = {}
         i2t = defaultdict(list)
         c2i = defaultdict(set)
+        if len(r) == 0:
+            return i2t, c2i
         cats = self.labels.category
-        for l, a, b, c in zip(r['label'].tolist(), (r['nt1'] - lo).tolist(), (r['nt2'] - lo).tolist(), r['crossing'].tolist()):
-            nm = names.get(l)
-            if nm is None:
-                nm = names[l] = self.labels.name(l)
+        lab = r['label']
+        cuts = np.flatnonzero(lab[1:] != lab[:-1]) + 1
+        starts = [0] + cuts.tolist()
+        ends = cuts.tolist() + [len(r)]
+        get = uid.__getitem__
+        u1 = list(map(get, (r['nt1'] - lo).tolist()))
+        u2 = list(map(get, (r['nt2'] - lo).tolist()))
+        cr = r['crossing'].astype(object)
+        cr[r['crossing'] < 0] = None
+        cr = cr.tolist()
+        seen = set()
+        for b, e, l in zip(starts, ends, lab[starts].tolist()):
+            nm = self.labels.name(l)
+            if l not in seen:
+                seen.add(l)
                 if l & _lib.LABEL_COVALENT:
                     c2i['covalent'].add(nm)
                 elif cats[l] is not None:
@@ -302,5 +317,5 @@ class BatchAnnotations(object):
                     c2i[cat].update(adds)
                     if cat == 'basepair':
                         c2i['basepair_detail'].update(adds)
-            i2t[nm].append((uid[a], uid[b], c if c >= 0 else None))
+            i2t[nm].extend(zip(u1[b:e], u2[b:e], cr[b:e]))
         return i2t, c2i
