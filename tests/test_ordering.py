@@ -141,3 +141,28 @@ def test_cuda_ordering_of_a_device_resident_discrepancy_matrix(golden):
     assert sorted(order2) == list(range(700))
     path_len = lambda o: float(sum(host[o[k], o[k + 1]] for k in range(len(o) - 1)))
     assert path_len(order2) < path_len(list(range(700)))
+
+
+@pytest.mark.gpu
+def test_cuda_ordering_random_matrices_against_oracle():
+    """Seeded random matrices beyond the golden set (n = 3 ... 90, continuous and tie-laden integer distances, both
+    copies, several repetition counts / seeds / penalty strengths): orders, scores and 2-opt reductions equal the oracle's."""
+    obs, sobs = _gpu_modules()
+    rng = np.random.Generator(np.random.PCG64(1650))
+    for trial in range(30):
+        n = int(rng.integers(3, 91))
+        if trial % 3 == 0:
+            pts = rng.integers(0, 5, (n, 3)).astype(float)
+            d = np.abs(pts[:, None] - pts[None]).sum(-1)
+        else:
+            pts = rng.normal(size=(n, int(rng.integers(1, 5))))
+            d = np.sqrt(((pts[:, None] - pts[None]) ** 2).sum(-1))
+        d = (d + d.T) / 2
+        np.fill_diagonal(d, 0.0)
+        reps, seed, strength = int(rng.integers(1, 9)), int(rng.integers(1, 1000)), float(rng.choice([0.0, 0.5, 1.0, 2.5]))
+        assert np.array_equal(obs.treePenalty(d), oo.treePenalty(d)), trial
+        assert obs.treePenalizedPathLength(d, reps, seed, strength) == oo.treePenalizedPathLength(d, reps, seed, strength), trial
+        assert sobs.treePenalizedPathLength(d, reps, seed) == oo.treePenalizedPathLength_search(d, reps, seed), trial
+        start = [int(v) for v in rng.permutation(n)]
+        assert list(obs.greedyInsertionPathLength(d, start)) == list(oo.greedyInsertionPathLength(d, start)), trial
+        assert list(obs.twoOptSwap(d, start)) == list(oo.twoOptSwap(d, start)), trial
