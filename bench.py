@@ -299,6 +299,8 @@ def main():
                     help="C4 heavy variant (SURVEY §8(d)): every structure is S_1S72_like, 9 tiled copies = 2 844 nt (implies "
                          "--no-cpu-baseline; not the headline configuration)")
     ap.add_argument("--chunks", type=int, default=8, help="chunks of the e2e pipeline per GPU")
+    ap.add_argument("--taper", default="0.4,0.8,1.2,1.2,1.2,1.2,1.2,0.8",
+                    help="relative chunk sizes of the e2e pipeline (comma separated, as many as --chunks; 'none' = equal chunks)")
     ap.add_argument("--no-graph", action="store_true", help="time Pipeline.run (one Python launch per kernel) instead of the CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -459,8 +461,12 @@ def main():
                               "gather of fixed-size blocks to rank 0 -> one D2H" % sh.n_chunks
             out["sharded_result"] = res
         else:
+            weights = None
+            if args.taper != "none":
+                weights = [float(v) for v in args.taper.split(",")]
+                weights = weights if len(weights) == min(args.chunks, batch_local.n_structures) else None
             pipe = Pipeline(eng, batch_local, pinned, bt, mask, n_chunks=args.chunks, pair_cap=n_pairs, hit_cap=n_hits,
-                            labels=labels, row_cap=n_rows)
+                            labels=labels, row_cap=n_rows, chunk_weights=weights)
             for _ in range(2):
                 res = pipe.run()
             assert res.n_pairs == n_pairs and len(res.rows) == n_rows, "pipelined pass disagrees with the calibration pass"
@@ -483,8 +489,9 @@ def main():
             out["h2d"] = pipe.h2d_bytes
             out["d2h"] = pipe.graph_d2h_bytes if use_graph else (n_rows * 16 + 8 * batch_local.n_structures + 96 * len(pipe.chunks))
             out["e2e_what"] = "engine.Pipeline.%s: pinned host nt records -> H2D -> K1..K4 + device tail -> D2H of the final rows " \
-                              "(label id, nt1, nt2, crossing; reference order), %d chunks on 3 streams%s" % (
+                              "(label id, nt1, nt2, crossing; reference order), %d chunks%s on 3 streams%s" % (
                                   "run_graph" if use_graph else "run", args.chunks,
+                                  " (relative sizes %s: small first and last chunks)" % args.taper if weights else "",
                                   ", the whole pass captured in ONE CUDA graph and replayed" if use_graph else "")
             if use_graph:          # the plain pipeline beside it
                 barrier()

@@ -444,8 +444,10 @@ class Pipeline(object):
     the hit records are then only copied back when want_hits is set."""
 
     def __init__(self, engine, batch, pinned, boxtable, category_mask, n_chunks=4, pair_cap=None, hit_cap=None,
-                 n_streams=3, labels=None, want_hits=None, row_cap=None, chunk_caps=None, row_out=None):
-        """chunk_caps: per chunk (pair_cap, hit_cap, row_cap) instead of the proportional split of pair_cap / hit_cap /
+                 n_streams=3, labels=None, want_hits=None, row_cap=None, chunk_caps=None, row_out=None, chunk_weights=None):
+        """chunk_weights: relative sizes of the chunks (default: equal).  The first chunk's upload and the last chunk's
+        kernels + download are the parts of a pass nothing overlaps with, so a tapered split (small first and last chunks)
+        shortens the pass.  chunk_caps: per chunk (pair_cap, hit_cap, row_cap) instead of the proportional split of pair_cap / hit_cap /
         row_cap; row_out(k, n_struct, row_cap) -> (rows, row_start, row_count, tcounters): caller-owned output tensors
         of chunk k (see Engine.add_tail_buffers), for enqueue() + a collective."""
         torch = engine.torch
@@ -460,7 +462,14 @@ class Pipeline(object):
             ident = tailmod.tail_ident(batch)
         S = batch.n_structures
         n_chunks = max(1, min(n_chunks, S))
-        bounds = [int(round(k * S / n_chunks)) for k in range(n_chunks + 1)]
+        if chunk_weights is not None and len(chunk_weights) == n_chunks and n_chunks > 1:
+            w = np.maximum(np.asarray(chunk_weights, dtype=float), 0.0)
+            cum = np.concatenate([[0.0], np.cumsum(w)]) / max(float(w.sum()), 1e-300)
+            bounds = [int(round(c * S)) for c in cum]
+            for k in range(1, n_chunks + 1):                      # every chunk keeps at least one structure
+                bounds[k] = min(max(bounds[k], bounds[k - 1] + 1), S - (n_chunks - k))
+        else:
+            bounds = [int(round(k * S / n_chunks)) for k in range(n_chunks + 1)]
         self.chunks = []
         dev = engine.device
         self.streams = [torch.cuda.Stream(device=dev) for _ in range(min(n_streams, n_chunks))]
