@@ -6,6 +6,7 @@ no CPU path in this package.
 """
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -399,7 +400,13 @@ class DeviceIdent(object):
         arrays = ident.chunk(s0, s1)
         self.n_struct, self.n_chains, self.n_ends = s1 - s0, arrays[5], arrays[6]
         self.host = arrays[:5]
-        self.max_struct_nt = int(np.diff(arrays[0]).max()) if s1 > s0 else 0     # large structures get their own tail kernel
+        # Large structures (>= 1 024 nts) get the tail's 1 024-thread blocks, one per SM: the shortest time for ONE structure.
+        # A batch of MANY of them is served better by the ordinary 256-thread blocks, four per SM (the heavy bench batch,
+        # 1000 x 2 844 nt: tail 3.6 ms with the large blocks, 2.8 ms without), so they are only announced when they are few.
+        sizes = np.diff(arrays[0]) if s1 > s0 else np.zeros(0, dtype=np.int64)
+        n_big = int((sizes >= 1024).sum())
+        limit = int(os.environ.get("FR3D_TAIL_BIG_LIMIT", "160"))      # ~ one block per SM
+        self.max_struct_nt = int(sizes.max()) if (len(sizes) and 0 < n_big <= limit) else 0
         offs, total = [], 0
         for a in self.host:
             offs.append(total)
