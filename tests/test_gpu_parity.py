@@ -947,3 +947,17 @@ def test_mixed_batch_of_small_and_large_structures():
         alone = NA.annotate_batch([spec], ALL9, tail="host")
         assert list(got[s][0].keys()) == list(alone[0][0].keys()), s
         assert as_plain(got[s]) == as_plain(alone[0]), s
+
+
+def test_large_structures_in_ordinary_tail_blocks(monkeypatch):
+    """Many large structures in one call are not announced (engine.DeviceIdent, FR3D_TAIL_BIG_LIMIT) and run in the
+    256-thread blocks, whose sorts beyond 2 048 keys are the radix sort: forced here for the 2 844-nt and the 25 280-nt
+    structure (key-only and (key, value) form), rows equal to the host tail."""
+    monkeypatch.setenv("FR3D_TAIL_BIG_LIMIT", "0")
+    base = synthetic.pack_base()
+    for copies, lattice, seed in ((9, (3, 3, 1), 1072), (80, (5, 4, 4), 25000)):
+        big = synthetic.make_tiled_structure(base, copies, lattice, seed=seed, pdb="BIGS%d" % copies)
+        dev = NA.annotate_batch(big, ALL9, as_arrays=True)
+        host = NA.annotate_batch(big, ALL9, tail="host")
+        assert list(dev[0][0].keys()) == list(host[0][0].keys())
+        assert as_plain(dev[0]) == as_plain(host[0])
