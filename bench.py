@@ -298,8 +298,8 @@ def main():
     ap.add_argument("--heavy", action="store_true",
                     help="C4 heavy variant (SURVEY §8(d)): every structure is S_1S72_like, 9 tiled copies = 2 844 nt (implies "
                          "--no-cpu-baseline; not the headline configuration)")
-    ap.add_argument("--chunks", type=int, default=8, help="chunks of the e2e pipeline per GPU")
-    ap.add_argument("--taper", default="0.4,0.8,1.2,1.2,1.2,1.2,1.2,0.8",
+    ap.add_argument("--chunks", type=int, default=10, help="chunks of the e2e pipeline per GPU")
+    ap.add_argument("--taper", default="0.3,0.7,1.2,1.3,1.3,1.3,1.3,1.2,0.9,0.5",
                     help="relative chunk sizes of the e2e pipeline (comma separated, as many as --chunks; 'none' = equal chunks)")
     ap.add_argument("--no-graph", action="store_true", help="time Pipeline.run (one Python launch per kernel) instead of the CUDA graph")
     args = ap.parse_args()

@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("FR3D_B200_LIB") or os.path.join(_HERE, "lib", "libfr3
 CSRC = os.path.join(_HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(_HERE), "include")
 
-ABI_VERSION = 6          # FR3D_ABI_VERSION of include/fr3d_b200.h
+ABI_VERSION = 7          # FR3D_ABI_VERSION of include/fr3d_b200.h
 BASE_SLOTS = 16
 BB_SLOTS = 10
 META_INTS = 8
@@ -37,7 +37,7 @@ EXPORTS = ["fr3d_version", "fr3d_last_error", "fr3d_init", "fr3d_upload_tables",
            "fr3d_fp64_fma_probe", "fr3d_ingest_last_error", "fr3d_ingest_tables", "fr3d_cif_parse", "fr3d_ingest_sizes",
            "fr3d_ingest_fill", "fr3d_ingest_free",
            "fr3d_order_workspace", "fr3d_tree_penalty", "fr3d_penalized_distance", "fr3d_order_paths", "fr3d_reorder_symmetric",
-           "fr3d_possibilities_first", "fr3d_possibilities_extend"]
+           "fr3d_possibilities_first", "fr3d_possibilities_extend", "fr3d_frames_fit_ragged", "fr3d_backbone_expand"]
 LABEL_COVALENT = 0x40000000
 TAIL_MAX_LABELS = 1024
 TAIL_MAX_NT = 1 << 17
@@ -167,6 +167,8 @@ def load():
         lib.fr3d_upload_tables.argtypes = [C.POINTER(StaticTables)]
         lib.fr3d_frames_fit.argtypes = [C.POINTER(NtsStruct), vp, C.c_int, vp]
         lib.fr3d_frames_fit_from.argtypes = [C.POINTER(NtsStruct), vp, i32, vp, vp, C.c_int, vp]
+        lib.fr3d_frames_fit_ragged.argtypes = [C.POINTER(NtsStruct), vp, vp, vp, vp, C.c_int, vp]
+        lib.fr3d_backbone_expand.argtypes = [vp, vp, i32, vp, vp, i32, vp, vp]
         lib.fr3d_pair_search_workspace.argtypes = [i32]
         lib.fr3d_pair_search_workspace.restype = C.c_size_t
         lib.fr3d_pair_search.argtypes = [C.POINTER(NtsStruct), dbl, vp, C.c_size_t, vp, vp, vp, i64, vp, vp]

@@ -204,7 +204,35 @@ int fr3d_frames_fit_from(const fr3d_nts_t *nts, const double *compact_base_xyz, 
     const int block = fr3d::FRAMES_WARPS * 32;
     const int grid = (nts->n_nt + block - 1) / block;
     fr3d::frames_fit_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(*nts, status, place_h, compact_base_xyz,
-                                                                                   compact_slots * 3, observed_mask);
+                                                                                   compact_slots * 3, observed_mask, nullptr);
+    CUDA_TRY(cudaGetLastError());
+    return FR3D_OK;
+}
+
+int fr3d_frames_fit_ragged(const fr3d_nts_t *nts, const double *ragged_xyz, const int32_t *group_off,
+                           const uint32_t *observed_mask, int32_t *status, int place_h, void *stream) {
+    if (!nts || !ragged_xyz || !group_off || !observed_mask) return fail(FR3D_E_ARG, "NULL argument");
+    if (observed_mask == nts->base_mask) return fail(FR3D_E_ARG, "the observed_mask plane must not be nts->base_mask (which is written)");
+    if (int rc = require_device(true, nullptr)) return rc;
+    if (nts->n_nt <= 0) return FR3D_OK;
+    const int block = fr3d::FRAMES_WARPS * 32;
+    const int grid = (nts->n_nt + block - 1) / block;
+    fr3d::frames_fit_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(*nts, status, place_h, ragged_xyz, 33,
+                                                                                   observed_mask, group_off);
+    CUDA_TRY(cudaGetLastError());
+    return FR3D_OK;
+}
+
+int fr3d_backbone_expand(const double *bb9, const int8_t *prev_rel, int32_t n_nt, const int32_t *extra_nt,
+                         const double *extra_xyz, int32_t n_extra, double *bb_xyz, void *stream) {
+    if (!bb9 || !prev_rel || !bb_xyz || (n_extra > 0 && (!extra_nt || !extra_xyz))) return fail(FR3D_E_ARG, "NULL argument");
+    if (n_nt < 0 || n_extra < 0) return fail(FR3D_E_ARG, "negative size");
+    int sm_count = 148;
+    if (int rc = require_device(false, &sm_count)) return rc;
+    if (n_nt == 0) return FR3D_OK;
+    const long long want = ((long long)n_nt * FR3D_BB_SLOTS * 3 + 255) / 256;
+    fr3d::backbone_expand_kernel<<<(int)(want < sm_count * 8 ? want : sm_count * 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        bb9, prev_rel, n_nt, extra_nt, extra_xyz, n_extra, bb_xyz);
     CUDA_TRY(cudaGetLastError());
     return FR3D_OK;
 }

@@ -161,9 +161,15 @@ __device__ __forceinline__ bool frames_fit_one(const fr3d_nts_t &nts, int32_t *_
 // (nullptr), or a compact plane [n][src_cols / 3][3] holding only the first slots of every record (the upload keeps
 // slots 0..10 when no hydrogen sits beyond them: they are placed here anyway) with its own mask plane; the full
 // 16-slot record and the completed mask are then written to nts.base_xyz / nts.base_mask.
+//
+// group_off != nullptr: src_plane is RAGGED - only the observed atoms of slots 0..10, nt by nt in slot order, and
+// group_off[g] is the first atom of the 32 nts of warp g (the upload then carries ~9.3 instead of 11 slots per nt).  The
+// warp copies its contiguous piece into the far end of its row buffer, every lane takes its own atoms (offset = a warp scan
+// of the mask bit counts) into registers, and after a __syncwarp writes them to their slots of its row.
 __global__ void __launch_bounds__(FRAMES_WARPS * 32) frames_fit_kernel(fr3d_nts_t nts, int32_t *__restrict__ status,
                                                                        int place_h, const double *__restrict__ src_plane,
-                                                                       int src_cols, const uint32_t *__restrict__ src_mask) {
+                                                                       int src_cols, const uint32_t *__restrict__ src_mask,
+                                                                       const int32_t *__restrict__ group_off) {
     __shared__ double s_std[FR3D_N_PARENTS][FR3D_BASE_SLOTS][3];
     __shared__ double s_rows[FRAMES_WARPS][32 * FRAMES_STRIDE];
     for (int item = threadIdx.x; item < FR3D_N_PARENTS * FR3D_BASE_SLOTS * 3; item += blockDim.x)
@@ -175,6 +181,45 @@ __global__ void __launch_bounds__(FRAMES_WARPS * 32) frames_fit_kernel(fr3d_nts_
     const int rows_here = min(32, max(0, nts.n_nt - n0));
     const bool compact = src_plane != nullptr;
     const int cols = compact ? src_cols : FR3D_BASE_SLOTS * 3;
+    if (group_off) {
+        constexpr int HEAVY = 11;                                         // every heavy base atom lies in slots 0..10
+        const int g = blockIdx.x * FRAMES_WARPS + warp;
+        double *flat = rows + 32 * FRAMES_STRIDE - 32 * HEAVY * 3;        // the last 1056 doubles of the warp's buffer
+        uint32_t m = 0;
+        int excl = 0;
+        if (rows_here > 0) {
+            const int a0 = group_off[g], a1 = group_off[g + 1];
+            for (int t = lane; t < (a1 - a0) * 3; t += 32) cp_async8(flat + t, src_plane + (size_t)a0 * 3 + t);
+            m = n < nts.n_nt ? (src_mask[n] & ((1u << HEAVY) - 1u)) : 0u;
+            int incl = __popc(m);
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const int v = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+                if (lane >= off) incl += v;
+            }
+            excl = incl - __popc(m);
+            cp_async_wait_all();
+        }
+        __syncwarp();
+        double v[HEAVY][3];
+        const int cnt = __popc(m);
+#pragma unroll
+        for (int k = 0; k < HEAVY; ++k) {
+            if (k < cnt) {
+                v[k][0] = flat[(excl + k) * 3]; v[k][1] = flat[(excl + k) * 3 + 1]; v[k][2] = flat[(excl + k) * 3 + 2];
+            }
+        }
+        __syncwarp();                                                     // everybody has its atoms: the rows may be written
+        double *row = rows + lane * FRAMES_STRIDE;
+        for (int c = 0; c < FR3D_BASE_SLOTS * 3; ++c) row[c] = 0.0;
+#pragma unroll
+        for (int k = 0; k < HEAVY; ++k) {
+            if (k < cnt) {
+                const int slot = __fns(m, 0, k + 1);                      // the (k + 1)-th observed slot
+                row[slot * 3] = v[k][0]; row[slot * 3 + 1] = v[k][1]; row[slot * 3 + 2] = v[k][2];
+            }
+        }
+    } else
     {   // stage the warp's records row by row (cols doubles each: lanes 0..31, then the first lanes for the rest)
         const double *src = (compact ? src_plane : nts.base_xyz) + (size_t)n0 * cols + lane;
         double *dst = rows + lane;
@@ -205,6 +250,23 @@ __global__ void __launch_bounds__(FRAMES_WARPS * 32) frames_fit_kernel(fr3d_nts_
         for (int r = 0; r < rows_here; ++r)
             if (lane < 24) dstg[r * (FR3D_BASE_SLOTS * 3) + 24 + lane] = rows[r * FRAMES_STRIDE + 24 + lane];
     }
+}
+
+// The upload's backbone plane carries slots 0..8; slot 9 (the O3' of the previous residue, NA:480-525) is filled here
+// from the previous ROW where prev_rel says so (the common case) and from a short explicit list otherwise.
+__global__ void backbone_expand_kernel(const double *__restrict__ bb9, const int8_t *__restrict__ prev_rel, int n_nt,
+                                       const int32_t *__restrict__ extra_nt, const double *__restrict__ extra_xyz, int n_extra,
+                                       double *__restrict__ bb_xyz) {
+    const long long total = (long long)n_nt * FR3D_BB_SLOTS * 3;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int n = (int)(t / (FR3D_BB_SLOTS * 3)), c = (int)(t % (FR3D_BB_SLOTS * 3));
+        double v = 0.0;
+        if (c < 27) v = bb9[(size_t)n * 27 + c];
+        else if (prev_rel[n] == 1 && n > 0) v = bb9[(size_t)(n - 1) * 27 + 5 * 3 + (c - 27)];
+        bb_xyz[t] = v;
+    }
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_extra * 3; e += gridDim.x * blockDim.x)
+        bb_xyz[(size_t)extra_nt[e / 3] * FR3D_BB_SLOTS * 3 + 27 + e % 3] = extra_xyz[e];
 }
 
 }  // namespace fr3d

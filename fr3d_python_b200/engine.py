@@ -201,7 +201,18 @@ class Engine(object):
     # ---------------------------------------------------------------- K1
     def _frames_fit(self, dbatch, status_ptr, place_h, st):
         compact = getattr(dbatch, "compact_base", None)
-        if compact is not None:
+        packed = getattr(dbatch, "packed", None)
+        if packed is not None:
+            # the packed upload: backbone slots 0..8 + previous-O3' links -> bb_xyz, ragged observed base atoms -> K1
+            _lib.check(self.lib.fr3d_backbone_expand(packed["bb9"].data_ptr(), packed["prev_rel"].data_ptr(), dbatch.n,
+                                                     packed["extra_nt"].data_ptr(), packed["extra_xyz"].data_ptr(),
+                                                     dbatch.packed_n_extra, dbatch.dev["bb_xyz"].data_ptr(), st),
+                       "fr3d_backbone_expand")
+            _lib.check(self.lib.fr3d_frames_fit_ragged(C.byref(dbatch.nts), packed["ragged"].data_ptr(),
+                                                       packed["group_off"].data_ptr(), compact[2].data_ptr(), status_ptr,
+                                                       1 if place_h else 0, st), "fr3d_frames_fit_ragged")
+            self.launches += 1
+        elif compact is not None:
             _lib.check(self.lib.fr3d_frames_fit_from(C.byref(dbatch.nts), compact[0].data_ptr(), compact[1],
                                                      compact[2].data_ptr(), status_ptr, 1 if place_h else 0, st),
                        "fr3d_frames_fit_from")
@@ -436,6 +447,28 @@ class Plan(object):
     pass
 
 
+def _pack_upload(base, base_mask, bb, bb_mask):
+    """The packed upload of one chunk (host numpy): base [n][11][3] with its observed-mask plane, bb [n][10][3] with its mask
+    -> ragged [A][3] (observed base atoms only, nt by nt in slot order), group_off [ceil(n / 32) + 1] (first atom of every
+    32 nts), bb9 [n][9][3], prev_rel int8 [n] (1: slot 9 is the previous ROW's O3'), and the explicit (nt, xyz) list of the
+    previous-O3' entries that are not."""
+    n = base.shape[0]
+    bits = ((base_mask.astype(np.uint32)[:, None] >> np.arange(base.shape[1], dtype=np.uint32)) & 1).astype(bool)
+    ragged = np.ascontiguousarray(base[bits])
+    off = np.concatenate([[0], np.cumsum(bits.sum(1))]).astype(np.int64)
+    group_off = off[np.minimum(np.arange(0, n + 32, 32), n)].astype(np.int32)
+    if group_off.shape[0] != (n + 31) // 32 + 1:
+        group_off = group_off[:(n + 31) // 32 + 1]
+    has9 = ((bb_mask >> 9) & 1).astype(bool)
+    prev_ok = np.zeros(n, dtype=bool)
+    if n > 1:
+        prev_ok[1:] = has9[1:] & ((bb_mask[:-1] >> 5) & 1).astype(bool) & np.all(bb[1:, 9] == bb[:-1, 5], axis=1)
+    extra = np.nonzero(has9 & ~prev_ok)[0].astype(np.int32)
+    return {"ragged": ragged if ragged.size else np.zeros((1, 3)), "group_off": group_off,
+            "bb9": np.ascontiguousarray(bb[:, :9]), "prev_rel": prev_ok.astype(np.int8),
+            "extra_nt": extra, "extra_xyz": np.ascontiguousarray(bb[extra, 9])}
+
+
 _FIELDS = ("center", "rot", "base_xyz", "bb_xyz", "base_mask", "bb_mask", "meta")
 
 
@@ -451,8 +484,12 @@ class Pipeline(object):
     the hit records are then only copied back when want_hits is set."""
 
     def __init__(self, engine, batch, pinned, boxtable, category_mask, n_chunks=4, pair_cap=None, hit_cap=None,
-                 n_streams=3, labels=None, want_hits=None, row_cap=None, chunk_caps=None, row_out=None, chunk_weights=None):
-        """chunk_weights: relative sizes of the chunks (default: equal).  The first chunk's upload and the last chunk's
+                 n_streams=3, labels=None, want_hits=None, row_cap=None, chunk_caps=None, row_out=None, chunk_weights=None,
+                 packed_upload=True):
+        """packed_upload (with a compact base plane): the upload carries only the OBSERVED base atoms (ragged, ~9.3 of 11
+        slots per nt) and backbone slots 0..8 - slot 9, the previous residue's O3', is rebuilt on the device from the
+        previous row - 490 instead of 552 bytes per nt over PCIe; K1 (fr3d_frames_fit_ragged) and fr3d_backbone_expand write
+        the ordinary records.  chunk_weights: relative sizes of the chunks (default: equal).  The first chunk's upload and the last chunk's
         kernels + download are the parts of a pass nothing overlaps with, so a tapered split (small first and last chunks)
         shortens the pass.  chunk_caps: per chunk (pair_cap, hit_cap, row_cap) instead of the proportional split of pair_cap / hit_cap /
         row_cap; row_out(k, n_struct, row_cap) -> (rows, row_start, row_count, tcounters): caller-owned output tensors
@@ -495,11 +532,21 @@ class Pipeline(object):
             # the full 16-slot records.
             compact = pinned["base_xyz"].shape[1] < _lib.BASE_SLOTS
             uploaded = [name for name in _FIELDS if name not in ("center", "rot")]
+            packed = None
+            if compact and packed_upload and n > 0:
+                packed = _pack_upload(pinned["base_xyz"][lo:hi].numpy(), pinned["base_mask"][lo:hi].numpy(),
+                                      pinned["bb_xyz"][lo:hi].numpy(), pinned["bb_mask"][lo:hi].numpy())
+                uploaded = [name for name in uploaded if name not in ("base_xyz", "bb_xyz")]
             offs, total = {}, 0
             for name in uploaded:
                 src = pinned[name][lo:hi]
                 offs[name] = (total, src.numel() * src.element_size(), src.dtype, tuple(src.shape))
                 total += (offs[name][1] + 255) // 256 * 256
+            poffs = {}
+            if packed is not None:
+                for name, arr in packed.items():
+                    poffs[name] = (total, arr.nbytes)
+                    total += (arr.nbytes + 255) // 256 * 256
             ch.ident = None
             if ident is not None:
                 ch.ident = DeviceIdent(torch, None, ident, ch.s0, ch.s1)
@@ -517,11 +564,26 @@ class Pipeline(object):
                 if name == "base_xyz" and compact:
                     ch.compact_base = [view, int(shape[1]), None]
                     ch.dev[name] = torch.empty((n, _lib.BASE_SLOTS, 3), dtype=dt, device=dev)
-                elif name == "base_mask" and compact:
+                elif name == "base_mask" and compact and packed is None:
                     ch.compact_base[2] = view          # the uploaded (observed) masks; K1 writes the record's own
                     ch.dev[name] = torch.empty((n,), dtype=dt, device=dev)
                 else:
                     ch.dev[name] = view
+            ch.packed = None
+            if packed is not None:
+                views = {}
+                for name, arr in packed.items():
+                    o, nb = poffs[name]
+                    if nb:
+                        ch.host_blob[o:o + nb].copy_(torch.from_numpy(arr.view(np.uint8).reshape(-1)))
+                    views[name] = ch.dev_blob[o:o + max(nb, 1)]
+                ch.packed = views
+                ch.packed_n_extra = int(packed["extra_nt"].shape[0])
+                ch.compact_base = [views["ragged"], 11, ch.dev_blob[offs["base_mask"][0]:offs["base_mask"][0] + offs["base_mask"][1]]
+                                   .view(pinned["base_mask"].dtype)]
+                ch.dev["base_xyz"] = torch.empty((n, _lib.BASE_SLOTS, 3), dtype=pinned["base_xyz"].dtype, device=dev)
+                ch.dev["base_mask"] = torch.empty((n,), dtype=pinned["base_mask"].dtype, device=dev)
+                ch.dev["bb_xyz"] = torch.empty((n, _lib.BB_SLOTS, 3), dtype=pinned["bb_xyz"].dtype, device=dev)
             if ch.ident is not None:
                 nb = ch.ident.host_blob.numel()
                 ch.host_blob[ident_off:ident_off + nb].copy_(ch.ident.host_blob)

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define FR3D_ABI_VERSION 6
+#define FR3D_ABI_VERSION 7
 
 #define FR3D_OK 0
 #define FR3D_E_CUDA (-1)      /* a CUDA runtime call failed; see fr3d_last_error */
@@ -159,6 +159,16 @@ int fr3d_upload_tables(const fr3d_static_tables_t *host_tables);   /* to the cur
  * the hydrogen placement arithmetic of infer_NA_hydrogens (components.py:452-462) when
  * place_h != 0.  Reads base_xyz/base_mask/meta; writes center, rot, missing hydrogen slots,
  * base_mask (hydrogen bits + FR3D_MASK_HAS_FRAME) and status[n] (0 ok, -1 no parent, -2 <3 atoms). */
+/* The same from a RAGGED upload plane: ragged_xyz holds only the observed atoms of slots 0..10 (every heavy base atom), nt by
+ * nt in slot order; group_off[g] = first atom of the 32 nts of group g ([ceil(n_nt / 32) + 1]); observed_mask as above.
+ * ~9.3 instead of 11 (or 16) slots per nt cross PCIe; the full 16-slot records are written to nts->base_xyz. */
+int fr3d_frames_fit_ragged(const fr3d_nts_t *nts, const double *ragged_xyz, const int32_t *group_off,
+                           const uint32_t *observed_mask, int32_t *status, int place_h, void *stream);
+/* Companion for the backbone plane: bb9 [n_nt][9][3] (slots 0..8) -> bb_xyz [n_nt][10][3]; slot 9, the O3' of the previous
+ * residue (NA_pairwise_interactions.py:480-525), is the previous ROW's O3' where prev_rel[n] == 1 and comes from the explicit
+ * list (extra_nt [n_extra], extra_xyz [n_extra][3]) otherwise; the presence bit lives in nts->bb_mask as always. */
+int fr3d_backbone_expand(const double *bb9, const int8_t *prev_rel, int32_t n_nt, const int32_t *extra_nt,
+                         const double *extra_xyz, int32_t n_extra, double *bb_xyz, void *stream);
 int fr3d_frames_fit(const fr3d_nts_t *nts, int32_t *status, int place_h, void *stream);
 /* Same, with the observed base atoms read from a compact plane [n][compact_slots][3] (11 <= compact_slots <= 16:
  * the first slots of every record; an upload without atoms in slots 11..15 keeps slots 0..10 only) and their

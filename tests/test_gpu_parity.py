@@ -961,3 +961,40 @@ def test_large_structures_in_ordinary_tail_blocks(monkeypatch):
         host = NA.annotate_batch(big, ALL9, tail="host")
         assert list(dev[0][0].keys()) == list(host[0][0].keys())
         assert as_plain(dev[0]) == as_plain(host[0])
+
+
+def test_packed_upload_equals_plain_upload(golden):
+    """Pipeline(packed_upload=True): ragged observed base atoms + backbone slots 0..8 over PCIe, the records completed on the
+    device (fr3d_frames_fit_ragged, fr3d_backbone_expand) - rows identical to the plain upload, on a perturbed batch with
+    missing atoms and on the variants structure (two models, symmetry copy, alternate ids: previous-O3' links that are not
+    the previous row)."""
+    import torch
+    from fr3d_python_b200.engine import Pipeline, pin_batch
+    eng = Engine.get()
+    bt, atoms, labels = NA._tables(NA._default_focused(ALL9['basepair']), NA.load_ideal_basepair_hydrogen_bonds())
+    mask = NA.category_mask(ALL9)
+    base = synthetic.pack_base()
+    batch = synthetic.make_structure_batch(base, 21, seed0=3100)
+    rng = np.random.default_rng(9)
+    lost = rng.random(batch.n) < 0.15
+    batch.base_mask[lost] &= ~np.uint32(1 << 4)                       # a missing base atom here and there
+    nobb = rng.random(batch.n) < 0.1
+    batch.bb_mask[nobb] &= ~np.uint32(1 << 5)                         # ... and a missing O3' (breaks the link of the next row)
+    variants = packing.pack_specs(golden("spec_1gid_variants.json.gz"))
+    for b in (batch, variants):
+        pinned = pin_batch(torch, b)
+        if pinned["base_xyz"].shape[1] >= 16:
+            continue
+        outs = []
+        for packed in (False, True):
+            pipe = Pipeline(eng, b, pinned, bt, mask, n_chunks=3, labels=labels, packed_upload=packed)
+            assert (pipe.chunks[0].packed is not None) == packed
+            for _ in range(2):
+                out = pipe.run_graph()
+            outs.append((out.n_pairs, out.rows.copy(), out.row_start.copy(), out.row_count.copy(), pipe.h2d_bytes))
+        assert outs[0][0] == outs[1][0]
+        for s in range(b.n_structures):
+            r0 = outs[0][1][outs[0][2][s]:outs[0][2][s] + outs[0][3][s]]
+            r1 = outs[1][1][outs[1][2][s]:outs[1][2][s] + outs[1][3][s]]
+            assert np.array_equal(r0, r1), s
+        assert outs[1][4] < 0.93 * outs[0][4]

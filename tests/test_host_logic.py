@@ -443,3 +443,39 @@ def test_identity_bookkeeping_equals_first_implementation(golden, name):
     for g, w, what in zip(got, want, ("meta", "bb_xyz", "bb_mask")):
         assert np.array_equal(g, w), what
     assert (got[2] >> defs.BB_PREV_O3 & 1).sum() > 0 or name == "chi_sweep"
+
+
+def test_packed_upload_layout_round_trips():
+    """engine._pack_upload: ragged observed base atoms + group offsets, backbone slots 0..8 + previous-O3' links; unpacking
+    on the host gives back every observed coordinate (what fr3d_frames_fit_ragged / fr3d_backbone_expand do on the device)."""
+    from fr3d_python_b200 import engine, synthetic
+    base = synthetic.pack_base()
+    batch = synthetic.make_structure_batch(base, 3, seed0=11)
+    rng = np.random.default_rng(5)
+    b = batch.base_xyz[:, :11].copy()
+    m = batch.base_mask.copy() & 0x7FF
+    drop = rng.random(len(m)) < 0.2
+    m[drop] &= ~np.uint32(1 << 3)                        # some residues lack an atom
+    bb, bbm = batch.bb_xyz.copy(), batch.bb_mask.copy()
+    odd = np.nonzero((bbm >> 9) & 1)[0][::7]
+    bb[odd, 9] += 0.25                                   # previous-O3' entries that are NOT the previous row's O3'
+    p = engine._pack_upload(b, m, bb, bbm)
+    n = len(m)
+    assert p["group_off"].shape[0] == (n + 31) // 32 + 1 and p["group_off"][-1] == p["ragged"].shape[0]
+    k = 0
+    for i in range(n):
+        if i % 32 == 0:
+            assert p["group_off"][i // 32] == k
+        for s in range(11):
+            if (m[i] >> s) & 1:
+                assert np.array_equal(p["ragged"][k], b[i, s])
+                k += 1
+    assert k == p["ragged"].shape[0]
+    out = np.zeros_like(bb)
+    out[:, :9] = p["bb9"]
+    rel = p["prev_rel"] == 1
+    out[1:][rel[1:], 9] = p["bb9"][:-1][rel[1:], 5]
+    out[p["extra_nt"], 9] = p["extra_xyz"]
+    has9 = ((bbm >> 9) & 1).astype(bool)
+    assert np.array_equal(out[has9, 9], bb[has9, 9]) and np.array_equal(out[:, :9], bb[:, :9])
+    assert set(odd.tolist()) <= set(p["extra_nt"].tolist()) and len(p["extra_nt"]) < 0.2 * has9.sum()
