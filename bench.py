@@ -301,6 +301,7 @@ def main():
     ap.add_argument("--chunks", type=int, default=10, help="chunks of the e2e pipeline per GPU")
     ap.add_argument("--taper", default="0.3,0.7,1.2,1.3,1.3,1.3,1.3,1.2,0.9,0.5",
                     help="relative chunk sizes of the e2e pipeline (comma separated, as many as --chunks; 'none' = equal chunks)")
+    ap.add_argument("--streams", type=int, default=3, help="streams the chunks of the e2e pipeline rotate over")
     ap.add_argument("--no-graph", action="store_true", help="time Pipeline.run (one Python launch per kernel) instead of the CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -466,7 +467,7 @@ def main():
                 weights = [float(v) for v in args.taper.split(",")]
                 weights = weights if len(weights) == min(args.chunks, batch_local.n_structures) else None
             pipe = Pipeline(eng, batch_local, pinned, bt, mask, n_chunks=args.chunks, pair_cap=n_pairs, hit_cap=n_hits,
-                            labels=labels, row_cap=n_rows, chunk_weights=weights)
+                            labels=labels, row_cap=n_rows, chunk_weights=weights, n_streams=args.streams)
             for _ in range(2):
                 res = pipe.run()
             assert res.n_pairs == n_pairs and len(res.rows) == n_rows, "pipelined pass disagrees with the calibration pass"
@@ -489,9 +490,9 @@ def main():
             out["h2d"] = pipe.h2d_bytes
             out["d2h"] = pipe.graph_d2h_bytes if use_graph else (n_rows * 16 + 8 * batch_local.n_structures + 96 * len(pipe.chunks))
             out["e2e_what"] = "engine.Pipeline.%s: pinned host nt records -> H2D -> K1..K4 + device tail -> D2H of the final rows " \
-                              "(label id, nt1, nt2, crossing; reference order), %d chunks%s on 3 streams%s" % (
+                              "(label id, nt1, nt2, crossing; reference order), %d chunks%s on %d streams%s" % (
                                   "run_graph" if use_graph else "run", args.chunks,
-                                  " (relative sizes %s: small first and last chunks)" % args.taper if weights else "",
+                                  " (relative sizes %s: small first and last chunks)" % args.taper if weights else "", args.streams,
                                   ", the whole pass captured in ONE CUDA graph and replayed" if use_graph else "")
             if use_graph:          # the plain pipeline beside it
                 barrier()
