@@ -153,6 +153,9 @@ static int init_current_device(int device) {
                                   (int)fr3d::disc_smem_bytes(fr3d::DISC_MAXN)));
     CUDA_TRY(cudaFuncSetAttribute(fr3d::tail_structure_kernel<fr3d::TAIL_THREADS, FR3D_TAIL_MINB, false>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fr3d::TAIL_SMEM));
+    CUDA_TRY(cudaFuncSetAttribute(fr3d::tail_structure_kernel<fr3d::TAIL_THREADS_MANY, 8, false>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)fr3d::tail_smem_bytes<fr3d::TAIL_THREADS_MANY>()));
     CUDA_TRY(cudaFuncSetAttribute(fr3d::tail_structure_kernel<fr3d::TAIL_THREADS_BIG, 1, true>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)fr3d::tail_smem_bytes<fr3d::TAIL_THREADS_BIG>()));
@@ -474,10 +477,18 @@ int fr3d_annotation_tail(const fr3d_nts_t *nts, const fr3d_tail_ident_t *ident, 
         fr3d::tail_bin_kernel<<<grid, 256, 0, st>>>(hits, hit_cap, counters, index_offset, *ident, ws, tail_counters);
         fr3d::tail_scan_kernel<<<1, 1024, 0, st>>>(ws, S);                        // both return at once unless a structure
         fr3d::tail_scatter_kernel<<<grid, 256, 0, st>>>(hits, hit_cap, counters, index_offset, *ident, ws, tail_counters);
-        const int blocks = S < sm_count * 7 ? S : sm_count * 7;
-        fr3d::tail_structure_kernel<fr3d::TAIL_THREADS, FR3D_TAIL_MINB, false>
-            <<<blocks, fr3d::TAIL_THREADS, fr3d::TAIL_SMEM, st>>>(*nts, *ident, *tables, hits, index_offset, ws, rows, row_cap,
-                                                                  row_start, row_count, tail_counters);
+        // more (small) structures than 256-thread blocks fit at once: 128-thread blocks, all structures in flight together
+        if (S > sm_count * FR3D_TAIL_MINB && nts->n_nt / S < fr3d::TAIL_BIG_NT) {
+            const int blocks = S < sm_count * 8 ? S : sm_count * 8;
+            fr3d::tail_structure_kernel<fr3d::TAIL_THREADS_MANY, 8, false>
+                <<<blocks, fr3d::TAIL_THREADS_MANY, fr3d::tail_smem_bytes<fr3d::TAIL_THREADS_MANY>(), st>>>(
+                    *nts, *ident, *tables, hits, index_offset, ws, rows, row_cap, row_start, row_count, tail_counters);
+        } else {
+            const int blocks = S < sm_count * FR3D_TAIL_MINB ? S : sm_count * FR3D_TAIL_MINB;
+            fr3d::tail_structure_kernel<fr3d::TAIL_THREADS, FR3D_TAIL_MINB, false>
+                <<<blocks, fr3d::TAIL_THREADS, fr3d::TAIL_SMEM, st>>>(*nts, *ident, *tables, hits, index_offset, ws, rows, row_cap,
+                                                                      row_start, row_count, tail_counters);
+        }
         if (ident->max_struct_nt >= fr3d::TAIL_BIG_NT) {                          // the large structures: 1024-thread blocks
             const int big_blocks = S < sm_count ? S : sm_count;
             fr3d::tail_structure_kernel<fr3d::TAIL_THREADS_BIG, 1, true>

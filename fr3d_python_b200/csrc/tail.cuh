@@ -33,6 +33,7 @@ namespace fr3d {
 #define FR3D_TAIL_MINB 4             // blocks per SM the structure kernel is compiled for (4: 64 registers, no spills)
 #endif
 constexpr int TAIL_THREADS = 256;        // block size for ordinary structures (four blocks per SM)
+constexpr int TAIL_THREADS_MANY = 128;   // ... when a call has more structures than 256-thread blocks fit at once (eight per SM)
 constexpr int TAIL_THREADS_BIG = 1024;   // ... for structures of TAIL_BIG_NT nts and more: one block per SM, four times the lanes
 constexpr int TAIL_BIG_NT = 1024;
 constexpr int TAIL_SORT_CAP = 2048;      // elements sorted in registers by 256 threads (exchange buffer: 16 KB of shared memory)
@@ -408,7 +409,7 @@ __device__ __noinline__ void tail_radix_sort(K *keys, uint32_t *vals, K *tmpk, u
 // 0.3 M cycles instead of 17.7 M through the global-memory network, 3.4 M with register tiles).
 template <int TT, typename K>
 __device__ __forceinline__ void tail_block_sort_keys(K *keys, int n, void *smem, void *tmp, int skip_low = 0) {
-    if (TT == TAIL_THREADS && n <= 8 * TT && !FR3D_TAIL_RADIX_ALWAYS) {
+    if (TT != TAIL_THREADS_BIG && n <= 8 * TT && !FR3D_TAIL_RADIX_ALWAYS) {
         __syncthreads();
         if (n <= 1) return;
         K *s_buf = reinterpret_cast<K *>(smem);
@@ -438,7 +439,10 @@ __device__ __forceinline__ TailEntrySrc tail_entry_of(const fr3d_hit_t &h, int d
 }
 
 // One block per structure (dynamic assignment through tc[1] / tc[3]).  BIG = false: blocks of 256 threads, four per SM, take
-// the structures below TAIL_BIG_NT nts (all of them when the caller does not announce large ones); BIG = true: blocks of
+// the structures below TAIL_BIG_NT nts (all of them when the caller does not announce large ones) - or blocks of 128
+// threads, eight per SM, when the call has more structures than 4 x SMs: a structure then takes longer, but all of them
+// are in flight at once instead of in 1.7 rounds (1000 structures: 0.35 -> 0.30 ms; a pipeline chunk of ~100 structures is
+// faster with the larger blocks, profiles/ab_tail_threads_r2.log); BIG = true: blocks of
 // 1024 threads, one per SM, take the others - the phases are block-wide networks and scans whose time falls with the lane
 // count, and a large structure has nobody to share the SM with anyway.
 template <int TT, int MINB, bool BIG>
