@@ -447,6 +447,20 @@ class Plan(object):
     pass
 
 
+def chunk_bounds(S, n_chunks, weights=None):
+    """Structure boundaries of the pipeline chunks: equal parts, or parts proportional to `weights` (one per chunk) with at
+    least one structure each."""
+    n_chunks = max(1, min(int(n_chunks), int(S))) if S > 0 else 1
+    if weights is not None and len(weights) == n_chunks and n_chunks > 1:
+        w = np.maximum(np.asarray(weights, dtype=float), 0.0)
+        cum = np.concatenate([[0.0], np.cumsum(w)]) / max(float(w.sum()), 1e-300)
+        bounds = [int(round(c * S)) for c in cum]
+        for k in range(1, n_chunks + 1):                      # every chunk keeps at least one structure
+            bounds[k] = min(max(bounds[k], bounds[k - 1] + 1), S - (n_chunks - k))
+        return bounds
+    return [int(round(k * S / n_chunks)) for k in range(n_chunks + 1)]
+
+
 def _pack_upload(base, base_mask, bb, bb_mask):
     """The packed upload of one chunk (host numpy): base [n][11][3] with its observed-mask plane, bb [n][10][3] with its mask
     -> ragged [A][3] (observed base atoms only, nt by nt in slot order), group_off [ceil(n / 32) + 1] (first atom of every
@@ -506,14 +520,7 @@ class Pipeline(object):
             ident = tailmod.tail_ident(batch)
         S = batch.n_structures
         n_chunks = max(1, min(n_chunks, S))
-        if chunk_weights is not None and len(chunk_weights) == n_chunks and n_chunks > 1:
-            w = np.maximum(np.asarray(chunk_weights, dtype=float), 0.0)
-            cum = np.concatenate([[0.0], np.cumsum(w)]) / max(float(w.sum()), 1e-300)
-            bounds = [int(round(c * S)) for c in cum]
-            for k in range(1, n_chunks + 1):                      # every chunk keeps at least one structure
-                bounds[k] = min(max(bounds[k], bounds[k - 1] + 1), S - (n_chunks - k))
-        else:
-            bounds = [int(round(k * S / n_chunks)) for k in range(n_chunks + 1)]
+        bounds = chunk_bounds(S, n_chunks, chunk_weights)
         self.chunks = []
         dev = engine.device
         self.streams = [torch.cuda.Stream(device=dev) for _ in range(min(n_streams, n_chunks))]

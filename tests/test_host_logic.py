@@ -479,3 +479,18 @@ def test_packed_upload_layout_round_trips():
     has9 = ((bbm >> 9) & 1).astype(bool)
     assert np.array_equal(out[has9, 9], bb[has9, 9]) and np.array_equal(out[:, :9], bb[:, :9])
     assert set(odd.tolist()) <= set(p["extra_nt"].tolist()) and len(p["extra_nt"]) < 0.2 * has9.sum()
+
+
+def test_pipeline_chunk_bounds():
+    """engine.chunk_bounds: equal chunks, tapered chunks (bench.py --taper), degenerate cases."""
+    from fr3d_python_b200.engine import chunk_bounds
+    assert chunk_bounds(1000, 8) == [0, 125, 250, 375, 500, 625, 750, 875, 1000]
+    w = [0.3, 0.7, 1.2, 1.3, 1.3, 1.3, 1.3, 1.2, 0.9, 0.5]
+    b = chunk_bounds(1000, 10, w)
+    assert b[0] == 0 and b[-1] == 1000 and all(y > x for x, y in zip(b, b[1:]))
+    sizes = np.diff(b)
+    assert sizes[0] == 30 and sizes[-1] == 50 and sizes.max() == 130
+    assert chunk_bounds(3, 10, w) == [0, 1, 2, 3]                       # fewer structures than chunks: the weights are dropped
+    b = chunk_bounds(5, 5, [0, 0, 0, 0, 1])                             # every chunk keeps a structure
+    assert b == [0, 1, 2, 3, 4, 5]
+    assert chunk_bounds(7, 1, [1.0]) == [0, 7]
