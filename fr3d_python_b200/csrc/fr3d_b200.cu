@@ -149,6 +149,8 @@ static int init_current_device(int device) {
     CUDA_TRY(cudaFuncSetAttribute(fr3d::classify_list2_kernel<true, fr3d::L2_WARPS_PAIR>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)fr3d::l2_smem_bytes<true, fr3d::L2_WARPS_PAIR>()));
+    CUDA_TRY(cudaFuncSetAttribute(fr3d::kabsch_batched_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)fr3d::KABSCH_SMEM));
     CUDA_TRY(cudaFuncSetAttribute(fr3d::discrepancy_all_vs_all_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)fr3d::disc_smem_bytes(fr3d::DISC_MAXN)));
     CUDA_TRY(cudaFuncSetAttribute(fr3d::tail_structure_kernel<fr3d::TAIL_THREADS, FR3D_TAIL_MINB, false>,
@@ -555,8 +557,8 @@ int fr3d_kabsch_batched(const double *set1, const double *set2, const double *w,
     if (!set1 || !set2 || !off) return fail(FR3D_E_ARG, "NULL argument");      // every output may be NULL
     if (int rc = require_device(false, nullptr)) return rc;
     if (n_prob <= 0) return FR3D_OK;
-    const int block = 128;
-    fr3d::kabsch_batched_kernel<<<(n_prob + block - 1) / block, block, 0, static_cast<cudaStream_t>(stream)>>>(
+    const int block = fr3d::KABSCH_WARPS * 32;
+    fr3d::kabsch_batched_kernel<<<(n_prob + block - 1) / block, block, fr3d::KABSCH_SMEM, static_cast<cudaStream_t>(stream)>>>(
         set1, set2, w, off, n_prob, U, mean1, mean2, rmsd, sse, new1);
     CUDA_TRY(cudaGetLastError());
     return FR3D_OK;

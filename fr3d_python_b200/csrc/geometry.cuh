@@ -15,60 +15,106 @@
 namespace fr3d {
 
 // ---------------------------------------------------------------- K5 -------
-__global__ void __launch_bounds__(128)
+// One thread per problem (ragged offsets).  A thread walking "its" rows in global memory makes every load of the warp
+// touch 32 different sectors (2.0 TB/s of DRAM traffic at 31 % of the HBM peak, profiles/geometry_r2_raw_metrics.txt), so
+// the rows of a warp's 32 problems - one contiguous block of set1 / set2 (/ w) - are first copied into shared memory with
+// coalesced cp.async, the three passes (means, covariance, fitted coordinates + sse) run out of shared memory, and the
+// fitted coordinates are written back to global memory the same coalesced way.  A warp whose 32 problems have more than
+// KABSCH_ROWS rows in total (long point sets) works from global memory as before.
+constexpr int KABSCH_WARPS = 4;
+#ifndef FR3D_KABSCH_ROWS
+#define FR3D_KABSCH_ROWS 384
+#endif
+constexpr int KABSCH_ROWS = FR3D_KABSCH_ROWS;    // rows staged per warp (384: 12 points per problem on average; 0: no staging)
+constexpr size_t KABSCH_SMEM = sizeof(double) * KABSCH_WARPS * KABSCH_ROWS * 7;
+
+__global__ void __launch_bounds__(KABSCH_WARPS * 32)
 kabsch_batched_kernel(const double *__restrict__ set1, const double *__restrict__ set2, const double *__restrict__ w,
                       const int32_t *__restrict__ off, int n_prob, double *__restrict__ Uo, double *__restrict__ mean1o,
                       double *__restrict__ mean2o, double *__restrict__ rmsdo, double *__restrict__ sseo,
                       double *__restrict__ new1o) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n_prob) return;
-    const int r0 = off[p], r1 = off[p + 1];
-    const int len = r1 - r0;
-    double m1[3] = {0, 0, 0}, m2[3] = {0, 0, 0};
-    for (int k = r0; k < r1; ++k) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) { m1[c] += set1[(size_t)k * 3 + c]; m2[c] += set2[(size_t)k * 3 + c]; }
+    extern __shared__ double kb_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int p0 = (blockIdx.x * KABSCH_WARPS + warp) * 32;
+    if (p0 >= n_prob) return;
+    const int p = p0 + lane;
+    const int R0 = off[p0], R1 = off[min(p0 + 32, n_prob)];
+    const int R = R1 - R0;
+    const bool staged = R <= KABSCH_ROWS;                                  // warp uniform
+    double *s1 = kb_smem + (size_t)warp * KABSCH_ROWS * 7, *s2 = s1 + KABSCH_ROWS * 3, *sw = s2 + KABSCH_ROWS * 3;
+    if (staged) {
+        for (int t = lane; t < R * 3; t += 32) {
+            cp_async8(s1 + t, set1 + (size_t)R0 * 3 + t);
+            cp_async8(s2 + t, set2 + (size_t)R0 * 3 + t);
+        }
+        if (w) for (int t = lane; t < R; t += 32) cp_async8(sw + t, w + R0 + t);
+        cp_async_wait_all();
+        __syncwarp();
     }
-    const double L = (double)len;
+    // a1[k * 3 + c] / a2 / aw[k] with GLOBAL row numbers k, whichever memory holds them; the fitted coordinates of a staged
+    // warp go to its set1 rows in place
+    const double *a1 = staged ? s1 - (size_t)R0 * 3 : set1;
+    const double *a2 = staged ? s2 - (size_t)R0 * 3 : set2;
+    const double *aw = w ? (staged ? sw - R0 : w) : nullptr;
+    double *out1 = staged ? s1 - (size_t)R0 * 3 : new1o;
+    if (p < n_prob) {
+        const int r0 = off[p], r1 = off[p + 1];
+        const int len = r1 - r0;
+        double m1[3] = {0, 0, 0}, m2[3] = {0, 0, 0};
+        for (int k = r0; k < r1; ++k) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) { m1[c] /= L; m2[c] /= L; }
-    // M = dev1^T diag(w) dev2   (= A^T of superpositions.py:53 / :109)
-    double M[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-    for (int k = r0; k < r1; ++k) {
-        const double wk = w ? w[k] : 1.0;
-        const double a0 = set1[(size_t)k * 3 + 0] - m1[0], a1 = set1[(size_t)k * 3 + 1] - m1[1],
-                     a2 = set1[(size_t)k * 3 + 2] - m1[2];
-        const double b0 = (set2[(size_t)k * 3 + 0] - m2[0]) * wk, b1 = (set2[(size_t)k * 3 + 1] - m2[1]) * wk,
-                     b2 = (set2[(size_t)k * 3 + 2] - m2[2]) * wk;
-        M[0][0] += a0 * b0; M[0][1] += a0 * b1; M[0][2] += a0 * b2;
-        M[1][0] += a1 * b0; M[1][1] += a1 * b1; M[1][2] += a1 * b2;
-        M[2][0] += a2 * b0; M[2][1] += a2 * b1; M[2][2] += a2 * b2;
-    }
-    double Q[3][3];
-    horn_rotation(M, Q);
-    // U = Q^T (row-vector convention: new1 = dev1 . U)
-    double sse = 0.0;
-    for (int k = r0; k < r1; ++k) {
-        const double a0 = set1[(size_t)k * 3 + 0] - m1[0], a1 = set1[(size_t)k * 3 + 1] - m1[1],
-                     a2 = set1[(size_t)k * 3 + 2] - m1[2];
-        const double n0 = a0 * Q[0][0] + a1 * Q[0][1] + a2 * Q[0][2];
-        const double n1 = a0 * Q[1][0] + a1 * Q[1][1] + a2 * Q[1][2];
-        const double n2 = a0 * Q[2][0] + a1 * Q[2][1] + a2 * Q[2][2];
-        if (new1o) { new1o[(size_t)k * 3 + 0] = n0; new1o[(size_t)k * 3 + 1] = n1; new1o[(size_t)k * 3 + 2] = n2; }
-        const double e0 = n0 - (set2[(size_t)k * 3 + 0] - m2[0]), e1 = n1 - (set2[(size_t)k * 3 + 1] - m2[1]),
-                     e2 = n2 - (set2[(size_t)k * 3 + 2] - m2[2]);
-        sse += e0 * e0 + e1 * e1 + e2 * e2;               // unweighted, RMSD.py:27
-    }
-    if (Uo) {
+            for (int c = 0; c < 3; ++c) { m1[c] += a1[(size_t)k * 3 + c]; m2[c] += a2[(size_t)k * 3 + c]; }
+        }
+        const double L = (double)len;
 #pragma unroll
-        for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) { m1[c] /= L; m2[c] /= L; }
+        // M = dev1^T diag(w) dev2   (= A^T of superpositions.py:53 / :109)
+        double M[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+        double ssq = 0.0;                                      // sum |a|^2 + sum |w b|^2: twice the eigenvalue bound
+        for (int k = r0; k < r1; ++k) {
+            const double wk = aw ? aw[k] : 1.0;
+            const double x0 = a1[(size_t)k * 3 + 0] - m1[0], x1 = a1[(size_t)k * 3 + 1] - m1[1],
+                         x2 = a1[(size_t)k * 3 + 2] - m1[2];
+            const double b0 = (a2[(size_t)k * 3 + 0] - m2[0]) * wk, b1 = (a2[(size_t)k * 3 + 1] - m2[1]) * wk,
+                         b2 = (a2[(size_t)k * 3 + 2] - m2[2]) * wk;
+            M[0][0] += x0 * b0; M[0][1] += x0 * b1; M[0][2] += x0 * b2;
+            M[1][0] += x1 * b0; M[1][1] += x1 * b1; M[1][2] += x1 * b2;
+            M[2][0] += x2 * b0; M[2][1] += x2 * b1; M[2][2] += x2 * b2;
+            ssq += (x0 * x0 + x1 * x1 + x2 * x2) + (b0 * b0 + b1 * b1 + b2 * b2);
+        }
+        double Q[3][3];
+        // largest eigenvector of Horn's matrix from its characteristic quartic + a pivoted adjugate column (rotfit.cuh; Jacobi
+        // fallback when the optimum is not unique): the cyclic Jacobi sweeps alone kept this kernel at 0.43 ms whatever the
+        // memory access pattern was
+        horn_rotation_pivot(M, 0.5 * ssq, Q);
+        // U = Q^T (row-vector convention: new1 = dev1 . U)
+        double sse = 0.0;
+        for (int k = r0; k < r1; ++k) {
+            const double x0 = a1[(size_t)k * 3 + 0] - m1[0], x1 = a1[(size_t)k * 3 + 1] - m1[1],
+                         x2 = a1[(size_t)k * 3 + 2] - m1[2];
+            const double n0 = x0 * Q[0][0] + x1 * Q[0][1] + x2 * Q[0][2];
+            const double n1 = x0 * Q[1][0] + x1 * Q[1][1] + x2 * Q[1][2];
+            const double n2 = x0 * Q[2][0] + x1 * Q[2][1] + x2 * Q[2][2];
+            if (new1o) { out1[(size_t)k * 3 + 0] = n0; out1[(size_t)k * 3 + 1] = n1; out1[(size_t)k * 3 + 2] = n2; }
+            const double e0 = n0 - (a2[(size_t)k * 3 + 0] - m2[0]), e1 = n1 - (a2[(size_t)k * 3 + 1] - m2[1]),
+                         e2 = n2 - (a2[(size_t)k * 3 + 2] - m2[2]);
+            sse += e0 * e0 + e1 * e1 + e2 * e2;               // unweighted, RMSD.py:27
+        }
+        if (Uo) {
 #pragma unroll
-            for (int c = 0; c < 3; ++c) Uo[(size_t)p * 9 + r * 3 + c] = Q[c][r];
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) Uo[(size_t)p * 9 + r * 3 + c] = Q[c][r];
+        }
+        if (mean1o) { mean1o[(size_t)p * 3 + 0] = m1[0]; mean1o[(size_t)p * 3 + 1] = m1[1]; mean1o[(size_t)p * 3 + 2] = m1[2]; }
+        if (mean2o) { mean2o[(size_t)p * 3 + 0] = m2[0]; mean2o[(size_t)p * 3 + 1] = m2[1]; mean2o[(size_t)p * 3 + 2] = m2[2]; }
+        if (sseo) sseo[p] = sse;
+        if (rmsdo) rmsdo[p] = sqrt(sse / L);                    // RMSD.py:15
     }
-    if (mean1o) { mean1o[(size_t)p * 3 + 0] = m1[0]; mean1o[(size_t)p * 3 + 1] = m1[1]; mean1o[(size_t)p * 3 + 2] = m1[2]; }
-    if (mean2o) { mean2o[(size_t)p * 3 + 0] = m2[0]; mean2o[(size_t)p * 3 + 1] = m2[1]; mean2o[(size_t)p * 3 + 2] = m2[2]; }
-    if (sseo) sseo[p] = sse;
-    if (rmsdo) rmsdo[p] = sqrt(sse / L);                    // RMSD.py:15
+    if (staged && new1o) {
+        __syncwarp();
+        for (int t = lane; t < R * 3; t += 32) new1o[(size_t)R0 * 3 + t] = s1[t];
+    }
 }
 
 // ---------------------------------------------------------------- K6 -------

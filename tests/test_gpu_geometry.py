@@ -62,6 +62,32 @@ def test_batched_kabsch_matches_oracle():
     assert np.abs(np.linalg.det(r["U"]) - 1).max() < 1e-12
 
 
+def test_batched_kabsch_short_and_mixed_point_sets():
+    """The staged form of K5 (a warp's 32 problems copied into shared memory when they have at most 384 rows in total): short
+    point sets (3-12 points: staged), mixed with a few long ones (their warps work from global memory), a batch that is
+    not a multiple of 32, weights - everything against the oracle, and against the same problems run one by one."""
+    rng = np.random.Generator(np.random.PCG64(12))
+    s1, s2, ws = [], [], []
+    for k in range(1013):
+        n = int(rng.integers(3, 13)) if k % 97 else int(rng.integers(60, 200))
+        a = rng.normal(size=(n, 3)) * 6
+        Q = synthetic.random_rotation(rng)
+        s1.append(a)
+        s2.append(a @ Q.T + rng.normal(size=(n, 3)) * 0.3 + rng.normal(size=3) * 20)
+        ws.append(rng.uniform(0.2, 2.0, size=n))
+    r = sup.besttransformation_batched(s1, s2)
+    rw = sup.besttransformation_batched(s1, s2, ws)
+    for k in range(0, 1013, 7):
+        U, new1, mean1, rmsd, sse, mean2 = O.besttransformation(s1[k], s2[k])
+        assert np.abs(r["U"][k] - U).max() < TOL and np.abs(r["new1"][k] - new1).max() < TOL
+        assert np.abs(r["mean1"][k] - mean1).max() < TOL and np.abs(r["mean2"][k] - mean2).max() < TOL
+        assert abs(r["sse"][k] - sse) < TOL * max(1.0, sse) and abs(r["rmsd"][k] - rmsd) < TOL
+        Uw, new1w = O.besttransformation_weighted(s1[k], s2[k], ws[k])[:2]
+        assert np.abs(rw["U"][k] - Uw).max() < TOL and np.abs(rw["new1"][k] - new1w).max() < TOL
+    one = sup.besttransformation_batched(s1[500:501], s2[500:501])
+    assert np.array_equal(one["U"][0], r["U"][500]) and np.array_equal(one["new1"][0], r["new1"][500])
+
+
 def _args(k):
     return ([np.array(c) for c in k["centers1"]], [np.array(r) for r in k["rotations1"]],
             [np.array(c) for c in k["centers2"]], [np.array(r) for r in k["rotations2"]])
