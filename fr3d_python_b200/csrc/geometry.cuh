@@ -229,7 +229,10 @@ constexpr size_t disc_smem_bytes(int n) {
 // Writes out[(r - row0) * ld + (c - col0)] for row0 <= r < row1, col0 <= c < N (col0 a multiple of 32).  col0 = 0,
 // ld = N: whole rows; col0 = row0, ld = N - row0: only the part of a row block at or right of the diagonal (the
 // multi-GPU split of the upper triangle, parallel.triangle_blocks; the mirror is fr3d_discrepancy_assemble).
-__global__ void __launch_bounds__(256)
+#ifndef FR3D_DISC_MINB
+#define FR3D_DISC_MINB 3      // 2 (116 registers) 21.83 ms, 3 (80, no spills) 20.12, 4 (64, spills) 19.96 for 20 000 x 20 000, n = 7
+#endif
+__global__ void __launch_bounds__(256, FR3D_DISC_MINB)
 discrepancy_all_vs_all_kernel(const double *__restrict__ centers, const double *__restrict__ rots,
                               const uint8_t *__restrict__ has_rot, int N, int n, double angle_weight, int row0,
                               int row1, int col0, int ld, double *__restrict__ out) {
