@@ -558,7 +558,8 @@ int fr3d_kabsch_batched(const double *set1, const double *set2, const double *w,
     if (int rc = require_device(false, nullptr)) return rc;
     if (n_prob <= 0) return FR3D_OK;
     const int block = fr3d::KABSCH_WARPS * 32;
-    fr3d::kabsch_batched_kernel<<<(n_prob + block - 1) / block, block, fr3d::KABSCH_SMEM, static_cast<cudaStream_t>(stream)>>>(
+    const size_t smem = w ? fr3d::KABSCH_SMEM : fr3d::KABSCH_SMEM / 7 * 6;          // no weights: no weight rows staged
+    fr3d::kabsch_batched_kernel<<<(n_prob + block - 1) / block, block, smem, static_cast<cudaStream_t>(stream)>>>(
         set1, set2, w, off, n_prob, U, mean1, mean2, rmsd, sse, new1);
     CUDA_TRY(cudaGetLastError());
     return FR3D_OK;

@@ -23,10 +23,10 @@ namespace fr3d {
 // KABSCH_ROWS rows in total (long point sets) works from global memory as before.
 constexpr int KABSCH_WARPS = 4;
 #ifndef FR3D_KABSCH_ROWS
-#define FR3D_KABSCH_ROWS 384
+#define FR3D_KABSCH_ROWS 352
 #endif
-constexpr int KABSCH_ROWS = FR3D_KABSCH_ROWS;    // rows staged per warp (384: 12 points per problem on average; 0: no staging)
-constexpr size_t KABSCH_SMEM = sizeof(double) * KABSCH_WARPS * KABSCH_ROWS * 7;
+constexpr int KABSCH_ROWS = FR3D_KABSCH_ROWS;    // rows staged per warp (352: 11 points per problem on average; 0: no staging)
+constexpr size_t KABSCH_SMEM = sizeof(double) * KABSCH_WARPS * KABSCH_ROWS * 7;      // with weights; 6 / 7 of it without
 
 __global__ void __launch_bounds__(KABSCH_WARPS * 32)
 kabsch_batched_kernel(const double *__restrict__ set1, const double *__restrict__ set2, const double *__restrict__ w,
@@ -41,7 +41,7 @@ kabsch_batched_kernel(const double *__restrict__ set1, const double *__restrict_
     const int R0 = off[p0], R1 = off[min(p0 + 32, n_prob)];
     const int R = R1 - R0;
     const bool staged = R <= KABSCH_ROWS;                                  // warp uniform
-    double *s1 = kb_smem + (size_t)warp * KABSCH_ROWS * 7, *s2 = s1 + KABSCH_ROWS * 3, *sw = s2 + KABSCH_ROWS * 3;
+    double *s1 = kb_smem + (size_t)warp * KABSCH_ROWS * (w ? 7 : 6), *s2 = s1 + KABSCH_ROWS * 3, *sw = s2 + KABSCH_ROWS * 3;
     if (staged) {
         for (int t = lane; t < R * 3; t += 32) {
             cp_async8(s1 + t, set1 + (size_t)R0 * 3 + t);

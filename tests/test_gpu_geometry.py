@@ -63,7 +63,7 @@ def test_batched_kabsch_matches_oracle():
 
 
 def test_batched_kabsch_short_and_mixed_point_sets():
-    """The staged form of K5 (a warp's 32 problems copied into shared memory when they have at most 384 rows in total): short
+    """The staged form of K5 (a warp's 32 problems copied into shared memory when they have at most 352 rows in total): short
     point sets (3-12 points: staged), mixed with a few long ones (their warps work from global memory), a batch that is
     not a multiple of 32, weights - everything against the oracle, and against the same problems run one by one."""
     rng = np.random.Generator(np.random.PCG64(12))
